@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE ONLY).
+
+Run in the build container (where /root/reference exists):   python oracle/make_goldens.py
+Every golden holds the exact inputs (initial variational parameters, pseudo-data, minibatch, noise seed) and
+the reference's outputs for: inner_elbo (+autograd grads), psvi_elbo (+grads), one full nested_step
+(hypergradients on u and v, final fast weights, u/v after their Adam step) and evaluate -- in fp32 (the
+reference's arithmetic) and in fp64 (same fp32 noise, used to decide "who is wrong": SURVEY.md section 4).
+Noise is injected through oracle.ref_import.NoiseFeeder, so the fixture only stores the seed.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference, NoiseFeeder  # noqa: E402
+
+import_reference()
+import torch  # noqa: E402
+from psvi.inference.psvi_classes import PSVILearnV, PSVI  # noqa: E402
+from psvi.inference.baselines import run_mfvi_subset  # noqa: E402
+from psvi.inference.utils import pseudo_subsample_init  # noqa: E402
+from psvi.experiments.experiments_utils import read_dataset  # noqa: E402
+from psvi.models.neural_net import VILinear  # noqa: E402
+
+CASES = [
+    # name, dataset, architecture, H, n_layers, M, S, T, B, init_sd, lr0net, cls
+    dict(name="logreg_hm_m10", dnm="halfmoon", arch="logistic_regression", H=0, n_layers=0, M=10, S=10, T=8, B=128,
+         init_sd=1e-3, lr0net=1e-3, cls="learn_v"),
+    dict(name="fn_hm_m50_t10", dnm="halfmoon", arch="fn", H=100, n_layers=1, M=50, S=10, T=10, B=128,
+         init_sd=1e-3, lr0net=1e-3, cls="learn_v"),
+    dict(name="fn_hm_m50_t100", dnm="halfmoon", arch="fn", H=100, n_layers=1, M=50, S=10, T=100, B=128,
+         init_sd=1e-3, lr0net=1e-3, cls="learn_v"),
+    dict(name="fn_hm_m10_sd1e-6", dnm="halfmoon", arch="fn", H=100, n_layers=1, M=10, S=10, T=20, B=128,
+         init_sd=1e-6, lr0net=1e-3, cls="learn_v"),
+    dict(name="fn_fb_m10", dnm="four_blobs", arch="fn", H=100, n_layers=1, M=10, S=10, T=10, B=128,
+         init_sd=1e-3, lr0net=1e-3, cls="learn_v"),
+    dict(name="fn_fb_l2_m13", dnm="four_blobs", arch="fn", H=24, n_layers=2, M=13, S=6, T=6, B=37,
+         init_sd=1e-2, lr0net=3e-3, cls="learn_v"),
+    dict(name="fn_hm_psvi_fixedv", dnm="halfmoon", arch="fn", H=40, n_layers=1, M=12, S=4, T=5, B=64,
+         init_sd=1e-3, lr0net=1e-3, cls="psvi"),
+]
+
+
+def get_data(dnm):
+    torch.manual_seed(0)  # four_blobs draws from the global RNG before any seeding; pin it
+    with contextlib.redirect_stdout(io.StringIO()):
+        return read_dataset(dnm, {"data_folder": "/tmp/psvi_data", "test_ratio": 0.2})
+
+
+def model_dims(model):
+    lins = [m for m in model.modules() if isinstance(m, VILinear)]
+    return [lins[0].in_features] + [m.out_features for m in lins]
+
+
+def get_mu_rho(model):
+    mu, rho = [], []
+    for m in model.modules():
+        if isinstance(m, VILinear):
+            mu += [m.weight.detach().reshape(-1), m.bias.detach().reshape(-1)]
+            rho += [m._weight_sd.detach().reshape(-1), m._bias_sd.detach().reshape(-1)]
+    return torch.cat(mu).double().numpy().copy(), torch.cat(rho).double().numpy().copy()
+
+
+def run_case(c, dt):
+    x, y, xt, yt, N, D, tr, te, nc = get_data(c["dnm"])
+    kw = dict(mc_samples=c["S"], num_epochs=0, data_minibatch=c["B"], D=D, N=N, inner_it=c["T"], trainer="nested",
+              log_every=10, lr0u=1e-4, lr0net=c["lr0net"], lr0v=1e-3, init_args="subsample", init_sd=c["init_sd"],
+              num_pseudo=c["M"], seed=0, architecture=c["arch"], n_hidden=c["H"], n_layers=c["n_layers"],
+              logistic_regression=(c["arch"] == "logistic_regression"), train_dataset=tr, test_dataset=te,
+              dnm=c["dnm"], nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=True)
+    Cls = PSVILearnV if c["cls"] == "learn_v" else PSVI
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = Cls(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float32 if dt == "32" else torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(1234)
+    v0 = (0.3 * rng.standard_normal(c["M"])).astype(np.float32) if c["cls"] == "learn_v" else obj.v.detach().numpy()
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(c["cls"] == "learn_v")
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    # optimisers must point at the re-typed leaves
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), c["lr0net"])
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    if obj.learn_v:
+        obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[: c["B"]].to(tdt), y[: c["B"]].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=c["S"], T=c["T"], M=c["M"], B=c["B"], lr0net=c["lr0net"], noise_seed=777,
+               vmode=1 if c["cls"] == "learn_v" else 0,
+               mu0=mu0, rho0=rho0, u0=obj.u.detach().double().numpy().copy(), z=obj.z.double().numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.double().numpy().copy(), yb=yb.double().numpy().copy(),
+               xt=xt.double().numpy().copy(), yt=yt.double().numpy().copy())
+    res = {}
+    params = list(obj.model.parameters())
+    with NoiseFeeder(dims, c["S"], 777) as nf:
+        # (i) inner_elbo + grads
+        L = obj.inner_elbo(model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u] + ([obj.v] if obj.learn_v else []))
+        res["inner_val"] = L.item()
+        res["inner_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).double().numpy()
+        res["inner_gu"] = gs[len(params)].double().numpy()
+        if obj.learn_v:
+            res["inner_gv"] = gs[len(params) + 1].double().numpy()
+        # (ii) psvi_elbo + grads
+        L = obj.psvi_elbo(xb, yb, model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u] + ([obj.v] if obj.learn_v else []))
+        res["outer_val"] = L.item()
+        res["outer_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).double().numpy()
+        res["outer_gu"] = gs[len(params)].double().numpy()
+        if obj.learn_v:
+            res["outer_gv"] = gs[len(params) + 1].double().numpy()
+        # (iii) nested_step
+        obj.elbos = []
+        loss = obj.nested_step(xb, yb)
+        res["nested_loss"] = loss.item()
+        res["nested_gu"] = obj.u.grad.double().numpy().copy()
+        if obj.learn_v:
+            res["nested_gv"] = obj.v.grad.double().numpy().copy()
+        res["nested_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().double().numpy()
+        res["nested_u_after"] = obj.u.detach().double().numpy().copy()
+        res["nested_v_after"] = obj.v.detach().double().numpy().copy()
+        res["nested_elbos"] = np.array([e[1] for e in obj.elbos], dtype=np.float64)
+        # (iv) evaluate with the post-step state
+        acc, nll, went, ness, vent = obj.evaluate()
+        res["eval"] = np.array([acc.item(), nll.item(), went.item(), ness.item(), vent.item()])
+        out["n_forwards"] = len(nf.history)
+    return out, res
+
+
+def run_mfvi_case():
+    """run_mfvi_subset (baselines.py:923-1062) on halfmoon, fn H=40, M=20, S=8, 6 iterations."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    M, S, H = 20, 8, 40
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        xs, ys = pseudo_subsample_init(x, y, num_pseudo=M, seed=3, nc=nc)
+        # initial parameters: same seeding as run_mfvi_subset does before set_up_model
+        import random
+        random.seed(3), np.random.seed(3), torch.manual_seed(3)
+        from psvi.experiments.experiments_utils import set_up_model
+        net0 = set_up_model(architecture="fn", D=D, n_hidden=H, nc=nc, mc_samples=S, init_sd=1e-3)
+        mu0, rho0 = get_mu_rho(net0)
+        # NB experiments_utils.set_up_model does not forward n_layers, so "fn" here has make_fcnet's default of
+        # TWO hidden layers (neural_net.py:271) -- unlike PSVI.set_up_model (psvi_classes.py:707-717).
+        dims = model_dims(net0)
+        with NoiseFeeder(dims, S, 4242) as nf:
+            res = run_mfvi_subset(x=x, y=y, xt=xt, yt=yt, mc_samples=S, data_minibatch=256, num_epochs=3, log_every=2,
+                                  D=D, lr0net=1e-3, seed=3, train_dataset=tr, test_dataset=te, num_pseudo=M,
+                                  init_args="subsample", architecture="fn", n_hidden=H, nc=nc, dnm="halfmoon",
+                                  init_sd=1e-3)
+            nfw = len(nf.history)
+    return dict(dims=np.array(dims), N=N, S=S, M=M, noise_seed=4242, n_forwards=nfw, lr0net=1e-3,
+                mu0=mu0, rho0=rho0, xs=xs.detach().double().numpy(), ys=ys.double().numpy(),
+                xt=xt.double().numpy(), yt=yt.double().numpy(),
+                ref_elbos=np.array(res["elbos"]), ref_accs=np.array(res["accs"]), ref_nlls=np.array(res["nlls"]))
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for c in CASES:
+        out32, r32 = run_case(c, "32")
+        out64, r64 = run_case(c, "64")
+        for k in ("mu0", "rho0", "u0", "xb"):
+            assert np.array_equal(out32[k], out64[k]), k
+        blob = dict(out32)
+        blob.update({"ref32_" + k: v for k, v in r32.items()})
+        blob.update({"ref64_" + k: v for k, v in r64.items()})
+        p = os.path.join(ROOT, "tests", "golden", c["name"] + ".npz")
+        np.savez_compressed(p, **blob)
+        print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"],
+              "size", os.path.getsize(p))
+    blob = run_mfvi_case()
+    p = os.path.join(ROOT, "tests", "golden", "mfvi_subset_hm.npz")
+    np.savez_compressed(p, **blob)
+    print("mfvi_subset_hm", blob["ref_elbos"], blob["ref_accs"], blob["ref_nlls"])
+
+
+if __name__ == "__main__":
+    main()

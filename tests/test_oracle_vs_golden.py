@@ -1,0 +1,113 @@
+"""Pins the CPU oracle (oracle/psvi_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/make_goldens.py with an injected noise stream).
+
+Tolerances: the fp64 oracle is compared with the fp64 reference run (same fp32 noise) -> tight (1e-9 rel);
+the fp32 reference is then compared at the float noise floor SURVEY.md section 4 calibrated
+(ELBO rtol 1e-4, hypergradients rel-L2 5e-3 at init_sd 1e-6 / 2e-4 at init_sd >= 1e-3)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import psvi_oracle as po
+from oracle.ref_import import NoiseFeeder
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if not os.path.basename(p).startswith("mfvi"))
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T = int(g["S"]), int(g["T"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    return g, dims, S, T, [e.astype(np.float64) for e in eps]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_inner_and_outer_elbo_and_grads(name):
+    g, dims, S, T, eps = load(name)
+    N, vmode = float(g["N"]), int(g["vmode"])
+    a = po.coreset_weights(g["v0"], N, vmode)
+    val, gmu, grho, gu, ga = po.inner_grad(g["mu0"], g["rho0"], eps[0], g["u0"], g["z"], a, dims)
+    assert abs(val - g["ref64_inner_val"]) <= 1e-9 * abs(val)
+    assert rel_l2(po.mu_rho_to_phi(gmu, grho, dims), g["ref64_inner_gparams"]) < 1e-9
+    assert rel_l2(gu, g["ref64_inner_gu"]) < 1e-9
+    if vmode:
+        assert rel_l2(po.coreset_weights_vjp(g["v0"], N, vmode, ga)[0], g["ref64_inner_gv"]) < 1e-9
+    val, gmu, grho, gu, ga, _ = po.psvi_elbo_grad(g["mu0"], g["rho0"], eps[1], g["u0"], g["z"], a, g["xb"], g["yb"], N, dims)
+    assert abs(val - g["ref64_outer_val"]) <= 1e-9 * abs(val)
+    assert rel_l2(po.mu_rho_to_phi(gmu, grho, dims), g["ref64_outer_gparams"]) < 1e-8
+    assert rel_l2(gu, g["ref64_outer_gu"]) < 1e-8
+    if vmode:
+        assert rel_l2(po.coreset_weights_vjp(g["v0"], N, vmode, ga)[0], g["ref64_outer_gv"]) < 1e-8
+    # fp32 reference sits at its own float noise floor around the fp64 answer
+    assert abs(g["ref32_outer_val"] - val) <= 1e-4 * abs(val)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_nested_step_hypergradient_and_evaluate(name):
+    g, dims, S, T, eps = load(name)
+    N, vmode = float(g["N"]), int(g["vmode"])
+    r = po.nested_step(g["mu0"], g["rho0"], np.stack(eps[2:2 + T]), eps[2 + T], g["u0"], g["z"], g["v0"],
+                       g["xb"], g["yb"], N, dims, float(g["lr0net"]), vmode=vmode)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-9 * abs(r["loss"])
+    assert rel_l2(po.mu_rho_to_phi(r["mu_T"], r["rho_T"], dims), g["ref64_nested_params"]) < 1e-10
+    assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-7
+    if vmode:
+        assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-7
+    # logged inner ELBOs (psvi_classes.py:553-559): every log_every(=10)-th inner loss then the outer one
+    ref_elbos = g["ref64_nested_elbos"]
+    mine = [-r["inner_losses"][t] for t in range(0, T, 10)] + [-r["loss"]]
+    np.testing.assert_allclose(mine, ref_elbos, rtol=1e-9)
+    # u, v after their first torch.optim.Adam step (psvi_classes.py:584-586)
+    u1, _, _ = po.torch_adam_step(g["u0"], r["u_grad"], 0 * g["u0"], 0 * g["u0"], 1, 1e-4)
+    np.testing.assert_allclose(u1, g["ref64_nested_u_after"], rtol=0, atol=1e-9)
+    # fp32 reference vs fp64 oracle: SURVEY section 4 tolerances
+    sd_small = "sd1e-6" in name
+    tol = 5e-3 if sd_small else 2e-4
+    assert abs(g["ref32_nested_loss"] - r["loss"]) <= (2e-5 if sd_small else 1e-5) * abs(r["loss"])
+    assert rel_l2(g["ref32_nested_gu"], r["u_grad"]) < tol
+    if vmode:
+        assert rel_l2(g["ref32_nested_gv"], r["v_grad"]) < tol
+    # evaluate() on the post-step state
+    v1 = g["ref64_nested_v_after"]
+    a1 = po.coreset_weights(v1, N, vmode)
+    nb = -(-g["xt"].shape[0] // int(g["B"]))
+    acc, nll, went, ness = po.evaluate(r["mu_T"], r["rho_T"], eps[3 + T:3 + T + nb], g["ref64_nested_u_after"], g["z"], a1,
+                                       g["xt"], g["yt"], dims, int(g["B"]))
+    ref = g["ref64_eval"]
+    assert abs(acc - ref[0]) < 1e-7  # the reference accumulates `corrects` in a float32 tensor
+    np.testing.assert_allclose([nll, went, ness], ref[1:4], rtol=1e-7)
+    f = po.softmax(v1, 0) if vmode else v1
+    np.testing.assert_allclose(f.sum() ** 2 / (f * f).sum() / len(f), ref[4], rtol=1e-9)
+
+
+def test_mfvi_subset_trace():
+    g = dict(np.load(os.path.join(GOLDEN, "mfvi_subset_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, N, M = int(g["S"]), float(g["N"]), int(g["M"])
+    eps = [e.astype(np.float32) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    dt = np.float32
+    mu, rho = g["mu0"].astype(dt), g["rho0"].astype(dt)
+    m = np.zeros(2 * len(mu), dt); v = np.zeros(2 * len(mu), dt)
+    xs, ys, xt, yt = g["xs"].astype(dt), g["ys"], g["xt"].astype(dt), g["yt"]
+    k, elbos, accs, nlls = 0, [], [], []
+    for i in range(6):
+        val, gmu, grho = po.mfvi_grad(mu, rho, eps[k], xs, ys, dt(N / M), dims); k += 1
+        phi, m, v = po.torch_adam_step(np.concatenate([mu, rho]), np.concatenate([gmu, grho]).astype(dt), m, v, i + 1,
+                                       dt(g["lr0net"]))
+        mu, rho = phi[:len(mu)].astype(dt), phi[len(mu):].astype(dt)
+        elbos.append(-val)
+        if i % 2 == 0:
+            c, nl = po.mfvi_predict(mu, rho, eps[k], xt, yt, dims); k += 1
+            accs.append(c / len(yt)); nlls.append(nl / len(yt))
+    np.testing.assert_allclose(elbos, g["ref_elbos"], rtol=2e-5)
+    np.testing.assert_allclose(accs, g["ref_accs"], atol=1e-6)
+    np.testing.assert_allclose(nlls, g["ref_nlls"], rtol=2e-5)
