@@ -1,0 +1,1490 @@
+// psvi_mf_engine.cu -- the "small regime" PSVI engine for mean-field MLP BNNs (logistic_regression, fn).
+//
+// ONE thread-block cluster (G <= 16 CTAs, one per group of MC samples) runs a whole bilevel PSVI step on-chip:
+//   T differentiable-Adam inner steps on inner_elbo  ->  outer psvi_elbo forward/backward  ->  reverse sweep through
+//   the T steps with hand-written Hessian-/mixed-vector products  ->  hypergradients on (u, v).
+// What the reference does with ~25k ATen launches and a double-backward autograd graph per outer step
+// (psvi/inference/psvi_classes.py:541-600, psvi/robust_higher/optim.py:152-257,299-367) is a single launch here.
+//
+// Parallel decomposition (B200: 148 SMs, clusters with distributed shared memory):
+//   * CTA `rank` owns MC samples s = rank, rank+G, ... : sampled weights, activations and adjoints of a sample never
+//     leave that CTA's shared memory.
+//   * the variational parameter vector (padded layout, Pp floats) is cut in G slices; CTA k is the *owner* of slice k:
+//     it holds the Adam moments / reverse-sweep carries of its slice, receives every CTA's per-sample weight-gradient
+//     partials through DSMEM pushes, reduces them in a fixed order (deterministic), updates, and pushes the new
+//     parameters (or the next HVP direction) back into every CTA's shared memory.  Two cluster barriers per step.
+//   * the trajectory (phi_t, g_t, m_t, v_t) goes to global memory, written and later re-read by the same owner thread.
+// Rows (pseudo-points u, then the minibatch) are processed in chunks of RC rows so that any M / B fits.
+//
+// Math: SURVEY.md Appendix A (A.1 layer, A.2 objectives, A.4 Adam VJP, A.6 HVP) == oracle/psvi_oracle.py.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "psvi_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NT = 256;  // threads per CTA
+constexpr int MAXL = PSVI_MAX_LAYERS;
+
+enum : int {
+  F_UNROLL = 1,       // T Adam steps on the inner objective
+  F_OUTER = 2,        // psvi_elbo forward + backward at the current phi
+  F_REVERSE = 4,      // reverse sweep through the trajectory
+  F_HVP = 8,          // one Hessian-vector pass along p.gdot
+  F_NOUPDATE = 16,    // F_UNROLL: compute the gradient but do not move phi (inner_grad entry point)
+  F_STORE_GOUT = 32,  // write the phase-boundary buffer (outer gradient wrt phi_T, direct u/a partials, d_s, loss)
+  F_LOAD_GOUT = 64,   // start the reverse sweep from the phase-boundary buffer
+  F_FINAL = 128,      // reduce ubar/abar over the cluster and write u_grad / v_grad
+  F_WRITE_PHI = 256   // write phi (and Adam moments if given) back after F_UNROLL
+};
+
+struct EP {
+  int L;
+  int dims[MAXL + 1];
+  int S, M, B, Btot;
+  int G, RC, slice;
+  float Nf;
+  int vmode;
+  float alpha;
+  int flags;
+  int T, step0;
+  float lr;
+  int adam_mode;
+  float kappa;
+  int noise_mode;
+  unsigned long long seed;
+  unsigned domain;
+  float* mu;
+  float* rho;
+  float* adam_m;
+  float* adam_v;
+  const float* u;
+  const int* z;
+  const float* v;
+  const float* roww;
+  const float* xb;
+  const int* yb;
+  const float* eps;
+  float* traj;
+  float* gout;
+  float* u_grad;
+  float* v_grad;
+  float* alpha_grad;
+  float* loss_out;
+  float* inner_losses;
+  float* g_out;
+  const float* gdot;
+  float* h_phi;
+  // predictive pass
+  int n_rows, batch, first_slab, eval_mode, n_slabs, chunks_per_slab;
+  float* eval_w;     // [n_slabs][S] importance weights
+  float* eval_part;  // [n_ctas][4] per-CTA partial sums
+  float* eval_out;   // [8]
+};
+
+struct Meta {
+  int din[MAXL + 1], dout[MAXL + 1], ldw[MAXL + 1], woff[MAXL + 1], boff[MAXL + 1], tlw[MAXL + 1], tlb[MAXL + 1];
+  int lda[MAXL + 1];
+  int Pt, Pp;
+};
+
+__host__ __device__ inline void make_meta(const int* dims, int L, Meta& m) {
+  int pp = 0, pt = 0;
+  for (int l = 0; l <= L; ++l) m.lda[l] = dims[l] | 1;
+  for (int l = 1; l <= L; ++l) {
+    const int din = dims[l - 1], dout = dims[l];
+    m.din[l] = din;
+    m.dout[l] = dout;
+    m.ldw[l] = din | 1;  // odd leading dimension: conflict-free shared-memory access along either index
+    m.woff[l] = pp;
+    pp += dout * m.ldw[l];
+    m.boff[l] = pp;
+    pp += dout;
+    m.tlw[l] = pt;
+    pt += dout * din;
+    m.tlb[l] = pt;
+    pt += dout;
+  }
+  m.Pt = pt;
+  m.Pp = pp;
+}
+
+// shared-memory carve-up (offsets in floats)
+struct Lay {
+  int mu, rho, sig, sgm, gmu, grho, theta, thetad, eps, acc1, acc2, acc3;  // Pp each (padded parameter layout)
+  int tl_of_pad, pad_of_tl;                                                // ints
+  int recv;                                                                // [G][3][slice]
+  int ost;                                                                 // owner state [10][slice]
+  int a, f, ubar, abar, su, sz;                                            // coreset: a[M] f[M] ubar[M*D] abar[M] u[M*ld0] z[M]
+  int lw, e, dsv, w, beta, gp;                                             // S each
+  int red, lossrecv;                                                       // 64, G
+  int lab, cw, nll;                                                        // RC each
+  int act[MAXL + 1], actd[MAXL + 1], adj[MAXL + 1], adjd[MAXL + 1];
+  int total;
+};
+
+__host__ __device__ inline void make_layout(const EP& p, const Meta& m, Lay& y) {
+  const bool dual = (p.flags & (F_REVERSE | F_HVP)) != 0;
+  int o = 0;
+  auto take = [&](int n) {
+    int r = o;
+    o += (n + 3) & ~3;
+    return r;
+  };
+  const int Pp = m.Pp;
+  y.mu = take(Pp); y.rho = take(Pp); y.sig = take(Pp); y.sgm = take(Pp); y.gmu = take(Pp); y.grho = take(Pp);
+  y.theta = take(Pp); y.thetad = take(Pp); y.eps = take(Pp); y.acc1 = take(Pp); y.acc2 = take(Pp); y.acc3 = take(Pp);
+  y.tl_of_pad = take(Pp); y.pad_of_tl = take(m.Pt);
+  y.recv = take(p.G * 3 * p.slice);
+  y.ost = take(10 * p.slice);
+  y.a = take(p.M); y.f = take(p.M); y.ubar = take(p.M * p.dims[0]); y.abar = take(p.M);
+  y.su = take(p.M * m.lda[0]); y.sz = take(p.M);
+  y.lw = take(2 * p.S); y.e = take(2 * p.S); y.dsv = take(p.S);  // lw, e hold doubles y.w = take(p.S); y.beta = take(p.S); y.gp = take(p.S);
+  y.red = take(64); y.lossrecv = take(p.G);
+  y.lab = take(p.RC); y.cw = take(p.RC); y.nll = take(p.RC);
+  for (int l = 0; l <= p.L; ++l) {
+    y.act[l] = take(p.RC * m.lda[l]);
+    y.adj[l] = take(p.RC * m.lda[l]);
+    y.actd[l] = dual ? take(p.RC * m.lda[l]) : 0;
+    y.adjd[l] = dual ? take(p.RC * m.lda[l]) : 0;
+  }
+  y.total = o;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// block-wide helpers
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect red against a previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NT / 32) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+__device__ __forceinline__ double block_sum_d(double v, float* red_) {
+  double* red = reinterpret_cast<double*>(red_ + 16);  // red[16..31] as 8 doubles (red is 16-byte aligned)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < NT / 32; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NT / 32) ? red[l] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return t;
+}
+
+// "for every output o in [0,nOut): store(o, sum_k term(ctx(o), k))".  When there are fewer outputs than threads,
+// g = 2,4,..32 lanes share one output and combine with shuffles (keeps skinny products such as H->C busy).
+template <class Setup, class Term, class Store>
+__device__ __forceinline__ void reduce_outputs(int nOut, int K, Setup setup, Term term, Store store) {
+  int g = 1;
+  while (g < 32 && nOut * (g * 2) <= NT && K >= 8 * g) g <<= 1;
+  const int tid = threadIdx.x, sub = tid & (g - 1), grp = tid / g, ngrp = NT / g;
+  for (int base = 0; base < nOut; base += ngrp) {
+    const int o = base + grp;
+    float acc = 0.f;
+    if (o < nOut) {
+      auto ctx = setup(o);
+      for (int k = sub; k < K; k += g) acc += term(ctx, k);
+    }
+    for (int off = g >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (o < nOut && sub == 0) store(o, acc);
+  }
+}
+
+struct Ctx2 {
+  int a, b;
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+struct Engine {
+  const EP& p;
+  const Meta& mt;
+  const Lay& ly;
+  float* sm;
+  cg::cluster_group cluster;
+  int rank, tid;
+
+  __device__ Engine(const EP& p_, const Meta& m_, const Lay& l_, float* s_)
+      : p(p_), mt(m_), ly(l_), sm(s_), cluster(cg::this_cluster()) {
+    rank = (int)cluster.block_rank();
+    tid = threadIdx.x;
+  }
+  __device__ __forceinline__ float* F(int off) const { return sm + off; }
+  __device__ __forceinline__ int* I(int off) const { return reinterpret_cast<int*>(sm + off); }
+  __device__ __forceinline__ float* remote(int off, int r) { return cluster.map_shared_rank(sm + off, r); }
+
+  // ---- refresh sigma = softplus(rho), sgm = sigmoid(rho) after phi changed -----------------------------------
+  __device__ void refresh_sigma() {
+    const int* top = I(ly.tl_of_pad);
+    for (int pp = tid; pp < mt.Pp; pp += NT) {
+      if (top[pp] >= 0) {
+        const float r = F(ly.rho)[pp];
+        F(ly.sig)[pp] = softplus_f(r);
+        F(ly.sgm)[pp] = sigmoid_f(r);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- draw eps for (slab, s) and build theta (and the tangent thetad); returns this thread's partial of
+  //      sampled_nkl_s = sum_i [-theta^2/2 + eps^2/2 + log sigma]  (neural_net.py:110-115)
+  __device__ float sample_theta(int s, int slab, bool tangent, float fold_beta) {
+    const int* pot = I(ly.pad_of_tl);
+    float nkl = 0.f;
+    const int Pt = mt.Pt;
+    const int n4 = (Pt + 3) >> 2;
+    for (int q4 = tid; q4 < n4; q4 += NT) {
+      float e4[4];
+      if (p.noise_mode == PSVI_NOISE_PHILOX) {
+        philox_normal4(p.seed, p.domain, (uint32_t)slab, (uint32_t)s, (uint32_t)q4, e4);
+      } else {
+        const float* src = p.eps + ((size_t)slab * p.S + s) * Pt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e4[j] = (4 * q4 + j < Pt) ? __ldg(src + 4 * q4 + j) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = 4 * q4 + j;
+        if (q < Pt) {
+          const int pp = pot[q];
+          const float e = e4[j], sg = F(ly.sig)[pp];
+          const float th = F(ly.mu)[pp] + sg * e;
+          F(ly.eps)[pp] = e;
+          F(ly.theta)[pp] = th;
+          if (tangent) F(ly.thetad)[pp] = F(ly.gmu)[pp] + F(ly.sgm)[pp] * F(ly.grho)[pp] * e;
+          nkl += -0.5f * th * th + 0.5f * e * e + logf(sg);
+          if (fold_beta != 0.f) {  // outer objective: d nkl_s / d theta = -theta, weighted by beta_s (A.2)
+            const float tb = -fold_beta * th;
+            F(ly.acc1)[pp] += tb;
+            F(ly.acc2)[pp] += tb * e;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    return nkl;
+  }
+
+  // ---- stage rows [r0, r0+nr) of the virtual row list (pseudo rows 0..M-1, then minibatch rows) -------------------
+  // returns the pointer to the layer-0 activations of the chunk
+  __device__ float* stage_rows(int r0, int nr) {
+    int* lab = I(ly.lab);
+    if (r0 < p.M) {  // pseudo chunk (never mixed with data rows): alias the resident copy of u
+      for (int rr = tid; rr < nr; rr += NT) lab[rr] = I(ly.sz)[r0 + rr];
+      return F(ly.su) + r0 * mt.lda[0];
+    }
+    const int D = p.dims[0], ld0 = mt.lda[0];
+    float* a0 = F(ly.act[0]);
+    const float* src = p.xb + (size_t)(r0 - p.M) * D;
+    for (int i = tid; i < nr * D; i += NT) {
+      const int rr = i / D, c = i - rr * D;
+      a0[rr * ld0 + c] = __ldg(src + i);
+    }
+    for (int rr = tid; rr < nr; rr += NT) lab[rr] = __ldg(p.yb + (r0 - p.M) + rr);
+    return a0;
+  }
+
+  // ---- forward through the MLP for one chunk (primal, optionally tangent) -----------------------------------------
+  __device__ void forward(const float* a0, int nr, bool dual) {
+    for (int l = 1; l <= p.L; ++l) {
+      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l];
+      const int ldi = mt.lda[l - 1], ldo = mt.lda[l];
+      const float* in = (l == 1) ? a0 : F(ly.act[l - 1]);
+      const float* ind = F(ly.actd[l - 1]);
+      const float* W = F(ly.theta) + mt.woff[l];
+      const float* bia = F(ly.theta) + mt.boff[l];
+      const float* Wd = F(ly.thetad) + mt.woff[l];
+      const float* bd = F(ly.thetad) + mt.boff[l];
+      float* out = F(ly.act[l]);
+      float* outd = F(ly.actd[l]);
+      const bool relu = l < p.L;
+      const bool has_ind = dual && l > 1;
+      auto setup = [&](int o) {
+        const int rr = o / dout;
+        return Ctx2{rr, o - rr * dout};
+      };
+      reduce_outputs(
+          nr * dout, din, setup, [&](const Ctx2& c, int k) { return in[c.a * ldi + k] * W[c.b * ldw + k]; },
+          [&](int o, float acc) {
+            const int rr = o / dout, oo = o - rr * dout;
+            acc += bia[oo];
+            out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc;
+          });
+      if (dual) {
+        // tangent pre-activation; the ReLU mask is applied below once the primal of the same element is final
+        reduce_outputs(
+            nr * dout, din, setup,
+            [&](const Ctx2& c, int k) {
+              float t = in[c.a * ldi + k] * Wd[c.b * ldw + k];
+              if (has_ind) t += ind[c.a * ldi + k] * W[c.b * ldw + k];
+              return t;
+            },
+            [&](int o, float acc) {
+              const int rr = o / dout, oo = o - rr * dout;
+              outd[rr * ldo + oo] = acc + bd[oo];
+            });
+      }
+      __syncthreads();
+      if (dual && relu) {
+        for (int i = tid; i < nr * dout; i += NT) {
+          const int rr = i / dout, oo = i - rr * dout;
+          if (!(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- softmax / NLL per row; fills the output adjoints.  mode 0: value only, 1: gradient, 2: HVP ------------------
+  // cw[rr] must hold the row weights.  nll[rr] receives -log softmax(o)[label].  For mode 2, abar_rows (nullable)
+  // accumulates A_c[r] = sum_c q_c * odot_c  (A.6) into abar[r0 + rr].
+  __device__ void loss_stage(int nr, int mode, int r0) {
+    const int C = p.dims[p.L], ld = mt.lda[p.L];
+    const float* o = F(ly.act[p.L]);
+    const float* od = F(ly.actd[p.L]);
+    float* ao = F(ly.adj[p.L]);
+    float* aod = F(ly.adjd[p.L]);
+    const int* lab = I(ly.lab);
+    const float* cw = F(ly.cw);
+    for (int rr = tid; rr < nr; rr += NT) {
+      const float* row = o + rr * ld;
+      float mx = row[0];
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+      const float lse = mx + logf(se);
+      const int y = lab[rr];
+      F(ly.nll)[rr] = lse - row[y];
+      if (mode == 0) continue;
+      const float w = cw[rr];
+      if (mode == 1) {
+        for (int c = 0; c < C; ++c) {
+          const float pc = expf(row[c] - lse);
+          ao[rr * ld + c] = w * (pc - (c == y ? 1.f : 0.f));
+        }
+      } else {
+        const float* rowd = od + rr * ld;
+        float pd = 0.f;
+        for (int c = 0; c < C; ++c) pd += expf(row[c] - lse) * rowd[c];
+        float ac = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float pc = expf(row[c] - lse);
+          const float qc = pc - (c == y ? 1.f : 0.f);
+          aod[rr * ld + c] = w * qc;                  // adjoint of odot
+          ao[rr * ld + c] = w * pc * (rowd[c] - pd);  // adjoint of o
+          ac += qc * rowd[c];
+        }
+        F(ly.abar)[r0 + rr] += ac;  // rows of an HVP pass are always pseudo rows
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- backward for one chunk.  dual=false: plain gradient (acc1 += tbar, acc2 += tbar*eps);
+  //      dual=true: adjoint of Ldot (acc1 += A_theta, acc2 += A_theta*eps, acc3 += A_thetadot*eps).
+  //      need_x: also produce the adjoint of the layer-0 input and add it to ubar[r0 + rr]. ---------------------------
+  __device__ void backward(const float* a0, int nr, bool dual, bool need_x, int r0) {
+    for (int l = p.L; l >= 1; --l) {
+      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l];
+      const int ldi = mt.lda[l - 1], ldo = mt.lda[l];
+      const float* in = (l == 1) ? a0 : F(ly.act[l - 1]);
+      const float* ind = F(ly.actd[l - 1]);
+      const float* A = F(ly.adj[l]);
+      const float* Ad = F(ly.adjd[l]);
+      const float* W = F(ly.theta) + mt.woff[l];
+      const float* Wd = F(ly.thetad) + mt.woff[l];
+      const float* eps = F(ly.eps);
+      float* acc1 = F(ly.acc1);
+      float* acc2 = F(ly.acc2);
+      float* acc3 = F(ly.acc3);
+      const int woff = mt.woff[l], boff = mt.boff[l];
+      const bool has_ind = dual && l > 1;
+      // -- weight / bias adjoints: outputs (o, i) with i == din meaning the bias
+      auto setup = [&](int o) {
+        const int oo = o / (din + 1);
+        return Ctx2{oo, o - oo * (din + 1)};
+      };
+      reduce_outputs(
+          dout * (din + 1), nr, setup,
+          [&](const Ctx2& c, int k) {
+            float t = A[k * ldo + c.a] * (c.b < din ? in[k * ldi + c.b] : 1.f);
+            if (has_ind && c.b < din) t += Ad[k * ldo + c.a] * ind[k * ldi + c.b];
+            return t;
+          },
+          [&](int o, float acc) {
+            const int oo = o / (din + 1), ii = o - oo * (din + 1);
+            const int pp = ii < din ? woff + oo * ldw + ii : boff + oo;
+            acc1[pp] += acc;
+            acc2[pp] += acc * eps[pp];
+          });
+      if (dual) {
+        reduce_outputs(
+            dout * (din + 1), nr, setup,
+            [&](const Ctx2& c, int k) { return Ad[k * ldo + c.a] * (c.b < din ? in[k * ldi + c.b] : 1.f); },
+            [&](int o, float acc) {
+              const int oo = o / (din + 1), ii = o - oo * (din + 1);
+              const int pp = ii < din ? woff + oo * ldw + ii : boff + oo;
+              acc3[pp] += acc * eps[pp];
+            });
+      }
+      // -- input adjoints
+      if (l > 1 || need_x) {
+        float* Ai = F(ly.adj[l - 1]);
+        float* Aid = F(ly.adjd[l - 1]);
+        auto setup2 = [&](int o) {
+          const int rr = o / din;
+          return Ctx2{rr, o - rr * din};
+        };
+        reduce_outputs(
+            nr * din, dout, setup2,
+            [&](const Ctx2& c, int k) {
+              float t = A[c.a * ldo + k] * W[k * ldw + c.b];
+              if (dual) t += Ad[c.a * ldo + k] * Wd[k * ldw + c.b];
+              return t;
+            },
+            [&](int o, float acc) {
+              const int rr = o / din, ii = o - rr * din;
+              if (l > 1) {
+                Ai[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f;
+              } else {
+                F(ly.ubar)[(r0 + rr) * din + ii] += acc;
+              }
+            });
+        if (dual && l > 1) {
+          reduce_outputs(
+              nr * din, dout, setup2, [&](const Ctx2& c, int k) { return Ad[c.a * ldo + k] * W[k * ldw + c.b]; },
+              [&](int o, float acc) {
+                const int rr = o / din, ii = o - rr * din;
+                Aid[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f;
+              });
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- push this CTA's accumulators to the slice owners, then clear them ------------------------------------------
+  __device__ void push_acc(int ncomp) {
+    const int slice = p.slice;
+    for (int pp = tid; pp < mt.Pp; pp += NT) {
+      const int owner = pp / slice, j = pp - owner * slice;
+      float* r = remote(ly.recv, owner) + (size_t)rank * 3 * slice + j;
+      r[0] = F(ly.acc1)[pp];
+      r[slice] = F(ly.acc2)[pp];
+      if (ncomp > 2) r[2 * slice] = F(ly.acc3)[pp];
+      F(ly.acc1)[pp] = 0.f;
+      F(ly.acc2)[pp] = 0.f;
+      F(ly.acc3)[pp] = 0.f;
+    }
+  }
+  __device__ __forceinline__ float recv_sum(int comp, int j) const {
+    float s = 0.f;
+    const float* r = sm + ly.recv + comp * p.slice + j;
+    for (int c = 0; c < p.G; ++c) s += r[(size_t)c * 3 * p.slice];
+    return s;
+  }
+  // owner writes a value of its slice element into the same padded slot of every CTA
+  __device__ __forceinline__ void bcast(int off, int pp, float val) {
+    for (int c = 0; c < p.G; ++c) remote(off, c)[pp] = val;
+  }
+
+  // ---- coreset weights a = N f(v)  (psvi_classes.py:476,505; f per class :111,:1358,:1486) ------------------------
+  __device__ void setup_coreset() {
+    float* a = F(ly.a);
+    float* f = F(ly.f);
+    const int M = p.M;
+    if (p.roww) {
+      for (int m = tid; m < M; m += NT) { a[m] = __ldg(p.roww + m); f[m] = 0.f; }
+      __syncthreads();
+      return;
+    }
+    if (p.vmode == PSVI_VMODE_IDENTITY) {
+      for (int m = tid; m < M; m += NT) { f[m] = __ldg(p.v + m); a[m] = p.Nf * f[m]; }
+      __syncthreads();
+      return;
+    }
+    float mx = -INFINITY;
+    for (int m = tid; m < M; m += NT) mx = fmaxf(mx, __ldg(p.v + m));
+    mx = block_max(mx, F(ly.red));
+    float se = 0.f;
+    for (int m = tid; m < M; m += NT) se += expf(__ldg(p.v + m) - mx);
+    se = block_sum(se, F(ly.red));
+    const float sc = p.Nf * (p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? expf(p.alpha) : 1.f);
+    for (int m = tid; m < M; m += NT) {
+      f[m] = expf(__ldg(p.v + m) - mx) / se;
+      a[m] = sc * f[m];
+    }
+    __syncthreads();
+  }
+
+  // ---- one gradient pass of the inner objective over the pseudo rows for sample s; returns sum_m a_m nll[s,m] -------
+  __device__ float inner_pass(int s, int slab, bool dual) {
+    sample_theta(s, slab, dual, 0.f);
+    float part = 0.f;
+    for (int r0 = 0; r0 < p.M; r0 += p.RC) {
+      const int nr = min(p.RC, p.M - r0);
+      const float* a0 = stage_rows(r0, nr);
+      for (int rr = tid; rr < nr; rr += NT) F(ly.cw)[rr] = F(ly.a)[r0 + rr];
+      __syncthreads();
+      forward(a0, nr, dual);
+      loss_stage(nr, dual ? 2 : 1, r0);
+      for (int rr = tid; rr < nr; rr += NT) part += F(ly.cw)[rr] * F(ly.nll)[rr];
+      backward(a0, nr, dual, dual, r0);
+    }
+    return part;
+  }
+
+  __device__ void init();
+  __device__ void run();
+  __device__ void eval_weights();
+  __device__ void eval_rows();
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// ---- init: zero shared memory, index maps, parameters, pseudo-data, coreset weights ----------------------------------
+__device__ void Engine::init() {
+  const int Pp = mt.Pp, Pt = mt.Pt;
+  int* top = I(ly.tl_of_pad);
+  int* pot = I(ly.pad_of_tl);
+  for (int i = tid; i < ly.total; i += NT) sm[i] = 0.f;
+  __syncthreads();
+  for (int pp = tid; pp < Pp; pp += NT) top[pp] = -1;
+  __syncthreads();
+  for (int q = tid; q < Pt; q += NT) {
+    int l = 1;
+    while (l < p.L && q >= mt.tlw[l + 1]) ++l;
+    int pp;
+    if (q < mt.tlb[l]) {
+      const int r = q - mt.tlw[l], oo = r / mt.din[l], ii = r - oo * mt.din[l];
+      pp = mt.woff[l] + oo * mt.ldw[l] + ii;
+    } else {
+      pp = mt.boff[l] + (q - mt.tlb[l]);
+    }
+    pot[q] = pp;
+    top[pp] = q;
+    F(ly.mu)[pp] = p.mu[q];
+    F(ly.rho)[pp] = p.rho[q];
+  }
+  {
+    const int D = p.dims[0], ld0 = mt.lda[0];
+    for (int i = tid; i < p.M * D; i += NT) {
+      const int m = i / D, c = i - m * D;
+      F(ly.su)[m * ld0 + c] = __ldg(p.u + i);
+    }
+    for (int m = tid; m < p.M; m += NT) I(ly.sz)[m] = __ldg(p.z + m);
+  }
+  __syncthreads();
+  refresh_sigma();
+  if (p.M > 0) setup_coreset();
+}
+
+__device__ void Engine::run() {
+  const int slice = p.slice, G = p.G, Pp = mt.Pp, Pt = mt.Pt;
+  const int j0 = rank * slice;  // first padded index of my slice
+  int* top = I(ly.tl_of_pad);
+  int* pot = I(ly.pad_of_tl);
+  float* ost = F(ly.ost);
+  // owner state rows: 0 pbar_mu 1 pbar_rho 2 mbar_mu 3 mbar_rho 4 vbar_mu 5 vbar_rho 6 am_mu 7 am_rho 8 av_mu 9 av_rho
+  auto OST = [&](int row, int j) -> float& { return ost[row * slice + j]; };
+  init();
+  if (p.adam_m && (p.flags & F_UNROLL)) {
+    for (int j = tid; j < slice; j += NT) {
+      const int pp = j0 + j;
+      const int q = pp < Pp ? top[pp] : -1;
+      if (q >= 0) {
+        OST(6, j) = p.adam_m[q];
+        OST(7, j) = p.adam_m[Pt + q];
+        OST(8, j) = p.adam_v[q];
+        OST(9, j) = p.adam_v[Pt + q];
+      }
+    }
+  }
+  cluster.sync();  // every CTA's shared memory is initialised before anybody pushes into it
+
+  // torch.optim.Adam defaults (psvi_classes.py:861).  The reference mixes Python doubles and fp32 tensors: betas and
+  // (1 - beta) reach the tensors as fp32 roundings of the double values; bias corrections are double arithmetic.
+  const double B1 = 0.9, B2 = 0.999;
+  const float b1 = (float)B1, b2 = (float)B2, omb1 = (float)(1.0 - B1), omb2 = (float)(1.0 - B2), aeps = 1e-8f;
+  const bool want_loss = p.inner_losses != nullptr;
+
+  // =================================================================================================================
+  // Phase U: T inner Adam steps  (psvi_classes.py:549-555 ; optim.py:224-229,303-367)
+  // =================================================================================================================
+  if (p.flags & F_UNROLL) {
+    double b1t = pow(B1, (double)p.step0), b2t = pow(B2, (double)p.step0);
+    for (int t = 0; t < p.T; ++t) {
+      float lpart = 0.f;
+      for (int s = rank; s < p.S; s += G) lpart += inner_pass(s, t, false);
+      push_acc(2);
+      if (want_loss) {
+        // KL(q||p) of my slice at phi_t (neural_net.py:101-108), added once (Q1)
+        for (int j = tid; j < slice; j += NT) {
+          const int pp = j0 + j;
+          if (pp < Pp && top[pp] >= 0) {
+            const float sg = F(ly.sig)[pp], m = F(ly.mu)[pp];
+            lpart += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
+          }
+        }
+        lpart = block_sum(lpart, F(ly.red));
+        if (tid == 0) remote(ly.lossrecv, 0)[rank] = lpart;
+      }
+      cluster.sync();
+      if (want_loss && rank == 0 && tid == 0) {
+        float s = 0.f;
+        for (int c = 0; c < G; ++c) s += F(ly.lossrecv)[c];
+        p.inner_losses[t] = s;
+      }
+      // ---- owner: gradient of my slice, Adam, trajectory, broadcast ----
+      b1t *= B1;
+      b2t *= B2;
+      const float bc1 = (float)(1.0 - b1t);
+      const float sq2 = (float)sqrt(1.0 - b2t);
+      const float bc2 = (float)(1.0 - b2t);
+      const float step_size = p.lr / bc1;
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        const float mu = F(ly.mu)[pp], rho = F(ly.rho)[pp], sg = F(ly.sig)[pp], sgm = F(ly.sgm)[pp];
+        const float g_mu = recv_sum(0, j) + mu;
+        const float g_rho = sgm * (recv_sum(1, j) + (sg - 1.f / sg));
+        float nm[2], nv[2], np[2];
+        const float gg[2] = {g_mu, g_rho}, pv[2] = {mu, rho};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float g = gg[c];
+          float m = OST(6 + c, j) * b1 + omb1 * g;
+          float v = OST(8 + c, j) * b2 + omb2 * g * g;
+          float den;
+          if (p.adam_mode == PSVI_ADAM_ROBUST_HIGHER) {
+            den = sqrtf(v + 1e-8f) / sq2 + aeps;                     // optim.py:346-363
+            np[c] = pv[c] - step_size * (m / den);
+          } else if (p.adam_mode == PSVI_ADAM_TORCH) {
+            den = sqrtf(v) / sq2 + aeps;
+            np[c] = pv[c] - step_size * (m / den);
+          } else {                                                    // hypergrad/diff_optimizers.py:184-213
+            v += 1e-12f;
+            den = sqrtf(v / bc2) + aeps;
+            np[c] = pv[c] - p.lr * (m / bc1 / den);
+          }
+          nm[c] = m;
+          nv[c] = v;
+        }
+        if (p.g_out) {
+          p.g_out[q] = g_mu;
+          p.g_out[Pt + q] = g_rho;
+        }
+        if (p.traj) {
+          float* tr = p.traj + (size_t)t * 8 * Pt;
+          tr[q] = mu; tr[Pt + q] = rho;
+          tr[2 * Pt + q] = g_mu; tr[3 * Pt + q] = g_rho;
+          tr[4 * Pt + q] = nm[0]; tr[5 * Pt + q] = nm[1];
+          tr[6 * Pt + q] = nv[0]; tr[7 * Pt + q] = nv[1];
+        }
+        if (!(p.flags & F_NOUPDATE)) {
+          OST(6, j) = nm[0]; OST(7, j) = nm[1]; OST(8, j) = nv[0]; OST(9, j) = nv[1];
+          bcast(ly.mu, pp, np[0]);
+          bcast(ly.rho, pp, np[1]);
+        }
+      }
+      cluster.sync();
+      refresh_sigma();
+    }
+    if (p.flags & F_WRITE_PHI) {
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        p.mu[q] = F(ly.mu)[pp];
+        p.rho[q] = F(ly.rho)[pp];
+        if (p.adam_m) {
+          p.adam_m[q] = OST(6, j); p.adam_m[Pt + q] = OST(7, j);
+          p.adam_v[q] = OST(8, j); p.adam_v[Pt + q] = OST(9, j);
+        }
+      }
+    }
+  }
+
+  // =================================================================================================================
+  // Phase O: outer objective psvi_elbo and its gradient at phi_T   (psvi_classes.py:445-486, A.2)
+  // =================================================================================================================
+  if (p.flags & F_OUTER) {
+    const int slab = p.T;
+    const int R = p.M + p.B;
+    const float dscale = p.Nf / (float)p.Btot;
+    // O1: per-sample p_s, d_s, nkl_s
+    for (int s = rank; s < p.S; s += G) {
+      float nkl = sample_theta(s, slab, false, 0.f);
+      float ps = 0.f, ds = 0.f;
+      for (int r0 = 0; r0 < R;) {
+        const int lim = r0 < p.M ? p.M : R;
+        const int nr = min(p.RC, lim - r0);
+        const float* a0 = stage_rows(r0, nr);
+        __syncthreads();
+        forward(a0, nr, false);
+        loss_stage(nr, 0, r0);
+        if (r0 < p.M) {
+          for (int rr = tid; rr < nr; rr += NT) ps += F(ly.a)[r0 + rr] * F(ly.nll)[rr];
+        } else {
+          for (int rr = tid; rr < nr; rr += NT) ds += F(ly.nll)[rr];
+        }
+        __syncthreads();
+        r0 += nr;
+      }
+      // the S per-sample sums are O(N) while the importance-weight adjoints depend on their *differences*:
+      // reduce and keep them in double (the fp32 reference loses ~2 digits here at init_sd=1e-6)
+      const double nkl_d = block_sum_d((double)nkl, F(ly.red));
+      const double ps_d = block_sum_d((double)ps, F(ly.red));
+      const double ds_d = block_sum_d((double)ds, F(ly.red)) * (double)dscale;
+      if (tid < G) {
+        reinterpret_cast<double*>(remote(ly.lw, tid))[s] = -ps_d + nkl_d;
+        reinterpret_cast<double*>(remote(ly.e, tid))[s] = ds_d - (double)p.kappa * ps_d;
+        remote(ly.dsv, tid)[s] = (float)ds_d;
+      }
+    }
+    cluster.sync();
+    // O2: importance weights and adjoint seeds (every CTA, redundantly; S is tiny)
+    if (tid == 0) {
+      const int S = p.S;
+      const double* lw = reinterpret_cast<const double*>(F(ly.lw));
+      const double* ev = reinterpret_cast<const double*>(F(ly.e));
+      double mx = -INFINITY;
+      for (int s = 0; s < S; ++s) mx = fmax(mx, lw[s]);
+      double se = 0.0;
+      for (int s = 0; s < S; ++s) se += exp(lw[s] - mx);
+      double ebar = 0.0, lwm = 0.0;
+      for (int s = 0; s < S; ++s) {
+        const double w = exp(lw[s] - mx) / se;
+        F(ly.w)[s] = (float)w;
+        ebar += w * ev[s];
+        lwm += lw[s];
+      }
+      lwm /= (double)S;
+      double bsum = 0.0;
+      for (int s = 0; s < S; ++s) {
+        const double w = exp(lw[s] - mx) / se;
+        const double beta = w * (ev[s] - ebar) - (double)p.kappa / (double)S;  // dLoss/dlw_s
+        F(ly.beta)[s] = (float)beta;
+        F(ly.gp)[s] = (float)(-(double)p.kappa * w - beta);                    // dLoss/dp_s
+        bsum += beta;
+      }
+      F(ly.red)[40] = (float)bsum;
+      const float lossv = (float)(ebar - (double)p.kappa * lwm);
+      if (rank == 0) {
+        if (p.loss_out) p.loss_out[0] = lossv;
+        if (p.flags & F_STORE_GOUT) {
+          float* go = p.gout + 2 * Pt + p.M * p.dims[0] + p.M;
+          for (int s = 0; s < S; ++s) go[s] = F(ly.dsv)[s];
+          go[S] = lossv;
+          go[S + 1] = (float)ebar;
+          go[S + 2] = (float)lwm;
+          go[S + 3] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    const float beta_sum = F(ly.red)[40];
+    // O3: backward with per-sample row weights
+    for (int s = rank; s < p.S; s += G) {
+      const float beta = F(ly.beta)[s], gp = F(ly.gp)[s], wd = F(ly.w)[s] * dscale;
+      sample_theta(s, slab, false, beta);
+      for (int r0 = 0; r0 < R;) {
+        const bool pseudo = r0 < p.M;
+        const int lim = pseudo ? p.M : R;
+        const int nr = min(p.RC, lim - r0);
+        const float* a0 = stage_rows(r0, nr);
+        for (int rr = tid; rr < nr; rr += NT) F(ly.cw)[rr] = pseudo ? gp * F(ly.a)[r0 + rr] : wd;
+        __syncthreads();
+        forward(a0, nr, false);
+        loss_stage(nr, 1, r0);
+        if (pseudo) {
+          for (int rr = tid; rr < nr; rr += NT) F(ly.abar)[r0 + rr] += gp * F(ly.nll)[rr];
+        }
+        backward(a0, nr, false, pseudo, r0);
+        r0 += nr;
+      }
+    }
+    push_acc(2);
+    cluster.sync();
+    // O4: owner: dLoss/dphi_T of my slice (no analytic-KL term in the outer objective)
+    for (int j = tid; j < slice; j += NT) {
+      const int pp = j0 + j;
+      const int q = pp < Pp ? top[pp] : -1;
+      if (q < 0) continue;
+      const float g_mu = recv_sum(0, j);
+      const float g_rho = F(ly.sgm)[pp] * (recv_sum(1, j) + beta_sum / F(ly.sig)[pp]);
+      OST(0, j) = g_mu;
+      OST(1, j) = g_rho;
+      if (p.flags & F_STORE_GOUT) {
+        p.gout[q] = g_mu;
+        p.gout[Pt + q] = g_rho;
+      }
+    }
+    cluster.sync();  // recv may be overwritten by the next phase's pushes only after every owner has read it
+  }
+
+  // =================================================================================================================
+  // Phase H: a single Hessian-vector pass along gdot (building block / hyper trainer)
+  // =================================================================================================================
+  if (p.flags & F_HVP) {
+    for (int q = tid; q < Pt; q += NT) {
+      F(ly.gmu)[pot[q]] = __ldg(p.gdot + q);
+      F(ly.grho)[pot[q]] = __ldg(p.gdot + Pt + q);
+    }
+    __syncthreads();
+    for (int s = rank; s < p.S; s += G) inner_pass(s, 0, true);
+    push_acc(3);
+    cluster.sync();
+    for (int j = tid; j < slice; j += NT) {
+      const int pp = j0 + j;
+      const int q = pp < Pp ? top[pp] : -1;
+      if (q < 0) continue;
+      const float sg = F(ly.sig)[pp], sgm = F(ly.sgm)[pp], md = F(ly.gmu)[pp], rd = F(ly.grho)[pp];
+      const float isg = 1.f / sg;
+      p.h_phi[q] = recv_sum(0, j) + md;
+      p.h_phi[Pt + q] = sgm * recv_sum(1, j) + sgm * (1.f - sgm) * rd * recv_sum(2, j) +
+                        ((1.f + isg * isg) * sgm * sgm + (sg - isg) * sgm * (1.f - sgm)) * rd;
+    }
+    cluster.sync();
+  }
+
+  // =================================================================================================================
+  // Phase R: reverse sweep through the T Adam steps   (A.4 + A.6; replaces autograd's double backward)
+  // =================================================================================================================
+  if (p.flags & F_REVERSE) {
+    if (p.flags & F_LOAD_GOUT) {
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        OST(0, j) = p.gout[q];
+        OST(1, j) = p.gout[Pt + q];
+      }
+      if (rank == 0) {
+        const int MD = p.M * p.dims[0];
+        for (int i = tid; i < MD; i += NT) F(ly.ubar)[i] = p.gout[2 * Pt + i];
+        for (int i = tid; i < p.M; i += NT) F(ly.abar)[i] = p.gout[2 * Pt + MD + i];
+      }
+      __syncthreads();
+    }
+    for (int t = p.T - 1; t >= 0; --t) {
+      const double b1t = pow(B1, (double)(t + 1)), b2t = pow(B2, (double)(t + 1));
+      const float k = p.lr / (float)(1.0 - b1t);
+      const float sq2 = (float)sqrt(1.0 - b2t);
+      const float* tr = p.traj + (size_t)t * 8 * Pt;
+      // ---- owner: Adam VJP of my slice -> direction gbar; broadcast gbar and phi_t ----
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        float gb[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float g = tr[(2 + c) * Pt + q], m = tr[(4 + c) * Pt + q], v = tr[(6 + c) * Pt + q];
+          const float pb = OST(0 + c, j);
+          const float qd = sqrtf(v + 1e-8f);
+          const float den = qd / sq2 + aeps;
+          const float mbar = OST(2 + c, j) - k * pb / den;
+          const float denbar = k * pb * m / (den * den);
+          float vbar = OST(4 + c, j) + denbar / (2.f * qd * sq2);
+          if (v == 0.f) vbar = 0.f;  // _maybe_mask hook (optim.py:40-52,346-347)
+          gb[c] = omb1 * mbar + 2.f * omb2 * g * vbar;
+          OST(2 + c, j) = b1 * mbar;
+          OST(4 + c, j) = b2 * vbar;
+        }
+        bcast(ly.gmu, pp, gb[0]);
+        bcast(ly.grho, pp, gb[1]);
+        bcast(ly.mu, pp, tr[q]);
+        bcast(ly.rho, pp, tr[Pt + q]);
+      }
+      cluster.sync();
+      refresh_sigma();
+      // ---- every CTA: HVP pass over its samples ----
+      for (int s = rank; s < p.S; s += G) inner_pass(s, t, true);
+      push_acc(3);
+      cluster.sync();
+      // ---- owner: phibar_t = phibar_{t+1} + H gbar ----
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        const float sg = F(ly.sig)[pp], sgm = F(ly.sgm)[pp], md = F(ly.gmu)[pp], rd = F(ly.grho)[pp];
+        const float isg = 1.f / sg;
+        OST(0, j) += recv_sum(0, j) + md;
+        OST(1, j) += sgm * recv_sum(1, j) + sgm * (1.f - sgm) * rd * recv_sum(2, j) +
+                     ((1.f + isg * isg) * sgm * sgm + (sg - isg) * sgm * (1.f - sgm)) * rd;
+      }
+      // (the next iteration's broadcasts happen before anyone pushes into recv again: the pushes come after the
+      //  cluster.sync() that follows the broadcasts)
+    }
+    if (p.g_out) {  // dLoss/dphi_0, useful for diagnostics
+      for (int j = tid; j < slice; j += NT) {
+        const int pp = j0 + j;
+        const int q = pp < Pp ? top[pp] : -1;
+        if (q < 0) continue;
+        p.g_out[q] = OST(0, j);
+        p.g_out[Pt + q] = OST(1, j);
+      }
+    }
+  }
+
+  // =================================================================================================================
+  // Final: reduce ubar / abar over the cluster (fixed order) and map abar -> v_grad through f
+  // =================================================================================================================
+  if (p.flags & (F_FINAL | F_STORE_GOUT)) {
+    cluster.sync();
+    if (rank == 0) {
+      const int MD = p.M * p.dims[0];
+      float* red = F(ly.red);
+      for (int i = tid; i < MD + p.M; i += NT) {
+        float s = 0.f;
+        const int off = i < MD ? ly.ubar + i : ly.abar + (i - MD);
+        for (int c = 0; c < G; ++c) s += *remote(off, c);
+        if (p.flags & F_STORE_GOUT) p.gout[2 * Pt + i] = s;
+        sm[off] = s;  // rank 0 now holds the totals (remote reads of rank 0 itself happened in this same iteration)
+      }
+      __syncthreads();
+      if (p.flags & F_FINAL) {
+        for (int i = tid; i < MD; i += NT) p.u_grad[i] = F(ly.ubar)[i];
+        if (p.v_grad) {
+          if (p.vmode == PSVI_VMODE_IDENTITY || p.roww) {
+            for (int m = tid; m < p.M; m += NT) p.v_grad[m] = p.Nf * F(ly.abar)[m];
+          } else {
+            float dot = 0.f;
+            for (int m = tid; m < p.M; m += NT) dot += F(ly.f)[m] * F(ly.abar)[m];
+            dot = block_sum(dot, red);
+            const float sc = p.Nf * (p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? expf(p.alpha) : 1.f);
+            for (int m = tid; m < p.M; m += NT) p.v_grad[m] = sc * F(ly.f)[m] * (F(ly.abar)[m] - dot);
+            if (p.alpha_grad && tid == 0)
+              p.alpha_grad[0] = p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? sc * dot : 0.f;
+          }
+        }
+      }
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+  }
+}
+
+// =================================================================================================================
+// Predictive pass (PSVI.evaluate, psvi_classes.py:1031-1108; run_mfvi_subset test loop, baselines.py:1035-1043)
+// =================================================================================================================
+// E1: one CTA per noise slab (= test batch): importance weights w_s = softmax_s(+sum_m a_m log p(z_m|theta_s)... )
+// NB the reference's sign quirk Q3: log_weights = -(+sum_m a_m log p) + nkl = (sum_m a_m nll) + nkl.
+__device__ void Engine::eval_weights() {
+  init();
+  const int slab_local = blockIdx.x;
+  const int slab = p.first_slab + slab_local;
+  for (int s = 0; s < p.S; ++s) {
+    float nkl = sample_theta(s, slab, false, 0.f);
+    float ps = 0.f;
+    for (int r0 = 0; r0 < p.M; r0 += p.RC) {
+      const int nr = min(p.RC, p.M - r0);
+      const float* a0 = stage_rows(r0, nr);
+      __syncthreads();
+      forward(a0, nr, false);
+      loss_stage(nr, 0, r0);
+      for (int rr = tid; rr < nr; rr += NT) ps += F(ly.a)[r0 + rr] * F(ly.nll)[rr];
+      __syncthreads();
+    }
+    nkl = block_sum(nkl, F(ly.red));
+    ps = block_sum(ps, F(ly.red));
+    if (tid == 0) F(ly.lw)[s] = ps + nkl;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int S = p.S;
+    float mx = -INFINITY;
+    for (int s = 0; s < S; ++s) mx = fmaxf(mx, F(ly.lw)[s]);
+    float se = 0.f;
+    for (int s = 0; s < S; ++s) se += expf(F(ly.lw)[s] - mx);
+    float ent = 0.f, sw = 0.f, sw2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float w = expf(F(ly.lw)[s] - mx) / se;
+      p.eval_w[(size_t)slab_local * S + s] = w;
+      if (w > 0.f) ent -= logf(w) * w;
+      sw += w;
+      sw2 += w * w;
+    }
+    if (slab_local == p.n_slabs - 1) {  // Q12: diagnostics of the LAST batch only
+      p.eval_out[3] = ent;
+      p.eval_out[4] = sw * sw / sw2 / (float)S;
+    }
+  }
+}
+
+// E2: one CTA per chunk of test rows; loops over the S samples (re-drawing the slab's noise) and accumulates the
+// predictive distribution of its rows in shared memory.
+__device__ void Engine::eval_rows() {
+  init();
+  const int slab_local = blockIdx.x / p.chunks_per_slab, chunk = blockIdx.x - slab_local * p.chunks_per_slab;
+  const int slab = p.first_slab + slab_local;
+  const int row_begin = slab_local * p.batch + chunk * p.RC;
+  const int slab_end = min((slab_local + 1) * p.batch, p.n_rows);
+  const int nr = min(p.RC, slab_end - row_begin);
+  const int C = p.dims[p.L], ld = mt.lda[p.L];
+  float nll_sum = 0.f, correct = 0.f;
+  if (nr > 0) {
+    float* probs = F(ly.adj[p.L]);  // zeroed by init()
+    const float* a0 = stage_rows(p.M + row_begin, nr);
+    __syncthreads();
+    for (int s = 0; s < p.S; ++s) {
+      sample_theta(s, slab, false, 0.f);
+      forward(a0, nr, false);
+      const float wgt = p.eval_mode == 0 ? p.eval_w[(size_t)slab_local * p.S + s] : 1.f / (float)p.S;
+      const float* o = F(ly.act[p.L]);
+      for (int rr = tid; rr < nr; rr += NT) {
+        const float* row = o + rr * ld;
+        if (p.eval_mode == 2) {
+          for (int c = 0; c < C; ++c) probs[rr * ld + c] += wgt * row[c];
+        } else {
+          float mx = row[0];
+          for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+          float se = 0.f;
+          for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+          const float inv = wgt / se;
+          for (int c = 0; c < C; ++c) probs[rr * ld + c] += inv * expf(row[c] - mx);
+        }
+      }
+      __syncthreads();
+    }
+    const int* lab = I(ly.lab);
+    for (int rr = tid; rr < nr; rr += NT) {
+      const float* pr = probs + rr * ld;
+      const int y = lab[rr];
+      int am = 0;
+      float best = pr[0];
+      for (int c = 1; c < C; ++c)
+        if (pr[c] > best) { best = pr[c]; am = c; }
+      correct += (am == y) ? 1.f : 0.f;
+      if (p.eval_mode == 2) {  // Categorical(logits=mean logits)
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += expf(pr[c] - best);
+        nll_sum += best + logf(se) - pr[y];
+      } else {                 // Categorical(probs=...): normalise, clamp to [eps, 1-eps], log
+        float tot = 0.f;
+        for (int c = 0; c < C; ++c) tot += pr[c];
+        float pn = pr[y] / tot;
+        pn = fminf(fmaxf(pn, 1.1920929e-07f), 1.f - 1.1920929e-07f);
+        nll_sum -= logf(pn);
+      }
+    }
+  }
+  nll_sum = block_sum(nll_sum, F(ly.red));
+  correct = block_sum(correct, F(ly.red));
+  if (tid == 0) {
+    float* o = p.eval_part + (size_t)blockIdx.x * 4;
+    o[0] = nll_sum; o[1] = correct; o[2] = (float)(nr > 0 ? nr : 0); o[3] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) psvi_mf_engine_kernel(const __grid_constant__ EP p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ Meta mt;
+  __shared__ Lay ly;
+  if (threadIdx.x == 0) {
+    make_meta(p.dims, p.L, mt);
+    make_layout(p, mt, ly);
+  }
+  __syncthreads();
+  Engine e(p, mt, ly, smem_dyn);
+  e.run();
+}
+
+
+__global__ void __launch_bounds__(NT, 1) psvi_mf_eval_weights_kernel(const __grid_constant__ EP p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ Meta mt;
+  __shared__ Lay ly;
+  if (threadIdx.x == 0) {
+    make_meta(p.dims, p.L, mt);
+    make_layout(p, mt, ly);
+  }
+  __syncthreads();
+  Engine e(p, mt, ly, smem_dyn);
+  e.rank = 0;
+  e.eval_weights();
+}
+
+__global__ void __launch_bounds__(NT, 1) psvi_mf_eval_rows_kernel(const __grid_constant__ EP p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ Meta mt;
+  __shared__ Lay ly;
+  if (threadIdx.x == 0) {
+    make_meta(p.dims, p.L, mt);
+    make_layout(p, mt, ly);
+  }
+  __syncthreads();
+  Engine e(p, mt, ly, smem_dyn);
+  e.rank = 0;
+  e.eval_rows();
+}
+
+// fixed-order final reduction of the per-CTA partials (deterministic, no atomics)
+__global__ void psvi_mf_eval_reduce_kernel(const float* part, int n, float* out) {
+  __shared__ double acc[3][NT];
+  double a = 0, b = 0, c = 0;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    a += part[4 * i];
+    b += part[4 * i + 1];
+    c += part[4 * i + 2];
+  }
+  acc[0][threadIdx.x] = a; acc[1][threadIdx.x] = b; acc[2][threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) {
+      double t = 0;
+      for (int i = 0; i < NT; ++i) t += acc[k][i];
+      out[k] = (float)t;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host side
+int validate_model(const psvi_mf_model* model) {
+  PSVI_REQUIRE(model != nullptr, PSVI_ERR_INVALID, "model is null");
+  PSVI_REQUIRE(model->n_layers >= 1 && model->n_layers <= MAXL, PSVI_ERR_UNSUPPORTED,
+               "n_layers=%d outside [1,%d]", model->n_layers, MAXL);
+  for (int l = 0; l <= model->n_layers; ++l)
+    PSVI_REQUIRE(model->dims[l] >= 1, PSVI_ERR_INVALID, "dims[%d]=%d must be >= 1", l, model->dims[l]);
+  PSVI_REQUIRE(model->mc_samples >= 1, PSVI_ERR_INVALID, "mc_samples=%d must be >= 1", model->mc_samples);
+  return PSVI_OK;
+}
+
+int launch_engine(EP& p, int rows_max, cudaStream_t stream) {
+  int dev = 0;
+  PSVI_CUDA_CHECK(cudaGetDevice(&dev));
+  int smem_max = 0;
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  Meta mt;
+  make_meta(p.dims, p.L, mt);
+  // cluster size: fewest CTAs that give every CTA the minimal number of samples, capped at 16 (non-portable max)
+  static int max_cluster = 0;
+  if (max_cluster == 0) {
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_engine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    max_cluster = 16;
+  }
+  int G = p.S < max_cluster ? p.S : max_cluster;
+  const int per = (p.S + G - 1) / G;
+  G = (p.S + per - 1) / per;
+  const bool dual = (p.flags & (F_REVERSE | F_HVP)) != 0;
+  for (;; --G) {
+    PSVI_REQUIRE(G >= 1, PSVI_ERR_UNSUPPORTED, "no feasible cluster size");
+    p.G = G;
+    p.slice = (mt.Pp + G - 1) / G;
+    // rows per chunk: the largest RC <= rows_max whose carve-up fits (static shared memory needs ~1 KB as well)
+    const size_t budget = (size_t)smem_max - 2048;
+    Lay ly;
+    p.RC = 1;
+    make_layout(p, mt, ly);
+    if ((size_t)ly.total * 4 > budget) {
+      if (G > 1) continue;  // a smaller cluster has larger slices but fewer receive buffers; try it
+      psvi_set_error("model too large for the shared-memory-resident engine (P_pad=%d, M=%d: %zu B needed, %zu B available)",
+                     mt.Pp, p.M, (size_t)ly.total * 4, budget);
+      return PSVI_ERR_UNSUPPORTED;
+    }
+    int lo = 1, hi = rows_max < 1 ? 1 : rows_max;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) / 2;
+      p.RC = mid;
+      make_layout(p, mt, ly);
+      if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+    }
+    p.RC = lo;
+    make_layout(p, mt, ly);
+    const size_t smem = (size_t)ly.total * 4;
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(G, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, psvi_mf_engine_kernel, &cfg);
+    if (qe != cudaSuccess || ncl < 1) {
+      (void)cudaGetLastError();
+      if (G == 1) {
+        psvi_set_error("cluster launch not possible even with one CTA: %s", cudaGetErrorString(qe));
+        return PSVI_ERR_CUDA;
+      }
+      // try the next smaller cluster that changes the samples-per-CTA count
+      continue;
+    }
+    cudaError_t le = cudaLaunchKernelEx(&cfg, psvi_mf_engine_kernel, p);
+    if (le != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (G == 1) {
+        psvi_set_error("engine launch failed: %s", cudaGetErrorString(le));
+        return PSVI_ERR_CUDA;
+      }
+      continue;
+    }
+    return PSVI_OK;
+  }
+}
+
+void fill_common(EP& p, const psvi_mf_model* model, const psvi_noise* noise, int M, float N, int vmode, float alpha) {
+  memset(&p, 0, sizeof(p));
+  p.L = model->n_layers;
+  for (int l = 0; l <= p.L; ++l) p.dims[l] = model->dims[l];
+  p.S = model->mc_samples;
+  p.M = M;
+  p.Nf = N;
+  p.vmode = vmode;
+  p.alpha = alpha;
+  p.kappa = 1.f;
+  p.noise_mode = noise->mode;
+  p.eps = noise->eps;
+  p.seed = noise->seed;
+  p.domain = noise->domain;
+  p.adam_mode = PSVI_ADAM_ROBUST_HIGHER;
+}
+
+int check_noise(const psvi_noise* noise) {
+  PSVI_REQUIRE(noise != nullptr, PSVI_ERR_INVALID, "noise is null");
+  PSVI_REQUIRE(noise->mode == PSVI_NOISE_EXTERNAL || noise->mode == PSVI_NOISE_PHILOX, PSVI_ERR_INVALID,
+               "unknown noise mode %d", noise->mode);
+  PSVI_REQUIRE(noise->mode != PSVI_NOISE_EXTERNAL || noise->eps != nullptr, PSVI_ERR_INVALID,
+               "external noise mode needs eps");
+  return PSVI_OK;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int64_t psvi_mf_num_theta(const psvi_mf_model* model) {
+  if (validate_model(model) != PSVI_OK) return PSVI_ERR_INVALID;
+  Meta mt;
+  make_meta(model->dims, model->n_layers, mt);
+  return mt.Pt;
+}
+
+size_t psvi_mf_traj_bytes(const psvi_mf_model* model, int32_t T) {
+  const int64_t P = psvi_mf_num_theta(model);
+  if (P < 0 || T < 0) return 0;
+  return (size_t)T * 8 * (size_t)P * sizeof(float);
+}
+
+int64_t psvi_mf_gout_floats(const psvi_mf_model* model, int32_t M) {
+  const int64_t P = psvi_mf_num_theta(model);
+  if (P < 0 || M < 0) return PSVI_ERR_INVALID;
+  return 2 * P + (int64_t)M * model->dims[0] + M + model->mc_samples + 4;
+}
+
+int psvi_mf_nested_step(const psvi_mf_model* model, const psvi_noise* noise, float* mu, float* rho, const float* u,
+                        const int32_t* z, const float* v, int32_t M, const float* xb, const int32_t* yb, int32_t B,
+                        int32_t n_total_rows, float N, int32_t vmode, float alpha, int32_t T, float lr,
+                        float pseudo_scale, int32_t phase_mask, float* traj, float* gout, float* u_grad, float* v_grad,
+                        float* alpha_grad, float* loss_out, float* inner_losses, void* stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(model->mc_samples > 1, PSVI_ERR_INVALID, "psvi_elbo needs mc_samples > 1 (psvi_classes.py:449)");
+  PSVI_REQUIRE(mu && rho && u && z && v && M > 0, PSVI_ERR_INVALID, "null parameter / pseudo-data pointer or M<=0");
+  PSVI_REQUIRE(T >= 0 && (T == 0 || traj), PSVI_ERR_INVALID, "T<0 or missing trajectory scratch");
+  PSVI_REQUIRE(phase_mask & (PSVI_PHASE_UNROLL | PSVI_PHASE_REVERSE), PSVI_ERR_INVALID, "empty phase_mask");
+  PSVI_REQUIRE(B >= 0 && n_total_rows >= B && n_total_rows > 0, PSVI_ERR_INVALID, "bad minibatch sizes B=%d total=%d",
+               B, n_total_rows);
+  PSVI_REQUIRE(B == 0 || (xb && yb), PSVI_ERR_INVALID, "minibatch pointers are null");
+  const bool both = (phase_mask & PSVI_PHASE_UNROLL) && (phase_mask & PSVI_PHASE_REVERSE);
+  PSVI_REQUIRE(both || gout, PSVI_ERR_INVALID, "split phases need the gout buffer");
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.B = B;
+  p.Btot = n_total_rows;
+  p.T = T;
+  p.lr = lr;
+  p.kappa = pseudo_scale;
+  p.mu = mu; p.rho = rho; p.u = u; p.z = z; p.v = v; p.xb = xb; p.yb = yb;
+  p.traj = traj; p.gout = gout; p.u_grad = u_grad; p.v_grad = v_grad; p.alpha_grad = alpha_grad;
+  p.loss_out = loss_out; p.inner_losses = inner_losses;
+  if (phase_mask & PSVI_PHASE_UNROLL) p.flags |= F_UNROLL | F_OUTER | F_WRITE_PHI;
+  if (phase_mask & PSVI_PHASE_REVERSE) {
+    PSVI_REQUIRE(u_grad != nullptr, PSVI_ERR_INVALID, "u_grad is null");
+    p.flags |= F_REVERSE | F_FINAL;
+  }
+  if (!both) p.flags |= (phase_mask & PSVI_PHASE_UNROLL) ? F_STORE_GOUT : F_LOAD_GOUT;
+  if (!(phase_mask & PSVI_PHASE_UNROLL)) p.inner_losses = nullptr;
+  return launch_engine(p, M > B ? M : B, (cudaStream_t)stream);
+}
+
+int psvi_mf_unroll(const psvi_mf_model* model, const psvi_noise* noise, float* mu, float* rho, float* adam_m,
+                   float* adam_v, int32_t step0, const float* x, const int32_t* y, const float* row_weights,
+                   const float* v, int32_t M, float N, int32_t vmode, float alpha, int32_t T, float lr,
+                   int32_t adam_mode, float* losses, void* stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(mu && rho && x && y && M > 0 && T >= 0 && step0 >= 0, PSVI_ERR_INVALID, "bad argument");
+  PSVI_REQUIRE(row_weights || v, PSVI_ERR_INVALID, "need row_weights or v");
+  PSVI_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), PSVI_ERR_INVALID, "adam_m / adam_v must come together");
+  PSVI_REQUIRE(adam_mode >= 0 && adam_mode <= 2, PSVI_ERR_INVALID, "unknown adam_mode %d", adam_mode);
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.T = T; p.step0 = step0; p.lr = lr; p.adam_mode = adam_mode;
+  p.mu = mu; p.rho = rho; p.adam_m = adam_m; p.adam_v = adam_v;
+  p.u = x; p.z = y; p.v = v; p.roww = row_weights;
+  p.inner_losses = losses;
+  p.flags = F_UNROLL | F_WRITE_PHI;
+  return launch_engine(p, M, (cudaStream_t)stream);
+}
+
+int psvi_mf_outer_grad(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                       const float* u, const int32_t* z, const float* v, int32_t M, const float* xb, const int32_t* yb,
+                       int32_t B, int32_t n_total_rows, float N, int32_t vmode, float alpha, float pseudo_scale,
+                       float* gout, float* u_grad, float* v_grad, float* alpha_grad, float* loss_out, void* stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(model->mc_samples > 1, PSVI_ERR_INVALID, "psvi_elbo needs mc_samples > 1 (psvi_classes.py:449)");
+  PSVI_REQUIRE(mu && rho && u && z && v && gout && u_grad && M > 0, PSVI_ERR_INVALID, "null pointer or M<=0");
+  PSVI_REQUIRE(B >= 0 && n_total_rows >= B && n_total_rows > 0 && (B == 0 || (xb && yb)), PSVI_ERR_INVALID,
+               "bad minibatch");
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.B = B; p.Btot = n_total_rows; p.T = 0; p.kappa = pseudo_scale;
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.u = u; p.z = z; p.v = v; p.xb = xb; p.yb = yb;
+  p.gout = gout; p.u_grad = u_grad; p.v_grad = v_grad; p.alpha_grad = alpha_grad; p.loss_out = loss_out;
+  p.flags = F_OUTER | F_STORE_GOUT | F_FINAL;
+  return launch_engine(p, M > B ? M : B, (cudaStream_t)stream);
+}
+
+int psvi_mf_inner_grad(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                       const float* u, const int32_t* z, const float* v, int32_t M, float N, int32_t vmode,
+                       float alpha, float* grad, float* value, void* stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(mu && rho && u && z && v && grad && M > 0, PSVI_ERR_INVALID, "null pointer or M<=0");
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.T = 1; p.lr = 0.f;
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.u = u; p.z = z; p.v = v;
+  p.g_out = grad; p.inner_losses = value;
+  p.flags = F_UNROLL | F_NOUPDATE;
+  return launch_engine(p, M, (cudaStream_t)stream);
+}
+
+int psvi_mf_inner_hvp(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                      const float* u, const int32_t* z, const float* v, int32_t M, float N, int32_t vmode,
+                      float alpha, const float* gdot, float* h_phi, float* h_u, float* h_v, float* h_alpha,
+                      void* stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(mu && rho && u && z && v && gdot && h_phi && h_u && M > 0, PSVI_ERR_INVALID, "null pointer or M<=0");
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.u = u; p.z = z; p.v = v;
+  p.gdot = gdot; p.h_phi = h_phi; p.u_grad = h_u; p.v_grad = h_v; p.alpha_grad = h_alpha;
+  p.flags = F_HVP | F_FINAL;
+  return launch_engine(p, M, (cudaStream_t)stream);
+}
+
+size_t psvi_mf_eval_scratch_bytes(const psvi_mf_model* model, int32_t n_rows, int32_t batch) {
+  if (validate_model(model) != PSVI_OK || n_rows <= 0 || batch <= 0) return 0;
+  const size_t n_slabs = ((size_t)n_rows + batch - 1) / batch;
+  const size_t chunks = ((size_t)(batch < n_rows ? batch : n_rows) + 31) / 32;
+  return (n_slabs * model->mc_samples + n_slabs * chunks * 4 + 64) * sizeof(float);
+}
+
+int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                     const float* u, const int32_t* z, const float* v, int32_t M, const float* xt, const int32_t* yt,
+                     int32_t n_rows, int32_t batch, int32_t first_slab, float N, int32_t vmode, float alpha,
+                     int32_t mode, float* out, void* scratch, void* stream_) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PSVI_REQUIRE(mu && rho && xt && yt && out && scratch, PSVI_ERR_INVALID, "null pointer");
+  PSVI_REQUIRE(n_rows > 0 && batch > 0 && first_slab >= 0, PSVI_ERR_INVALID, "bad n_rows/batch/first_slab");
+  PSVI_REQUIRE(mode >= 0 && mode <= 2, PSVI_ERR_INVALID, "unknown evaluate mode %d", mode);
+  PSVI_REQUIRE(mode != 0 || (u && z && v && M > 0), PSVI_ERR_INVALID, "importance-weighted mode needs pseudo-data");
+  PSVI_REQUIRE(mode != 0 || model->mc_samples > 1, PSVI_ERR_INVALID, "evaluate needs mc_samples > 1 (psvi_classes.py:1036)");
+  if (mode != 0) M = 0;
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.u = u; p.z = z; p.v = v; p.xb = xt; p.yb = yt;
+  p.n_rows = n_rows; p.batch = batch; p.first_slab = first_slab; p.eval_mode = mode;
+  p.n_slabs = (n_rows + batch - 1) / batch;
+  p.eval_w = (float*)scratch;
+  p.eval_part = p.eval_w + (size_t)p.n_slabs * p.S;
+  p.eval_out = out;
+  p.G = 1; p.flags = 0;
+  int dev = 0, smem_max = 0;
+  PSVI_CUDA_CHECK(cudaGetDevice(&dev));
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  Meta mt;
+  make_meta(p.dims, p.L, mt);
+  p.slice = mt.Pp;
+  const size_t budget = (size_t)smem_max - 2048;
+  Lay ly;
+  const int rows_cap = batch < n_rows ? batch : n_rows;
+  const int want = (M > rows_cap ? M : rows_cap) < 256 ? (M > rows_cap ? M : rows_cap) : 256;
+  int lo = 0, hi = want;
+  while (lo < hi) {  // largest RC <= want that fits
+    const int mid = (lo + hi + 1) / 2;
+    p.RC = mid;
+    make_layout(p, mt, ly);
+    if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+  }
+  PSVI_REQUIRE(lo >= 32 || lo >= want, PSVI_ERR_UNSUPPORTED,
+               "model too large for the shared-memory-resident predictive kernel (rows per chunk %d)", lo);
+  p.RC = lo;
+  make_layout(p, mt, ly);
+  const size_t smem = (size_t)ly.total * 4;
+  p.chunks_per_slab = (rows_cap + p.RC - 1) / p.RC;
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_eval_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_eval_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (mode == 0) {
+    psvi_mf_eval_weights_kernel<<<p.n_slabs, NT, smem, stream>>>(p);
+    PSVI_CUDA_CHECK(cudaGetLastError());
+  }
+  const int nctas = p.n_slabs * p.chunks_per_slab;
+  psvi_mf_eval_rows_kernel<<<nctas, NT, smem, stream>>>(p);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  psvi_mf_eval_reduce_kernel<<<1, NT, 0, stream>>>(p.eval_part, nctas, out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+}  // extern "C"

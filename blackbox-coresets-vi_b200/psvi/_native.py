@@ -1,0 +1,208 @@
+"""ctypes binding of libpsvi_b200.so (include/psvi_b200.h) -- the only door from Python to the CUDA hot path.
+
+Thin on purpose: every function passes `tensor.data_ptr()`s, sizes and the current CUDA stream.  There is no CPU
+fallback and no other backend: if the shared library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libpsvi_b200.so")
+
+MAX_LAYERS = 6
+VMODE_IDENTITY, VMODE_SOFTMAX, VMODE_EXPALPHA_SOFTMAX = 0, 1, 2
+ADAM_ROBUST_HIGHER, ADAM_TORCH, ADAM_HYPERGRAD = 0, 1, 2
+NOISE_EXTERNAL, NOISE_PHILOX = 0, 1
+PHASE_UNROLL, PHASE_REVERSE = 1, 2
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class MfModel(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)), ("mc_samples", C.c_int32)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("eps", C.c_void_p), ("seed", C.c_uint64), ("domain", C.c_uint32)]
+
+
+_lib = None
+
+_SIGS = {
+    "psvi_last_error": (C.c_char_p, []),
+    "psvi_device_sm_count": (C.c_int, []),
+    "psvi_mf_num_theta": (C.c_int64, [C.POINTER(MfModel)]),
+    "psvi_mf_traj_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32]),
+    "psvi_mf_gout_floats": (C.c_int64, [C.POINTER(MfModel), C.c_int32]),
+    "psvi_mf_nested_step": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "psvi_mf_unroll": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                 C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
+    "psvi_mf_outer_grad": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_float, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_inner_grad": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "psvi_mf_inner_hvp": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_eval_scratch_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32, C.c_int32]),
+    "psvi_mf_evaluate": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/psvi_b200.h declares (used by the CPU-side loader test)."""
+    return sorted(_SIGS)
+
+
+def lib():
+    """Loads libpsvi_b200.so (built by `__graft_entry__.build()` / `make -C csrc`).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                              " -- there is no CPU/PyTorch fallback for the PSVI hot path")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise NativeError("the PSVI hot path needs a CUDA device (sm_100a); there is no CPU fallback")
+    n = lib().psvi_device_sm_count()
+    if n <= 0:
+        raise NativeError("libpsvi_b200: " + last_error())
+    return n
+
+
+def last_error():
+    return lib().psvi_last_error().decode()
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(f"libpsvi_b200 error {rc}: {last_error()}")
+
+
+def make_model(dims, mc_samples):
+    dims = [int(d) for d in dims]
+    if not (2 <= len(dims) <= MAX_LAYERS + 1):
+        raise NativeError(f"unsupported number of layers: dims={dims}")
+    m = MfModel()
+    m.n_layers = len(dims) - 1
+    for i, d in enumerate(dims):
+        m.dims[i] = d
+    m.mc_samples = int(mc_samples)
+    return m
+
+
+def make_noise(eps=None, seed=0, domain=0):
+    n = Noise()
+    if eps is not None:
+        _chk(eps, torch.float32)
+        n.mode, n.eps = NOISE_EXTERNAL, eps.data_ptr()
+    else:
+        n.mode, n.eps = NOISE_PHILOX, None
+    n.seed, n.domain = int(seed) & (2**64 - 1), int(domain) & 0xFFFFFFFF
+    return n
+
+
+def _chk(t, dtype):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise NativeError(f"expected a contiguous CUDA {dtype} tensor, got {t.device} {t.dtype} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def _p(t, dtype=torch.float32):
+    return _chk(t, dtype)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def num_theta(model):
+    return int(lib().psvi_mf_num_theta(C.byref(model)))
+
+
+def traj_floats(model, T):
+    return int(lib().psvi_mf_traj_bytes(C.byref(model), T)) // 4
+
+
+def gout_floats(model, M):
+    return int(lib().psvi_mf_gout_floats(C.byref(model), M))
+
+
+def nested_step(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, alpha, T, lr, pseudo_scale, phase_mask,
+                traj, gout, u_grad, v_grad, alpha_grad, loss_out, inner_losses):
+    B = 0 if xb is None else xb.shape[0]
+    _check(lib().psvi_mf_nested_step(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
+                                     u.shape[0], _p(xb), _p(yb, torch.int32), B, n_total_rows, N, vmode, alpha, T, lr,
+                                     pseudo_scale, phase_mask, _p(traj), _p(gout), _p(u_grad), _p(v_grad),
+                                     _p(alpha_grad), _p(loss_out), _p(inner_losses), _stream()))
+
+
+def unroll(model, noise, mu, rho, adam_m, adam_v, step0, x, y, row_weights, v, N, vmode, alpha, T, lr, adam_mode, losses):
+    _check(lib().psvi_mf_unroll(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(adam_m), _p(adam_v), step0, _p(x),
+                                _p(y, torch.int32), _p(row_weights), _p(v), x.shape[0], N, vmode, alpha, T, lr,
+                                adam_mode, _p(losses), _stream()))
+
+
+def outer_grad(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, alpha, pseudo_scale, gout, u_grad, v_grad,
+               alpha_grad, loss_out):
+    B = 0 if xb is None else xb.shape[0]
+    _check(lib().psvi_mf_outer_grad(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
+                                    u.shape[0], _p(xb), _p(yb, torch.int32), B, n_total_rows, N, vmode, alpha,
+                                    pseudo_scale, _p(gout), _p(u_grad), _p(v_grad), _p(alpha_grad), _p(loss_out),
+                                    _stream()))
+
+
+def inner_grad(model, noise, mu, rho, u, z, v, N, vmode, alpha, grad, value):
+    _check(lib().psvi_mf_inner_grad(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
+                                    u.shape[0], N, vmode, alpha, _p(grad), _p(value), _stream()))
+
+
+def inner_hvp(model, noise, mu, rho, u, z, v, N, vmode, alpha, gdot, h_phi, h_u, h_v, h_alpha=None):
+    _check(lib().psvi_mf_inner_hvp(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
+                                   u.shape[0], N, vmode, alpha, _p(gdot), _p(h_phi), _p(h_u), _p(h_v), _p(h_alpha),
+                                   _stream()))
+
+
+def eval_scratch_floats(model, n_rows, batch):
+    return int(lib().psvi_mf_eval_scratch_bytes(C.byref(model), n_rows, batch)) // 4
+
+
+def evaluate(model, noise, mu, rho, u, z, v, xt, yt, batch, first_slab, N, vmode, alpha, mode, out, scratch):
+    M = 0 if u is None else u.shape[0]
+    _check(lib().psvi_mf_evaluate(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
+                                  _p(xt), _p(yt, torch.int32), xt.shape[0], batch, first_slab, N, vmode, alpha, mode,
+                                  _p(out), _p(scratch), _stream()))
+
+
+def philox_normal(seed, domain, first_slab, n_slabs, S, P, out):
+    _check(lib().psvi_philox_normal(int(seed) & (2**64 - 1), int(domain) & 0xFFFFFFFF, first_slab, n_slabs, S, P,
+                                    _p(out), _stream()))

@@ -1,0 +1,171 @@
+/*
+ * psvi_b200.h -- C ABI of libpsvi_b200.so: the B200-native (sm_100a) PSVI hot path.
+ *
+ * The reference (souravc83/Blackbox-Coresets-VI) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b), so every entry point below cites the reference *Python* interface it replaces.
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing synchronises inside;
+ *   - no allocation inside: the caller owns every buffer; *_workspace_bytes() say how large scratch must be;
+ *   - return 0 on success, negative on error (PSVI_ERR_*); psvi_last_error() gives a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns PSVI_ERR_CUDA.
+ *
+ * Layouts ("TL" = theta layout): for an MLP with L VILinear layers of sizes dims[0..L]
+ *   (psvi/models/neural_net.py:267-297, psvi/inference/psvi_classes.py:694-717) a per-sample weight vector is, per
+ *   layer l=1..L, W_l[dims[l]][dims[l-1]] row-major followed by b_l[dims[l]];  P = sum_l dims[l]*(dims[l-1]+1).
+ *   mu[P], rho[P] are the variational means / pre-softplus scales in TL (sigma = softplus(rho), neural_net.py:129-131).
+ *   eps[...][S][P] are standard-normal draws in TL, one [S][P] slab per forward (weight draw then bias draw per
+ *   layer, neural_net.py:155-162).  Labels are int32 class ids (the reference casts with .long(), Q11).
+ */
+#ifndef PSVI_B200_H
+#define PSVI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSVI_MAX_LAYERS 6
+
+#define PSVI_OK 0
+#define PSVI_ERR_INVALID (-1)     /* bad argument / null pointer                       */
+#define PSVI_ERR_UNSUPPORTED (-2) /* shape does not fit this kernel family             */
+#define PSVI_ERR_CUDA (-3)        /* CUDA runtime error (message in psvi_last_error)   */
+
+/* f(v) of the coreset weights a = N * f(v):  psvi_classes.py:111 (identity), :1358-1360 (softmax), :1486-1488. */
+#define PSVI_VMODE_IDENTITY 0
+#define PSVI_VMODE_SOFTMAX 1
+#define PSVI_VMODE_EXPALPHA_SOFTMAX 2
+
+/* inner optimiser arithmetic */
+#define PSVI_ADAM_ROBUST_HIGHER 0 /* psvi/robust_higher/optim.py:303-367 (DifferentiableAdam, +1e-8 and v==0 mask) */
+#define PSVI_ADAM_TORCH 1         /* torch.optim.Adam (baselines.py:1013)                                           */
+#define PSVI_ADAM_HYPERGRAD 2     /* psvi/hypergrad/diff_optimizers.py:184-213 (u += 1e-12, sqrt(u/bc2)+eps)        */
+
+/* noise source */
+#define PSVI_NOISE_EXTERNAL 0 /* caller supplies eps (exact-noise mode, used for parity)                   */
+#define PSVI_NOISE_PHILOX 1   /* in-kernel Philox4x32-10 + Box-Muller keyed by (seed, domain, slab, s, idx) */
+
+/* phases of psvi_mf_nested_step */
+#define PSVI_PHASE_UNROLL 1  /* T differentiable Adam steps on inner_elbo + outer psvi_elbo forward/backward */
+#define PSVI_PHASE_REVERSE 2 /* reverse sweep through the T steps -> hypergradients                            */
+
+typedef struct psvi_mf_model {
+  int32_t n_layers;                   /* L >= 1: number of VILinear layers (1 = logistic_regression)  */
+  int32_t dims[PSVI_MAX_LAYERS + 1];  /* dims[0]=D ... dims[L]=C                                       */
+  int32_t mc_samples;                 /* S (psvi_classes.py:107)                                       */
+} psvi_mf_model;
+
+typedef struct psvi_noise {
+  int32_t mode;          /* PSVI_NOISE_*                                                            */
+  const float* eps;      /* EXTERNAL: [n_slabs][S][P] (TL); ignored for PHILOX                      */
+  uint64_t seed;         /* PHILOX key                                                              */
+  uint32_t domain;       /* PHILOX: stream id (callers bump it per outer step / evaluate call)      */
+} psvi_noise;
+
+/* ---- error string ------------------------------------------------------------------------------------------- */
+const char* psvi_last_error(void);
+/* number of SMs of the current device, or negative error: lets callers check a GPU is really there */
+int psvi_device_sm_count(void);
+
+/* ---- sizes -------------------------------------------------------------------------------------------------- */
+/* P for a model (host arithmetic only). */
+int64_t psvi_mf_num_theta(const psvi_mf_model* model);
+/* bytes of trajectory scratch psvi_mf_nested_step / psvi_mf_unroll need for T steps: T*8*P floats */
+size_t psvi_mf_traj_bytes(const psvi_mf_model* model, int32_t T);
+/* floats in the phase-boundary buffer `gout` (what multi-GPU callers all-reduce between the two phases):
+ * [2P: dLoss/d(mu_T,rho_T)] [M*D: direct dLoss/du] [M: direct dLoss/da] [S: data_nll_s] [4: loss terms] */
+int64_t psvi_mf_gout_floats(const psvi_mf_model* model, int32_t M);
+
+/* ---- the bilevel step: replaces PSVI.nested_step + innerloop_ctx + DifferentiableAdam -----------------------
+ * reference: psvi/inference/psvi_classes.py:541-600 (nested_step), :445-486 (psvi_elbo), :488-511 (inner_elbo);
+ *            psvi/robust_higher/__init__.py:28-95, optim.py:152-257,299-367.
+ * Computes, on device, T unrolled Adam steps on inner_elbo over the pseudo-data (u,z) weighted by a = N f(v), the outer
+ * objective psvi_elbo on (u | xb), and its hypergradient wrt u and v by a hand-written reverse sweep (no autograd).
+ * noise slabs: t = 0..T-1 inner steps, slab T = outer forward.
+ *   mu, rho   [P]  in: phi_0 ; out (after PHASE_UNROLL): phi_T  (the copy-back of psvi_classes.py:596-599)
+ *   u [M][D], z [M] int32, v [M], xb [B][D], yb [B] int32      (B = rows of the minibatch held by THIS rank)
+ *   n_total_rows: B summed over ranks (= the reference's Nx);  pseudo_scale: 1/world_size (1 on a single GPU)
+ *   traj: scratch of psvi_mf_traj_bytes();  gout: psvi_mf_gout_floats() floats
+ *   u_grad [M][D], v_grad [M], alpha_grad [1] (nullable unless vmode 2)   (PHASE_REVERSE outputs)
+ *   loss_out [1]: psvi_elbo value (this rank's share when sharded: shares sum to the loss)
+ *   inner_losses [T] (nullable): inner_elbo value at every inner step (psvi_classes.py:551-554)
+ */
+int psvi_mf_nested_step(const psvi_mf_model* model, const psvi_noise* noise,
+                        float* mu, float* rho,
+                        const float* u, const int32_t* z, const float* v, int32_t M,
+                        const float* xb, const int32_t* yb, int32_t B, int32_t n_total_rows,
+                        float N, int32_t vmode, float alpha,
+                        int32_t T, float lr, float pseudo_scale, int32_t phase_mask,
+                        float* traj, float* gout,
+                        float* u_grad, float* v_grad, float* alpha_grad,
+                        float* loss_out, float* inner_losses, void* stream);
+
+/* ---- plain (non-differentiated) inner optimisation: replaces run_mfvi_subset's training loop and hyper_step's
+ * inner loop.  reference: psvi/inference/baselines.py:1019-1032;  psvi_classes.py:622-654 + hypergrad/diff_optimizers.py
+ * Runs T Adam steps on  sum_s sum_m a_m nll[s,m] + KL  with a_m = row_weights[m] (nullable -> N f(v) from v).
+ *   adam_m, adam_v [2P] in/out moments ([mu part | rho part] in TL), step0 = number of steps already taken.
+ *   losses [T] nullable.  noise slabs t = 0..T-1. */
+int psvi_mf_unroll(const psvi_mf_model* model, const psvi_noise* noise,
+                   float* mu, float* rho, float* adam_m, float* adam_v, int32_t step0,
+                   const float* x, const int32_t* y, const float* row_weights, const float* v, int32_t M,
+                   float N, int32_t vmode, float alpha,
+                   int32_t T, float lr, int32_t adam_mode, float* losses, void* stream);
+
+/* ---- objective values and first/second-order products at a fixed phi (building blocks; also what the hyper trainer
+ * and the parity tests call).
+ * psvi_mf_outer_grad: psvi_elbo value and gradient wrt (mu, rho), u, v.   reference psvi_classes.py:445-486 (+ autograd)
+ *   gout as in psvi_mf_gout_floats(); u_grad/v_grad receive the *direct* partials. noise slab 0. */
+int psvi_mf_outer_grad(const psvi_mf_model* model, const psvi_noise* noise,
+                       const float* mu, const float* rho,
+                       const float* u, const int32_t* z, const float* v, int32_t M,
+                       const float* xb, const int32_t* yb, int32_t B, int32_t n_total_rows,
+                       float N, int32_t vmode, float alpha, float pseudo_scale,
+                       float* gout, float* u_grad, float* v_grad, float* alpha_grad, float* loss_out, void* stream);
+
+/* psvi_mf_inner_grad: inner_elbo value and gradient wrt (mu, rho).        reference psvi_classes.py:488-511 (+ autograd)
+ *   grad [2P] = [d/dmu | d/drho]; value [1]. noise slab 0. */
+int psvi_mf_inner_grad(const psvi_mf_model* model, const psvi_noise* noise,
+                       const float* mu, const float* rho,
+                       const float* u, const int32_t* z, const float* v, int32_t M,
+                       float N, int32_t vmode, float alpha,
+                       float* grad, float* value, void* stream);
+
+/* psvi_mf_inner_hvp: second-order products of inner_elbo along direction gdot [2P]:
+ *   h_phi [2P] = (d2 L / dphi dphi) gdot,  h_u [M][D] = (d2 L / du dphi) gdot,  h_v [M] = (d2 L / dv dphi) gdot.
+ * reference: what torch.autograd's double backward yields inside nested_step (optim.py:224-229) and inside
+ * hypergrad.CG_normaleq / jvp (psvi/hypergrad/hypergradients.py:199-244,308-311). noise slab 0. */
+int psvi_mf_inner_hvp(const psvi_mf_model* model, const psvi_noise* noise,
+                      const float* mu, const float* rho,
+                      const float* u, const int32_t* z, const float* v, int32_t M,
+                      float N, int32_t vmode, float alpha,
+                      const float* gdot, float* h_phi, float* h_u, float* h_v, float* h_alpha, void* stream);
+
+/* ---- predictive pass: replaces PSVI.evaluate (importance-weighted, psvi_classes.py:1031-1108) and the test loop of
+ * run_mfvi_subset (mean-of-logits, baselines.py:1035-1043).
+ *   xt [n_rows][D], yt [n_rows] int32: the rows held by THIS rank; batch = data_minibatch (rows per noise slab);
+ *   first_slab: global index of this rank's first batch (so a sharded pass consumes the same slabs as one rank would).
+ *   mode 0: importance-weighted (correction=True), 1: plain mean over samples of softmax (correction=False),
+ *        2: softmax of mean logits (mfvi baselines; u/z/v ignored).
+ *   out [8] (accumulated into with atomics-free two-stage reduction; caller zeroes it):
+ *        [0] sum nll, [1] #correct, [2] #rows, [3] IW entropy (last slab), [4] normalised ESS (last slab), [5..7] spare
+ *   scratch: psvi_mf_eval_scratch_bytes() bytes. */
+size_t psvi_mf_eval_scratch_bytes(const psvi_mf_model* model, int32_t n_rows, int32_t batch);
+int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise,
+                     const float* mu, const float* rho,
+                     const float* u, const int32_t* z, const float* v, int32_t M,
+                     const float* xt, const int32_t* yt, int32_t n_rows, int32_t batch, int32_t first_slab,
+                     float N, int32_t vmode, float alpha, int32_t mode,
+                     float* out, void* scratch, void* stream);
+
+/* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
+ * call consumes.  out [n_slabs][S][P]. */
+int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSVI_B200_H */
