@@ -38,7 +38,8 @@ enum : int {
   F_STORE_GOUT = 32,  // write the phase-boundary buffer (outer gradient wrt phi_T, direct u/a partials, d_s, loss)
   F_LOAD_GOUT = 64,   // start the reverse sweep from the phase-boundary buffer
   F_FINAL = 128,      // reduce ubar/abar over the cluster and write u_grad / v_grad
-  F_WRITE_PHI = 256   // write phi (and Adam moments if given) back after F_UNROLL
+  F_WRITE_PHI = 256,  // write phi (and Adam moments if given) back after F_UNROLL
+  F_EVAL = 512        // predictive kernels: forward only, lean shared-memory carve-up
 };
 
 struct EP {
@@ -135,14 +136,18 @@ __host__ __device__ inline void make_layout(const EP& p, const Meta& m, Lay& y) 
     return r;
   };
   const int Pp = m.Pp;
-  y.mu = take(Pp); y.rho = take(Pp); y.sig = take(Pp); y.sgm = take(Pp); y.gmu = take(Pp); y.grho = take(Pp);
-  y.theta = take(Pp); y.thetad = take(Pp); y.eps = take(Pp); y.acc1 = take(Pp); y.acc2 = take(Pp); y.acc3 = take(Pp);
+  const bool ev = (p.flags & F_EVAL) != 0;  // forward-only kernels do not need adjoint / owner storage
+  y.mu = take(Pp); y.rho = take(Pp); y.sig = take(Pp); y.sgm = take(Pp);
+  y.gmu = take(ev ? 0 : Pp); y.grho = take(ev ? 0 : Pp);
+  y.theta = take(Pp); y.thetad = take(ev ? 0 : Pp); y.eps = take(Pp);
+  y.acc1 = take(ev ? 0 : Pp); y.acc2 = take(ev ? 0 : Pp); y.acc3 = take(ev ? 0 : Pp);
   y.tl_of_pad = take(Pp); y.pad_of_tl = take(m.Pt);
-  y.recv = take(p.G * 3 * p.slice);
-  y.ost = take(10 * p.slice);
-  y.a = take(p.M); y.f = take(p.M); y.ubar = take(p.M * p.dims[0]); y.abar = take(p.M);
+  y.recv = take(ev ? 0 : p.G * 3 * p.slice);
+  y.ost = take(ev ? 0 : 10 * p.slice);
+  y.a = take(p.M); y.f = take(p.M); y.ubar = take(ev ? 0 : p.M * p.dims[0]); y.abar = take(ev ? 0 : p.M);
   y.su = take(p.M * m.lda[0]); y.sz = take(p.M);
-  y.lw = take(2 * p.S); y.e = take(2 * p.S); y.dsv = take(p.S);  // lw, e hold doubles y.w = take(p.S); y.beta = take(p.S); y.gp = take(p.S);
+  // lw, e hold doubles
+  y.lw = take(2 * p.S); y.e = take(2 * p.S); y.dsv = take(p.S); y.w = take(p.S); y.beta = take(p.S); y.gp = take(p.S);
   y.red = take(64); y.lossrecv = take(p.G);
   y.lab = take(p.RC); y.cw = take(p.RC); y.nll = take(p.RC);
   for (int l = 0; l <= p.L; ++l) {
@@ -797,7 +802,12 @@ __device__ void Engine::run() {
           go[S] = lossv;
           go[S + 1] = (float)ebar;
           go[S + 2] = (float)lwm;
-          go[S + 3] = 0.f;
+          go[S + 3] = (float)bsum;
+          for (int s = 0; s < S; ++s) {  // diagnostics (rank-local, not meant to be all-reduced)
+            go[S + 4 + s] = F(ly.w)[s];
+            go[2 * S + 4 + s] = F(ly.beta)[s];
+            go[3 * S + 4 + s] = F(ly.gp)[s];
+          }
         }
       }
     }
@@ -1297,7 +1307,7 @@ size_t psvi_mf_traj_bytes(const psvi_mf_model* model, int32_t T) {
 int64_t psvi_mf_gout_floats(const psvi_mf_model* model, int32_t M) {
   const int64_t P = psvi_mf_num_theta(model);
   if (P < 0 || M < 0) return PSVI_ERR_INVALID;
-  return 2 * P + (int64_t)M * model->dims[0] + M + model->mc_samples + 4;
+  return 2 * P + (int64_t)M * model->dims[0] + M + 4 * (int64_t)model->mc_samples + 4;
 }
 
 int psvi_mf_nested_step(const psvi_mf_model* model, const psvi_noise* noise, float* mu, float* rho, const float* u,
@@ -1449,7 +1459,7 @@ int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise, const 
   p.eval_w = (float*)scratch;
   p.eval_part = p.eval_w + (size_t)p.n_slabs * p.S;
   p.eval_out = out;
-  p.G = 1; p.flags = 0;
+  p.G = 1; p.flags = F_EVAL;
   int dev = 0, smem_max = 0;
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

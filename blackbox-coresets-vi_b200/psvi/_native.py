@@ -123,6 +123,7 @@ def make_noise(eps=None, seed=0, domain=0):
     if eps is not None:
         _chk(eps, torch.float32)
         n.mode, n.eps = NOISE_EXTERNAL, eps.data_ptr()
+        n._keepalive = eps  # the struct only carries the raw pointer: pin the tensor's lifetime to it
     else:
         n.mode, n.eps = NOISE_PHILOX, None
     n.seed, n.domain = int(seed) & (2**64 - 1), int(domain) & 0xFFFFFFFF

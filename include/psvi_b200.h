@@ -76,7 +76,8 @@ int64_t psvi_mf_num_theta(const psvi_mf_model* model);
 /* bytes of trajectory scratch psvi_mf_nested_step / psvi_mf_unroll need for T steps: T*8*P floats */
 size_t psvi_mf_traj_bytes(const psvi_mf_model* model, int32_t T);
 /* floats in the phase-boundary buffer `gout` (what multi-GPU callers all-reduce between the two phases):
- * [2P: dLoss/d(mu_T,rho_T)] [M*D: direct dLoss/du] [M: direct dLoss/da] [S: data_nll_s] [4: loss terms] */
+ * [2P: dLoss/d(mu_T,rho_T)] [M*D: direct dLoss/du] [M: direct dLoss/da] [S: data_nll_s] [4: loss, sum_s w_s e_s,
+ * mean_s lw_s, sum_s beta_s] -- the all-reduced part ends here -- [S: w_s] [S: beta_s] [S: dLoss/dp_s] (diagnostics) */
 int64_t psvi_mf_gout_floats(const psvi_mf_model* model, int32_t M);
 
 /* ---- the bilevel step: replaces PSVI.nested_step + innerloop_ctx + DifferentiableAdam -----------------------

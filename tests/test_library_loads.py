@@ -34,7 +34,7 @@ def test_size_queries_match_oracle(nat):
         m = nat.make_model(dims, 10)
         assert nat.num_theta(m) == po.p_theta(dims)
         assert nat.traj_floats(m, 7) == 7 * 8 * po.p_theta(dims)
-        assert nat.gout_floats(m, 13) == 2 * po.p_theta(dims) + 13 * dims[0] + 13 + 10 + 4
+        assert nat.gout_floats(m, 13) == 2 * po.p_theta(dims) + 13 * dims[0] + 13 + 4 * 10 + 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
