@@ -84,6 +84,8 @@ struct EP {
   float* eval_w;     // [n_slabs][S] importance weights
   float* eval_part;  // [n_ctas][4] per-CTA partial sums
   float* eval_out;   // [8]
+  // plain forward
+  float* logits_out; float* theta_out; float* nkl_out; float* kl_out;
 };
 
 struct Meta {
@@ -562,6 +564,7 @@ struct Engine {
   __device__ void run();
   __device__ void eval_weights();
   __device__ void eval_rows();
+  __device__ void forward_rows();
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1106,6 +1109,47 @@ __device__ void Engine::eval_rows() {
   }
 }
 
+// Plain sampled forward (module-level API: VILinear / nn.Sequential forward, neural_net.py:155-179): one CTA per
+// (sample, row chunk); also exports the sampled weights, sampled_nkl and the analytic KL.
+__device__ void Engine::forward_rows() {
+  init();
+  const int s = blockIdx.x / p.chunks_per_slab, chunk = blockIdx.x - s * p.chunks_per_slab;
+  const int row_begin = chunk * p.RC;
+  const int nr = min(p.RC, p.n_rows - row_begin);
+  const int C = p.dims[p.L], ld = mt.lda[p.L];
+  float nkl = sample_theta(s, 0, false, 0.f);
+  if (chunk == 0) {
+    if (p.nkl_out) {
+      nkl = block_sum(nkl, F(ly.red));
+      if (tid == 0) p.nkl_out[s] = nkl;
+    }
+    if (p.theta_out) {
+      const int* pot = I(ly.pad_of_tl);
+      for (int q = tid; q < mt.Pt; q += NT) p.theta_out[(size_t)s * mt.Pt + q] = F(ly.theta)[pot[q]];
+    }
+    if (p.kl_out && s == 0) {
+      const int* top = I(ly.tl_of_pad);
+      float kl = 0.f;
+      for (int pp = tid; pp < mt.Pp; pp += NT)
+        if (top[pp] >= 0) {
+          const float sg = F(ly.sig)[pp], m = F(ly.mu)[pp];
+          kl += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
+        }
+      kl = block_sum(kl, F(ly.red));
+      if (tid == 0) p.kl_out[0] = kl;
+    }
+  }
+  if (nr <= 0) return;
+  const float* a0 = stage_rows(p.M + row_begin, nr);
+  __syncthreads();
+  forward(a0, nr, false);
+  const float* o = F(ly.act[p.L]);
+  for (int i = tid; i < nr * C; i += NT) {
+    const int rr = i / C, c = i - rr * C;
+    p.logits_out[((size_t)s * p.n_rows + row_begin + rr) * C + c] = o[rr * ld + c];
+  }
+}
+
 __global__ void __launch_bounds__(NT, 1) psvi_mf_engine_kernel(const __grid_constant__ EP p) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ Meta mt;
@@ -1146,6 +1190,20 @@ __global__ void __launch_bounds__(NT, 1) psvi_mf_eval_rows_kernel(const __grid_c
   Engine e(p, mt, ly, smem_dyn);
   e.rank = 0;
   e.eval_rows();
+}
+
+__global__ void __launch_bounds__(NT, 1) psvi_mf_forward_kernel(const __grid_constant__ EP p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ Meta mt;
+  __shared__ Lay ly;
+  if (threadIdx.x == 0) {
+    make_meta(p.dims, p.L, mt);
+    make_layout(p, mt, ly);
+  }
+  __syncthreads();
+  Engine e(p, mt, ly, smem_dyn);
+  e.rank = 0;
+  e.forward_rows();
 }
 
 // fixed-order final reduction of the per-CTA partials (deterministic, no atomics)
@@ -1493,6 +1551,48 @@ int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise, const 
   psvi_mf_eval_rows_kernel<<<nctas, NT, smem, stream>>>(p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   psvi_mf_eval_reduce_kernel<<<1, NT, 0, stream>>>(p.eval_part, nctas, out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_mf_forward(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                    const float* x, int32_t n_rows, float* logits, float* theta_out, float* nkl_out, float* kl_out,
+                    void* stream_) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  PSVI_REQUIRE(mu && rho && x && logits && n_rows > 0, PSVI_ERR_INVALID, "null pointer or n_rows<=0");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EP p;
+  fill_common(p, model, noise, 0, 0.f, 0, 0.f);
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.xb = x; p.n_rows = n_rows;
+  p.logits_out = logits; p.theta_out = theta_out; p.nkl_out = nkl_out; p.kl_out = kl_out;
+  p.G = 1; p.flags = F_EVAL;
+  int dev = 0, smem_max = 0;
+  PSVI_CUDA_CHECK(cudaGetDevice(&dev));
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  Meta mt;
+  make_meta(p.dims, p.L, mt);
+  p.slice = mt.Pp;
+  const size_t budget = (size_t)smem_max - 2048;
+  Lay ly;
+  const int want = n_rows < 128 ? n_rows : 128;
+  int lo = 0, hi = want;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    p.RC = mid;
+    make_layout(p, mt, ly);
+    if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+  }
+  PSVI_REQUIRE(lo >= 1, PSVI_ERR_UNSUPPORTED, "model too large for the shared-memory-resident forward kernel");
+  p.RC = lo;
+  make_layout(p, mt, ly);
+  const size_t smem = (size_t)ly.total * 4;
+  p.chunks_per_slab = (n_rows + p.RC - 1) / p.RC;
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psvi_mf_forward_kernel<<<p.S * p.chunks_per_slab, NT, smem, stream>>>(p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

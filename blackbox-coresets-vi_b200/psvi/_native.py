@@ -63,6 +63,8 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
+    "psvi_mf_forward": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -207,3 +209,8 @@ def evaluate(model, noise, mu, rho, u, z, v, xt, yt, batch, first_slab, N, vmode
 def philox_normal(seed, domain, first_slab, n_slabs, S, P, out):
     _check(lib().psvi_philox_normal(int(seed) & (2**64 - 1), int(domain) & 0xFFFFFFFF, first_slab, n_slabs, S, P,
                                     _p(out), _stream()))
+
+
+def forward(model, noise, mu, rho, x, logits, theta_out=None, nkl_out=None, kl_out=None):
+    _check(lib().psvi_mf_forward(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x), x.shape[0], _p(logits),
+                                 _p(theta_out), _p(nkl_out), _p(kl_out), _stream()))

@@ -1,0 +1,160 @@
+"""Mean-field VI baselines of the BNN flows on the B200 path: run_mfvi_subset (reference psvi/inference/baselines.py
+:923-1062) and run_mfvi (:824-920).  Same keyword surface and results dict; training runs through psvi_mf_unroll
+(fused sampled forward + backward + torch.optim.Adam arithmetic, Adam moments resident on the device) and the test
+loop through psvi_mf_evaluate in its mean-of-logits mode.  The remaining functions of the reference file (Laplace /
+GIGA / SparseVI / OPSVI logistic-regression coresets, k-means / EL2N selection, regression MFVI) are different
+algorithms on CPU tensors and out of scope."""
+from __future__ import annotations
+
+import random
+import time
+from typing import Any, Dict
+
+import numpy as np
+import torch
+
+from psvi import _native
+from psvi.experiments.experiments_utils import set_up_model
+from psvi.inference.utils import pseudo_rand_init, pseudo_subsample_init
+from psvi.models.neural_net import MeanFieldMLP, categorical_fn
+
+
+def _not_built(name, where):
+    def f(*a, **k):
+        raise NotImplementedError(f"{name} ({where}) is outside the PSVI hot-path scope (SURVEY.md section 2 row 5b)")
+    f.__name__ = name
+    return f
+
+
+run_random = _not_built("run_random", "baselines.py:35")
+run_giga = _not_built("run_giga", "baselines.py:178")
+run_sparsevi = _not_built("run_sparsevi", "baselines.py:330")
+run_opsvi = _not_built("run_opsvi", "baselines.py:560")
+run_mfvi_regressor = _not_built("run_mfvi_regressor", "baselines.py:1066")
+run_mfvi_subset_regressor = _not_built("run_mfvi_subset_regressor", "baselines.py:1200")
+
+
+class _Trainer:
+    """Device-resident state of one mean-field VI fit."""
+
+    def __init__(self, net, seed, noise_source=None):
+        if not isinstance(net, MeanFieldMLP):
+            raise NotImplementedError("the CUDA path covers mean-field MLPs (logistic_regression, fn)")
+        _native.require_cuda()
+        net.check_supported()
+        self.net, self.seed, self.noise_source, self.domain = net, seed, noise_source, 0
+        self.device = next(net.parameters()).device
+        self.desc = _native.make_model(net.dims, net.n_samples())
+        self.mu, self.rho = net.flat()
+        P = self.mu.numel()
+        self.am, self.av = torch.zeros(2 * P, device=self.device), torch.zeros(2 * P, device=self.device)
+        self.steps = 0
+        self._scratch = None
+
+    def noise(self, n):
+        if self.noise_source is not None:
+            return _native.make_noise(self.noise_source.take(n, self.device))
+        self.domain += 1
+        return _native.make_noise(None, seed=self.seed, domain=self.domain)
+
+    def train(self, x, y32, scale, T, lr):
+        """T Adam steps on  -scale * sum_{s,m} log p + sum KL  (baselines.py:1023-1030); returns the T losses."""
+        losses = torch.zeros(T, device=self.device)
+        roww = torch.full((x.shape[0],), float(scale), device=self.device)
+        _native.unroll(self.desc, self.noise(T), self.mu, self.rho, self.am, self.av, self.steps, x, y32, roww, None,
+                       1.0, 0, 0.0, T, lr, _native.ADAM_TORCH, losses)
+        self.steps += T
+        return losses
+
+    def test(self, xt, yt32, batch):
+        """(acc, nll) with test_logits = net(xt).mean(0) per batch (baselines.py:1035-1043)."""
+        n = xt.shape[0]
+        need = _native.eval_scratch_floats(self.desc, n, batch)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.zeros(need, device=self.device)
+        out = torch.zeros(8, device=self.device)
+        _native.evaluate(self.desc, self.noise(-(-n // batch)), self.mu, self.rho, None, None, None, xt, yt32, batch, 0,
+                         1.0, 0, 0.0, 2, out, self._scratch)
+        o = out.cpu()
+        return (o[1] / o[2]).item(), (o[0] / o[2]).item()
+
+
+def run_mfvi_subset(x=None, y=None, xt=None, yt=None, mc_samples=4, data_minibatch=128, num_epochs=100, log_every=10,
+                    D=None, lr0net=1e-3, mul_fact=2, seed=0, distr_fn=categorical_fn, log_pseudodata=False,
+                    train_dataset=None, test_dataset=None, num_pseudo=100, init_args="subsample", architecture=None,
+                    n_hidden=None, nc=2, dnm=None, init_sd=None, noise_source=None, **kwargs) -> Dict[str, Any]:
+    """Mean-field VI on a random class-balanced subset (reference baselines.py:923-1062)."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
+    nlls, accs, times, elbos = [], [], [0], []
+    t_start = time.time()
+    net = set_up_model(architecture=architecture, D=D, n_hidden=n_hidden, nc=nc, mc_samples=mc_samples,
+                       init_sd=init_sd).to(device)
+    if dnm == "MNIST":
+        raise NotImplementedError("vision datasets are out of scope (no network; SURVEY.md section 2 row 9)")
+    xbatch, ybatch = (pseudo_rand_init(x, y, num_pseudo=num_pseudo, seed=seed, nc=nc) if init_args == "random"
+                      else pseudo_subsample_init(x, y, num_pseudo=num_pseudo, seed=seed, nc=nc))
+    n_train = len(train_dataset)
+    tr = _Trainer(net, seed, noise_source)
+    xs = xbatch.detach().to(device, torch.float32).contiguous()
+    ys = ybatch.detach().to(device).to(torch.int32).contiguous()
+    xtd = torch.as_tensor(test_dataset.data).to(device, torch.float32).reshape(len(test_dataset), -1).contiguous()
+    ytd = torch.as_tensor(test_dataset.targets).to(device).to(torch.int32).contiguous()
+    sum_scaling = n_train / num_pseudo
+    total = mul_fact * num_epochs
+    i = 0
+    while i < total:
+        # iterations up to and including the next evaluation point (evaluations happen after steps 0, k, 2k, ...)
+        nxt = i if i % log_every == 0 else min(((i // log_every) + 1) * log_every, total - 1)
+        T = nxt - i + 1
+        losses = tr.train(xs, ys, sum_scaling, T, lr0net)
+        elbos += [-v for v in losses.cpu().tolist()]
+        i += T
+        if (i - 1) % log_every == 0:
+            acc, nll = tr.test(xtd, ytd, int(data_minibatch))
+            times.append(times[-1] + time.time() - t_start)
+            nlls.append(nll)
+            accs.append(acc)
+            if not kwargs.get("quiet", False):
+                print(f"predictive accuracy: {(100*accs[-1]):.2f}%")
+    results = {"accs": accs, "nlls": nlls, "times": times[1:], "elbos": elbos, "csizes": [num_pseudo] * total}
+    if log_pseudodata:
+        results["us"], results["zs"], results["vs"] = xbatch.detach(), ybatch.detach(), [sum_scaling] * num_pseudo
+        results["grid_preds"] = []
+    return results
+
+
+def run_mfvi(xt=None, yt=None, mc_samples=4, data_minibatch=128, num_epochs=100, log_every=10, N=None, D=None,
+             lr0net=1e-3, mul_fact=2, seed=0, distr_fn=categorical_fn, architecture=None, n_hidden=None, nc=2,
+             log_pseudodata=False, train_dataset=None, test_dataset=None, init_sd=None, noise_source=None,
+             **kwargs) -> Dict[str, Any]:
+    """Mean-field VI on the full training set with random minibatches (reference baselines.py:824-920)."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
+    nlls, accs, times, elbos = [], [], [0], []
+    t_start = time.time()
+    net = set_up_model(architecture=architecture, D=D, n_hidden=n_hidden, nc=nc, mc_samples=mc_samples,
+                       init_sd=init_sd).to(device)
+    tr = _Trainer(net, seed, noise_source)
+    xd = torch.as_tensor(train_dataset.data).to(device, torch.float32).reshape(len(train_dataset), -1).contiguous()
+    yd = torch.as_tensor(train_dataset.targets).to(device).to(torch.int32).contiguous()
+    xtd = torch.as_tensor(test_dataset.data).to(device, torch.float32).reshape(len(test_dataset), -1).contiguous()
+    ytd = torch.as_tensor(test_dataset.targets).to(device).to(torch.int32).contiguous()
+    n_train = xd.shape[0]
+    total = mul_fact * num_epochs
+    for i in range(total):
+        idx = torch.randperm(n_train)[: min(int(data_minibatch), n_train)].to(device)
+        xb, yb = xd[idx].contiguous(), yd[idx].contiguous()
+        losses = tr.train(xb, yb, n_train / xb.shape[0], 1, lr0net)
+        elbos.append(-losses.item())
+        if i % log_every == 0 or i == total - 1:
+            acc, nll = tr.test(xtd, ytd, int(data_minibatch))
+            times.append(times[-1] + time.time() - t_start)
+            nlls.append(nll)
+            accs.append(acc)
+            if not kwargs.get("quiet", False):
+                print(f"predictive accuracy: {(100*accs[-1]):.2f}%")
+    results = {"accs": accs, "nlls": nlls, "times": times[1:], "elbos": elbos, "csizes": None}
+    if log_pseudodata:
+        results["grid_preds"] = []
+    return results

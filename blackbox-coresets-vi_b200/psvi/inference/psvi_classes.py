@@ -1,0 +1,551 @@
+"""Black-box PSVI on the B200: same class / method names and argument surface as the reference's
+psvi/inference/psvi_classes.py, with the objectives, their gradients, the unrolled inner loop and its reverse-mode
+hypergradient executed by hand-written CUDA (libpsvi_b200) instead of autograd + `higher`.
+
+Reference map (psvi/inference/psvi_classes.py):
+  PSVI.__init__ :89-227        pseudo_subsample_init :229-285   pseudo_rand_init :287-308
+  psvi_elbo :445-486           inner_elbo :488-511              nested_step :541-600      hyper_step :602-687
+  set_up_model :689-758        run_psvi :761-1028               evaluate :1031-1108       weight_reset :1110-1128
+  PSVILearnV :1344-1360        PSVI_No_Rescaling :1363          PSVIFreeV :1376           PSVIAV :1475-1619
+  PSVIFixedU :1622             PSVIAFixedU :1743
+Deviations, all deliberate and listed in DESIGN.md: model noise comes from an in-kernel Philox stream (or an injected
+exact-noise source for parity tests) instead of the CUDA generator; minibatches are gathered on the device from a
+device-resident copy of the dataset; when torch.distributed is initialised the data term and the test set are sharded
+over the ranks with a single all-reduce per outer step / per evaluate.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.utils.data import DataLoader, Dataset
+from tqdm import tqdm
+
+from psvi import _native
+from psvi.inference.utils import LogResource, compute_empirical_mean
+from psvi.models.neural_net import (MeanFieldMLP, VILinear, VILinearMultivariateNormal, categorical_fn, make_fc2net,
+                                    make_fcnet, make_lenet, make_logistic_regression, set_mc_samples)
+
+
+class SubsetPreservingTransforms(Dataset):
+    """Subset of a tensor dataset at given indices (reference :51-80; the image branch needs torchvision datasets,
+    which are out of scope here)."""
+
+    def __init__(self, dataset, indices=None, dim=2, dnm="Cifar10"):
+        self.dataset, self.indices, self.dnm, self.dim = dataset, indices, dnm, dim
+
+    def __getitem__(self, idx):
+        if self.dnm in {"MNIST", "FashionMNIST", "Cifar10"}:
+            raise NotImplementedError("vision datasets are out of scope (no network; SURVEY.md section 2 row 9)")
+        return self.dataset.data[self.indices[idx]].reshape((self.dim,))
+
+    def __len__(self):
+        return len(self.indices)
+
+
+class ExternalNoise:
+    """Exact-noise source for parity tests: hands out pre-drawn standard-normal slabs [n, S, P] in consumption order."""
+
+    def __init__(self, slabs):
+        self.slabs, self.pos = slabs, 0
+
+    def take(self, n, device):
+        out = self.slabs[self.pos:self.pos + n]
+        assert len(out) == n, "external noise exhausted"
+        self.pos += n
+        return torch.as_tensor(np.stack(out)).to(device=device, dtype=torch.float32).contiguous()
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous split of n items over `world` ranks (first ranks get the remainder)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PSVI(object):
+    r"""PSVI with fixed rescaled coefficients on pseudodata (reference class PSVI)."""
+
+    _vmode = _native.VMODE_IDENTITY
+
+    def __init__(
+        self, u=None, z=None, train_dataset=None, test_dataset=None, N=None, D=None, model=None, optim=None,
+        optim_u=None, optim_net=None, optim_v=None, optim_z=None, register_elbos=True, num_pseudo=None, seed=0,
+        compute_weights_entropy=True, mc_samples=None, reset=False, reset_interval=10, learn_v=False,
+        f=lambda *x: x[0], distr_fn=categorical_fn, dnm="MNIST", nc=10, init_dataset=None, parameterised=False,
+        learn_z=False, prune=False, prune_interval=None, prune_sizes=None, increment=False, increment_interval=None,
+        increment_sizes=None, lr0alpha=1e-3, retrain_on_coreset=False, device_id=None, data_folder=None,
+        results_folder=None, mfvi_selection_method="random", load_from_saved=False, pretrain_epochs=5, lr0net=1e-3,
+        multiple_pts_per_cluster=True, loaded_from_psvi=True, alpha_dirichlet=0, choose_difficult=True,
+        scoring_run=False, noise_source=None, **kwargs,
+    ):
+        np.random.seed(seed), torch.manual_seed(seed)
+        self.device = torch.device(f"cuda:{device_id}" if device_id else ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.u, self.z = u, z
+        self.train_dataset, self.test_dataset = train_dataset, test_dataset
+        self.N, self.D, self.dnm, self.nc = N, D, dnm, nc
+        self.distr_fn = distr_fn
+        self.model, self.optim, self.optim_u, self.optim_net, self.optim_v, self.optim_z = (
+            model, optim, optim_u, optim_net, optim_v, optim_z)
+        self.register_elbos, self.compute_weights_entropy = register_elbos, compute_weights_entropy
+        self.elbos = []
+        self.num_pseudo, self.mc_samples = (num_pseudo if not increment else increment_sizes[0]), mc_samples
+        self.reset, self.reset_interval, self.learn_v, self.learn_z = reset, reset_interval, learn_v, learn_z
+        for flag, name in ((learn_z, "learn_z"), (prune, "prune"), (increment, "increment"),
+                           (retrain_on_coreset, "retrain_on_coreset"), (scoring_run, "scoring_run")):
+            if flag:
+                raise NotImplementedError(f"{name}=True is outside the hot path built so far (SURVEY.md section 8f)")
+        with torch.no_grad():
+            self.v = 1.0 / self.num_pseudo * torch.ones(self.num_pseudo, device=self.device)
+        self.v.requires_grad_(self.learn_v)
+        self.f, self.parameterised = f, parameterised
+        self.init_dataset = init_dataset
+        self.results = {}
+        self.prune, self.increment, self.retrain_on_coreset = prune, increment, retrain_on_coreset
+        self.lr0alpha, self.lr0net = lr0alpha, lr0net
+        self.data_folder, self.results_folder = data_folder, results_folder
+        self.chosen_indices = []
+        self.seed = seed
+        self.alpha = None
+        self.noise_source = noise_source
+        self._noise_domain = 0
+        self._ws = {}
+        self._dev_data = {}
+
+    # ------------------------------------------------------------------------------------------------ noise
+    def _noise(self, n_slabs):
+        if self.noise_source is not None:
+            return _native.make_noise(self.noise_source.take(n_slabs, self.device))
+        self._noise_domain += 1
+        return _native.make_noise(None, seed=self.seed, domain=self._noise_domain)
+
+    # ------------------------------------------------------------------------------------------------ pseudo-data init
+    def pseudo_subsample_init(self):
+        """Class-balanced random subset of the training data (reference :229-285, same loader-driven RNG use)."""
+        chosen = self.train_dataset if self.init_dataset is None else self.init_dataset
+        ppc = [self.num_pseudo // self.nc] * self.nc
+        ppc[-1] = self.num_pseudo - sum(ppc[:-1])
+        with torch.no_grad():
+            self.z = torch.tensor([c for c, k in enumerate(ppc) for _ in range(k)]).float().to(self.device)
+        lst = []
+        for c in range(self.nc):
+            idx = (torch.as_tensor(chosen.targets).clone().detach() == c).nonzero()
+            loader = DataLoader(SubsetPreservingTransforms(chosen, indices=idx, dnm=self.dnm, dim=self.D),
+                                batch_size=ppc[c], shuffle=True)
+            lst.append(next(iter(loader)).to(device=self.device))
+        self.u = torch.cat(lst).float().requires_grad_(True)
+
+    def pseudo_rand_init(self, variance=1.0):
+        """Noisy empirical mean + labels split equally among classes (reference :287-308)."""
+        self.u = ((compute_empirical_mean(self.train_loader) + variance * torch.randn(self.num_pseudo, self.D))
+                  .clone()).to(self.device).float().requires_grad_(True)
+        z = [c * torch.ones(self.num_pseudo // self.nc if c < self.nc - 1
+                            else self.num_pseudo - (self.nc - 1) * (self.num_pseudo // self.nc)) for c in range(self.nc)]
+        self.z = torch.cat(z).to(self.device)
+
+    # ------------------------------------------------------------------------------------------------ native plumbing
+    def _model_desc(self, model=None):
+        model = self.model if model is None else model
+        if not isinstance(model, MeanFieldMLP):
+            raise NotImplementedError("the CUDA path covers mean-field MLPs (logistic_regression, fn); got "
+                                      f"{type(model).__name__}")
+        model.check_supported()
+        S = model.n_samples()
+        return model, _native.make_model(model.dims, S), S
+
+    def _buf(self, name, n):
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.device != self.device:
+            t = torch.zeros(max(int(n), 1), device=self.device, dtype=torch.float32)
+            self._ws[name] = t
+        return t
+
+    def _z32(self):
+        return self.z.detach().to(torch.int32).contiguous()
+
+    def _alpha_value(self):
+        return float(self.alpha.item()) if self.alpha is not None else 0.0
+
+    def _uv(self):
+        return (self.u.detach().float().contiguous(), self.v.detach().float().contiguous())
+
+    # ------------------------------------------------------------------------------------------------ objectives
+    def psvi_elbo(self, xbatch, ybatch, model=None, params=None, hyperopt=False):
+        """Negative PSVI-ELBO (reference :445-486).  Returns a 0-dim tensor; its gradients wrt the variational
+        parameters, u and v are left in `self._last_outer` (the fused kernel produces them in the same pass)."""
+        assert self.mc_samples > 1
+        model, desc, S = self._model_desc(model)
+        mu, rho = model.flat()
+        u, v = self._uv()
+        M, D = u.shape
+        P = mu.numel()
+        gout = self._buf("gout", _native.gout_floats(desc, M))
+        ug, vg, ag, loss = torch.zeros(M, D, device=self.device), torch.zeros(M, device=self.device), \
+            torch.zeros(1, device=self.device), torch.zeros(1, device=self.device)
+        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
+        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        _native.outer_grad(desc, self._noise(1), mu, rho, u, self._z32(), v, xb, yb, xb.shape[0], float(self.N),
+                           self._vmode, self._alpha_value(), 1.0, gout, ug, vg, ag, loss)
+        self._last_outer = dict(phi_grad=gout[:2 * P].clone(), u_grad=ug, v_grad=vg, alpha_grad=ag)
+        return loss[0]
+
+    def inner_elbo(self, model=None, params=None, hyperopt=False):
+        """Negative ELBO on the pseudo-data (reference :488-511).  Gradient wrt (mu, rho) in `self._last_inner`."""
+        model, desc, S = self._model_desc(model)
+        mu, rho = model.flat()
+        u, v = self._uv()
+        grad, val = torch.zeros(2 * mu.numel(), device=self.device), torch.zeros(1, device=self.device)
+        _native.inner_grad(desc, self._noise(1), mu, rho, u, self._z32(), v, float(self.N), self._vmode,
+                           self._alpha_value(), grad, val)
+        self._last_inner = grad
+        return val[0]
+
+    # ------------------------------------------------------------------------------------------------ optimisation
+    def _zero_grads(self):
+        for o in (self.optim_u, self.optim_net, self.optim_v if self.learn_v else None, getattr(self, "optim_alpha", None)):
+            if o is not None:
+                o.zero_grad()
+
+    def nested_step(self, xbatch, ybatch, truncated=False, K=5):
+        """One bilevel step (reference :541-600): T differentiable Adam steps on inner_elbo, psvi_elbo, hypergradient on
+        (u, v[, alpha]) -- one fused CUDA launch (two around an all-reduce when sharded) -- then the Adam steps on u, v."""
+        if truncated:
+            raise NotImplementedError("truncated=True is never taken by run_psvi (SURVEY.md section 8a, a8)")
+        self._zero_grads()
+        model, desc, S = self._model_desc()
+        mu, rho = model.flat()
+        u, v = self._uv()
+        M, D = u.shape
+        P, T = mu.numel(), int(self.inner_it)
+        lr = float(self.optim_net.param_groups[0]["lr"])
+        traj = self._buf("traj", _native.traj_floats(desc, T))
+        gout = self._buf("gout", _native.gout_floats(desc, M))
+        ug, vg = torch.zeros(M, D, device=self.device), torch.zeros(M, device=self.device)
+        ag, loss = torch.zeros(1, device=self.device), torch.zeros(1, device=self.device)
+        il = self._buf("il", T) if self.register_elbos else None
+        xb = xbatch.detach().to(self.device, torch.float32)
+        yb = ybatch.detach().to(self.device).to(torch.int32)
+        dist, rank, world = _dist_info()
+        n_total = xb.shape[0]
+        noise = self._noise(T + 1)
+        args = lambda xs, ys, kappa: (desc, noise, mu, rho, u, self._z32(), v, xs, ys, n_total, float(self.N),  # noqa: E731
+                                      self._vmode, self._alpha_value(), T, lr, kappa)
+        if world == 1:
+            _native.nested_step(*args(xb.contiguous(), yb.contiguous(), 1.0),
+                                _native.PHASE_UNROLL | _native.PHASE_REVERSE, traj, None, ug, vg, ag, loss, il)
+        else:
+            lo, hi = shard_bounds(n_total, rank, world)
+            xs, ys = xb[lo:hi].contiguous(), yb[lo:hi].contiguous()
+            a = args(xs if hi > lo else None, ys if hi > lo else None, 1.0 / world)
+            _native.nested_step(*a, _native.PHASE_UNROLL, traj, gout, ug, vg, ag, loss, il)
+            n_red = 2 * P + M * D + M + S + 4      # [dL/dphi_T | direct du | direct da | d_s | loss terms]
+            dist.all_reduce(gout[:n_red])           # the ONE collective of the step (NCCL over NVLink)
+            loss = gout[2 * P + M * D + M + S:2 * P + M * D + M + S + 1].clone()
+            _native.nested_step(*a, _native.PHASE_REVERSE, traj, gout, ug, vg, ag, None, None)
+        if self.register_elbos:
+            ilc = il[:T].cpu()
+            for in_it in range(0, T, max(int(self.log_every), 1)):
+                self.elbos.append((1, -ilc[in_it].item()))
+            self.elbos.append((0, -loss.item()))
+        self.u.grad = ug.to(self.u.dtype)
+        if self.learn_v:
+            self.v.grad = vg.to(self.v.dtype)
+        if self.alpha is not None and self.alpha.requires_grad:
+            self.alpha.grad = ag.to(self.alpha.dtype)
+        self._step_outer_optimisers()
+        if self.scheduler_optim_net:
+            self.scheduler_optim_net.step()
+        # the fast weights phi_T were written back into the model's parameters by the kernel (reference :596-599)
+        return loss[0] if loss.dim() else loss
+
+    def _step_outer_optimisers(self):
+        self.optim_u.step()
+        if self.learn_v:
+            self.optim_v.step()
+            if not self.parameterised:
+                with torch.no_grad():
+                    torch.clamp_(self.v, min=0.0)
+        if getattr(self, "optim_alpha", None) is not None and self.learn_v:
+            self.optim_alpha.step()
+
+    def hyper_step(self, xbatch, ybatch, T=50, inner_opt_class=None, K=30, linsys_lr=1e-4,
+                   hypergrad_approx="CG_normaleq", **kwargs):
+        """Implicit-differentiation step (reference :602-687 with hypergrad.CG_normaleq :199-244 / fixed_point :83-140):
+        T plain Adam steps (hypergrad.DifferentiableAdam arithmetic), then K iterations of CG on the normal equations of
+        the fixed-point map  Phi(w) = w - linsys_lr * grad inner(w)  whose Jacobian products are Hessian-vector products
+        of the inner objective -- each one fused CUDA pass.  Noise is consumed in the reference's order (the JVP's
+        double-VJP evaluates Phi twice, the first draw is discarded)."""
+        from psvi.hypergrad.hypergradients import cg_normaleq_native, fixed_point_native
+        T = int(self.inner_it)
+        self._zero_grads()
+        model, desc, S = self._model_desc()
+        mu, rho = model.flat()
+        P = mu.numel()
+        u, v = self._uv()
+        z32 = self._z32()
+        lr = float(self.optim_net.param_groups[0]["lr"])
+        am, av = torch.zeros(2 * P, device=self.device), torch.zeros(2 * P, device=self.device)
+        _native.unroll(desc, self._noise(T), mu, rho, am, av, 0, u, z32, None, v, float(self.N), self._vmode,
+                       self._alpha_value(), T, lr, _native.ADAM_HYPERGRAD, None)
+        solver = cg_normaleq_native if hypergrad_approx == "CG_normaleq" else fixed_point_native
+        ug, vg, ag = solver(self, desc, mu, rho, u, z32, v, xbatch, ybatch, K, linsys_lr)
+        self.u.grad = ug if self.u.grad is None else self.u.grad + ug
+        if self.learn_v:
+            self.v.grad = vg if self.v.grad is None else self.v.grad + vg
+        if self.alpha is not None and self.alpha.requires_grad:
+            self.alpha.grad = ag
+        self._step_outer_optimisers()
+        ll = self.psvi_elbo(xbatch, ybatch, model=self.model)
+        return ll.item()
+
+    def joint_step(self, xbatch, ybatch):
+        raise NotImplementedError("--trainer joint is outside the hot path (SURVEY.md section 8a: nested / hyper)")
+
+    alternating_step = joint_step
+
+    # ------------------------------------------------------------------------------------------------ model
+    def set_up_model(self):
+        """reference :689-758 (same constructor order, hence the same CPU RNG stream and initial weights)."""
+        if self.logistic_regression:
+            self.model = make_logistic_regression(self.D, self.nc, init_sd=self.init_sd,
+                                                  mc_samples=self.mc_samples).to(self.device)
+        elif self.architecture in {"fn", "residual_fn"}:
+            self.model = make_fcnet(self.D, self.n_hidden, self.nc, n_layers=self.n_layers, linear_class=VILinear,
+                                    nonl_class=nn.ReLU, mc_samples=self.mc_samples,
+                                    residual=(self.architecture == "residual_fn"), init_sd=self.init_sd).to(self.device)
+        elif self.architecture == "fn2":
+            self.model = make_fc2net(self.D, self.n_hidden, self.nc, mc_samples=self.mc_samples, init_sd=self.init_sd)
+        elif self.architecture == "lenet":
+            self.model = make_lenet(mc_samples=self.mc_samples, init_sd=self.init_sd)
+        else:
+            raise NotImplementedError(f"architecture {self.architecture!r} is outside the PSVI hot-path scope")
+        if isinstance(self.model, MeanFieldMLP) and self.device.type == "cuda":
+            self.model.flat()
+
+    # ------------------------------------------------------------------------------------------------ data
+    def _device_dataset(self, ds, key):
+        c = self._dev_data.get(key)
+        if c is None or c[0] is not ds:
+            x = torch.as_tensor(ds.data).to(self.device, torch.float32).reshape(len(ds), -1).contiguous()
+            y = torch.as_tensor(ds.targets).to(self.device).to(torch.int32).contiguous()
+            c = (ds, x, y)
+            self._dev_data[key] = c
+        return c[1], c[2]
+
+    def _next_minibatch(self):
+        """`next(iter(train_loader))` of the reference (:895): a fresh uniformly random batch of min(B, N) rows every
+        outer step -- gathered on the device from the resident copy of the training set."""
+        x, y = self._device_dataset(self.train_dataset, "train")
+        n = x.shape[0]
+        idx = torch.randperm(n)[: min(int(self.data_minibatch), n)].to(self.device, non_blocking=True)
+        return x[idx], y[idx]
+
+    # ------------------------------------------------------------------------------------------------ main loop
+    def run_psvi(self, init_args="subsample", trainer="nested", n_layers=1, logistic_regression=True, n_hidden=None,
+                 architecture=None, log_every=10, inner_it=10, data_minibatch=None, lr0net=1e-3, lr0u=1e-3,
+                 lr0joint=1e-3, lr0v=1e-2, lr0z=1e-2, init_sd=1e-3, num_epochs=1000, log_pseudodata=False,
+                 prune_idx=0, increment_idx=0, gamma=1.0, **kwargs):
+        """Run inference (reference :761-1028); returns the same results dict."""
+        self.init_args, self.trainer, self.logistic_regression = init_args, trainer, logistic_regression
+        self.architecture, self.n_hidden, self.n_layers, self.init_sd = architecture, n_hidden, n_layers, init_sd
+        self.log_every, self.log_pseudodata = log_every, log_pseudodata
+        self.data_minibatch = data_minibatch
+        self.inner_it, self.num_epochs = inner_it, num_epochs
+        self.scheduler_optim_net = None
+        self.gamma = gamma
+        epoch_quarter = (self.N // self.data_minibatch) // 4
+        scheduler_kwargs = {"step_size": epoch_quarter if epoch_quarter > 0 else 10000, "gamma": self.gamma}
+        self.train_loader = DataLoader(self.train_dataset, batch_size=self.data_minibatch, shuffle=True)
+        self.test_loader = DataLoader(self.test_dataset, batch_size=self.data_minibatch, shuffle=False)
+        self.set_up_model()
+        nlls_psvi, accs_psvi, core_idcs_psvi, iws_entropy, nesses, vs_entropy, us, zs, vs, grid_preds, times = (
+            [], [], [], [], [], [], [], [], [], [], [0])
+        {"random": self.pseudo_rand_init, "subsample": self.pseudo_subsample_init}[self.init_args]()
+        self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
+        self.optim_u = torch.optim.Adam([self.u], lr0u)
+        self.scheduler_optim_net = torch.optim.lr_scheduler.StepLR(self.optim_net, **scheduler_kwargs)
+        if self.learn_v:
+            self.optim_v = torch.optim.Adam([self.v], lr0v)
+        optimizers = {"nested": self.nested_step, "hyper": self.hyper_step}
+        if self.trainer not in optimizers:
+            raise NotImplementedError(f"--trainer {self.trainer} is outside the hot path (nested / hyper are built)")
+        psvi_step = optimizers[self.trainer]
+        t_start = time.time()
+        log_resource = LogResource()
+        for it in tqdm(range(self.num_epochs), disable=kwargs.get("quiet", False)):
+            xbatch, ybatch = self._next_minibatch()
+            if it % self.log_every == 0:
+                test_acc, test_nll, iw_ent, ness, v_ent = self.evaluate()
+                with torch.no_grad():
+                    nlls_psvi.append(test_nll.item())
+                    accs_psvi.append(test_acc.item())
+                    if not kwargs.get("quiet", False):
+                        print(f"\npredictive accuracy: {(100*test_acc.item()):.2f}%")
+                    core_idcs_psvi.append(self.num_pseudo)
+                    times.append(times[-1] + time.time() - t_start)
+                    vs.append(self.v.clone().cpu().detach().numpy())
+                    if iw_ent is not None:
+                        iws_entropy.append(iw_ent.item())
+                    if ness is not None:
+                        nesses.append(ness.item())
+                    if v_ent is not None:
+                        vs_entropy.append(v_ent.item())
+                    if self.log_pseudodata:
+                        us.append(self.u.clone().cpu().detach().numpy())
+                        zs.append(self.z.clone().cpu().detach().numpy())
+            if self.reset and it % self.reset_interval == 0:
+                self.weight_reset()
+            psvi_step(xbatch, ybatch)
+            log_resource.update()
+        resource_data = log_resource.get_resources()
+        self.results["accs"] = accs_psvi
+        self.results["nlls"] = nlls_psvi
+        self.results["csizes"] = core_idcs_psvi
+        self.results["times"] = times[1:]
+        self.results["elbos"] = self.elbos
+        self.results["went"] = iws_entropy
+        self.results["ness"] = nesses
+        self.results["vent"] = vs_entropy
+        self.results["vs"] = vs
+        self.results["avg_epoch_time"] = resource_data["time"]
+        self.results["gpu_memory"] = resource_data["memory"]
+        self.results["chosen_indices"] = self.chosen_indices
+        if self.log_pseudodata:
+            self.results["us"], self.results["zs"], self.results["grid_preds"] = us, zs, grid_preds
+        return self.results
+
+    # ------------------------------------------------------------------------------------------------ evaluation
+    def evaluate(self, correction=True, **kwargs):
+        """Importance-weighted predictive metrics over the test set (reference :1031-1108): one streaming CUDA pass,
+        a fresh noise slab per test batch as in the reference; sharded by test batch over the ranks when distributed.
+        Returns (acc, nll, iw_entropy, ness, v_entropy) as 0-dim tensors."""
+        assert self.mc_samples > 1
+        model, desc, S = self._model_desc()
+        mu, rho = model.flat()
+        u, v = self._uv()
+        xt, yt = self._device_dataset(self.test_dataset, "test")
+        batch = int(self.data_minibatch)
+        n = xt.shape[0]
+        n_slabs = -(-n // batch)
+        dist, rank, world = _dist_info()
+        out = torch.zeros(8, device=self.device)
+        noise = self._noise(n_slabs)
+        lo, hi = shard_bounds(n_slabs, rank, world)
+        if hi > lo:
+            r0, r1 = lo * batch, min(hi * batch, n)
+            scratch = self._buf("eval", _native.eval_scratch_floats(desc, r1 - r0, batch))
+            if noise.mode == _native.NOISE_EXTERNAL and lo > 0:   # external slabs are indexed from this rank's first
+                noise = _native.make_noise(noise._keepalive[lo:hi].contiguous())
+            _native.evaluate(desc, noise, mu, rho, u, self._z32(), v, xt[r0:r1], yt[r0:r1], batch,
+                             0 if noise.mode == _native.NOISE_EXTERNAL else lo, float(self.N), self._vmode,
+                             self._alpha_value(), 0 if correction else 1, out, scratch)
+            if hi != n_slabs:
+                out[3:5] = 0.0   # Q12: the weight diagnostics are those of the globally last batch
+        if dist is not None:
+            dist.all_reduce(out)
+        vs = self.f(self.v.detach(), 0)
+        v_entropy = vs.sum().square() / vs.square().sum() / self.num_pseudo if self.compute_weights_entropy else None
+        return (out[1] / out[2], out[0] / out[2], out[3] if self.compute_weights_entropy else None, out[4], v_entropy)
+
+    def weight_reset(self):
+        """Reset variational parameters to initialisation (reference :1110-1128)."""
+        for layer in self.model.modules():
+            if isinstance(layer, VILinear) and hasattr(layer, "reset_parameters_variational"):
+                layer.reset_parameters_variational()   # in-place inits: the flat-buffer views stay valid
+
+    def pred_on_grid(self, n_test_per_dim=250, correction=True, **kwargs):
+        raise NotImplementedError("pred_on_grid (plots) is outside the hot path (SURVEY.md section 8f item 3)")
+
+
+class PSVILearnV(PSVI):
+    r"""PSVI with learnable v on a simplex: f = softmax (reference :1344-1360)."""
+
+    _vmode = _native.VMODE_SOFTMAX
+
+    def __init__(self, learn_v=True, parameterised=True, **kwargs):
+        super().__init__(**kwargs)
+        self.learn_v, self.parameterised = learn_v, parameterised
+        with torch.no_grad():
+            self.v = torch.zeros(self.num_pseudo, device=self.device)
+        self.v.requires_grad_(True)
+        self.f = torch.softmax
+
+
+class PSVI_No_Rescaling(PSVI):
+    r"""PSVI without any rescaling of the coreset likelihood (reference :1363-1373)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.v *= 1.0 / self.N
+
+
+class PSVIFreeV(PSVI):
+    r"""PSVI with learnable non-negative v (reference :1376-1385)."""
+
+    def __init__(self, learn_v=True, **kwargs):
+        super().__init__(**kwargs)
+        self.learn_v = True
+        self.v.requires_grad_(True)
+
+
+class PSVIAV(PSVILearnV):
+    r"""Learnable simplex weights and learnable total evidence: f = exp(alpha) softmax(v) (reference :1475-1619)."""
+
+    _vmode = _native.VMODE_EXPALPHA_SOFTMAX
+
+    def __init__(self, learn_v=True, **kwargs):
+        super().__init__(**kwargs)
+        self.alpha = torch.tensor([0.0], device=self.device)
+        self.alpha.requires_grad_(True)
+        self.f = lambda *x: torch.exp(self.alpha.detach()) * torch.softmax(x[0], x[1])
+        self.optim_alpha = torch.optim.Adam([self.alpha], self.lr0alpha)
+        self.results["alpha"] = []
+
+    def evaluate(self, **kwargs):
+        self.results["alpha"].append(self.alpha.clone().cpu().detach().numpy())
+        return super().evaluate(**kwargs)
+
+
+class PSVIFixedU(PSVILearnV):
+    r"""Fixed coreset locations, learnable weights (reference :1622-1740): the u update is skipped."""
+
+    def _step_outer_optimisers(self):
+        self.u.grad = None
+        if self.learn_v:
+            self.optim_v.step()
+
+
+class PSVIAFixedU(PSVIAV):
+    r"""Fixed locations, learnable weights and evidence scale (reference :1743-1883)."""
+
+    def _step_outer_optimisers(self):
+        self.u.grad = None
+        if self.learn_v:
+            self.optim_v.step()
+            self.optim_alpha.step()
+
+
+def _out_of_scope(name, where):
+    class _Stub(PSVI):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} ({where}) is outside the PSVI hot path built so far "
+                                      "(SURVEY.md section 8f item 1)")
+    _Stub.__name__ = name
+    return _Stub
+
+
+PSVI_Ablated = _out_of_scope("PSVI_Ablated", "reference psvi_classes.py:1388-1408")
+PSVI_No_IW = _out_of_scope("PSVI_No_IW", "reference psvi_classes.py:1411-1472")
+PSVIEvaluate = _out_of_scope("PSVIEvaluate", "reference psvi_classes.py:1885")
+PSVI_regressor = _out_of_scope("PSVI_regressor", "reference psvi_classes.py:1940")
+PSVILearnV_regressor = _out_of_scope("PSVILearnV_regressor", "reference psvi_classes.py:2100")
+PSVIAV_regressor = _out_of_scope("PSVIAV_regressor", "reference psvi_classes.py:2200")

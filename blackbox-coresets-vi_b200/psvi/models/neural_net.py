@@ -1,0 +1,295 @@
+"""Bayesian layers and model factories of the PSVI hot path -- same names, constructor arguments, parameter names and
+RNG-consumption order as the reference's psvi/models/neural_net.py, with the math executed by libpsvi_b200 (CUDA).
+
+Reference map (psvi/models/neural_net.py):  VIMixin :60-173, VILinear :176-179, make_fcnet :267-297,
+categorical_fn :22-23, set_mc_samples :26-29, inverse_softplus :32-35.  `state_dict`s interchange with the reference
+(parameter names weight, bias, _weight_sd, _bias_sd; module names lin{i}, nonl{i}, classifier).
+
+What is native here: a whole mean-field MLP (nn.Sequential of VILinear / ReLU, as built by make_fcnet or by
+PSVI.set_up_model for `logistic_regression`) is evaluated by ONE fused kernel (sampling -> per-sample GEMMs -> ReLU ->
+logits), see MeanFieldMLP.forward.  Gradients are not obtained with autograd: the PSVI objectives, their gradients and
+the hypergradient are separate fused kernels driven by psvi.inference.psvi_classes.
+Full-covariance (fn2) and convolutional (lenet) families are declared for API compatibility and raise
+NotImplementedError at construction in this round (DESIGN.md "not yet covered").
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from psvi import _native
+
+
+def categorical_fn(logits=None, probs=None):
+    # reference neural_net.py:22-23 (kept for callers that pass `distr_fn`; the fused kernels implement it directly)
+    return torch.distributions.Categorical(logits=logits, probs=probs)
+
+
+def gaussian_fn(loc=None, scale=None):
+    return torch.distributions.normal.Normal(loc, scale)
+
+
+def set_mc_samples(net, mc_samples):
+    for module in net.modules():
+        if isinstance(module, VIMixin):
+            module.mc_samples = mc_samples
+
+
+def inverse_softplus(x):
+    if torch.is_tensor(x):
+        return x.expm1().log()
+    return np.log(np.expm1(x))
+
+
+class _NoiseCounter:
+    """Hands out Philox stream ids ("domains") so that no two native calls of a process reuse noise."""
+    value = 0
+
+    @classmethod
+    def next(cls):
+        cls.value += 1
+        return cls.value
+
+
+class VIMixin(nn.Module):
+    """Mean-field Gaussian over weight and bias; sigma = softplus(rho); prior N(0, prior_sd) -- reference :60-173."""
+
+    def __init__(self, *args, init_sd=0.01, prior_sd=1.0, mc_samples=1, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._weight_sd = nn.Parameter(inverse_softplus(torch.full_like(self.weight, init_sd)))
+        if self.bias is not None:
+            self._bias_sd = nn.Parameter(inverse_softplus(torch.full_like(self.bias, init_sd)))
+        else:
+            self.register_parameter("_bias_sd", None)
+        self.prior_sd, self.mc_samples, self._cached_weight, self._cached_bias, self._init_sd = (
+            prior_sd, mc_samples, None, None, init_sd)
+        self.reset_parameters_variational()
+
+    def reset_parameters_variational(self) -> None:
+        super().reset_parameters()  # second nn.Linear init draw, as in the reference (:87-88)
+        self._weight_sd.data.copy_(inverse_softplus(torch.full_like(self.weight, self._init_sd)))
+        if self.bias is not None:
+            self._bias_sd.data.copy_(inverse_softplus(torch.full_like(self.bias, self._init_sd)))
+        self._cached_weight, self._cached_bias = None, None
+
+    @property
+    def weight_sd(self):
+        return F.softplus(self._weight_sd)
+
+    @property
+    def bias_sd(self):
+        return F.softplus(self._bias_sd) if self.bias is not None else None
+
+    def kl(self):
+        """KL(q || N(0, prior_sd)) in closed form (reference :101-108 via torch.distributions)."""
+        def one(mu, sd):
+            ps = self.prior_sd
+            return (0.5 * ((sd * sd + mu * mu) / (ps * ps) - 1.0) - torch.log(sd / ps)).sum()
+        out = one(self.weight, self.weight_sd)
+        if self.bias is not None:
+            out = out + one(self.bias, self.bias_sd)
+        return out
+
+    def sampled_nkl(self):
+        """log p(theta_s) - log q(theta_s) of the cached sample (reference :110-115) -> [S] (scalar if mc_samples==1)."""
+        if self._cached_weight is None:
+            raise RuntimeError("sampled_nkl() needs a forward pass first")
+        c = 0.5 * float(np.log(2 * np.pi))
+
+        def one(th, mu, sd, nd):
+            ps = self.prior_sd
+            lp = -0.5 * (th / ps) ** 2 - float(np.log(ps)) - c
+            lq = -0.5 * ((th - mu) / sd) ** 2 - torch.log(sd) - c
+            return (lp - lq).flatten(-nd).sum(-1)
+        out = one(self._cached_weight, self.weight, self.weight_sd, self.weight.ndim)
+        if self.bias is not None:
+            b = self._cached_bias.squeeze(1) if self.mc_samples > 1 else self._cached_bias
+            out = out + one(b, self.bias, self.bias_sd, self.bias.ndim)
+        return out
+
+    @property
+    def weight_batch_shape(self):
+        return torch.Size((self.mc_samples,) if self.mc_samples > 1 else ())
+
+    @property
+    def bias_batch_shape(self):
+        return torch.Size((self.mc_samples, 1) if self.mc_samples > 1 else ())
+
+    def extra_repr(self):
+        return f"{super().extra_repr()}, mc_samples={self.mc_samples}"
+
+
+class VILinear(VIMixin, nn.Linear):
+    """reference :176-179.  A lone VILinear evaluates through the same fused kernel as a 1-layer MeanFieldMLP."""
+
+    def rsample(self):
+        _forward_stack([self], torch.zeros(1, self.in_features, device=self.weight.device))
+        return self._cached_weight, self._cached_bias
+
+    def forward(self, x):
+        if x.dim() != 2:
+            raise NotImplementedError(
+                "a stand-alone VILinear takes [rows, in_features] inputs; per-sample [S, rows, in] activations only "
+                "occur inside a stack, which MeanFieldMLP (make_fcnet) evaluates as one fused kernel")
+        return _forward_stack([self], x)
+
+
+def _layer_tensors(layers):
+    mu = torch.cat([t.detach().reshape(-1) for m in layers for t in (m.weight, m.bias)]).float().contiguous()
+    rho = torch.cat([t.detach().reshape(-1) for m in layers for t in (m._weight_sd, m._bias_sd)]).float().contiguous()
+    return mu, rho
+
+
+def _forward_stack(layers, x, noise=None, flat=None):
+    """Sampled forward of a stack of VILinear layers (ReLU between) on the GPU: returns logits [S, R, C] ([R, C] if
+    mc_samples == 1) and fills every layer's _cached_weight / _cached_bias with views of the sampled weights."""
+    _native.require_cuda()
+    S = int(layers[0].mc_samples)
+    for m in layers:
+        if m.bias is None:
+            raise NotImplementedError("bias=False VILinear layers are not supported by the fused kernels")
+        if float(m.prior_sd) != 1.0:
+            raise NotImplementedError("prior_sd != 1 is not supported by the fused kernels")
+        if int(m.mc_samples) != S:
+            raise ValueError("all VI layers of a stack must share mc_samples")
+    dims = [layers[0].in_features] + [m.out_features for m in layers]
+    model = _native.make_model(dims, max(S, 1))
+    mu, rho = flat if flat is not None else _layer_tensors(layers)
+    x = x.detach().to(device=mu.device, dtype=torch.float32).contiguous()
+    R, P = x.shape[0], mu.numel()
+    logits = torch.empty(max(S, 1), R, dims[-1], device=mu.device)
+    theta = torch.empty(max(S, 1), P, device=mu.device)
+    if noise is None:
+        noise = _native.make_noise(None, seed=torch.initial_seed(), domain=_NoiseCounter.next())
+    _native.forward(model, noise, mu, rho, x, logits, theta_out=theta)
+    off = 0
+    for m in layers:
+        nw, nb = m.weight.numel(), m.bias.numel()
+        w = theta[:, off:off + nw].view(max(S, 1), *m.weight.shape)
+        b = theta[:, off + nw:off + nw + nb].view(max(S, 1), 1, nb)
+        m._cached_weight, m._cached_bias = (w, b) if S > 1 else (w[0], b[0, 0])
+        off += nw + nb
+    return logits if S > 1 else logits[0]
+
+
+class MeanFieldMLP(nn.Sequential):
+    """nn.Sequential of VILinear / ReLU evaluated by one fused kernel.  Also owns the flat (mu, rho) device buffers the
+    PSVI kernels update in place; the modules' nn.Parameters are views into them, so `state_dict`, `parameters()` and
+    torch optimisers keep working unchanged."""
+
+    def vi_layers(self):
+        return [m for m in self if isinstance(m, VILinear)]
+
+    def check_supported(self):
+        mods = list(self)
+        ok = len(mods) >= 1 and isinstance(mods[-1], VILinear)
+        for i, m in enumerate(mods[:-1]):
+            ok = ok and (isinstance(m, VILinear) if i % 2 == 0 else isinstance(m, nn.ReLU))
+        if not ok or len(self.vi_layers()) > _native.MAX_LAYERS:
+            raise NotImplementedError("fused kernels cover VILinear (ReLU VILinear)* stacks with at most "
+                                      f"{_native.MAX_LAYERS} VI layers; got {self}")
+
+    @property
+    def dims(self):
+        ls = self.vi_layers()
+        return [ls[0].in_features] + [m.out_features for m in ls]
+
+    def n_samples(self):
+        return int(self.vi_layers()[0].mc_samples)
+
+    def flat(self):
+        """(mu, rho): contiguous fp32 device tensors in theta layout whose storage backs the layer parameters."""
+        ls = self.vi_layers()
+        f = getattr(self, "_flat", None)
+        if f is not None:
+            ok, off = f[0].device == ls[0].weight.device, 0
+            for m in ls:
+                for t, base in ((m.weight, f[0]), (m.bias, f[0])):
+                    ok = ok and t.data_ptr() == base.data_ptr() + 4 * off
+                    off += t.numel()
+            off = 0
+            for m in ls:
+                for t in (m._weight_sd, m._bias_sd):
+                    ok = ok and t.data_ptr() == f[1].data_ptr() + 4 * off
+                    off += t.numel()
+            if ok:
+                return f
+        mu, rho = _layer_tensors(ls)
+        off = 0
+        for m in ls:
+            for t_mu, t_rho in ((m.weight, m._weight_sd), (m.bias, m._bias_sd)):
+                n = t_mu.numel()
+                t_mu.data = mu[off:off + n].view(t_mu.shape)
+                t_rho.data = rho[off:off + n].view(t_rho.shape)
+                off += n
+        object.__setattr__(self, "_flat", (mu, rho))
+        return self._flat
+
+    def forward(self, x, noise=None):
+        self.check_supported()
+        return _forward_stack(self.vi_layers(), x, noise=noise, flat=self.flat() if self.vi_layers()[0].weight.is_cuda else None)
+
+
+def make_fcnet(in_dim, h_dim, out_dim, n_layers=2, linear_class=None, nonl_class=None, mc_samples=4, residual=False,
+               **kwargs):
+    """reference :267-297 (module names lin{i}, nonl{i}, classifier; default n_layers=2)."""
+    if linear_class is None:
+        linear_class = VILinear
+    if nonl_class is None:
+        nonl_class = nn.ReLU
+    net = MeanFieldMLP() if (linear_class is VILinear and nonl_class is nn.ReLU) else nn.Sequential()
+    for i in range(n_layers):
+        net.add_module(f"lin{i}", linear_class(in_dim if i == 0 else h_dim, h_dim, **kwargs))
+        net.add_module(f"nonl{i}", nonl_class())
+    net.add_module("classifier", linear_class(h_dim, out_dim, **kwargs))
+    for module in net.modules():
+        module.mc_samples = mc_samples
+    return net
+
+
+def make_logistic_regression(in_dim, out_dim, **kwargs):
+    """nn.Sequential(VILinear(D, nc, ...)) of PSVI.set_up_model (psvi_classes.py:694-699)."""
+    return MeanFieldMLP(VILinear(in_dim, out_dim, **kwargs))
+
+
+# ---- families that are part of the reference surface but not yet covered by kernels (a3, a4) ----
+class MultivariateNormalVIMixin(nn.Module):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("full-covariance layers (fn2, reference neural_net.py:408-491) are not built yet "
+                                  "in the B200 path; see DESIGN.md 'not yet covered'")
+
+
+class VILinearMultivariateNormal(MultivariateNormalVIMixin, nn.Linear):
+    pass
+
+
+class VIConv2d(VIMixin, nn.Conv2d):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("VIConv2d / lenet (reference neural_net.py:194-246,334-359) is not built yet in the "
+                                  "B200 path; see DESIGN.md 'not yet covered'")
+
+
+class BatchMaxPool2d(nn.MaxPool2d):
+    pass
+
+
+def make_fc2net(*args, **kwargs):
+    raise NotImplementedError("fn2 (full-covariance BNN, reference neural_net.py:494-524) is not built yet")
+
+
+def make_lenet(*args, **kwargs):
+    raise NotImplementedError("lenet (reference neural_net.py:334-359) is not built yet")
+
+
+def make_alexnet(*args, **kwargs):
+    raise NotImplementedError("alexnet is outside the PSVI hot-path scope (SURVEY.md section 2, row 1)")
+
+
+def make_regressor_net(*args, **kwargs):
+    raise NotImplementedError("regressor nets are outside the PSVI hot-path scope (SURVEY.md section 8f)")
+
+
+def make_resnet(*args, **kwargs):
+    raise NotImplementedError("resnet is outside the PSVI hot-path scope (SURVEY.md section 2, row 1)")

@@ -161,6 +161,14 @@ int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise,
                      float N, int32_t vmode, float alpha, int32_t mode,
                      float* out, void* scratch, void* stream);
 
+/* ---- module-level forward: replaces nn.Sequential(VILinear, ReLU, ..., VILinear)(x)  (neural_net.py:155-179,267-297)
+ *   x [n_rows][D] -> logits [S][n_rows][C]; theta_out [S][P] (nullable) receives the sampled weights in TL (the
+ *   reference's _cached_weight/_cached_bias), nkl_out [S] (nullable) sum_layers sampled_nkl() (:110-115), kl_out [1]
+ *   (nullable) sum_layers kl() (:101-108).  noise slab 0. */
+int psvi_mf_forward(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                    const float* x, int32_t n_rows, float* logits, float* theta_out, float* nkl_out, float* kl_out,
+                    void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,
