@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- PSVI hot-path benchmark on B200 (contract: see the task description; metric from BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference path
+
+Workload (BASELINE.json configs[1], "cfg2" in SURVEY.md section 8): halfmoon-shaped data (N=800, D=2, C=2),
+`fn` BNN with one hidden layer of 100 units, psvi_learn_v, coreset M=50, S=10 MC samples, T=100 unrolled inner Adam
+steps, minibatch B=128.  One STEP = one PSVI outer step = PSVILearnV.nested_step: T inner steps + outer psvi_elbo +
+hypergradient on (u, v) + the Adam updates of u and v.
+
+  value : outer steps/s with the minibatch already resident in HBM (device-timed, CUDA events per step, L2 flushed
+          between steps)
+  e2e   : outer steps/s through the public API with HOST (pinned) minibatches: H2D copy of x/y and D2H read of the
+          loss inside the timed region
+  N > 1 : one independent PSVI chain (trial) per GPU -- the reference's own multi-GPU mode
+          (flow-psvi-parallel.py:455-479) -- so `value` is the sum over ranks ("weak" scaling, no data-path
+          collective); the sharded full-data pass (the part of the path that does shard, one all-reduce) is measured
+          separately and reported under "sharded".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "blackbox-coresets-vi_b200"))
+
+CFG = dict(workload="cfg2: halfmoon N=800 D=2 C=2, fn H=100 (1 hidden layer), psvi_learn_v, M=50, S=10, T=100, B=128",
+           D=2, H=100, C=2, M=50, S=10, T=100, B=128, N=800, init_sd=1e-3)
+METRIC, UNIT = "psvi_outer_steps_per_sec", "outer_steps/s"
+
+
+def flops_outer_step(c):
+    """Algorithmic FLOPs of one outer step: F_fwd(R) = 2 S R (D H + H C);
+    inner step = 3 F_fwd(M); reverse step = 6 F_fwd(M); outer fwd+bwd = 3 F_fwd(M+B)."""
+    f = lambda R: 2.0 * c["S"] * R * (c["D"] * c["H"] + c["H"] * c["C"])  # noqa: E731
+    return c["T"] * (3 + 6) * f(c["M"]) + 3 * f(c["M"] + c["B"])
+
+
+def make_data(seed=42):
+    import numpy as np
+    import torch
+    from sklearn.datasets import make_moons
+    X, Y = make_moons(n_samples=1000, noise=0.1, random_state=seed)
+    X, Y = torch.from_numpy(X.astype(np.float32)), torch.from_numpy(Y.astype(np.float32))
+    return X[:800], Y[:800], X[800:], Y[800:]
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(c):
+    """One outer step of the oracle port (numpy restatement of the reference path, fp32 like the reference)."""
+    import numpy as np
+    from oracle import psvi_oracle as po
+    rng = np.random.default_rng(0)
+    dims = [c["D"], c["H"], c["C"]]
+    P = po.p_theta(dims)
+    x, y, _, _ = make_data()
+    x, y = x.numpy(), y.numpy()
+    f32 = np.float32
+    mu = (rng.standard_normal(P) * 0.3).astype(f32)
+    rho = np.full(P, po.inverse_softplus(c["init_sd"]), f32)
+    u = x[: c["M"]].astype(f32).copy()
+    z = y[: c["M"]].astype(f32)
+    v = np.zeros(c["M"], f32)
+    st = dict(mu=mu, rho=rho, u=u, v=v)
+
+    def step():
+        eps = rng.standard_normal((c["T"] + 1, c["S"], P)).astype(f32)
+        idx = rng.permutation(c["N"])[: c["B"]]
+        r = po.nested_step(st["mu"], st["rho"], eps[: c["T"]], eps[c["T"]], st["u"], z, st["v"], x[idx].astype(f32),
+                           y[idx], f32(c["N"]), dims, f32(1e-3), vmode=1)
+        st["mu"], st["rho"] = r["mu_T"].astype(f32), r["rho_T"].astype(f32)
+        st["u"] = (st["u"] - 1e-4 * np.sign(r["u_grad"])).astype(f32)   # first-step Adam == sign step
+        st["v"] = (st["v"] - 1e-3 * np.sign(r["v_grad"])).astype(f32)
+        return float(r["loss"])
+    return step
+
+
+def time_cpu(c, steps, warmup):
+    step = cpu_step_fn(c)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 3))
+    sps, sec = time_cpu(CFG, steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(CFG),
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{steps} full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single thread); "
+                                       "the reference itself is Python and cannot travel to the GPU box"},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_chain(c, seed, device):
+    import torch
+    from psvi.experiments.experiments_utils import SynthDataset
+    from psvi.inference.psvi_classes import PSVILearnV
+    x, y, xt, yt = make_data()
+    tr, te = SynthDataset(x, y), SynthDataset(xt, yt)
+    kw = dict(mc_samples=c["S"], num_epochs=0, data_minibatch=c["B"], D=c["D"], N=c["N"], inner_it=c["T"],
+              trainer="nested", log_every=150, lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample",
+              init_sd=c["init_sd"], num_pseudo=c["M"], seed=seed, architecture="fn", n_hidden=c["H"], n_layers=1,
+              logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="halfmoon", nc=c["C"],
+              compute_weights_entropy=False, register_elbos=False, quiet=True)
+    obj = PSVILearnV(**kw)
+    obj.run_psvi(**kw)
+    return obj, (x, y, xt, yt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from psvi import _native
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _native.require_cuda()
+    c = CFG
+    K, W = args.steps, max(args.warmup, 3)
+
+    # -------- chain (one per rank; independent trials when world > 1) ----------------------------------------------
+    import torch.distributed as _d
+    # independent replicas: the sharded code path of nested_step must stay off for the headline number
+    obj, (x, y, xt, yt) = build_chain(c, seed=rank, device=dev)
+    import psvi.inference.psvi_classes as pc
+    real_dist_info = pc._dist_info
+    pc._dist_info = lambda: (None, 0, 1)
+    xd, yd = x.to(dev), y.to(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    idxs = [torch.randperm(c["N"], generator=g)[: c["B"]] for _ in range(K + W)]
+    dev_batches = [(xd[i.to(dev)].contiguous(), yd[i.to(dev)].contiguous()) for i in idxs]
+    host_batches = [(x[i].contiguous().pin_memory(), y[i].contiguous().pin_memory()) for i in idxs]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MiB > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # -------- value: device-resident inputs, per-step CUDA events, L2 flush between steps ----------------------------
+    launches0 = _native.launch_count() if hasattr(_native, "launch_count") else 0
+    for i in range(W):
+        obj.nested_step(*dev_batches[i])
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches1 = _native.launch_count()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record(stream)
+        obj.nested_step(*dev_batches[W + i])
+        ev[i][1].record(stream)
+    barrier()
+    launches = _native.launch_count() - launches1
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(ms)
+
+    # -------- kernel-only time of the dominant kernel (same launches, events right around the native call) ----------
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 50))]
+    for i, (a, b) in enumerate(kev):
+        flush.zero_()
+        _native.EVENT_HOOK = (a, b, stream)
+        obj.nested_step(*dev_batches[W + i])
+    _native.EVENT_HOOK = None
+    torch.cuda.synchronize()
+    kms = sorted(a.elapsed_time(b) for a, b in kev)
+    kernel_ms = sum(kms) / len(kms)
+
+    # -------- e2e: host (pinned) minibatches, H2D + D2H of the loss inside the timed region -------------------------
+    for i in range(W):
+        xb, yb = host_batches[i]
+        obj.nested_step(xb.to(dev, non_blocking=True), yb.to(dev, non_blocking=True)).item()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        xb, yb = host_batches[W + i]
+        loss = obj.nested_step(xb.to(dev, non_blocking=True), yb.to(dev, non_blocking=True))
+        loss.item()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+
+    # -------- secondary metric: MC log-lik evals/s (fn, M=50) -- both readings of SURVEY.md section 8d --------------
+    model, desc, S = obj._model_desc()
+    mu, rho = model.flat()
+    u, v = obj._uv()
+    am, av = torch.zeros(2 * mu.numel(), device=dev), torch.zeros(2 * mu.numel(), device=dev)
+    mu2, rho2 = mu.clone(), rho.clone()
+    n_ev = 200
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        a.record(stream)
+        _native.unroll(desc, obj._noise(n_ev), mu2, rho2, am, av, 0, u, obj._z32(), None, v, float(c["N"]), 1, 0.0, n_ev,
+                       1e-3, _native.ADAM_ROBUST_HIGHER, None)
+        b.record(stream)
+        torch.cuda.synchronize()
+    inner_evals = n_ev / (a.elapsed_time(b) * 1e-3)
+    for rep in range(3):
+        a.record(stream)
+        for _ in range(20):
+            obj.evaluate()
+        b.record(stream)
+        torch.cuda.synchronize()
+    pred_evals = 20 / (a.elapsed_time(b) * 1e-3)
+
+    # -------- sharded full-data predictive pass (the part of the path that shards; one all-reduce) -------------------
+    pc._dist_info = real_dist_info
+    sharded = None
+    try:
+        from psvi.experiments.experiments_utils import SynthDataset, make_synthetic_rows
+        n_big = 2_000_000
+        xt_big, yt_big = make_synthetic_rows(n_big, c["D"], c["C"], seed=0)
+        obj.test_dataset = SynthDataset(xt_big, yt_big.float())
+        obj.data_minibatch = 8192
+        obj._dev_data.pop("test", None)
+        obj.evaluate()
+        barrier()
+        a.record(stream)
+        reps = 3
+        for _ in range(reps):
+            obj.evaluate()
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = t.item() * 1e-3 / reps
+        sharded = {"what": f"PSVI.evaluate over {n_big} synthetic rows (D=2, fn H=100, S=10, M=50, batch 8192), rows "
+                           f"sharded over {world} rank(s), one all-reduce of 8 floats",
+                   "passes_per_s": 1.0 / sec, "row_samples_per_s": n_big * c["S"] / sec}
+    except Exception as e:  # never lose the headline number to the secondary section
+        sharded = {"error": repr(e)[:200]}
+
+    # -------- reduce over ranks ---------------------------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    value = world * K / (total_ms * 1e-3)
+    e2e = world * K / (e2e_ms * 1e-3)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        fl = flops_outer_step(c)
+        ach = fl / (kernel_ms * 1e-3) / 1e12
+        sm = _native.lib().psvi_device_sm_count()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": dict(c, parallelism="single chain" if world == 1 else
+                               f"{world} independent chains (trials), one per GPU, no data-path collective",
+                               l2="flushed between timed steps (256 MiB write)", noise="in-kernel Philox4x32-10"),
+                "clocks": clk,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": c["B"] * c["D"] * 4 + c["B"] * 4,
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": ach / peak_tf, "traffic": None,
+                             "kernel": "psvi_mf_engine_kernel", "kernel_ms": kernel_ms,
+                             "flops_per_launch": fl,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
+                             "note": "fp32 CUDA-core kernel on a 10-CTA cluster (10 of %d SMs); the GEMMs have K=D=2 / N=C=2 "
+                                     "and a T=100-long serial dependence, so the step is latency/issue bound and tensor "
+                                     "cores cannot be fed (SURVEY.md section 8d); the fraction against the tensor peak is "
+                                     "reported because the contract asks for it" % sm},
+                "extra": {"mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
+                                                    "full_data_predictive_passes_200rows": pred_evals},
+                          "sharded": sharded, "kernel_only_ms": kernel_ms,
+                          "per_step_ms_min_med_max": [min(ms), sorted(ms)[len(ms) // 2], max(ms)]}}
+        if not args.no_cpu_baseline and world == 1:
+            sps, sec = time_cpu(c, 12, 1)
+            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "12 full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single "
+                                              "thread) on this box's host CPU"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,17 +95,20 @@ struct Meta {
 };
 
 __host__ __device__ inline void make_meta(const int* dims, int L, Meta& m) {
+  // Padded layouts.  Activations of layer l are rows of lda[l] = (d_l + 1) | 1 floats: d_l values, then a constant 1
+  // (the tangent buffers keep 0 there), so that the bias is just one more weight column: sampled weights of layer l are
+  // rows of ldw[l] = (d_{l-1} + 1) | 1 floats [W[o][0..din-1], b[o], pad].  Odd leading dimensions keep shared-memory
+  // accesses conflict-free along either index.
   int pp = 0, pt = 0;
-  for (int l = 0; l <= L; ++l) m.lda[l] = dims[l] | 1;
+  for (int l = 0; l <= L; ++l) m.lda[l] = (dims[l] + 1) | 1;
   for (int l = 1; l <= L; ++l) {
     const int din = dims[l - 1], dout = dims[l];
     m.din[l] = din;
     m.dout[l] = dout;
-    m.ldw[l] = din | 1;  // odd leading dimension: conflict-free shared-memory access along either index
+    m.ldw[l] = (din + 1) | 1;
     m.woff[l] = pp;
+    m.boff[l] = pp + din;  // bias of output o lives at woff + o*ldw + din
     pp += dout * m.ldw[l];
-    m.boff[l] = pp;
-    pp += dout;
     m.tlw[l] = pt;
     pt += dout * din;
     m.tlb[l] = pt;
@@ -198,28 +201,109 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
-// "for every output o in [0,nOut): store(o, sum_k term(ctx(o), k))".  When there are fewer outputs than threads,
-// g = 2,4,..32 lanes share one output and combine with shuffles (keeps skinny products such as H->C busy).
-template <class Setup, class Term, class Store>
-__device__ __forceinline__ void reduce_outputs(int nOut, int K, Setup setup, Term term, Store store) {
-  int g = 1;
-  while (g < 32 && nOut * (g * 2) <= NT && K >= 8 * g) g <<= 1;
-  const int tid = threadIdx.x, sub = tid & (g - 1), grp = tid / g, ngrp = NT / g;
-  for (int base = 0; base < nOut; base += ngrp) {
-    const int o = base + grp;
-    float acc = 0.f;
-    if (o < nOut) {
-      auto ctx = setup(o);
-      for (int k = sub; k < K; k += g) acc += term(ctx, k);
+// Small shared-memory GEMM:  C(r, c) = sum_k A(r, k) * B(k, c)  [+ sum_k A2(r, k) * B2(k, c)]  for r < nrows, c < ncols,
+// with A(r,k) = A[r*a_rs + k*a_ks], B(k,c) = B[c*b_cs + k*b_ks]; epi(r, c, value) consumes every output exactly once.
+// Division-free thread mapping: the block is a (row-groups x column-lanes x k-split) grid with power-of-two extents;
+// when there are fewer outputs than threads the spare threads split K (g lanes per output, combined by shuffles);
+// otherwise each thread register-blocks 4 rows so that a B element is loaded once per 4 FMAs.
+struct GemmOp {
+  const float* A;
+  int a_rs, a_ks;
+  const float* B;
+  int b_cs, b_ks;
+  const float* A2;
+  const float* B2;
+};
+
+template <class Epi>
+__device__ __forceinline__ void small_gemm(int nrows, int ncols, int K, const GemmOp& op, Epi epi) {
+  int cl_sh = 0;
+  while ((1 << cl_sh) < ncols && (1 << cl_sh) < NT) ++cl_sh;
+  const int CL = 1 << cl_sh;
+  int RG = NT >> cl_sh;  // row groups before the k-split
+  int g_sh = 0;
+  while ((2 << g_sh) <= 32 && nrows * (2 << g_sh) <= RG && K >= (8 << g_sh)) ++g_sh;
+  const int g = 1 << g_sh;
+  RG >>= g_sh;
+  const int tid = threadIdx.x;
+  const int ks = tid & (g - 1), col = (tid >> g_sh) & (CL - 1), rg = tid >> (g_sh + cl_sh);
+  const bool two = op.A2 != nullptr;
+  for (int cb = 0; cb < ncols; cb += CL) {
+    const int cc = cb + col;
+    const bool cok = cc < ncols;
+    const float* Bp = op.B + (cok ? cc : 0) * op.b_cs;
+    const float* B2p = two ? op.B2 + (cok ? cc : 0) * op.b_cs : nullptr;
+    if (g == 1) {
+      int rr = rg;
+      // 4-row register blocking
+      for (; rr + 3 * RG < nrows; rr += 4 * RG) {
+        const float* A0 = op.A + rr * op.a_rs;
+        const int st = RG * op.a_rs;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        if (cok) {
+#pragma unroll 4
+          for (int k = 0; k < K; ++k) {
+            const float b = Bp[k * op.b_ks];
+            const float* a = A0 + k * op.a_ks;
+            c0 = fmaf(a[0], b, c0);
+            c1 = fmaf(a[st], b, c1);
+            c2 = fmaf(a[2 * st], b, c2);
+            c3 = fmaf(a[3 * st], b, c3);
+          }
+          if (two) {
+            const float* A20 = op.A2 + rr * op.a_rs;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+              const float b = B2p[k * op.b_ks];
+              const float* a = A20 + k * op.a_ks;
+              c0 = fmaf(a[0], b, c0);
+              c1 = fmaf(a[st], b, c1);
+              c2 = fmaf(a[2 * st], b, c2);
+              c3 = fmaf(a[3 * st], b, c3);
+            }
+          }
+          epi(rr, cc, c0);
+          epi(rr + RG, cc, c1);
+          epi(rr + 2 * RG, cc, c2);
+          epi(rr + 3 * RG, cc, c3);
+        }
+      }
+      for (; rr < nrows; rr += RG) {
+        if (cok) {
+          const float* A0 = op.A + rr * op.a_rs;
+          float c0 = 0.f;
+#pragma unroll 4
+          for (int k = 0; k < K; ++k) c0 = fmaf(A0[k * op.a_ks], Bp[k * op.b_ks], c0);
+          if (two) {
+            const float* A20 = op.A2 + rr * op.a_rs;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) c0 = fmaf(A20[k * op.a_ks], B2p[k * op.b_ks], c0);
+          }
+          epi(rr, cc, c0);
+        }
+      }
+    } else {
+      // k-split: every lane of a warp runs the same trip count (shuffles need the full warp)
+      for (int rb = 0; rb < nrows; rb += RG) {
+        const int rr = rb + rg;
+        const bool ok = cok && rr < nrows;
+        float c0 = 0.f;
+        if (ok) {
+          const float* A0 = op.A + rr * op.a_rs;
+#pragma unroll 4
+          for (int k = ks; k < K; k += g) c0 = fmaf(A0[k * op.a_ks], Bp[k * op.b_ks], c0);
+          if (two) {
+            const float* A20 = op.A2 + rr * op.a_rs;
+#pragma unroll 4
+            for (int k = ks; k < K; k += g) c0 = fmaf(A20[k * op.a_ks], B2p[k * op.b_ks], c0);
+          }
+        }
+        for (int off = g >> 1; off > 0; off >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+        if (ok && ks == 0) epi(rr, cc, c0);
+      }
     }
-    for (int off = g >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (o < nOut && sub == 0) store(o, acc);
   }
 }
-
-struct Ctx2 {
-  int a, b;
-};
 
 // ----------------------------------------------------------------------------------------------------------------
 struct Engine {
@@ -254,7 +338,7 @@ struct Engine {
 
   // ---- draw eps for (slab, s) and build theta (and the tangent thetad); returns this thread's partial of
   //      sampled_nkl_s = sum_i [-theta^2/2 + eps^2/2 + log sigma]  (neural_net.py:110-115)
-  __device__ float sample_theta(int s, int slab, bool tangent, float fold_beta) {
+  __device__ float sample_theta(int s, int slab, bool tangent, float fold_beta, bool want_nkl = false) {
     const int* pot = I(ly.pad_of_tl);
     float nkl = 0.f;
     const int Pt = mt.Pt;
@@ -278,7 +362,7 @@ struct Engine {
           F(ly.eps)[pp] = e;
           F(ly.theta)[pp] = th;
           if (tangent) F(ly.thetad)[pp] = F(ly.gmu)[pp] + F(ly.sgm)[pp] * F(ly.grho)[pp] * e;
-          nkl += -0.5f * th * th + 0.5f * e * e + logf(sg);
+          if (want_nkl) nkl += -0.5f * th * th + 0.5f * e * e + logf(sg);
           if (fold_beta != 0.f) {  // outer objective: d nkl_s / d theta = -theta, weighted by beta_s (A.2)
             const float tb = -fold_beta * th;
             F(ly.acc1)[pp] += tb;
@@ -302,15 +386,28 @@ struct Engine {
     const int D = p.dims[0], ld0 = mt.lda[0];
     float* a0 = F(ly.act[0]);
     const float* src = p.xb + (size_t)(r0 - p.M) * D;
-    for (int i = tid; i < nr * D; i += NT) {
-      const int rr = i / D, c = i - rr * D;
-      a0[rr * ld0 + c] = __ldg(src + i);
+    if (D <= 4) {  // tiny rows: one thread per row
+      for (int rr = tid; rr < nr; rr += NT) {
+        for (int c = 0; c < D; ++c) a0[rr * ld0 + c] = __ldg(src + rr * D + c);
+        a0[rr * ld0 + D] = 1.f;
+      }
+    } else {       // coalesced: consecutive threads read consecutive floats of the [nr][D] block
+      int rr = 0, c = tid;
+      while (c >= D) { c -= D; ++rr; }
+      const int step_r = NT / D, step_c = NT - step_r * D;
+      for (int i = tid; i < nr * D; i += NT) {
+        a0[rr * ld0 + c] = __ldg(src + i);
+        rr += step_r; c += step_c;
+        if (c >= D) { c -= D; ++rr; }
+      }
+      for (int r2 = tid; r2 < nr; r2 += NT) a0[r2 * ld0 + D] = 1.f;
     }
     for (int rr = tid; rr < nr; rr += NT) lab[rr] = __ldg(p.yb + (r0 - p.M) + rr);
     return a0;
   }
 
   // ---- forward through the MLP for one chunk (primal, optionally tangent) -----------------------------------------
+  // bias = the weight column that multiplies the constant-one slot of the layer input (K = din + 1)
   __device__ void forward(const float* a0, int nr, bool dual) {
     for (int l = 1; l <= p.L; ++l) {
       const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l];
@@ -318,43 +415,25 @@ struct Engine {
       const float* in = (l == 1) ? a0 : F(ly.act[l - 1]);
       const float* ind = F(ly.actd[l - 1]);
       const float* W = F(ly.theta) + mt.woff[l];
-      const float* bia = F(ly.theta) + mt.boff[l];
       const float* Wd = F(ly.thetad) + mt.woff[l];
-      const float* bd = F(ly.thetad) + mt.boff[l];
       float* out = F(ly.act[l]);
       float* outd = F(ly.actd[l]);
       const bool relu = l < p.L;
-      const bool has_ind = dual && l > 1;
-      auto setup = [&](int o) {
-        const int rr = o / dout;
-        return Ctx2{rr, o - rr * dout};
-      };
-      reduce_outputs(
-          nr * dout, din, setup, [&](const Ctx2& c, int k) { return in[c.a * ldi + k] * W[c.b * ldw + k]; },
-          [&](int o, float acc) {
-            const int rr = o / dout, oo = o - rr * dout;
-            acc += bia[oo];
-            out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc;
-          });
+      GemmOp op{in, ldi, 1, W, ldw, 1, nullptr, nullptr};
+      small_gemm(nr, dout, din + 1, op,
+                 [&](int rr, int oo, float acc) { out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc; });
       if (dual) {
-        // tangent pre-activation; the ReLU mask is applied below once the primal of the same element is final
-        reduce_outputs(
-            nr * dout, din, setup,
-            [&](const Ctx2& c, int k) {
-              float t = in[c.a * ldi + k] * Wd[c.b * ldw + k];
-              if (has_ind) t += ind[c.a * ldi + k] * W[c.b * ldw + k];
-              return t;
-            },
-            [&](int o, float acc) {
-              const int rr = o / dout, oo = o - rr * dout;
-              outd[rr * ldo + oo] = acc + bd[oo];
-            });
+        // tangent pre-activation  x Wd^T (+ xd W^T for l > 1; xd of the input layer is zero); masked below
+        GemmOp opd{in, ldi, 1, Wd, ldw, 1, l > 1 ? ind : nullptr, l > 1 ? W : nullptr};
+        small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) { outd[rr * ldo + oo] = acc; });
       }
       __syncthreads();
       if (dual && relu) {
-        for (int i = tid; i < nr * dout; i += NT) {
-          const int rr = i / dout, oo = i - rr * dout;
-          if (!(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
+        const int cl = 1 << (32 - __clz(dout - 1 | 1));  // power of two >= dout (>= 2)
+        const int sh = 31 - __clz(cl);
+        for (int i = tid; i < (nr << sh); i += NT) {
+          const int rr = i >> sh, oo = i & (cl - 1);
+          if (oo < dout && !(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
         }
         __syncthreads();
       }
@@ -419,70 +498,41 @@ struct Engine {
       const float* Ad = F(ly.adjd[l]);
       const float* W = F(ly.theta) + mt.woff[l];
       const float* Wd = F(ly.thetad) + mt.woff[l];
-      const float* eps = F(ly.eps);
-      float* acc1 = F(ly.acc1);
-      float* acc2 = F(ly.acc2);
-      float* acc3 = F(ly.acc3);
-      const int woff = mt.woff[l], boff = mt.boff[l];
+      const float* eps = F(ly.eps) + mt.woff[l];
+      float* acc1 = F(ly.acc1) + mt.woff[l];
+      float* acc2 = F(ly.acc2) + mt.woff[l];
+      float* acc3 = F(ly.acc3) + mt.woff[l];
       const bool has_ind = dual && l > 1;
-      // -- weight / bias adjoints: outputs (o, i) with i == din meaning the bias
-      auto setup = [&](int o) {
-        const int oo = o / (din + 1);
-        return Ctx2{oo, o - oo * (din + 1)};
-      };
-      reduce_outputs(
-          dout * (din + 1), nr, setup,
-          [&](const Ctx2& c, int k) {
-            float t = A[k * ldo + c.a] * (c.b < din ? in[k * ldi + c.b] : 1.f);
-            if (has_ind && c.b < din) t += Ad[k * ldo + c.a] * ind[k * ldi + c.b];
-            return t;
-          },
-          [&](int o, float acc) {
-            const int oo = o / (din + 1), ii = o - oo * (din + 1);
-            const int pp = ii < din ? woff + oo * ldw + ii : boff + oo;
-            acc1[pp] += acc;
-            acc2[pp] += acc * eps[pp];
-          });
+      // -- weight + bias adjoints: C(o, i) = sum_r A[r][o] * in[r][i], i <= din (in[r][din] == 1)
+      GemmOp ow{A, 1, ldo, in, 1, ldi, has_ind ? Ad : nullptr, has_ind ? ind : nullptr};
+      small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
+        const int pp = oo * ldw + ii;
+        acc1[pp] += acc;
+        acc2[pp] += acc * eps[pp];
+      });
       if (dual) {
-        reduce_outputs(
-            dout * (din + 1), nr, setup,
-            [&](const Ctx2& c, int k) { return Ad[k * ldo + c.a] * (c.b < din ? in[k * ldi + c.b] : 1.f); },
-            [&](int o, float acc) {
-              const int oo = o / (din + 1), ii = o - oo * (din + 1);
-              const int pp = ii < din ? woff + oo * ldw + ii : boff + oo;
-              acc3[pp] += acc * eps[pp];
-            });
+        GemmOp owd{Ad, 1, ldo, in, 1, ldi, nullptr, nullptr};
+        small_gemm(dout, din + 1, nr, owd, [&](int oo, int ii, float acc) {
+          const int pp = oo * ldw + ii;
+          acc3[pp] += acc * eps[pp];
+        });
       }
-      // -- input adjoints
+      // -- input adjoints: C(r, i) = sum_o A[r][o] * W[o][i]  (+ Ad[r][o] * Wd[o][i])
       if (l > 1 || need_x) {
         float* Ai = F(ly.adj[l - 1]);
         float* Aid = F(ly.adjd[l - 1]);
-        auto setup2 = [&](int o) {
-          const int rr = o / din;
-          return Ctx2{rr, o - rr * din};
-        };
-        reduce_outputs(
-            nr * din, dout, setup2,
-            [&](const Ctx2& c, int k) {
-              float t = A[c.a * ldo + k] * W[k * ldw + c.b];
-              if (dual) t += Ad[c.a * ldo + k] * Wd[k * ldw + c.b];
-              return t;
-            },
-            [&](int o, float acc) {
-              const int rr = o / din, ii = o - rr * din;
-              if (l > 1) {
-                Ai[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f;
-              } else {
-                F(ly.ubar)[(r0 + rr) * din + ii] += acc;
-              }
-            });
-        if (dual && l > 1) {
-          reduce_outputs(
-              nr * din, dout, setup2, [&](const Ctx2& c, int k) { return Ad[c.a * ldo + k] * W[k * ldw + c.b]; },
-              [&](int o, float acc) {
-                const int rr = o / din, ii = o - rr * din;
-                Aid[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f;
-              });
+        GemmOp ox{A, ldo, 1, W, 1, ldw, dual ? Ad : nullptr, dual ? Wd : nullptr};
+        if (l > 1) {
+          small_gemm(nr, din, dout, ox,
+                     [&](int rr, int ii, float acc) { Ai[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f; });
+          if (dual) {
+            GemmOp oxd{Ad, ldo, 1, W, 1, ldw, nullptr, nullptr};
+            small_gemm(nr, din, dout, oxd,
+                       [&](int rr, int ii, float acc) { Aid[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f; });
+          }
+        } else {
+          float* ub = F(ly.ubar) + r0 * din;
+          small_gemm(nr, din, dout, ox, [&](int rr, int ii, float acc) { ub[rr * din + ii] += acc; });
         }
       }
       __syncthreads();
@@ -492,15 +542,19 @@ struct Engine {
   // ---- push this CTA's accumulators to the slice owners, then clear them ------------------------------------------
   __device__ void push_acc(int ncomp) {
     const int slice = p.slice;
-    for (int pp = tid; pp < mt.Pp; pp += NT) {
-      const int owner = pp / slice, j = pp - owner * slice;
-      float* r = remote(ly.recv, owner) + (size_t)rank * 3 * slice + j;
-      r[0] = F(ly.acc1)[pp];
-      r[slice] = F(ly.acc2)[pp];
-      if (ncomp > 2) r[2 * slice] = F(ly.acc3)[pp];
-      F(ly.acc1)[pp] = 0.f;
-      F(ly.acc2)[pp] = 0.f;
-      F(ly.acc3)[pp] = 0.f;
+    for (int owner = 0; owner < p.G; ++owner) {
+      float* r = remote(ly.recv, owner) + (size_t)rank * 3 * slice;
+      const int base = owner * slice;
+      const int n = min(slice, mt.Pp - base);
+      for (int j = tid; j < n; j += NT) {
+        const int pp = base + j;
+        r[j] = F(ly.acc1)[pp];
+        r[slice + j] = F(ly.acc2)[pp];
+        if (ncomp > 2) r[2 * slice + j] = F(ly.acc3)[pp];
+        F(ly.acc1)[pp] = 0.f;
+        F(ly.acc2)[pp] = 0.f;
+        if (ncomp > 2) F(ly.acc3)[pp] = 0.f;
+      }
     }
   }
   __device__ __forceinline__ float recv_sum(int comp, int j) const {
@@ -585,7 +639,7 @@ __device__ void Engine::init() {
       const int r = q - mt.tlw[l], oo = r / mt.din[l], ii = r - oo * mt.din[l];
       pp = mt.woff[l] + oo * mt.ldw[l] + ii;
     } else {
-      pp = mt.boff[l] + (q - mt.tlb[l]);
+      pp = mt.boff[l] + (q - mt.tlb[l]) * mt.ldw[l];
     }
     pot[q] = pp;
     top[pp] = q;
@@ -598,7 +652,12 @@ __device__ void Engine::init() {
       const int m = i / D, c = i - m * D;
       F(ly.su)[m * ld0 + c] = __ldg(p.u + i);
     }
-    for (int m = tid; m < p.M; m += NT) I(ly.sz)[m] = __ldg(p.z + m);
+    for (int m = tid; m < p.M; m += NT) {
+      I(ly.sz)[m] = __ldg(p.z + m);
+      F(ly.su)[m * ld0 + D] = 1.f;  // constant-one slot (multiplies the bias column)
+    }
+    for (int l = 1; l < p.L; ++l)
+      for (int rr = tid; rr < p.RC; rr += NT) F(ly.act[l])[rr * mt.lda[l] + p.dims[l]] = 1.f;
   }
   __syncthreads();
   refresh_sigma();
@@ -741,7 +800,7 @@ __device__ void Engine::run() {
     const float dscale = p.Nf / (float)p.Btot;
     // O1: per-sample p_s, d_s, nkl_s
     for (int s = rank; s < p.S; s += G) {
-      float nkl = sample_theta(s, slab, false, 0.f);
+      float nkl = sample_theta(s, slab, false, 0.f, true);
       float ps = 0.f, ds = 0.f;
       for (int r0 = 0; r0 < R;) {
         const int lim = r0 < p.M ? p.M : R;
@@ -795,7 +854,7 @@ __device__ void Engine::run() {
         F(ly.gp)[s] = (float)(-(double)p.kappa * w - beta);                    // dLoss/dp_s
         bsum += beta;
       }
-      F(ly.red)[40] = (float)bsum;
+      F(ly.red)[60] = (float)bsum;
       const float lossv = (float)(ebar - (double)p.kappa * lwm);
       if (rank == 0) {
         if (p.loss_out) p.loss_out[0] = lossv;
@@ -815,7 +874,7 @@ __device__ void Engine::run() {
       }
     }
     __syncthreads();
-    const float beta_sum = F(ly.red)[40];
+    const float beta_sum = F(ly.red)[60];
     // O3: backward with per-sample row weights
     for (int s = rank; s < p.S; s += G) {
       const float beta = F(ly.beta)[s], gp = F(ly.gp)[s], wd = F(ly.w)[s] * dscale;
@@ -1007,7 +1066,7 @@ __device__ void Engine::eval_weights() {
   const int slab_local = blockIdx.x;
   const int slab = p.first_slab + slab_local;
   for (int s = 0; s < p.S; ++s) {
-    float nkl = sample_theta(s, slab, false, 0.f);
+    float nkl = sample_theta(s, slab, false, 0.f, true);
     float ps = 0.f;
     for (int r0 = 0; r0 < p.M; r0 += p.RC) {
       const int nr = min(p.RC, p.M - r0);
@@ -1117,7 +1176,7 @@ __device__ void Engine::forward_rows() {
   const int row_begin = chunk * p.RC;
   const int nr = min(p.RC, p.n_rows - row_begin);
   const int C = p.dims[p.L], ld = mt.lda[p.L];
-  float nkl = sample_theta(s, 0, false, 0.f);
+  float nkl = sample_theta(s, 0, false, 0.f, p.nkl_out != nullptr);
   if (chunk == 0) {
     if (p.nkl_out) {
       nkl = block_sum(nkl, F(ly.red));

@@ -33,6 +33,17 @@ class Noise(C.Structure):
 
 
 _lib = None
+_LAUNCHES = 0      # kernels of libpsvi_b200 launched by this process (bench.py reports it as gpu_launches)
+EVENT_HOOK = None  # (start_event, end_event, stream): bench.py brackets the dominant kernel with CUDA events
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def _count(n):
+    global _LAUNCHES
+    _LAUNCHES += n
 
 _SIGS = {
     "psvi_last_error": (C.c_char_p, []),
@@ -163,13 +174,20 @@ def gout_floats(model, M):
 def nested_step(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, alpha, T, lr, pseudo_scale, phase_mask,
                 traj, gout, u_grad, v_grad, alpha_grad, loss_out, inner_losses):
     B = 0 if xb is None else xb.shape[0]
+    _count(1)
+    hook = EVENT_HOOK
+    if hook is not None:
+        hook[0].record(hook[2])
     _check(lib().psvi_mf_nested_step(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
                                      u.shape[0], _p(xb), _p(yb, torch.int32), B, n_total_rows, N, vmode, alpha, T, lr,
                                      pseudo_scale, phase_mask, _p(traj), _p(gout), _p(u_grad), _p(v_grad),
                                      _p(alpha_grad), _p(loss_out), _p(inner_losses), _stream()))
+    if hook is not None:
+        hook[1].record(hook[2])
 
 
 def unroll(model, noise, mu, rho, adam_m, adam_v, step0, x, y, row_weights, v, N, vmode, alpha, T, lr, adam_mode, losses):
+    _count(1)
     _check(lib().psvi_mf_unroll(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(adam_m), _p(adam_v), step0, _p(x),
                                 _p(y, torch.int32), _p(row_weights), _p(v), x.shape[0], N, vmode, alpha, T, lr,
                                 adam_mode, _p(losses), _stream()))
@@ -178,6 +196,7 @@ def unroll(model, noise, mu, rho, adam_m, adam_v, step0, x, y, row_weights, v, N
 def outer_grad(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, alpha, pseudo_scale, gout, u_grad, v_grad,
                alpha_grad, loss_out):
     B = 0 if xb is None else xb.shape[0]
+    _count(1)
     _check(lib().psvi_mf_outer_grad(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
                                     u.shape[0], _p(xb), _p(yb, torch.int32), B, n_total_rows, N, vmode, alpha,
                                     pseudo_scale, _p(gout), _p(u_grad), _p(v_grad), _p(alpha_grad), _p(loss_out),
@@ -185,11 +204,13 @@ def outer_grad(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, a
 
 
 def inner_grad(model, noise, mu, rho, u, z, v, N, vmode, alpha, grad, value):
+    _count(1)
     _check(lib().psvi_mf_inner_grad(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
                                     u.shape[0], N, vmode, alpha, _p(grad), _p(value), _stream()))
 
 
 def inner_hvp(model, noise, mu, rho, u, z, v, N, vmode, alpha, gdot, h_phi, h_u, h_v, h_alpha=None):
+    _count(1)
     _check(lib().psvi_mf_inner_hvp(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
                                    u.shape[0], N, vmode, alpha, _p(gdot), _p(h_phi), _p(h_u), _p(h_v), _p(h_alpha),
                                    _stream()))
@@ -201,16 +222,19 @@ def eval_scratch_floats(model, n_rows, batch):
 
 def evaluate(model, noise, mu, rho, u, z, v, xt, yt, batch, first_slab, N, vmode, alpha, mode, out, scratch):
     M = 0 if u is None else u.shape[0]
+    _count(3 if mode == 0 else 2)
     _check(lib().psvi_mf_evaluate(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
                                   _p(xt), _p(yt, torch.int32), xt.shape[0], batch, first_slab, N, vmode, alpha, mode,
                                   _p(out), _p(scratch), _stream()))
 
 
 def philox_normal(seed, domain, first_slab, n_slabs, S, P, out):
+    _count(1)
     _check(lib().psvi_philox_normal(int(seed) & (2**64 - 1), int(domain) & 0xFFFFFFFF, first_slab, n_slabs, S, P,
                                     _p(out), _stream()))
 
 
 def forward(model, noise, mu, rho, x, logits, theta_out=None, nkl_out=None, kl_out=None):
+    _count(1)
     _check(lib().psvi_mf_forward(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x), x.shape[0], _p(logits),
                                  _p(theta_out), _p(nkl_out), _p(kl_out), _stream()))

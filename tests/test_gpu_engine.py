@@ -73,7 +73,8 @@ def test_outer_grad(nat, name):
     assert np.all(np.abs(go[2 * P + M * D:2 * P + M * D + M] - ga) <= tol_u * np.abs(ga) + atol)
     np.testing.assert_allclose(go[2 * P + M * D + M:2 * P + M * D + M + S], parts["ds"], rtol=5e-5)
     gv = po.coreset_weights_vjp(g["v0"], N, vmode, ga)[0]
-    assert rel_l2(vg.cpu().numpy(), gv) < max(5e-4, 2 * floor)
+    fmax = po.softmax(g["v0"], 0).max() if vmode else 1.0
+    assert np.all(np.abs(vg.cpu().numpy() - gv) <= max(5e-4, tol_u) * np.abs(gv) + 2 * N * fmax * atol.max())
     assert rel_l2(ug.cpu().numpy(), g["ref64_outer_gu"]) < tol_u
 
 
