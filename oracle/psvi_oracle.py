@@ -294,17 +294,24 @@ def psvi_elbo(mu, rho, eps, u, z, a, xb, yb, N, dims):
     return psvi_elbo_parts(mu, rho, eps, u, z, a, xb, yb, N, dims)[0]
 
 
-def psvi_elbo_grad(mu, rho, eps, u, z, a, xb, yb, N, dims):
-    """value, d/dmu, d/drho, d/du, d/da of psvi_elbo (SURVEY A.2 closed forms)."""
+def psvi_elbo_grad(mu, rho, eps, u, z, a, xb, yb, N, dims, kappa=1.0, n_total_rows=None):
+    """value, d/dmu, d/drho, d/du, d/da of psvi_elbo (SURVEY A.2 closed forms).
+    kappa / n_total_rows describe one rank's share when the minibatch rows are sharded over R ranks:
+    L_r = sum_s w_s (d_s^r - kappa p_s) - kappa mean(lw) with kappa = 1/R and d_s^r = (N / n_total_rows) sum over the
+    rank's rows; the shares (values and gradients) sum to the unsharded objective because w is rank-independent."""
     loss, t = psvi_elbo_parts(mu, rho, eps, u, z, a, xb, yb, N, dims)
     S = eps.shape[0]
     M, B = u.shape[0], xb.shape[0]
-    w, e = t["w"], t["ds"] - t["ps"]
-    beta = w * (e - np.sum(w * e)) - 1.0 / S          # dLoss/dlw_s
-    gp = -w - beta                                      # dLoss/dp_s
+    if n_total_rows is not None:
+        t["ds"] = t["ds"] * (B / n_total_rows)
+    Btot = B if n_total_rows is None else n_total_rows
+    w, e = t["w"], t["ds"] - kappa * t["ps"]
+    loss = np.sum(w * e) - kappa * t["lw"].mean()
+    beta = w * (e - np.sum(w * e)) - kappa / S        # dLoss/dlw_s
+    gp = -kappa * w - beta                              # dLoss/dp_s
     q = t["p"].copy()
     np.add.at(q, (slice(None), np.arange(M + B), t["lab"].astype(np.int64)), -1.0)
-    rw = np.concatenate([gp[:, None] * a[None, :], np.broadcast_to((w * N / B)[:, None], (S, B))], 1)  # [S,R]
+    rw = np.concatenate([gp[:, None] * a[None, :], np.broadcast_to((w * N / Btot)[:, None], (S, B))], 1)  # [S,R]
     obar = rw[:, :, None] * q
     tb, xbar = mlp_backward(t["theta"], t["cache"], dims, obar)
     tb = tb - beta[:, None] * t["theta"]               # d nkl_s / d theta = -theta
