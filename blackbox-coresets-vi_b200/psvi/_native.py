@@ -76,6 +76,11 @@ _SIGS = {
                                    C.c_void_p]),
     "psvi_mf_forward": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_lr_predictive_tc_scratch_bytes": (C.c_size_t, [C.POINTER(MfModel)]),
+    "psvi_lr_predictive_tc": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -238,3 +243,20 @@ def forward(model, noise, mu, rho, x, logits, theta_out=None, nkl_out=None, kl_o
     _count(1)
     _check(lib().psvi_mf_forward(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x), x.shape[0], _p(logits),
                                  _p(theta_out), _p(nkl_out), _p(kl_out), _stream()))
+
+
+def lr_predictive_tc_scratch_floats(model):
+    return (int(lib().psvi_lr_predictive_tc_scratch_bytes(C.byref(model))) + 3) // 4
+
+
+def lr_predictive_tc(model, noise, mu, rho, u, z, v, xt_bf16, yt, slab, N, vmode, alpha, mode, out, scratch):
+    M = 0 if u is None else u.shape[0]
+    _count(6 if mode == 0 else 3)
+    _check(lib().psvi_lr_predictive_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
+                                       _p(xt_bf16, torch.bfloat16), _p(yt, torch.int32), xt_bf16.shape[0], slab, N, vmode,
+                                       alpha, mode, _p(out), _p(scratch), _stream()))
+
+
+def f32_to_bf16(src, dst):
+    _count(1)
+    _check(lib().psvi_f32_to_bf16(_p(src), _p(dst, torch.bfloat16), src.numel(), _stream()))

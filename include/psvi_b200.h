@@ -169,6 +169,21 @@ int psvi_mf_forward(const psvi_mf_model* model, const psvi_noise* noise, const f
                     const float* x, int32_t n_rows, float* logits, float* theta_out, float* nkl_out, float* kl_out,
                     void* stream);
 
+/* ---- tensor-core full-data predictive pass for the single-layer model (logistic_regression): the HBM-bound member of
+ * the predictive kernels.  Same quantities as psvi_mf_evaluate (PSVI.evaluate,
+ * psvi_classes.py:1031-1108) for ONE noise slab over all n_rows (the reference with data_minibatch >= n_rows), computed
+ * with bf16 operands / fp32 accumulation: TMA-streamed row tiles, tcgen05.mma into TMEM, fused softmax / mixture / NLL.
+ *   xt_bf16 [n_rows][D] bf16 row-major (16-byte aligned; D a multiple of 64, <= 256), yt [n_rows] int32,
+ *   needs C <= 16 and S <= 16;  mode 0: importance weighted, 1: uniform mean of softmax.
+ *   out [8] as psvi_mf_evaluate;  scratch: psvi_lr_predictive_tc_scratch_bytes() bytes. */
+size_t psvi_lr_predictive_tc_scratch_bytes(const psvi_mf_model* model);
+int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                          const float* u, const int32_t* z, const float* v, int32_t M, const void* xt_bf16,
+                          const int32_t* yt, int64_t n_rows, int32_t slab, float N, int32_t vmode, float alpha,
+                          int32_t mode, float* out, void* scratch, void* stream);
+/* fp32 -> bf16 (round to nearest even) copy of a row matrix, for callers that keep fp32 masters. */
+int psvi_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,
