@@ -16,6 +16,11 @@
 
 #include "psvi_common.cuh"
 
+// defined in psvi_mf_engine.cu (internal, not part of the C ABI)
+int psvi_internal_eval_logweights(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                                  const float* u, const int32_t* z, const float* v, int32_t M, int32_t slab, float N,
+                                  int32_t vmode, float alpha, float* lw, cudaStream_t stream);
+
 namespace {
 
 constexpr int BM = 128;      // rows per tile (UMMA M)
@@ -31,7 +36,7 @@ struct TcParams {
   int mode;                              // 0 importance weighted, 1 uniform weights
   int stages;                            // A-operand pipeline depth actually used (2..STAGES)
   const float* bias;                     // [NP]
-  const float* wts;                      // [S]
+  const float* wts;                      // [S] LOG importance weights (mode 0)
   const int* labels;                     // [n_rows]
   float* part;                           // [grid][4]
 };
@@ -137,7 +142,14 @@ psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.NP; i += TC_THREADS) s_bias[i] = p.bias[i] * 1.4426950408889634f;  // log2(e) folded in
-  if (threadIdx.x < 16) s_w[threadIdx.x] = threadIdx.x < p.S ? (p.mode == 0 ? p.wts[threadIdx.x] : 1.f / (float)p.S) : 0.f;
+  if (threadIdx.x == 0) {  // importance weights: softmax over the S log-weights (mode 0) or uniform
+    float mx = -INFINITY, se = 0.f;
+    if (p.mode == 0) {
+      for (int s = 0; s < p.S; ++s) mx = fmaxf(mx, p.wts[s]);
+      for (int s = 0; s < p.S; ++s) se += expf(p.wts[s] - mx);
+    }
+    for (int s = 0; s < 16; ++s) s_w[s] = s < p.S ? (p.mode == 0 ? expf(p.wts[s] - mx) / se : 1.f / (float)p.S) : 0.f;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(bfull, 1);
@@ -332,18 +344,32 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
     dst[i] = __float2bfloat16(src[i]);
 }
 
-__global__ void tc_reduce_kernel(const float* part, int n, float* out) {
+__global__ void tc_reduce_kernel(const float* part, int n, float* out, const float* lw, int S) {
   __shared__ double acc[3][256];
   double a = 0, b = 0, c = 0;
   for (int i = threadIdx.x; i < n; i += 256) { a += part[4 * i]; b += part[4 * i + 1]; c += part[4 * i + 2]; }
   acc[0][threadIdx.x] = a; acc[1][threadIdx.x] = b; acc[2][threadIdx.x] = c;
   __syncthreads();
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     for (int k = 0; k < 3; ++k) {
       double t = 0;
       for (int i = 0; i < 256; ++i) t += acc[k][i];
       out[k] = (float)t;
     }
+    if (lw) {  // importance-weight entropy and normalised ESS (psvi_classes.py:1085-1092)
+      float mx = -INFINITY, se = 0.f, ent = 0.f, sw = 0.f, sw2 = 0.f;
+      for (int s = 0; s < S; ++s) mx = fmaxf(mx, lw[s]);
+      for (int s = 0; s < S; ++s) se += expf(lw[s] - mx);
+      for (int s = 0; s < S; ++s) {
+        const float w = expf(lw[s] - mx) / se;
+        if (w > 0.f) ent -= logf(w) * w;
+        sw += w;
+        sw2 += w * w;
+      }
+      out[3] = ent;
+      out[4] = sw * sw / sw2 / (float)S;
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -409,18 +435,11 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
   float* bias = reinterpret_cast<float*>(sc + (size_t)NP * D * 2);
   float* wts = bias + NP;
   float* part = wts + 64;
-  float* eval_scratch = part + 148 * 4 + 64;
-  // 1. importance weights of this slab from the pseudo-data forward (fp32, the shared-memory engine's E1 kernel)
+  // 1. log importance weights of this slab from the pseudo-data forward (fp32, one CTA per sample)
   if (mode == 0) {
     PSVI_REQUIRE(u && z && v && M > 0, PSVI_ERR_INVALID, "importance-weighted mode needs pseudo-data");
-    psvi_noise n1 = *noise;
-    // psvi_mf_evaluate on a single dummy row of slab `slab`: its first stage leaves w_s in the scratch head
-    float dummy_out_unused[1];
-    (void)dummy_out_unused;
-    int rc = psvi_mf_evaluate(model, &n1, mu, rho, u, z, v, M, mu /*any D floats*/, yt, 1, 1, slab, N, vmode, alpha, 0,
-                              out, eval_scratch, stream_);
+    int rc = psvi_internal_eval_logweights(model, noise, mu, rho, u, z, v, M, slab, N, vmode, alpha, wts, stream);
     if (rc) return rc;
-    PSVI_CUDA_CHECK(cudaMemcpyAsync(wts, eval_scratch, S * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   // 2. stacked sampled weights in bf16
   lr_prep_kernel<<<(NP * D + 255) / 256, 256, 0, stream>>>(mu, rho, *noise, slab, S, C, D, Wb, bias);
@@ -460,8 +479,8 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
   else PSVI_TC_LAUNCH(16);
 #undef PSVI_TC_LAUNCH
   PSVI_CUDA_CHECK(cudaGetLastError());
-  // 4. fixed-order reduction; out[3], out[4] (weight diagnostics) were written by step 1
-  tc_reduce_kernel<<<1, 256, 0, stream>>>(part, grid, out);
+  // 4. fixed-order reduction + weight diagnostics
+  tc_reduce_kernel<<<1, 256, 0, stream>>>(part, grid, out, mode == 0 ? wts : nullptr, S);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

@@ -81,7 +81,7 @@ struct EP {
   float* h_phi;
   // predictive pass
   int n_rows, batch, first_slab, eval_mode, n_slabs, chunks_per_slab;
-  float* eval_w;     // [n_slabs][S] importance weights
+  float* eval_w;     // [n_slabs][S] LOG importance weights (softmax-ed by the consumers)
   float* eval_part;  // [n_ctas][4] per-CTA partial sums
   float* eval_out;   // [8]
   // plain forward
@@ -1059,48 +1059,27 @@ __device__ void Engine::run() {
 // =================================================================================================================
 // Predictive pass (PSVI.evaluate, psvi_classes.py:1031-1108; run_mfvi_subset test loop, baselines.py:1035-1043)
 // =================================================================================================================
-// E1: one CTA per noise slab (= test batch): importance weights w_s = softmax_s(+sum_m a_m log p(z_m|theta_s)... )
+// E1: one CTA per (noise slab, MC sample): the log importance weight  lw_s = sum_m a_m nll[s,m] + nkl_s.
 // NB the reference's sign quirk Q3: log_weights = -(+sum_m a_m log p) + nkl = (sum_m a_m nll) + nkl.
+// The consumers (E2, the tensor-core kernel) turn the S log-weights of a slab into softmax weights in their prologue.
 __device__ void Engine::eval_weights() {
   init();
-  const int slab_local = blockIdx.x;
+  const int slab_local = blockIdx.x / p.S, s = blockIdx.x - slab_local * p.S;
   const int slab = p.first_slab + slab_local;
-  for (int s = 0; s < p.S; ++s) {
-    float nkl = sample_theta(s, slab, false, 0.f, true);
-    float ps = 0.f;
-    for (int r0 = 0; r0 < p.M; r0 += p.RC) {
-      const int nr = min(p.RC, p.M - r0);
-      const float* a0 = stage_rows(r0, nr);
-      __syncthreads();
-      forward(a0, nr, false);
-      loss_stage(nr, 0, r0);
-      for (int rr = tid; rr < nr; rr += NT) ps += F(ly.a)[r0 + rr] * F(ly.nll)[rr];
-      __syncthreads();
-    }
-    nkl = block_sum(nkl, F(ly.red));
-    ps = block_sum(ps, F(ly.red));
-    if (tid == 0) F(ly.lw)[s] = ps + nkl;
+  float nkl = sample_theta(s, slab, false, 0.f, true);
+  float ps = 0.f;
+  for (int r0 = 0; r0 < p.M; r0 += p.RC) {
+    const int nr = min(p.RC, p.M - r0);
+    const float* a0 = stage_rows(r0, nr);
+    __syncthreads();
+    forward(a0, nr, false);
+    loss_stage(nr, 0, r0);
+    for (int rr = tid; rr < nr; rr += NT) ps += F(ly.a)[r0 + rr] * F(ly.nll)[rr];
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid == 0) {
-    const int S = p.S;
-    float mx = -INFINITY;
-    for (int s = 0; s < S; ++s) mx = fmaxf(mx, F(ly.lw)[s]);
-    float se = 0.f;
-    for (int s = 0; s < S; ++s) se += expf(F(ly.lw)[s] - mx);
-    float ent = 0.f, sw = 0.f, sw2 = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float w = expf(F(ly.lw)[s] - mx) / se;
-      p.eval_w[(size_t)slab_local * S + s] = w;
-      if (w > 0.f) ent -= logf(w) * w;
-      sw += w;
-      sw2 += w * w;
-    }
-    if (slab_local == p.n_slabs - 1) {  // Q12: diagnostics of the LAST batch only
-      p.eval_out[3] = ent;
-      p.eval_out[4] = sw * sw / sw2 / (float)S;
-    }
-  }
+  nkl = block_sum(nkl, F(ly.red));
+  ps = block_sum(ps, F(ly.red));
+  if (tid == 0) p.eval_w[(size_t)slab_local * p.S + s] = ps + nkl;
 }
 
 // E2: one CTA per chunk of test rows; loops over the S samples (re-drawing the slab's noise) and accumulates the
@@ -1114,6 +1093,17 @@ __device__ void Engine::eval_rows() {
   const int nr = min(p.RC, slab_end - row_begin);
   const int C = p.dims[p.L], ld = mt.lda[p.L];
   float nll_sum = 0.f, correct = 0.f;
+  if (p.eval_mode == 0) {  // importance weights of this slab: softmax over the S log-weights of E1
+    if (tid == 0) {
+      const float* lw = p.eval_w + (size_t)slab_local * p.S;
+      float mx = -INFINITY;
+      for (int s = 0; s < p.S; ++s) mx = fmaxf(mx, lw[s]);
+      float se = 0.f;
+      for (int s = 0; s < p.S; ++s) se += expf(lw[s] - mx);
+      for (int s = 0; s < p.S; ++s) F(ly.w)[s] = expf(lw[s] - mx) / se;
+    }
+    __syncthreads();
+  }
   if (nr > 0) {
     float* probs = F(ly.adj[p.L]);  // zeroed by init()
     const float* a0 = stage_rows(p.M + row_begin, nr);
@@ -1121,7 +1111,7 @@ __device__ void Engine::eval_rows() {
     for (int s = 0; s < p.S; ++s) {
       sample_theta(s, slab, false, 0.f);
       forward(a0, nr, false);
-      const float wgt = p.eval_mode == 0 ? p.eval_w[(size_t)slab_local * p.S + s] : 1.f / (float)p.S;
+      const float wgt = p.eval_mode == 0 ? F(ly.w)[s] : 1.f / (float)p.S;
       const float* o = F(ly.act[p.L]);
       for (int rr = tid; rr < nr; rr += NT) {
         const float* row = o + rr * ld;
@@ -1265,8 +1255,9 @@ __global__ void __launch_bounds__(NT, 1) psvi_mf_forward_kernel(const __grid_con
   e.forward_rows();
 }
 
-// fixed-order final reduction of the per-CTA partials (deterministic, no atomics)
-__global__ void psvi_mf_eval_reduce_kernel(const float* part, int n, float* out) {
+// fixed-order final reduction of the per-CTA partials (deterministic, no atomics); also the importance-weight
+// diagnostics of the LAST slab (Q12): entropy -sum w log w and normalised ESS (psvi_classes.py:1085-1092)
+__global__ void psvi_mf_eval_reduce_kernel(const float* part, int n, float* out, const float* lw_last, int S) {
   __shared__ double acc[3][NT];
   double a = 0, b = 0, c = 0;
   for (int i = threadIdx.x; i < n; i += NT) {
@@ -1281,6 +1272,21 @@ __global__ void psvi_mf_eval_reduce_kernel(const float* part, int n, float* out)
       double t = 0;
       for (int i = 0; i < NT; ++i) t += acc[k][i];
       out[k] = (float)t;
+    }
+    if (lw_last) {
+      float mx = -INFINITY;
+      for (int s = 0; s < S; ++s) mx = fmaxf(mx, lw_last[s]);
+      float se = 0.f;
+      for (int s = 0; s < S; ++s) se += expf(lw_last[s] - mx);
+      float ent = 0.f, sw = 0.f, sw2 = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const float w = expf(lw_last[s] - mx) / se;
+        if (w > 0.f) ent -= logf(w) * w;
+        sw += w;
+        sw2 += w * w;
+      }
+      out[3] = ent;
+      out[4] = sw * sw / sw2 / (float)S;
     }
   }
 }
@@ -1404,6 +1410,46 @@ int check_noise(const psvi_noise* noise) {
 }
 
 }  // namespace
+
+// Internal (not part of the C ABI): log importance weights lw[S] of one noise slab, used by psvi_lr_tc.cu.
+int psvi_internal_eval_logweights(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                                  const float* u, const int32_t* z, const float* v, int32_t M, int32_t slab, float N,
+                                  int32_t vmode, float alpha, float* lw, cudaStream_t stream) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  rc = check_noise(noise);
+  if (rc) return rc;
+  EP p;
+  fill_common(p, model, noise, M, N, vmode, alpha);
+  p.mu = const_cast<float*>(mu); p.rho = const_cast<float*>(rho);
+  p.u = u; p.z = z; p.v = v;
+  p.n_rows = 1; p.batch = 1; p.first_slab = slab; p.eval_mode = 0; p.n_slabs = 1;
+  p.eval_w = lw;
+  p.G = 1; p.flags = F_EVAL;
+  int dev = 0, smem_max = 0;
+  PSVI_CUDA_CHECK(cudaGetDevice(&dev));
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  Meta mt;
+  make_meta(p.dims, p.L, mt);
+  p.slice = mt.Pp;
+  const size_t budget = (size_t)smem_max - 2048;
+  Lay ly;
+  int lo = 0, hi = M < 256 ? M : 256;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    p.RC = mid;
+    make_layout(p, mt, ly);
+    if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+  }
+  PSVI_REQUIRE(lo >= 1, PSVI_ERR_UNSUPPORTED, "model too large for the shared-memory-resident importance-weight kernel");
+  p.RC = lo;
+  make_layout(p, mt, ly);
+  const size_t smem = (size_t)ly.total * 4;
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_eval_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psvi_mf_eval_weights_kernel<<<p.S, NT, smem, stream>>>(p);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
 
 // ================================================================================================================
 extern "C" {
@@ -1603,13 +1649,14 @@ int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise, const 
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_eval_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_eval_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (mode == 0) {
-    psvi_mf_eval_weights_kernel<<<p.n_slabs, NT, smem, stream>>>(p);
+    psvi_mf_eval_weights_kernel<<<p.n_slabs * p.S, NT, smem, stream>>>(p);
     PSVI_CUDA_CHECK(cudaGetLastError());
   }
   const int nctas = p.n_slabs * p.chunks_per_slab;
   psvi_mf_eval_rows_kernel<<<nctas, NT, smem, stream>>>(p);
   PSVI_CUDA_CHECK(cudaGetLastError());
-  psvi_mf_eval_reduce_kernel<<<1, NT, 0, stream>>>(p.eval_part, nctas, out);
+  psvi_mf_eval_reduce_kernel<<<1, NT, 0, stream>>>(p.eval_part, nctas, out,
+                                                    mode == 0 ? p.eval_w + (size_t)(p.n_slabs - 1) * p.S : nullptr, p.S);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

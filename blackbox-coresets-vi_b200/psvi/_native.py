@@ -251,7 +251,7 @@ def lr_predictive_tc_scratch_floats(model):
 
 def lr_predictive_tc(model, noise, mu, rho, u, z, v, xt_bf16, yt, slab, N, vmode, alpha, mode, out, scratch):
     M = 0 if u is None else u.shape[0]
-    _count(6 if mode == 0 else 3)
+    _count(4 if mode == 0 else 3)
     _check(lib().psvi_lr_predictive_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
                                        _p(xt_bf16, torch.bfloat16), _p(yt, torch.int32), xt_bf16.shape[0], slab, N, vmode,
                                        alpha, mode, _p(out), _p(scratch), _stream()))
