@@ -442,12 +442,26 @@ class PSVI(object):
         lo, hi = shard_bounds(n_slabs, rank, world)
         if hi > lo:
             r0, r1 = lo * batch, min(hi * batch, n)
-            scratch = self._buf("eval", _native.eval_scratch_floats(desc, r1 - r0, batch))
             if noise.mode == _native.NOISE_EXTERNAL and lo > 0:   # external slabs are indexed from this rank's first
                 noise = _native.make_noise(noise._keepalive[lo:hi].contiguous())
-            _native.evaluate(desc, noise, mu, rho, u, self._z32(), v, xt[r0:r1], yt[r0:r1], batch,
-                             0 if noise.mode == _native.NOISE_EXTERNAL else lo, float(self.N), self._vmode,
-                             self._alpha_value(), 0 if correction else 1, out, scratch)
+            first = 0 if noise.mode == _native.NOISE_EXTERNAL else lo
+            if self._use_tensor_core_eval(model, r1 - r0, batch):
+                # large single-layer case: TMA + tcgen05 kernel, bf16 operands; one launch set per slab
+                xb16 = self._device_bf16(xt, "test")
+                scratch = self._buf("eval_tc", _native.lr_predictive_tc_scratch_floats(desc))
+                acc = torch.zeros(8, device=self.device)
+                for k in range(hi - lo):
+                    a0, a1 = r0 + k * batch, min(r0 + (k + 1) * batch, r1)
+                    _native.lr_predictive_tc(desc, noise, mu, rho, u, self._z32(), v, xb16[a0:a1], yt[a0:a1], first + k,
+                                             float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1,
+                                             out, scratch)
+                    acc[:3] += out[:3]
+                acc[3:5] = out[3:5]
+                out = acc
+            else:
+                scratch = self._buf("eval", _native.eval_scratch_floats(desc, r1 - r0, batch))
+                _native.evaluate(desc, noise, mu, rho, u, self._z32(), v, xt[r0:r1], yt[r0:r1], batch, first,
+                                 float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1, out, scratch)
             if hi != n_slabs:
                 out[3:5] = 0.0   # Q12: the weight diagnostics are those of the globally last batch
         if dist is not None:
@@ -455,6 +469,28 @@ class PSVI(object):
         vs = self.f(self.v.detach(), 0)
         v_entropy = vs.sum().square() / vs.square().sum() / self.num_pseudo if self.compute_weights_entropy else None
         return (out[1] / out[2], out[0] / out[2], out[3] if self.compute_weights_entropy else None, out[4], v_entropy)
+
+    tensor_core_eval = "auto"   # "auto": use the tcgen05 predictive kernel for >= 64k-row slabs; True / False force it
+
+    def _use_tensor_core_eval(self, model, rows, batch):
+        dims = model.dims
+        fits = (len(dims) == 2 and dims[0] % 64 == 0 and 64 <= dims[0] <= 256 and dims[1] <= 16
+                and model.n_samples() <= 16)
+        if self.tensor_core_eval is True:
+            if not fits:
+                raise NotImplementedError("tensor-core predictive kernel: needs a single-layer model, D % 64 == 0, "
+                                          "D <= 256, C <= 16, S <= 16")
+            return True
+        return bool(fits and self.tensor_core_eval == "auto" and min(rows, batch) >= 65536)
+
+    def _device_bf16(self, x, key):
+        c = self._dev_data.get(key + "_bf16")
+        if c is None or c[0] is not x:
+            xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+            _native.f32_to_bf16(x.contiguous(), xb)
+            c = (x, xb)
+            self._dev_data[key + "_bf16"] = c
+        return c[1]
 
     def weight_reset(self):
         """Reset variational parameters to initialisation (reference :1110-1128)."""
