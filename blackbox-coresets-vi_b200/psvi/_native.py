@@ -21,7 +21,10 @@ PHASE_UNROLL, PHASE_REVERSE = 1, 2
 
 
 class NativeError(RuntimeError):
-    pass
+    code = None
+
+
+ERR_UNSUPPORTED = -2
 
 
 class MfModel(C.Structure):
@@ -81,6 +84,13 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "psvi_mf_stream_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32]),
+    "psvi_mf_unroll_stream": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
+                                        C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_evaluate_stream": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -121,7 +131,9 @@ def last_error():
 
 def _check(rc):
     if rc != 0:
-        raise NativeError(f"libpsvi_b200 error {rc}: {last_error()}")
+        e = NativeError(f"libpsvi_b200 error {rc}: {last_error()}")
+        e.code = rc
+        raise e
 
 
 def make_model(dims, mc_samples):
@@ -191,11 +203,44 @@ def nested_step(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, 
         hook[1].record(hook[2])
 
 
+def coreset_weights(v, N, vmode, alpha):
+    """a = N f(v) on the device (host-side plumbing for the streaming entry points)."""
+    if vmode == VMODE_IDENTITY:
+        return (N * v).contiguous()
+    sc = N * (float(torch.exp(torch.tensor(alpha))) if vmode == VMODE_EXPALPHA_SOFTMAX else 1.0)
+    return (sc * torch.softmax(v, 0)).contiguous()
+
+
+_stream_ws = {}
+
+
+def _workspace(model, n_rows, device):
+    n = (int(lib().psvi_mf_stream_workspace_bytes(C.byref(model), n_rows)) + 3) // 4
+    key = (device, )
+    t = _stream_ws.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros(n, device=device, dtype=torch.float32)
+        _stream_ws[key] = t
+    return t
+
+
 def unroll(model, noise, mu, rho, adam_m, adam_v, step0, x, y, row_weights, v, N, vmode, alpha, T, lr, adam_mode, losses):
+    """psvi_mf_unroll; models too large for the shared-memory-resident engine go through psvi_mf_unroll_stream."""
     _count(1)
-    _check(lib().psvi_mf_unroll(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(adam_m), _p(adam_v), step0, _p(x),
-                                _p(y, torch.int32), _p(row_weights), _p(v), x.shape[0], N, vmode, alpha, T, lr,
-                                adam_mode, _p(losses), _stream()))
+    rc = lib().psvi_mf_unroll(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(adam_m), _p(adam_v), step0, _p(x),
+                              _p(y, torch.int32), _p(row_weights), _p(v), x.shape[0], N, vmode, alpha, T, lr,
+                              adam_mode, _p(losses), _stream())
+    if rc != ERR_UNSUPPORTED:
+        return _check(rc)
+    _count(4 * T - 1)
+    if row_weights is None:
+        row_weights = coreset_weights(v, N, vmode, alpha)
+    if adam_m is None:
+        adam_m, adam_v = torch.zeros(2 * mu.numel(), device=mu.device), torch.zeros(2 * mu.numel(), device=mu.device)
+    ws = _workspace(model, 0, mu.device)
+    _check(lib().psvi_mf_unroll_stream(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(adam_m), _p(adam_v), step0,
+                                       _p(x), _p(y, torch.int32), _p(row_weights), 0.0, x.shape[0], T, lr, adam_mode,
+                                       _p(losses), _p(ws), _stream()))
 
 
 def outer_grad(model, noise, mu, rho, u, z, v, xb, yb, n_total_rows, N, vmode, alpha, pseudo_scale, gout, u_grad, v_grad,
@@ -226,11 +271,19 @@ def eval_scratch_floats(model, n_rows, batch):
 
 
 def evaluate(model, noise, mu, rho, u, z, v, xt, yt, batch, first_slab, N, vmode, alpha, mode, out, scratch):
+    """psvi_mf_evaluate; models too large for the shared-memory-resident kernels go through psvi_mf_evaluate_stream."""
     M = 0 if u is None else u.shape[0]
     _count(3 if mode == 0 else 2)
-    _check(lib().psvi_mf_evaluate(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
-                                  _p(xt), _p(yt, torch.int32), xt.shape[0], batch, first_slab, N, vmode, alpha, mode,
-                                  _p(out), _p(scratch), _stream()))
+    rc = lib().psvi_mf_evaluate(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
+                                _p(xt), _p(yt, torch.int32), xt.shape[0], batch, first_slab, N, vmode, alpha, mode,
+                                _p(out), _p(scratch), _stream())
+    if rc != ERR_UNSUPPORTED:
+        return _check(rc)
+    a = coreset_weights(v, N, vmode, alpha) if mode == 0 else None
+    ws = _workspace(model, xt.shape[0], mu.device)
+    _check(lib().psvi_mf_evaluate_stream(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(a),
+                                         M, _p(xt), _p(yt, torch.int32), xt.shape[0], batch, first_slab, mode, _p(out),
+                                         _p(ws), _stream()))
 
 
 def philox_normal(seed, domain, first_slab, n_slabs, S, P, out):

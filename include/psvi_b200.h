@@ -169,6 +169,22 @@ int psvi_mf_forward(const psvi_mf_model* model, const psvi_noise* noise, const f
                     const float* x, int32_t n_rows, float* logits, float* theta_out, float* nkl_out, float* kl_out,
                     void* stream);
 
+/* ---- streaming ("medium regime") variants for models whose parameter vector does not fit the shared-memory-resident
+ * engine (psvi_mf_unroll / psvi_mf_evaluate return PSVI_ERR_UNSUPPORTED), e.g. the baselines' fn with two 100-unit hidden
+ * layers (experiments_utils.py:346-371: P = 10 602).  Same arithmetic, parameters in global memory, one CTA per MC
+ * sample; `workspace` of psvi_mf_stream_workspace_bytes(model, n_rows) bytes (n_rows = 0 for training only).
+ *   psvi_mf_unroll_stream: row weights either an array [M] or the scalar `row_weight_scalar`; adam_m/adam_v required.
+ *   psvi_mf_evaluate_stream: a_weights [M] = N f(v) (mode 0); out [8] as psvi_mf_evaluate (zeroed inside). */
+size_t psvi_mf_stream_workspace_bytes(const psvi_mf_model* model, int32_t n_rows);
+int psvi_mf_unroll_stream(const psvi_mf_model* model, const psvi_noise* noise, float* mu, float* rho, float* adam_m,
+                          float* adam_v, int32_t step0, const float* x, const int32_t* y, const float* row_weights,
+                          float row_weight_scalar, int32_t M, int32_t T, float lr, int32_t adam_mode, float* losses,
+                          void* workspace, void* stream);
+int psvi_mf_evaluate_stream(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                            const float* u, const int32_t* z, const float* a_weights, int32_t M, const float* xt,
+                            const int32_t* yt, int32_t n_rows, int32_t batch, int32_t first_slab, int32_t mode,
+                            float* out, void* workspace, void* stream);
+
 /* ---- tensor-core full-data predictive pass for the single-layer model (logistic_regression): the HBM-bound member of
  * the predictive kernels.  Same quantities as psvi_mf_evaluate (PSVI.evaluate,
  * psvi_classes.py:1031-1108) for ONE noise slab over all n_rows (the reference with data_minibatch >= n_rows), computed

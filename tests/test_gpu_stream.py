@@ -1,0 +1,102 @@
+"""Streaming ("medium regime") path: models whose parameters do not fit the shared-memory-resident engine -- here the
+baselines' fn with two 100-unit hidden layers (P = 10 602, experiments_utils.py:346-371) -- against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import psvi_oracle as po
+from tests.gpu_util import dev, rel_l2, zeros
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(dims, S, M, seed=0):
+    rng = np.random.default_rng(seed)
+    P = po.p_theta(dims)
+    mu = (0.2 * rng.standard_normal(P)).astype(np.float32)
+    rho = np.full(P, po.inverse_softplus(1e-2), np.float32)
+    x = rng.standard_normal((M, dims[0])).astype(np.float32)
+    y = rng.integers(0, dims[-1], M)
+    return rng, P, mu, rho, x, y
+
+
+@pytest.mark.parametrize("dims,S,M", [([2, 100, 100, 2], 10, 50), ([5, 64, 64, 64, 3], 4, 37)])
+def test_unroll_stream_matches_oracle(dims, S, M):
+    from psvi import _native as nat
+    nat.require_cuda()
+    rng, P, mu, rho, x, y = setup(dims, S, M)
+    T, lr, scale = 4, 1e-3, 16.0
+    eps = rng.standard_normal((T, S, P)).astype(np.float32)
+    model = nat.make_model(dims, S)
+    dmu, drho, am, av = dev(mu), dev(rho), zeros(2 * P), zeros(2 * P)
+    losses = zeros(T)
+    roww = torch.full((M,), scale, device="cuda")
+    # the engine must refuse this size, the binding then streams
+    rc = nat.lib().psvi_mf_unroll(__import__("ctypes").byref(model), __import__("ctypes").byref(nat.make_noise(dev(eps))),
+                                  dmu.data_ptr(), drho.data_ptr(), am.data_ptr(), av.data_ptr(), 0, dev(x).data_ptr(),
+                                  dev(y, torch.int32).data_ptr(), roww.data_ptr(), None, M, 1.0, 0, 0.0, 0, lr, 1, None, None)
+    assert rc == nat.ERR_UNSUPPORTED
+    nat.unroll(model, nat.make_noise(dev(eps)), dmu, drho, am, av, 0, dev(x), dev(y, torch.int32), roww, None, 1.0, 0, 0.0,
+               T, lr, nat.ADAM_TORCH, losses)
+    torch.cuda.synchronize()
+    m64, r64 = mu.astype(np.float64), rho.astype(np.float64)
+    m = np.zeros(2 * P); v = np.zeros(2 * P)
+    ref_losses = []
+    for t in range(T):
+        val, gmu, grho = po.mfvi_grad(m64, r64, eps[t].astype(np.float64), x.astype(np.float64), y, scale, dims)
+        phi, m, v = po.torch_adam_step(np.concatenate([m64, r64]), np.concatenate([gmu, grho]), m, v, t + 1, lr)
+        m64, r64 = phi[:P], phi[P:]
+        ref_losses.append(val)
+    np.testing.assert_allclose(losses.cpu().numpy(), ref_losses, rtol=5e-5)
+    assert rel_l2(dmu.cpu().numpy(), m64) < 1e-5
+    assert rel_l2(drho.cpu().numpy(), r64) < 1e-5
+    assert rel_l2(am.cpu().numpy(), m) < 2e-4
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_evaluate_stream_matches_oracle(mode):
+    from psvi import _native as nat
+    nat.require_cuda()
+    dims, S, M = [2, 100, 100, 2], 8, 20
+    rng, P, mu, rho, u, z = setup(dims, S, M, seed=3)
+    n_rows, batch, N = 300, 128, 800.0
+    nb = -(-n_rows // batch)
+    eps = rng.standard_normal((nb, S, P)).astype(np.float32)
+    xt = rng.standard_normal((n_rows, 2)).astype(np.float32)
+    yt = rng.integers(0, 2, n_rows)
+    v = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    model = nat.make_model(dims, S)
+    out = zeros(8)
+    scratch = zeros(nat.eval_scratch_floats(model, n_rows, batch))
+    nat.evaluate(model, nat.make_noise(dev(eps)), dev(mu), dev(rho), dev(u), dev(z, torch.int32), dev(v), dev(xt),
+                 dev(yt, torch.int32), batch, 0, N, 1, 0.0, mode, out, scratch)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    m64, r64 = mu.astype(np.float64), rho.astype(np.float64)
+    if mode == 0:
+        a = po.coreset_weights(v.astype(np.float64), N, 1)
+        acc, nll, went, ness = po.evaluate(m64, r64, eps.astype(np.float64), u.astype(np.float64), z, a,
+                                           xt.astype(np.float64), yt, dims, batch)
+        np.testing.assert_allclose([o[3], o[4]], [went, ness], rtol=2e-3, atol=1e-5)
+    else:
+        c = nl = 0.0
+        for k in range(nb):
+            ck, nk = po.mfvi_predict(m64, r64, eps[k].astype(np.float64), xt[k * batch:(k + 1) * batch].astype(np.float64),
+                                     yt[k * batch:(k + 1) * batch], dims)
+            c += ck; nl += nk
+        acc, nll = c / n_rows, nl / n_rows
+    assert o[2] == n_rows
+    assert abs(o[1] / o[2] - acc) <= 1.0 / n_rows + 1e-6
+    np.testing.assert_allclose(o[0] / o[2], nll, rtol=2e-4)
+
+
+def test_run_mfvi_subset_n_hidden_100():
+    """BASELINE config 2: mfvi_subset with --n_hidden 100 (two hidden layers in the baselines' set_up_model)."""
+    from psvi.experiments.experiments_utils import read_dataset
+    from psvi.inference.baselines import run_mfvi_subset
+    x, y, xt, yt, N, D, tr, te, nc = read_dataset("halfmoon", {"test_ratio": 0.2})
+    res = run_mfvi_subset(x=x, y=y, xt=xt, yt=yt, mc_samples=10, data_minibatch=128, num_epochs=150, log_every=100, D=D,
+                          lr0net=1e-2, seed=0, train_dataset=tr, test_dataset=te, num_pseudo=50, init_args="subsample",
+                          architecture="fn", n_hidden=100, nc=nc, dnm="halfmoon", init_sd=1e-3, quiet=True)
+    assert len(res["elbos"]) == 300 and len(res["accs"]) == 3
+    assert np.isfinite(res["nlls"]).all() and res["accs"][-1] > 0.8 and res["elbos"][-1] > res["elbos"][0]
