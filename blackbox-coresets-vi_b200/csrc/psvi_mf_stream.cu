@@ -36,6 +36,14 @@ struct SP {
   const int* y;          // [R]
   const float* roww;     // [R] row weights (nullable -> wscale)
   float wscale;
+  // generic per-sample pass (psvi_net_pass)
+  const float* thetad;   // [S][P] tangent weights (dual mode)
+  const float* cwm;      // [S][R] per-sample row weights
+  float* nll_out;        // [S][R]
+  float* tdbar;          // [S][P]
+  float* xbar;           // [S][R][D]
+  float* acbar;          // [S][R]
+  float* logits_out;     // [S][R][C] (forward mode)
   // predictive
   int n_rows, row0, eval_mode;
   const float* lw;       // [S] log importance weights (mode 0)
@@ -43,19 +51,22 @@ struct SP {
 };
 
 struct SLay {
-  int theta, lab, cw, nll, red, w;
-  int act[MAXL + 1], adj[MAXL + 1];
+  int theta, thetad, lab, cw, nll, red, w;
+  int act[MAXL + 1], adj[MAXL + 1], actd[MAXL + 1], adjd[MAXL + 1];
   int total;
 };
 
-__host__ __device__ inline void make_slay(const SP& p, const Meta& m, SLay& y, bool need_adj) {
+__host__ __device__ inline void make_slay(const SP& p, const Meta& m, SLay& y, bool need_adj, bool dual = false) {
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   y.theta = take(m.Pp);
+  y.thetad = dual ? take(m.Pp) : 0;
   y.lab = take(p.RC); y.cw = take(p.RC); y.nll = take(p.RC); y.red = take(64); y.w = take(32);
   for (int l = 0; l <= p.L; ++l) {
     y.act[l] = take(p.RC * m.lda[l]);
     y.adj[l] = (need_adj || l == p.L) ? take(p.RC * m.lda[l]) : 0;
+    y.actd[l] = dual ? take(p.RC * m.lda[l]) : 0;
+    y.adjd[l] = dual ? take(p.RC * m.lda[l]) : 0;
   }
   y.total = o;
 }
@@ -90,11 +101,11 @@ struct Worker {
   __device__ __forceinline__ int* I(int off) const { return reinterpret_cast<int*>(sm + off); }
 
   // sampled weights of sample s: TL (global) -> padded rows [W[o][0..din-1], b[o], pad]
-  __device__ void load_theta(int s) {
-    const float* src = p.theta + (size_t)s * mt.Pt;
+  __device__ void load_theta(int s) { load_weights(p.theta + (size_t)s * mt.Pt, ly.theta); }
+  __device__ void load_weights(const float* src, int dst_off) {
     for (int l = 1; l <= p.L; ++l) {
       const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l];
-      float* W = F(ly.theta) + mt.woff[l];
+      float* W = F(dst_off) + mt.woff[l];
       int oo = 0, ii = tid;
       while (ii >= din) { ii -= din; ++oo; }
       const int so = NT / din, si = NT - so * din;
@@ -182,6 +193,101 @@ struct Worker {
       __syncthreads();
     }
   }
+  // ---- dual (primal + tangent) machinery: SURVEY Appendix A.6, same structure as the cluster engine ----------------
+  __device__ void forward_dual(int nr) {
+    for (int l = 1; l <= p.L; ++l) {
+      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l], ldi = mt.lda[l - 1], ldo = mt.lda[l];
+      const float* in = F(ly.act[l - 1]);
+      const float* ind = F(ly.actd[l - 1]);
+      const float* W = F(ly.theta) + mt.woff[l];
+      const float* Wd = F(ly.thetad) + mt.woff[l];
+      float* out = F(ly.act[l]);
+      float* outd = F(ly.actd[l]);
+      const bool relu = l < p.L;
+      GemmOp op{in, ldi, 1, W, ldw, 1, nullptr, nullptr};
+      small_gemm(nr, dout, din + 1, op, [&](int rr, int oo, float acc) { out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc; });
+      GemmOp opd{in, ldi, 1, Wd, ldw, 1, l > 1 ? ind : nullptr, l > 1 ? W : nullptr};
+      small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) { outd[rr * ldo + oo] = acc; });
+      __syncthreads();
+      if (relu) {
+        for (int rr = 0; rr < nr; ++rr)
+          for (int oo = tid; oo < dout; oo += NT)
+            if (!(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
+        __syncthreads();
+      }
+    }
+  }
+  __device__ void loss_dual(int nr, float* ac_out) {
+    const int C = p.dims[p.L], ld = mt.lda[p.L];
+    const float* o = F(ly.act[p.L]);
+    const float* od = F(ly.actd[p.L]);
+    float* ao = F(ly.adj[p.L]);
+    float* aod = F(ly.adjd[p.L]);
+    for (int rr = tid; rr < nr; rr += NT) {
+      const float* row = o + rr * ld;
+      const float* rowd = od + rr * ld;
+      float mx = row[0];
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, row[c]);
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) se += expf(row[c] - mx);
+      const float lse = mx + logf(se);
+      const int y = I(ly.lab)[rr];
+      F(ly.nll)[rr] = lse - row[y];
+      const float w = F(ly.cw)[rr];
+      float pd = 0.f;
+      for (int c = 0; c < C; ++c) pd += expf(row[c] - lse) * rowd[c];
+      float ac = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float pc = expf(row[c] - lse), qc = pc - (c == y ? 1.f : 0.f);
+        aod[rr * ld + c] = w * qc;
+        ao[rr * ld + c] = w * pc * (rowd[c] - pd);
+        ac += qc * rowd[c];
+      }
+      if (ac_out) ac_out[rr] = ac;
+    }
+    __syncthreads();
+  }
+  // generic backward: dual=false -> tbar; dual=true -> tbar = A_theta, tdbar = A_thetadot; xbar rows (nullable)
+  __device__ void backward_any(int nr, bool dual, float* tbar, float* tdbar, float* xbar, bool first_chunk) {
+    for (int l = p.L; l >= 1; --l) {
+      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l], ldi = mt.lda[l - 1], ldo = mt.lda[l];
+      const float* in = F(ly.act[l - 1]);
+      const float* ind = F(ly.actd[l - 1]);
+      const float* A = F(ly.adj[l]);
+      const float* Ad = F(ly.adjd[l]);
+      const float* W = F(ly.theta) + mt.woff[l];
+      const float* Wd = F(ly.thetad) + mt.woff[l];
+      const bool has_ind = dual && l > 1;
+      const int tlw = mt.tlw[l], tlb = mt.tlb[l];
+      GemmOp ow{A, 1, ldo, in, 1, ldi, has_ind ? Ad : nullptr, has_ind ? ind : nullptr};
+      small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
+        float* dst = tbar + (ii < din ? tlw + oo * din + ii : tlb + oo);
+        *dst = first_chunk ? acc : *dst + acc;
+      });
+      if (dual) {
+        GemmOp owd{Ad, 1, ldo, in, 1, ldi, nullptr, nullptr};
+        small_gemm(dout, din + 1, nr, owd, [&](int oo, int ii, float acc) {
+          float* dst = tdbar + (ii < din ? tlw + oo * din + ii : tlb + oo);
+          *dst = first_chunk ? acc : *dst + acc;
+        });
+      }
+      if (l > 1 || xbar) {
+        GemmOp ox{A, ldo, 1, W, 1, ldw, dual ? Ad : nullptr, dual ? Wd : nullptr};
+        if (l > 1) {
+          float* Ai = F(ly.adj[l - 1]);
+          float* Aid = F(ly.adjd[l - 1]);
+          small_gemm(nr, din, dout, ox, [&](int rr, int ii, float acc) { Ai[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f; });
+          if (dual) {
+            GemmOp oxd{Ad, ldo, 1, W, 1, ldw, nullptr, nullptr};
+            small_gemm(nr, din, dout, oxd, [&](int rr, int ii, float acc) { Aid[rr * ldi + ii] = (in[rr * ldi + ii] > 0.f) ? acc : 0.f; });
+          }
+        } else {
+          small_gemm(nr, din, dout, ox, [&](int rr, int ii, float acc) { xbar[rr * din + ii] = acc; });
+        }
+      }
+      __syncthreads();
+    }
+  }
 };
 
 // ---- K2 ------------------------------------------------------------------------------------------------------------
@@ -208,6 +314,49 @@ __global__ void __launch_bounds__(NT, 1) fwdbwd_kernel(const __grid_constant__ S
   }
   part = block_sum(part, w.F(ly.red));
   if (threadIdx.x == 0) p.loss_part[s] = part;
+}
+
+
+// ---- generic per-sample pass on externally supplied weights (any variational family) ---------------------------------
+// mode 0: forward only (nll); 1: gradient; 2: dual (Hessian-vector) pass
+__global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__ SP p, int mode) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  __shared__ Meta mt;
+  __shared__ SLay ly;
+  if (threadIdx.x == 0) { make_meta(p.dims, p.L, mt); make_slay(p, mt, ly, mode > 0, mode == 2); }
+  __syncthreads();
+  Worker w(p, mt, ly, smem_dyn);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  w.init_ones();
+  w.load_theta(s);
+  if (mode == 2) { w.load_weights(p.thetad + (size_t)s * mt.Pt, ly.thetad); }
+  const int D = p.dims[0];
+  for (int r0 = 0; r0 < p.R; r0 += p.RC) {
+    const int nr = min(p.RC, p.R - r0);
+    w.stage(p.x, p.y, r0, nr);
+    if (mode > 0) {
+      for (int rr = tid; rr < nr; rr += NT) w.F(ly.cw)[rr] = __ldg(p.cwm + (size_t)s * p.R + r0 + rr);
+      __syncthreads();
+    }
+    float* xb = p.xbar ? p.xbar + ((size_t)s * p.R + r0) * D : nullptr;
+    if (mode == 2) {
+      w.forward_dual(nr);
+      w.loss_dual(nr, p.acbar ? p.acbar + (size_t)s * p.R + r0 : nullptr);
+      w.backward_any(nr, true, p.tbar + (size_t)s * mt.Pt, p.tdbar + (size_t)s * mt.Pt, xb, r0 == 0);
+    } else {
+      w.forward(nr);
+      w.loss(nr, mode == 1);
+      if (mode == 1) w.backward_any(nr, false, p.tbar + (size_t)s * mt.Pt, nullptr, xb, r0 == 0);
+    }
+    if (p.nll_out)
+      for (int rr = tid; rr < nr; rr += NT) p.nll_out[(size_t)s * p.R + r0 + rr] = w.F(ly.nll)[rr];
+    if (p.logits_out) {
+      const int C = p.dims[p.L], ldc = mt.lda[p.L];
+      for (int rr = 0; rr < nr; ++rr)
+        for (int c = tid; c < C; c += NT) p.logits_out[((size_t)s * p.R + r0 + rr) * C + c] = w.F(ly.act[p.L])[rr * ldc + c];
+    }
+    __syncthreads();
+  }
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------------------------
@@ -520,6 +669,73 @@ int psvi_mf_evaluate_stream(const psvi_mf_model* model, const psvi_noise* noise,
     predict_kernel<<<ctas, NT, smem, stream>>>(p);
     accumulate_kernel<<<1, 32, 0, stream>>>(p.part, ctas, out, mode == 0 ? lw : nullptr, p.S);
   }
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+                  const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                  float* logits, void* stream_) {
+  PSVI_REQUIRE(model && theta && x && y && R > 0, PSVI_ERR_INVALID, "null pointer or R<=0");
+  PSVI_REQUIRE(model->n_layers >= 1 && model->n_layers <= MAXL, PSVI_ERR_INVALID, "bad n_layers");
+  const int mode = thetad ? 2 : (tbar ? 1 : 0);
+  PSVI_REQUIRE(mode == 0 || (cw && tbar), PSVI_ERR_INVALID, "gradient / dual pass needs row weights and tbar");
+  PSVI_REQUIRE(mode != 2 || tdbar, PSVI_ERR_INVALID, "dual pass needs tdbar");
+  PSVI_REQUIRE(mode != 0 || nll || logits, PSVI_ERR_INVALID, "forward pass needs nll or logits");
+  Meta mt;
+  make_meta(model->dims, model->n_layers, mt);
+  SP p;
+  psvi_noise dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  fill_sp(p, model, &dummy);
+  p.theta = const_cast<float*>(theta); p.thetad = thetad; p.x = x; p.y = y; p.cwm = cw; p.R = R;
+  p.nll_out = nll; p.tbar = tbar; p.tdbar = tdbar; p.xbar = xbar; p.acbar = acbar; p.logits_out = logits;
+  int dev = 0, smem_max = 0;
+  PSVI_CUDA_CHECK(cudaGetDevice(&dev));
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t budget = (size_t)smem_max - 2048;
+  SLay ly;
+  int lo = 0, hi = R < 256 ? R : 256;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    p.RC = mid;
+    make_slay(p, mt, ly, mode > 0, mode == 2);
+    if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+  }
+  PSVI_REQUIRE(lo >= 1, PSVI_ERR_UNSUPPORTED, "one sample's weights (P_pad=%d floats%s) plus one row of activations must "
+               "fit in %zu B of shared memory", mt.Pp, mode == 2 ? ", twice" : "", budget);
+  p.RC = lo;
+  make_slay(p, mt, ly, mode > 0, mode == 2);
+  const size_t smem = (size_t)ly.total * 4;
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(net_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  net_pass_kernel<<<p.S, NT, smem, (cudaStream_t)stream_>>>(p, mode);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_net_predict(const psvi_mf_model* model, const float* theta, const float* log_weights, int32_t mode,
+                     const float* xt, const int32_t* yt, int32_t n_rows, float* out, void* workspace, void* stream_) {
+  PSVI_REQUIRE(model && theta && xt && yt && out && workspace && n_rows > 0, PSVI_ERR_INVALID, "null pointer or n_rows<=0");
+  PSVI_REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || log_weights), PSVI_ERR_INVALID, "bad mode / missing log weights");
+  PSVI_REQUIRE(model->mc_samples <= 32, PSVI_ERR_UNSUPPORTED, "streaming predictive kernel supports S <= 32");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Meta mt;
+  make_meta(model->dims, model->n_layers, mt);
+  SP p;
+  psvi_noise dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  fill_sp(p, model, &dummy);
+  p.theta = const_cast<float*>(theta); p.x = xt; p.y = yt; p.row0 = 0; p.n_rows = n_rows; p.eval_mode = mode;
+  p.lw = log_weights; p.part = static_cast<float*>(workspace);
+  size_t smem = 0;
+  int rc = fit_rows(p, mt, n_rows < 128 ? n_rows : 128, false, &smem);
+  if (rc) return rc;
+  PSVI_REQUIRE(p.RC >= 4 || p.RC >= n_rows, PSVI_ERR_UNSUPPORTED, "fewer than 4 rows per chunk fit (P_pad=%d)", mt.Pp);
+  const int ctas = (n_rows + p.RC - 1) / p.RC;
+  PSVI_CUDA_CHECK(cudaMemsetAsync(out, 0, 8 * sizeof(float), stream));
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  predict_kernel<<<ctas, NT, smem, stream>>>(p);
+  accumulate_kernel<<<1, 32, 0, stream>>>(p.part, ctas, out, mode == 0 ? log_weights : nullptr, p.S);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

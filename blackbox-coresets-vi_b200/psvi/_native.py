@@ -91,6 +91,14 @@ _SIGS = {
     "psvi_mf_evaluate_stream": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_net_pass": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_net_predict": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_fc_matvec": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_void_p, C.c_int32, C.c_void_p]),
+    "psvi_fc_outer": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -313,3 +321,27 @@ def lr_predictive_tc(model, noise, mu, rho, u, z, v, xt_bf16, yt, slab, N, vmode
 def f32_to_bf16(src, dst):
     _count(1)
     _check(lib().psvi_f32_to_bf16(_p(src), _p(dst, torch.bfloat16), src.numel(), _stream()))
+
+
+def net_pass(model, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, logits=None):
+    _count(1)
+    _check(lib().psvi_net_pass(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), x.shape[0],
+                               _p(nll), _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(logits), _stream()))
+
+
+def net_predict(model, theta, log_weights, mode, xt, yt, out):
+    _count(2)
+    ws = _workspace(model, xt.shape[0], theta.device)
+    _check(lib().psvi_net_predict(C.byref(model), _p(theta), _p(log_weights), mode, _p(xt), _p(yt, torch.int32),
+                                  xt.shape[0], _p(out), _p(ws), _stream()))
+
+
+def fc_matvec(n, S, base, dg, off, eps_ptr, ld_eps, out_ptr, ld_out):
+    """eps_ptr / out_ptr are raw device addresses (views into [S][P] slabs at a layer offset)."""
+    _count(1)
+    _check(lib().psvi_fc_matvec(n, S, _p(base), _p(dg), _p(off), eps_ptr, ld_eps, out_ptr, ld_out, _stream()))
+
+
+def fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, g_base, g_dg, g_off):
+    _count(1)
+    _check(lib().psvi_fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, _p(g_base), _p(g_dg), _p(g_off), _stream()))

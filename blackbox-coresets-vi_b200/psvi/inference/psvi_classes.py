@@ -25,7 +25,7 @@ from tqdm import tqdm
 
 from psvi import _native
 from psvi.inference.utils import LogResource, compute_empirical_mean
-from psvi.models.neural_net import (MeanFieldMLP, VILinear, VILinearMultivariateNormal, categorical_fn, make_fc2net,
+from psvi.models.neural_net import (FullCovMLP, MeanFieldMLP, VILinear, VILinearMultivariateNormal, categorical_fn, make_fc2net,
                                     make_fcnet, make_lenet, make_logistic_regression, set_mc_samples)
 
 
@@ -155,12 +155,64 @@ class PSVI(object):
     # ------------------------------------------------------------------------------------------------ native plumbing
     def _model_desc(self, model=None):
         model = self.model if model is None else model
-        if not isinstance(model, MeanFieldMLP):
-            raise NotImplementedError("the CUDA path covers mean-field MLPs (logistic_regression, fn); got "
+        if not isinstance(model, (MeanFieldMLP, FullCovMLP)):
+            raise NotImplementedError("the CUDA path covers mean-field MLPs (logistic_regression, fn) and fn2; got "
                                       f"{type(model).__name__}")
         model.check_supported()
         S = model.n_samples()
         return model, _native.make_model(model.dims, S), S
+
+    # ---- engine choice: fused cluster kernel when the model fits its shared-memory budget, streaming path otherwise ----
+    def _stream(self, model):
+        """StreamEngine for `model` (fn2, or a mean-field MLP the fused engine reported as PSVI_ERR_UNSUPPORTED)."""
+        from psvi.inference.stream import FullCovFamily, MeanFieldFamily, StreamEngine
+        key = id(model)
+        eng = self._ws.get(("stream", key))
+        if eng is None:
+            fam = FullCovFamily(model) if isinstance(model, FullCovMLP) else MeanFieldFamily(model)
+            eng = StreamEngine(fam, model.dims, model.n_samples())
+            self._ws[("stream", key)] = eng
+        if isinstance(model, MeanFieldMLP):
+            eng.fam.mu, eng.fam.rho = model.flat()
+        return eng
+
+    def _use_stream(self, model):
+        return isinstance(model, FullCovMLP) or self._ws.get(("force_stream", id(model)), False)
+
+    def _fused(self, model, fn):
+        """Run fn() on the fused engine; if the model does not fit it, remember that and return None."""
+        pos, dom = getattr(self.noise_source, "pos", None), self._noise_domain
+        try:
+            return fn()
+        except _native.NativeError as e:
+            if e.code != _native.ERR_UNSUPPORTED:
+                raise
+            self._ws[("force_stream", id(model))] = True
+            if pos is not None:
+                self.noise_source.pos = pos      # the refused call consumed no noise
+            self._noise_domain = dom
+            return None
+
+    def _noise_tensor(self, n_slabs, Pt, S):
+        if self.noise_source is not None:
+            return self.noise_source.take(n_slabs, self.device)
+        self._noise_domain += 1
+        eps = torch.empty(n_slabs, S, Pt, device=self.device)
+        _native.philox_normal(self.seed, self._noise_domain, 0, n_slabs, S, Pt, eps)
+        return eps
+
+    def _a(self):
+        return _native.coreset_weights(self.v.detach().float(), float(self.N), self._vmode, self._alpha_value())
+
+    def _v_grad_from_abar(self, abar):
+        """dLoss/dv (and dalpha) from dLoss/da through a = N f(v)."""
+        N = float(self.N)
+        if self._vmode == _native.VMODE_IDENTITY:
+            return N * abar, None
+        f = torch.softmax(self.v.detach().float(), 0)
+        sc = N * (float(torch.exp(self.alpha.detach())) if self._vmode == _native.VMODE_EXPALPHA_SOFTMAX else 1.0)
+        dot = (f * abar).sum()
+        return sc * f * (abar - dot), (sc * dot).reshape(1)
 
     def _buf(self, name, n):
         t = self._ws.get(name)
@@ -184,6 +236,22 @@ class PSVI(object):
         parameters, u and v are left in `self._last_outer` (the fused kernel produces them in the same pass)."""
         assert self.mc_samples > 1
         model, desc, S = self._model_desc(model)
+        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
+        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        if not self._use_stream(model):
+            out = self._fused(model, lambda: self._psvi_elbo_fused(model, desc, xb, yb))
+            if out is not None:
+                return out
+        eng = self._stream(model)
+        u, _ = self._uv()
+        phi = eng.fam.get_phi()
+        loss, pbar, ubar, abar, _ = eng.outer_grad(phi, self._noise_tensor(1, eng.Pt, S)[0], u, self._z32(), self._a(), xb,
+                                                   yb, float(self.N))
+        vg, ag = self._v_grad_from_abar(abar)
+        self._last_outer = dict(phi_grad=pbar, u_grad=ubar, v_grad=vg, alpha_grad=ag)
+        return loss
+
+    def _psvi_elbo_fused(self, model, desc, xb, yb):
         mu, rho = model.flat()
         u, v = self._uv()
         M, D = u.shape
@@ -191,8 +259,6 @@ class PSVI(object):
         gout = self._buf("gout", _native.gout_floats(desc, M))
         ug, vg, ag, loss = torch.zeros(M, D, device=self.device), torch.zeros(M, device=self.device), \
             torch.zeros(1, device=self.device), torch.zeros(1, device=self.device)
-        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
-        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
         _native.outer_grad(desc, self._noise(1), mu, rho, u, self._z32(), v, xb, yb, xb.shape[0], float(self.N),
                            self._vmode, self._alpha_value(), 1.0, gout, ug, vg, ag, loss)
         self._last_outer = dict(phi_grad=gout[:2 * P].clone(), u_grad=ug, v_grad=vg, alpha_grad=ag)
@@ -201,6 +267,17 @@ class PSVI(object):
     def inner_elbo(self, model=None, params=None, hyperopt=False):
         """Negative ELBO on the pseudo-data (reference :488-511).  Gradient wrt (mu, rho) in `self._last_inner`."""
         model, desc, S = self._model_desc(model)
+        if not self._use_stream(model):
+            out = self._fused(model, lambda: self._inner_elbo_fused(model, desc))
+            if out is not None:
+                return out
+        eng = self._stream(model)
+        u, _ = self._uv()
+        val, g = eng.inner_grad(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], u, self._z32(), self._a())
+        self._last_inner = g
+        return val.float()
+
+    def _inner_elbo_fused(self, model, desc):
         mu, rho = model.flat()
         u, v = self._uv()
         grad, val = torch.zeros(2 * mu.numel(), device=self.device), torch.zeros(1, device=self.device)
@@ -222,6 +299,42 @@ class PSVI(object):
             raise NotImplementedError("truncated=True is never taken by run_psvi (SURVEY.md section 8a, a8)")
         self._zero_grads()
         model, desc, S = self._model_desc()
+        if not self._use_stream(model):
+            out = self._fused(model, lambda: self._nested_step_fused(model, desc, S, xbatch, ybatch))
+            if out is not None:
+                return out
+        return self._nested_step_stream(model, S, xbatch, ybatch)
+
+    def _nested_step_stream(self, model, S, xbatch, ybatch):
+        """Same step through the streaming path (fn2 / medium-size models): per-sample network kernels + packed
+        full-covariance products, sequenced on the host (psvi/inference/stream.py).  Single GPU."""
+        if _dist_info()[2] > 1:
+            raise NotImplementedError("the streaming path is replicated, not sharded: run one chain per rank")
+        eng = self._stream(model)
+        T, lr = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"])
+        u, _ = self._uv()
+        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
+        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u, self._z32(),
+                                                 self._a(), xb, yb, float(self.N), T, lr, want_losses=self.register_elbos)
+        eng.fam.set_phi(phi_T)                 # copy-back of the fast weights (reference :596-599)
+        if self.register_elbos:
+            ilc = il.cpu()
+            for in_it in range(0, T, max(int(self.log_every), 1)):
+                self.elbos.append((1, -ilc[in_it].item()))
+            self.elbos.append((0, -loss.item()))
+        vg, ag = self._v_grad_from_abar(abar)
+        self.u.grad = ubar.to(self.u.dtype)
+        if self.learn_v:
+            self.v.grad = vg.to(self.v.dtype)
+        if self.alpha is not None and self.alpha.requires_grad and ag is not None:
+            self.alpha.grad = ag.to(self.alpha.dtype)
+        self._step_outer_optimisers()
+        if self.scheduler_optim_net:
+            self.scheduler_optim_net.step()
+        return loss
+
+    def _nested_step_fused(self, model, desc, S, xbatch, ybatch):
         mu, rho = model.flat()
         u, v = self._uv()
         M, D = u.shape
@@ -323,7 +436,8 @@ class PSVI(object):
                                     nonl_class=nn.ReLU, mc_samples=self.mc_samples,
                                     residual=(self.architecture == "residual_fn"), init_sd=self.init_sd).to(self.device)
         elif self.architecture == "fn2":
-            self.model = make_fc2net(self.D, self.n_hidden, self.nc, mc_samples=self.mc_samples, init_sd=self.init_sd)
+            self.model = make_fc2net(self.D, self.n_hidden, self.nc, mc_samples=self.mc_samples,
+                                     init_sd=self.init_sd).to(self.device)
         elif self.architecture == "lenet":
             self.model = make_lenet(mc_samples=self.mc_samples, init_sd=self.init_sd)
         else:
@@ -430,9 +544,19 @@ class PSVI(object):
         Returns (acc, nll, iw_entropy, ness, v_entropy) as 0-dim tensors."""
         assert self.mc_samples > 1
         model, desc, S = self._model_desc()
+        xt, yt = self._device_dataset(self.test_dataset, "test")
+        if isinstance(model, FullCovMLP):
+            eng = self._stream(model)
+            u, _ = self._uv()
+            batch = int(self.data_minibatch)
+            n_slabs = -(-xt.shape[0] // batch)
+            out = eng.evaluate(eng.fam.get_phi(), self._noise_tensor(n_slabs, eng.Pt, S), u, self._z32(), self._a(), xt, yt,
+                               batch, mode=0 if correction else 1)
+            vs = self.f(self.v.detach(), 0)
+            v_entropy = vs.sum().square() / vs.square().sum() / self.num_pseudo if self.compute_weights_entropy else None
+            return (out[1] / out[2], out[0] / out[2], out[3] if self.compute_weights_entropy else None, out[4], v_entropy)
         mu, rho = model.flat()
         u, v = self._uv()
-        xt, yt = self._device_dataset(self.test_dataset, "test")
         batch = int(self.data_minibatch)
         n = xt.shape[0]
         n_slabs = -(-n // batch)

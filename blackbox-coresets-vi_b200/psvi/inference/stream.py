@@ -1,0 +1,257 @@
+"""Streaming PSVI path: the bilevel step, objectives and predictive pass for models that do not fit the fused
+cluster engine -- medium-size mean-field MLPs and the full-covariance family (fn2).
+
+Structure: the objectives only see the variational family through sample / tangent / kl / nkl
+and their adjoints, so the heavy per-sample work -- forward, softmax-NLL, backward and the Hessian-vector (dual) pass of
+the network on sampled weights -- is ONE native kernel (`psvi_net_pass`, one CTA per MC sample, weights and activations in
+shared memory), the dense full-covariance products are native kernels on the packed triangle (`psvi_fc_matvec`,
+`psvi_fc_outer`), and this file holds the host-side sequencing: the unrolled robust-Adam loop of
+psvi/robust_higher/optim.py:303-367 and its reverse sweep, with the P-length elementwise updates
+expressed as torch tensor ops on the device.  Nothing here runs on the CPU.
+
+Reference map: PSVI.inner_elbo / psvi_elbo / nested_step / evaluate (psvi/inference/psvi_classes.py:488-511, 445-486,
+541-600, 1031-1108); VIMixin (neural_net.py:60-173); MultivariateNormalVIMixin (neural_net.py:408-491).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from psvi import _native
+
+B1, B2 = 0.9, 0.999
+OMB1, OMB2, AEPS = float(1.0 - B1), float(1.0 - B2), 1e-8
+
+
+class MeanFieldFamily:
+    """phi = [mu | rho] in theta layout (the flat buffers that back the module parameters)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.mu, self.rho = model.flat()
+        self.Pt = self.mu.numel()
+
+    def get_phi(self):
+        return torch.cat([self.mu, self.rho])
+
+    def set_phi(self, phi):
+        self.mu.copy_(phi[:self.Pt])
+        self.rho.copy_(phi[self.Pt:])
+
+    def sample(self, phi, eps):
+        return (phi[:self.Pt] + F.softplus(phi[self.Pt:]) * eps).contiguous()
+
+    def tangent(self, phi, phidot, eps):
+        return (phidot[:self.Pt] + torch.sigmoid(phi[self.Pt:]) * phidot[self.Pt:] * eps).contiguous()
+
+    def kl(self, phi):
+        mu, sg = phi[:self.Pt], F.softplus(phi[self.Pt:])
+        return (0.5 * (sg * sg + mu * mu - 1.0) - torch.log(sg)).sum()
+
+    def nkl(self, phi, eps, theta):
+        sg = F.softplus(phi[self.Pt:])
+        return (-0.5 * theta * theta + 0.5 * eps * eps + torch.log(sg)).double().sum(1)
+
+    def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
+        mu, rho = phi[:self.Pt], phi[self.Pt:]
+        sg, sig = F.softplus(rho), torch.sigmoid(rho)
+        gmu = tbar.sum(0) + kl_coef * mu
+        grho = sig * ((tbar * eps).sum(0) + kl_coef * (sg - 1 / sg) + nkl_coef / sg)
+        return torch.cat([gmu, grho])
+
+    def hvp(self, phi, phidot, eps, A_t, A_td):
+        rho, md, rd = phi[self.Pt:], phidot[:self.Pt], phidot[self.Pt:]
+        sg, sig = F.softplus(rho), torch.sigmoid(rho)
+        hmu = A_t.sum(0) + md
+        hrho = (sig * (A_t * eps).sum(0) + sig * (1 - sig) * rd * (A_td * eps).sum(0)
+                + ((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rd)
+        return torch.cat([hmu, hrho])
+
+
+class FullCovFamily:
+    """phi = per layer [mean | _sd | _corr] (torch parameters_to_vector order of the fn2 model)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.layers = model.vi_layers()
+        self.ns = [m.num_params for m in self.layers]
+        self.ncs = [m._corr.numel() for m in self.layers]
+        self.Pt = sum(self.ns)
+        self.offs, self.toffs, o, t = [], [], 0, 0
+        for n, c in zip(self.ns, self.ncs):
+            self.offs.append(o)
+            self.toffs.append(t)
+            o += 2 * n + c
+            t += n
+
+    def get_phi(self):
+        return torch.cat([p.detach().reshape(-1).float() for m in self.layers for p in (m.mean, m._sd, m._corr)])
+
+    def set_phi(self, phi):
+        with torch.no_grad():
+            for (m, sd, corr, n), layer in zip(self._split(phi), self.layers):
+                layer.mean.copy_(m)
+                layer._sd.copy_(sd)
+                layer._corr.copy_(corr)
+
+    def _split(self, phi):
+        out = []
+        for o, n, c in zip(self.offs, self.ns, self.ncs):
+            out.append((phi[o:o + n], phi[o + n:o + 2 * n], phi[o + 2 * n:o + 2 * n + c], n))
+        return out
+
+    def _matvec(self, parts, eps):
+        S = eps.shape[0]
+        out = torch.empty(S, self.Pt, device=eps.device)
+        for (base, dg, off, n), t in zip(parts, self.toffs):
+            _native.fc_matvec(n, S, base.contiguous(), dg.contiguous(), off.contiguous(), eps.data_ptr() + 4 * t, self.Pt,
+                              out.data_ptr() + 4 * t, self.Pt)
+        return out
+
+    def sample(self, phi, eps):
+        return self._matvec([(m, F.softplus(sd), corr, n) for (m, sd, corr, n) in self._split(phi)], eps)
+
+    def tangent(self, phi, phidot, eps):
+        parts = [(md, torch.sigmoid(sd) * sdd, corrd, n)
+                 for (m, sd, corr, n), (md, sdd, corrd, _) in zip(self._split(phi), self._split(phidot))]
+        return self._matvec(parts, eps)
+
+    def kl(self, phi):
+        t = 0.0
+        for (m, sd, corr, n) in self._split(phi):
+            d = F.softplus(sd)
+            t = t + 0.5 * ((d * d).sum() + (corr * corr).sum() + (m * m).sum() - n) - torch.log(d).sum()
+        return t
+
+    def nkl(self, phi, eps, theta):
+        logdet = sum(torch.log(F.softplus(sd)).double().sum() for (_, sd, _, _) in self._split(phi))
+        return -0.5 * (theta.double() ** 2).sum(1) + 0.5 * (eps.double() ** 2).sum(1) + logdet
+
+    def _outer(self, A, eps, n, c, t):
+        S = eps.shape[0]
+        gb, gd = torch.empty(n, device=eps.device), torch.empty(n, device=eps.device)
+        go = torch.zeros(max(c, 1), device=eps.device)
+        _native.fc_outer(n, S, A.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t, self.Pt, gb, gd, go)
+        return gb, gd, go[:c]
+
+    def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
+        out = []
+        for (m, sd, corr, n), c, t in zip(self._split(phi), self.ncs, self.toffs):
+            gb, gd, go = self._outer(tbar, eps, n, c, t)
+            d, sig = F.softplus(sd), torch.sigmoid(sd)
+            out += [gb + kl_coef * m, sig * (gd + kl_coef * (d - 1 / d) + nkl_coef / d), go + kl_coef * corr]
+        return torch.cat(out)
+
+    def hvp(self, phi, phidot, eps, A_t, A_td):
+        out = []
+        for (m, sd, corr, n), (md, sdd, corrd, _), c, t in zip(self._split(phi), self._split(phidot), self.ncs, self.toffs):
+            gb, gd, go = self._outer(A_t, eps, n, c, t)
+            _, gdd, _ = self._outer(A_td, eps, n, c, t)
+            d, sig = F.softplus(sd), torch.sigmoid(sd)
+            out += [gb + md,
+                    sig * gd + sig * (1 - sig) * sdd * gdd + ((1 + 1 / (d * d)) * sig * sig + (d - 1 / d) * sig * (1 - sig)) * sdd,
+                    go + corrd]
+        return torch.cat(out)
+
+
+class StreamEngine:
+    def __init__(self, fam, dims, S):
+        self.fam, self.S, self.dims = fam, S, list(dims)
+        self.desc = _native.make_model(dims, S)
+        self.Pt = fam.Pt
+
+    # ---- objectives --------------------------------------------------------------------------------------------------
+    def inner_grad(self, phi, eps, u, z32, a):
+        S, M = self.S, u.shape[0]
+        theta = self.fam.sample(phi, eps)
+        nll, tbar = torch.empty(S, M, device=u.device), torch.empty(S, self.Pt, device=u.device)
+        _native.net_pass(self.desc, theta, None, u, z32, a.expand(S, M).contiguous(), nll=nll, tbar=tbar)
+        val = (nll.double() @ a.double()).sum() + self.fam.kl(phi).double()
+        return val, self.fam.grad(phi, eps, tbar, 1.0, 0.0)
+
+    def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None):
+        S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
+        n_total = B if n_total is None else n_total
+        theta = self.fam.sample(phi, eps)
+        X, lab = torch.cat([u, xb]).contiguous(), torch.cat([z32, yb32]).contiguous()
+        nll = torch.empty(S, M + B, device=dev)
+        _native.net_pass(self.desc, theta, None, X, lab, None, nll=nll)
+        nd = nll.double()
+        ps, ds = nd[:, :M] @ a.double(), (N / n_total) * nd[:, M:].sum(1)
+        lw = -ps + self.fam.nkl(phi, eps, theta)
+        w = torch.softmax(lw, 0)
+        e = ds - kappa * ps
+        ebar = (w * e).sum()
+        loss = ebar - kappa * lw.mean()
+        beta = w * (e - ebar) - kappa / S
+        gp = -kappa * w - beta
+        cw = torch.cat([gp[:, None] * a.double()[None, :], (w * N / n_total)[:, None].expand(S, B)], 1).float().contiguous()
+        tbar, xbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, M + B, X.shape[1], device=dev)
+        _native.net_pass(self.desc, theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
+        tbar = tbar - beta.float()[:, None] * theta
+        pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
+        return loss.float(), pbar, xbar[:, :M].sum(0), (gp.float() @ nll[:, :M]), ds.float()
+
+    def hvp(self, phi, eps, u, z32, a, phidot):
+        S, M, dev = self.S, u.shape[0], u.device
+        theta, thetad = self.fam.sample(phi, eps), self.fam.tangent(phi, phidot, eps)
+        tbar, tdbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, self.Pt, device=dev)
+        xbar, ac = torch.empty(S, M, u.shape[1], device=dev), torch.empty(S, M, device=dev)
+        _native.net_pass(self.desc, theta, thetad, u, z32, a.expand(S, M).contiguous(), tbar=tbar, tdbar=tdbar, xbar=xbar,
+                         acbar=ac)
+        return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
+
+    # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
+    def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False):
+        """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None)."""
+        m, v = torch.zeros_like(phi), torch.zeros_like(phi)
+        traj, losses = [], []
+        for t in range(T):
+            val, g = self.inner_grad(phi, eps_all[t], u, z32, a)
+            if want_losses:
+                losses.append(val)
+            m = m * B1 + OMB1 * g
+            v = v * B2 + OMB2 * g * g
+            sq2 = math.sqrt(1.0 - B2 ** (t + 1))
+            den = torch.sqrt(v + 1e-8) / sq2 + AEPS
+            traj.append((phi, g, m, v))
+            phi = phi - (lr / (1.0 - B1 ** (t + 1))) * (m / den)
+        loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N)
+        phi_T = phi
+        mbar, vbar = torch.zeros_like(pbar), torch.zeros_like(pbar)
+        for t in range(T - 1, -1, -1):
+            phi_t, g, m_t, v_t = traj[t]
+            k = lr / (1.0 - B1 ** (t + 1))
+            sq2 = math.sqrt(1.0 - B2 ** (t + 1))
+            q = torch.sqrt(v_t + 1e-8)
+            den = q / sq2 + AEPS
+            mb = mbar - k * pbar / den
+            vb = vbar + (k * pbar * m_t / (den * den)) / (2.0 * q * sq2)
+            vb = torch.where(v_t == 0, torch.zeros_like(vb), vb)       # _maybe_mask hook (optim.py:40-52,346-347)
+            gbar = OMB1 * mb + 2.0 * OMB2 * g * vb
+            mbar, vbar = B1 * mb, B2 * vb
+            h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar)
+            pbar, ubar, abar = pbar + h, ubar + hu, abar + ha
+        return loss, ubar, abar, phi_T, (torch.stack(losses).float() if want_losses else None)
+
+    # ---- predictive pass (psvi_classes.py:1031-1108) -----------------------------------------------------------------
+    def evaluate(self, phi, eps_slabs, u, z32, a, xt, yt32, batch, mode=0):
+        """eps_slabs [n_slabs, S, P]; returns out[8] accumulated over slabs (diagnostics of the last slab, Q12)."""
+        dev, S = xt.device, self.S
+        tot = torch.zeros(8, device=dev)
+        out = torch.zeros(8, device=dev)
+        n = xt.shape[0]
+        for k, r0 in enumerate(range(0, n, batch)):
+            theta = self.fam.sample(phi, eps_slabs[k])
+            lw = None
+            if mode == 0:
+                M = u.shape[0]
+                nll = torch.empty(S, M, device=dev)
+                _native.net_pass(self.desc, theta, None, u, z32, None, nll=nll)
+                lw = ((nll.double() @ a.double()) + self.fam.nkl(phi, eps_slabs[k], theta)).float().contiguous()  # Q3
+            _native.net_predict(self.desc, theta, lw, mode, xt[r0:r0 + batch].contiguous(), yt32[r0:r0 + batch].contiguous(), out)
+            tot[:3] += out[:3]
+            tot[3:5] = out[3:5]
+        return tot

@@ -9,8 +9,9 @@ What is native here: a whole mean-field MLP (nn.Sequential of VILinear / ReLU, a
 PSVI.set_up_model for `logistic_regression`) is evaluated by ONE fused kernel (sampling -> per-sample GEMMs -> ReLU ->
 logits), see MeanFieldMLP.forward.  Gradients are not obtained with autograd: the PSVI objectives, their gradients and
 the hypergradient are separate fused kernels driven by psvi.inference.psvi_classes.
-Full-covariance (fn2) and convolutional (lenet) families are declared for API compatibility and raise
-NotImplementedError at construction in this round (DESIGN.md "not yet covered").
+The full-covariance family (fn2) evaluates through the streaming path (packed-triangle products + the per-sample
+network kernel).  The convolutional family (lenet) is declared for API compatibility and raises NotImplementedError at
+construction in this round (DESIGN.md "not yet covered").
 """
 from __future__ import annotations
 
@@ -254,17 +255,130 @@ def make_logistic_regression(in_dim, out_dim, **kwargs):
     return MeanFieldMLP(VILinear(in_dim, out_dim, **kwargs))
 
 
-# ---- families that are part of the reference surface but not yet covered by kernels (a3, a4) ----
+# ---- full-covariance family (fn2): reference neural_net.py:408-524 ------------------------------------------------------
 class MultivariateNormalVIMixin(nn.Module):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("full-covariance layers (fn2, reference neural_net.py:408-491) are not built yet "
-                                  "in the B200 path; see DESIGN.md 'not yet covered'")
+    """Full-covariance Gaussian over ALL parameters of a layer jointly (reference :408-482): theta_s = mean + L eps_s with
+    L = scale_tril: diag = softplus(_sd); the strictly-lower entries of the top-left (n-1)x(n-1) block are `_corr`
+    (torch.tril_indices(n-1, n-1, -1) order), the last row has no off-diagonals (Q6).  Parameter names mean / _sd / _corr
+    and their sizes match the reference, so state_dicts interchange."""
+
+    def __init__(self, *args, init_sd=0.01, prior_sd=1.0, mc_samples=1, **kwargs):
+        super().__init__(*args, **kwargs)   # nn.Linear init: consumes the RNG exactly as the reference does
+        self.mc_samples, self.prior_sd = mc_samples, prior_sd
+        self.param_names, self.param_shapes = [], []
+        for n, p in list(self.named_parameters()):
+            self.param_names.append(n)
+            self.param_shapes.append(p.shape)
+            delattr(self, n)
+        self.param_numels = [int(np.prod(s)) for s in self.param_shapes]
+        n = sum(self.param_numels)
+        self.mean = nn.Parameter(p.new_zeros(n))
+        self._sd = nn.Parameter(inverse_softplus(p.new_full((n,), init_sd)))
+        self._corr = nn.Parameter(p.new_zeros(torch.tril_indices(n - 1, n - 1, offset=-1)[0].numel()))
+        self.num_params = n
+        self._cached = None
+
+    def reset_parameters_variational(self) -> None:
+        raise NotImplementedError
+
+    @property
+    def scale_tril(self):
+        """Dense L, built the way the reference does (:452-461) -- for inspection only; the kernels keep L packed."""
+        k = self.mean.new_zeros(self.num_params, self.num_params)
+        k[torch.arange(self.num_params), torch.arange(self.num_params)] = F.softplus(self._sd)
+        d = self.mean.size(-1) - 1
+        i = torch.tril_indices(d, d, offset=-1)
+        k[i[0], i[1]] = self._corr
+        return k
+
+    def kl(self):
+        d = F.softplus(self._sd)
+        return 0.5 * ((d * d).sum() + (self._corr ** 2).sum() + (self.mean ** 2).sum() - self.num_params) - torch.log(d).sum()
+
+    def sampled_nkl(self):
+        if self._cached is None:
+            raise RuntimeError("sampled_nkl() needs a forward pass first")
+        theta, eps = self._cached
+        return -0.5 * (theta ** 2).sum(-1) + 0.5 * (eps ** 2).sum(-1) + torch.log(F.softplus(self._sd)).sum()
 
 
 class VILinearMultivariateNormal(MultivariateNormalVIMixin, nn.Linear):
-    pass
+    """reference :485-491.  Evaluated inside a FullCovMLP stack (one fused per-sample network kernel)."""
+
+    def extra_repr(self):
+        return f"num_params={self.num_params}, mc_samples={self.mc_samples}"
+
+    def forward(self, x, **kwargs):
+        if x.dim() != 2:
+            raise NotImplementedError("a stand-alone VILinearMultivariateNormal takes [rows, in_features] inputs")
+        return FullCovMLP(self).forward(x)
 
 
+class FullCovMLP(nn.Sequential):
+    """nn.Sequential of VILinearMultivariateNormal / ReLU (fn2).  Forward: packed L eps products (psvi_fc_matvec) to
+    sample every layer's weights, then one per-sample network kernel (psvi_net_pass)."""
+
+    def vi_layers(self):
+        return [m for m in self if isinstance(m, VILinearMultivariateNormal)]
+
+    def check_supported(self):
+        mods = list(self)
+        ok = len(mods) >= 1 and isinstance(mods[-1], VILinearMultivariateNormal)
+        for i, m in enumerate(mods[:-1]):
+            ok = ok and (isinstance(m, VILinearMultivariateNormal) if i % 2 == 0 else isinstance(m, nn.ReLU))
+        if not ok or len(self.vi_layers()) > _native.MAX_LAYERS:
+            raise NotImplementedError(f"fused kernels cover VILinearMultivariateNormal (ReLU ...)* stacks; got {self}")
+        for m in self.vi_layers():
+            if float(m.prior_sd) != 1.0:
+                raise NotImplementedError("prior_sd != 1 is not supported by the fused kernels")
+
+    @property
+    def dims(self):
+        shapes = [m.param_shapes[0] for m in self.vi_layers()]      # weight shapes [out, in]
+        return [int(shapes[0][1])] + [int(s[0]) for s in shapes]
+
+    def n_samples(self):
+        return int(self.vi_layers()[0].mc_samples)
+
+    def forward(self, x, eps=None):
+        from psvi.inference.stream import FullCovFamily
+        _native.require_cuda()
+        self.check_supported()
+        fam = FullCovFamily(self)
+        S = max(self.n_samples(), 1)
+        dev = self.vi_layers()[0].mean.device
+        if eps is None:
+            eps = torch.empty(1, S, fam.Pt, device=dev)
+            _native.philox_normal(torch.initial_seed(), _NoiseCounter.next(), 0, 1, S, fam.Pt, eps)
+            eps = eps[0]
+        theta = fam.sample(fam.get_phi(), eps)
+        x = x.detach().to(dev, torch.float32).contiguous()
+        logits = torch.empty(S, x.shape[0], self.dims[-1], device=dev)
+        y = torch.zeros(x.shape[0], device=dev, dtype=torch.int32)
+        _native.net_pass(_native.make_model(self.dims, S), theta, None, x, y, None, logits=logits)
+        for m, t in zip(fam.layers, fam.toffs):
+            m._cached = (theta[:, t:t + m.num_params], eps[:, t:t + m.num_params])
+        return logits if self.n_samples() > 1 else logits[0]
+
+
+def make_fc2net(in_dim, h_dim, out_dim, n_layers=2, linear_class=None, nonl_class=None, mc_samples=4, residual=False,
+                **kwargs):
+    """reference :494-524 (default n_layers=2 hidden layers, Q7)."""
+    if linear_class is None:
+        linear_class = VILinearMultivariateNormal
+    if nonl_class is None:
+        nonl_class = nn.ReLU
+    net = FullCovMLP() if (linear_class is VILinearMultivariateNormal and nonl_class is nn.ReLU) else nn.Sequential()
+    for i in range(n_layers):
+        net.add_module(f"lin{i}", linear_class(in_dim if i == 0 else h_dim, h_dim, mc_samples=mc_samples, **kwargs))
+        net.add_module(f"nonl{i}", nonl_class())
+    net.add_module("classifier", linear_class(h_dim, out_dim, mc_samples=mc_samples, **kwargs))
+    for module in net.modules():
+        module.mc_samples = mc_samples
+    return net
+
+
+# ---- families that are part of the reference surface but not yet covered by kernels (SURVEY section 8a: a4) ----
 class VIConv2d(VIMixin, nn.Conv2d):
     def __init__(self, *args, **kwargs):
         raise NotImplementedError("VIConv2d / lenet (reference neural_net.py:194-246,334-359) is not built yet in the "
@@ -273,10 +387,6 @@ class VIConv2d(VIMixin, nn.Conv2d):
 
 class BatchMaxPool2d(nn.MaxPool2d):
     pass
-
-
-def make_fc2net(*args, **kwargs):
-    raise NotImplementedError("fn2 (full-covariance BNN, reference neural_net.py:494-524) is not built yet")
 
 
 def make_lenet(*args, **kwargs):

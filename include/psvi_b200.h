@@ -185,6 +185,34 @@ int psvi_mf_evaluate_stream(const psvi_mf_model* model, const psvi_noise* noise,
                             const int32_t* yt, int32_t n_rows, int32_t batch, int32_t first_slab, int32_t mode,
                             float* out, void* workspace, void* stream);
 
+/* ---- building blocks of the streaming path for ANY variational family: the per-sample network pass on externally
+ * supplied weights, and the predictive kernel on externally supplied weights.  Used with the mean-field sampling for
+ * medium-size MLPs and with the full-covariance layer (fn2) below.
+ * psvi_net_pass: theta [S][P] (TL); thetad [S][P] nullable.  thetad == NULL, tbar == NULL: forward only -> nll [S][R];
+ *   thetad == NULL: gradient pass with per-sample row weights cw [S][R] -> tbar [S][P] (d/dtheta_s), xbar [S][R][D]
+ *   (nullable, d/dx per sample), nll;  thetad != NULL: dual (Hessian-vector) pass, SURVEY Appendix A.6 -> tbar = A_theta,
+ *   tdbar = A_thetadot, xbar = A_x, acbar [S][R] = adjoint of the row weights.
+ *   Replaces VILinear(MultivariateNormal).forward + Categorical.log_prob + autograd (neural_net.py:176-179,485-491). */
+int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+                  const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                  float* logits /* [S][R][C], nullable */, void* stream);
+/* psvi_net_predict: predictive metrics of rows xt with sampled weights theta [S][P]; mode 0 needs log_weights [S]
+ *   (softmax-ed inside); out [8] as psvi_mf_evaluate; workspace of psvi_mf_stream_workspace_bytes(model, n_rows). */
+int psvi_net_predict(const psvi_mf_model* model, const float* theta, const float* log_weights, int32_t mode,
+                     const float* xt, const int32_t* yt, int32_t n_rows, float* out, void* workspace, void* stream);
+
+/* ---- full-covariance layer (fn2): MultivariateNormalVIMixin, psvi/models/neural_net.py:408-491.  L = scale_tril stays
+ * PACKED: dg[n] (diagonal), off[(n-1)(n-2)/2] in torch.tril_indices(n-1, n-1, -1) order (k = r(r-1)/2 + c; last row has
+ * no off-diagonals, Q6).
+ * psvi_fc_matvec: out[s][i] = base[i] + dg[i] eps[s][i] + sum_{c<i} off[k(i,c)] eps[s][c]   (rsample :467-472; base may
+ *   be NULL; with (mdot, Ldot) it yields the tangent sample);  eps / out are row-major with leading dims ld_eps / ld_out.
+ * psvi_fc_outer: g_base[i] = sum_s A[s][i]; g_dg[i] = sum_s A[s][i] eps[s][i]; g_off[k(r,c)] = sum_s A[s][r] eps[s][c]
+ *   (what autograd accumulates into mean / _sd / _corr through scale_tril, :452-461). */
+int psvi_fc_matvec(int32_t n, int32_t S, const float* base, const float* dg, const float* off, const float* eps,
+                   int32_t ld_eps, float* out, int32_t ld_out, void* stream);
+int psvi_fc_outer(int32_t n, int32_t S, const float* A, int32_t ld_a, const float* eps, int32_t ld_eps, float* g_base,
+                  float* g_dg, float* g_off, void* stream);
+
 /* ---- tensor-core full-data predictive pass for the single-layer model (logistic_regression): the HBM-bound member of
  * the predictive kernels.  Same quantities as psvi_mf_evaluate (PSVI.evaluate,
  * psvi_classes.py:1031-1108) for ONE noise slab over all n_rows (the reference with data_minibatch >= n_rows), computed

@@ -167,6 +167,69 @@ def run_mfvi_case():
                 ref_elbos=np.array(res["elbos"]), ref_accs=np.array(res["accs"]), ref_nlls=np.array(res["nlls"]))
 
 
+def run_fn2_case(name="fn2_hm_h6", H=6, M=8, S=5, T=3, B=32, init_sd=0.05, lr0net=1e-3):
+    """fn2 (full covariance, reference neural_net.py:408-524) in fp64 -- the reference is numerically unstable in fp32 and
+    at small init_sd, so the golden is taken in the well-conditioned regime."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn2", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=True)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(99)
+    # non-trivial state: random means and correlations (the reference initialises both to zero)
+    with torch.no_grad():
+        for n_, p_ in obj.model.named_parameters():
+            if n_.endswith("mean"):
+                p_.copy_(torch.tensor(0.3 * rng.standard_normal(p_.shape)))
+            if n_.endswith("_corr"):
+                p_.copy_(torch.tensor(0.01 * rng.standard_normal(p_.shape)))
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = [D, H, H, nc]     # make_fc2net default n_layers=2 (Q7)
+    params = list(obj.model.parameters())
+    phi0 = torch.nn.utils.parameters_to_vector(params).detach().numpy().copy()
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, lr0net=lr0net, noise_seed=555, vmode=1, phi0=phi0,
+               u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy(), xt=xt.double().numpy().copy(), yt=yt.double().numpy().copy())
+    te.data = te.data.double()
+    with NoiseFeeder(dims, S, 555, fullcov=True) as nf:
+        L = obj.inner_elbo(model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u, obj.v])
+        out["ref64_inner_val"] = L.item()
+        out["ref64_inner_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).numpy()
+        out["ref64_inner_gu"], out["ref64_inner_gv"] = gs[-2].numpy(), gs[-1].numpy()
+        L = obj.psvi_elbo(xb, yb, model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u, obj.v])
+        out["ref64_outer_val"] = L.item()
+        out["ref64_outer_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).numpy()
+        out["ref64_outer_gu"], out["ref64_outer_gv"] = gs[-2].numpy(), gs[-1].numpy()
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_nested_gu"], out["ref64_nested_gv"] = obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy()
+        out["ref64_nested_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_nested_u_after"], out["ref64_nested_v_after"] = obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy()
+        acc, nll, went, ness, vent = obj.evaluate()
+        out["ref64_eval"] = np.array([acc.item(), nll.item(), went.item(), ness.item(), vent.item()])
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards"], "nested_loss", out["ref64_nested_loss"], "size", os.path.getsize(pth))
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for c in CASES:
@@ -181,6 +244,7 @@ def main():
         np.savez_compressed(p, **blob)
         print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"],
               "size", os.path.getsize(p))
+    run_fn2_case()
     blob = run_mfvi_case()
     p = os.path.join(ROOT, "tests", "golden", "mfvi_subset_hm.npz")
     np.savez_compressed(p, **blob)

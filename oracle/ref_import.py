@@ -55,7 +55,7 @@ class NoiseFeeder:
     noise stream in its own draw order (per VI layer: weight draw [S,out,in], then bias draw [S,1,out];
     neural_net.py:155-170).  One [S, P_theta] array ("TL" layout, see psvi_oracle.py) is generated per forward."""
 
-    def __init__(self, dims, S, seed):
+    def __init__(self, dims, S, seed, fullcov=False):
         import numpy as np
         self.dims, self.S = list(dims), S
         self.rng = np.random.default_rng(seed)
@@ -63,7 +63,11 @@ class NoiseFeeder:
         self._pos = 0
         self._shapes = []
         for l in range(1, len(dims)):
-            self._shapes += [(S, dims[l], dims[l - 1]), (S, 1, dims[l])]
+            if fullcov:   # MultivariateNormal.rsample: ONE [S, n] draw per layer (neural_net.py:467-472)
+                self._shapes += [(S, 1, dims[l] * (dims[l - 1] + 1))]
+            else:
+                self._shapes += [(S, dims[l], dims[l - 1]), (S, 1, dims[l])]
+        self._fullcov = fullcov
         self._call = 0
 
     @staticmethod
@@ -82,19 +86,27 @@ class NoiseFeeder:
             self.history.append(self.rng.standard_normal((self.S, P)).astype(np.float32))
             self._pos = 0
         exp = self._shapes[self._call]
-        assert tuple(shape) == exp, (tuple(shape), exp)
+        if self._fullcov:
+            assert tuple(shape) == (exp[0], exp[2]), (tuple(shape), exp)
+            shape_out = (exp[0], exp[2])
+        else:
+            assert tuple(shape) == exp, (tuple(shape), exp)
+            shape_out = exp
         n = exp[1] * exp[2]
-        out = self.history[-1][:, self._pos:self._pos + n].reshape(exp)
+        out = self.history[-1][:, self._pos:self._pos + n].reshape(shape_out)
         self._pos += n
         self._call = (self._call + 1) % len(self._shapes)
         return torch.from_numpy(np.ascontiguousarray(out)).to(dtype=dtype, device=device)
 
     def __enter__(self):
+        import torch.distributions.multivariate_normal as tdm
         import torch.distributions.normal as tdn
-        self._orig = tdn._standard_normal
+        self._orig = (tdn._standard_normal, tdm._standard_normal)
         tdn._standard_normal = self
+        tdm._standard_normal = self
         return self
 
     def __exit__(self, *a):
+        import torch.distributions.multivariate_normal as tdm
         import torch.distributions.normal as tdn
-        tdn._standard_normal = self._orig
+        tdn._standard_normal, tdm._standard_normal = self._orig

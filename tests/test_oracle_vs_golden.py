@@ -111,3 +111,52 @@ def test_mfvi_subset_trace():
     np.testing.assert_allclose(elbos, g["ref_elbos"], rtol=2e-5)
     np.testing.assert_allclose(accs, g["ref_accs"], atol=1e-6)
     np.testing.assert_allclose(nlls, g["ref_nlls"], rtol=2e-5)
+
+
+def test_generic_oracle_reduces_to_meanfield_oracle():
+    from oracle import psvi_oracle_generic as pg
+    g, dims, S, T, eps = load("fn_fb_l2_m13")
+    N, vmode = float(g["N"]), int(g["vmode"])
+    fam = pg.MeanField(dims)
+    phi0 = po.mu_rho_to_phi(g["mu0"], g["rho0"], dims)
+    r = pg.nested_step(fam, phi0, eps[2:2 + T], eps[2 + T], g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N,
+                       float(g["lr0net"]), vmode=vmode)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-9 * abs(r["loss"])
+    assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-7
+    assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-7
+    assert rel_l2(r["phi_T"], g["ref64_nested_params"]) < 1e-10
+
+
+def test_fullcov_oracle_matches_reference_fn2():
+    """fn2 (MultivariateNormalVIMixin, neural_net.py:408-491): the closed forms (no triangular solve) against the
+    reference's autograd / higher run in fp64."""
+    from oracle import psvi_oracle_generic as pg
+    g = dict(np.load(os.path.join(GOLDEN, "fn2_hm_h6.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, N = int(g["S"]), int(g["T"]), float(g["N"])
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    fam = pg.FullCov(dims)
+    assert fam.Pphi == len(g["phi0"])
+    a = po.coreset_weights(g["v0"], N, 1)
+    val, gphi, gu, ga = pg.inner_grad(fam, g["phi0"], eps[0], g["u0"], g["z"], a)
+    assert abs(val - g["ref64_inner_val"]) <= 1e-9 * abs(val)
+    assert rel_l2(gphi, g["ref64_inner_gparams"]) < 1e-8
+    assert rel_l2(gu, g["ref64_inner_gu"]) < 1e-8
+    val, gphi, gu, ga = pg.outer_grad(fam, g["phi0"], eps[1], g["u0"], g["z"], a, g["xb"], g["yb"], N)
+    assert abs(val - g["ref64_outer_val"]) <= 1e-9 * abs(val)
+    assert rel_l2(gphi, g["ref64_outer_gparams"]) < 1e-7
+    assert rel_l2(gu, g["ref64_outer_gu"]) < 1e-7
+    assert rel_l2(po.coreset_weights_vjp(g["v0"], N, 1, ga)[0], g["ref64_outer_gv"]) < 1e-7
+    r = pg.nested_step(fam, g["phi0"], eps[2:2 + T], eps[2 + T], g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N,
+                       float(g["lr0net"]), vmode=1)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-8 * abs(r["loss"])
+    assert rel_l2(r["phi_T"], g["ref64_nested_params"]) < 1e-9
+    assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-6
+    assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-6
+    a1 = po.coreset_weights(g["ref64_nested_v_after"], N, 1)
+    B = int(g["B"])
+    nb = -(-g["xt"].shape[0] // B)
+    acc, nll, went, ness = pg.evaluate(fam, r["phi_T"], eps[3 + T:3 + T + nb], g["ref64_nested_u_after"], g["z"], a1,
+                                       g["xt"], g["yt"], B)
+    assert abs(acc - g["ref64_eval"][0]) < 1e-7
+    np.testing.assert_allclose([nll, went, ness], g["ref64_eval"][1:4], rtol=1e-6)
