@@ -230,6 +230,47 @@ def run_fn2_case(name="fn2_hm_h6", H=6, M=8, S=5, T=3, B=32, init_sd=0.05, lr0ne
     print(name, "forwards", out["n_forwards"], "nested_loss", out["ref64_nested_loss"], "size", os.path.getsize(pth))
 
 
+def run_hyper_case(name="hyper_fn_hm", H=20, M=10, S=6, T=6, B=64, K=4, init_sd=1e-2, lr0net=1e-3):
+    """PSVI.hyper_step (psvi_classes.py:602-687) with hypergrad.CG_normaleq (hypergradients.py:199-244), fp64."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="hyper", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(5)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, K=K, lr0net=lr0net, linsys_lr=1e-2, noise_seed=4321, vmode=1,
+               mu0=mu0, rho0=rho0, u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy())
+    with NoiseFeeder(dims, S, 4321) as nf:
+        ll = obj.hyper_step(xb, yb, K=K, linsys_lr=1e-2)
+        out["ref64_ll"] = ll
+        out["ref64_gu"], out["ref64_gv"] = obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy()
+        out["ref64_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_u_after"], out["ref64_v_after"] = obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy()
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards"], "ll", ll, "|gu|", np.abs(out["ref64_gu"]).max(), "size", os.path.getsize(pth))
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for c in CASES:
@@ -245,6 +286,7 @@ def main():
         print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"],
               "size", os.path.getsize(p))
     run_fn2_case()
+    run_hyper_case()
     blob = run_mfvi_case()
     p = os.path.join(ROOT, "tests", "golden", "mfvi_subset_hm.npz")
     np.savez_compressed(p, **blob)

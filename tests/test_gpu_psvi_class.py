@@ -137,3 +137,39 @@ def test_flow_psvi_cli_writes_results(tmp_path):
     r = res["halfmoon"]["psvi_learn_v"][10][0]
     assert len(r["accs"]) == 3 and np.isfinite(r["nlls"]).all()
     assert os.path.exists(tmp_path / "r.json")
+
+
+def test_hyper_step_matches_reference():
+    """--trainer hyper: PSVI.hyper_step + CG_normaleq (reference psvi_classes.py:602-687, hypergradients.py:199-244) with
+    the reference's noise-consumption order (T inner, outer, w_mapped, 2 per JVP, final outer)."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.experiments_utils import read_dataset
+    from psvi.inference.psvi_classes import ExternalNoise, PSVILearnV
+    g = dict(np.load(os.path.join(GOLDEN, "hyper_fn_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, M, B, K = int(g["S"]), int(g["T"]), int(g["M"]), int(g["B"]), int(g["K"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    x, y, xt, yt, N, D, tr, te, nc = read_dataset("halfmoon", {"test_ratio": 0.2})
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="hyper", log_every=10, lr0u=1e-4,
+              lr0net=float(g["lr0net"]), lr0v=1e-3, init_args="subsample", init_sd=1e-2, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=dims[1], n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, compute_weights_entropy=True, register_elbos=False, quiet=True)
+    obj = PSVILearnV(**kw)
+    obj.run_psvi(**kw)
+    mu, rho = obj.model.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    with torch.no_grad():
+        obj.u.copy_(torch.as_tensor(g["u0"]))
+        obj.v.copy_(torch.as_tensor(g["v0"]))
+    obj.z = torch.as_tensor(g["z"]).float().cuda()
+    obj.scheduler_optim_net = None
+    obj.noise_source = ExternalNoise(eps)
+    xb, yb = torch.as_tensor(g["xb"]).float().cuda(), torch.as_tensor(g["yb"]).cuda()
+    ll = obj.hyper_step(xb, yb, K=K, linsys_lr=float(g["linsys_lr"]))
+    assert obj.noise_source.pos == int(g["n_forwards"])            # same number of forwards as the reference
+    assert abs(ll - g["ref64_ll"]) <= 2e-4 * abs(g["ref64_ll"])
+    assert rel_l2(obj.u.grad.cpu().numpy(), g["ref64_gu"]) < 2e-3
+    assert rel_l2(obj.v.grad.cpu().numpy(), g["ref64_gv"]) < 2e-3
+    vec = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().cpu().numpy()
+    assert rel_l2(vec, g["ref64_params"]) < 1e-5
+    np.testing.assert_allclose(obj.u.detach().cpu().numpy(), g["ref64_u_after"], atol=2e-6)
