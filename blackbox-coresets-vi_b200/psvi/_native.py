@@ -84,6 +84,13 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "psvi_fn_tc_scratch_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int64, C.c_int32]),
+    "psvi_fn_predictive_tc": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_fn_nll_tc": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "psvi_mf_stream_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32]),
     "psvi_mf_unroll_stream": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
@@ -316,6 +323,27 @@ def lr_predictive_tc(model, noise, mu, rho, u, z, v, xt_bf16, yt, slab, N, vmode
     _check(lib().psvi_lr_predictive_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
                                        _p(xt_bf16, torch.bfloat16), _p(yt, torch.int32), xt_bf16.shape[0], slab, N, vmode,
                                        alpha, mode, _p(out), _p(scratch), _stream()))
+
+
+def fn_tc_scratch_floats(model, max_rows, M):
+    return (int(lib().psvi_fn_tc_scratch_bytes(C.byref(model), max_rows, M)) + 3) // 4
+
+
+def fn_predictive_tc(model, noise, mu, rho, u, z, v, xt_bf16, yt, slab, N, vmode, alpha, mode, out, scratch):
+    """Tensor-core predictive pass for fn with one hidden layer (large regime); same contract as lr_predictive_tc."""
+    M = 0 if u is None else u.shape[0]
+    _count(10 if mode == 0 else 5)
+    _check(lib().psvi_fn_predictive_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v), M,
+                                       _p(xt_bf16, torch.bfloat16), _p(yt, torch.int32), xt_bf16.shape[0], slab, N, vmode,
+                                       alpha, mode, _p(out), _p(scratch), _stream()))
+
+
+def fn_nll_tc(model, noise, mu, rho, x_bf16, labels, row_weights, slab, wsum_out, nkl_out, nll_out, scratch):
+    """Per-sample weighted NLL sums (and optionally nkl / per-row NLL) of fn on the tensor path."""
+    _count(5)
+    _check(lib().psvi_fn_nll_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x_bf16, torch.bfloat16),
+                                _p(labels, torch.int32), _p(row_weights), x_bf16.shape[0], slab, _p(wsum_out), _p(nkl_out),
+                                _p(nll_out), _p(scratch), _stream()))
 
 
 def f32_to_bf16(src, dst):

@@ -228,6 +228,25 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
 /* fp32 -> bf16 (round to nearest even) copy of a row matrix, for callers that keep fp32 masters. */
 int psvi_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* ---- tensor-core sampled-GEMM forward for `fn` with ONE hidden layer in the large regime (kernels
+ * A/D "large"; BASELINE config 5: D=256, H=1024, S=64): VILinear -> ReLU -> VILinear -> Categorical log-lik
+ * (neural_net.py:155-179,267-297; psvi_classes.py:488-511,1031-1108) with bf16 operands / fp32 accumulation.  Sampled
+ * first-layer weights stream from L2 by TMA, both GEMMs run on tcgen05 (the hidden activations stay in TMEM), softmax /
+ * NLL / importance-weighted mixture are fused into the epilogue.
+ *   needs n_layers == 2, D a multiple of 64 (<= 256), H a multiple of 128, C <= 16, S <= 64.
+ * psvi_fn_predictive_tc: same contract as psvi_lr_predictive_tc (one noise slab over all n_rows; out [8]).
+ * psvi_fn_nll_tc: wsum_out[s] = sum_r row_weights[r] * nll[s, r] (row_weights nullable -> 1), nkl_out[s] (nullable) =
+ *   sum_layers sampled_nkl(), nll_out [S][n_rows] (nullable) -- the per-sample terms of inner_elbo / psvi_elbo.
+ *   scratch: psvi_fn_tc_scratch_bytes(model, max rows of any call, M) bytes. */
+size_t psvi_fn_tc_scratch_bytes(const psvi_mf_model* model, int64_t max_rows, int32_t M);
+int psvi_fn_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                          const float* u, const int32_t* z, const float* v, int32_t M, const void* xt_bf16,
+                          const int32_t* yt, int64_t n_rows, int32_t slab, float N, int32_t vmode, float alpha,
+                          int32_t mode, float* out, void* scratch, void* stream);
+int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                   const void* x_bf16, const int32_t* labels, const float* row_weights, int64_t n_rows, int32_t slab,
+                   float* wsum_out, float* nkl_out, float* nll_out, void* scratch, void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,
