@@ -15,26 +15,31 @@
 //   GEMM2  tcgen05.mma (A from TMEM), M=128, N=16 classes, K=128 hidden units, B = W2_s chunk (smem, SW128), accumulated
 //          over the H/128 chunks of the sample in a 16-column TMEM accumulator (two buffers across samples);
 //   final  (4 warps per sample, alternating halves): tcgen05.ld 16 logits -> + b2 -> softmax / NLL / mixture.
-// The hidden activations never leave the SM.  The MMA warp software-pipelines GEMM2(i) behind GEMM1(i+1) so the tensor pipe
+// The hidden activations never leave the SM.  Every work item starts at a different (sample, hidden chunk) position
+// (rotation by the item index) so that concurrently running CTAs stream different parts of W1 instead of hammering the same
+// L2 lines in lockstep.  The MMA warp software-pipelines GEMM2(i) behind GEMM1(i+1) so the tensor pipe
 // stays busy while the epilogue warps convert chunk i.
 #include "psvi_tc.cuh"
+#include <stdlib.h>
 
 using namespace psvi_tc;
 
 namespace {
 
 constexpr int BM = 128, BK = 64, BN = 128;   // row tile, K chunk (one 128-byte swizzle atom of bf16), hidden chunk
-constexpr int BST = 6;                       // W1 ring depth (6 x 16 KB)
+constexpr int BST = 10;                      // W1 ring depth (10 x 16 KB)
 constexpr int WST = 4;                       // second-layer chunk ring depth (4 x (4 KB + 512 B))
 constexpr int CW = 16;                       // classes padded to 16
 constexpr int FN_THREADS = 128 + 256;        // 4 role warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int STAGE_BYTES = BN * BK * 2;     // 16 KB: one [128 x 64] bf16 operand tile
 constexpr int W2_STAGE_BYTES = 2 * CW * 128; // two SW128 atoms of [16 rows x 64 k]
-constexpr int COL_ACC = 0, COL_HBF = 256, COL_D2 = 384;  // TMEM columns: 2 x 128 fp32 | 2 x 64 (bf16 pairs) | 2 x 16 fp32
+constexpr int COL_X = 0, COL_ACC = 128, COL_D2 = 384;  // TMEM columns: X tile (D/2 <= 128, bf16 pairs) | 2 x 128 fp32 (the
+                                                        // bf16 hidden activations overwrite them in place) | 2 x 16 fp32 logits
 constexpr int NKL_BLOCKS = 64;
 
 struct FnParams {
-  int n_rows, n_tiles, kc, H, hc, S, nsplit, mode;
+  int n_rows, n_tiles, D, kc, H, hc, S, nsplit, mode;
+  const __nv_bfloat16* x;  // [n_rows][D] bf16 rows
   const float* b1;       // [S][H]
   const float* b2;       // [S][CW]  (padding classes = -inf)
   const float* cw;       // [n_rows] row weights (mode 0; nullable -> 1)
@@ -63,37 +68,47 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) 
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));   // .x (first argument) -> low 16 bits
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __global__ void __launch_bounds__(FN_THREADS, 1)
-psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
-                          const __grid_constant__ CUtensorMap map_w2, const FnParams p) {
+psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                          const FnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve-up: [X: kc x 16 KB] [W1 ring: BST x 16 KB] [W2 ring: WST x 4 KB] [b1 ring: WST x 512 B] [w: 64 f32]
-  //           [xch: CW x 128 f32] [red: 8 f32] [barriers] [tmem slot]
-  uint8_t* sX = smem;
-  uint8_t* sB = sX + p.kc * STAGE_BYTES;
+  // carve-up: [W1 ring: BST x 16 KB] [W2 ring: WST x 4 KB] [b1 ring: WST x 512 B] [w: 64 f32] [xch: CW x 128 f32]
+  //           [red: 8 f32] [barriers] [tmem slot]
+  uint8_t* sB = smem;
   uint8_t* sW2 = sB + BST * STAGE_BYTES;
   float* sB1 = reinterpret_cast<float*>(sW2 + WST * W2_STAGE_BYTES);
   float* s_w = sB1 + WST * BN;
   float* s_xch = s_w + 64;
   float* s_red = s_xch + CW * BM;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8);
-  uint64_t* xfull = bars;            // [1]  X tile landed
+  uint64_t* xfull = bars;            // [1]  the 8 epilogue warps have stored the X tile into TMEM
   uint64_t* xempty = bars + 1;       // [1]  every GEMM1 of the item has read the X tile
   uint64_t* full = bars + 2;         // [BST] W1 stage landed
   uint64_t* empty = full + BST;      // [BST] W1 stage consumed
   uint64_t* wfull = empty + BST;     // [WST] W2 chunk + b1 chunk landed
   uint64_t* wempty = wfull + WST;    // [WST] GEMM2 done with the W2 chunk (1 commit) and the 8 epilogue warps done with b1
   uint64_t* tfull = wempty + WST;    // [2]  GEMM1 accumulator complete
-  uint64_t* tempty = tfull + 2;      // [2]  the 8 epilogue warps have read the accumulator
-  uint64_t* hfull = tempty + 2;      // [2]  the 8 epilogue warps have stored the bf16 hidden activations
-  uint64_t* hempty = hfull + 2;      // [2]  GEMM2 has consumed them
-  uint64_t* lfull = hempty + 2;      // [2]  logits of a sample complete
+  uint64_t* hfull = tfull + 2;       // [2]  the 8 epilogue warps have stored the bf16 hidden activations (in place)
+  uint64_t* lfull = hfull + 2;       // [2]  logits of a sample complete
   uint64_t* lempty = lfull + 2;      // [2]  the 4 final warps have read them
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lempty + 2);
 
@@ -105,12 +120,11 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
       for (int s = 0; s < p.S; ++s) se += expf(p.lw[s] - mx);
     }
     for (int s = 0; s < 64; ++s) s_w[s] = s < p.S ? (p.mode == 1 ? expf(p.lw[s] - mx) / se : 1.f / (float)p.S) : 0.f;
-    mbar_init(xfull, 1); mbar_init(xempty, 1);
+    mbar_init(xfull, 8); mbar_init(xempty, 1);
     for (int i = 0; i < BST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 9); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8);
-      mbar_init(&hfull[i], 8); mbar_init(&hempty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&hfull[i], 8);
       mbar_init(&lfull[i], 1); mbar_init(&lempty[i], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -127,84 +141,100 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      int st = 0, it = 0, item = 0;
-      uint32_t ph = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-        const int tile = w / p.nsplit, split = w - tile * p.nsplit;
-        mbar_wait(xempty, (item & 1) ^ 1);
-        mbar_expect_tx(xfull, (uint32_t)(p.kc * STAGE_BYTES));
-        for (int k = 0; k < p.kc; ++k) tma_load_2d(&map_x, xfull, sX + k * STAGE_BYTES, k * BK, tile * BM);
-        for (int s = split; s < p.S; s += p.nsplit) {
-          for (int h = 0; h < p.hc; ++h, ++it) {
-            const int wi = it % WST;
-            mbar_wait(&wempty[wi], ((it / WST) & 1) ^ 1);
+    // (the whole warp runs the loop so that control flow stays warp-uniform; one elected lane issues the copies)
+    int st = 0, it = 0;
+    uint32_t ph = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int tile = w / p.nsplit, split = w - tile * p.nsplit;
+      const int ns = (p.S - split + p.nsplit - 1) / p.nsplit, srot = w % ns, hrot = (w / ns) % p.hc;
+      for (int js = 0; js < ns; ++js) {
+        const int s = split + ((js + srot) % ns) * p.nsplit;
+        for (int hh = 0; hh < p.hc; ++hh, ++it) {
+          const int h = (hh + hrot) % p.hc;
+          const int wi = it % WST;
+          mbar_wait(&wempty[wi], ((it / WST) & 1) ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&wfull[wi], W2_STAGE_BYTES + BN * 4);
             tma_load_2d(&map_w2, &wfull[wi], sW2 + wi * W2_STAGE_BYTES, h * BN, s * CW);
             tma_load_2d(&map_w2, &wfull[wi], sW2 + wi * W2_STAGE_BYTES + CW * 128, h * BN + BK, s * CW);
             bulk_load_1d(sB1 + wi * BN, p.b1 + (size_t)s * p.H + h * BN, BN * 4, &wfull[wi]);
-            for (int k = 0; k < p.kc; ++k) {
-              mbar_wait(&empty[st], ph ^ 1);
+          }
+          __syncwarp();
+          for (int k = 0; k < p.kc; ++k) {
+            mbar_wait(&empty[st], ph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(&full[st], STAGE_BYTES);
               tma_load_2d(&map_w1, &full[st], sB + st * STAGE_BYTES, k * BK, s * p.H + h * BN);
-              if (++st == BST) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++st == BST) { st = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int st = 0, it = 0, item = 0, jsamp = 0;
-      uint32_t ph = 0;
-      int pend_it = -1, pend_h = 0, pend_js = 0;   // GEMM2 of chunk `pend_it` is issued after GEMM1 of the next chunk
-      auto gemm2 = [&](int c_it, int c_h, int c_js) {
-        const int buf = c_it & 1, wi = c_it % WST, sb = c_js & 1;
-        mbar_wait(&wfull[wi], (c_it / WST) & 1);
-        if (c_h == 0) mbar_wait(&lempty[sb], ((c_js >> 1) & 1) ^ 1);
-        mbar_wait(&hfull[buf], (c_it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t d2 = tmem_base + COL_D2 + sb * CW, a2 = tmem_base + COL_HBF + buf * (BN / 2);
-        const uint32_t b0 = smem_u32(sW2 + wi * W2_STAGE_BYTES);
+    // warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit (keeps ptxas from wrapping every
+    // uniform-datapath instruction in a per-thread serialisation loop).  tcgen05.mma operations execute in issue order,
+    // so GEMM1(i+2) overwriting the accumulator buffer that GEMM2(i) reads as its A operand needs no barrier.
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int st = 0, it = 0, item = 0, jsamp = 0;
+    uint32_t ph = 0;
+    int pend_it = -1, pend_h = 0, pend_js = 0;   // GEMM2 of chunk `pend_it` is issued after GEMM1 of the next chunk
+    auto gemm2 = [&](int c_it, int c_h, int c_js) {
+      const int buf = c_it & 1, wi = c_it % WST, sb = c_js & 1;
+      mbar_wait(&wfull[wi], (c_it / WST) & 1);
+      if (c_h == 0) mbar_wait(&lempty[sb], ((c_js >> 1) & 1) ^ 1);
+      mbar_wait(&hfull[buf], (c_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d2 = tmem_base + COL_D2 + sb * CW, a2 = tmem_base + COL_ACC + buf * BN;
+      const uint32_t b0 = smem_u32(sW2 + wi * W2_STAGE_BYTES);
+      const uint32_t acc0 = c_h != 0;
+      if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < BN / 16; ++j)
-          umma_bf16_ts(d2, a2 + j * 8, make_desc_sw128(b0 + (j >> 2) * (CW * 128) + (j & 3) * 32), idesc2, (c_h | j) != 0);
-        umma_commit(&hempty[buf]);
+        for (int j = 0; j < BN / 16; ++j)   // the bf16 activations of hidden units 64 part + 16 jj .. sit at columns 64 part + 8 jj
+          umma_bf16_ts(d2, a2 + (j >> 2) * 64 + (j & 3) * 8, make_desc_sw128(b0 + (j >> 2) * (CW * 128) + (j & 3) * 32), idesc2,
+                       j ? 1u : acc0);
         umma_commit(&wempty[wi]);
         if (c_h == p.hc - 1) umma_commit(&lfull[sb]);
-      };
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-        const int tile = w / p.nsplit, split = w - tile * p.nsplit;
-        (void)tile;
-        mbar_wait(xfull, item & 1);
-        tc_fence_after();
-        for (int s = split; s < p.S; s += p.nsplit, ++jsamp) {
-          for (int h = 0; h < p.hc; ++h, ++it) {
-            const int buf = it & 1;
-            mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+      }
+      __syncwarp();
+    };
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
+      const int tile = w / p.nsplit, split = w - tile * p.nsplit;
+      (void)tile;
+      mbar_wait(xfull, item & 1);
+      tc_fence_after();
+      const int ns = (p.S - split + p.nsplit - 1) / p.nsplit;
+      for (int js = 0; js < ns; ++js, ++jsamp) {
+        for (int h = 0; h < p.hc; ++h, ++it) {   // h counts chunks in issue order (the producer rotates the actual chunk)
+          const int buf = it & 1;
+          const uint32_t tmem_d = tmem_base + COL_ACC + buf * BN;
+          for (int k = 0; k < p.kc; ++k) {
+            mbar_wait(&full[st], ph);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + COL_ACC + buf * BN;
-            for (int k = 0; k < p.kc; ++k) {
-              mbar_wait(&full[st], ph);
-              tc_fence_after();
-              const uint32_t a0 = smem_u32(sX + k * STAGE_BYTES), b0 = smem_u32(sB + st * STAGE_BYTES);
+            const uint32_t a0 = tmem_base + COL_X + k * (BK / 2), b0 = smem_u32(sB + st * STAGE_BYTES);
+            const uint32_t acc0 = k != 0;
+            if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j)
-                umma_bf16(tmem_d, make_desc_sw128(a0 + j * 32), make_desc_sw128(b0 + j * 32), idesc1, (k | j) != 0);
+                umma_bf16_ts(tmem_d, a0 + j * 8, make_desc_sw128(b0 + j * 32), idesc1, j ? 1u : acc0);
               umma_commit(&empty[st]);
-              if (++st == BST) { st = 0; ph ^= 1; }
+              if (k == p.kc - 1) umma_commit(&tfull[buf]);
             }
-            umma_commit(&tfull[buf]);
-            if (pend_it >= 0) gemm2(pend_it, pend_h, pend_js);
-            pend_it = it; pend_h = h; pend_js = jsamp;
+            __syncwarp();
+            if (++st == BST) { st = 0; ph ^= 1; }
           }
+          if (pend_it >= 0) gemm2(pend_it, pend_h, pend_js);
+          pend_it = it; pend_h = h; pend_js = jsamp;
         }
-        umma_commit(xempty);  // every GEMM1 that reads this X tile has completed when this arrives
       }
-      if (pend_it >= 0) gemm2(pend_it, pend_h, pend_js);
+      // the epilogue warps store the next X tile only after they have finished this item's last sample, which needs the
+      // pending GEMM2: flush it here (one short bubble per work item)
+      if (pend_it >= 0) { gemm2(pend_it, pend_h, pend_js); pend_it = -1; }
+      if (elect_one()) umma_commit(xempty);  // every GEMM1 that reads this X tile has completed when this arrives
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------------- epilogue warps
@@ -213,17 +243,40 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     float nll_sum = 0.f, correct = 0.f;
-    int it = 0, jsamp = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    int it = 0, jsamp = 0, item = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const int tile = w / p.nsplit, split = w - tile * p.nsplit;
       const int row = tile * BM + rl;
       const bool rok = row < p.n_rows;
       const int y = rok ? __ldg(p.labels + row) : 0;
       const float cwr = (rok && p.mode == 0) ? (p.cw ? __ldg(p.cw + row) : 1.f) : 0.f;
+      {
+        // X tile -> TMEM as the A operand of GEMM1: thread (row) stores its own bf16 row, the two warps of a lane quarter
+        // take one half of the K range each (column c holds K elements 2c, 2c+1)
+        mbar_wait(xempty, (item & 1) ^ 1);
+        tc_fence_after();
+        const int qn = p.D >> 6;          // 16-column groups per half row (D/2 columns per row, D/4 per warp)
+        const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)row * p.D) + part * (p.D >> 4);
+        for (int g = 0; g < qn; ++g) {
+          uint32_t xr[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 t = rok ? __ldg(src + g * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
+            xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w;
+          }
+          tmem_st16(lane_addr + COL_X + part * (p.D >> 2) + g * 16, xr);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xfull);
+      }
       float probs[CW];
 #pragma unroll
       for (int c = 0; c < CW; ++c) probs[c] = 0.f;
-      for (int s = split; s < p.S; s += p.nsplit, ++jsamp) {
+      const int ns = (p.S - split + p.nsplit - 1) / p.nsplit, srot = w % ns;
+      for (int js = 0; js < ns; ++js, ++jsamp) {
+        const int s = split + ((js + srot) % ns) * p.nsplit;
         for (int h = 0; h < p.hc; ++h, ++it) {
           const int buf = it & 1, wi = it % WST;
           mbar_wait(&wfull[wi], (it / WST) & 1);      // b1 chunk
@@ -243,12 +296,11 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
               pk[g * 16 + j * 2 + 1] = pack_relu_bf16(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
             }
           }
-          mbar_wait(&hempty[buf], ((it >> 1) & 1) ^ 1);   // GEMM2 of chunk it-2 has consumed this buffer
-          tc_fence_after();
-          tmem_st32(lane_addr + COL_HBF + buf * (BN / 2) + part * 32, pk);
+          // in place: this warp has read all 64 fp32 columns it owns; the bf16 pairs go into the first 32 of them
+          tmem_st32(taddr, pk);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { mbar_arrive(&hfull[buf]); mbar_arrive(&tempty[buf]); mbar_arrive(&wempty[wi]); }
+          if (lane == 0) { mbar_arrive(&hfull[buf]); mbar_arrive(&wempty[wi]); }
         }
         if (part == (jsamp & 1)) {
           // logits of this sample: softmax / NLL / mixture (the two warps of a lane quarter alternate samples)
@@ -594,24 +646,23 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles = (int)((n_rows + BM - 1) / BM);
   const int nsplit = split_for(tiles, S, sms < 148 ? sms : 148);
-  CUtensorMap map_x, map_w1, map_w2;
-  int rc = make_map_2d_bf16(&map_x, x_bf16, (uint64_t)D, (uint64_t)n_rows, BK, BM);
-  if (rc) return rc;
-  rc = make_map_2d_bf16(&map_w1, sc.W1b, (uint64_t)D, (uint64_t)S * H, BK, BN);
+  CUtensorMap map_w1, map_w2;
+  int rc = make_map_2d_bf16(&map_w1, sc.W1b, (uint64_t)D, (uint64_t)S * H, BK, BN);
   if (rc) return rc;
   rc = make_map_2d_bf16(&map_w2, sc.W2b, (uint64_t)H, (uint64_t)S * CW, BK, CW);
   if (rc) return rc;
   FnParams p;
   memset(&p, 0, sizeof(p));
-  p.n_rows = (int)n_rows; p.n_tiles = tiles; p.kc = D / BK; p.H = H; p.hc = H / BN; p.S = S; p.nsplit = nsplit; p.mode = mode;
+  p.n_rows = (int)n_rows; p.n_tiles = tiles; p.D = D; p.kc = D / BK; p.H = H; p.hc = H / BN; p.S = S; p.nsplit = nsplit;
+  p.mode = mode; p.x = static_cast<const __nv_bfloat16*>(x_bf16);
   p.b1 = sc.b1; p.b2 = sc.b2; p.cw = cw; p.lw = lw; p.labels = labels; p.nll_out = nll_out; p.part = sc.part;
   p.probs_out = sc.probs;
   const int items = tiles * nsplit;
   const int grid = items < sms ? items : sms;
-  const size_t smem = (size_t)p.kc * STAGE_BYTES + BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 +
-                      CW * BM * 4 + 8 * 4 + (2 + 2 * BST + 2 * WST + 12) * 8 + 16 + 1024;
+  const size_t smem = (size_t)BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 + CW * BM * 4 + 8 * 4 +
+                      (2 + 2 * BST + 2 * WST + 8) * 8 + 16 + 1024;
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  psvi_fn_forward_tc_kernel<<<grid, FN_THREADS, smem, stream>>>(map_x, map_w1, map_w2, p);
+  psvi_fn_forward_tc_kernel<<<grid, FN_THREADS, smem, stream>>>(map_w1, map_w2, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   if (mode == 0) {
     fn_sum_tiles_kernel<<<1, 64, 0, stream>>>(sc.part, tiles, S, add, out);
