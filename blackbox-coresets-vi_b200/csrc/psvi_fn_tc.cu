@@ -27,19 +27,21 @@ using namespace psvi_tc;
 namespace {
 
 constexpr int BM = 128, BK = 64, BN = 128;   // row tile, K chunk (one 128-byte swizzle atom of bf16), hidden chunk
-constexpr int BST = 10;                      // W1 ring depth (10 x 16 KB)
+constexpr int BST = 5;                       // W1 ring depth (5 stages of up to two [128 x 64] K-chunks = 32 KB)
 constexpr int WST = 4;                       // second-layer chunk ring depth (4 x (4 KB + 512 B))
 constexpr int CW = 16;                       // classes padded to 16
 constexpr int FN_THREADS = 128 + 256;        // 4 role warps + 8 epilogue warps (two per TMEM lane quarter)
-constexpr int STAGE_BYTES = BN * BK * 2;     // 16 KB: one [128 x 64] bf16 operand tile
+constexpr int KCH_BYTES = BN * BK * 2;       // 16 KB: one [128 x 64] bf16 operand tile (one K-chunk)
+constexpr int STAGE_BYTES = 2 * KCH_BYTES;   // a ring stage holds two K-chunks (one when D / 64 is odd)
 constexpr int W2_STAGE_BYTES = 2 * CW * 128; // two SW128 atoms of [16 rows x 64 k]
 constexpr int COL_X = 0, COL_ACC = 128, COL_D2 = 384;  // TMEM columns: X tile (D/2 <= 128, bf16 pairs) | 2 x 128 fp32 (the
-                                                        // bf16 hidden activations overwrite them in place) | 2 x 16 fp32 logits
+                                                        // bf16 hidden activations overwrite them in place) | 2 x (4 x 16) fp32 logits
 constexpr int NKL_BLOCKS = 64;
 
 struct FnParams {
-  int n_rows, n_tiles, D, kc, H, hc, S, nsplit, mode;
+  int n_rows, n_tiles, D, kc, ks, H, hc, S, nsplit, mode;   // kc = D / 64 K-chunks, ks = K-chunks per ring stage
   const __nv_bfloat16* x;  // [n_rows][D] bf16 rows
+  unsigned long long* prof;  // PSVI_FN_PROF builds: [grid][4][8] cycle counters
   const float* b1;       // [S][H]
   const float* b2;       // [S][CW]  (padding classes = -inf)
   const float* cw;       // [n_rows] row weights (mode 0; nullable -> 1)
@@ -77,6 +79,18 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));   // .x (first argument) -> low 16 bits
   return *reinterpret_cast<uint32_t*>(&t);
 }
+
+// cycle-counter instrumentation of the role warps (build with -DPSVI_FN_PROF; scratch/prof_fn_tc.py prints it)
+#ifdef PSVI_FN_PROF
+#define PROF_DECL unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tstart = clock64();
+#define PROF_T(slot, stmt) do { const long long _t0 = clock64(); stmt; pc[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+#define PROF_OUT(row) do { if (p.prof && lane == 0) { unsigned long long* o = p.prof + (size_t)blockIdx.x * 32 + (row) * 8; \
+    for (int i = 0; i < 7; ++i) o[i] = pc[i]; o[7] = (unsigned long long)(clock64() - tstart); } } while (0)
+#else
+#define PROF_DECL
+#define PROF_T(slot, stmt) stmt
+#define PROF_OUT(row)
+#endif
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
   asm volatile(
@@ -144,6 +158,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     // (the whole warp runs the loop so that control flow stays warp-uniform; one elected lane issues the copies)
     int st = 0, it = 0;
     uint32_t ph = 0;
+    PROF_DECL
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int tile = w / p.nsplit, split = w - tile * p.nsplit;
       const int ns = (p.S - split + p.nsplit - 1) / p.nsplit, srot = w % ns, hrot = (w / ns) % p.hc;
@@ -152,7 +167,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         for (int hh = 0; hh < p.hc; ++hh, ++it) {
           const int h = (hh + hrot) % p.hc;
           const int wi = it % WST;
-          mbar_wait(&wempty[wi], ((it / WST) & 1) ^ 1);
+          PROF_T(0, mbar_wait(&wempty[wi], ((it / WST) & 1) ^ 1));
           if (elect_one()) {
             mbar_expect_tx(&wfull[wi], W2_STAGE_BYTES + BN * 4);
             tma_load_2d(&map_w2, &wfull[wi], sW2 + wi * W2_STAGE_BYTES, h * BN, s * CW);
@@ -160,11 +175,12 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
             bulk_load_1d(sB1 + wi * BN, p.b1 + (size_t)s * p.H + h * BN, BN * 4, &wfull[wi]);
           }
           __syncwarp();
-          for (int k = 0; k < p.kc; ++k) {
-            mbar_wait(&empty[st], ph ^ 1);
+          for (int k = 0; k < p.kc; k += p.ks) {
+            PROF_T(1, mbar_wait(&empty[st], ph ^ 1));
             if (elect_one()) {
-              mbar_expect_tx(&full[st], STAGE_BYTES);
-              tma_load_2d(&map_w1, &full[st], sB + st * STAGE_BYTES, k * BK, s * p.H + h * BN);
+              mbar_expect_tx(&full[st], (uint32_t)(p.ks * KCH_BYTES));
+              for (int kk = 0; kk < p.ks; ++kk)
+                tma_load_2d(&map_w1, &full[st], sB + st * STAGE_BYTES + kk * KCH_BYTES, (k + kk) * BK, s * p.H + h * BN);
             }
             __syncwarp();
             if (++st == BST) { st = 0; ph ^= 1; }
@@ -172,6 +188,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         }
       }
     }
+    PROF_OUT(0);
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     // warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit (keeps ptxas from wrapping every
@@ -182,47 +199,53 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     int st = 0, it = 0, item = 0, jsamp = 0;
     uint32_t ph = 0;
     int pend_it = -1, pend_h = 0, pend_js = 0;   // GEMM2 of chunk `pend_it` is issued after GEMM1 of the next chunk
+    PROF_DECL
     auto gemm2 = [&](int c_it, int c_h, int c_js) {
       const int buf = c_it & 1, wi = c_it % WST, sb = c_js & 1;
-      mbar_wait(&wfull[wi], (c_it / WST) & 1);
-      if (c_h == 0) mbar_wait(&lempty[sb], ((c_js >> 1) & 1) ^ 1);
-      mbar_wait(&hfull[buf], (c_it >> 1) & 1);
+      PROF_T(0, mbar_wait(&wfull[wi], (c_it / WST) & 1));
+      if (c_h == 0) PROF_T(1, mbar_wait(&lempty[sb], ((c_js >> 1) & 1) ^ 1));
+      PROF_T(2, mbar_wait(&hfull[buf], (c_it >> 1) & 1));
       tc_fence_after();
-      const uint32_t d2 = tmem_base + COL_D2 + sb * CW, a2 = tmem_base + COL_ACC + buf * BN;
+      const uint32_t d2 = tmem_base + COL_D2 + sb * (4 * CW), a2 = tmem_base + COL_ACC + buf * BN;
       const uint32_t b0 = smem_u32(sW2 + wi * W2_STAGE_BYTES);
       const uint32_t acc0 = c_h != 0;
-      if (elect_one()) {
+      PROF_T(3, if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < BN / 16; ++j)   // the bf16 activations of hidden units 64 part + 16 jj .. sit at columns 64 part + 8 jj
-          umma_bf16_ts(d2, a2 + (j >> 2) * 64 + (j & 3) * 8, make_desc_sw128(b0 + (j >> 2) * (CW * 128) + (j & 3) * 32), idesc2,
-                       j ? 1u : acc0);
+          umma_bf16_ts(d2 + (j & 3) * CW, a2 + (j >> 2) * 64 + (j & 3) * 8,
+                       make_desc_sw128(b0 + (j >> 2) * (CW * 128) + (j & 3) * 32), idesc2, (j >> 2) ? 1u : acc0);
         umma_commit(&wempty[wi]);
         if (c_h == p.hc - 1) umma_commit(&lfull[sb]);
-      }
+      });
       __syncwarp();
     };
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const int tile = w / p.nsplit, split = w - tile * p.nsplit;
       (void)tile;
-      mbar_wait(xfull, item & 1);
+      PROF_T(4, mbar_wait(xfull, item & 1));
       tc_fence_after();
       const int ns = (p.S - split + p.nsplit - 1) / p.nsplit;
       for (int js = 0; js < ns; ++js, ++jsamp) {
         for (int h = 0; h < p.hc; ++h, ++it) {   // h counts chunks in issue order (the producer rotates the actual chunk)
           const int buf = it & 1;
           const uint32_t tmem_d = tmem_base + COL_ACC + buf * BN;
-          for (int k = 0; k < p.kc; ++k) {
-            mbar_wait(&full[st], ph);
+          for (int k = 0; k < p.kc; k += p.ks) {
+            PROF_T(5, mbar_wait(&full[st], ph));
             tc_fence_after();
             const uint32_t a0 = tmem_base + COL_X + k * (BK / 2), b0 = smem_u32(sB + st * STAGE_BYTES);
             const uint32_t acc0 = k != 0;
-            if (elect_one()) {
+            PROF_T(6, if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j)
                 umma_bf16_ts(tmem_d, a0 + j * 8, make_desc_sw128(b0 + j * 32), idesc1, j ? 1u : acc0);
+              if (p.ks == 2) {
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j)
+                  umma_bf16_ts(tmem_d, a0 + BK / 2 + j * 8, make_desc_sw128(b0 + KCH_BYTES + j * 32), idesc1, 1u);
+              }
               umma_commit(&empty[st]);
-              if (k == p.kc - 1) umma_commit(&tfull[buf]);
-            }
+              if (k + p.ks >= p.kc) umma_commit(&tfull[buf]);
+            });
             __syncwarp();
             if (++st == BST) { st = 0; ph ^= 1; }
           }
@@ -236,6 +259,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       if (elect_one()) umma_commit(xempty);  // every GEMM1 that reads this X tile has completed when this arrives
       __syncwarp();
     }
+    PROF_OUT(1);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------------- epilogue warps
     const int q = warp & 3, part = (warp - 4) >> 2;  // TMEM lane quarter; which half of the 128 hidden columns
@@ -244,6 +268,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     float nll_sum = 0.f, correct = 0.f;
     int it = 0, jsamp = 0, item = 0;
+    PROF_DECL
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const int tile = w / p.nsplit, split = w - tile * p.nsplit;
       const int row = tile * BM + rl;
@@ -279,9 +304,12 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         const int s = split + ((js + srot) % ns) * p.nsplit;
         for (int h = 0; h < p.hc; ++h, ++it) {
           const int buf = it & 1, wi = it % WST;
-          mbar_wait(&wfull[wi], (it / WST) & 1);      // b1 chunk
-          mbar_wait(&tfull[buf], (it >> 1) & 1);
+          PROF_T(0, mbar_wait(&wfull[wi], (it / WST) & 1));      // b1 chunk
+          PROF_T(1, mbar_wait(&tfull[buf], (it >> 1) & 1));
           tc_fence_after();
+#ifdef PSVI_FN_PROF
+          const long long _tw = clock64();
+#endif
           const float4* b1 = reinterpret_cast<const float4*>(sB1 + wi * BN + part * 64);
           const uint32_t taddr = lane_addr + COL_ACC + buf * BN + part * 64;
           uint32_t pk[32];
@@ -301,14 +329,24 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { mbar_arrive(&hfull[buf]); mbar_arrive(&wempty[wi]); }
+#ifdef PSVI_FN_PROF
+          pc[2] += (unsigned long long)(clock64() - _tw);
+#endif
         }
         if (part == (jsamp & 1)) {
           // logits of this sample: softmax / NLL / mixture (the two warps of a lane quarter alternate samples)
           const int sb = jsamp & 1;
-          mbar_wait(&lfull[sb], (jsamp >> 1) & 1);
+          PROF_T(3, mbar_wait(&lfull[sb], (jsamp >> 1) & 1));
           tc_fence_after();
           float lg[CW];
-          tmem_ld16(lane_addr + COL_D2 + sb * CW, lg);
+          tmem_ld16(lane_addr + COL_D2 + sb * (4 * CW), lg);
+#pragma unroll
+          for (int a = 1; a < 4; ++a) {   // GEMM2 rotates over four accumulators (no dependent chain of tiny MMAs)
+            float t[CW];
+            tmem_ld16(lane_addr + COL_D2 + sb * (4 * CW) + a * CW, t);
+#pragma unroll
+            for (int c = 0; c < CW; ++c) lg[c] += t[c];
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&lempty[sb]);
@@ -371,6 +409,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         asm volatile("bar.sync 1, 256;" ::: "memory");   // s_xch is reused by the next item
       }
     }
+    if (warp == 4) PROF_OUT(2);
+    if (warp == 8) PROF_OUT(3);
     if (p.mode != 0 && p.nsplit == 1 && part == 0) {
       nll_sum = warp_sum(nll_sum);
       correct = warp_sum(correct);
@@ -653,17 +693,39 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   if (rc) return rc;
   FnParams p;
   memset(&p, 0, sizeof(p));
-  p.n_rows = (int)n_rows; p.n_tiles = tiles; p.D = D; p.kc = D / BK; p.H = H; p.hc = H / BN; p.S = S; p.nsplit = nsplit;
+  p.n_rows = (int)n_rows; p.n_tiles = tiles; p.D = D; p.kc = D / BK; p.ks = (p.kc % 2 == 0) ? 2 : 1; p.H = H; p.hc = H / BN; p.S = S; p.nsplit = nsplit;
   p.mode = mode; p.x = static_cast<const __nv_bfloat16*>(x_bf16);
   p.b1 = sc.b1; p.b2 = sc.b2; p.cw = cw; p.lw = lw; p.labels = labels; p.nll_out = nll_out; p.part = sc.part;
   p.probs_out = sc.probs;
   const int items = tiles * nsplit;
   const int grid = items < sms ? items : sms;
+#ifdef PSVI_FN_PROF
+  static unsigned long long* prof_buf = nullptr;
+  const bool prof = getenv("PSVI_FN_PROF") != nullptr;
+  if (prof && !prof_buf) cudaMalloc(&prof_buf, 256 * 32 * 8);
+  if (prof) cudaMemsetAsync(prof_buf, 0, 256 * 32 * 8, stream);
+  p.prof = prof ? prof_buf : nullptr;
+#endif
   const size_t smem = (size_t)BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 + CW * BM * 4 + 8 * 4 +
                       (2 + 2 * BST + 2 * WST + 8) * 8 + 16 + 1024;
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   psvi_fn_forward_tc_kernel<<<grid, FN_THREADS, smem, stream>>>(map_w1, map_w2, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
+#ifdef PSVI_FN_PROF
+  if (prof) {
+    static unsigned long long hb[256 * 32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hb, prof_buf, sizeof(hb), cudaMemcpyDeviceToHost);
+    const char* names[4] = {"producer: wempty empty - - - - - total", "mma: wfull lempty hfull g2issue xfull full g1issue total",
+                            "epi w4: wfull tfull work lfull - - - total", "epi w8: same"};
+    for (int b = 0; b < grid; b += (grid > 4 ? grid / 2 : 1))
+      for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "[prof cta %d] %s:", b, names[r]);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", hb[b * 32 + r * 8 + i]);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
   if (mode == 0) {
     fn_sum_tiles_kernel<<<1, 64, 0, stream>>>(sc.part, tiles, S, add, out);
   } else if (nsplit > 1) {

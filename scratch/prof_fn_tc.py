@@ -2,6 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "blackbox-coresets-vi_b200"))
 import numpy as np, torch
 from psvi import _native as nat
+nat.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpsvi_b200_prof.so')  # -DPSVI_FN_PROF build
 D, H, C, S, M = 256, 1024, 10, 64, 1000
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 model = nat.make_model([D, H, C], S)
