@@ -1,0 +1,582 @@
+// psvi_lenet.cu -- the convolutional family of the PSVI hot path: the per-sample network pass
+// of `lenet` (reference psvi/models/neural_net.py:194-246 VIConv2d, :249-255 BatchMaxPool2d, :334-359 make_lenet) on
+// externally supplied sampled weights theta [S][P], in the three flavours the streaming PSVI engine needs
+// (psvi/inference/stream.py; same contract as psvi_net_pass):
+//   forward          -> nll [S][R] (and logits)
+//   gradient pass    -> tbar = d/dtheta_s, xbar = d/dx per sample, with per-sample row weights cw [S][R]
+//   dual (HVP) pass  -> tbar = A_theta, tdbar = A_thetadot, xbar = A_x, acbar = adjoint of the row weights  (SURVEY A.6,
+//                       generalised: a conv layer is a linear map, ReLU + max-pool a fixed selection)
+// Network: conv(1->6, 5x5, pad 2) ReLU pool2 | conv(6->16, 5x5) ReLU pool2 | flatten 400 | fc 120 ReLU | fc 84 ReLU | fc 10.
+// theta layout (TL): per layer weight then bias: W1[6][1][5][5] b1[6] W2[16][6][5][5] b2[16] W3[120][400] b3[120]
+// W4[84][120] b4[84] W5[10][84] b5[10]  (P = 61 706).
+// fp32 on the CUDA cores: the products have K = 25 / 150 and N = 6 / 16 -- far below a 128-wide UMMA tile -- and the
+// reference computes this family in fp32.  One CTA per (row, sample) keeps a whole image's feature maps in shared memory:
+// conv + ReLU + pool are fused (the full-resolution maps never reach global memory; only the pooled map and a 3-bit
+// selection code per pooled element do), and the backward kernels scatter through that code on the fly.
+#include "psvi_common.cuh"
+
+namespace {
+
+constexpr int LN_P = 61706;
+constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 = 50572, O_W4 = 50692, O_B4 = 60772,
+              O_W5 = 60856, O_B5 = 61696;
+constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
+constexpr int RT = 8;   // rows per CTA of the fully connected kernels
+
+// ------------------------------------------------------------------------------------------------ conv + ReLU + pool
+// out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
+// sel = argmax (first maximum in row-major window order, as torch's max_pool2d) | (max > 0) << 2;
+// tangent: the same selection applied to conv(in1, w1) + conv(in2, w2) + bias (all of them tangent quantities).
+template <int CI, int CO, int HIN, int PAD>
+__global__ void __launch_bounds__(256)
+conv_pool_fwd_kernel(const float* __restrict__ in1, size_t ss1, const float* __restrict__ w1, const float* __restrict__ in2,
+                     size_t ss2, const float* __restrict__ w2, const float* __restrict__ bias, int R, uint8_t* sel,
+                     int tangent, float* __restrict__ out) {
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25;
+  __shared__ float s_in1[CI * HP * HP], s_in2[CI * HP * HP], s_w1[NW], s_w2[NW], s_a[CO * HO * HO];
+  const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const float* i1 = in1 + (size_t)s * ss1 + (size_t)r * CI * HIN * HIN;
+  const float* i2 = in2 ? in2 + (size_t)s * ss2 + (size_t)r * CI * HIN * HIN : nullptr;
+  for (int i = tid; i < CI * HP * HP; i += 256) {
+    const int ci = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
+    const bool ok = yy >= 0 && yy < HIN && xx >= 0 && xx < HIN;
+    s_in1[i] = ok ? i1[(ci * HIN + yy) * HIN + xx] : 0.f;
+    s_in2[i] = (ok && i2) ? i2[(ci * HIN + yy) * HIN + xx] : 0.f;
+  }
+  for (int i = tid; i < NW; i += 256) {
+    s_w1[i] = w1[(size_t)s * LN_P + i];
+    s_w2[i] = w2 ? w2[(size_t)s * LN_P + i] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < CO * HO * HO; idx += 256) {
+    const int co = idx / (HO * HO), y = (idx / HO) % HO, x = idx % HO;
+    float acc = bias ? bias[(size_t)s * LN_P + co] : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      const float* a = s_in1 + (ci * HP + y) * HP + x;
+      const float* w = s_w1 + (co * CI + ci) * 25;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) acc = fmaf(a[ky * HP + kx], w[ky * 5 + kx], acc);
+    }
+    if (i2) {
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const float* a = s_in2 + (ci * HP + y) * HP + x;
+        const float* w = s_w2 + (co * CI + ci) * 25;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) acc = fmaf(a[ky * HP + kx], w[ky * 5 + kx], acc);
+      }
+    }
+    s_a[idx] = acc;
+  }
+  __syncthreads();
+  const size_t ob = ((size_t)s * R + r) * (CO * HQ * HQ);
+  for (int idx = tid; idx < CO * HQ * HQ; idx += 256) {
+    const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ;
+    const float* a = s_a + (co * HO + 2 * py) * HO + 2 * px;
+    const float c0 = a[0], c1 = a[1], c2 = a[HO], c3 = a[HO + 1];
+    if (!tangent) {
+      float best = fmaxf(c0, 0.f);
+      int k = 0;
+      if (fmaxf(c1, 0.f) > best) { best = fmaxf(c1, 0.f); k = 1; }
+      if (fmaxf(c2, 0.f) > best) { best = fmaxf(c2, 0.f); k = 2; }
+      if (fmaxf(c3, 0.f) > best) { best = fmaxf(c3, 0.f); k = 3; }
+      sel[ob + idx] = (uint8_t)(k | ((best > 0.f) ? 4 : 0));
+      out[ob + idx] = best;
+    } else {
+      const int c = sel[ob + idx], k = c & 3;
+      const float v = k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3));
+      out[ob + idx] = (c & 4) ? v : 0.f;
+    }
+  }
+}
+
+// d/d(input map) of the fused conv + ReLU + pool: the pooled adjoints pb1 (and pb2) are scattered to full resolution through
+// the selection code, then out[ci][y][x] = sum_co sum_k a1[co][y+PAD-ky][x+PAD-kx] w1[co][ci][ky][kx]  (+ the same with a2, w2).
+template <int CI, int CO, int HIN, int PAD>
+__global__ void __launch_bounds__(256)
+conv_bwd_data_kernel(const float* __restrict__ pb1, const float* __restrict__ w1, const float* __restrict__ pb2,
+                     const float* __restrict__ w2, const uint8_t* __restrict__ sel, int R, float* __restrict__ out) {
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25;
+  __shared__ float s_a1[CO * HO * HO], s_a2[CO * HO * HO], s_w1[NW], s_w2[NW];
+  const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < CO * HO * HO; i += 256) { s_a1[i] = 0.f; s_a2[i] = 0.f; }
+  for (int i = tid; i < NW; i += 256) {
+    s_w1[i] = w1[(size_t)s * LN_P + i];
+    s_w2[i] = w2 ? w2[(size_t)s * LN_P + i] : 0.f;
+  }
+  __syncthreads();
+  const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
+  for (int idx = tid; idx < CO * HQ * HQ; idx += 256) {
+    const int c = sel[pbase + idx];
+    if (c & 4) {
+      const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ, k = c & 3;
+      const int o = (co * HO + 2 * py + (k >> 1)) * HO + 2 * px + (k & 1);
+      s_a1[o] = pb1[pbase + idx];
+      if (pb2) s_a2[o] = pb2[pbase + idx];
+    }
+  }
+  __syncthreads();
+  const size_t ob = ((size_t)s * R + r) * (CI * HIN * HIN);
+  for (int idx = tid; idx < CI * HIN * HIN; idx += 256) {
+    const int ci = idx / (HIN * HIN), y = (idx / HIN) % HIN, x = idx % HIN;
+    float acc = 0.f;
+    for (int co = 0; co < CO; ++co) {
+      const float* wa = s_w1 + (co * CI + ci) * 25;
+      const float* wb = s_w2 + (co * CI + ci) * 25;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        const int oy = y + PAD - ky;
+        if (oy < 0 || oy >= HO) continue;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const int ox = x + PAD - kx;
+          if (ox < 0 || ox >= HO) continue;
+          const int o = (co * HO + oy) * HO + ox;
+          acc = fmaf(s_a1[o], wa[ky * 5 + kx], acc);
+          if (pb2) acc = fmaf(s_a2[o], wb[ky * 5 + kx], acc);
+        }
+      }
+    }
+    out[ob + idx] = acc;
+  }
+}
+
+// d/d(weights, bias) of the fused conv + ReLU + pool, one CTA per (output channel, sample), reduced over rows and positions:
+//   wbar[s][co][ci][ky][kx] (+)= sum_r sum_{y,x} a[s][r][co][y][x] in[(s)][r][ci][y+ky-PAD][x+kx-PAD];  bbar[s][co] = sum a
+template <int CI, int CO, int HIN, int PAD>
+__global__ void __launch_bounds__(256)
+conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__ sel, const float* __restrict__ in, size_t ss,
+                       int R, float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NO = CI * 25, NG = 256 / NO;
+  __shared__ float s_a[HO * HO], s_in[CI * HP * HP], s_red[256];
+  const int co = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const int o = tid % NO, g = tid / NO;
+  const bool active = g < NG;
+  const int ci = o / 25, ky = (o % 25) / 5, kx = o % 5;
+  float acc = 0.f, bacc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const float* ip = in + (size_t)s * ss + (size_t)r * CI * HIN * HIN;
+    for (int i = tid; i < CI * HP * HP; i += 256) {
+      const int c = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
+      s_in[i] = (yy >= 0 && yy < HIN && xx >= 0 && xx < HIN) ? ip[(c * HIN + yy) * HIN + xx] : 0.f;
+    }
+    for (int i = tid; i < HO * HO; i += 256) s_a[i] = 0.f;
+    __syncthreads();
+    const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ) + (size_t)co * HQ * HQ;
+    for (int idx = tid; idx < HQ * HQ; idx += 256) {
+      const int c = sel[pbase + idx];
+      if (c & 4) {
+        const int py = idx / HQ, px = idx % HQ, k = c & 3;
+        s_a[(2 * py + (k >> 1)) * HO + 2 * px + (k & 1)] = pb[pbase + idx];
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const float* ib = s_in + (ci * HP + ky) * HP + kx;
+      for (int pos = g; pos < HO * HO; pos += NG) acc = fmaf(s_a[pos], ib[(pos / HO) * HP + pos % HO], acc);
+    }
+    if (bbar)
+      for (int pos = tid; pos < HO * HO; pos += 256) bacc += s_a[pos];
+    __syncthreads();
+  }
+  s_red[tid] = active ? acc : 0.f;
+  __syncthreads();
+  if (tid < NO) {
+    float t = 0.f;
+    for (int k = 0; k < NG; ++k) t += s_red[tid + k * NO];
+    float* dst = wbar + (size_t)s * LN_P + co * NO + tid;
+    *dst = accumulate ? *dst + t : t;
+  }
+  if (bbar) {
+    __syncthreads();
+    s_red[tid] = bacc;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+      if (tid < k) s_red[tid] += s_red[tid + k];
+      __syncthreads();
+    }
+    if (tid == 0) bbar[(size_t)s * LN_P + co] = s_red[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fully connected layers
+// out[s][r][o] = (bias[s][o] + sum_i x1[s][r][i] w1[s][o][i] (+ x2 . w2)); relu -> max(., 0); maskfrom -> * (maskfrom > 0)
+__global__ void __launch_bounds__(128)
+lin_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ x2,
+               const float* __restrict__ w2, const float* __restrict__ bias, int R, int IN, int OUT, int relu,
+               const float* __restrict__ maskfrom, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sx1 = sm;
+  float* sx2 = sm + RT * IN;
+  const int r0 = blockIdx.x * RT, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < RT * IN; i += 128) {
+    const int rr = i / IN, row = r0 + rr;
+    const size_t src = ((size_t)s * R + row) * IN + i % IN;
+    sx1[i] = row < R ? x1[src] : 0.f;
+    sx2[i] = (row < R && x2) ? x2[src] : 0.f;
+  }
+  __syncthreads();
+  for (int o = tid; o < OUT; o += 128) {
+    float acc[RT];
+    const float b = bias ? bias[(size_t)s * LN_P + o] : 0.f;
+#pragma unroll
+    for (int k = 0; k < RT; ++k) acc[k] = b;
+    const float* wa = w1 + (size_t)s * LN_P + (size_t)o * IN;
+    for (int i = 0; i < IN; ++i) {
+      const float w = wa[i];
+#pragma unroll
+      for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx1[k * IN + i], w, acc[k]);
+    }
+    if (x2) {
+      const float* wb = w2 + (size_t)s * LN_P + (size_t)o * IN;
+      for (int i = 0; i < IN; ++i) {
+        const float w = wb[i];
+#pragma unroll
+        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx2[k * IN + i], w, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RT; ++k) {
+      const int row = r0 + k;
+      if (row >= R) break;
+      const size_t dst = ((size_t)s * R + row) * OUT + o;
+      float v = relu ? fmaxf(acc[k], 0.f) : acc[k];
+      if (maskfrom) v = maskfrom[dst] > 0.f ? v : 0.f;
+      out[dst] = v;
+    }
+  }
+}
+
+// out[s][r][i] = sum_o (y1[s][r][o] w1[s][o][i] (+ y2 . w2)), then * (maskfrom[s][r][i] > 0) if given
+__global__ void __launch_bounds__(128)
+lin_bwd_data_kernel(const float* __restrict__ y1, const float* __restrict__ w1, const float* __restrict__ y2,
+                    const float* __restrict__ w2, int R, int IN, int OUT, const float* __restrict__ maskfrom,
+                    float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* sy1 = sm;
+  float* sy2 = sm + RT * OUT;
+  const int r0 = blockIdx.x * RT, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < RT * OUT; i += 128) {
+    const int rr = i / OUT, row = r0 + rr;
+    const size_t src = ((size_t)s * R + row) * OUT + i % OUT;
+    sy1[i] = row < R ? y1[src] : 0.f;
+    sy2[i] = (row < R && y2) ? y2[src] : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < IN; i += 128) {
+    float acc[RT];
+#pragma unroll
+    for (int k = 0; k < RT; ++k) acc[k] = 0.f;
+    const float* wa = w1 + (size_t)s * LN_P + i;
+    const float* wb = w2 ? w2 + (size_t)s * LN_P + i : nullptr;
+    for (int o = 0; o < OUT; ++o) {
+      const float w = wa[(size_t)o * IN];
+#pragma unroll
+      for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy1[k * OUT + o], w, acc[k]);
+      if (wb) {
+        const float v = wb[(size_t)o * IN];
+#pragma unroll
+        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy2[k * OUT + o], v, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RT; ++k) {
+      const int row = r0 + k;
+      if (row >= R) break;
+      const size_t dst = ((size_t)s * R + row) * IN + i;
+      out[dst] = (maskfrom && !(maskfrom[dst] > 0.f)) ? 0.f : acc[k];
+    }
+  }
+}
+
+// wbar[s][o][i] (+)= sum_r y[s][r][o] x[s][r][i];  bbar[s][o] = sum_r y[s][r][o]   (one CTA per 8 outputs and sample)
+__global__ void __launch_bounds__(128)
+lin_bwd_weight_kernel(const float* __restrict__ y, const float* __restrict__ x, int R, int IN, int OUT,
+                      float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
+  extern __shared__ float sy[];   // [R][8]
+  const int o0 = blockIdx.x * 8, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < R * 8; i += 128) {
+    const int r = i >> 3, o = o0 + (i & 7);
+    sy[i] = o < OUT ? y[((size_t)s * R + r) * OUT + o] : 0.f;
+  }
+  __syncthreads();
+  const float* xs = x + (size_t)s * R * IN;
+  for (int i = tid; i < IN; i += 128) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float xv = xs[(size_t)r * IN + i];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(sy[r * 8 + k], xv, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (o0 + k >= OUT) break;
+      float* dst = wbar + (size_t)s * LN_P + (size_t)(o0 + k) * IN + i;
+      *dst = accumulate ? *dst + acc[k] : acc[k];
+    }
+  }
+  if (bbar && tid < 8 && o0 + tid < OUT) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += sy[r * 8 + tid];
+    bbar[(size_t)s * LN_P + o0 + tid] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ softmax / NLL head
+// mode 0: nll;  mode 1: nll, g_o = cw (p - onehot);  mode 2 (dual, needs od): G_o = cw p (od - <p, od>), G_od = cw (p - onehot),
+// acbar = (p - onehot) . od     
+__global__ void lenet_head_kernel(const float* __restrict__ o, const float* __restrict__ od, const int* __restrict__ y,
+                                  const float* __restrict__ cw, int S, int R, int mode, float* __restrict__ nll,
+                                  float* __restrict__ g_o, float* __restrict__ g_od, float* __restrict__ acbar) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * R) return;
+  const int r = idx % R;
+  const float* lo = o + (size_t)idx * N_O;
+  float p[N_O], mx = -INFINITY, se = 0.f;
+#pragma unroll
+  for (int c = 0; c < N_O; ++c) mx = fmaxf(mx, lo[c]);
+#pragma unroll
+  for (int c = 0; c < N_O; ++c) { p[c] = expf(lo[c] - mx); se += p[c]; }
+  const int lab = y[r];
+  if (nll) nll[idx] = -(lo[lab] - mx - logf(se));
+  if (mode == 0) return;
+  const float w = cw ? cw[idx] : 1.f, inv = 1.f / se;
+#pragma unroll
+  for (int c = 0; c < N_O; ++c) p[c] *= inv;
+  if (mode == 1) {
+#pragma unroll
+    for (int c = 0; c < N_O; ++c) g_o[(size_t)idx * N_O + c] = w * (p[c] - (c == lab ? 1.f : 0.f));
+    return;
+  }
+  const float* ld = od + (size_t)idx * N_O;
+  float dot = 0.f, qd = 0.f;
+#pragma unroll
+  for (int c = 0; c < N_O; ++c) { dot += p[c] * ld[c]; qd += (p[c] - (c == lab ? 1.f : 0.f)) * ld[c]; }
+#pragma unroll
+  for (int c = 0; c < N_O; ++c) {
+    g_o[(size_t)idx * N_O + c] = w * p[c] * (ld[c] - dot);
+    g_od[(size_t)idx * N_O + c] = w * (p[c] - (c == lab ? 1.f : 0.f));
+  }
+  if (acbar) acbar[idx] = qd;
+}
+
+// predictive metrics from per-sample logits [S][R][C] (psvi_classes.py:1072-1092): one CTA, fixed-order reduction
+__global__ void __launch_bounds__(256)
+logits_predict_kernel(const float* __restrict__ logits, const float* __restrict__ lw, int mode, const int* __restrict__ y, int S,
+                      int R, int C, float* __restrict__ out) {
+  __shared__ float s_w[64], s_red[2][256];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    float mx = -INFINITY, se = 0.f;
+    if (mode == 0) {
+      for (int s = 0; s < S; ++s) mx = fmaxf(mx, lw[s]);
+      for (int s = 0; s < S; ++s) se += expf(lw[s] - mx);
+    }
+    for (int s = 0; s < S; ++s) s_w[s] = mode == 0 ? expf(lw[s] - mx) / se : 1.f / (float)S;
+  }
+  __syncthreads();
+  float nll = 0.f, corr = 0.f;
+  for (int r = tid; r < R; r += 256) {
+    float pr[16];
+    for (int c = 0; c < C; ++c) pr[c] = 0.f;
+    if (mode == 2) {   // softmax of the mean logits (mfvi baselines)
+      for (int s = 0; s < S; ++s)
+        for (int c = 0; c < C; ++c) pr[c] += logits[((size_t)s * R + r) * C + c] / (float)S;
+      float mx = -INFINITY, se = 0.f;
+      for (int c = 0; c < C; ++c) mx = fmaxf(mx, pr[c]);
+      for (int c = 0; c < C; ++c) { pr[c] = expf(pr[c] - mx); se += pr[c]; }
+      for (int c = 0; c < C; ++c) pr[c] /= se;
+    } else {
+      for (int s = 0; s < S; ++s) {
+        const float* lo = logits + ((size_t)s * R + r) * C;
+        float mx = -INFINITY, se = 0.f;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, lo[c]);
+        for (int c = 0; c < C; ++c) se += expf(lo[c] - mx);
+        const float sc = s_w[s] / se;
+        for (int c = 0; c < C; ++c) pr[c] += sc * expf(lo[c] - mx);
+      }
+    }
+    float tot = 0.f, best = -1.f;
+    int am = 0;
+    for (int c = 0; c < C; ++c) {
+      tot += pr[c];
+      if (pr[c] > best) { best = pr[c]; am = c; }
+    }
+    const int lab = y[r];
+    nll -= logf(fminf(fmaxf(pr[lab] / tot, 1.1920929e-07f), 1.f - 1.1920929e-07f));
+    corr += (am == lab) ? 1.f : 0.f;
+  }
+  s_red[0][tid] = nll; s_red[1][tid] = corr;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < 256; ++i) { a += s_red[0][i]; b += s_red[1][i]; }
+    out[0] = (float)a; out[1] = (float)b; out[2] = (float)R; out[3] = 0.f; out[4] = 0.f;
+    if (mode == 0) {
+      float ent = 0.f, sw = 0.f, sw2 = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const float w = s_w[s];
+        if (w > 0.f) ent -= logf(w) * w;
+        sw += w; sw2 += w * w;
+      }
+      out[3] = ent;
+      out[4] = sw * sw / sw2 / (float)S;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host sequencing
+struct Ws {
+  float *p1, *p2, *h3, *h4, *o, *pd1, *pd2, *hd3, *hd4, *od;
+  float *g1, *g1d, *g2, *g2d, *g3, *g3d, *g4, *g4d, *go, *god;
+  uint8_t *sel1, *sel2;
+  size_t total;
+};
+void carve_ws(int S, int R, uint8_t* base, Ws& w) {
+  size_t off = 0;
+  const size_t n = (size_t)S * R;
+  auto takef = [&](size_t floats) { float* p = base ? reinterpret_cast<float*>(base + off) : nullptr; off += ((floats * 4 + 255) & ~(size_t)255); return p; };
+  w.p1 = takef(n * N_P1); w.p2 = takef(n * N_P2); w.h3 = takef(n * N_H3); w.h4 = takef(n * N_H4); w.o = takef(n * N_O);
+  w.pd1 = takef(n * N_P1); w.pd2 = takef(n * N_P2); w.hd3 = takef(n * N_H3); w.hd4 = takef(n * N_H4); w.od = takef(n * N_O);
+  w.g1 = takef(n * N_P1); w.g1d = takef(n * N_P1); w.g2 = takef(n * N_P2); w.g2d = takef(n * N_P2);
+  w.g3 = takef(n * N_H3); w.g3d = takef(n * N_H3); w.g4 = takef(n * N_H4); w.g4d = takef(n * N_H4);
+  w.go = takef(n * N_O); w.god = takef(n * N_O);
+  w.sel1 = base ? base + off : nullptr; off += ((n * N_P1 + 255) & ~(size_t)255);
+  w.sel2 = base ? base + off : nullptr; off += ((n * N_P2 + 255) & ~(size_t)255);
+  w.total = off;
+}
+
+#define LN_CHECK() PSVI_CUDA_CHECK(cudaGetLastError())
+
+}  // namespace
+
+extern "C" {
+
+int64_t psvi_lenet_num_theta(void) { return LN_P; }
+
+size_t psvi_lenet_workspace_bytes(int32_t S, int32_t R) {
+  if (S <= 0 || R <= 0) return 0;
+  Ws w;
+  carve_ws(S, R, nullptr, w);
+  return w.total + 256;
+}
+
+int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const float* x, const int32_t* y, const float* cw,
+                    int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
+                    void* workspace, void* stream_) {
+  PSVI_REQUIRE(theta && x && y && workspace, PSVI_ERR_INVALID, "null pointer");
+  PSVI_REQUIRE(S >= 1 && S <= 64 && R >= 1, PSVI_ERR_INVALID, "bad S / R");
+  PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
+  PSVI_REQUIRE(R * 8 * 4 <= 200 * 1024, PSVI_ERR_UNSUPPORTED, "at most 6400 rows per call");
+  cudaStream_t st = (cudaStream_t)stream_;
+  Ws w;
+  carve_ws(S, R, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255), w);
+  const dim3 gimg(R, S), grow((R + RT - 1) / RT, S);
+  const size_t sR = (size_t)R;
+  auto lin_fwd = [&](const float* x1, const float* w1, const float* x2, const float* w2, const float* b, int IN, int OUT,
+                     int relu, const float* mask, float* out) {
+    lin_fwd_kernel<<<grow, 128, 2 * RT * IN * sizeof(float), st>>>(x1, w1, x2, w2, b, R, IN, OUT, relu, mask, out);
+  };
+  auto lin_bwd_data = [&](const float* y1, const float* w1, const float* y2, const float* w2, int IN, int OUT, const float* mask,
+                          float* out) {
+    lin_bwd_data_kernel<<<grow, 128, 2 * RT * OUT * sizeof(float), st>>>(y1, w1, y2, w2, R, IN, OUT, mask, out);
+  };
+  auto lin_bwd_weight = [&](const float* yy, const float* xx, int IN, int OUT, float* wb, float* bb, int acc) {
+    lin_bwd_weight_kernel<<<dim3((OUT + 7) / 8, S), 128, sR * 8 * sizeof(float), st>>>(yy, xx, R, IN, OUT, wb, bb, acc);
+  };
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(lin_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  // ---- primal forward
+  conv_pool_fwd_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, R, w.sel1, 0, w.p1);
+  conv_pool_fwd_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2, R,
+                                                          w.sel2, 0, w.p2);
+  lin_fwd(w.p2, theta + O_W3, nullptr, nullptr, theta + O_B3, N_P2, N_H3, 1, nullptr, w.h3);
+  lin_fwd(w.h3, theta + O_W4, nullptr, nullptr, theta + O_B4, N_H3, N_H4, 1, nullptr, w.h4);
+  lin_fwd(w.h4, theta + O_W5, nullptr, nullptr, theta + O_B5, N_H4, N_O, 0, nullptr, w.o);
+  LN_CHECK();
+  if (logits) PSVI_CUDA_CHECK(cudaMemcpyAsync(logits, w.o, sR * S * N_O * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int hb = (S * R + 127) / 128;
+  if (!tbar) {
+    lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, y, nullptr, S, R, 0, nll, nullptr, nullptr, nullptr);
+    LN_CHECK();
+    return PSVI_OK;
+  }
+  if (!thetad) {
+    // ---- gradient pass
+    lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, y, cw, S, R, 1, nll, w.go, nullptr, nullptr);
+    lin_bwd_weight(w.go, w.h4, N_H4, N_O, tbar + O_W5, tbar + O_B5, 0);
+    lin_bwd_data(w.go, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4);
+    lin_bwd_weight(w.g4, w.h3, N_H3, N_H4, tbar + O_W4, tbar + O_B4, 0);
+    lin_bwd_data(w.g4, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3);
+    lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
+    lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
+    conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2, w.sel2, w.p1, sR * N_P1, R, tbar + O_W2, tbar + O_B2, 0);
+    conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1);
+    conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1, w.sel1, x, 0, R, tbar + O_W1, tbar + O_B1, 0);
+    if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, nullptr, nullptr, w.sel1, R, xbar);
+    LN_CHECK();
+    return PSVI_OK;
+  }
+  // ---- dual pass: tangent forward (x itself carries no tangent)
+  conv_pool_fwd_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(x, 0, thetad + O_W1, nullptr, 0, nullptr, thetad + O_B1, R, w.sel1, 1, w.pd1);
+  conv_pool_fwd_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.pd1, sR * N_P1, theta + O_W2, w.p1, sR * N_P1, thetad + O_W2,
+                                                          thetad + O_B2, R, w.sel2, 1, w.pd2);
+  lin_fwd(w.pd2, theta + O_W3, w.p2, thetad + O_W3, thetad + O_B3, N_P2, N_H3, 0, w.h3, w.hd3);
+  lin_fwd(w.hd3, theta + O_W4, w.h3, thetad + O_W4, thetad + O_B4, N_H3, N_H4, 0, w.h4, w.hd4);
+  lin_fwd(w.hd4, theta + O_W5, w.h4, thetad + O_W5, thetad + O_B5, N_H4, N_O, 0, nullptr, w.od);
+  lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, w.od, y, cw, S, R, 2, nll, w.go, w.god, acbar);
+  LN_CHECK();
+  // layer 5
+  lin_bwd_weight(w.go, w.h4, N_H4, N_O, tbar + O_W5, tbar + O_B5, 0);
+  lin_bwd_weight(w.god, w.hd4, N_H4, N_O, tbar + O_W5, nullptr, 1);
+  lin_bwd_weight(w.god, w.h4, N_H4, N_O, tdbar + O_W5, tdbar + O_B5, 0);
+  lin_bwd_data(w.go, theta + O_W5, w.god, thetad + O_W5, N_H4, N_O, w.h4, w.g4);
+  lin_bwd_data(w.god, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4d);
+  // layer 4
+  lin_bwd_weight(w.g4, w.h3, N_H3, N_H4, tbar + O_W4, tbar + O_B4, 0);
+  lin_bwd_weight(w.g4d, w.hd3, N_H3, N_H4, tbar + O_W4, nullptr, 1);
+  lin_bwd_weight(w.g4d, w.h3, N_H3, N_H4, tdbar + O_W4, tdbar + O_B4, 0);
+  lin_bwd_data(w.g4, theta + O_W4, w.g4d, thetad + O_W4, N_H3, N_H4, w.h3, w.g3);
+  lin_bwd_data(w.g4d, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3d);
+  // layer 3
+  lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
+  lin_bwd_weight(w.g3d, w.pd2, N_P2, N_H3, tbar + O_W3, nullptr, 1);
+  lin_bwd_weight(w.g3d, w.p2, N_P2, N_H3, tdbar + O_W3, tdbar + O_B3, 0);
+  lin_bwd_data(w.g3, theta + O_W3, w.g3d, thetad + O_W3, N_P2, N_H3, nullptr, w.g2);
+  lin_bwd_data(w.g3d, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2d);
+  LN_CHECK();
+  // conv 2
+  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2, w.sel2, w.p1, sR * N_P1, R, tbar + O_W2, tbar + O_B2, 0);
+  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2d, w.sel2, w.pd1, sR * N_P1, R, tbar + O_W2, nullptr, 1);
+  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2d, w.sel2, w.p1, sR * N_P1, R, tdbar + O_W2, tdbar + O_B2, 0);
+  conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, R, w.g1);
+  conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1d);
+  // conv 1
+  conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1, w.sel1, x, 0, R, tbar + O_W1, tbar + O_B1, 0);
+  conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1d, w.sel1, x, 0, R, tdbar + O_W1, tdbar + O_B1, 0);
+  if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, R, xbar);
+  LN_CHECK();
+  return PSVI_OK;
+}
+
+int psvi_logits_predict(const float* logits, const float* log_weights, int32_t mode, const int32_t* yt, int32_t S, int32_t R,
+                        int32_t C, float* out, void* stream) {
+  PSVI_REQUIRE(logits && yt && out, PSVI_ERR_INVALID, "null pointer");
+  PSVI_REQUIRE(S >= 1 && S <= 64 && C >= 1 && C <= 16 && R >= 1, PSVI_ERR_INVALID, "bad S / C / R");
+  PSVI_REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || log_weights), PSVI_ERR_INVALID, "bad mode / missing log weights");
+  logits_predict_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, log_weights, mode, yt, S, R, C, out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+}  // extern "C"

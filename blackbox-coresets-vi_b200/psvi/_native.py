@@ -106,6 +106,12 @@ _SIGS = {
                                  C.c_void_p, C.c_int32, C.c_void_p]),
     "psvi_fc_outer": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    "psvi_lenet_num_theta": (C.c_int64, []),
+    "psvi_lenet_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "psvi_lenet_pass": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_logits_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -373,3 +379,29 @@ def fc_matvec(n, S, base, dg, off, eps_ptr, ld_eps, out_ptr, ld_out):
 def fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, g_base, g_dg, g_off):
     _count(1)
     _check(lib().psvi_fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, _p(g_base), _p(g_dg), _p(g_off), _stream()))
+
+
+_lenet_ws = {}
+
+
+def lenet_num_theta():
+    return int(lib().psvi_lenet_num_theta())
+
+
+def lenet_pass(S, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, logits=None):
+    """Per-sample lenet pass (forward / gradient / dual) on sampled weights theta [S][P]; x [R][784]."""
+    R = x.shape[0]
+    n = (int(lib().psvi_lenet_workspace_bytes(S, R)) + 3) // 4
+    ws = _lenet_ws.get(theta.device)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(n, device=theta.device, dtype=torch.float32)
+        _lenet_ws[theta.device] = ws
+    _count(6 if tbar is None else (16 if thetad is None else 36))
+    _check(lib().psvi_lenet_pass(S, _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll), _p(tbar), _p(tdbar),
+                                 _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))
+
+
+def logits_predict(logits, log_weights, mode, yt, out):
+    S, R, Cc = logits.shape
+    _count(1)
+    _check(lib().psvi_logits_predict(_p(logits), _p(log_weights), mode, _p(yt, torch.int32), S, R, Cc, _p(out), _stream()))

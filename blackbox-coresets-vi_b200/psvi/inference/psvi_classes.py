@@ -25,20 +25,25 @@ from tqdm import tqdm
 
 from psvi import _native
 from psvi.inference.utils import LogResource, compute_empirical_mean
-from psvi.models.neural_net import (FullCovMLP, MeanFieldMLP, VILinear, VILinearMultivariateNormal, categorical_fn, make_fc2net,
+from psvi.models.neural_net import (FullCovMLP, MeanFieldLeNet, MeanFieldMLP, VILinear, VILinearMultivariateNormal, categorical_fn, make_fc2net,
                                     make_fcnet, make_lenet, make_logistic_regression, set_mc_samples)
 
 
 class SubsetPreservingTransforms(Dataset):
-    """Subset of a tensor dataset at given indices (reference :51-80; the image branch needs torchvision datasets,
-    which are out of scope here)."""
+    """Subset of a dataset at given indices (reference :51-80): rows of `.data` for tabular datasets; for MNIST-like image
+    datasets (uint8 `.data` [N, 28, 28] + `.transform`) the transformed image, as the reference's image branch does."""
 
     def __init__(self, dataset, indices=None, dim=2, dnm="Cifar10"):
         self.dataset, self.indices, self.dnm, self.dim = dataset, indices, dnm, dim
 
     def __getitem__(self, idx):
-        if self.dnm in {"MNIST", "FashionMNIST", "Cifar10"}:
-            raise NotImplementedError("vision datasets are out of scope (no network; SURVEY.md section 2 row 9)")
+        if self.dnm in {"MNIST", "FashionMNIST"}:
+            from PIL import Image
+            import numpy as np
+            im = Image.fromarray(np.reshape(self.dataset.data[self.indices[idx]].numpy(), (28, 28)), mode="L")
+            return self.dataset.transform(im)
+        if self.dnm == "Cifar10":
+            raise NotImplementedError("Cifar10 needs the architectures outside the PSVI hot-path scope (SURVEY.md section 2)")
         return self.dataset.data[self.indices[idx]].reshape((self.dim,))
 
     def __len__(self):
@@ -160,24 +165,29 @@ class PSVI(object):
                                       f"{type(model).__name__}")
         model.check_supported()
         S = model.n_samples()
+        if isinstance(model, MeanFieldLeNet):
+            return model, None, S          # evaluated by the streaming path only (no psvi_mf_model descriptor)
         return model, _native.make_model(model.dims, S), S
 
     # ---- engine choice: fused cluster kernel when the model fits its shared-memory budget, streaming path otherwise ----
     def _stream(self, model):
         """StreamEngine for `model` (fn2, or a mean-field MLP the fused engine reported as PSVI_ERR_UNSUPPORTED)."""
-        from psvi.inference.stream import FullCovFamily, MeanFieldFamily, StreamEngine
+        from psvi.inference.stream import FullCovFamily, LenetFamily, LenetNet, MeanFieldFamily, StreamEngine
         key = id(model)
         eng = self._ws.get(("stream", key))
         if eng is None:
-            fam = FullCovFamily(model) if isinstance(model, FullCovMLP) else MeanFieldFamily(model)
-            eng = StreamEngine(fam, model.dims, model.n_samples())
+            if isinstance(model, MeanFieldLeNet):
+                eng = StreamEngine(LenetFamily(model), model.dims, model.n_samples(), net=LenetNet(model.n_samples()))
+            else:
+                fam = FullCovFamily(model) if isinstance(model, FullCovMLP) else MeanFieldFamily(model)
+                eng = StreamEngine(fam, model.dims, model.n_samples())
             self._ws[("stream", key)] = eng
         if isinstance(model, MeanFieldMLP):
             eng.fam.mu, eng.fam.rho = model.flat()
         return eng
 
     def _use_stream(self, model):
-        return isinstance(model, FullCovMLP) or self._ws.get(("force_stream", id(model)), False)
+        return isinstance(model, (FullCovMLP, MeanFieldLeNet)) or self._ws.get(("force_stream", id(model)), False)
 
     def _fused(self, model, fn):
         """Run fn() on the fused engine; if the model does not fit it, remember that and return None."""
@@ -228,7 +238,8 @@ class PSVI(object):
         return float(self.alpha.item()) if self.alpha is not None else 0.0
 
     def _uv(self):
-        return (self.u.detach().float().contiguous(), self.v.detach().float().contiguous())
+        # image pseudo-data [M, 1, 28, 28] (lenet) is handed to the kernels as rows [M, 784]
+        return (self.u.detach().float().reshape(self.u.shape[0], -1).contiguous(), self.v.detach().float().contiguous())
 
     # ------------------------------------------------------------------------------------------------ objectives
     def psvi_elbo(self, xbatch, ybatch, model=None, params=None, hyperopt=False):
@@ -236,7 +247,7 @@ class PSVI(object):
         parameters, u and v are left in `self._last_outer` (the fused kernel produces them in the same pass)."""
         assert self.mc_samples > 1
         model, desc, S = self._model_desc(model)
-        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
+        xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
         yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
         if not self._use_stream(model):
             out = self._fused(model, lambda: self._psvi_elbo_fused(model, desc, xb, yb))
@@ -313,7 +324,7 @@ class PSVI(object):
         eng = self._stream(model)
         T, lr = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"])
         u, _ = self._uv()
-        xb = xbatch.detach().to(self.device, torch.float32).contiguous()
+        xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
         yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
         loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u, self._z32(),
                                                  self._a(), xb, yb, float(self.N), T, lr, want_losses=self.register_elbos)
@@ -324,7 +335,7 @@ class PSVI(object):
                 self.elbos.append((1, -ilc[in_it].item()))
             self.elbos.append((0, -loss.item()))
         vg, ag = self._v_grad_from_abar(abar)
-        self.u.grad = ubar.to(self.u.dtype)
+        self.u.grad = ubar.to(self.u.dtype).reshape(self.u.shape)
         if self.learn_v:
             self.v.grad = vg.to(self.v.dtype)
         if self.alpha is not None and self.alpha.requires_grad and ag is not None:
@@ -439,17 +450,24 @@ class PSVI(object):
             self.model = make_fc2net(self.D, self.n_hidden, self.nc, mc_samples=self.mc_samples,
                                      init_sd=self.init_sd).to(self.device)
         elif self.architecture == "lenet":
-            self.model = make_lenet(mc_samples=self.mc_samples, init_sd=self.init_sd)
+            self.model = make_lenet(linear_class=VILinear, nonl_class=nn.ReLU, mc_samples=self.mc_samples,
+                                    init_sd=self.init_sd).to(self.device)
         else:
             raise NotImplementedError(f"architecture {self.architecture!r} is outside the PSVI hot-path scope")
         if isinstance(self.model, MeanFieldMLP) and self.device.type == "cuda":
-            self.model.flat()
+            self.model.flat()    # (MeanFieldLeNet is a MeanFieldMLP: same flat parameter buffers)
 
     # ------------------------------------------------------------------------------------------------ data
     def _device_dataset(self, ds, key):
         c = self._dev_data.get(key)
         if c is None or c[0] is not ds:
-            x = torch.as_tensor(ds.data).to(self.device, torch.float32).reshape(len(ds), -1).contiguous()
+            raw = torch.as_tensor(ds.data)
+            if raw.dtype == torch.uint8 and getattr(ds, "transform", None) is not None:
+                # image datasets (MNIST-like): the reference's loaders apply ds.transform (ToTensor + Normalize,
+                # experiments_utils.py:42-46) per item; do it once and keep the result on the device
+                x = torch.stack([ds[i][0] for i in range(len(ds))]).to(self.device, torch.float32).reshape(len(ds), -1).contiguous()
+            else:
+                x = raw.to(self.device, torch.float32).reshape(len(ds), -1).contiguous()
             y = torch.as_tensor(ds.targets).to(self.device).to(torch.int32).contiguous()
             c = (ds, x, y)
             self._dev_data[key] = c
@@ -545,7 +563,7 @@ class PSVI(object):
         assert self.mc_samples > 1
         model, desc, S = self._model_desc()
         xt, yt = self._device_dataset(self.test_dataset, "test")
-        if isinstance(model, FullCovMLP):
+        if isinstance(model, (FullCovMLP, MeanFieldLeNet)):
             eng = self._stream(model)
             u, _ = self._uv()
             batch = int(self.data_minibatch)

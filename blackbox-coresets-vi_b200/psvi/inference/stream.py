@@ -26,12 +26,21 @@ OMB1, OMB2, AEPS = float(1.0 - B1), float(1.0 - B2), 1e-8
 
 
 class MeanFieldFamily:
-    """phi = [mu | rho] in theta layout (the flat buffers that back the module parameters)."""
+    """phi = [mu | rho] in theta layout (the flat buffers that back the module parameters).  `mask` (None = all ones) marks
+    the parameters that enter the KL / sampled-nkl sums (the reference filters those sums on VILinear)."""
+
+    mask = None
 
     def __init__(self, model):
         self.model = model
         self.mu, self.rho = model.flat()
         self.Pt = self.mu.numel()
+
+    def _m(self, t):
+        return t if self.mask is None else t * self.mask
+
+    def fix_eps(self, eps):
+        return eps
 
     def get_phi(self):
         return torch.cat([self.mu, self.rho])
@@ -48,26 +57,47 @@ class MeanFieldFamily:
 
     def kl(self, phi):
         mu, sg = phi[:self.Pt], F.softplus(phi[self.Pt:])
-        return (0.5 * (sg * sg + mu * mu - 1.0) - torch.log(sg)).sum()
+        return self._m(0.5 * (sg * sg + mu * mu - 1.0) - torch.log(sg)).sum()
 
     def nkl(self, phi, eps, theta):
         sg = F.softplus(phi[self.Pt:])
-        return (-0.5 * theta * theta + 0.5 * eps * eps + torch.log(sg)).double().sum(1)
+        return self._m(-0.5 * theta * theta + 0.5 * eps * eps + torch.log(sg)).double().sum(1)
+
+    def nkl_theta_grad(self, theta):
+        """d nkl_s / d theta_s through the sample."""
+        return -self._m(theta)
 
     def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
         mu, rho = phi[:self.Pt], phi[self.Pt:]
         sg, sig = F.softplus(rho), torch.sigmoid(rho)
-        gmu = tbar.sum(0) + kl_coef * mu
-        grho = sig * ((tbar * eps).sum(0) + kl_coef * (sg - 1 / sg) + nkl_coef / sg)
+        gmu = tbar.sum(0) + self._m(kl_coef * mu)
+        grho = sig * ((tbar * eps).sum(0) + self._m(kl_coef * (sg - 1 / sg) + nkl_coef / sg))
         return torch.cat([gmu, grho])
 
     def hvp(self, phi, phidot, eps, A_t, A_td):
         rho, md, rd = phi[self.Pt:], phidot[:self.Pt], phidot[self.Pt:]
         sg, sig = F.softplus(rho), torch.sigmoid(rho)
-        hmu = A_t.sum(0) + md
+        hmu = A_t.sum(0) + self._m(md)
         hrho = (sig * (A_t * eps).sum(0) + sig * (1 - sig) * rd * (A_td * eps).sum(0)
-                + ((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rd)
+                + self._m(((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rd))
         return torch.cat([hmu, hrho])
+
+
+class LenetFamily(MeanFieldFamily):
+    """Mean-field family of make_lenet (reference neural_net.py:334-359): conv layers carry no KL / nkl (Q5) and the last
+    VILinear has mc_samples = 1, i.e. ONE noise draw shared by all samples (Q4): its block of every [S, P] noise slab is
+    sample 0's row."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.mask = model.kl_mask()
+        self.tail = model.shared_tail()
+
+    def fix_eps(self, eps):
+        if self.tail:
+            eps = eps.clone()
+            eps[..., :, -self.tail:] = eps[..., :1, -self.tail:]
+        return eps
 
 
 class FullCovFamily:
@@ -85,6 +115,12 @@ class FullCovFamily:
             self.toffs.append(t)
             o += 2 * n + c
             t += n
+
+    def fix_eps(self, eps):
+        return eps
+
+    def nkl_theta_grad(self, theta):
+        return -theta
 
     def get_phi(self):
         return torch.cat([p.detach().reshape(-1).float() for m in self.layers for p in (m.mean, m._sd, m._corr)])
@@ -156,28 +192,58 @@ class FullCovFamily:
         return torch.cat(out)
 
 
-class StreamEngine:
-    def __init__(self, fam, dims, S):
-        self.fam, self.S, self.dims = fam, S, list(dims)
+class MlpNet:
+    """Per-sample MLP pass on sampled weights: psvi_net_pass / psvi_net_predict (one CTA per MC sample)."""
+
+    def __init__(self, dims, S):
         self.desc = _native.make_model(dims, S)
+
+    def pass_(self, theta, thetad, x, y, cw, **out):
+        _native.net_pass(self.desc, theta, thetad, x, y, cw, **out)
+
+    def predict(self, theta, lw, mode, xt, yt, out):
+        _native.net_predict(self.desc, theta, lw, mode, xt, yt, out)
+
+
+class LenetNet:
+    """Per-sample lenet pass: fused conv + ReLU + pool kernels and the fc kernels of csrc/psvi_lenet.cu."""
+
+    def __init__(self, S):
+        self.S = S
+
+    def pass_(self, theta, thetad, x, y, cw, **out):
+        _native.lenet_pass(self.S, theta, thetad, x, y, cw, **out)
+
+    def predict(self, theta, lw, mode, xt, yt, out):
+        logits = torch.empty(self.S, xt.shape[0], 10, device=xt.device)
+        _native.lenet_pass(self.S, theta, None, xt, yt, None, logits=logits)
+        _native.logits_predict(logits, lw, mode, yt, out)
+
+
+class StreamEngine:
+    def __init__(self, fam, dims, S, net=None):
+        self.fam, self.S, self.dims = fam, S, list(dims)
+        self.net = net if net is not None else MlpNet(dims, S)
         self.Pt = fam.Pt
 
     # ---- objectives --------------------------------------------------------------------------------------------------
     def inner_grad(self, phi, eps, u, z32, a):
         S, M = self.S, u.shape[0]
+        eps = self.fam.fix_eps(eps)
         theta = self.fam.sample(phi, eps)
         nll, tbar = torch.empty(S, M, device=u.device), torch.empty(S, self.Pt, device=u.device)
-        _native.net_pass(self.desc, theta, None, u, z32, a.expand(S, M).contiguous(), nll=nll, tbar=tbar)
+        self.net.pass_(theta, None, u, z32, a.expand(S, M).contiguous(), nll=nll, tbar=tbar)
         val = (nll.double() @ a.double()).sum() + self.fam.kl(phi).double()
         return val, self.fam.grad(phi, eps, tbar, 1.0, 0.0)
 
     def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None):
         S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
         n_total = B if n_total is None else n_total
+        eps = self.fam.fix_eps(eps)
         theta = self.fam.sample(phi, eps)
         X, lab = torch.cat([u, xb]).contiguous(), torch.cat([z32, yb32]).contiguous()
         nll = torch.empty(S, M + B, device=dev)
-        _native.net_pass(self.desc, theta, None, X, lab, None, nll=nll)
+        self.net.pass_(theta, None, X, lab, None, nll=nll)
         nd = nll.double()
         ps, ds = nd[:, :M] @ a.double(), (N / n_total) * nd[:, M:].sum(1)
         lw = -ps + self.fam.nkl(phi, eps, theta)
@@ -189,23 +255,24 @@ class StreamEngine:
         gp = -kappa * w - beta
         cw = torch.cat([gp[:, None] * a.double()[None, :], (w * N / n_total)[:, None].expand(S, B)], 1).float().contiguous()
         tbar, xbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, M + B, X.shape[1], device=dev)
-        _native.net_pass(self.desc, theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
-        tbar = tbar - beta.float()[:, None] * theta
+        self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
+        tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
         pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
         return loss.float(), pbar, xbar[:, :M].sum(0), (gp.float() @ nll[:, :M]), ds.float()
 
     def hvp(self, phi, eps, u, z32, a, phidot):
         S, M, dev = self.S, u.shape[0], u.device
+        eps = self.fam.fix_eps(eps)
         theta, thetad = self.fam.sample(phi, eps), self.fam.tangent(phi, phidot, eps)
         tbar, tdbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, self.Pt, device=dev)
         xbar, ac = torch.empty(S, M, u.shape[1], device=dev), torch.empty(S, M, device=dev)
-        _native.net_pass(self.desc, theta, thetad, u, z32, a.expand(S, M).contiguous(), tbar=tbar, tdbar=tdbar, xbar=xbar,
-                         acbar=ac)
+        self.net.pass_(theta, thetad, u, z32, a.expand(S, M).contiguous(), tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
         return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
     def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False):
         """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None)."""
+        eps_all = self.fam.fix_eps(eps_all)
         m, v = torch.zeros_like(phi), torch.zeros_like(phi)
         traj, losses = [], []
         for t in range(T):
@@ -240,6 +307,7 @@ class StreamEngine:
     def evaluate(self, phi, eps_slabs, u, z32, a, xt, yt32, batch, mode=0):
         """eps_slabs [n_slabs, S, P]; returns out[8] accumulated over slabs (diagnostics of the last slab, Q12)."""
         dev, S = xt.device, self.S
+        eps_slabs = self.fam.fix_eps(eps_slabs)
         tot = torch.zeros(8, device=dev)
         out = torch.zeros(8, device=dev)
         n = xt.shape[0]
@@ -249,9 +317,9 @@ class StreamEngine:
             if mode == 0:
                 M = u.shape[0]
                 nll = torch.empty(S, M, device=dev)
-                _native.net_pass(self.desc, theta, None, u, z32, None, nll=nll)
+                self.net.pass_(theta, None, u, z32, None, nll=nll)
                 lw = ((nll.double() @ a.double()) + self.fam.nkl(phi, eps_slabs[k], theta)).float().contiguous()  # Q3
-            _native.net_predict(self.desc, theta, lw, mode, xt[r0:r0 + batch].contiguous(), yt32[r0:r0 + batch].contiguous(), out)
+            self.net.predict(theta, lw, mode, xt[r0:r0 + batch].contiguous(), yt32[r0:r0 + batch].contiguous(), out)
             tot[:3] += out[:3]
             tot[3:5] = out[3:5]
         return tot

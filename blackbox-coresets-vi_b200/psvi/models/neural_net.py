@@ -10,8 +10,8 @@ PSVI.set_up_model for `logistic_regression`) is evaluated by ONE fused kernel (s
 logits), see MeanFieldMLP.forward.  Gradients are not obtained with autograd: the PSVI objectives, their gradients and
 the hypergradient are separate fused kernels driven by psvi.inference.psvi_classes.
 The full-covariance family (fn2) evaluates through the streaming path (packed-triangle products + the per-sample
-network kernel).  The convolutional family (lenet) is declared for API compatibility and raises NotImplementedError at
-construction in this round (DESIGN.md "not yet covered").
+network kernel).  The convolutional family (lenet: VIConv2d / BatchMaxPool2d / make_lenet, reference :194-255,334-359)
+evaluates through the same streaming path with the fused conv + ReLU + pool kernels of csrc/psvi_lenet.cu.
 """
 from __future__ import annotations
 
@@ -378,19 +378,113 @@ def make_fc2net(in_dim, h_dim, out_dim, n_layers=2, linear_class=None, nonl_clas
     return net
 
 
-# ---- families that are part of the reference surface but not yet covered by kernels (a4) ----
+# ---- convolutional family (lenet): reference neural_net.py:194-255,334-359 ---------------------------------------------
 class VIConv2d(VIMixin, nn.Conv2d):
+    """reference :194-246 (per-sample convolution; the reference stacks the S samples on the channel axis and uses
+    groups = S).  Evaluated inside a MeanFieldLeNet stack by the fused conv + ReLU + pool kernels of libpsvi_b200."""
+
     def __init__(self, *args, **kwargs):
-        raise NotImplementedError("VIConv2d / lenet (reference neural_net.py:194-246,334-359) is not built yet in the "
-                                  "B200 path; see DESIGN.md 'not yet covered'")
+        if "groups" in kwargs:
+            raise ValueError("Cannot use groups argument for variational conv layer as this is used for parallelizing "
+                             "across samples.")
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x):
+        raise NotImplementedError("a stand-alone VIConv2d is not evaluated on its own: the CUDA path covers the lenet stack "
+                                  "(make_lenet), whose conv + ReLU + pool stages are fused kernels")
 
 
 class BatchMaxPool2d(nn.MaxPool2d):
-    pass
+    """reference :249-255 (2x2 max-pool over the flattened (S, N) batch); fused into the conv kernels of the lenet stack."""
 
 
-def make_lenet(*args, **kwargs):
-    raise NotImplementedError("lenet (reference neural_net.py:334-359) is not built yet")
+class MeanFieldLeNet(MeanFieldMLP):
+    """nn.Sequential built by make_lenet, evaluated by libpsvi_b200's lenet pass (psvi_lenet_pass).  The flat (mu, rho)
+    buffers of MeanFieldMLP back the parameters of all five VI layers (module order = theta layout)."""
+
+    def vi_layers(self):
+        return [m for m in self if isinstance(m, VIMixin)]
+
+    def check_supported(self):
+        mods = list(self)
+        kinds = [VIConv2d, nn.ReLU, BatchMaxPool2d, VIConv2d, nn.ReLU, BatchMaxPool2d, nn.Flatten, VILinear, nn.ReLU, VILinear,
+                 nn.ReLU, VILinear]
+        ok = len(mods) == len(kinds) and all(isinstance(m, k) for m, k in zip(mods, kinds))
+        if ok:
+            c1, c2, f1, f2, f3 = self.vi_layers()
+            ok = (tuple(c1.weight.shape) == (6, 1, 5, 5) and tuple(c1.padding) == (2, 2) and tuple(c2.weight.shape) == (16, 6, 5, 5)
+                  and tuple(c2.padding) == (0, 0) and tuple(f1.weight.shape) == (120, 400) and tuple(f2.weight.shape) == (84, 120)
+                  and tuple(f3.weight.shape) == (10, 84) and all(m.bias is not None and float(m.prior_sd) == 1.0
+                                                                 for m in self.vi_layers()))
+        if not ok:
+            raise NotImplementedError(f"the convolutional CUDA path covers the lenet stack of make_lenet; got {self}")
+
+    @property
+    def dims(self):
+        return [784, 10]
+
+    def shared_tail(self):
+        """Number of trailing theta entries whose noise is ONE draw shared by all samples: make_lenet builds the last
+        VILinear without kwargs, so it keeps mc_samples = 1 (reference :358)."""
+        last = self.vi_layers()[-1]
+        return last.weight.numel() + last.bias.numel() if int(last.mc_samples) == 1 and self.n_samples() > 1 else 0
+
+    def kl_mask(self):
+        """1 for parameters of VILinear layers, 0 for VIConv2d ones: the reference's KL / sampled-nkl sums filter on
+        isinstance(VILinear) (psvi_classes.py:479-483,506-510; quirk Q5)."""
+        dev = self.vi_layers()[0].weight.device
+        return torch.cat([torch.full((m.weight.numel() + m.bias.numel(),), 1.0 if isinstance(m, VILinear) else 0.0, device=dev)
+                          for m in self.vi_layers()])
+
+    def forward(self, x, eps=None):
+        from psvi.inference.stream import LenetFamily
+        _native.require_cuda()
+        self.check_supported()
+        fam = LenetFamily(self)
+        S = max(self.n_samples(), 1)
+        dev = fam.mu.device
+        if eps is None:
+            eps = torch.empty(1, S, fam.Pt, device=dev)
+            _native.philox_normal(torch.initial_seed(), _NoiseCounter.next(), 0, 1, S, fam.Pt, eps)
+            eps = eps[0]
+        eps = fam.fix_eps(eps)
+        theta = fam.sample(fam.get_phi(), eps)
+        x = x.detach().to(dev, torch.float32).reshape(x.shape[0], -1).contiguous()
+        logits = torch.empty(S, x.shape[0], 10, device=dev)
+        y = torch.zeros(x.shape[0], device=dev, dtype=torch.int32)
+        _native.lenet_pass(S, theta, None, x, y, None, logits=logits)
+        off = 0
+        for m in self.vi_layers():
+            nw, nb = m.weight.numel(), m.bias.numel()
+            shared = int(m.mc_samples) == 1 and S > 1
+            w = theta[:, off:off + nw].view(S, *m.weight.shape)
+            b = theta[:, off + nw:off + nw + nb].view(S, 1, nb)
+            m._cached_weight, m._cached_bias = (w[0], b[0, 0]) if (shared or S == 1) else (w, b)
+            off += nw + nb
+        return logits if S > 1 else logits[0]
+
+
+def make_lenet(conv_class=None, linear_class=None, pool_class=None, nonl_class=None, **kwargs):
+    """reference :334-359 (NB the last linear layer is built WITHOUT kwargs: mc_samples = 1, init_sd = 0.01)."""
+    conv_class = VIConv2d if conv_class is None else conv_class
+    linear_class = VILinear if linear_class is None else linear_class
+    pool_class = BatchMaxPool2d if pool_class is None else pool_class
+    nonl_class = nn.ReLU if nonl_class is None else nonl_class
+    native = conv_class is VIConv2d and linear_class is VILinear and pool_class is BatchMaxPool2d and nonl_class is nn.ReLU
+    return (MeanFieldLeNet if native else nn.Sequential)(
+        conv_class(1, 6, 5, padding=2, **kwargs),
+        nonl_class(),
+        pool_class(2, 2),
+        conv_class(6, 16, 5, padding=0, **kwargs),
+        nonl_class(),
+        pool_class(2, 2),
+        nn.Flatten(-3, -1),
+        linear_class(400, 120, **kwargs),
+        nonl_class(),
+        linear_class(120, 84, **kwargs),
+        nonl_class(),
+        linear_class(84, 10),
+    )
 
 
 def make_alexnet(*args, **kwargs):

@@ -247,6 +247,24 @@ int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const fl
                    const void* x_bf16, const int32_t* labels, const float* row_weights, int64_t n_rows, int32_t slab,
                    float* wsum_out, float* nkl_out, float* nll_out, void* scratch, void* stream);
 
+/* ---- convolutional family (lenet): per-sample network pass on externally supplied weights, same contract as
+ * psvi_net_pass.  Replaces VIConv2d.forward (grouped conv over samples), BatchMaxPool2d, nn.Flatten and the three VILinear
+ * layers of make_lenet + Categorical.log_prob + autograd (psvi/models/neural_net.py:194-255,334-359).
+ *   theta / thetad [S][P] with P = psvi_lenet_num_theta() = 61 706 in TL (per layer weight then bias, module order);
+ *   x [R][784] (1 x 28 x 28 images, shared by all samples), y [R] int32, cw [S][R] per-sample row weights (nullable -> 1);
+ *   tbar == NULL: forward only -> nll [S][R] (+ logits [S][R][10]);  thetad == NULL: gradient pass -> tbar [S][P], xbar
+ *   [S][R][784] (nullable);  thetad != NULL: dual (Hessian-vector) pass -> tbar = A_theta, tdbar = A_thetadot, xbar = A_x,
+ *   acbar [S][R] = adjoint of the row weights.   workspace: psvi_lenet_workspace_bytes(S, R) bytes.
+ * psvi_logits_predict: predictive metrics (PSVI.evaluate, psvi_classes.py:1072-1092; baselines.py:1039-1043) from per-sample
+ *   logits [S][R][C]; mode / out [8] as psvi_mf_evaluate (mode 0 needs log_weights [S], softmax-ed inside). */
+int64_t psvi_lenet_num_theta(void);
+size_t psvi_lenet_workspace_bytes(int32_t S, int32_t R);
+int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const float* x, const int32_t* y, const float* cw,
+                    int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
+                    void* workspace, void* stream);
+int psvi_logits_predict(const float* logits, const float* log_weights, int32_t mode, const int32_t* yt, int32_t S, int32_t R,
+                        int32_t C, float* out, void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,

@@ -271,6 +271,72 @@ def run_hyper_case(name="hyper_fn_hm", H=20, M=10, S=6, T=6, B=64, K=4, init_sd=
     print(name, "forwards", out["n_forwards"], "ll", ll, "|gu|", np.abs(out["ref64_gu"]).max(), "size", os.path.getsize(pth))
 
 
+from tests.fake_mnist import FakeMNIST  # noqa: E402
+
+
+def run_lenet_case(name="lenet_m10", M=10, S=3, T=2, B=6, init_sd=1e-2, lr0net=1e-3, n_test=24):
+    """lenet (VIConv2d / BatchMaxPool2d / make_lenet, neural_net.py:194-255,334-359) in fp64 through PSVILearnV."""
+    from oracle.ref_import import LeNetNoiseFeeder
+    tr, te = FakeMNIST(64, 0), FakeMNIST(n_test, 1)
+    N, D, nc = len(tr), 784, 10
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="lenet", n_hidden=0, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="MNIST", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=True)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(11)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb = torch.stack([tr[i][0] for i in range(B)]).to(tdt)
+    yb = torch.tensor([tr[i][1] for i in range(B)]).to(tdt)
+    xt = torch.stack([te[i][0] for i in range(n_test)]).to(tdt)
+    yt = torch.tensor([te[i][1] for i in range(n_test)])
+    params = list(obj.model.parameters())
+    phi0 = torch.nn.utils.parameters_to_vector(params).detach().numpy().copy()
+    out = dict(N=N, S=S, T=T, M=M, B=B, lr0net=lr0net, noise_seed=909, vmode=1, phi0=phi0,
+               u0=obj.u.detach().numpy().reshape(M, 784).copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().reshape(B, 784).copy(), yb=yb.numpy().copy(), xt=xt.numpy().reshape(n_test, 784).copy(),
+               yt=yt.double().numpy().copy())
+    # evaluate() iterates the reference's own test loader: batches of B rows in dataset order (shuffle=False)
+    with LeNetNoiseFeeder(S, 909) as nf:
+        L = obj.inner_elbo(model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u, obj.v])
+        out["ref64_inner_val"] = L.item()
+        out["ref64_inner_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).numpy()
+        out["ref64_inner_gu"], out["ref64_inner_gv"] = gs[-2].numpy().reshape(M, 784), gs[-1].numpy()
+        L = obj.psvi_elbo(xb, yb, model=obj.model)
+        gs = torch.autograd.grad(L, params + [obj.u, obj.v])
+        out["ref64_outer_val"] = L.item()
+        out["ref64_outer_gparams"] = torch.cat([g.reshape(-1) for g in gs[:len(params)]]).numpy()
+        out["ref64_outer_gu"], out["ref64_outer_gv"] = gs[-2].numpy().reshape(M, 784), gs[-1].numpy()
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_nested_gu"], out["ref64_nested_gv"] = obj.u.grad.numpy().reshape(M, 784).copy(), obj.v.grad.numpy().copy()
+        out["ref64_nested_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_nested_u_after"] = obj.u.detach().numpy().reshape(M, 784).copy()
+        out["ref64_nested_v_after"] = obj.v.detach().numpy().copy()
+        obj.test_loader = [(xt[i:i + B], yt[i:i + B]) for i in range(0, n_test, B)]
+        acc, nll, went, ness, vent = obj.evaluate()
+        out["ref64_eval"] = np.array([acc.item(), nll.item(), went.item(), ness.item(), vent.item()])
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards"], "inner", out["ref64_inner_val"], "nested_loss", out["ref64_nested_loss"], "eval",
+          out["ref64_eval"], "size", os.path.getsize(pth))
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for c in CASES:
@@ -286,6 +352,7 @@ def main():
         print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"],
               "size", os.path.getsize(p))
     run_fn2_case()
+    run_lenet_case()
     run_hyper_case()
     blob = run_mfvi_case()
     p = os.path.join(ROOT, "tests", "golden", "mfvi_subset_hm.npz")

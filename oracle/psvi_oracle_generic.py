@@ -151,6 +151,34 @@ class FullCov:
 
 
 # ---------------------------------------------------------------------------------------------- generic objectives
+class _MLP:
+    """The network seen through four maps; families may carry their own (`fam.net`, e.g. oracle.lenet_oracle.LeNet)."""
+
+    def __init__(self, dims):
+        self.dims = dims
+
+    def forward(self, theta, X):
+        return po.mlp_forward(theta, X, self.dims)
+
+    def backward(self, theta, cache, obar):
+        return po.mlp_backward(theta, cache, self.dims, obar)
+
+    def dual_forward(self, theta, thetad, X):
+        return po.mlp_dual_forward(theta, thetad, X, self.dims)
+
+    def dual_backward(self, theta, thetad, cache, A_o, A_od):
+        return po.mlp_dual_backward(theta, thetad, cache, self.dims, A_o, A_od)
+
+
+def _net(fam):
+    return getattr(fam, "net", None) or _MLP(fam.dims)
+
+
+def _nkl_theta_grad(fam, theta):
+    f = getattr(fam, "nkl_theta_grad", None)
+    return f(theta) if f is not None else -theta
+
+
 def _q(p, lab):
     q = p.copy()
     np.add.at(q, (slice(None), np.arange(len(lab)), lab.astype(np.int64)), -1.0)
@@ -159,16 +187,16 @@ def _q(p, lab):
 
 def inner_grad(fam, phi, eps, u, z, a):
     theta = fam.sample(phi, eps)
-    logits, cache = po.mlp_forward(theta, u, fam.dims)
+    logits, cache = _net(fam).forward(theta, u)
     nll, p = po.nll_rows(logits, z)
-    tb, xbar = po.mlp_backward(theta, cache, fam.dims, a[None, :, None] * _q(p, z))
+    tb, xbar = _net(fam).backward(theta, cache, a[None, :, None] * _q(p, z))
     return np.sum(nll @ a) + fam.kl(phi), fam.grad(phi, eps, tb, 1.0, 0.0), xbar.sum(0), nll.sum(0)
 
 
 def outer_grad(fam, phi, eps, u, z, a, xb, yb, N):
     theta = fam.sample(phi, eps)
     X, lab = np.concatenate([u, xb], 0), np.concatenate([z, yb], 0)
-    logits, cache = po.mlp_forward(theta, X, fam.dims)
+    logits, cache = _net(fam).forward(theta, X)
     nll, p = po.nll_rows(logits, lab)
     S, M, B = eps.shape[0], u.shape[0], xb.shape[0]
     ps, ds = nll[:, :M] @ a, (N / B) * nll[:, M:].sum(-1)
@@ -179,18 +207,18 @@ def outer_grad(fam, phi, eps, u, z, a, xb, yb, N):
     beta = w * (e - np.sum(w * e)) - 1.0 / S
     gp = -w - beta
     rw = np.concatenate([gp[:, None] * a[None, :], np.broadcast_to((w * N / B)[:, None], (S, B))], 1)
-    tb, xbar = po.mlp_backward(theta, cache, fam.dims, rw[:, :, None] * _q(p, lab))
-    tb = tb - beta[:, None] * theta
+    tb, xbar = _net(fam).backward(theta, cache, rw[:, :, None] * _q(p, lab))
+    tb = tb + beta[:, None] * _nkl_theta_grad(fam, theta)
     return loss, fam.grad(phi, eps, tb, 0.0, beta.sum()), xbar[:, :M].sum(0), gp @ nll[:, :M]
 
 
 def inner_hvp(fam, phi, eps, u, z, a, phidot):
     theta, thetad = fam.sample(phi, eps), fam.tangent(phi, phidot, eps)
-    o, od, cache = po.mlp_dual_forward(theta, thetad, u, fam.dims)
+    o, od, cache = _net(fam).dual_forward(theta, thetad, u)
     _, p = po.nll_rows(o, z)
     q = _q(p, z)
     c = a[None, :, None]
-    A_t, A_td, A_x = po.mlp_dual_backward(theta, thetad, cache, fam.dims, c * p * (od - (p * od).sum(-1, keepdims=True)), c * q)
+    A_t, A_td, A_x = _net(fam).dual_backward(theta, thetad, cache, c * p * (od - (p * od).sum(-1, keepdims=True)), c * q)
     return fam.hvp(phi, phidot, eps, A_t, A_td), A_x.sum(0), (q * od).sum(-1).sum(0)
 
 
@@ -224,7 +252,7 @@ def evaluate(fam, phi, eps_batches, u, z, a, xt, yt, batch):
     for k, s0 in enumerate(range(0, xt.shape[0], batch)):
         xb, yb = xt[s0:s0 + batch], yt[s0:s0 + batch]
         theta = fam.sample(phi, eps_batches[k])
-        logits, _ = po.mlp_forward(theta, np.concatenate([u, xb], 0), fam.dims)
+        logits, _ = _net(fam).forward(theta, np.concatenate([u, xb], 0))
         lw = (po.nll_rows(logits[:, :M], z)[0] @ a) + fam.nkl(phi, eps_batches[k], theta)   # sign quirk Q3
         w = po.softmax(lw, 0)
         probs = (po.softmax(logits[:, M:], -1) * w[:, None, None]).sum(0)

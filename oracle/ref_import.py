@@ -110,3 +110,53 @@ class NoiseFeeder:
         import torch.distributions.multivariate_normal as tdm
         import torch.distributions.normal as tdn
         tdn._standard_normal, tdm._standard_normal = self._orig
+
+
+class LeNetNoiseFeeder(NoiseFeeder):
+    """NoiseFeeder for make_lenet (neural_net.py:334-359): per layer weight draw [S, *weight.shape] then bias draw
+    [S, 1, n_bias]; the last VILinear has mc_samples = 1 (Q4) and draws [10, 84], [10] ONCE -- its block of the [S, P] slab is
+    sample 0's row replicated, which is how the CUDA path and the oracle consume a shared draw."""
+
+    SHAPES = [((6, 1, 5, 5), False), ((6,), False), ((16, 6, 5, 5), False), ((16,), False), ((120, 400), False), ((120,), False),
+              ((84, 120), False), ((84,), False), ((10, 84), True), ((10,), True)]
+
+    def __init__(self, S, seed):
+        import numpy as np
+        self.S = S
+        self.rng = np.random.default_rng(seed)
+        self.history = []
+        self._pos = 0
+        self._call = 0
+        self.P = sum(int(np.prod(s)) for s, _ in self.SHAPES)
+
+    @staticmethod
+    def _share(e):
+        e[:, -850:] = e[:1, -850:]
+        return e
+
+    @staticmethod
+    def stream(S, seed, n):
+        import numpy as np
+        rng = np.random.default_rng(seed)
+        P = sum(int(np.prod(s)) for s, _ in LeNetNoiseFeeder.SHAPES)
+        return [LeNetNoiseFeeder._share(rng.standard_normal((S, P)).astype(np.float32)) for _ in range(n)]
+
+    def __call__(self, shape, dtype, device):
+        import numpy as np
+        import torch
+        if self._call == 0:
+            self.history.append(self._share(self.rng.standard_normal((self.S, self.P)).astype(np.float32)))
+            self._pos = 0
+        base, shared = self.SHAPES[self._call]
+        n = int(np.prod(base))
+        blk = self.history[-1][:, self._pos:self._pos + n]
+        if shared:
+            exp = tuple(base)
+            out = blk[0].reshape(exp)
+        else:
+            exp = (self.S,) + tuple(base) if len(base) > 1 else (self.S, 1) + tuple(base)
+            out = blk.reshape(exp)
+        assert tuple(shape) == exp, (tuple(shape), exp)
+        self._pos += n
+        self._call = (self._call + 1) % len(self.SHAPES)
+        return torch.from_numpy(np.ascontiguousarray(out)).to(dtype=dtype, device=device)
