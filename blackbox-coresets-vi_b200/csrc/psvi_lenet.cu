@@ -22,6 +22,7 @@ constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 =
               O_W5 = 60856, O_B5 = 61696;
 constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
 constexpr int RT = 8;   // rows per CTA of the fully connected kernels
+constexpr int N_CHUNKS = 16;   // row chunks of the conv weight-gradient kernels (16 x S CTAs)
 
 // ------------------------------------------------------------------------------------------------ conv + ReLU + pool
 // out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
@@ -146,61 +147,82 @@ conv_bwd_data_kernel(const float* __restrict__ pb1, const float* __restrict__ w1
   }
 }
 
-// d/d(weights, bias) of the fused conv + ReLU + pool, one CTA per (output channel, sample), reduced over rows and positions:
+// d/d(weights, bias) of the fused conv + ReLU + pool.  One CTA per (row chunk, sample) computes the contribution of its
+// rows to ALL CO*CI*25 weight gradients (each thread owns up to ceil(CO*CI*25 / 256) of them in registers) and to the CO
+// bias gradients, and writes a partial [chunk][s][CO*CI*25 + CO]; conv_wgrad_reduce_kernel sums the chunks in fixed order:
 //   wbar[s][co][ci][ky][kx] (+)= sum_r sum_{y,x} a[s][r][co][y][x] in[(s)][r][ci][y+ky-PAD][x+kx-PAD];  bbar[s][co] = sum a
 template <int CI, int CO, int HIN, int PAD>
 __global__ void __launch_bounds__(256)
 conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__ sel, const float* __restrict__ in, size_t ss,
-                       int R, float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NO = CI * 25, NG = 256 / NO;
-  __shared__ float s_a[HO * HO], s_in[CI * HP * HP], s_red[256];
-  const int co = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
-  const int o = tid % NO, g = tid / NO;
-  const bool active = g < NG;
-  const int ci = o / 25, ky = (o % 25) / 5, kx = o % 5;
-  float acc = 0.f, bacc = 0.f;
-  for (int r = 0; r < R; ++r) {
+                       int R, int rows_per_chunk, float* __restrict__ part) {
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NOUT = CO * CI * 25, NJ = (NOUT + 255) / 256;
+  __shared__ float s_a[CO * HO * HO], s_in[CI * HP * HP];
+  const int chunk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const int r0 = chunk * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
+  float acc[NJ], bacc[2] = {0.f, 0.f};   // bias gradients: warp w owns channels w and w + 8
+  int a_off[NJ], i_off[NJ];
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int o = tid + 256 * j;
+    acc[j] = 0.f;
+    const int oo = o < NOUT ? o : 0;
+    const int co = oo / (CI * 25), ci = (oo / 25) % CI, ky = (oo % 25) / 5, kx = oo % 5;
+    a_off[j] = co * HO * HO;
+    i_off[j] = (ci * HP + ky) * HP + kx;
+  }
+  for (int r = r0; r < r1; ++r) {
     const float* ip = in + (size_t)s * ss + (size_t)r * CI * HIN * HIN;
     for (int i = tid; i < CI * HP * HP; i += 256) {
       const int c = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
       s_in[i] = (yy >= 0 && yy < HIN && xx >= 0 && xx < HIN) ? ip[(c * HIN + yy) * HIN + xx] : 0.f;
     }
-    for (int i = tid; i < HO * HO; i += 256) s_a[i] = 0.f;
+    const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
+    for (int i = tid; i < CO * HO * HO; i += 256) {   // the pooled adjoint scattered to full resolution, built in one pass
+      const int co = i / (HO * HO), y = (i / HO) % HO, x = i % HO;
+      const int q = (co * HQ + (y >> 1)) * HQ + (x >> 1), c = sel[pbase + q];
+      s_a[i] = ((c & 4) && (c & 3) == ((y & 1) * 2 + (x & 1))) ? pb[pbase + q] : 0.f;
+    }
     __syncthreads();
-    const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ) + (size_t)co * HQ * HQ;
-    for (int idx = tid; idx < HQ * HQ; idx += 256) {
-      const int c = sel[pbase + idx];
-      if (c & 4) {
-        const int py = idx / HQ, px = idx % HQ, k = c & 3;
-        s_a[(2 * py + (k >> 1)) * HO + 2 * px + (k & 1)] = pb[pbase + idx];
+    for (int y = 0; y < HO; ++y)
+      for (int x = 0; x < HO; ++x) {
+        const int pa = y * HO + x, pi = y * HP + x;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = fmaf(s_a[a_off[j] + pa], s_in[i_off[j] + pi], acc[j]);
+      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int co = warp + 8 * h;
+      if (co < CO) {
+        float t = 0.f;
+        for (int pos = lane; pos < HO * HO; pos += 32) t += s_a[co * HO * HO + pos];
+        bacc[h] += warp_sum(t);
       }
     }
     __syncthreads();
-    if (active) {
-      const float* ib = s_in + (ci * HP + ky) * HP + kx;
-      for (int pos = g; pos < HO * HO; pos += NG) acc = fmaf(s_a[pos], ib[(pos / HO) * HP + pos % HO], acc);
-    }
-    if (bbar)
-      for (int pos = tid; pos < HO * HO; pos += 256) bacc += s_a[pos];
-    __syncthreads();
   }
-  s_red[tid] = active ? acc : 0.f;
-  __syncthreads();
-  if (tid < NO) {
-    float t = 0.f;
-    for (int k = 0; k < NG; ++k) t += s_red[tid + k * NO];
-    float* dst = wbar + (size_t)s * LN_P + co * NO + tid;
-    *dst = accumulate ? *dst + t : t;
+  float* dst = part + ((size_t)chunk * gridDim.y + s) * (NOUT + CO);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+    if (tid + 256 * j < NOUT) dst[tid + 256 * j] = acc[j];
+  if (lane == 0) {
+    if (warp < CO) dst[NOUT + warp] = bacc[0];
+    if (warp + 8 < CO) dst[NOUT + warp + 8] = bacc[1];
   }
-  if (bbar) {
-    __syncthreads();
-    s_red[tid] = bacc;
-    __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-      if (tid < k) s_red[tid] += s_red[tid + k];
-      __syncthreads();
-    }
-    if (tid == 0) bbar[(size_t)s * LN_P + co] = s_red[0];
+}
+
+// wbar[s][..] (+)= sum_chunks part;  bbar[s][co] = sum_chunks  (bbar nullable)
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int n_chunks, int S, int NOUT, int CO,
+                                         float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (i >= NOUT + CO) return;
+  float t = 0.f;
+  for (int c = 0; c < n_chunks; ++c) t += part[((size_t)c * S + s) * (NOUT + CO) + i];
+  if (i < NOUT) {
+    float* d = wbar + (size_t)s * LN_P + i;
+    *d = accumulate ? *d + t : t;
+  } else if (bbar) {
+    bbar[(size_t)s * LN_P + (i - NOUT)] = t;
   }
 }
 
@@ -294,37 +316,54 @@ lin_bwd_data_kernel(const float* __restrict__ y1, const float* __restrict__ w1, 
   }
 }
 
-// wbar[s][o][i] (+)= sum_r y[s][r][o] x[s][r][i];  bbar[s][o] = sum_r y[s][r][o]   (one CTA per 8 outputs and sample)
+// wbar[s][o][i] (+)= sum_r y[s][r][o] x[s][r][i];  bbar[s][o] = sum_r y[s][r][o]   (one CTA per 4 outputs and sample; a thread
+// owns up to four input columns i, i + 128, ... at once so that four independent loads are in flight per row)
 __global__ void __launch_bounds__(128)
 lin_bwd_weight_kernel(const float* __restrict__ y, const float* __restrict__ x, int R, int IN, int OUT,
                       float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
-  extern __shared__ float sy[];   // [R][8]
-  const int o0 = blockIdx.x * 8, s = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < R * 8; i += 128) {
-    const int r = i >> 3, o = o0 + (i & 7);
+  extern __shared__ float sy[];   // [R][4]
+  const int o0 = blockIdx.x * 4, s = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < R * 4; i += 128) {
+    const int r = i >> 2, o = o0 + (i & 3);
     sy[i] = o < OUT ? y[((size_t)s * R + r) * OUT + o] : 0.f;
   }
   __syncthreads();
   const float* xs = x + (size_t)s * R * IN;
-  for (int i = tid; i < IN; i += 128) {
-    float acc[8];
+  float acc[4][4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int r = 0; r < R; ++r) {
-      const float xv = xs[(size_t)r * IN + i];
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(sy[r * 8 + k], xv, acc[k]);
-    }
+    for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+  int col[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (o0 + k >= OUT) break;
-      float* dst = wbar + (size_t)s * LN_P + (size_t)(o0 + k) * IN + i;
-      *dst = accumulate ? *dst + acc[k] : acc[k];
+  for (int c = 0; c < 4; ++c) col[c] = tid + 128 * c;
+#pragma unroll 2
+  for (int r = 0; r < R; ++r) {
+    const float4 yv = *reinterpret_cast<const float4*>(sy + r * 4);
+    float xv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xv[c] = col[c] < IN ? xs[(size_t)r * IN + col[c]] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc[c][0] = fmaf(yv.x, xv[c], acc[c][0]);
+      acc[c][1] = fmaf(yv.y, xv[c], acc[c][1]);
+      acc[c][2] = fmaf(yv.z, xv[c], acc[c][2]);
+      acc[c][3] = fmaf(yv.w, xv[c], acc[c][3]);
     }
   }
-  if (bbar && tid < 8 && o0 + tid < OUT) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (col[c] >= IN) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (o0 + k >= OUT) break;
+      float* dst = wbar + (size_t)s * LN_P + (size_t)(o0 + k) * IN + col[c];
+      *dst = accumulate ? *dst + acc[c][k] : acc[c][k];
+    }
+  }
+  if (bbar && tid < 4 && o0 + tid < OUT) {
     float t = 0.f;
-    for (int r = 0; r < R; ++r) t += sy[r * 8 + tid];
+    for (int r = 0; r < R; ++r) t += sy[r * 4 + tid];
     bbar[(size_t)s * LN_P + o0 + tid] = t;
   }
 }
@@ -437,6 +476,7 @@ struct Ws {
   float *p1, *p2, *h3, *h4, *o, *pd1, *pd2, *hd3, *hd4, *od;
   float *g1, *g1d, *g2, *g2d, *g3, *g3d, *g4, *g4d, *go, *god;
   uint8_t *sel1, *sel2;
+  float* wpart;   // conv weight-gradient partials [N_CHUNKS][S][2416]
   size_t total;
 };
 void carve_ws(int S, int R, uint8_t* base, Ws& w) {
@@ -448,6 +488,7 @@ void carve_ws(int S, int R, uint8_t* base, Ws& w) {
   w.g1 = takef(n * N_P1); w.g1d = takef(n * N_P1); w.g2 = takef(n * N_P2); w.g2d = takef(n * N_P2);
   w.g3 = takef(n * N_H3); w.g3d = takef(n * N_H3); w.g4 = takef(n * N_H4); w.g4d = takef(n * N_H4);
   w.go = takef(n * N_O); w.god = takef(n * N_O);
+  w.wpart = takef((size_t)N_CHUNKS * S * 2416);
   w.sel1 = base ? base + off : nullptr; off += ((n * N_P1 + 255) & ~(size_t)255);
   w.sel2 = base ? base + off : nullptr; off += ((n * N_P2 + 255) & ~(size_t)255);
   w.total = off;
@@ -474,7 +515,7 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   PSVI_REQUIRE(theta && x && y && workspace, PSVI_ERR_INVALID, "null pointer");
   PSVI_REQUIRE(S >= 1 && S <= 64 && R >= 1, PSVI_ERR_INVALID, "bad S / R");
   PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
-  PSVI_REQUIRE(R * 8 * 4 <= 200 * 1024, PSVI_ERR_UNSUPPORTED, "at most 6400 rows per call");
+  PSVI_REQUIRE(R * 4 * 4 <= 200 * 1024, PSVI_ERR_UNSUPPORTED, "at most 12800 rows per call");
   cudaStream_t st = (cudaStream_t)stream_;
   Ws w;
   carve_ws(S, R, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255), w);
@@ -489,7 +530,16 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     lin_bwd_data_kernel<<<grow, 128, 2 * RT * OUT * sizeof(float), st>>>(y1, w1, y2, w2, R, IN, OUT, mask, out);
   };
   auto lin_bwd_weight = [&](const float* yy, const float* xx, int IN, int OUT, float* wb, float* bb, int acc) {
-    lin_bwd_weight_kernel<<<dim3((OUT + 7) / 8, S), 128, sR * 8 * sizeof(float), st>>>(yy, xx, R, IN, OUT, wb, bb, acc);
+    lin_bwd_weight_kernel<<<dim3((OUT + 3) / 4, S), 128, sR * 4 * sizeof(float), st>>>(yy, xx, R, IN, OUT, wb, bb, acc);
+  };
+  const int rpc = (R + N_CHUNKS - 1) / N_CHUNKS, nch = (R + rpc - 1) / rpc;
+  auto conv2_wgrad = [&](const float* pbv, const float* inp, float* wb, float* bb, int acc) {
+    conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(nch, S), 256, 0, st>>>(pbv, w.sel2, inp, sR * N_P1, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((2416 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 2400, 16, wb, bb, acc);
+  };
+  auto conv1_wgrad = [&](const float* pbv, float* wb, float* bb, int acc) {
+    conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(nch, S), 256, 0, st>>>(pbv, w.sel1, x, 0, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 150, 6, wb, bb, acc);
   };
   static bool attr_set = false;
   if (!attr_set) {
@@ -520,9 +570,9 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     lin_bwd_data(w.g4, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3);
     lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
-    conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2, w.sel2, w.p1, sR * N_P1, R, tbar + O_W2, tbar + O_B2, 0);
+    conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
     conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1);
-    conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1, w.sel1, x, 0, R, tbar + O_W1, tbar + O_B1, 0);
+    conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
     if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, nullptr, nullptr, w.sel1, R, xbar);
     LN_CHECK();
     return PSVI_OK;
@@ -556,14 +606,14 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   lin_bwd_data(w.g3d, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2d);
   LN_CHECK();
   // conv 2
-  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2, w.sel2, w.p1, sR * N_P1, R, tbar + O_W2, tbar + O_B2, 0);
-  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2d, w.sel2, w.pd1, sR * N_P1, R, tbar + O_W2, nullptr, 1);
-  conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(16, S), 256, 0, st>>>(w.g2d, w.sel2, w.p1, sR * N_P1, R, tdbar + O_W2, tdbar + O_B2, 0);
+  conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
+  conv2_wgrad(w.g2d, w.pd1, tbar + O_W2, nullptr, 1);
+  conv2_wgrad(w.g2d, w.p1, tdbar + O_W2, tdbar + O_B2, 0);
   conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, R, w.g1);
   conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1d);
   // conv 1
-  conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1, w.sel1, x, 0, R, tbar + O_W1, tbar + O_B1, 0);
-  conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(6, S), 256, 0, st>>>(w.g1d, w.sel1, x, 0, R, tdbar + O_W1, tdbar + O_B1, 0);
+  conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
+  conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1, 0);
   if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, R, xbar);
   LN_CHECK();
   return PSVI_OK;
