@@ -362,6 +362,85 @@ def main():
     except Exception as e:
         fulldata = {"error": repr(e)[:300]}
 
+    # -------- tensor-bound member of the path (cfg5 shapes): sampled-GEMM forward of fn D=256 H=1024 C=10 with S=64 MC
+    # samples over the full data (psvi_fn_predictive_tc: importance weights from M=1000 pseudo-points + mixture over rows);
+    # rows sharded over ranks (weak: 524 288 rows per rank), ONE all-reduce of the 8-float result.
+    fn_tc = None
+    try:
+        Df, Hf, Cf, Sf, Mf, rows_f = 256, 1024, 10, 64, 1000, 524_288
+        fmodel = _native.make_model([Df, Hf, Cf], Sf)
+        Pf = _native.num_theta(fmodel)
+        gg = torch.Generator(device=dev).manual_seed(17 + rank)
+        fmu = torch.cat([torch.randn(Hf * Df, device=dev, generator=gg) / Df ** 0.5, torch.zeros(Hf, device=dev),
+                         torch.randn(Cf * Hf, device=dev, generator=gg) / Hf ** 0.5, torch.zeros(Cf, device=dev)]).contiguous()
+        frho = torch.full((Pf,), -6.9, device=dev)
+        fu = torch.randn(Mf, Df, device=dev, generator=gg)
+        fz = torch.randint(0, Cf, (Mf,), device=dev, dtype=torch.int32, generator=gg)
+        fv = torch.zeros(Mf, device=dev)
+        fx = torch.randn(rows_f, Df, device=dev, generator=gg, dtype=torch.bfloat16)
+        fy = torch.randint(0, Cf, (rows_f,), device=dev, dtype=torch.int32, generator=gg)
+        fout = torch.zeros(8, device=dev)
+        fscr = torch.zeros(_native.fn_tc_scratch_floats(fmodel, rows_f, Mf), device=dev)
+        fnoise = _native.make_noise(None, seed=13, domain=1)
+
+        def fn_pass():
+            _native.fn_predictive_tc(fmodel, fnoise, fmu, frho, fu, fz, fv, fx, fy, 0, 1.0e4, 1, 0.0, 0, fout, fscr)
+            if world > 1:
+                dist.all_reduce(fout)
+        for _ in range(3):
+            fn_pass()
+        barrier()
+        reps = 8
+        a.record(stream)
+        for _ in range(reps):
+            fn_pass()
+        b.record(stream)
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = tt.item() * 1e-3 / reps
+        fl_f = 2.0 * Sf * (rows_f + Mf) * (Df * Hf + Hf * Cf)       # F_fwd(N) of SURVEY.md section 8d, per rank
+        fn_tc = {"what": f"psvi_fn_predictive_tc: fn D=256 H=1024 C=10, S=64, M=1000, {rows_f} bf16 rows per rank x {world} "
+                         "rank(s); whole call (Philox sampling of 64 x 273k weights, pseudo-data forward for the importance "
+                         "weights, TMA/tcgen05 forward over the rows, reduce)" + (" + all-reduce" if world > 1 else ""),
+                 "ms_per_pass": sec * 1e3, "rows_per_s": world * rows_f / sec, "row_samples_per_s": world * rows_f * Sf / sec,
+                 "flops_per_pass_per_rank": fl_f, "TFLOPs_per_gpu": fl_f / sec / 1e12}
+    except Exception as e:
+        fn_tc = {"error": repr(e)[:300]}
+
+    # -------- cfg4 (lenet, M=200, S=10, B=128): one PSVI outer step through the convolutional kernels, T=20 as in the
+    # reference's own lenet runs ------------------------------------------------------------------------
+    lenet = None
+    try:
+        from tests.fake_mnist import FakeMNIST
+        ltr, lte = FakeMNIST(1024, 0), FakeMNIST(256, 1)
+        lkw = dict(mc_samples=10, num_epochs=0, data_minibatch=128, D=784, N=len(ltr), inner_it=20, trainer="nested",
+                   log_every=150, lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-3, num_pseudo=200,
+                   seed=rank, architecture="lenet", n_hidden=0, n_layers=1, logistic_regression=False, train_dataset=ltr,
+                   test_dataset=lte, dnm="MNIST", nc=10, compute_weights_entropy=False, register_elbos=False, quiet=True)
+        from psvi.inference.psvi_classes import PSVILearnV
+        lobj = PSVILearnV(**lkw)
+        lobj.run_psvi(**lkw)
+        pc._dist_info = lambda: (None, 0, 1)
+        lxb, lyb = lobj._next_minibatch()
+        lobj.nested_step(lxb, lyb)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(3):
+            lobj.nested_step(lxb, lyb)
+        b.record(stream)
+        torch.cuda.synchronize()
+        pc._dist_info = real_dist_info
+        lms = a.elapsed_time(b) / 3
+        lflops = 2.0 * 10 * (28 * 28 * 25 * 6 + 100 * 150 * 16 + 400 * 120 + 120 * 84 + 84 * 10)   # fwd FLOPs per row, S=10
+        lfl = 20 * 9 * lflops * 200 + 3 * lflops * 328
+        lenet = {"what": "PSVILearnV.nested_step, lenet (P=61 706 per sample), M=200, S=10, B=128, T=20, fp32 CUDA-core "
+                         "conv/fc kernels (psvi_lenet_pass), host-sequenced streaming engine",
+                 "ms_per_outer_step": lms, "outer_steps_per_s": 1e3 / lms, "TFLOPs": lfl / (lms * 1e-3) / 1e12}
+    except Exception as e:
+        lenet = {"error": repr(e)[:300]}
+
     # -------- reduce over ranks ---------------------------------------------------------------------------------------
     value = world * K / (total_ms * 1e-3)
     e2e = world * K / (e2e_ms * 1e-3)
@@ -401,7 +480,15 @@ def main():
                     "note": "per GPU; algorithmic bytes = rows*(D*2+4) = 4.128 GB per launch; traffic = dram__bytes_read+write of "
                             "one ncu --set full capture of the same launch (profiles/r1_lr_tc_ncu_summary.md); peak = measured "
                             "copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"},
-                "extra": {"fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
+                "roofline_fn_tc": None if not fn_tc or "error" in fn_tc else {
+                    "bound": "tensor", "achieved": fn_tc["TFLOPs_per_gpu"], "peak": peaks.get("bf16_tflops_sustained", 1400.0),
+                    "unit": "TFLOP/s", "frac": fn_tc["TFLOPs_per_gpu"] / peaks.get("bf16_tflops_sustained", 1400.0),
+                    "traffic": None, "kernel": "psvi_fn_forward_tc_kernel",
+                    "note": "per GPU; algorithmic FLOPs = 2 S (rows + M) (D H + H C) with C = 10 (the kernel pads C to 16); "
+                            "time = whole psvi_fn_predictive_tc call incl. weight sampling; peak = measured SUSTAINED bf16 "
+                            "matmul throughput (the kernel runs for tens of ms back to back); ncu: "
+                            "profiles/r1_fn_tc_ncu_summary.md"},
+                "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
                                                     "full_data_predictive_passes_200rows": pred_evals},
                           "sharded": sharded, "kernel_only_ms": kernel_ms,
                           "per_step_ms_min_med_max": [min(ms), sorted(ms)[len(ms) // 2], max(ms)]}}
