@@ -107,7 +107,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// 2-D bf16 tensor map of a row-major [outer][inner] view whose rows are `ld` elements apart (ld >= inner)
+inline int make_map_2d_bf16_ld(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                               uint32_t box_outer);
 inline int make_map_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  return make_map_2d_bf16_ld(map, base, inner, outer, inner, box_inner, box_outer);
+}
+inline int make_map_2d_bf16_ld(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                               uint32_t box_outer) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -117,7 +124,7 @@ inline int make_map_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, 
     fn = reinterpret_cast<EncodeTiledFn>(ptr);
   }
   const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint64_t strides[1] = {ld * 2};
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,

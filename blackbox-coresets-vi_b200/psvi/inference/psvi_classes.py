@@ -178,6 +178,11 @@ class PSVI(object):
         if eng is None:
             if isinstance(model, MeanFieldLeNet):
                 eng = StreamEngine(LenetFamily(model), model.dims, model.n_samples(), net=LenetNet(model.n_samples()))
+            elif isinstance(model, MeanFieldMLP) and self._is_large_fn(model):
+                # large regime (BASELINE config 5): batched TMA + tcgen05 GEMMs, bf16 operands
+                from psvi.inference.stream import FnLargeNet
+                eng = StreamEngine(MeanFieldFamily(model), model.dims, model.n_samples(),
+                                   net=FnLargeNet(model.dims, model.n_samples()))
             else:
                 fam = FullCovFamily(model) if isinstance(model, FullCovMLP) else MeanFieldFamily(model)
                 eng = StreamEngine(fam, model.dims, model.n_samples())
@@ -185,6 +190,13 @@ class PSVI(object):
         if isinstance(model, MeanFieldMLP):
             eng.fam.mu, eng.fam.rho = model.flat()
         return eng
+
+    @staticmethod
+    def _is_large_fn(model):
+        """One-hidden-layer fn whose per-sample weights (> 40 k floats) fit no CTA and whose shape suits the tensor path."""
+        from psvi.inference.stream import FnLargeNet
+        dims = model.dims
+        return (FnLargeNet.fits(dims, model.n_samples()) and dims[1] * (dims[0] + 1) + dims[2] * (dims[1] + 1) > 40000)
 
     def _use_stream(self, model):
         return isinstance(model, (FullCovMLP, MeanFieldLeNet)) or self._ws.get(("force_stream", id(model)), False)
@@ -563,7 +575,11 @@ class PSVI(object):
         assert self.mc_samples > 1
         model, desc, S = self._model_desc()
         xt, yt = self._device_dataset(self.test_dataset, "test")
-        if isinstance(model, (FullCovMLP, MeanFieldLeNet)):
+        large_fn = isinstance(model, MeanFieldMLP) and not isinstance(model, MeanFieldLeNet) and self._is_large_fn(model)
+        if large_fn:
+            self._ws[("force_stream", id(model))] = True
+        use_fn_tc = large_fn and self._fits_fn_tc(model) and self.noise_source is None
+        if self._use_stream(model) and not use_fn_tc:
             eng = self._stream(model)
             u, _ = self._uv()
             batch = int(self.data_minibatch)
@@ -587,7 +603,20 @@ class PSVI(object):
             if noise.mode == _native.NOISE_EXTERNAL and lo > 0:   # external slabs are indexed from this rank's first
                 noise = _native.make_noise(noise._keepalive[lo:hi].contiguous())
             first = 0 if noise.mode == _native.NOISE_EXTERNAL else lo
-            if self._use_tensor_core_eval(model, r1 - r0, batch):
+            if use_fn_tc:
+                # large fn: sampled-GEMM forward on tcgen05 (psvi_fn_predictive_tc), bf16 operands, one launch set per slab
+                xb16 = self._device_bf16(xt, "test")
+                scratch = self._buf("eval_fn_tc", _native.fn_tc_scratch_floats(desc, min(batch, r1 - r0), u.shape[0]))
+                acc = torch.zeros(8, device=self.device)
+                for k in range(hi - lo):
+                    a0, a1 = r0 + k * batch, min(r0 + (k + 1) * batch, r1)
+                    _native.fn_predictive_tc(desc, noise, mu, rho, u, self._z32(), v, xb16[a0:a1], yt[a0:a1], first + k,
+                                             float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1,
+                                             out, scratch)
+                    acc[:3] += out[:3]
+                acc[3:5] = out[3:5]
+                out = acc
+            elif self._use_tensor_core_eval(model, r1 - r0, batch):
                 # large single-layer case: TMA + tcgen05 kernel, bf16 operands; one launch set per slab
                 xb16 = self._device_bf16(xt, "test")
                 scratch = self._buf("eval_tc", _native.lr_predictive_tc_scratch_floats(desc))
@@ -624,6 +653,11 @@ class PSVI(object):
                                           "D <= 256, C <= 16, S <= 16")
             return True
         return bool(fits and self.tensor_core_eval == "auto" and min(rows, batch) >= 65536)
+
+    @staticmethod
+    def _fits_fn_tc(model):
+        d = model.dims
+        return len(d) == 3 and d[0] % 64 == 0 and 64 <= d[0] <= 256 and d[1] % 128 == 0 and d[2] <= 16 and model.n_samples() <= 64
 
     def _device_bf16(self, x, key):
         c = self._dev_data.get(key + "_bf16")

@@ -205,6 +205,25 @@ class MlpNet:
         _native.net_predict(self.desc, theta, lw, mode, xt, yt, out)
 
 
+class FnLargeNet:
+    """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu)."""
+
+    def __init__(self, dims, S):
+        self.desc, self.S, self.C = _native.make_model(dims, S), S, dims[-1]
+
+    @staticmethod
+    def fits(dims, S):
+        return len(dims) == 3 and dims[0] % 64 == 0 and dims[1] % 128 == 0 and dims[2] <= 16 and S <= 64
+
+    def pass_(self, theta, thetad, x, y, cw, **out):
+        _native.fnl_pass(self.desc, theta, thetad, x, y, cw, **out)
+
+    def predict(self, theta, lw, mode, xt, yt, out):
+        logits = torch.empty(self.S, xt.shape[0], self.C, device=xt.device)
+        _native.fnl_pass(self.desc, theta, None, xt, yt, None, logits=logits)
+        _native.logits_predict(logits, lw, mode, yt, out)
+
+
 class LenetNet:
     """Per-sample lenet pass: fused conv + ReLU + pool kernels and the fc kernels of csrc/psvi_lenet.cu."""
 

@@ -247,6 +247,17 @@ int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const fl
                    const void* x_bf16, const int32_t* labels, const float* row_weights, int64_t n_rows, int32_t slab,
                    float* wsum_out, float* nkl_out, float* nll_out, void* scratch, void* stream);
 
+/* ---- large-regime per-sample network pass for `fn` with ONE hidden layer (BASELINE config 5: D=256, H=1024, S=64,
+ * M=1000): same contract as psvi_net_pass (forward / gradient / dual Hessian-vector pass on sampled weights theta [S][P],
+ * reference neural_net.py:155-179 + autograd), for models whose per-sample weights fit no CTA.  Every matrix product is a
+ * batched bf16 TMA + tcgen05 GEMM with fp32 accumulation (csrc/psvi_fn_large.cu); the hidden activations are kept in bf16.
+ *   needs n_layers == 2, D a multiple of 64, H a multiple of 128, C <= 16, S <= 64;  x [R][D] fp32, y [R] int32,
+ *   cw [S][R] (nullable -> 1);  outputs as psvi_net_pass (logits [S][R][C]);  workspace: psvi_fnl_workspace_bytes(). */
+size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R);
+int psvi_fnl_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+                  const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
+                  void* workspace, void* stream);
+
 /* ---- convolutional family (lenet): per-sample network pass on externally supplied weights, same contract as
  * psvi_net_pass.  Replaces VIConv2d.forward (grouped conv over samples), BatchMaxPool2d, nn.Flatten and the three VILinear
  * layers of make_lenet + Categorical.log_prob + autograd (psvi/models/neural_net.py:194-255,334-359).
