@@ -6,34 +6,45 @@
 // (psvi/models/neural_net.py:155-179,267-297; psvi_classes.py:445-511,541-600; robust_higher/optim.py:224-229).
 //
 // Every matrix product of the pass is ONE launch of a batched "TN" GEMM kernel, C[b] = A[b] B[b]^T with
-// bf16 K-major operands and fp32 accumulation: TMA (128-byte swizzle) -> 6-stage shared-memory ring -> tcgen05.mma
-// (M = N = 128, K = 16) -> double-buffered TMEM accumulator -> 8 epilogue warps (tcgen05.ld, bias / ReLU / ReLU-mask,
-// fp32, bf16 and transposed-bf16 stores).  Sums of two products are one GEMM over a concatenated K dimension
-// ([hdot | h] [W2 | W2dot]^T etc.); products with K = C <= 16 use zero-padded K = 64 operand blocks.  Activations that feed
-// a later GEMM as the K dimension are stored transposed by the producing epilogue.  Reductions over rows with a C- or 1-wide
-// output (second-layer and bias gradients) are CUDA-core column reductions.
+// K-major operands and fp32 accumulation: TMA (128-byte swizzle) -> shared-memory ring -> tcgen05.mma (M = N = 128) ->
+// double-buffered TMEM accumulator -> 8 epilogue warps (tcgen05.ld, bias / ReLU / ReLU-mask, plain fp32 stores, operand
+// stores and transposed operand stores).  Two arithmetic modes:
+//   precision 0 (bf16)    operands rounded to bf16, one kind::f16 MMA per K step: full tensor rate, ~1e-2 relative error per
+//                         pass -- fine for values, first-order training (mfvi) and prediction;
+//   precision 1 (tf32x3)  every operand is kept as an fp32 pair (hi, lo) of TF32-representable numbers (hi = rna_tf32(x),
+//                         lo = rna_tf32(x - hi)) and every K step issues three kind::tf32 MMAs (hi hi + hi lo + lo hi):
+//                         fp32-class accuracy (~2^-21) at 1/6 of the bf16 rate.  The unrolled hypergradient needs it:
+//                         the reverse sweep through Adam divides by |g_i|, so per-coordinate gradient errors of bf16 size
+//                         destroy it (measured in DESIGN.md 4.8).
+// Sums of two products are one GEMM over a concatenated K dimension ([hdot | h] [W2 | W2dot]^T etc.); products with
+// K = C <= 16 use zero-padded K blocks (one 128-byte swizzle row).  Activations that feed a later GEMM as the K dimension
+// are stored transposed by the producing epilogue.  Reductions over rows with a C- or 1-wide output (second-layer and
+// bias gradients) are CUDA-core column reductions.
 #include "psvi_tc.cuh"
 
 using namespace psvi_tc;
 
 namespace {
 
-constexpr int GM = 128, GN = 128, GK = 64;
-constexpr int GST = 6;                          // ring depth: 6 x (16 KB A + 16 KB B)
+constexpr int GM = 128, GN = 128;
 constexpr int G_THREADS = 128 + 256;            // 4 role warps + 8 epilogue warps
-constexpr int G_TILE_BYTES = GM * GK * 2;       // 16 KB
-constexpr int CW = 16, CP = 64;                 // classes padded to 16 (fp32 side) / 64 (bf16 K blocks)
+constexpr int G_TILE_BYTES = GM * 128;          // 16 KB: 128 rows of one 128-byte swizzle row
+constexpr int CW = 16;                          // classes padded to 16 on the fp32 side
+
+template <int X3> struct Prec;
+template <> struct Prec<0> { static constexpr int ES = 2, GK = 64, TILES = 2, GST = 6; };   // bf16
+template <> struct Prec<1> { static constexpr int ES = 4, GK = 32, TILES = 4, GST = 3; };   // tf32 (hi, lo) pairs
 
 struct GemmP {
-  int batch, m_tiles, n_tiles, kc;              // kc = K / 64
+  int batch, m_tiles, n_tiles, kc;              // kc = K / GK
   int M_valid, N_valid;
   int a_brows, b_brows;                         // rows per batch in the A / B tensor maps (0: operand shared by all batches)
   const float* bias; long long bias_bs;         // + bias[b * bias_bs + n]
   int relu;
-  const __nv_bfloat16* mask; long long mask_bs; int mask_ld;    // * (mask[b][m][n] > 0)
+  const void* mask; long long mask_bs; int mask_ld;             // * (mask[b][m][n] > 0)   (bf16, or the fp32 hi part)
   float* of; long long of_bs; int of_ld;                       // fp32 out [b][m][n], m < M_valid, n < N_valid
-  __nv_bfloat16* ob; long long ob_bs; int ob_ld; int ob_rows;   // bf16 out [b][m][n], m < ob_rows (zeros for m >= M_valid)
-  __nv_bfloat16* obt; long long obt_bs; int obt_ld;             // bf16 transposed out [b][n][m], m < ob_rows
+  void *ob, *ob_lo; long long ob_bs; int ob_ld; int ob_rows;    // operand out [b][m][n], m < ob_rows (zeros for m >= M_valid)
+  void *obt, *obt_lo; long long obt_bs; int obt_ld;             // transposed operand out [b][n][m], m < ob_rows
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -41,21 +52,46 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// x = hi + lo with hi, lo representable in TF32 (10 explicit mantissa bits), |x - hi - lo| <= 2^-22 |x|
+__host__ __device__ __forceinline__ float tf32_rna(float x) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r & 0xFFFFE000u);
+#else
+  return x;
+#endif
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
 
+template <int X3>
 __global__ void __launch_bounds__(G_THREADS, 1)
-tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmP p) {
+tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bl, const GemmP p) {
+  using PR = Prec<X3>;
+  constexpr int STAGE = PR::TILES * G_TILE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* ring = smem;                                    // [GST][A tile | B tile]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + GST * 2 * G_TILE_BYTES);
-  uint64_t* full = bars;             // [GST]
-  uint64_t* empty = bars + GST;      // [GST]
-  uint64_t* tfull = empty + GST;     // [2]
-  uint64_t* tempty = tfull + 2;      // [2]
+  uint8_t* ring = smem;                                    // [GST][A (| A lo) | B (| B lo)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + PR::GST * STAGE);
+  uint64_t* full = bars;                 // [GST]
+  uint64_t* empty = bars + PR::GST;      // [GST]
+  uint64_t* tfull = empty + PR::GST;     // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < PR::GST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -78,17 +114,25 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int k = 0; k < p.kc; ++k) {
         mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
-          uint8_t* dst = ring + st * 2 * G_TILE_BYTES;
-          mbar_expect_tx(&full[st], 2 * G_TILE_BYTES);
-          tma_load_2d(&map_a, &full[st], dst, k * GK, arow);
-          tma_load_2d(&map_b, &full[st], dst + G_TILE_BYTES, k * GK, brow);
+          uint8_t* dst = ring + st * STAGE;
+          mbar_expect_tx(&full[st], STAGE);
+          tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
+          if (X3) {
+            tma_load_2d(&map_al, &full[st], dst + G_TILE_BYTES, k * PR::GK, arow);
+            tma_load_2d(&map_b, &full[st], dst + 2 * G_TILE_BYTES, k * PR::GK, brow);
+            tma_load_2d(&map_bl, &full[st], dst + 3 * G_TILE_BYTES, k * PR::GK, brow);
+          } else {
+            tma_load_2d(&map_b, &full[st], dst + G_TILE_BYTES, k * PR::GK, brow);
+          }
         }
         __syncwarp();
-        if (++st == GST) { st = 0; ph ^= 1; }
+        if (++st == PR::GST) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+    // instruction descriptor: D = f32, A = B = bf16 (format 1) or tf32 (format 2), both K-major, N = 128, M = 128
+    const uint32_t fmt = X3 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
     int st = 0, it = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < n_total; t += gridDim.x, ++it) {
@@ -99,17 +143,28 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int k = 0; k < p.kc; ++k) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(ring + st * 2 * G_TILE_BYTES), b0 = a0 + G_TILE_BYTES;
+        const uint32_t s0 = smem_u32(ring + st * STAGE);
         const uint32_t acc0 = k != 0;
         if (elect_one()) {
+          if (X3) {
+            const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
 #pragma unroll
-          for (int j = 0; j < GK / 16; ++j)
-            umma_bf16(tmem_d, make_desc_sw128(a0 + j * 32), make_desc_sw128(b0 + j * 32), idesc, j ? 1u : acc0);
+            for (int j = 0; j < 4; ++j) {   // K = 8 fp32 = 32 bytes per step; small terms first
+              umma_tf32(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
+              umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
+              umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
+            }
+          } else {
+            const uint32_t a0 = s0, b0 = s0 + G_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)     // K = 16 bf16 = 32 bytes per step
+              umma_bf16(tmem_d, make_desc_sw128(a0 + j * 32), make_desc_sw128(b0 + j * 32), idesc, j ? 1u : acc0);
+          }
           umma_commit(&empty[st]);
           if (k == p.kc - 1) umma_commit(&tfull[buf]);
         }
         __syncwarp();
-        if (++st == GST) { st = 0; ph ^= 1; }
+        if (++st == PR::GST) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -138,18 +193,31 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask && vm) {   // N_valid is a multiple of 32 whenever a mask / bf16 output is used
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)b * p.mask_bs + (long long)m * p.mask_ld + n0);
+          if (p.mask && vm) {   // N_valid is a multiple of 32 whenever a mask / operand output is used
+            if (X3) {
+              const float4* mp = reinterpret_cast<const float4*>(static_cast<const float*>(p.mask) + (long long)b * p.mask_bs +
+                                                                 (long long)m * p.mask_ld + n0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 mk = __ldg(mp + i);
-              const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+              for (int i = 0; i < 8; ++i) {
+                const float4 mk = __ldg(mp + i);
+                if (!(mk.x > 0.f)) v[4 * i] = 0.f;
+                if (!(mk.y > 0.f)) v[4 * i + 1] = 0.f;
+                if (!(mk.z > 0.f)) v[4 * i + 2] = 0.f;
+                if (!(mk.w > 0.f)) v[4 * i + 3] = 0.f;
+              }
+            } else {
+              const uint4* mp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask) + (long long)b * p.mask_bs +
+                                                               (long long)m * p.mask_ld + n0);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // bf16 > 0  <=>  sign bit clear and not zero
-                const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
-                if (!(lo != 0 && !(lo & 0x8000u))) v[i * 8 + e * 2] = 0.f;
-                if (!(hi != 0 && !(hi & 0x8000u))) v[i * 8 + e * 2 + 1] = 0.f;
+              for (int i = 0; i < 4; ++i) {
+                const uint4 mk = __ldg(mp + i);
+                const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {   // bf16 > 0  <=>  sign bit clear and not zero
+                  const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+                  if (!(lo != 0 && !(lo & 0x8000u))) v[i * 8 + e * 2] = 0.f;
+                  if (!(hi != 0 && !(hi & 0x8000u))) v[i * 8 + e * 2 + 1] = 0.f;
+                }
               }
             }
           }
@@ -164,22 +232,49 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (n0 + j < p.N_valid) op[j] = v[j];
           }
           if (p.ob && m < p.ob_rows) {
-            uint4* op = reinterpret_cast<uint4*>(p.ob + (long long)b * p.ob_bs + (long long)m * p.ob_ld + n0);
+            const long long off = (long long)b * p.ob_bs + (long long)m * p.ob_ld + n0;
+            if (X3) {
+              float4* oh = reinterpret_cast<float4*>(static_cast<float*>(p.ob) + off);
+              float4* ol = reinterpret_cast<float4*>(static_cast<float*>(p.ob_lo) + off);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t w[4];
+              for (int i = 0; i < 8; ++i) {
+                float h4[4], l4[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i * 8 + e * 2], v[i * 8 + e * 2 + 1]);
-                w[e] = *reinterpret_cast<uint32_t*>(&t2);
+                for (int e = 0; e < 4; ++e) split_tf32(v[4 * i + e], h4[e], l4[e]);
+                oh[i] = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                ol[i] = make_float4(l4[0], l4[1], l4[2], l4[3]);
               }
-              op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob) + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i * 8 + e * 2], v[i * 8 + e * 2 + 1]);
+                  w[e] = *reinterpret_cast<uint32_t*>(&t2);
+                }
+                op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
             }
           }
           if (p.obt && m < p.ob_rows) {
-            __nv_bfloat16* op = p.obt + (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + m;
+            const long long off = (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + m;
+            if (X3) {
+              float* oh = static_cast<float*>(p.obt) + off;
+              float* ol = static_cast<float*>(p.obt_lo) + off;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[(long long)j * p.obt_ld] = __float2bfloat16(v[j]);
+              for (int j = 0; j < 32; ++j) {
+                float hi, lo;
+                split_tf32(v[j], hi, lo);
+                oh[(long long)j * p.obt_ld] = hi;
+                ol[(long long)j * p.obt_ld] = lo;
+              }
+            } else {
+              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.obt) + off;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[(long long)j * p.obt_ld] = __float2bfloat16(v[j]);
+            }
           }
         }
       }
@@ -196,29 +291,48 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// ------------------------------------------------------------------------------------------------ operand packing
-// x fp32 [R][D] -> Xb bf16 [Rp][D] (padding rows zero) and XT bf16 [D][Rp]
-__global__ void fnl_prep_x_kernel(const float* __restrict__ x, int R, int Rp, int D, __nv_bfloat16* __restrict__ Xb,
-                                  __nv_bfloat16* __restrict__ XT) {
+// ------------------------------------------------------------------------------------------------ operand stores
+// one operand element: bf16 (X3 = 0) or the (hi, lo) fp32 pair (X3 = 1)
+template <int X3>
+__device__ __forceinline__ void put(void* hi_base, void* lo_base, size_t i, float v) {
+  if (X3) {
+    float h, l;
+    split_tf32(v, h, l);
+    static_cast<float*>(hi_base)[i] = h;
+    static_cast<float*>(lo_base)[i] = l;
+  } else {
+    static_cast<__nv_bfloat16*>(hi_base)[i] = __float2bfloat16(v);
+  }
+}
+template <int X3>
+__device__ __forceinline__ float get(const void* hi_base, const void* lo_base, size_t i) {
+  if (X3) return static_cast<const float*>(hi_base)[i] + static_cast<const float*>(lo_base)[i];
+  return __bfloat162float(static_cast<const __nv_bfloat16*>(hi_base)[i]);
+}
+
+// x fp32 [R][D] -> X [Rp][D] (padding rows zero) and XT [D][Rp]
+template <int X3>
+__global__ void fnl_prep_x_kernel(const float* __restrict__ x, int R, int Rp, int D, void* Xh, void* Xl, void* XTh, void* XTl) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, d0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
   for (int i = ty; i < 32; i += 8) {
     const int r = r0 + i, d = d0 + tx;
     const float v = (r < R && d < D) ? x[(size_t)r * D + d] : 0.f;
     tile[i][tx] = v;
-    if (r < Rp && d < D) Xb[(size_t)r * D + d] = __float2bfloat16(v);
+    if (r < Rp && d < D) put<X3>(Xh, Xl, (size_t)r * D + d, v);
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int d = d0 + i, r = r0 + tx;
-    if (d < D && r < Rp) XT[(size_t)d * Rp + r] = __float2bfloat16(tile[tx][i]);
+    if (d < D && r < Rp) put<X3>(XTh, XTl, (size_t)d * Rp + r, tile[tx][i]);
   }
 }
 
-// first-layer weights of theta (or thetadot) [S][P] -> W1 bf16 [S][H][D] and its transpose into W1T2 [S][D][2H] at column
-// offset `toff` (0: primal, H: tangent)
-__global__ void fnl_pack_w1_kernel(const float* __restrict__ theta, long long P, int D, int H, __nv_bfloat16* __restrict__ W1b,
-                                   __nv_bfloat16* __restrict__ W1T2, int toff) {
+// first-layer weights of theta (or thetadot) [S][P] -> W1 [S][H][D] and its transpose into W1T2 [S][D][2H] at column offset
+// `toff` (0: primal, H: tangent)
+template <int X3>
+__global__ void fnl_pack_w1_kernel(const float* __restrict__ theta, long long P, int D, int H, void* W1h, void* W1l, void* Th,
+                                   void* Tl, int toff) {
   __shared__ float tile[32][33];
   const int d0 = blockIdx.x * 32, h0 = blockIdx.y * 32, s = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
   const float* th = theta + (long long)s * P;
@@ -226,47 +340,46 @@ __global__ void fnl_pack_w1_kernel(const float* __restrict__ theta, long long P,
     const int h = h0 + i, d = d0 + tx;
     const float v = th[(size_t)h * D + d];
     tile[i][tx] = v;
-    W1b[((size_t)s * H + h) * D + d] = __float2bfloat16(v);
+    put<X3>(W1h, W1l, ((size_t)s * H + h) * D + d, v);
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int d = d0 + i, h = h0 + tx;
-    W1T2[((size_t)s * D + d) * (2 * H) + toff + h] = __float2bfloat16(tile[tx][i]);
+    put<X3>(Th, Tl, ((size_t)s * D + d) * (2 * H) + toff + h, tile[tx][i]);
   }
 }
 
-// second-layer weights: W2p bf16 [S][128][2H] rows c < C at column offset poff; W2T bf16 [S][H][128] at column offset coff
-__global__ void fnl_pack_w2_kernel(const float* __restrict__ theta, long long P, int D, int H, int C, __nv_bfloat16* __restrict__ W2p,
-                                   int poff, __nv_bfloat16* __restrict__ W2T, int coff) {
+// second-layer weights: W2p [S][128][2H] rows c < C at column offset poff; W2T [S][H][2 CP] at column offset coff
+template <int X3>
+__global__ void fnl_pack_w2_kernel(const float* __restrict__ theta, long long P, int D, int H, int C, void* W2ph, void* W2pl,
+                                   int poff, void* W2Th, void* W2Tl, int coff, int cp2) {
   const int s = blockIdx.y;
   const float* w2 = theta + (long long)s * P + (long long)H * D + H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * H; i += gridDim.x * blockDim.x) {
     const int c = i / H, h = i - c * H;
-    const __nv_bfloat16 v = __float2bfloat16(w2[i]);
-    W2p[((size_t)s * 128 + c) * (2 * H) + poff + h] = v;
-    W2T[((size_t)s * H + h) * 128 + coff + c] = v;
+    const float v = w2[i];
+    put<X3>(W2ph, W2pl, ((size_t)s * 128 + c) * (2 * H) + poff + h, v);
+    put<X3>(W2Th, W2Tl, ((size_t)s * H + h) * cp2 + coff + c, v);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ softmax / NLL head
-// logits o [S][Rp][16] (bias b2 still to be added) and, in dual mode, od (+ b2dot).
-//   mode 0: nll;  mode 1: nll, go = cw (p - onehot) -> fp32 [S][R][16] and bf16 AA[s][r][0..63];
-//   mode 2: go = cw p (od - <p, od>) -> fp32 + AA[..][64..127], god = cw (p - onehot) -> fp32 + AA[..][0..63], acbar = q . od
+// logits o [S][Rp][16] (bias b2 still to be added) and, in dual mode, od (+ b2dot).  AA [S][Rp][2 CP]: K blocks of CP entries.
+//   mode 0: nll;  mode 1: nll, go = cw (p - onehot) -> fp32 [S][R][16] and AA block 0;
+//   mode 2: go = cw p (od - <p, od>) -> fp32 + AA block 1, god = cw (p - onehot) -> fp32 + AA block 0, acbar = q . od
+template <int X3>
 __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __restrict__ od, const float* __restrict__ b2,
                                 const float* __restrict__ b2d, long long P, const int* __restrict__ y, const float* __restrict__ cw,
                                 int S, int R, int Rp, int C, int mode, float* __restrict__ nll, float* __restrict__ logits_out,
-                                float* __restrict__ go, float* __restrict__ god, __nv_bfloat16* __restrict__ AA,
-                                float* __restrict__ acbar) {
+                                float* __restrict__ go, float* __restrict__ god, void* AAh, void* AAl, float* __restrict__ acbar) {
+  constexpr int CPK = Prec<X3>::GK;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * Rp) return;
   const int s = idx / Rp, r = idx - s * Rp;
-  if (r >= R) {
-    if (AA && mode >= 1) {
-      uint4* a = reinterpret_cast<uint4*>(AA + (size_t)idx * 128);
-      for (int i = 0; i < 16; ++i) a[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    return;
-  }
+  const size_t ab = (size_t)idx * 2 * CPK;
+  if (mode >= 1)
+    for (int c = 0; c < 2 * CPK; ++c) put<X3>(AAh, AAl, ab + c, 0.f);
+  if (r >= R) return;
   const float* lo = o + (size_t)idx * CW;
   float lg[CW], p[CW], mx = -INFINITY, se = 0.f;
 #pragma unroll
@@ -289,11 +402,9 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
   float q[CW];
 #pragma unroll
   for (int c = 0; c < CW; ++c) { p[c] *= inv; q[c] = c < C ? p[c] - (c == lab ? 1.f : 0.f) : 0.f; }
-  __nv_bfloat16* a = AA + (size_t)idx * 128;
   if (mode == 1) {
 #pragma unroll
-    for (int c = 0; c < CW; ++c) { go[oidx * CW + c] = w * q[c]; a[c] = __float2bfloat16(w * q[c]); }
-    for (int c = CW; c < 128; ++c) a[c] = __float2bfloat16(0.f);
+    for (int c = 0; c < CW; ++c) { go[oidx * CW + c] = w * q[c]; put<X3>(AAh, AAl, ab + c, w * q[c]); }
     return;
   }
   const float* ld = od + (size_t)idx * CW;
@@ -304,33 +415,33 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
     dot += p[c] * dd[c];
     qd += q[c] * dd[c];
   }
-  for (int c = 0; c < 128; ++c) a[c] = __float2bfloat16(0.f);
 #pragma unroll
   for (int c = 0; c < CW; ++c) {
     const float g1 = c < C ? w * p[c] * (dd[c] - dot) : 0.f, g2 = w * q[c];
     go[oidx * CW + c] = g1;
     god[oidx * CW + c] = g2;
-    a[CP + c] = __float2bfloat16(g1);
-    a[c] = __float2bfloat16(g2);
+    put<X3>(AAh, AAl, ab + CPK + c, g1);
+    put<X3>(AAh, AAl, ab + c, g2);
   }
   if (acbar) acbar[oidx] = qd;
 }
 
 // out[s * P + c * H + h] (+)= sum_r W[s][r][c] * Y[s][r][h]   (W == NULL: C = 1, weight 1 -> column sums)
+template <int X3>
 __global__ void __launch_bounds__(128)
-fnl_colreduce_kernel(const __nv_bfloat16* __restrict__ Y, long long y_bs, int y_ld, const float* __restrict__ W, int R, int H, int C,
-                     float* __restrict__ out, long long P, int accumulate) {
+fnl_colreduce_kernel(const void* Yh, const void* Yl, long long y_off, long long y_bs, int y_ld, const float* __restrict__ W, int R,
+                     int H, int C, float* __restrict__ out, long long P, int accumulate) {
   const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y;
   if (h >= H) return;
   float acc[CW];
 #pragma unroll
   for (int c = 0; c < CW; ++c) acc[c] = 0.f;
-  const __nv_bfloat16* yp = Y + (long long)s * y_bs + h;
+  const size_t y0 = (size_t)(y_off + (long long)s * y_bs + h);
   if (W) {
     const float4* wp = reinterpret_cast<const float4*>(W + (size_t)s * R * CW);
 #pragma unroll 2
     for (int r = 0; r < R; ++r) {
-      const float yv = __bfloat162float(yp[(long long)r * y_ld]);
+      const float yv = get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
       const float4 w0 = __ldg(wp + r * 4), w1 = __ldg(wp + r * 4 + 1), w2 = __ldg(wp + r * 4 + 2), w3 = __ldg(wp + r * 4 + 3);
       acc[0] = fmaf(w0.x, yv, acc[0]); acc[1] = fmaf(w0.y, yv, acc[1]); acc[2] = fmaf(w0.z, yv, acc[2]); acc[3] = fmaf(w0.w, yv, acc[3]);
       acc[4] = fmaf(w1.x, yv, acc[4]); acc[5] = fmaf(w1.y, yv, acc[5]); acc[6] = fmaf(w1.z, yv, acc[6]); acc[7] = fmaf(w1.w, yv, acc[7]);
@@ -339,7 +450,7 @@ fnl_colreduce_kernel(const __nv_bfloat16* __restrict__ Y, long long y_bs, int y_
     }
   } else {
 #pragma unroll 4
-    for (int r = 0; r < R; ++r) acc[0] += __bfloat162float(yp[(long long)r * y_ld]);
+    for (int r = 0; r < R; ++r) acc[0] += get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
   }
   for (int c = 0; c < C; ++c) {
     float* d = out + (long long)s * P + (long long)c * H + h;
@@ -363,28 +474,33 @@ __global__ void fnl_colsum16_kernel(const float* __restrict__ W, int R, int C, f
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// an operand array: the hi part (or the bf16 array) and, in tf32x3 mode, the lo part right behind it
+struct Buf {
+  uint8_t *hi, *lo;
+};
 struct Lws {
-  __nv_bfloat16 *Xb, *XT, *W1b, *W1db, *W1T2, *W2p, *W2T, *hh, *aa, *aT, *adT, *AA;
+  Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA;
   float *o, *od, *go, *god;
   size_t total;
 };
 
-void carve_l(int S, int R, int D, int H, uint8_t* base, Lws& w) {
-  const size_t Rp = (size_t)((R + 127) / 128) * 128;
+void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
+  const size_t Rp = (size_t)((R + 127) / 128) * 128, es = x3 ? 4 : 2, cp2 = x3 ? 64 : 128;
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
-  w.Xb = (__nv_bfloat16*)take(Rp * D * 2);
-  w.XT = (__nv_bfloat16*)take((size_t)D * Rp * 2);
-  w.W1b = (__nv_bfloat16*)take((size_t)S * H * D * 2);
-  w.W1db = (__nv_bfloat16*)take((size_t)S * H * D * 2);
-  w.W1T2 = (__nv_bfloat16*)take((size_t)S * D * 2 * H * 2);
-  w.W2p = (__nv_bfloat16*)take((size_t)S * 128 * 2 * H * 2);
-  w.W2T = (__nv_bfloat16*)take((size_t)S * H * 128 * 2);
-  w.hh = (__nv_bfloat16*)take((size_t)S * Rp * 2 * H * 2);
-  w.aa = (__nv_bfloat16*)take((size_t)S * Rp * 2 * H * 2);
-  w.aT = (__nv_bfloat16*)take((size_t)S * H * Rp * 2);
-  w.adT = (__nv_bfloat16*)take((size_t)S * H * Rp * 2);
-  w.AA = (__nv_bfloat16*)take((size_t)S * Rp * 128 * 2);
+  auto takeb = [&](size_t elems) { Buf b; b.hi = take(elems * es); b.lo = x3 ? take(elems * es) : nullptr; return b; };
+  w.X = takeb(Rp * D);
+  w.XT = takeb((size_t)D * Rp);
+  w.W1 = takeb((size_t)S * H * D);
+  w.W1d = takeb((size_t)S * H * D);
+  w.W1T2 = takeb((size_t)S * D * 2 * H);
+  w.W2p = takeb((size_t)S * 128 * 2 * H);
+  w.W2T = takeb((size_t)S * H * cp2);
+  w.hh = takeb((size_t)S * Rp * 2 * H);
+  w.aa = takeb((size_t)S * Rp * 2 * H);
+  w.aT = takeb((size_t)S * H * Rp);
+  w.adT = takeb((size_t)S * H * Rp);
+  w.AA = takeb((size_t)S * Rp * cp2);
   w.o = (float*)take((size_t)S * Rp * CW * 4);
   w.od = (float*)take((size_t)S * Rp * CW * 4);
   w.go = (float*)take((size_t)S * R * CW * 4);
@@ -393,18 +509,53 @@ void carve_l(int S, int R, int D, int H, uint8_t* base, Lws& w) {
 }
 
 struct Operand {
-  const __nv_bfloat16* base;
+  Buf buf;
+  uint64_t eoff;               // element offset of the view inside the buffer
   uint64_t inner, outer, ld;   // K extent, rows, leading dimension (elements)
   int brows;                   // rows per batch (0: shared)
 };
 
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_map_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                 uint32_t box_outer) {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    PSVI_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr));
+    PSVI_REQUIRE(ptr != nullptr && qr == cudaDriverEntryPointSuccess, PSVI_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {ld * 4};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PSVI_REQUIRE(r == CUDA_SUCCESS, PSVI_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return PSVI_OK;
+}
+
+template <int X3>
 int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream_t st) {
-  CUtensorMap ma, mb;
-  int rc = make_map_2d_bf16_ld(&ma, A.base, A.inner, A.outer, A.ld, GK, GM);
-  if (rc) return rc;
-  rc = make_map_2d_bf16_ld(&mb, B.base, B.inner, B.outer, B.ld, GK, GN);
-  if (rc) return rc;
-  p.kc = (int)(A.inner / GK);
+  using PR = Prec<X3>;
+  CUtensorMap ma, mal, mb, mbl;
+  int rc;
+  if (X3) {
+    if ((rc = make_map_f32(&ma, A.buf.hi + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
+    if ((rc = make_map_f32(&mal, A.buf.lo + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
+    if ((rc = make_map_f32(&mb, B.buf.hi + B.eoff * 4, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+    if ((rc = make_map_f32(&mbl, B.buf.lo + B.eoff * 4, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+  } else {
+    if ((rc = make_map_2d_bf16_ld(&ma, A.buf.hi + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mb, B.buf.hi + B.eoff * 2, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+    mal = ma;
+    mbl = mb;
+  }
+  p.kc = (int)(A.inner / PR::GK);
   p.a_brows = A.brows;
   p.b_brows = B.brows;
   p.m_tiles = (p.M_valid + GM - 1) / GM;
@@ -412,13 +563,13 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   if (p.ob && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  const size_t smem = (size_t)GST * 2 * G_TILE_BYTES + (2 * GST + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  tn_gemm_kernel<<<grid, G_THREADS, smem, st>>>(ma, mb, p);
+  tn_gemm_kernel<X3><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }
@@ -433,111 +584,103 @@ int check_large(const psvi_mf_model* model) {
   return PSVI_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R) {
-  if (!model || model->n_layers != 2 || R <= 0) return 0;
-  Lws w;
-  carve_l(model->mc_samples, R, model->dims[0], model->dims[1], nullptr, w);
-  return w.total + 1024;
-}
-
-int psvi_fnl_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+template <int X3>
+int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
                   const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
-                  void* workspace, void* stream_) {
-  PSVI_REQUIRE(theta && x && y && workspace, PSVI_ERR_INVALID, "null pointer");
-  int rc = check_large(model);
-  if (rc) return rc;
-  PSVI_REQUIRE(R >= 1, PSVI_ERR_INVALID, "bad R");
-  PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
+                  void* workspace, cudaStream_t st) {
+  constexpr int CP = Prec<X3>::GK;      // classes padded to one K block (64 bf16 / 32 fp32)
+  constexpr size_t ES = Prec<X3>::ES;
   const int D = model->dims[0], H = model->dims[1], C = model->dims[2], S = model->mc_samples;
   const long long P = (long long)H * D + H + (long long)C * H + C;
   const long long o_b1 = (long long)H * D, o_w2 = o_b1 + H, o_b2 = o_w2 + (long long)C * H;
   const int Rp = ((R + 127) / 128) * 128;
-  cudaStream_t st = (cudaStream_t)stream_;
-  int dev = 0, sms = 0;
+  int dev = 0, sms = 0, rc;
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   Lws w;
-  carve_l(S, R, D, H, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023), w);
+  carve_l(S, R, D, H, X3, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023), w);
   const bool dual = thetad != nullptr;
   // ---- operands
-  fnl_prep_x_kernel<<<dim3((Rp + 31) / 32, (D + 31) / 32), dim3(32, 8), 0, st>>>(x, R, Rp, D, w.Xb, w.XT);
-  PSVI_CUDA_CHECK(cudaMemsetAsync(w.W2p, 0, (size_t)S * 128 * 2 * H * 2, st));
-  PSVI_CUDA_CHECK(cudaMemsetAsync(w.W2T, 0, (size_t)S * H * 128 * 2, st));
-  fnl_pack_w1_kernel<<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(theta, P, D, H, w.W1b, w.W1T2, 0);
-  fnl_pack_w2_kernel<<<dim3(8, S), 256, 0, st>>>(theta, P, D, H, C, w.W2p, 0, w.W2T, CP);
+  fnl_prep_x_kernel<X3><<<dim3((Rp + 31) / 32, (D + 31) / 32), dim3(32, 8), 0, st>>>(x, R, Rp, D, w.X.hi, w.X.lo, w.XT.hi, w.XT.lo);
+  for (int part = 0; part < (X3 ? 2 : 1); ++part) {
+    PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.W2p.lo : w.W2p.hi, 0, (size_t)S * 128 * 2 * H * ES, st));
+    PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.W2T.lo : w.W2T.hi, 0, (size_t)S * H * 2 * CP * ES, st));
+  }
+  fnl_pack_w1_kernel<X3><<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(theta, P, D, H, w.W1.hi, w.W1.lo, w.W1T2.hi, w.W1T2.lo, 0);
+  fnl_pack_w2_kernel<X3><<<dim3(8, S), 256, 0, st>>>(theta, P, D, H, C, w.W2p.hi, w.W2p.lo, 0, w.W2T.hi, w.W2T.lo, CP, 2 * CP);
   if (dual) {
-    fnl_pack_w1_kernel<<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(thetad, P, D, H, w.W1db, w.W1T2, H);
-    fnl_pack_w2_kernel<<<dim3(8, S), 256, 0, st>>>(thetad, P, D, H, C, w.W2p, H, w.W2T, 0);
+    fnl_pack_w1_kernel<X3><<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(thetad, P, D, H, w.W1d.hi, w.W1d.lo, w.W1T2.hi,
+                                                                         w.W1T2.lo, H);
+    fnl_pack_w2_kernel<X3><<<dim3(8, S), 256, 0, st>>>(thetad, P, D, H, C, w.W2p.hi, w.W2p.lo, H, w.W2T.hi, w.W2T.lo, 0, 2 * CP);
   }
   PSVI_CUDA_CHECK(cudaGetLastError());
-  const Operand opX{w.Xb, (uint64_t)D, (uint64_t)Rp, (uint64_t)D, 0};
-  const Operand opXT{w.XT, (uint64_t)Rp, (uint64_t)D, (uint64_t)Rp, 0};
-  const Operand opW1{w.W1b, (uint64_t)D, (uint64_t)S * H, (uint64_t)D, H};
-  const Operand opW1d{w.W1db, (uint64_t)D, (uint64_t)S * H, (uint64_t)D, H};
-  const uint64_t H2 = 2 * (uint64_t)H;
-  const Operand opH{w.hh + H, (uint64_t)H, (uint64_t)S * Rp, H2, Rp};            // h
-  const Operand opHH{w.hh, H2, (uint64_t)S * Rp, H2, Rp};                        // [hdot | h]
-  const Operand opW2{w.W2p, (uint64_t)H, (uint64_t)S * 128, H2, 128};            // W2 (rows >= C zero)
-  const Operand opW22{w.W2p, H2, (uint64_t)S * 128, H2, 128};                    // [W2 | W2dot]
-  const Operand opA0{w.AA, (uint64_t)CP, (uint64_t)S * Rp, 128, Rp};             // first K block of AA
-  const Operand opAA{w.AA, 128, (uint64_t)S * Rp, 128, Rp};                      // [A_od | A_o]
-  const Operand opW2T1{w.W2T + CP, (uint64_t)CP, (uint64_t)S * H, 128, H};       // W2^T (padded to 64 classes)
-  const Operand opW2TT{w.W2T, 128, (uint64_t)S * H, 128, H};                     // [W2dot^T | W2^T]
-  const Operand opA{w.aa, (uint64_t)H, (uint64_t)S * Rp, H2, Rp};                // abar / A_a
-  const Operand opAAh{w.aa, H2, (uint64_t)S * Rp, H2, Rp};                       // [A_a | A_adot]
-  const Operand opW1T{w.W1T2, (uint64_t)H, (uint64_t)S * D, H2, D};              // W1^T
-  const Operand opW1TT{w.W1T2, H2, (uint64_t)S * D, H2, D};                      // [W1^T | W1dot^T]
-  const Operand opAT{w.aT, (uint64_t)Rp, (uint64_t)S * H, (uint64_t)Rp, H};
-  const Operand opADT{w.adT, (uint64_t)Rp, (uint64_t)S * H, (uint64_t)Rp, H};
+  const uint64_t H2 = 2 * (uint64_t)H, uH = (uint64_t)H, uD = (uint64_t)D, uRp = (uint64_t)Rp, uS = (uint64_t)S;
+  const Operand opX{w.X, 0, uD, uRp, uD, 0};
+  const Operand opXT{w.XT, 0, uRp, uD, uRp, 0};
+  const Operand opW1{w.W1, 0, uD, uS * H, uD, H};
+  const Operand opW1d{w.W1d, 0, uD, uS * H, uD, H};
+  const Operand opH{w.hh, uH, uH, uS * Rp, H2, Rp};                   // h
+  const Operand opHH{w.hh, 0, H2, uS * Rp, H2, Rp};                   // [hdot | h]
+  const Operand opW2{w.W2p, 0, uH, uS * 128, H2, 128};                // W2 (rows >= C zero)
+  const Operand opW22{w.W2p, 0, H2, uS * 128, H2, 128};               // [W2 | W2dot]
+  const Operand opA0{w.AA, 0, (uint64_t)CP, uS * Rp, 2 * (uint64_t)CP, Rp};          // first K block of AA
+  const Operand opAA{w.AA, 0, 2 * (uint64_t)CP, uS * Rp, 2 * (uint64_t)CP, Rp};      // [A_od | A_o]
+  const Operand opW2T1{w.W2T, (uint64_t)CP, (uint64_t)CP, uS * H, 2 * (uint64_t)CP, H};   // W2^T (classes padded to one K block)
+  const Operand opW2TT{w.W2T, 0, 2 * (uint64_t)CP, uS * H, 2 * (uint64_t)CP, H};          // [W2dot^T | W2^T]
+  const Operand opA{w.aa, 0, uH, uS * Rp, H2, Rp};                    // abar / A_a
+  const Operand opAAh{w.aa, 0, H2, uS * Rp, H2, Rp};                  // [A_a | A_adot]
+  const Operand opW1T{w.W1T2, 0, uH, uS * D, H2, D};                  // W1^T
+  const Operand opW1TT{w.W1T2, 0, H2, uS * D, H2, D};                 // [W1^T | W1dot^T]
+  const Operand opAT{w.aT, 0, uRp, uS * H, uRp, H};
+  const Operand opADT{w.adT, 0, uRp, uS * H, uRp, H};
   GemmP z;
   memset(&z, 0, sizeof(z));
   z.batch = S;
   const long long hh_bs = (long long)Rp * 2 * H;
+  auto at = [&](const Buf& b, size_t eoff, bool lo) -> void* { return (lo ? b.lo : b.hi) ? (lo ? b.lo : b.hi) + eoff * ES : nullptr; };
+  auto set_mask_h = [&](GemmP& p) { p.mask = at(w.hh, H, false); p.mask_bs = hh_bs; p.mask_ld = 2 * H; };
+  auto set_ob = [&](GemmP& p, const Buf& b, size_t eoff) {
+    p.ob = at(b, eoff, false); p.ob_lo = at(b, eoff, true); p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp;
+  };
+  auto set_obt = [&](GemmP& p, const Buf& b) {
+    p.obt = b.hi; p.obt_lo = b.lo; p.obt_bs = (long long)H * Rp; p.obt_ld = Rp;
+  };
   // ---- primal forward: h = relu(X W1^T + b1);  o = h W2^T
   {
     GemmP p = z;
     p.M_valid = R; p.N_valid = H; p.bias = theta + o_b1; p.bias_bs = P; p.relu = 1;
-    p.ob = w.hh + H; p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp;
-    rc = launch_gemm(opX, opW1, p, sms, st);
-    if (rc) return rc;
+    set_ob(p, w.hh, H);
+    if ((rc = launch_gemm<X3>(opX, opW1, p, sms, st))) return rc;
     p = z;
     p.M_valid = R; p.N_valid = CW; p.of = w.o; p.of_bs = (long long)Rp * CW; p.of_ld = CW;
-    rc = launch_gemm(opH, opW2, p, sms, st);
-    if (rc) return rc;
+    if ((rc = launch_gemm<X3>(opH, opW2, p, sms, st))) return rc;
   }
   const int hb = (S * Rp + 127) / 128;
   if (!tbar) {
-    fnl_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, nullptr, S, R, Rp, C, 0, nll, logits, nullptr,
-                                       nullptr, nullptr, nullptr);
+    fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, nullptr, S, R, Rp, C, 0, nll, logits, nullptr,
+                                           nullptr, nullptr, nullptr, nullptr);
     PSVI_CUDA_CHECK(cudaGetLastError());
     return PSVI_OK;
   }
   const dim3 gcol(H / 128, S);
   if (!dual) {
     // ---- gradient pass
-    fnl_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, cw, S, R, Rp, C, 1, nll, logits, w.go, nullptr,
-                                       w.AA, nullptr);
+    fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, cw, S, R, Rp, C, 1, nll, logits, w.go, nullptr,
+                                           w.AA.hi, w.AA.lo, nullptr);
     GemmP p = z;      // abar = (obar W2) * (h > 0), also transposed
-    p.M_valid = R; p.N_valid = H; p.mask = w.hh + H; p.mask_bs = hh_bs; p.mask_ld = 2 * H;
-    p.ob = w.aa; p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp; p.obt = w.aT; p.obt_bs = (long long)H * Rp; p.obt_ld = Rp;
-    rc = launch_gemm(opA0, opW2T1, p, sms, st);
-    if (rc) return rc;
+    p.M_valid = R; p.N_valid = H;
+    set_mask_h(p); set_ob(p, w.aa, 0); set_obt(p, w.aT);
+    if ((rc = launch_gemm<X3>(opA0, opW2T1, p, sms, st))) return rc;
     p = z;            // W1bar = abar^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
-    rc = launch_gemm(opAT, opXT, p, sms, st);
-    if (rc) return rc;
-    fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.aa, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);
-    fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.hh + H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);
+    if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
+    fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, 0, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);
+    fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);
     fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
     if (xbar) {
       p = z;          // xbar = abar W1
       p.M_valid = R; p.N_valid = D; p.of = xbar; p.of_bs = (long long)R * D; p.of_ld = D;
-      rc = launch_gemm(opA, opW1T, p, sms, st);
-      if (rc) return rc;
+      if ((rc = launch_gemm<X3>(opA, opW1T, p, sms, st))) return rc;
     }
     PSVI_CUDA_CHECK(cudaGetLastError());
     return PSVI_OK;
@@ -545,49 +688,68 @@ int psvi_fnl_pass(const psvi_mf_model* model, const float* theta, const float* t
   // ---- dual pass: tangent forward
   {
     GemmP p = z;      // hdot = (X W1dot^T + b1dot) * (h > 0)
-    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P; p.mask = w.hh + H; p.mask_bs = hh_bs; p.mask_ld = 2 * H;
-    p.ob = w.hh; p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp;
-    rc = launch_gemm(opX, opW1d, p, sms, st);
-    if (rc) return rc;
+    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P;
+    set_mask_h(p); set_ob(p, w.hh, 0);
+    if ((rc = launch_gemm<X3>(opX, opW1d, p, sms, st))) return rc;
     p = z;            // odot = hdot W2^T + h W2dot^T
     p.M_valid = R; p.N_valid = CW; p.of = w.od; p.of_bs = (long long)Rp * CW; p.of_ld = CW;
-    rc = launch_gemm(opHH, opW22, p, sms, st);
-    if (rc) return rc;
+    if ((rc = launch_gemm<X3>(opHH, opW22, p, sms, st))) return rc;
   }
-  fnl_head_kernel<<<hb, 128, 0, st>>>(w.o, w.od, theta + o_b2, thetad + o_b2, P, y, cw, S, R, Rp, C, 2, nll, logits, w.go, w.god,
-                                     w.AA, acbar);
+  fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, w.od, theta + o_b2, thetad + o_b2, P, y, cw, S, R, Rp, C, 2, nll, logits, w.go, w.god,
+                                         w.AA.hi, w.AA.lo, acbar);
   {
     GemmP p = z;      // A_a = (A_od W2dot + A_o W2) * (h > 0)
-    p.M_valid = R; p.N_valid = H; p.mask = w.hh + H; p.mask_bs = hh_bs; p.mask_ld = 2 * H;
-    p.ob = w.aa; p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp; p.obt = w.aT; p.obt_bs = (long long)H * Rp; p.obt_ld = Rp;
-    rc = launch_gemm(opAA, opW2TT, p, sms, st);
-    if (rc) return rc;
-    p.ob = w.aa + H; p.obt = w.adT;      // A_adot = (A_od W2) * (h > 0)
-    rc = launch_gemm(opA0, opW2T1, p, sms, st);
-    if (rc) return rc;
+    p.M_valid = R; p.N_valid = H;
+    set_mask_h(p); set_ob(p, w.aa, 0); set_obt(p, w.aT);
+    if ((rc = launch_gemm<X3>(opAA, opW2TT, p, sms, st))) return rc;
+    set_ob(p, w.aa, H); set_obt(p, w.adT);      // A_adot = (A_od W2) * (h > 0)
+    if ((rc = launch_gemm<X3>(opA0, opW2T1, p, sms, st))) return rc;
     p = z;            // A_W1 = A_a^T X;  A_W1dot = A_adot^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
-    rc = launch_gemm(opAT, opXT, p, sms, st);
-    if (rc) return rc;
+    if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
     p.of = tdbar;
-    rc = launch_gemm(opADT, opXT, p, sms, st);
-    if (rc) return rc;
+    if ((rc = launch_gemm<X3>(opADT, opXT, p, sms, st))) return rc;
     if (xbar) {
       p = z;          // A_x = A_a W1 + A_adot W1dot
       p.M_valid = R; p.N_valid = D; p.of = xbar; p.of_bs = (long long)R * D; p.of_ld = D;
-      rc = launch_gemm(opAAh, opW1TT, p, sms, st);
-      if (rc) return rc;
+      if ((rc = launch_gemm<X3>(opAAh, opW1TT, p, sms, st))) return rc;
     }
   }
-  fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.aa, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);          // A_b1
-  fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.aa + H, hh_bs, 2 * H, nullptr, R, H, 1, tdbar + o_b1, P, 0);     // A_b1dot
-  fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.hh + H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);         // A_o^T h
-  fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.hh, hh_bs, 2 * H, w.god, R, H, C, tbar + o_w2, P, 1);            // + A_od^T hdot
-  fnl_colreduce_kernel<<<gcol, 128, 0, st>>>(w.hh + H, hh_bs, 2 * H, w.god, R, H, C, tdbar + o_w2, P, 0);       // A_od^T h
+  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, 0, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);     // A_b1
+  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, H, hh_bs, 2 * H, nullptr, R, H, 1, tdbar + o_b1, P, 0);    // A_b1dot
+  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);        // A_o^T h
+  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, 0, hh_bs, 2 * H, w.god, R, H, C, tbar + o_w2, P, 1);       // + A_od^T hdot
+  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.god, R, H, C, tdbar + o_w2, P, 0);      // A_od^T h
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.god, R, C, tdbar + o_b2, P);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R, int32_t precision) {
+  if (!model || model->n_layers != 2 || R <= 0) return 0;
+  Lws w;
+  carve_l(model->mc_samples, R, model->dims[0], model->dims[1], precision ? 1 : 0, nullptr, w);
+  return w.total + 1024;
+}
+
+int psvi_fnl_pass(const psvi_mf_model* model, int32_t precision, const float* theta, const float* thetad, const float* x,
+                  const int32_t* y, const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                  float* logits, void* workspace, void* stream_) {
+  PSVI_REQUIRE(theta && x && y && workspace, PSVI_ERR_INVALID, "null pointer");
+  int rc = check_large(model);
+  if (rc) return rc;
+  PSVI_REQUIRE(R >= 1, PSVI_ERR_INVALID, "bad R");
+  PSVI_REQUIRE(precision == 0 || precision == 1, PSVI_ERR_INVALID, "precision must be 0 (bf16) or 1 (tf32x3)");
+  PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (precision)
+    return fnl_pass_impl<1>(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, workspace, st);
+  return fnl_pass_impl<0>(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, workspace, st);
 }
 
 }  // extern "C"

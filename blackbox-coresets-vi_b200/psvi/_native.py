@@ -106,8 +106,8 @@ _SIGS = {
                                  C.c_void_p, C.c_int32, C.c_void_p]),
     "psvi_fc_outer": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
-    "psvi_fnl_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32]),
-    "psvi_fnl_pass": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+    "psvi_fnl_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32, C.c_int32]),
+    "psvi_fnl_pass": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_lenet_num_theta": (C.c_int64, []),
     "psvi_lenet_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -413,14 +413,17 @@ def logits_predict(logits, log_weights, mode, yt, out):
 _fnl_ws = {}
 
 
-def fnl_pass(model, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, logits=None):
-    """Large-regime fn pass (batched tcgen05 GEMMs) on sampled weights theta [S][P]; same contract as net_pass."""
+PREC_BF16, PREC_TF32X3 = 0, 1
+
+
+def fnl_pass(model, precision, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, logits=None):
+    """Large-regime fn pass (batched tcgen05 GEMMs; bf16 or tf32x3 arithmetic) on sampled weights theta [S][P]."""
     R = x.shape[0]
-    n = (int(lib().psvi_fnl_workspace_bytes(C.byref(model), R)) + 3) // 4
+    n = (int(lib().psvi_fnl_workspace_bytes(C.byref(model), R, precision)) + 3) // 4
     ws = _fnl_ws.get(theta.device)
     if ws is None or ws.numel() < n:
         ws = torch.empty(n, device=theta.device, dtype=torch.float32)
         _fnl_ws[theta.device] = ws
     _count(8 if tbar is None else (14 if thetad is None else 25))
-    _check(lib().psvi_fnl_pass(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll), _p(tbar),
-                               _p(tdbar), _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))
+    _check(lib().psvi_fnl_pass(C.byref(model), precision, _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll),
+                               _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))

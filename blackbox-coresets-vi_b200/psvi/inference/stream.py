@@ -206,21 +206,23 @@ class MlpNet:
 
 
 class FnLargeNet:
-    """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu)."""
+    """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu).
+    `precision`: _native.PREC_TF32X3 (default; fp32-class accuracy, needed by the unrolled hypergradient) or PREC_BF16 (6x
+    the tensor rate, ~1e-2 relative error per pass: values, first-order training, prediction)."""
 
-    def __init__(self, dims, S):
-        self.desc, self.S, self.C = _native.make_model(dims, S), S, dims[-1]
+    def __init__(self, dims, S, precision=_native.PREC_TF32X3):
+        self.desc, self.S, self.C, self.precision = _native.make_model(dims, S), S, dims[-1], precision
 
     @staticmethod
     def fits(dims, S):
         return len(dims) == 3 and dims[0] % 64 == 0 and dims[1] % 128 == 0 and dims[2] <= 16 and S <= 64
 
     def pass_(self, theta, thetad, x, y, cw, **out):
-        _native.fnl_pass(self.desc, theta, thetad, x, y, cw, **out)
+        _native.fnl_pass(self.desc, self.precision, theta, thetad, x, y, cw, **out)
 
     def predict(self, theta, lw, mode, xt, yt, out):
         logits = torch.empty(self.S, xt.shape[0], self.C, device=xt.device)
-        _native.fnl_pass(self.desc, theta, None, xt, yt, None, logits=logits)
+        _native.fnl_pass(self.desc, self.precision, theta, None, xt, yt, None, logits=logits)
         _native.logits_predict(logits, lw, mode, yt, out)
 
 

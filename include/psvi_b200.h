@@ -250,13 +250,16 @@ int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const fl
 /* ---- large-regime per-sample network pass for `fn` with ONE hidden layer (BASELINE config 5: D=256, H=1024, S=64,
  * M=1000): same contract as psvi_net_pass (forward / gradient / dual Hessian-vector pass on sampled weights theta [S][P],
  * reference neural_net.py:155-179 + autograd), for models whose per-sample weights fit no CTA.  Every matrix product is a
- * batched bf16 TMA + tcgen05 GEMM with fp32 accumulation (csrc/psvi_fn_large.cu); the hidden activations are kept in bf16.
+ * batched TMA + tcgen05 GEMM with fp32 accumulation (csrc/psvi_fn_large.cu).  precision 0: bf16 operands / activations
+ * (full tensor rate, ~1e-2 relative error: values, first-order training, prediction); precision 1: "tf32x3" -- every operand
+ * is an fp32 (hi, lo) pair of TF32 numbers and every K step issues three kind::tf32 MMAs (fp32-class accuracy, which the
+ * unrolled hypergradient of nested_step needs: its reverse sweep through Adam divides by |g_i|).
  *   needs n_layers == 2, D a multiple of 64, H a multiple of 128, C <= 16, S <= 64;  x [R][D] fp32, y [R] int32,
  *   cw [S][R] (nullable -> 1);  outputs as psvi_net_pass (logits [S][R][C]);  workspace: psvi_fnl_workspace_bytes(). */
-size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R);
-int psvi_fnl_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
-                  const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
-                  void* workspace, void* stream);
+size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R, int32_t precision);
+int psvi_fnl_pass(const psvi_mf_model* model, int32_t precision, const float* theta, const float* thetad, const float* x,
+                  const int32_t* y, const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                  float* logits, void* workspace, void* stream);
 
 /* ---- convolutional family (lenet): per-sample network pass on externally supplied weights, same contract as
  * psvi_net_pass.  Replaces VIConv2d.forward (grouped conv over samples), BatchMaxPool2d, nn.Flatten and the three VILinear

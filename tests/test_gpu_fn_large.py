@@ -38,7 +38,53 @@ def make_case(D, H, C, S, R, seed):
 
 
 @pytest.mark.parametrize("D,H,C,S,R", [(64, 128, 3, 2, 100), (128, 256, 10, 3, 300), (256, 384, 4, 2, 129), (192, 128, 16, 2, 260)])
-def test_fnl_pass_matches_oracle(D, H, C, S, R):
+def test_fnl_pass_tf32x3_matches_oracle(D, H, C, S, R):
+    """precision 1 (three kind::tf32 MMAs on (hi, lo) operand pairs): fp32-class accuracy -- rel-L2 2e-5 on every output
+    against the fp64 oracle with un-rounded operands."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    rng = np.random.default_rng(D + H + C + S + R)
+    dims = [D, H, C]
+    theta = np.concatenate([rng.standard_normal((S, H * D)) / np.sqrt(D), 0.1 * rng.standard_normal((S, H)),
+                            rng.standard_normal((S, C * H)) / np.sqrt(H), 0.1 * rng.standard_normal((S, C))], 1).astype(np.float32)
+    thetad = (rng.standard_normal(theta.shape) * np.abs(theta).mean() * 0.5).astype(np.float32)
+    X = rng.standard_normal((R, D)).astype(np.float32)
+    y = rng.integers(0, C, R)
+    cw = rng.uniform(0.5, 1.5, (S, R)).astype(np.float32)
+    model = nat.make_model(dims, S)
+    P = theta.shape[1]
+    th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
+    t64, td64, X64, cw64 = theta.astype(np.float64), thetad.astype(np.float64), X.astype(np.float64), cw.astype(np.float64)
+    nll, logits = zeros(S, R), zeros(S, R, C)
+    nat.fnl_pass(model, nat.PREC_TF32X3, th, None, x_, y_, None, nll=nll, logits=logits)
+    o, cache = po.mlp_forward(t64, X64, dims)
+    ref_nll, p = po.nll_rows(o, y)
+    assert rel_l2(logits.cpu().numpy(), o) < 2e-5
+    np.testing.assert_allclose(nll.cpu().numpy(), ref_nll, rtol=1e-4, atol=2e-5)
+    q = p.copy()
+    q[:, np.arange(R), y] -= 1.0
+    At, Ax = po.mlp_backward(t64, cache, dims, cw64[:, :, None] * q)
+    tbar, xbar = zeros(S, P), zeros(S, R, D)
+    nat.fnl_pass(model, nat.PREC_TF32X3, th, None, x_, y_, cw_, nll=nll, tbar=tbar, xbar=xbar)
+    blocks = ((0, H * D), (H * D, H * D + H), (H * D + H, H * D + H + C * H), (H * D + H + C * H, P))
+    for lo, hi in blocks:
+        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 2e-5
+    assert rel_l2(xbar.cpu().numpy(), Ax) < 2e-5
+    o, od, c2 = po.mlp_dual_forward(t64, td64, X64, dims)
+    c = cw64[:, :, None]
+    At, Atd, Ax = po.mlp_dual_backward(t64, td64, c2, dims, c * p * (od - (p * od).sum(-1, keepdims=True)), c * q)
+    tbar, tdbar, xbar, ac = zeros(S, P), zeros(S, P), zeros(S, R, D), zeros(S, R)
+    nat.fnl_pass(model, nat.PREC_TF32X3, th, thd, x_, y_, cw_, tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
+    torch.cuda.synchronize()
+    for lo, hi in blocks:
+        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 5e-5
+        assert rel_l2(tdbar.cpu().numpy()[:, lo:hi], Atd[:, lo:hi]) < 2e-5
+    assert rel_l2(xbar.cpu().numpy(), Ax) < 5e-5
+    assert rel_l2(ac.cpu().numpy(), (q * od).sum(-1)) < 2e-5
+
+
+@pytest.mark.parametrize("D,H,C,S,R", [(64, 128, 3, 2, 100), (128, 256, 10, 3, 300), (256, 384, 4, 2, 129), (192, 128, 16, 2, 260)])
+def test_fnl_pass_bf16_matches_oracle(D, H, C, S, R):
     from psvi import _native as nat
     nat.require_cuda()
     dims, theta, thetad, X, y, cw = make_case(D, H, C, S, R, D + H + C + S + R)
@@ -47,7 +93,7 @@ def test_fnl_pass_matches_oracle(D, H, C, S, R):
     th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
     # forward
     nll, logits = zeros(S, R), zeros(S, R, C)
-    nat.fnl_pass(model, th, None, x_, y_, None, nll=nll, logits=logits)
+    nat.fnl_pass(model, nat.PREC_BF16, th, None, x_, y_, None, nll=nll, logits=logits)
     # oracle with the hidden layer rounded to bf16 like the kernel does
     W1 = theta[:, :H * D].reshape(S, H, D)
     b1 = theta[:, H * D:H * D + H]
@@ -64,7 +110,7 @@ def test_fnl_pass_matches_oracle(D, H, C, S, R):
     q[:, np.arange(R), y] -= 1.0
     At, Ax = po.mlp_backward(theta, cache, dims, cw[:, :, None] * q)
     tbar, xbar = zeros(S, P), zeros(S, R, D)
-    nat.fnl_pass(model, th, None, x_, y_, cw_, nll=nll, tbar=tbar, xbar=xbar)
+    nat.fnl_pass(model, nat.PREC_BF16, th, None, x_, y_, cw_, nll=nll, tbar=tbar, xbar=xbar)
     assert rel_l2(tbar.cpu().numpy(), At) < 1.5e-2 and cos(tbar.cpu().numpy(), At) > 0.9999
     assert rel_l2(xbar.cpu().numpy(), Ax) < 1.5e-2
     # per-block check (the small blocks must not hide behind the large first-layer block)
@@ -75,7 +121,7 @@ def test_fnl_pass_matches_oracle(D, H, C, S, R):
     c = cw[:, :, None]
     At, Atd, Ax = po.mlp_dual_backward(theta, thetad, c2, dims, c * p * (od - (p * od).sum(-1, keepdims=True)), c * q)
     tbar, tdbar, xbar, ac = zeros(S, P), zeros(S, P), zeros(S, R, D), zeros(S, R)
-    nat.fnl_pass(model, th, thd, x_, y_, cw_, tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
+    nat.fnl_pass(model, nat.PREC_BF16, th, thd, x_, y_, cw_, tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
     torch.cuda.synchronize()
     assert rel_l2(tbar.cpu().numpy(), At) < 1.5e-2 and cos(tbar.cpu().numpy(), At) > 0.9999
     assert rel_l2(tdbar.cpu().numpy(), Atd) < 1.5e-2 and cos(tdbar.cpu().numpy(), Atd) > 0.9999
@@ -89,7 +135,7 @@ def test_fnl_pass_matches_oracle(D, H, C, S, R):
 def test_large_fn_nested_step_and_evaluate_through_psvi_class():
     """PSVILearnV on a model in the large regime (P = 50 691 per sample): the class picks the batched-GEMM tensor path
     (FnLargeNet) for inner_elbo / psvi_elbo / nested_step and the fused tcgen05 forward for evaluate; checked against the
-    fp64 oracle.  Tolerance: bf16 operands and intermediates -> values rtol 2e-3, hypergradients rel-L2 5e-2, cosine > 0.999."""
+    fp64 oracle.  The bilevel step runs in tf32x3 arithmetic (fp32-class accuracy): hypergradients rel-L2 5e-3."""
     from oracle.ref_import import NoiseFeeder
     from psvi.experiments.experiments_utils import SynthDataset, make_synthetic_rows
     from psvi.inference.psvi_classes import ExternalNoise, PSVILearnV
@@ -117,12 +163,12 @@ def test_large_fn_nested_step_and_evaluate_through_psvi_class():
     e64 = [e.astype(np.float64) for e in eps]
     r = po.nested_step(mu, rho, np.stack(e64[:T]), e64[T], u0, z, v0, X[:B].numpy().astype(np.float64), Y[:B].numpy(), 500.0,
                        dims, 1e-3, vmode=1)
-    assert abs(loss.item() - r["loss"]) <= 2e-3 * abs(r["loss"])
+    assert abs(loss.item() - r["loss"]) <= 1e-4 * abs(r["loss"])
     gu, gv = obj.u.grad.cpu().numpy(), obj.v.grad.cpu().numpy()
-    assert rel_l2(gu, r["u_grad"]) < 5e-2 and cos(gu, r["u_grad"]) > 0.999
-    assert rel_l2(gv, r["v_grad"]) < 5e-2 and cos(gv, r["v_grad"]) > 0.999
+    assert rel_l2(gu, r["u_grad"]) < 5e-3 and cos(gu, r["u_grad"]) > 0.9999
+    assert rel_l2(gv, r["v_grad"]) < 5e-3 and cos(gv, r["v_grad"]) > 0.9999
     muT, rhoT = [t.cpu().numpy() for t in obj.model.flat()]
-    assert rel_l2(muT, r["mu_T"]) < 1e-3 and rel_l2(rhoT, r["rho_T"]) < 1e-3
+    assert rel_l2(muT, r["mu_T"]) < 1e-5 and rel_l2(rhoT, r["rho_T"]) < 1e-5
     # evaluate: fused tcgen05 forward (in-kernel Philox noise) -- sanity of the metrics on a learnable synthetic problem
     obj.noise_source = None
     acc, nll, went, ness, vent = obj.evaluate()
