@@ -426,21 +426,24 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
   if (acbar) acbar[oidx] = qd;
 }
 
-// out[s * P + c * H + h] (+)= sum_r W[s][r][c] * Y[s][r][h]   (W == NULL: C = 1, weight 1 -> column sums)
+// part[z][s][c][h] = sum over the z-th row chunk of W[s][r][c] * Y[s][r][h]   (W == NULL: C = 1, weight 1 -> column sums);
+// fnl_colreduce_finish_kernel adds the chunks in fixed order: out[s * P + c * H + h] (+)= sum_z part[z][s][c][h]
+constexpr int RSPLIT = 8;
 template <int X3>
 __global__ void __launch_bounds__(128)
 fnl_colreduce_kernel(const void* Yh, const void* Yl, long long y_off, long long y_bs, int y_ld, const float* __restrict__ W, int R,
-                     int H, int C, float* __restrict__ out, long long P, int accumulate) {
-  const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y;
+                     int H, int C, float* __restrict__ part) {
+  const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, zc = blockIdx.z;
   if (h >= H) return;
+  const int rpc = (R + RSPLIT - 1) / RSPLIT, r0 = zc * rpc, r1 = min(R, r0 + rpc);
   float acc[CW];
 #pragma unroll
   for (int c = 0; c < CW; ++c) acc[c] = 0.f;
   const size_t y0 = (size_t)(y_off + (long long)s * y_bs + h);
   if (W) {
     const float4* wp = reinterpret_cast<const float4*>(W + (size_t)s * R * CW);
-#pragma unroll 2
-    for (int r = 0; r < R; ++r) {
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
       const float yv = get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
       const float4 w0 = __ldg(wp + r * 4), w1 = __ldg(wp + r * 4 + 1), w2 = __ldg(wp + r * 4 + 2), w3 = __ldg(wp + r * 4 + 3);
       acc[0] = fmaf(w0.x, yv, acc[0]); acc[1] = fmaf(w0.y, yv, acc[1]); acc[2] = fmaf(w0.z, yv, acc[2]); acc[3] = fmaf(w0.w, yv, acc[3]);
@@ -449,13 +452,20 @@ fnl_colreduce_kernel(const void* Yh, const void* Yl, long long y_off, long long 
       acc[12] = fmaf(w3.x, yv, acc[12]); acc[13] = fmaf(w3.y, yv, acc[13]); acc[14] = fmaf(w3.z, yv, acc[14]); acc[15] = fmaf(w3.w, yv, acc[15]);
     }
   } else {
-#pragma unroll 4
-    for (int r = 0; r < R; ++r) acc[0] += get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) acc[0] += get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
   }
-  for (int c = 0; c < C; ++c) {
-    float* d = out + (long long)s * P + (long long)c * H + h;
-    *d = accumulate ? *d + acc[c] : acc[c];
-  }
+  for (int c = 0; c < C; ++c) part[(((size_t)zc * gridDim.y + s) * C + c) * H + h] = acc[c];
+}
+__global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int S, int H, int C, float* __restrict__ out, long long P,
+                                            int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;   // i = c * H + h
+  if (i >= C * H) return;
+  float t = 0.f;
+#pragma unroll
+  for (int zc = 0; zc < RSPLIT; ++zc) t += part[((size_t)zc * S + s) * C * H + i];
+  float* d = out + (long long)s * P + i;
+  *d = accumulate ? *d + t : t;
 }
 
 // out[s * P + c] = sum_r W[s][r][c]
@@ -480,7 +490,7 @@ struct Buf {
 };
 struct Lws {
   Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA;
-  float *o, *od, *go, *god;
+  float *o, *od, *go, *god, *cpart;
   size_t total;
 };
 
@@ -505,6 +515,7 @@ void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
   w.od = (float*)take((size_t)S * Rp * CW * 4);
   w.go = (float*)take((size_t)S * R * CW * 4);
   w.god = (float*)take((size_t)S * R * CW * 4);
+  w.cpart = (float*)take((size_t)RSPLIT * S * CW * H * 4);
   w.total = off;
 }
 
@@ -662,7 +673,10 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     PSVI_CUDA_CHECK(cudaGetLastError());
     return PSVI_OK;
   }
-  const dim3 gcol(H / 128, S);
+  auto colreduce = [&](const Buf& Y, long long y_off, const float* W, int Cc, float* out, int accumulate) {
+    fnl_colreduce_kernel<X3><<<dim3(H / 128, S, RSPLIT), 128, 0, st>>>(Y.hi, Y.lo, y_off, hh_bs, 2 * H, W, R, H, Cc, w.cpart);
+    fnl_colreduce_finish_kernel<<<dim3((Cc * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, Cc, out, P, accumulate);
+  };
   if (!dual) {
     // ---- gradient pass
     fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, cw, S, R, Rp, C, 1, nll, logits, w.go, nullptr,
@@ -674,8 +688,8 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     p = z;            // W1bar = abar^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
     if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
-    fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, 0, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);
-    fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);
+    colreduce(w.aa, 0, nullptr, 1, tbar + o_b1, 0);
+    colreduce(w.hh, H, w.go, C, tbar + o_w2, 0);
     fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
     if (xbar) {
       p = z;          // xbar = abar W1
@@ -715,11 +729,11 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
       if ((rc = launch_gemm<X3>(opAAh, opW1TT, p, sms, st))) return rc;
     }
   }
-  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, 0, hh_bs, 2 * H, nullptr, R, H, 1, tbar + o_b1, P, 0);     // A_b1
-  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.aa.hi, w.aa.lo, H, hh_bs, 2 * H, nullptr, R, H, 1, tdbar + o_b1, P, 0);    // A_b1dot
-  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.go, R, H, C, tbar + o_w2, P, 0);        // A_o^T h
-  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, 0, hh_bs, 2 * H, w.god, R, H, C, tbar + o_w2, P, 1);       // + A_od^T hdot
-  fnl_colreduce_kernel<X3><<<gcol, 128, 0, st>>>(w.hh.hi, w.hh.lo, H, hh_bs, 2 * H, w.god, R, H, C, tdbar + o_w2, P, 0);      // A_od^T h
+  colreduce(w.aa, 0, nullptr, 1, tbar + o_b1, 0);      // A_b1
+  colreduce(w.aa, H, nullptr, 1, tdbar + o_b1, 0);     // A_b1dot
+  colreduce(w.hh, H, w.go, C, tbar + o_w2, 0);         // A_o^T h
+  colreduce(w.hh, 0, w.god, C, tbar + o_w2, 1);        // + A_od^T hdot
+  colreduce(w.hh, H, w.god, C, tdbar + o_w2, 0);       // A_od^T h
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.god, R, C, tdbar + o_b2, P);
   PSVI_CUDA_CHECK(cudaGetLastError());

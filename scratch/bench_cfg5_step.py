@@ -32,3 +32,25 @@ print(f"cfg5 nested_step T={T} S={S}: {ms:.1f} ms/outer step, {fl/ms/1e9:.1f} TF
       f"mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 t0 = time.time(); acc, nll, *_ = obj.evaluate(); torch.cuda.synchronize()
 print(f"evaluate 4000 rows: {1e3*(time.time()-t0):.1f} ms acc {acc.item():.3f} nll {nll.item():.3f}")
+# ---- phase timing
+import collections
+eng = obj._stream(obj.model)
+acc_t = collections.defaultdict(float)
+def wrap(name):
+    f = getattr(eng, name)
+    def g(*a, **k):
+        torch.cuda.synchronize(); t0 = time.time()
+        r = f(*a, **k)
+        torch.cuda.synchronize(); acc_t[name] += time.time() - t0
+        return r
+    setattr(eng, name, g)
+for nme in ("inner_grad", "outer_grad", "hvp"):
+    wrap(nme)
+orig_noise = obj._noise_tensor
+def nt(*a, **k):
+    torch.cuda.synchronize(); t0 = time.time(); r = orig_noise(*a, **k); torch.cuda.synchronize(); acc_t["noise"] += time.time() - t0; return r
+obj._noise_tensor = nt
+torch.cuda.synchronize(); t0 = time.time()
+obj.nested_step(xb, yb)
+torch.cuda.synchronize(); tot = time.time() - t0
+print("phases (ms):", {k: round(1e3 * v, 1) for k, v in acc_t.items()}, "total", round(1e3 * tot, 1))
