@@ -329,17 +329,30 @@ class PSVI(object):
         return self._nested_step_stream(model, S, xbatch, ybatch)
 
     def _nested_step_stream(self, model, S, xbatch, ybatch):
-        """Same step through the streaming path (fn2 / medium-size models): per-sample network kernels + packed
-        full-covariance products, sequenced on the host (psvi/inference/stream.py).  Single GPU."""
-        if _dist_info()[2] > 1:
-            raise NotImplementedError("the streaming path is replicated, not sharded: run one chain per rank")
+        """Same step through the streaming path (fn2 / lenet / medium and large mean-field models): per-sample network kernels
+        sequenced on the host (psvi/inference/stream.py).  Under torch.distributed the data term is sharded over the ranks."""
+        dist, rank, world = _dist_info()
         eng = self._stream(model)
         T, lr = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"])
         u, _ = self._uv()
         xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
         yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        kappa, n_total, reduce_fn = 1.0, None, None
+        if world > 1:
+            # the data term shards over ranks (contiguous row ranges of the SAME global minibatch); one all-reduce of
+            # [loss | dL/dphi_T | direct dL/du | direct dL/da]; inner loop and reverse sweep replicated (same seeds)
+            n_total = xb.shape[0]
+            lo, hi = shard_bounds(n_total, rank, world)
+            xb, yb, kappa = xb[lo:hi].contiguous(), yb[lo:hi].contiguous(), 1.0 / world
+
+            def reduce_fn(loss, pbar, ubar, abar):
+                flat = torch.cat([loss.reshape(1), pbar.reshape(-1), ubar.reshape(-1), abar.reshape(-1)]).float()
+                dist.all_reduce(flat)
+                n1, n2 = pbar.numel(), ubar.numel()
+                return flat[0], flat[1:1 + n1], flat[1 + n1:1 + n1 + n2].reshape(ubar.shape), flat[1 + n1 + n2:]
         loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u, self._z32(),
-                                                 self._a(), xb, yb, float(self.N), T, lr, want_losses=self.register_elbos)
+                                                 self._a(), xb, yb, float(self.N), T, lr, want_losses=self.register_elbos,
+                                                 kappa=kappa, n_total=n_total, reduce_fn=reduce_fn)
         eng.fam.set_phi(phi_T)                 # copy-back of the fast weights (reference :596-599)
         if self.register_elbos:
             ilc = il.cpu()

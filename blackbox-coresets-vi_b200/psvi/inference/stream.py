@@ -257,16 +257,33 @@ class StreamEngine:
         val = (nll.double() @ a.double()).sum() + self.fam.kl(phi).double()
         return val, self.fam.grad(phi, eps, tbar, 1.0, 0.0)
 
+    ROW_CHUNK = 8192   # data rows per network pass when the minibatch is large (full-data term, sharded over ranks)
+
     def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None):
+        """psvi_elbo value and gradients.  `kappa` / `n_total` describe one rank's share when the data rows are sharded over
+        R ranks: L_r = sum_s w_s (d_s^r - kappa p_s) - kappa mean(lw), kappa = 1/R, d_s^r = (N / n_total) * sum over
+        this rank's rows; the shares (value and every gradient) add up to the unsharded objective because the importance
+        weights depend on the pseudo-data only.  Large minibatches are processed in chunks of ROW_CHUNK rows."""
         S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
         n_total = B if n_total is None else n_total
         eps = self.fam.fix_eps(eps)
         theta = self.fam.sample(phi, eps)
-        X, lab = torch.cat([u, xb]).contiguous(), torch.cat([z32, yb32]).contiguous()
-        nll = torch.empty(S, M + B, device=dev)
-        self.net.pass_(theta, None, X, lab, None, nll=nll)
-        nd = nll.double()
-        ps, ds = nd[:, :M] @ a.double(), (N / n_total) * nd[:, M:].sum(1)
+        if M + B <= self.ROW_CHUNK:
+            X, lab = torch.cat([u, xb]).contiguous(), torch.cat([z32, yb32]).contiguous()
+            nll = torch.empty(S, M + B, device=dev)
+            self.net.pass_(theta, None, X, lab, None, nll=nll)
+            nd = nll.double()
+            nll_u, ds_sum = nll[:, :M], nd[:, M:].sum(1)
+        else:
+            nll_u = torch.empty(S, M, device=dev)
+            self.net.pass_(theta, None, u, z32, None, nll=nll_u)
+            ds_sum = torch.zeros(S, device=dev, dtype=torch.float64)
+            for r0 in range(0, B, self.ROW_CHUNK):
+                xc, yc = xb[r0:r0 + self.ROW_CHUNK].contiguous(), yb32[r0:r0 + self.ROW_CHUNK].contiguous()
+                nc = torch.empty(S, xc.shape[0], device=dev)
+                self.net.pass_(theta, None, xc, yc, None, nll=nc)
+                ds_sum += nc.double().sum(1)
+        ps, ds = nll_u.double() @ a.double(), (N / n_total) * ds_sum
         lw = -ps + self.fam.nkl(phi, eps, theta)
         w = torch.softmax(lw, 0)
         e = ds - kappa * ps
@@ -274,12 +291,26 @@ class StreamEngine:
         loss = ebar - kappa * lw.mean()
         beta = w * (e - ebar) - kappa / S
         gp = -kappa * w - beta
-        cw = torch.cat([gp[:, None] * a.double()[None, :], (w * N / n_total)[:, None].expand(S, B)], 1).float().contiguous()
-        tbar, xbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, M + B, X.shape[1], device=dev)
-        self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
+        cw_u = (gp[:, None] * a.double()[None, :]).float()
+        wd = (w * N / n_total).float()
+        tbar = torch.empty(S, self.Pt, device=dev)
+        if M + B <= self.ROW_CHUNK:
+            cw = torch.cat([cw_u, wd[:, None].expand(S, B)], 1).contiguous()
+            xbar = torch.empty(S, M + B, X.shape[1], device=dev)
+            self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
+            xbar_u, nll_u = xbar[:, :M], nll[:, :M]
+        else:
+            xbar_u = torch.empty(S, M, u.shape[1], device=dev)
+            self.net.pass_(theta, None, u, z32, cw_u.contiguous(), nll=nll_u, tbar=tbar, xbar=xbar_u)
+            tb = torch.empty_like(tbar)
+            for r0 in range(0, B, self.ROW_CHUNK):
+                xc, yc = xb[r0:r0 + self.ROW_CHUNK].contiguous(), yb32[r0:r0 + self.ROW_CHUNK].contiguous()
+                nc = torch.empty(S, xc.shape[0], device=dev)
+                self.net.pass_(theta, None, xc, yc, wd[:, None].expand(S, xc.shape[0]).contiguous(), nll=nc, tbar=tb)
+                tbar += tb
         tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
         pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
-        return loss.float(), pbar, xbar[:, :M].sum(0), (gp.float() @ nll[:, :M]), ds.float()
+        return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
     def hvp(self, phi, eps, u, z32, a, phidot):
         S, M, dev = self.S, u.shape[0], u.device
@@ -291,8 +322,11 @@ class StreamEngine:
         return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
-    def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False):
-        """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None)."""
+    def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None, reduce_fn=None):
+        """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None).
+        Sharded data term: pass this rank's rows with kappa = 1/world, n_total = rows over all ranks and a `reduce_fn` that
+        all-reduces (loss, pbar, ubar, abar) -- the ONE exchange step of the bilevel step; the inner loop and
+        the reverse sweep are replicated (identical seeds => identical trajectories on every rank)."""
         eps_all = self.fam.fix_eps(eps_all)
         m, v = torch.zeros_like(phi), torch.zeros_like(phi)
         traj, losses = [], []
@@ -306,7 +340,9 @@ class StreamEngine:
             den = torch.sqrt(v + 1e-8) / sq2 + AEPS
             traj.append((phi, g, m, v))
             phi = phi - (lr / (1.0 - B1 ** (t + 1))) * (m / den)
-        loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N)
+        loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total)
+        if reduce_fn is not None:
+            loss, pbar, ubar, abar = reduce_fn(loss, pbar, ubar, abar)
         phi_T = phi
         mbar, vbar = torch.zeros_like(pbar), torch.zeros_like(pbar)
         for t in range(T - 1, -1, -1):

@@ -57,6 +57,27 @@ def main():
         ok = (same and abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item()) and rel(ug, ref.u.grad) < 2e-4
               and rel(vg, ref.v.grad) < 2e-4 and np.allclose(ev, ev_ref, rtol=2e-4, atol=1e-5))
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+    # ---- the streaming path (fn2 / lenet / medium and large models): data term sharded, one all-reduce
+    obj2, x, y = build(seed=0)
+    obj2._ws[("force_stream", id(obj2.model))] = True
+    loss2 = obj2.nested_step(xb, yb)
+    ug2, vg2 = obj2.u.grad.clone(), obj2.v.grad.clone()
+    g = [torch.zeros_like(ug2) for _ in range(world)]
+    dist.all_gather(g, ug2)
+    same2 = all(torch.equal(g[0], t) for t in g)
+    if rank == 0:
+        real = pc._dist_info
+        pc._dist_info = lambda: (None, 0, 1)
+        ref2, _, _ = build(seed=0)
+        ref2._ws[("force_stream", id(ref2.model))] = True
+        loss2_ref = ref2.nested_step(xb, yb)
+        pc._dist_info = real
+        rel = lambda a, b: float((a - b).norm() / b.norm())  # noqa: E731
+        print(f"stream: world={world} identical_across_ranks={same2} loss {loss2.item():.5f} vs {loss2_ref.item():.5f} "
+              f"u_grad rel {rel(ug2, ref2.u.grad):.2e} v_grad rel {rel(vg2, ref2.v.grad):.2e}")
+        ok2 = (same2 and abs(loss2.item() - loss2_ref.item()) <= 2e-5 * abs(loss2_ref.item())
+               and rel(ug2, ref2.u.grad) < 5e-4 and rel(vg2, ref2.v.grad) < 5e-4)
+        print("MULTI_GPU_CHECK_STREAM", "PASS" if ok2 else "FAIL")
     dist.destroy_process_group()
 
 

@@ -100,3 +100,38 @@ def test_run_mfvi_subset_n_hidden_100():
                           architecture="fn", n_hidden=100, nc=nc, dnm="halfmoon", init_sd=1e-3, quiet=True)
     assert len(res["elbos"]) == 300 and len(res["accs"]) == 3
     assert np.isfinite(res["nlls"]).all() and res["accs"][-1] > 0.8 and res["elbos"][-1] > res["elbos"][0]
+
+
+def test_stream_outer_grad_row_chunks_and_rank_shares_add_up():
+    """StreamEngine.outer_grad: (i) processing the data rows in chunks equals one concatenated pass; (ii) the shares of R
+    emulated ranks (kappa = 1/R, contiguous row shards of the same minibatch) add up to the unsharded value and gradients --
+    the identity behind the ONE all-reduce of the sharded bilevel step."""
+    from psvi.inference.stream import MeanFieldFamily, StreamEngine
+    from psvi.models.neural_net import make_fcnet
+    torch.manual_seed(0)
+    D, H, C, S, M, B = 6, 40, 3, 5, 12, 50
+    net = make_fcnet(D, H, C, n_layers=1, mc_samples=S, init_sd=1e-2).cuda()
+    net.flat()
+    eng = StreamEngine(MeanFieldFamily(net), net.dims, S)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u, xb = torch.randn(M, D, device="cuda", generator=g), torch.randn(B, D, device="cuda", generator=g)
+    z = torch.randint(0, C, (M,), device="cuda", generator=g, dtype=torch.int32)
+    yb = torch.randint(0, C, (B,), device="cuda", generator=g, dtype=torch.int32)
+    a = torch.rand(M, device="cuda", generator=g) * 40
+    eps = torch.randn(S, eng.Pt, device="cuda", generator=g)
+    phi = eng.fam.get_phi()
+    full = eng.outer_grad(phi, eps, u, z, a, xb, yb, 500.0)
+    eng.ROW_CHUNK = 16
+    chunked = eng.outer_grad(phi, eps, u, z, a, xb, yb, 500.0)
+    for x1, x2 in zip(full[:4], chunked[:4]):
+        assert rel_l2(x2.cpu().numpy(), x1.cpu().numpy()) < 2e-5
+    for R in (2, 3):
+        for chunk in (8192, 16):
+            eng.ROW_CHUNK = chunk
+            parts = []
+            for r in range(R):
+                lo, hi = (B * r) // R, (B * (r + 1)) // R
+                parts.append(eng.outer_grad(phi, eps, u, z, a, xb[lo:hi], yb[lo:hi], 500.0, kappa=1.0 / R, n_total=B))
+            for i in range(4):
+                tot = sum(p[i].double() for p in parts)
+                assert rel_l2(tot.cpu().numpy(), full[i].double().cpu().numpy()) < 5e-5
