@@ -443,6 +443,36 @@ def main():
     except Exception as e:
         lenet = {"error": repr(e)[:300]}
 
+    # -------- cfg3 (fn2: full-covariance BNN, two hidden layers of 40 units, P = 1 356 286; synthetic 2-d data, M=100,
+    # S=32, T=20, B=128): one PSVI outer step through the packed-triangle streaming path ---------------------------------
+    fn2 = None
+    try:
+        from psvi.experiments.experiments_utils import SynthDataset as _SD, make_synthetic_rows as _msr
+        from psvi.inference.psvi_classes import PSVILearnV as _PL
+        X3, Y3 = _msr(100000, 2, 2, seed=0)
+        t3, e3 = _SD(X3[:90000], Y3[:90000].float()), _SD(X3[90000:], Y3[90000:].float())
+        k3 = dict(mc_samples=32, num_epochs=0, data_minibatch=128, D=2, N=90000, inner_it=20, trainer="nested", log_every=1000,
+                  lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-2, num_pseudo=100, seed=rank,
+                  architecture="fn2", n_hidden=40, n_layers=1, logistic_regression=False, train_dataset=t3, test_dataset=e3,
+                  dnm="synthetic", nc=2, compute_weights_entropy=False, register_elbos=False, quiet=True)
+        o3 = _PL(**k3)
+        o3.run_psvi(**k3)
+        pc._dist_info = lambda: (None, 0, 1)
+        x3b, y3b = o3._next_minibatch()
+        o3.nested_step(x3b, y3b)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(3):
+            o3.nested_step(x3b, y3b)
+        b.record(stream)
+        torch.cuda.synchronize()
+        pc._dist_info = real_dist_info
+        fn2 = {"what": "PSVILearnV.nested_step, fn2 dims [2, 40, 40, 2] (1 356 286 variational parameters, packed scale_tril), "
+                       "N=90 000, M=100, S=32, B=128, T=20", "ms_per_outer_step": a.elapsed_time(b) / 3,
+               "outer_steps_per_s": 3e3 / a.elapsed_time(b)}
+    except Exception as e:
+        fn2 = {"error": repr(e)[:300]}
+
     # -------- reduce over ranks ---------------------------------------------------------------------------------------
     value = world * K / (total_ms * 1e-3)
     e2e = world * K / (e2e_ms * 1e-3)
@@ -490,7 +520,7 @@ def main():
                             "time = whole psvi_fn_predictive_tc call incl. weight sampling; peak = measured SUSTAINED bf16 "
                             "matmul throughput (the kernel runs for tens of ms back to back); ncu: "
                             "profiles/r1_fn_tc_ncu_summary.md"},
-                "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
+                "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fn2_cfg3": fn2, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
                                                     "full_data_predictive_passes_200rows": pred_evals},
                           "sharded": sharded, "kernel_only_ms": kernel_ms,
                           "per_step_ms_min_med_max": [min(ms), sorted(ms)[len(ms) // 2], max(ms)]}}
