@@ -28,122 +28,140 @@ constexpr int N_CHUNKS = 16;   // row chunks of the conv weight-gradient kernels
 // out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
 // sel = argmax (first maximum in row-major window order, as torch's max_pool2d) | (max > 0) << 2;
 // tangent: the same selection applied to conv(in1, w1) + conv(in2, w2) + bias (all of them tangent quantities).
-template <int CI, int CO, int HIN, int PAD>
-__global__ void __launch_bounds__(256)
+// One CTA per (row, sample); a thread owns one pooling window of one output channel: the 6x6 input patch and the 25 weights
+// of a channel pair live in registers for 100 FMAs (0.6 shared-memory loads per FMA instead of 2), and the pooling is
+// thread-local, so the full-resolution map is never materialised.
+template <int CI, int CO, int HIN, int PAD, int NT>
+__global__ void __launch_bounds__(NT)
 conv_pool_fwd_kernel(const float* __restrict__ in1, size_t ss1, const float* __restrict__ w1, const float* __restrict__ in2,
                      size_t ss2, const float* __restrict__ w2, const float* __restrict__ bias, int R, uint8_t* sel,
                      int tangent, float* __restrict__ out) {
   constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25;
-  __shared__ float s_in1[CI * HP * HP], s_in2[CI * HP * HP], s_w1[NW], s_w2[NW], s_a[CO * HO * HO];
+  __shared__ float s_in1[CI * HP * HP], s_in2[CI * HP * HP], s_w1[NW], s_w2[NW];
   const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const float* i1 = in1 + (size_t)s * ss1 + (size_t)r * CI * HIN * HIN;
   const float* i2 = in2 ? in2 + (size_t)s * ss2 + (size_t)r * CI * HIN * HIN : nullptr;
-  for (int i = tid; i < CI * HP * HP; i += 256) {
+  for (int i = tid; i < CI * HP * HP; i += NT) {
     const int ci = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
     const bool ok = yy >= 0 && yy < HIN && xx >= 0 && xx < HIN;
     s_in1[i] = ok ? i1[(ci * HIN + yy) * HIN + xx] : 0.f;
     s_in2[i] = (ok && i2) ? i2[(ci * HIN + yy) * HIN + xx] : 0.f;
   }
-  for (int i = tid; i < NW; i += 256) {
+  for (int i = tid; i < NW; i += NT) {
     s_w1[i] = w1[(size_t)s * LN_P + i];
     s_w2[i] = w2 ? w2[(size_t)s * LN_P + i] : 0.f;
   }
   __syncthreads();
-  for (int idx = tid; idx < CO * HO * HO; idx += 256) {
-    const int co = idx / (HO * HO), y = (idx / HO) % HO, x = idx % HO;
-    float acc = bias ? bias[(size_t)s * LN_P + co] : 0.f;
-#pragma unroll
-    for (int ci = 0; ci < CI; ++ci) {
-      const float* a = s_in1 + (ci * HP + y) * HP + x;
-      const float* w = s_w1 + (co * CI + ci) * 25;
-#pragma unroll
-      for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) acc = fmaf(a[ky * HP + kx], w[ky * 5 + kx], acc);
-    }
-    if (i2) {
-#pragma unroll
+  const size_t ob = ((size_t)s * R + r) * (CO * HQ * HQ);
+  for (int task = tid; task < CO * HQ * HQ; task += NT) {
+    const int co = task / (HQ * HQ), py = (task / HQ) % HQ, px = task % HQ;
+    const float b0 = bias ? bias[(size_t)s * LN_P + co] : 0.f;
+    float acc[4] = {b0, b0, b0, b0};
+#pragma unroll 1
+    for (int term = 0; term < 2; ++term) {
+      if (term == 1 && !i2) break;
+      const float* sin = term ? s_in2 : s_in1;
+      const float* sw = term ? s_w2 : s_w1;
+#pragma unroll 1
       for (int ci = 0; ci < CI; ++ci) {
-        const float* a = s_in2 + (ci * HP + y) * HP + x;
-        const float* w = s_w2 + (co * CI + ci) * 25;
+        const float* a = sin + (ci * HP + 2 * py) * HP + 2 * px;
+        const float* w = sw + (co * CI + ci) * 25;
+        float pt[6][6], wv[25];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) pt[i][j] = a[i * HP + j];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) wv[i] = w[i];
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 5; ++kx) acc = fmaf(a[ky * HP + kx], w[ky * 5 + kx], acc);
+          for (int kx = 0; kx < 5; ++kx) {
+            const float wk = wv[ky * 5 + kx];
+            acc[0] = fmaf(pt[ky][kx], wk, acc[0]);
+            acc[1] = fmaf(pt[ky][kx + 1], wk, acc[1]);
+            acc[2] = fmaf(pt[ky + 1][kx], wk, acc[2]);
+            acc[3] = fmaf(pt[ky + 1][kx + 1], wk, acc[3]);
+          }
       }
     }
-    s_a[idx] = acc;
-  }
-  __syncthreads();
-  const size_t ob = ((size_t)s * R + r) * (CO * HQ * HQ);
-  for (int idx = tid; idx < CO * HQ * HQ; idx += 256) {
-    const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ;
-    const float* a = s_a + (co * HO + 2 * py) * HO + 2 * px;
-    const float c0 = a[0], c1 = a[1], c2 = a[HO], c3 = a[HO + 1];
     if (!tangent) {
-      float best = fmaxf(c0, 0.f);
+      float best = fmaxf(acc[0], 0.f);
       int k = 0;
-      if (fmaxf(c1, 0.f) > best) { best = fmaxf(c1, 0.f); k = 1; }
-      if (fmaxf(c2, 0.f) > best) { best = fmaxf(c2, 0.f); k = 2; }
-      if (fmaxf(c3, 0.f) > best) { best = fmaxf(c3, 0.f); k = 3; }
-      sel[ob + idx] = (uint8_t)(k | ((best > 0.f) ? 4 : 0));
-      out[ob + idx] = best;
+      if (fmaxf(acc[1], 0.f) > best) { best = fmaxf(acc[1], 0.f); k = 1; }
+      if (fmaxf(acc[2], 0.f) > best) { best = fmaxf(acc[2], 0.f); k = 2; }
+      if (fmaxf(acc[3], 0.f) > best) { best = fmaxf(acc[3], 0.f); k = 3; }
+      sel[ob + task] = (uint8_t)(k | ((best > 0.f) ? 4 : 0));
+      out[ob + task] = best;
     } else {
-      const int c = sel[ob + idx], k = c & 3;
-      const float v = k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3));
-      out[ob + idx] = (c & 4) ? v : 0.f;
+      const int c = sel[ob + task], k = c & 3;
+      const float v = k == 0 ? acc[0] : (k == 1 ? acc[1] : (k == 2 ? acc[2] : acc[3]));
+      out[ob + task] = (c & 4) ? v : 0.f;
     }
   }
 }
 
 // d/d(input map) of the fused conv + ReLU + pool: the pooled adjoints pb1 (and pb2) are scattered to full resolution through
-// the selection code, then out[ci][y][x] = sum_co sum_k a1[co][y+PAD-ky][x+PAD-kx] w1[co][ci][ky][kx]  (+ the same with a2, w2).
-template <int CI, int CO, int HIN, int PAD>
-__global__ void __launch_bounds__(256)
+// the selection code into a zero-padded map, then out[ci][y][x] = sum_co sum_k a1[co][y+PAD-ky][x+PAD-kx] w1[co][ci][ky][kx]
+// (+ the same with a2, w2).  A thread owns a 2x2 block of one input channel (6x6 adjoint patch + 25 weights in registers per
+// output channel).
+template <int CI, int CO, int HIN, int PAD, int NT>
+__global__ void __launch_bounds__(NT)
 conv_bwd_data_kernel(const float* __restrict__ pb1, const float* __restrict__ w1, const float* __restrict__ pb2,
                      const float* __restrict__ w2, const uint8_t* __restrict__ sel, int R, float* __restrict__ out) {
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25;
-  __shared__ float s_a1[CO * HO * HO], s_a2[CO * HO * HO], s_w1[NW], s_w2[NW];
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25, LP = 4 - PAD, HA = HO + 2 * LP, HB = HIN / 2;
+  static_assert(NT >= CI * HB * HB, "one 2x2 output block per thread");
+  __shared__ float s_a[CO * HA * HA], s_w[NW];
   const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < CO * HO * HO; i += 256) { s_a1[i] = 0.f; s_a2[i] = 0.f; }
-  for (int i = tid; i < NW; i += 256) {
-    s_w1[i] = w1[(size_t)s * LN_P + i];
-    s_w2[i] = w2 ? w2[(size_t)s * LN_P + i] : 0.f;
-  }
-  __syncthreads();
   const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
-  for (int idx = tid; idx < CO * HQ * HQ; idx += 256) {
-    const int c = sel[pbase + idx];
-    if (c & 4) {
-      const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ, k = c & 3;
-      const int o = (co * HO + 2 * py + (k >> 1)) * HO + 2 * px + (k & 1);
-      s_a1[o] = pb1[pbase + idx];
-      if (pb2) s_a2[o] = pb2[pbase + idx];
-    }
-  }
-  __syncthreads();
-  const size_t ob = ((size_t)s * R + r) * (CI * HIN * HIN);
-  for (int idx = tid; idx < CI * HIN * HIN; idx += 256) {
-    const int ci = idx / (HIN * HIN), y = (idx / HIN) % HIN, x = idx % HIN;
-    float acc = 0.f;
-    for (int co = 0; co < CO; ++co) {
-      const float* wa = s_w1 + (co * CI + ci) * 25;
-      const float* wb = s_w2 + (co * CI + ci) * 25;
-#pragma unroll
-      for (int ky = 0; ky < 5; ++ky) {
-        const int oy = y + PAD - ky;
-        if (oy < 0 || oy >= HO) continue;
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-          const int ox = x + PAD - kx;
-          if (ox < 0 || ox >= HO) continue;
-          const int o = (co * HO + oy) * HO + ox;
-          acc = fmaf(s_a1[o], wa[ky * 5 + kx], acc);
-          if (pb2) acc = fmaf(s_a2[o], wb[ky * 5 + kx], acc);
-        }
+  const bool active = tid < CI * HB * HB;
+  const int ci = active ? tid / (HB * HB) : 0, by = (tid / HB) % HB, bx = tid % HB;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int term = 0; term < 2; ++term) {
+    const float* pb = term ? pb2 : pb1;
+    const float* wg = term ? w2 : w1;
+    if (!pb) break;
+    if (term) __syncthreads();
+    for (int i = tid; i < CO * HA * HA; i += NT) s_a[i] = 0.f;
+    for (int i = tid; i < NW; i += NT) s_w[i] = wg[(size_t)s * LN_P + i];
+    __syncthreads();
+    for (int idx = tid; idx < CO * HQ * HQ; idx += NT) {
+      const int c = sel[pbase + idx];
+      if (c & 4) {
+        const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ, k = c & 3;
+        s_a[(co * HA + LP + 2 * py + (k >> 1)) * HA + LP + 2 * px + (k & 1)] = pb[pbase + idx];
       }
     }
-    out[ob + idx] = acc;
+    __syncthreads();
+    if (active) {
+#pragma unroll 1
+      for (int co = 0; co < CO; ++co) {
+        const float* a = s_a + (co * HA + 2 * by) * HA + 2 * bx;
+        const float* w = s_w + (co * CI + ci) * 25;
+        float pt[6][6], wv[25];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) pt[i][j] = a[i * HA + j];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) wv[i] = w[i];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const float wk = wv[ky * 5 + kx];
+            acc[0] = fmaf(pt[4 - ky][4 - kx], wk, acc[0]);
+            acc[1] = fmaf(pt[4 - ky][5 - kx], wk, acc[1]);
+            acc[2] = fmaf(pt[5 - ky][4 - kx], wk, acc[2]);
+            acc[3] = fmaf(pt[5 - ky][5 - kx], wk, acc[3]);
+          }
+      }
+    }
+  }
+  if (active) {
+    float* o = out + ((size_t)s * R + r) * (CI * HIN * HIN) + (ci * HIN + 2 * by) * HIN + 2 * bx;
+    o[0] = acc[0]; o[1] = acc[1]; o[HIN] = acc[2]; o[HIN + 1] = acc[3];
   }
 }
 
@@ -547,8 +565,8 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     attr_set = true;
   }
   // ---- primal forward
-  conv_pool_fwd_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, R, w.sel1, 0, w.p1);
-  conv_pool_fwd_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2, R,
+  conv_pool_fwd_kernel<1, 6, 28, 2, 256><<<gimg, 256, 0, st>>>(x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, R, w.sel1, 0, w.p1);
+  conv_pool_fwd_kernel<6, 16, 14, 0, 416><<<gimg, 416, 0, st>>>(w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2, R,
                                                           w.sel2, 0, w.p2);
   lin_fwd(w.p2, theta + O_W3, nullptr, nullptr, theta + O_B3, N_P2, N_H3, 1, nullptr, w.h3);
   lin_fwd(w.h3, theta + O_W4, nullptr, nullptr, theta + O_B4, N_H3, N_H4, 1, nullptr, w.h4);
@@ -571,15 +589,15 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
     conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
-    conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1);
+    conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1);
     conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
-    if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, nullptr, nullptr, w.sel1, R, xbar);
+    if (xbar) conv_bwd_data_kernel<1, 6, 28, 2, 224><<<gimg, 224, 0, st>>>(w.g1, theta + O_W1, nullptr, nullptr, w.sel1, R, xbar);
     LN_CHECK();
     return PSVI_OK;
   }
   // ---- dual pass: tangent forward (x itself carries no tangent)
-  conv_pool_fwd_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(x, 0, thetad + O_W1, nullptr, 0, nullptr, thetad + O_B1, R, w.sel1, 1, w.pd1);
-  conv_pool_fwd_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.pd1, sR * N_P1, theta + O_W2, w.p1, sR * N_P1, thetad + O_W2,
+  conv_pool_fwd_kernel<1, 6, 28, 2, 256><<<gimg, 256, 0, st>>>(x, 0, thetad + O_W1, nullptr, 0, nullptr, thetad + O_B1, R, w.sel1, 1, w.pd1);
+  conv_pool_fwd_kernel<6, 16, 14, 0, 416><<<gimg, 416, 0, st>>>(w.pd1, sR * N_P1, theta + O_W2, w.p1, sR * N_P1, thetad + O_W2,
                                                           thetad + O_B2, R, w.sel2, 1, w.pd2);
   lin_fwd(w.pd2, theta + O_W3, w.p2, thetad + O_W3, thetad + O_B3, N_P2, N_H3, 0, w.h3, w.hd3);
   lin_fwd(w.hd3, theta + O_W4, w.h3, thetad + O_W4, thetad + O_B4, N_H3, N_H4, 0, w.h4, w.hd4);
@@ -609,12 +627,12 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
   conv2_wgrad(w.g2d, w.pd1, tbar + O_W2, nullptr, 1);
   conv2_wgrad(w.g2d, w.p1, tdbar + O_W2, tdbar + O_B2, 0);
-  conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, R, w.g1);
-  conv_bwd_data_kernel<6, 16, 14, 0><<<gimg, 256, 0, st>>>(w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1d);
+  conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, R, w.g1);
+  conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1d);
   // conv 1
   conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
   conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1, 0);
-  if (xbar) conv_bwd_data_kernel<1, 6, 28, 2><<<gimg, 256, 0, st>>>(w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, R, xbar);
+  if (xbar) conv_bwd_data_kernel<1, 6, 28, 2, 224><<<gimg, 224, 0, st>>>(w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, R, xbar);
   LN_CHECK();
   return PSVI_OK;
 }
