@@ -22,7 +22,9 @@ constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 =
               O_W5 = 60856, O_B5 = 61696;
 constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
 constexpr int RT = 8;   // rows per CTA of the fully connected kernels
-constexpr int N_CHUNKS = 16;   // row chunks of the conv weight-gradient kernels (16 x S CTAs)
+// makes a loaded value opaque to the optimiser, so it stays in a register instead of being re-read from shared memory
+#define KEEP_IN_REG(x) asm volatile("" : "+f"(x))
+constexpr int N_CHUNKS = 64;   // row chunks of the conv weight-gradient kernels (up to 64 x S CTAs)
 
 // ------------------------------------------------------------------------------------------------ conv + ReLU + pool
 // out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
@@ -70,9 +72,9 @@ conv_pool_fwd_kernel(const float* __restrict__ in1, size_t ss1, const float* __r
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) pt[i][j] = a[i * HP + j];
+          for (int j = 0; j < 6; ++j) { pt[i][j] = a[i * HP + j]; KEEP_IN_REG(pt[i][j]); }
 #pragma unroll
-        for (int i = 0; i < 25; ++i) wv[i] = w[i];
+        for (int i = 0; i < 25; ++i) { wv[i] = w[i]; KEEP_IN_REG(wv[i]); }
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
@@ -143,9 +145,9 @@ conv_bwd_data_kernel(const float* __restrict__ pb1, const float* __restrict__ w1
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) pt[i][j] = a[i * HA + j];
+          for (int j = 0; j < 6; ++j) { pt[i][j] = a[i * HA + j]; KEEP_IN_REG(pt[i][j]); }
 #pragma unroll
-        for (int i = 0; i < 25; ++i) wv[i] = w[i];
+        for (int i = 0; i < 25; ++i) { wv[i] = w[i]; KEEP_IN_REG(wv[i]); }
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
