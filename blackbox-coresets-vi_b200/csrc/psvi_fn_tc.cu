@@ -92,6 +92,28 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
 #define PROF_OUT(row)
 #endif
 
+// ---- thread-block-cluster helpers (CL = 2: the two CTAs of a cluster share every W1 stage through TMA multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -100,6 +122,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) 
       : "memory");
 }
 
+template <int CL>
 __global__ void __launch_bounds__(FN_THREADS, 1)
 psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                           const FnParams p) {
@@ -135,7 +158,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     }
     for (int s = 0; s < 64; ++s) s_w[s] = s < p.S ? (p.mode == 1 ? expf(p.lw[s] - mx) / se : 1.f / (float)p.S) : 0.f;
     mbar_init(xfull, 8); mbar_init(xempty, 1);
-    for (int i = 0; i < BST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < BST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // CL MMA warps release a shared stage
     for (int i = 0; i < WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 9); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1); mbar_init(&hfull[i], 8);
@@ -148,10 +171,14 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_tiles * p.nsplit;
+  // work items are enumerated per cluster: item w = (group of CL consecutive row tiles, sample split); CTA `crank` of the
+  // cluster takes tile CL * group + crank, so both CTAs walk the same (sample, hidden chunk) sequence in lockstep
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int n_items = ((p.n_tiles + CL - 1) / CL) * p.nsplit;
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
@@ -159,8 +186,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     int st = 0, it = 0;
     uint32_t ph = 0;
     PROF_DECL
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int tile = w / p.nsplit, split = w - tile * p.nsplit;
+    for (int w = cid; w < n_items; w += ncl) {
+      const int split = w % p.nsplit;
       const int ns = (p.S - split + p.nsplit - 1) / p.nsplit, srot = w % ns, hrot = (w / ns) % p.hc;
       for (int js = 0; js < ns; ++js) {
         const int s = split + ((js + srot) % ns) * p.nsplit;
@@ -179,8 +206,13 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
             PROF_T(1, mbar_wait(&empty[st], ph ^ 1));
             if (elect_one()) {
               mbar_expect_tx(&full[st], (uint32_t)(p.ks * KCH_BYTES));
-              for (int kk = 0; kk < p.ks; ++kk)
-                tma_load_2d(&map_w1, &full[st], sB + st * STAGE_BYTES + kk * KCH_BYTES, (k + kk) * BK, s * p.H + h * BN);
+              for (int kk = 0; kk < p.ks; ++kk) {
+                if (CL > 1)   // this CTA fetches rows [64 crank, +64) of the chunk and multicasts them into both CTAs
+                  tma_load_2d_mc(&map_w1, &full[st], sB + st * STAGE_BYTES + kk * KCH_BYTES + crank * (KCH_BYTES / 2),
+                                 (k + kk) * BK, s * p.H + h * BN + crank * (BN / 2), (uint16_t)3);
+                else
+                  tma_load_2d(&map_w1, &full[st], sB + st * STAGE_BYTES + kk * KCH_BYTES, (k + kk) * BK, s * p.H + h * BN);
+              }
             }
             __syncwarp();
             if (++st == BST) { st = 0; ph ^= 1; }
@@ -219,9 +251,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       });
       __syncwarp();
     };
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-      const int tile = w / p.nsplit, split = w - tile * p.nsplit;
-      (void)tile;
+    for (int w = cid; w < n_items; w += ncl, ++item) {
+      const int split = w % p.nsplit;
       PROF_T(4, mbar_wait(xfull, item & 1));
       tc_fence_after();
       const int ns = (p.S - split + p.nsplit - 1) / p.nsplit;
@@ -243,7 +274,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
                 for (int j = 0; j < BK / 16; ++j)
                   umma_bf16_ts(tmem_d, a0 + BK / 2 + j * 8, make_desc_sw128(b0 + KCH_BYTES + j * 32), idesc1, 1u);
               }
-              umma_commit(&empty[st]);
+              if (CL > 1) umma_commit_mc(&empty[st], (uint16_t)3); else umma_commit(&empty[st]);
               if (k + p.ks >= p.kc) umma_commit(&tfull[buf]);
             });
             __syncwarp();
@@ -269,8 +300,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     float nll_sum = 0.f, correct = 0.f;
     int it = 0, jsamp = 0, item = 0;
     PROF_DECL
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
-      const int tile = w / p.nsplit, split = w - tile * p.nsplit;
+    for (int w = cid; w < n_items; w += ncl, ++item) {
+      const int tile = (w / p.nsplit) * CL + crank, split = w % p.nsplit;   // tile may be >= n_tiles (odd tile count): no valid rows
       const int row = tile * BM + rl;
       const bool rok = row < p.n_rows;
       const int y = rok ? __ldg(p.labels + row) : 0;
@@ -368,7 +399,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
             const float nll = rok ? (mx - ly) * LN2 + logf(se) : 0.f;
             if (p.nll_out && rok) p.nll_out[(size_t)s * p.n_rows + row] = nll;
             const float t = warp_sum(cwr * nll);
-            if (lane == 0) p.part[((size_t)tile * 4 + q) * p.S + s] = t;
+            if (lane == 0 && tile < p.n_tiles) p.part[((size_t)tile * 4 + q) * p.S + s] = t;
           } else {
             const float sc = __fdividef(s_w[s], se);
 #pragma unroll
@@ -418,7 +449,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may leave while its peer can still multicast into it
   if (threadIdx.x == 0 && p.mode != 0 && p.nsplit == 1) {
     float a = 0.f, b = 0.f;
     for (int q = 0; q < 4; ++q) { a += s_red[q * 2]; b += s_red[q * 2 + 1]; }
@@ -685,9 +716,15 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles = (int)((n_rows + BM - 1) / BM);
-  const int nsplit = split_for(tiles, S, sms < 148 ? sms : 148);
+  // optional (PSVI_FN_CLUSTER=2): clusters of two CTAs sharing every W1 stage by TMA multicast.  Measured on B200: correct, but not
+  // faster (1.09 vs 1.17 PFLOP/s at 131 k rows) -- the L2 already de-duplicates the concurrent reads and the two CTAs run in
+  // lockstep -- so one CTA per SM without clusters stays the default.
+  static const int cl_env = getenv("PSVI_FN_CLUSTER") ? atoi(getenv("PSVI_FN_CLUSTER")) : 1;
+  const int CLv = (cl_env == 2 && tiles >= 2) ? 2 : 1;
+  const int groups = (tiles + CLv - 1) / CLv;
+  const int nsplit = split_for(groups, S, (sms < 148 ? sms : 148) / CLv);
   CUtensorMap map_w1, map_w2;
-  int rc = make_map_2d_bf16(&map_w1, sc.W1b, (uint64_t)D, (uint64_t)S * H, BK, BN);
+  int rc = make_map_2d_bf16(&map_w1, sc.W1b, (uint64_t)D, (uint64_t)S * H, BK, BN / CLv);
   if (rc) return rc;
   rc = make_map_2d_bf16(&map_w2, sc.W2b, (uint64_t)H, (uint64_t)S * CW, BK, CW);
   if (rc) return rc;
@@ -697,8 +734,8 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   p.mode = mode; p.x = static_cast<const __nv_bfloat16*>(x_bf16);
   p.b1 = sc.b1; p.b2 = sc.b2; p.cw = cw; p.lw = lw; p.labels = labels; p.nll_out = nll_out; p.part = sc.part;
   p.probs_out = sc.probs;
-  const int items = tiles * nsplit;
-  const int grid = items < sms ? items : sms;
+  const int items = groups * nsplit;
+  const int grid = CLv * (items < sms / CLv ? items : sms / CLv);
 #ifdef PSVI_FN_PROF
   static unsigned long long* prof_buf = nullptr;
   const bool prof = getenv("PSVI_FN_PROF") != nullptr;
@@ -708,8 +745,24 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
 #endif
   const size_t smem = (size_t)BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 + CW * BM * 4 + 8 * 4 +
                       (2 + 2 * BST + 2 * WST + 8) * 8 + 16 + 1024;
-  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  psvi_fn_forward_tc_kernel<<<grid, FN_THREADS, smem, stream>>>(map_w1, map_w2, p);
+  if (CLv == 2) {
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(FN_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PSVI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, psvi_fn_forward_tc_kernel<2>, map_w1, map_w2, p));
+  } else {
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    psvi_fn_forward_tc_kernel<1><<<grid, FN_THREADS, smem, stream>>>(map_w1, map_w2, p);
+  }
   PSVI_CUDA_CHECK(cudaGetLastError());
 #ifdef PSVI_FN_PROF
   if (prof) {
