@@ -30,7 +30,9 @@ constexpr int BM = 128, BK = 64, BN = 128;   // row tile, K chunk (one 128-byte 
 constexpr int BST = 5;                       // W1 ring depth (5 stages of up to two [128 x 64] K-chunks = 32 KB)
 constexpr int WST = 4;                       // second-layer chunk ring depth (4 x (4 KB + 512 B))
 constexpr int CW = 16;                       // classes padded to 16
-constexpr int FN_THREADS = 128 + 256;        // 4 role warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int EPW = 2;                       // epilogue warps per TMEM lane quarter (each owns 128 / EPW accumulator columns; 4 measured: no gain)
+constexpr int CPW = BN / EPW;                // fp32 accumulator columns per epilogue warp
+constexpr int FN_THREADS = 128 + 128 * EPW;  // 4 role warps + 4 * EPW epilogue warps
 constexpr int KCH_BYTES = BN * BK * 2;       // 16 KB: one [128 x 64] bf16 operand tile (one K-chunk)
 constexpr int STAGE_BYTES = 2 * KCH_BYTES;   // a ring stage holds two K-chunks (one when D / 64 is odd)
 constexpr int W2_STAGE_BYTES = 2 * CW * 128; // two SW128 atoms of [16 rows x 64 k]
@@ -135,7 +137,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
   float* sB1 = reinterpret_cast<float*>(sW2 + WST * W2_STAGE_BYTES);
   float* s_w = sB1 + WST * BN;
   float* s_xch = s_w + 64;
-  float* s_red = s_xch + CW * BM;
+  float* s_red = s_xch + (EPW - 1) * CW * BM;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8);
   uint64_t* xfull = bars;            // [1]  the 8 epilogue warps have stored the X tile into TMEM
   uint64_t* xempty = bars + 1;       // [1]  every GEMM1 of the item has read the X tile
@@ -159,9 +161,9 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
     for (int s = 0; s < 64; ++s) s_w[s] = s < p.S ? (p.mode == 1 ? expf(p.lw[s] - mx) / se : 1.f / (float)p.S) : 0.f;
     mbar_init(xfull, 8); mbar_init(xempty, 1);
     for (int i = 0; i < BST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // CL MMA warps release a shared stage
-    for (int i = 0; i < WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 9); }
+    for (int i = 0; i < WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1 + 4 * EPW); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&hfull[i], 8);
+      mbar_init(&tfull[i], 1); mbar_init(&hfull[i], 4 * EPW);
       mbar_init(&lfull[i], 1); mbar_init(&lempty[i], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,8 +245,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       const uint32_t acc0 = c_h != 0;
       PROF_T(3, if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < BN / 16; ++j)   // the bf16 activations of hidden units 64 part + 16 jj .. sit at columns 64 part + 8 jj
-          umma_bf16_ts(d2 + (j & 3) * CW, a2 + (j >> 2) * 64 + (j & 3) * 8,
+        for (int j = 0; j < BN / 16; ++j)   // the bf16 activations of hidden units CPW part + 2 c, + 1 sit at column CPW part + c
+          umma_bf16_ts(d2 + (j & 3) * CW, a2 + ((j * 16) / CPW) * CPW + ((j * 16) % CPW) / 2,
                        make_desc_sw128(b0 + (j >> 2) * (CW * 128) + (j & 3) * 32), idesc2, (j >> 2) ? 1u : acc0);
         umma_commit(&wempty[wi]);
         if (c_h == p.hc - 1) umma_commit(&lfull[sb]);
@@ -311,7 +313,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         // take one half of the K range each (column c holds K elements 2c, 2c+1)
         mbar_wait(xempty, (item & 1) ^ 1);
         tc_fence_after();
-        const int qn = p.D >> 6;          // 16-column groups per half row (D/2 columns per row, D/4 per warp)
+        const int qn = part < 2 ? p.D >> 6 : 0;   // 16-column groups per half row (D/2 columns per row; warps 0 and 1 of the quarter)
         const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)row * p.D) + part * (p.D >> 4);
         for (int g = 0; g < qn; ++g) {
           uint32_t xr[16];
@@ -325,7 +327,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(xfull);
+        if (lane == 0 && part < 2) mbar_arrive(xfull);
       }
       float probs[CW];
 #pragma unroll
@@ -341,11 +343,11 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
 #ifdef PSVI_FN_PROF
           const long long _tw = clock64();
 #endif
-          const float4* b1 = reinterpret_cast<const float4*>(sB1 + wi * BN + part * 64);
-          const uint32_t taddr = lane_addr + COL_ACC + buf * BN + part * 64;
-          uint32_t pk[32];
+          const float4* b1 = reinterpret_cast<const float4*>(sB1 + wi * BN + part * CPW);
+          const uint32_t taddr = lane_addr + COL_ACC + buf * BN + part * CPW;
+          uint32_t pk[CPW / 2];
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < CPW / 32; ++g) {
             float v[32];
             tmem_ld32(taddr + g * 32, v);
 #pragma unroll
@@ -355,8 +357,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
               pk[g * 16 + j * 2 + 1] = pack_relu_bf16(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
             }
           }
-          // in place: this warp has read all 64 fp32 columns it owns; the bf16 pairs go into the first 32 of them
-          tmem_st32(taddr, pk);
+          // in place: this warp has read all CPW fp32 columns it owns; the bf16 pairs go into the first CPW / 2 of them
+          if (CPW == 64) tmem_st32(taddr, pk); else { tmem_st16(taddr, pk); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { mbar_arrive(&hfull[buf]); mbar_arrive(&wempty[wi]); }
@@ -364,7 +366,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
           pc[2] += (unsigned long long)(clock64() - _tw);
 #endif
         }
-        if (part == (jsamp & 1)) {
+        if (part == (jsamp & (EPW - 1))) {
           // logits of this sample: softmax / NLL / mixture (the two warps of a lane quarter alternate samples)
           const int sb = jsamp & 1;
           PROF_T(3, mbar_wait(&lfull[sb], (jsamp >> 1) & 1));
@@ -409,14 +411,16 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       }
       if (p.mode != 0) {
         // combine the mixtures of the two warps of each lane quarter
-        if (part == 1) {
+        if (part > 0) {
 #pragma unroll
-          for (int c = 0; c < CW; ++c) s_xch[c * BM + rl] = probs[c];
+          for (int c = 0; c < CW; ++c) s_xch[((part - 1) * CW + c) * BM + rl] = probs[c];
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EPW) : "memory");
         if (part == 0) {
 #pragma unroll
-          for (int c = 0; c < CW; ++c) probs[c] += s_xch[c * BM + rl];
+          for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int e = 0; e < EPW - 1; ++e) probs[c] += s_xch[(e * CW + c) * BM + rl];
           if (p.nsplit > 1) {
             if (rok) {
               float* o = p.probs_out + ((size_t)split * p.n_rows + row) * CW;
@@ -437,11 +441,11 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
             correct += (am == y) ? 1.f : 0.f;
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // s_xch is reused by the next item
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EPW) : "memory");   // s_xch is reused by the next item
       }
     }
     if (warp == 4) PROF_OUT(2);
-    if (warp == 8) PROF_OUT(3);
+    if (warp == 4 + 4 * (EPW - 1)) PROF_OUT(3);
     if (p.mode != 0 && p.nsplit == 1 && part == 0) {
       nll_sum = warp_sum(nll_sum);
       correct = warp_sum(correct);
@@ -743,7 +747,7 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   if (prof) cudaMemsetAsync(prof_buf, 0, 256 * 32 * 8, stream);
   p.prof = prof ? prof_buf : nullptr;
 #endif
-  const size_t smem = (size_t)BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 + CW * BM * 4 + 8 * 4 +
+  const size_t smem = (size_t)BST * STAGE_BYTES + WST * W2_STAGE_BYTES + WST * BN * 4 + 64 * 4 + (EPW - 1) * CW * BM * 4 + 8 * 4 +
                       (2 + 2 * BST + 2 * WST + 8) * 8 + 16 + 1024;
   if (CLv == 2) {
     PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
