@@ -109,6 +109,15 @@ _SIGS = {
     "psvi_fnl_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32, C.c_int32]),
     "psvi_fnl_pass": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_sample": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_tangent": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_reparam_grad": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "psvi_mf_reparam_hvp": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_mf_nkl_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "psvi_mf_nkl_kl": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "psvi_lenet_num_theta": (C.c_int64, []),
     "psvi_lenet_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "psvi_lenet_pass": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
@@ -427,3 +436,48 @@ def fnl_pass(model, precision, theta, thetad, x, y, cw, nll=None, tbar=None, tdb
     _count(8 if tbar is None else (14 if thetad is None else 25))
     _check(lib().psvi_fnl_pass(C.byref(model), precision, _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll),
                                _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))
+
+
+# ---- the mean-field family as fused maps over [S][P] slabs (csrc/psvi_family.cu)
+def mf_sample(mu, rho, eps):
+    S, P = eps.shape
+    theta = torch.empty_like(eps)
+    _count(1)
+    _check(lib().psvi_mf_sample(S, P, _p(mu), _p(rho), _p(eps), _p(theta), _stream()))
+    return theta
+
+
+def mf_tangent(rho, mud, rhod, eps):
+    S, P = eps.shape
+    thetad = torch.empty_like(eps)
+    _count(1)
+    _check(lib().psvi_mf_tangent(S, P, _p(rho), _p(mud), _p(rhod), _p(eps), _p(thetad), _stream()))
+    return thetad
+
+
+def mf_reparam_grad(mu, rho, eps, tbar, kl_coef, nkl_coef, mask=None, beta=None, theta=None):
+    S, P = eps.shape
+    g = torch.empty(2 * P, device=eps.device)
+    _count(1)
+    _check(lib().psvi_mf_reparam_grad(S, P, _p(mu), _p(rho), _p(eps), _p(tbar), _p(beta), _p(theta), _p(mask), float(kl_coef),
+                                      float(nkl_coef), _p(g), _stream()))
+    return g
+
+
+def mf_reparam_hvp(rho, mud, rhod, eps, A_t, A_td, mask=None):
+    S, P = eps.shape
+    h = torch.empty(2 * P, device=eps.device)
+    _count(1)
+    _check(lib().psvi_mf_reparam_hvp(S, P, _p(rho), _p(mud), _p(rhod), _p(eps), _p(A_t), _p(A_td), _p(mask), _p(h), _stream()))
+    return h
+
+
+def mf_nkl_kl(mu, rho, eps, theta, mask=None):
+    """-> double tensor [S + 1]: sampled nkl per sample, then the KL."""
+    S, P = eps.shape
+    out = torch.empty(S + 1, device=eps.device, dtype=torch.float64)
+    scratch = torch.empty((int(lib().psvi_mf_nkl_scratch_bytes(S)) + 7) // 8, device=eps.device, dtype=torch.float64)
+    _count(2)
+    _check(lib().psvi_mf_nkl_kl(S, P, _p(mu), _p(rho), _p(eps), _p(theta), _p(mask), _p(out, torch.float64), _p(scratch, torch.float64),
+                                _stream()))
+    return out

@@ -49,38 +49,35 @@ class MeanFieldFamily:
         self.mu.copy_(phi[:self.Pt])
         self.rho.copy_(phi[self.Pt:])
 
+    # the [S][P] maps are fused native kernels (csrc/psvi_family.cu): each reads every slab once
     def sample(self, phi, eps):
-        return (phi[:self.Pt] + F.softplus(phi[self.Pt:]) * eps).contiguous()
+        return _native.mf_sample(phi[:self.Pt], phi[self.Pt:], eps.contiguous())
 
     def tangent(self, phi, phidot, eps):
-        return (phidot[:self.Pt] + torch.sigmoid(phi[self.Pt:]) * phidot[self.Pt:] * eps).contiguous()
+        return _native.mf_tangent(phi[self.Pt:], phidot[:self.Pt].contiguous(), phidot[self.Pt:].contiguous(), eps.contiguous())
 
     def kl(self, phi):
         mu, sg = phi[:self.Pt], F.softplus(phi[self.Pt:])
         return self._m(0.5 * (sg * sg + mu * mu - 1.0) - torch.log(sg)).sum()
 
     def nkl(self, phi, eps, theta):
-        sg = F.softplus(phi[self.Pt:])
-        return self._m(-0.5 * theta * theta + 0.5 * eps * eps + torch.log(sg)).double().sum(1)
+        return _native.mf_nkl_kl(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), theta, self.mask)[:eps.shape[0]]
 
     def nkl_theta_grad(self, theta):
         """d nkl_s / d theta_s through the sample."""
         return -self._m(theta)
 
     def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
-        mu, rho = phi[:self.Pt], phi[self.Pt:]
-        sg, sig = F.softplus(rho), torch.sigmoid(rho)
-        gmu = tbar.sum(0) + self._m(kl_coef * mu)
-        grho = sig * ((tbar * eps).sum(0) + self._m(kl_coef * (sg - 1 / sg) + nkl_coef / sg))
-        return torch.cat([gmu, grho])
+        return _native.mf_reparam_grad(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), tbar, kl_coef, nkl_coef, mask=self.mask)
+
+    def grad_with_nkl(self, phi, eps, tbar, beta, theta):
+        """phi_bar of the outer objective: tbar plus the d nkl_s / d theta_s path (weights beta_s) and the log-sigma term."""
+        return _native.mf_reparam_grad(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), tbar, 0.0, float(beta.sum()), mask=self.mask,
+                                       beta=beta.float().contiguous(), theta=theta)
 
     def hvp(self, phi, phidot, eps, A_t, A_td):
-        rho, md, rd = phi[self.Pt:], phidot[:self.Pt], phidot[self.Pt:]
-        sg, sig = F.softplus(rho), torch.sigmoid(rho)
-        hmu = A_t.sum(0) + self._m(md)
-        hrho = (sig * (A_t * eps).sum(0) + sig * (1 - sig) * rd * (A_td * eps).sum(0)
-                + self._m(((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rd))
-        return torch.cat([hmu, hrho])
+        return _native.mf_reparam_hvp(phi[self.Pt:], phidot[:self.Pt].contiguous(), phidot[self.Pt:].contiguous(), eps.contiguous(),
+                                      A_t, A_td, mask=self.mask)
 
 
 class LenetFamily(MeanFieldFamily):
@@ -308,8 +305,11 @@ class StreamEngine:
                 nc = torch.empty(S, xc.shape[0], device=dev)
                 self.net.pass_(theta, None, xc, yc, wd[:, None].expand(S, xc.shape[0]).contiguous(), nll=nc, tbar=tb)
                 tbar += tb
-        tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
-        pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
+        if hasattr(self.fam, "grad_with_nkl"):
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+        else:
+            tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
+            pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
         return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
     def hvp(self, phi, eps, u, z32, a, phidot):

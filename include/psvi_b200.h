@@ -279,6 +279,28 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
 int psvi_logits_predict(const float* logits, const float* log_weights, int32_t mode, const int32_t* yt, int32_t S, int32_t R,
                         int32_t C, float* out, void* stream);
 
+/* ---- the mean-field family as fused maps over [S][P] slabs (theta layout), used by the streaming engine.  Replace
+ * VIMixin.rsample / kl / sampled_nkl (psvi/models/neural_net.py:101-115,155-162) and what autograd accumulates into
+ * (weight, bias, _weight_sd, _bias_sd) through theta = mu + softplus(rho) eps.
+ * `mask` [P] (nullable = ones): 1 for parameters that enter the KL / sampled-nkl sums (0 for conv layers, quirk Q5).
+ *   psvi_mf_sample:       theta[s] = mu + softplus(rho) eps[s]
+ *   psvi_mf_tangent:      thetad[s] = mud + sigmoid(rho) rhod eps[s]
+ *   psvi_mf_reparam_grad: g [2P] = [sum_s tb + mask kl_coef mu | sigmoid(rho)(sum_s tb eps + mask (kl_coef (sg - 1/sg) + nkl_coef/sg))]
+ *                         with tb = tbar - beta[s] mask theta[s]  (beta [S] / theta nullable)
+ *   psvi_mf_reparam_hvp:  h [2P] from A_theta, A_thetadot (SURVEY A.6 last line)
+ *   psvi_mf_nkl_kl:       out[0..S-1] = sampled nkl per sample, out[S] = KL (double); scratch psvi_mf_nkl_scratch_bytes(S) */
+int psvi_mf_sample(int32_t S, int64_t P, const float* mu, const float* rho, const float* eps, float* theta, void* stream);
+int psvi_mf_tangent(int32_t S, int64_t P, const float* rho, const float* mud, const float* rhod, const float* eps, float* thetad,
+                    void* stream);
+int psvi_mf_reparam_grad(int32_t S, int64_t P, const float* mu, const float* rho, const float* eps, const float* tbar,
+                         const float* beta, const float* theta, const float* mask, float kl_coef, float nkl_coef, float* g,
+                         void* stream);
+int psvi_mf_reparam_hvp(int32_t S, int64_t P, const float* rho, const float* mud, const float* rhod, const float* eps,
+                        const float* A_t, const float* A_td, const float* mask, float* h, void* stream);
+size_t psvi_mf_nkl_scratch_bytes(int32_t S);
+int psvi_mf_nkl_kl(int32_t S, int64_t P, const float* mu, const float* rho, const float* eps, const float* theta, const float* mask,
+                   double* out, void* scratch, void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,

@@ -135,3 +135,44 @@ def test_stream_outer_grad_row_chunks_and_rank_shares_add_up():
             for i in range(4):
                 tot = sum(p[i].double() for p in parts)
                 assert rel_l2(tot.cpu().numpy(), full[i].double().cpu().numpy()) < 5e-5
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_fused_meanfield_family_kernels_match_formulas(masked):
+    """csrc/psvi_family.cu (sample / tangent / nkl / reparameterisation gradient and HVP tails over [S][P] slabs) against the
+    closed forms of SURVEY Appendix A.1 / A.6 written with torch ops in fp64."""
+    from psvi import _native as nat
+    import torch.nn.functional as F
+    nat.require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    S, P = 5, 1003
+    mu, rho = torch.randn(P, device="cuda", generator=g) * 0.3, torch.randn(P, device="cuda", generator=g) - 3.0
+    mud, rhod = torch.randn(P, device="cuda", generator=g), torch.randn(P, device="cuda", generator=g)
+    eps, tbar = torch.randn(S, P, device="cuda", generator=g), torch.randn(S, P, device="cuda", generator=g)
+    Atd, beta = torch.randn(S, P, device="cuda", generator=g), torch.randn(S, device="cuda", generator=g)
+    mask = (torch.rand(P, device="cuda", generator=g) > 0.4).float() if masked else None
+    mk = (mask if masked else torch.ones(P, device="cuda")).double()
+    m64, r64, e64, t64 = mu.double(), rho.double(), eps.double(), tbar.double()
+    sg, sig = F.softplus(r64), torch.sigmoid(r64)
+    theta = nat.mf_sample(mu, rho, eps)
+    assert rel_l2(theta.cpu().numpy(), (m64 + sg * e64).cpu().numpy()) < 1e-6
+    thd = nat.mf_tangent(rho, mud, rhod, eps)
+    assert rel_l2(thd.cpu().numpy(), (mud.double() + sig * rhod.double() * e64).cpu().numpy()) < 1e-6
+    th64 = theta.double()
+    out = nat.mf_nkl_kl(mu, rho, eps, theta, mask)
+    nkl = (mk * (-0.5 * th64 ** 2 + 0.5 * e64 ** 2 + torch.log(sg))).sum(1)
+    kl = (mk * (0.5 * (sg ** 2 + m64 ** 2 - 1) - torch.log(sg))).sum()
+    np.testing.assert_allclose(out[:S].cpu().numpy(), nkl.cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(out[S].item(), kl.item(), rtol=1e-5)
+    for kc, nc_, use_beta in ((1.0, 0.0, False), (0.0, 0.7, True)):
+        gg = nat.mf_reparam_grad(mu, rho, eps, tbar, kc, nc_, mask=mask, beta=beta if use_beta else None,
+                                 theta=theta if use_beta else None)
+        tb = t64 - (beta.double()[:, None] * mk * th64 if use_beta else 0.0)
+        ref = torch.cat([tb.sum(0) + mk * kc * m64, sig * ((tb * e64).sum(0) + mk * (kc * (sg - 1 / sg) + nc_ / sg))])
+        assert rel_l2(gg.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    h = nat.mf_reparam_hvp(rho, mud, rhod, eps, tbar, Atd, mask=mask)
+    rd = rhod.double()
+    ref = torch.cat([t64.sum(0) + mk * mud.double(),
+                     sig * (t64 * e64).sum(0) + sig * (1 - sig) * rd * (Atd.double() * e64).sum(0)
+                     + mk * ((1 + 1 / sg ** 2) * sig ** 2 + (sg - 1 / sg) * sig * (1 - sig)) * rd])
+    assert rel_l2(h.cpu().numpy(), ref.cpu().numpy()) < 2e-6
