@@ -468,6 +468,19 @@ __global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int 
   *d = accumulate ? *d + t : t;
 }
 
+// out[s * P + h] = sum_r YT[s][h][r]   (row sums of a transposed operand array; one warp per row, fixed order)
+template <int X3>
+__global__ void __launch_bounds__(256)
+fnl_rowsum_kernel(const void* Yh, const void* Yl, int H, int Rp, int R, float* __restrict__ out, long long P) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), s = blockIdx.y, lane = threadIdx.x & 31;
+  if (row >= H) return;
+  const size_t base = ((size_t)s * H + row) * Rp;
+  float t = 0.f;
+  for (int r = lane; r < R; r += 32) t += get<X3>(Yh, Yl, base + r);
+  t = warp_sum(t);
+  if (lane == 0) out[(long long)s * P + row] = t;
+}
+
 // out[s * P + c] = sum_r W[s][r][c]
 __global__ void fnl_colsum16_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ out, long long P) {
   const int s = blockIdx.x, c = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 x 16 threads
@@ -571,7 +584,7 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   p.b_brows = B.brows;
   p.m_tiles = (p.M_valid + GM - 1) / GM;
   p.n_tiles = (p.N_valid + GN - 1) / GN;
-  if (p.ob && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
+  if ((p.ob || p.obt) && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   const size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
@@ -681,14 +694,16 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     // ---- gradient pass
     fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, nullptr, theta + o_b2, nullptr, P, y, cw, S, R, Rp, C, 1, nll, logits, w.go, nullptr,
                                            w.AA.hi, w.AA.lo, nullptr);
-    GemmP p = z;      // abar = (obar W2) * (h > 0), also transposed
+    GemmP p = z;      // abar = (obar W2) * (h > 0): transposed (K-major for the next GEMM); row-major only if xbar needs it
     p.M_valid = R; p.N_valid = H;
-    set_mask_h(p); set_ob(p, w.aa, 0); set_obt(p, w.aT);
+    set_mask_h(p); set_obt(p, w.aT);
+    p.ob_rows = Rp;
+    if (xbar) set_ob(p, w.aa, 0);
     if ((rc = launch_gemm<X3>(opA0, opW2T1, p, sms, st))) return rc;
     p = z;            // W1bar = abar^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
     if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
-    colreduce(w.aa, 0, nullptr, 1, tbar + o_b1, 0);
+    fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);   // b1bar
     colreduce(w.hh, H, w.go, C, tbar + o_w2, 0);
     fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
     if (xbar) {
