@@ -173,7 +173,7 @@ class PSVI(object):
     def _stream(self, model):
         """StreamEngine for `model` (fn2, or a mean-field MLP the fused engine reported as PSVI_ERR_UNSUPPORTED)."""
         from psvi.inference.stream import FullCovFamily, LenetFamily, LenetNet, MeanFieldFamily, StreamEngine
-        key = id(model)
+        key = (id(model), model.n_samples())    # PSVI_No_IW switches mc_samples between training and evaluation
         eng = self._ws.get(("stream", key))
         if eng is None:
             if isinstance(model, MeanFieldLeNet):
@@ -197,6 +197,15 @@ class PSVI(object):
         from psvi.inference.stream import FnLargeNet
         dims = model.dims
         return (FnLargeNet.fits(dims, model.n_samples()) and dims[1] * (dims[0] + 1) + dims[2] * (dims[1] + 1) > 40000)
+
+    _outer_kind = "psvi"      # which outer objective nested_step differentiates ("ablated": PSVI_Ablated / PSVI_No_IW)
+
+    def _inner_pseudo(self, u, z32, a):
+        """(u, z, a) as the inner objective sees them (hook for the mc_samples == 1 quirk of PSVI_No_IW)."""
+        return u, z32, a
+
+    def _collapse_pseudo(self, ubar, abar):
+        return ubar, abar
 
     def _use_stream(self, model):
         return isinstance(model, (FullCovMLP, MeanFieldLeNet)) or self._ws.get(("force_stream", id(model)), False)
@@ -350,9 +359,11 @@ class PSVI(object):
                 dist.all_reduce(flat)
                 n1, n2 = pbar.numel(), ubar.numel()
                 return flat[0], flat[1:1 + n1], flat[1 + n1:1 + n1 + n2].reshape(ubar.shape), flat[1 + n1 + n2:]
-        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u, self._z32(),
-                                                 self._a(), xb, yb, float(self.N), T, lr, want_losses=self.register_elbos,
-                                                 kappa=kappa, n_total=n_total, reduce_fn=reduce_fn)
+        u_in, z_in, a_in = self._inner_pseudo(u, self._z32(), self._a())
+        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u_in, z_in, a_in,
+                                                 xb, yb, float(self.N), T, lr, want_losses=self.register_elbos,
+                                                 kappa=kappa, n_total=n_total, reduce_fn=reduce_fn, outer=self._outer_kind)
+        ubar, abar = self._collapse_pseudo(ubar, abar)
         eng.fam.set_phi(phi_T)                 # copy-back of the fast weights (reference :596-599)
         if self.register_elbos:
             ilc = il.cpu()
@@ -768,8 +779,65 @@ def _out_of_scope(name, where):
     return _Stub
 
 
-PSVI_Ablated = _out_of_scope("PSVI_Ablated", "reference psvi_classes.py:1388-1408")
-PSVI_No_IW = _out_of_scope("PSVI_No_IW", "reference psvi_classes.py:1411-1472")
+class PSVI_Ablated(PSVILearnV):
+    r"""PSVI with ablated importance sampling (reference :1388-1408): the outer objective is
+    mean_s (N/B) sum_b nll[s, b] - mean_s sampled_nkl_s.  Runs on the streaming engine (per-sample network kernels)."""
+
+    _outer_kind = "ablated"
+
+    def _use_stream(self, model):
+        return True
+
+    def psvi_elbo(self, xbatch, ybatch, model=None, params=None, hyperopt=False):
+        model, desc, S = self._model_desc(model)
+        xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
+        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        eng = self._stream(model)
+        loss, pbar = eng.outer_grad_ablated(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], xb, yb, float(self.N))
+        u, v = self._uv()
+        self._last_outer = dict(phi_grad=pbar, u_grad=torch.zeros_like(u), v_grad=torch.zeros_like(v), alpha_grad=None)
+        return loss
+
+
+class PSVI_No_IW(PSVI_Ablated):
+    r"""Single-sample training / multi-sample testing (reference :1411-1472).  With mc_samples == 1 the reference's
+    inner_elbo scores pseudo-point i against EVERY label z_j (logits.unsqueeze_(1) at :493-494 makes
+    Categorical.log_prob broadcast to [M, M]; the matmul with N f(v) weights column j by a_j): inner = sum_i sum_c A_c
+    nll(u_i, c) + kl with A_c = sum_{j: z_j = c} a_j.  Reproduced by expanding the pseudo-data to M C weighted rows."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.mc_samples = 1
+
+    def _inner_pseudo(self, u, z32, a):
+        C, M = int(self.nc), u.shape[0]
+        A = torch.zeros(C, device=a.device, dtype=a.dtype).index_add_(0, z32.long(), a)
+        z2 = torch.arange(C, device=u.device, dtype=torch.int32).repeat(M)
+        return u.repeat_interleave(C, 0).contiguous(), z2.contiguous(), A[z2.long()].contiguous()
+
+    def _collapse_pseudo(self, ubar, abar):
+        C, M = int(self.nc), self.u.shape[0]
+        return ubar.reshape(M, C, -1).sum(1), abar.reshape(M, C).sum(0)[self._z32().long()]
+
+    def inner_elbo(self, model=None, params=None, hyperopt=False):
+        model, desc, S = self._model_desc(model)
+        eng = self._stream(model)
+        u, _ = self._uv()
+        u_in, z_in, a_in = self._inner_pseudo(u, self._z32(), self._a())
+        val, g = eng.inner_grad(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], u_in, z_in, a_in)
+        self._last_inner = g
+        return val.float()
+
+    def evaluate(self, correction=True, mc_samples_eval=5, mc_samples_train=1, **kwargs):
+        self.mc_samples = mc_samples_eval
+        set_mc_samples(self.model, self.mc_samples)       # multi-sample for testing
+        try:
+            return super().evaluate(correction=True, **kwargs)
+        finally:
+            self.mc_samples = 1
+            set_mc_samples(self.model, mc_samples_train)  # single-sample for training
+
+
 PSVIEvaluate = _out_of_scope("PSVIEvaluate", "reference psvi_classes.py:1885")
 PSVI_regressor = _out_of_scope("PSVI_regressor", "reference psvi_classes.py:1940")
 PSVILearnV_regressor = _out_of_scope("PSVILearnV_regressor", "reference psvi_classes.py:2100")

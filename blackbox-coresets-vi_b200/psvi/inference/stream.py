@@ -312,6 +312,32 @@ class StreamEngine:
             pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
         return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
+    def outer_grad_ablated(self, phi, eps, xb, yb32, N, kappa=1.0, n_total=None):
+        """PSVI_Ablated.psvi_elbo (reference psvi_classes.py:1397-1408): mean_s (N/B) sum_b nll[s, b] - mean_s sampled_nkl_s --
+        no importance weights and no pseudo-data term (its direct partials wrt u, v are zero).  kappa / n_total: one rank's
+        share when the data rows are sharded (the nkl term is counted kappa times)."""
+        S, B, dev = self.S, xb.shape[0], xb.device
+        n_total = B if n_total is None else n_total
+        eps = self.fam.fix_eps(eps)
+        theta = self.fam.sample(phi, eps)
+        tbar, tb = torch.zeros(S, self.Pt, device=dev), torch.empty(S, self.Pt, device=dev)
+        ds = torch.zeros(S, device=dev, dtype=torch.float64)
+        for r0 in range(0, B, self.ROW_CHUNK):
+            xc, yc = xb[r0:r0 + self.ROW_CHUNK].contiguous(), yb32[r0:r0 + self.ROW_CHUNK].contiguous()
+            nc = torch.empty(S, xc.shape[0], device=dev)
+            cw = torch.full((S, xc.shape[0]), N / n_total / S, device=dev)
+            self.net.pass_(theta, None, xc, yc, cw, nll=nc, tbar=tb)
+            tbar += tb
+            ds += nc.double().sum(1)
+        nkl = self.fam.nkl(phi, eps, theta)
+        loss = (N / n_total) * ds.mean() - kappa * nkl.mean()
+        beta = torch.full((S,), -kappa / S, device=dev)
+        if hasattr(self.fam, "grad_with_nkl"):
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+        else:
+            pbar = self.fam.grad(phi, eps, tbar + beta[:, None] * self.fam.nkl_theta_grad(theta), 0.0, float(beta.sum()))
+        return loss.float(), pbar
+
     def hvp(self, phi, eps, u, z32, a, phidot):
         S, M, dev = self.S, u.shape[0], u.device
         eps = self.fam.fix_eps(eps)
@@ -322,7 +348,8 @@ class StreamEngine:
         return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
-    def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None, reduce_fn=None):
+    def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None, reduce_fn=None,
+               outer="psvi"):
         """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None).
         Sharded data term: pass this rank's rows with kappa = 1/world, n_total = rows over all ranks and a `reduce_fn` that
         all-reduces (loss, pbar, ubar, abar) -- the ONE exchange step of the bilevel step; the inner loop and
@@ -340,7 +367,11 @@ class StreamEngine:
             den = torch.sqrt(v + 1e-8) / sq2 + AEPS
             traj.append((phi, g, m, v))
             phi = phi - (lr / (1.0 - B1 ** (t + 1))) * (m / den)
-        loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total)
+        if outer == "ablated":
+            loss, pbar = self.outer_grad_ablated(phi, eps_all[T], xb, yb32, N, kappa=kappa, n_total=n_total)
+            ubar, abar = torch.zeros_like(u), torch.zeros_like(a)
+        else:
+            loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total)
         if reduce_fn is not None:
             loss, pbar, ubar, abar = reduce_fn(loss, pbar, ubar, abar)
         phi_T = phi

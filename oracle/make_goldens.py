@@ -337,6 +337,54 @@ def run_lenet_case(name="lenet_m10", M=10, S=3, T=2, B=6, init_sd=1e-2, lr0net=1
           out["ref64_eval"], "size", os.path.getsize(pth))
 
 
+def run_ablated_case(name, cls_name, S, H=30, M=10, T=4, B=32, init_sd=1e-2, lr0net=1e-3):
+    """PSVI_Ablated / PSVI_No_IW (psvi_classes.py:1388-1472): outer objective without importance weights; fp64."""
+    import psvi.inference.psvi_classes as rc
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = getattr(rc, cls_name)(**kw)
+        obj.run_psvi(**kw)
+    S = int(obj.mc_samples)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(21)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    params = list(obj.model.parameters())
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, lr0net=lr0net, noise_seed=8080, vmode=1, mu0=mu0, rho0=rho0,
+               u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64), xb=xb.numpy().copy(),
+               yb=yb.numpy().copy())
+    with NoiseFeeder(dims, S, 8080) as nf:
+        L = obj.psvi_elbo(xb, yb, model=obj.model)
+        gs = torch.autograd.grad(L, params)
+        out["ref64_outer_val"] = L.item()
+        out["ref64_outer_gparams"] = torch.cat([g.reshape(-1) for g in gs]).numpy()
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_nested_gu"], out["ref64_nested_gv"] = obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy()
+        out["ref64_nested_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "S", S, "forwards", out["n_forwards"], "outer", out["ref64_outer_val"], "nested_loss", out["ref64_nested_loss"],
+          "|gu|", np.abs(out["ref64_nested_gu"]).max(), "size", os.path.getsize(pth))
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for c in CASES:
@@ -352,6 +400,8 @@ def main():
         print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"],
               "size", os.path.getsize(p))
     run_fn2_case()
+    run_ablated_case("ablated_fn_hm", "PSVI_Ablated", S=5)
+    run_ablated_case("noiw_fn_hm", "PSVI_No_IW", S=5)      # PSVI_No_IW forces mc_samples = 1 for training
     run_lenet_case()
     run_hyper_case()
     blob = run_mfvi_case()

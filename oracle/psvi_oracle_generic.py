@@ -212,6 +212,19 @@ def outer_grad(fam, phi, eps, u, z, a, xb, yb, N):
     return loss, fam.grad(phi, eps, tb, 0.0, beta.sum()), xbar[:, :M].sum(0), gp @ nll[:, :M]
 
 
+def outer_grad_ablated(fam, phi, eps, xb, yb, N):
+    """PSVI_Ablated.psvi_elbo (psvi_classes.py:1397-1408): mean_s (N/B) sum_b nll[s, b] - mean_s sampled_nkl_s -- no importance
+    weights, no pseudo-data term; value and d/dphi (the direct partials wrt u and v are zero)."""
+    theta = fam.sample(phi, eps)
+    logits, cache = _net(fam).forward(theta, xb)
+    nll, p = po.nll_rows(logits, yb)
+    S, B = eps.shape[0], xb.shape[0]
+    loss = np.mean((N / B) * nll.sum(-1)) - np.mean(fam.nkl(phi, eps, theta))
+    tb, _ = _net(fam).backward(theta, cache, (N / B / S) * _q(p, yb))
+    tb = tb - (1.0 / S) * _nkl_theta_grad(fam, theta)
+    return loss, fam.grad(phi, eps, tb, 0.0, -1.0)
+
+
 def inner_hvp(fam, phi, eps, u, z, a, phidot):
     theta, thetad = fam.sample(phi, eps), fam.tangent(phi, phidot, eps)
     o, od, cache = _net(fam).dual_forward(theta, thetad, u)
@@ -222,24 +235,49 @@ def inner_hvp(fam, phi, eps, u, z, a, phidot):
     return fam.hvp(phi, phidot, eps, A_t, A_td), A_x.sum(0), (q * od).sum(-1).sum(0)
 
 
-def nested_step(fam, phi0, eps_inner, eps_outer, u, z, v, xb, yb, N, lr, vmode=1):
+def no_iw_expand(u, z, a, C):
+    """Quirk of inner_elbo with mc_samples == 1 (psvi_classes.py:493-494,497,505): logits [M, C] are unsqueezed at dim 1, so
+    Categorical(logits [M, 1, C]).log_prob(z [M]) broadcasts to [M, M] -- pseudo-point i is scored against EVERY label z_j --
+    and the matmul with N f(v) weights column j by a_j:  inner = sum_i sum_j a_j nll(u_i, z_j) + kl
+    = sum_i sum_c A_c nll(u_i, c) with A_c = sum_{j: z_j = c} a_j.  Restated as an ordinary weighted objective over M C rows."""
+    M = len(z)
+    A = np.bincount(z.astype(np.int64), weights=a, minlength=C)
+    z2 = np.tile(np.arange(C), M)
+    return np.repeat(u, C, 0), z2.astype(z.dtype), A[z2]
+
+
+def no_iw_collapse(u_bar2, a_bar2, z, C):
+    M = len(z)
+    return u_bar2.reshape(M, C, -1).sum(1), a_bar2.reshape(M, C).sum(0)[z.astype(np.int64)]
+
+
+def nested_step(fam, phi0, eps_inner, eps_outer, u, z, v, xb, yb, N, lr, vmode=1, outer="psvi", no_iw_classes=None):
+    """outer = "psvi" (PSVI.psvi_elbo) or "ablated" (PSVI_Ablated.psvi_elbo, psvi_classes.py:1388-1408);
+    no_iw_classes = C reproduces the mc_samples == 1 quirk of inner_elbo (see no_iw_expand)."""
     T = len(eps_inner)
     a = po.coreset_weights(v, N, vmode)
+    u_in, z_in, a_in = (u, z, a) if no_iw_classes is None else no_iw_expand(u, z, a, no_iw_classes)
     phi = phi0.copy()
     m, vv = np.zeros_like(phi), np.zeros_like(phi)
     traj, inner_losses = [], []
     for t in range(T):
-        val, g, _, _ = inner_grad(fam, phi, eps_inner[t], u, z, a)
+        val, g, _, _ = inner_grad(fam, phi, eps_inner[t], u_in, z_in, a_in)
         phi_new, m, vv = po.robust_adam_step(phi, g, m, vv, t + 1, lr)
         traj.append((phi, g, m, vv))
         inner_losses.append(val)
         phi = phi_new
-    loss, pbar, u_bar, a_bar = outer_grad(fam, phi, eps_outer, u, z, a, xb, yb, N)
+    if outer == "ablated":
+        loss, pbar = outer_grad_ablated(fam, phi, eps_outer, xb, yb, N)
+        u_bar, a_bar = np.zeros_like(u), np.zeros_like(a)
+    else:
+        loss, pbar, u_bar, a_bar = outer_grad(fam, phi, eps_outer, u, z, a, xb, yb, N)
     mbar, vbar = np.zeros_like(pbar), np.zeros_like(pbar)
     for t in range(T - 1, -1, -1):
         phi_t, g, m_t, v_t = traj[t]
         gbar, mbar, vbar = po.robust_adam_step_vjp(pbar, mbar, vbar, g, m_t, v_t, t + 1, lr)
-        h, hu, ha = inner_hvp(fam, phi_t, eps_inner[t], u, z, a, gbar)
+        h, hu, ha = inner_hvp(fam, phi_t, eps_inner[t], u_in, z_in, a_in, gbar)
+        if no_iw_classes is not None:
+            hu, ha = no_iw_collapse(hu, ha, z, no_iw_classes)
         pbar, u_bar, a_bar = pbar + h, u_bar + hu, a_bar + ha
     v_bar, _ = po.coreset_weights_vjp(v, N, vmode, a_bar)
     return dict(loss=loss, u_grad=u_bar, v_grad=v_bar, phi_T=phi, inner_losses=np.array(inner_losses))

@@ -86,6 +86,14 @@ class NoiseFeeder:
             self.history.append(self.rng.standard_normal((self.S, P)).astype(np.float32))
             self._pos = 0
         exp = self._shapes[self._call]
+        if self.S == 1 and not self._fullcov and tuple(shape) != exp:
+            # mc_samples == 1: the reference draws without the sample dimension (neural_net.py:164-170)
+            assert tuple(shape) == (exp[1], exp[2]) or (exp[1] == 1 and tuple(shape) == (exp[2],)), (tuple(shape), exp)
+            n = exp[1] * exp[2]
+            out = self.history[-1][0, self._pos:self._pos + n].reshape(tuple(shape))
+            self._pos += n
+            self._call = (self._call + 1) % len(self._shapes)
+            return torch.from_numpy(np.ascontiguousarray(out)).to(dtype=dtype, device=device)
         if self._fullcov:
             assert tuple(shape) == (exp[0], exp[2]), (tuple(shape), exp)
             shape_out = (exp[0], exp[2])

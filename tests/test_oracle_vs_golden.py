@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet")))
+               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw")))
 
 
 def rel_l2(a, b):
@@ -160,3 +160,25 @@ def test_fullcov_oracle_matches_reference_fn2():
                                        g["xt"], g["yt"], B)
     assert abs(acc - g["ref64_eval"][0]) < 1e-7
     np.testing.assert_allclose([nll, went, ness], g["ref64_eval"][1:4], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["ablated_fn_hm", "noiw_fn_hm"])
+def test_ablated_outer_objective_matches_reference(name):
+    """PSVI_Ablated / PSVI_No_IW (psvi_classes.py:1388-1472): outer objective mean_s data_nll - mean_s sampled_nkl (no importance
+    weights); PSVI_No_IW trains with mc_samples = 1.  fp64 reference run vs the generic oracle with outer="ablated"."""
+    from oracle import psvi_oracle_generic as pg
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, N = int(g["S"]), int(g["T"]), float(g["N"])
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    fam = pg.MeanField(dims)
+    phi0 = po.mu_rho_to_phi(g["mu0"], g["rho0"], dims)
+    val, gphi = pg.outer_grad_ablated(fam, phi0, eps[0], g["xb"], g["yb"], N)
+    assert abs(val - g["ref64_outer_val"]) <= 1e-9 * abs(val)
+    assert rel_l2(gphi, g["ref64_outer_gparams"]) < 1e-8
+    r = pg.nested_step(fam, phi0, eps[1:1 + T], eps[1 + T], g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N, float(g["lr0net"]),
+                       vmode=1, outer="ablated", no_iw_classes=dims[-1] if S == 1 else None)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-8 * abs(r["loss"])
+    assert rel_l2(r["phi_T"], g["ref64_nested_params"]) < 1e-9
+    assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-6
+    assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-6
