@@ -429,7 +429,7 @@ __global__ void lenet_head_kernel(const float* __restrict__ o, const float* __re
 // predictive metrics from per-sample logits [S][R][C] (psvi_classes.py:1072-1092): one CTA, fixed-order reduction
 __global__ void __launch_bounds__(256)
 logits_predict_kernel(const float* __restrict__ logits, const float* __restrict__ lw, int mode, const int* __restrict__ y, int S,
-                      int R, int C, float* __restrict__ out) {
+                      int R, int C, float* __restrict__ out, float* __restrict__ probs_out) {
   __shared__ float s_w[64], s_red[2][256];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -467,7 +467,9 @@ logits_predict_kernel(const float* __restrict__ logits, const float* __restrict_
     for (int c = 0; c < C; ++c) {
       tot += pr[c];
       if (pr[c] > best) { best = pr[c]; am = c; }
+      if (probs_out) probs_out[(size_t)r * C + c] = pr[c];
     }
+    if (!y) continue;
     const int lab = y[r];
     nll -= logf(fminf(fmaxf(pr[lab] / tot, 1.1920929e-07f), 1.f - 1.1920929e-07f));
     corr += (am == lab) ? 1.f : 0.f;
@@ -640,11 +642,11 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
 }
 
 int psvi_logits_predict(const float* logits, const float* log_weights, int32_t mode, const int32_t* yt, int32_t S, int32_t R,
-                        int32_t C, float* out, void* stream) {
-  PSVI_REQUIRE(logits && yt && out, PSVI_ERR_INVALID, "null pointer");
+                        int32_t C, float* out, float* probs_out, void* stream) {
+  PSVI_REQUIRE(logits && out && (yt || probs_out), PSVI_ERR_INVALID, "null pointer");
   PSVI_REQUIRE(S >= 1 && S <= 64 && C >= 1 && C <= 16 && R >= 1, PSVI_ERR_INVALID, "bad S / C / R");
   PSVI_REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || log_weights), PSVI_ERR_INVALID, "bad mode / missing log weights");
-  logits_predict_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, log_weights, mode, yt, S, R, C, out);
+  logits_predict_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, log_weights, mode, yt, S, R, C, out, probs_out);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

@@ -123,7 +123,7 @@ _SIGS = {
     "psvi_lenet_pass": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_logits_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_philox_normal": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]),
 }
@@ -413,10 +413,11 @@ def lenet_pass(S, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar
                                  _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))
 
 
-def logits_predict(logits, log_weights, mode, yt, out):
+def logits_predict(logits, log_weights, mode, yt, out, probs_out=None):
     S, R, Cc = logits.shape
     _count(1)
-    _check(lib().psvi_logits_predict(_p(logits), _p(log_weights), mode, _p(yt, torch.int32), S, R, Cc, _p(out), _stream()))
+    _check(lib().psvi_logits_predict(_p(logits), _p(log_weights), mode, _p(yt, torch.int32), S, R, Cc, _p(out), _p(probs_out),
+                                     _stream()))
 
 
 _fnl_ws = {}

@@ -105,8 +105,7 @@ class PSVI(object):
         self.elbos = []
         self.num_pseudo, self.mc_samples = (num_pseudo if not increment else increment_sizes[0]), mc_samples
         self.reset, self.reset_interval, self.learn_v, self.learn_z = reset, reset_interval, learn_v, learn_z
-        for flag, name in ((learn_z, "learn_z"), (prune, "prune"), (increment, "increment"),
-                           (retrain_on_coreset, "retrain_on_coreset"), (scoring_run, "scoring_run")):
+        for flag, name in ((learn_z, "learn_z"), (increment, "increment"), (scoring_run, "scoring_run")):
             if flag:
                 raise NotImplementedError(f"{name}=True is outside the hot path built so far (SURVEY.md section 8f)")
         with torch.no_grad():
@@ -116,6 +115,7 @@ class PSVI(object):
         self.init_dataset = init_dataset
         self.results = {}
         self.prune, self.increment, self.retrain_on_coreset = prune, increment, retrain_on_coreset
+        self.prune_interval, self.prune_sizes = prune_interval, prune_sizes
         self.lr0alpha, self.lr0net = lr0alpha, lr0net
         self.data_folder, self.results_folder = data_folder, results_folder
         self.chosen_indices = []
@@ -547,12 +547,18 @@ class PSVI(object):
         if self.trainer not in optimizers:
             raise NotImplementedError(f"--trainer {self.trainer} is outside the hot path (nested / hyper are built)")
         psvi_step = optimizers[self.trainer]
+        total_checkpts = list(range(self.num_epochs))[::max(int(log_every), 1)]
+        downsample = 1
+        lpit = total_checkpts[::downsample]     # iterations at which the predictive grid is logged (reference :888-890)
         t_start = time.time()
         log_resource = LogResource()
         for it in tqdm(range(self.num_epochs), disable=kwargs.get("quiet", False)):
             xbatch, ybatch = self._next_minibatch()
             if it % self.log_every == 0:
                 test_acc, test_nll, iw_ent, ness, v_ent = self.evaluate()
+                if (self.log_pseudodata and it in lpit
+                        and self.dnm not in {"MNIST", "FashionMNIST", "Cifar10", "adult", "phishing", "webspam"} and self.D == 2):
+                    grid_preds.append(self.pred_on_grid().detach().cpu().numpy().T)      # reference :903-909
                 with torch.no_grad():
                     nlls_psvi.append(test_nll.item())
                     accs_psvi.append(test_acc.item())
@@ -574,6 +580,34 @@ class PSVI(object):
                 self.weight_reset()
             psvi_step(xbatch, ybatch)
             log_resource.update()
+            # prune the coreset to smaller sizes (reference :935-944)
+            if self.prune and it > 0 and it % self.prune_interval == 0 and prune_idx < len(self.prune_sizes):
+                self.prune_coreset(to_size=self.prune_sizes[prune_idx], lr0v=lr0v, lr0net=lr0net)
+                prune_idx += 1
+                self.weight_reset()
+        # retrain the model on the extracted coreset only, for the same number of epochs (reference :969-997)
+        if self.retrain_on_coreset:
+            if not isinstance(self.model, MeanFieldMLP):
+                raise NotImplementedError("retrain_on_coreset covers the mean-field models (flat (mu, rho) parameter buffers)")
+            self.weight_reset()
+            flat = [torch.nn.Parameter(t) for t in self.model.flat()]      # share storage with the flat (mu, rho) buffers
+            opt_retrain = torch.optim.Adam(flat, lr0joint)
+            for it in tqdm(range(self.num_epochs), disable=kwargs.get("quiet", False)):
+                if it % self.log_every == 0:
+                    test_acc, test_nll, iw_ent, ness, v_ent = self.evaluate(correction=False)
+                    nlls_psvi.append(test_nll.item())
+                    accs_psvi.append(test_acc.item())
+                    core_idcs_psvi.append(self.num_pseudo)
+                    times.append(times[-1] + time.time() - t_start)
+                    vs.append(self.f(self.v.detach(), 0).clone().cpu().numpy())
+                    if iw_ent is not None:
+                        iws_entropy.append(iw_ent.item())
+                    if ness is not None:
+                        nesses.append(ness.item())
+                    if v_ent is not None:
+                        vs_entropy.append(v_ent.item())
+                opt_retrain.zero_grad()
+                self._retrain_step(opt_retrain, flat)
         resource_data = log_resource.get_resources()
         self.results["accs"] = accs_psvi
         self.results["nlls"] = nlls_psvi
@@ -699,7 +733,35 @@ class PSVI(object):
                 layer.reset_parameters_variational()   # in-place inits: the flat-buffer views stay valid
 
     def pred_on_grid(self, n_test_per_dim=250, correction=True, **kwargs):
-        raise NotImplementedError("pred_on_grid (plots) is outside the hot path (SURVEY.md section 8f item 3)")
+        """Predictive probabilities over the 2-d grid [-3, 4] x [-2, 3] (reference :1130-1175): importance-weighted mixture
+        under one noise draw.  Returns [n_test_per_dim**2, nc] (row-major over (x0, x1), as the reference's view(-1, 2))."""
+        model, desc, S = self._model_desc()
+        x0 = torch.linspace(-3, 4, n_test_per_dim)
+        x1 = torch.linspace(-2, 3, n_test_per_dim)
+        grid = torch.stack(torch.meshgrid(x0, x1, indexing="ij"), dim=-1).reshape(-1, 2).to(self.device).contiguous()
+        eng = self._stream(model)
+        u, _ = self._uv()
+        return eng.predict_probs(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], u, self._z32(), self._a(), grid,
+                                 correction=correction)
+
+    def prune_coreset(self, to_size, lr0v=1e-3, lr0net=1e-4):
+        """Prune the coreset to a smaller size by sampling points without replacement from f(v) (reference :1177-1193;
+        designed for the fixed-u methods)."""
+        self.num_pseudo = to_size
+        keep_v = torch.multinomial(self.f(self.v.detach(), 0), to_size, replacement=False)
+        self.v = torch.zeros_like(self.v[keep_v]).clone().detach().requires_grad_(True)
+        self.optim_v = torch.optim.Adam([self.v], lr0v)
+        self.u = torch.index_select(self.u.detach(), 0, keep_v).requires_grad_(True)
+        self.z = torch.index_select(self.z, 0, keep_v)
+        self.optim_u = torch.optim.Adam([self.u], self.optim_u.param_groups[0]["lr"])
+        self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
+
+    def _retrain_step(self, opt, params):
+        """One Adam step of the model on inner_elbo over the (fixed) coreset (reference :994-997)."""
+        self.inner_elbo(model=self.model)
+        g, P = self._last_inner, params[0].numel()
+        params[0].grad, params[1].grad = g[:P].clone(), g[P:].clone()
+        opt.step()
 
 
 class PSVILearnV(PSVI):

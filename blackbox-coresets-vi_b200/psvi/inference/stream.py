@@ -201,6 +201,12 @@ class MlpNet:
     def predict(self, theta, lw, mode, xt, yt, out):
         _native.net_predict(self.desc, theta, lw, mode, xt, yt, out)
 
+    def logits(self, theta, x):
+        S, C = theta.shape[0], self.desc.dims[self.desc.n_layers]
+        lg = torch.empty(S, x.shape[0], C, device=x.device)
+        _native.net_pass(self.desc, theta, None, x, torch.zeros(x.shape[0], device=x.device, dtype=torch.int32), None, logits=lg)
+        return lg
+
 
 class FnLargeNet:
     """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu).
@@ -217,10 +223,14 @@ class FnLargeNet:
     def pass_(self, theta, thetad, x, y, cw, **out):
         _native.fnl_pass(self.desc, self.precision, theta, thetad, x, y, cw, **out)
 
+    def logits(self, theta, x):
+        lg = torch.empty(self.S, x.shape[0], self.C, device=x.device)
+        _native.fnl_pass(self.desc, self.precision, theta, None, x, torch.zeros(x.shape[0], device=x.device, dtype=torch.int32),
+                         None, logits=lg)
+        return lg
+
     def predict(self, theta, lw, mode, xt, yt, out):
-        logits = torch.empty(self.S, xt.shape[0], self.C, device=xt.device)
-        _native.fnl_pass(self.desc, self.precision, theta, None, xt, yt, None, logits=logits)
-        _native.logits_predict(logits, lw, mode, yt, out)
+        _native.logits_predict(self.logits(theta, xt), lw, mode, yt, out)
 
 
 class LenetNet:
@@ -232,10 +242,13 @@ class LenetNet:
     def pass_(self, theta, thetad, x, y, cw, **out):
         _native.lenet_pass(self.S, theta, thetad, x, y, cw, **out)
 
+    def logits(self, theta, x):
+        lg = torch.empty(self.S, x.shape[0], 10, device=x.device)
+        _native.lenet_pass(self.S, theta, None, x, torch.zeros(x.shape[0], device=x.device, dtype=torch.int32), None, logits=lg)
+        return lg
+
     def predict(self, theta, lw, mode, xt, yt, out):
-        logits = torch.empty(self.S, xt.shape[0], 10, device=xt.device)
-        _native.lenet_pass(self.S, theta, None, xt, yt, None, logits=logits)
-        _native.logits_predict(logits, lw, mode, yt, out)
+        _native.logits_predict(self.logits(theta, xt), lw, mode, yt, out)
 
 
 class StreamEngine:
@@ -390,6 +403,25 @@ class StreamEngine:
             h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar)
             pbar, ubar, abar = pbar + h, ubar + hu, abar + ha
         return loss, ubar, abar, phi_T, (torch.stack(losses).float() if want_losses else None)
+
+    def predict_probs(self, phi, eps, u, z32, a, x, correction=True, chunk=8192):
+        """Predictive class probabilities of rows x under ONE noise slab (PSVI.pred_on_grid, psvi_classes.py:1130-1175):
+        importance-weighted mixture sum_s w_s softmax(logits_s) (w from the pseudo-data, sign quirk Q3) or the plain mean."""
+        eps = self.fam.fix_eps(eps)
+        theta = self.fam.sample(phi, eps)
+        lw = None
+        if correction:
+            nll = torch.empty(self.S, u.shape[0], device=x.device)
+            self.net.pass_(theta, None, u, z32, None, nll=nll)
+            lw = ((nll.double() @ a.double()) + self.fam.nkl(phi, eps, theta)).float().contiguous()
+        probs, out = [], torch.zeros(8, device=x.device)
+        for r0 in range(0, x.shape[0], chunk):
+            xc = x[r0:r0 + chunk].contiguous()
+            lg = self.net.logits(theta, xc)
+            pc = torch.empty(xc.shape[0], lg.shape[2], device=x.device)
+            _native.logits_predict(lg, lw, 0 if correction else 1, None, out, probs_out=pc)
+            probs.append(pc)
+        return torch.cat(probs)
 
     # ---- predictive pass (psvi_classes.py:1031-1108) -----------------------------------------------------------------
     def evaluate(self, phi, eps_slabs, u, z32, a, xt, yt32, batch, mode=0):

@@ -277,7 +277,8 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
                     int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
                     void* workspace, void* stream);
 int psvi_logits_predict(const float* logits, const float* log_weights, int32_t mode, const int32_t* yt, int32_t S, int32_t R,
-                        int32_t C, float* out, void* stream);
+                        int32_t C, float* out, float* probs_out /* [R][C] mixture per row, nullable; yt nullable then */,
+                        void* stream);
 
 /* ---- the mean-field family as fused maps over [S][P] slabs (theta layout), used by the streaming engine.  Replace
  * VIMixin.rsample / kl / sampled_nkl (psvi/models/neural_net.py:101-115,155-162) and what autograd accumulates into

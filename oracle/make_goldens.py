@@ -385,6 +385,43 @@ def run_ablated_case(name, cls_name, S, H=30, M=10, T=4, B=32, init_sd=1e-2, lr0
           "|gu|", np.abs(out["ref64_nested_gu"]).max(), "size", os.path.getsize(pth))
 
 
+def run_grid_case(name="grid_fn_hm", H=20, M=10, S=6, n=12, init_sd=5e-2):
+    """PSVI.pred_on_grid (psvi_classes.py:1130-1175): importance-weighted predictive probabilities over a 2-d grid, fp64."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=32, D=D, N=N, inner_it=2, trainer="nested", log_every=10, lr0u=1e-4,
+              lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0, architecture="fn", n_hidden=H,
+              n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="halfmoon", nc=nc,
+              data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    obj.model.to(torch.float64)
+    rng = np.random.default_rng(31)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=torch.float64)
+    obj.u = obj.u.detach().to(torch.float64)
+    obj.z = obj.z.to(torch.float64)
+    obj.N = 30.0     # keep the importance weights away from a one-hot vector so that the mixture is actually exercised
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=obj.N, S=S, M=M, n=n, noise_seed=6060, vmode=1, mu0=mu0, rho0=rho0,
+               u0=obj.u.numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64))
+    _orig_linspace = torch.linspace
+    torch.linspace = lambda *a, **k: _orig_linspace(*a, **k).double()
+    try:
+        with NoiseFeeder(dims, S, 6060) as nf:
+            out["ref64_grid_iw"] = obj.pred_on_grid(n_test_per_dim=n, correction=True).numpy().copy()
+            out["ref64_grid_mean"] = obj.pred_on_grid(n_test_per_dim=n, correction=False).numpy().copy()
+            out["n_forwards"] = len(nf.history)
+    finally:
+        torch.linspace = _orig_linspace
+    pth = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, out["ref64_grid_iw"].shape, out["ref64_grid_iw"][:2], "size", os.path.getsize(pth))
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for c in CASES:
@@ -403,6 +440,7 @@ def main():
     run_ablated_case("ablated_fn_hm", "PSVI_Ablated", S=5)
     run_ablated_case("noiw_fn_hm", "PSVI_No_IW", S=5)      # PSVI_No_IW forces mc_samples = 1 for training
     run_lenet_case()
+    run_grid_case()
     run_hyper_case()
     blob = run_mfvi_case()
     p = os.path.join(ROOT, "tests", "golden", "mfvi_subset_hm.npz")

@@ -207,3 +207,41 @@ def test_ablated_and_no_iw_match_reference(name):
     acc, nll, went, ness, vent = obj.evaluate()
     assert 0.0 <= acc.item() <= 1.0 and np.isfinite(nll.item())
     assert obj.model.n_samples() == S      # PSVI_No_IW evaluates with 5 samples and switches back to 1
+
+
+def test_pred_on_grid_matches_reference():
+    """PSVI.pred_on_grid (reference :1130-1175) against the reference's fp64 output with the same injected noise: importance-
+    weighted mixture and plain mean over a 12 x 12 grid."""
+    import os
+    from oracle.ref_import import NoiseFeeder
+    g = dict(np.load(os.path.join(GOLDEN, "grid_fn_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, n = int(g["S"]), int(g["n"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    g2 = dict(g, B=32, lr0net=1e-3)
+    obj = make_obj("x_hm", g2, dims, S, 2, eps, init_sd=5e-2)
+    obj.N = float(g["N"])
+    p_iw = obj.pred_on_grid(n_test_per_dim=n, correction=True).cpu().numpy()
+    p_mean = obj.pred_on_grid(n_test_per_dim=n, correction=False).cpu().numpy()
+    assert p_iw.shape == (n * n, 2)
+    np.testing.assert_allclose(p_iw, g["ref64_grid_iw"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(p_mean, g["ref64_grid_mean"], rtol=2e-4, atol=2e-5)
+
+
+def test_prune_and_retrain_on_coreset_run():
+    """run_psvi with prune=True (reference :935-944,1177-1193) and retrain_on_coreset=True (:969-997): the coreset shrinks to
+    the requested sizes, the retraining phase appends its own evaluations, and the model still classifies halfmoon."""
+    from psvi.experiments.experiments_utils import read_dataset
+    from psvi.inference.psvi_classes import PSVIFixedU
+    torch.manual_seed(0)
+    x, y, xt, yt, N, D, tr, te, nc = read_dataset("halfmoon", {"test_ratio": 0.2})
+    kw = dict(mc_samples=8, num_epochs=41, data_minibatch=128, D=D, N=N, inner_it=20, trainer="nested", log_every=10, lr0u=1e-3,
+              lr0net=1e-2, lr0v=1e-2, lr0joint=1e-2, init_args="subsample", init_sd=1e-3, num_pseudo=40, seed=0, architecture="fn",
+              n_hidden=30, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="halfmoon", nc=nc,
+              compute_weights_entropy=True, register_elbos=False, quiet=True, prune=True, prune_interval=15, prune_sizes=[30, 20],
+              retrain_on_coreset=True)
+    obj = PSVIFixedU(**kw)
+    res = obj.run_psvi(**kw)
+    assert obj.num_pseudo == 20 and obj.u.shape[0] == 20 and obj.v.shape[0] == 20 and obj.z.shape[0] == 20
+    assert res["csizes"][:5] == [40, 40, 30, 30, 20] and len(res["accs"]) == 10      # 5 PSVI + 5 retraining evaluations
+    assert res["accs"][-1] > 0.8 and all(np.isfinite(res["nlls"]))
