@@ -47,15 +47,16 @@ def _outer(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch):
     return gout[:2 * P].clone(), ug, vg, ag
 
 
-def cg_normaleq_native(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch, K, eta, tol=1e-10):
-    """CG on the normal equations (I - J)(I - J^T) x = (I - J) g  (reference :199-244), K iterations."""
-    hvp = _Hvp(psvi, desc, mu, rho, u, z32, v)
-    g, ug0, vg0, ag0 = _outer(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch)   # o_loss and its gradients
-    noise_a = psvi._noise(1)                                                    # w_mapped = fp_map(params, hparams)
+def _cg_normaleq(hvp, outer, new_noise, K, eta, tol=1e-10):
+    """CG on the normal equations (I - J)(I - J^T) x = (I - J) g  (reference :199-244), K iterations.
+    hvp(noise, vec) -> (H_phiphi vec, H_uphi vec, H_vphi vec, H_alphaphi vec); outer() -> (g, u_grad0, v_grad0, alpha_grad0);
+    new_noise() draws one noise slab (token) in the reference's consumption order."""
+    g, ug0, vg0, ag0 = outer()                    # o_loss and its gradients
+    noise_a = new_noise()                         # w_mapped = fp_map(params, hparams)
 
     def fresh():
-        psvi._noise(1)           # first Phi evaluation inside jvp(): its draw is discarded (hypergradients.py:308-311)
-        return psvi._noise(1)
+        new_noise()              # first Phi evaluation inside jvp(): its draw is discarded (hypergradients.py:308-311)
+        return new_noise()
 
     def A(x):
         t = eta * hvp(noise_a, x)[0]              # x - J^T x
@@ -77,18 +78,50 @@ def cg_normaleq_native(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch, K, eta, t
     return ug0 - eta * hu, vg0 - eta * hv, ag0 - eta * ha
 
 
-def fixed_point_native(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch, K, eta, tol=1e-10):
+def _fixed_point(hvp, outer, new_noise, K, eta, tol=1e-10):
     """Stochastic fixed-point iteration v <- J^T v + g (reference :83-140 with stochastic=True)."""
-    hvp = _Hvp(psvi, desc, mu, rho, u, z32, v)
-    g, ug0, vg0, ag0 = _outer(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch)
+    g, ug0, vg0, ag0 = outer()
     vs = torch.zeros_like(g)
     for _ in range(K):
         prev = vs
-        vs = vs - eta * hvp(psvi._noise(1), vs)[0] + g
+        vs = vs - eta * hvp(new_noise(), vs)[0] + g
         if float(torch.norm(vs - prev)) < tol:
             break
-    _, hu, hv, ha = hvp(psvi._noise(1), vs)
+    _, hu, hv, ha = hvp(new_noise(), vs)
     return ug0 - eta * hu, vg0 - eta * hv, ag0 - eta * ha
+
+
+def cg_normaleq_native(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch, K, eta, tol=1e-10):
+    hvp = _Hvp(psvi, desc, mu, rho, u, z32, v)
+    return _cg_normaleq(hvp, lambda: _outer(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch), lambda: psvi._noise(1), K, eta, tol)
+
+
+def fixed_point_native(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch, K, eta, tol=1e-10):
+    hvp = _Hvp(psvi, desc, mu, rho, u, z32, v)
+    return _fixed_point(hvp, lambda: _outer(psvi, desc, mu, rho, u, z32, v, xbatch, ybatch), lambda: psvi._noise(1), K, eta, tol)
+
+
+def hyper_stream(psvi, eng, S, phi, u, z32, a, xb, yb, K, eta, approx="CG_normaleq", tol=1e-10):
+    """The same solvers over the streaming engine (fn2, lenet, medium / large mean-field models): Hessian-vector products by
+    StreamEngine.hvp, the outer gradient by StreamEngine.outer_grad; dL/da is mapped to (dL/dv, dL/dalpha) by the caller's f."""
+    dev = phi.device
+
+    def to_v(abar):
+        vg, ag = psvi._v_grad_from_abar(abar)
+        return vg, (ag if ag is not None else torch.zeros(1, device=dev))
+
+    def hvp(eps, vec):
+        h, hu, ha = eng.hvp(phi, eps, u, z32, a, vec.contiguous())
+        return (h, hu) + to_v(ha)
+
+    def outer():
+        _, pbar, ubar, abar, _ = eng.outer_grad(phi, new_noise(), u, z32, a, xb, yb, float(psvi.N))
+        return (pbar, ubar) + to_v(abar)
+
+    def new_noise():
+        return psvi._noise_tensor(1, eng.Pt, S)[0]
+    solver = _cg_normaleq if approx == "CG_normaleq" else _fixed_point
+    return solver(hvp, outer, new_noise, K, eta, tol)
 
 
 def CG_normaleq(*args, **kwargs):

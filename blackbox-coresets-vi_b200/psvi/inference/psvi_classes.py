@@ -448,6 +448,8 @@ class PSVI(object):
         T = int(self.inner_it)
         self._zero_grads()
         model, desc, S = self._model_desc()
+        if self._use_stream(model) or (isinstance(model, MeanFieldMLP) and self._is_large_fn(model)):
+            return self._hyper_step_stream(model, S, xbatch, ybatch, K, linsys_lr, hypergrad_approx)
         mu, rho = model.flat()
         P = mu.numel()
         u, v = self._uv()
@@ -458,6 +460,37 @@ class PSVI(object):
                        self._alpha_value(), T, lr, _native.ADAM_HYPERGRAD, None)
         solver = cg_normaleq_native if hypergrad_approx == "CG_normaleq" else fixed_point_native
         ug, vg, ag = solver(self, desc, mu, rho, u, z32, v, xbatch, ybatch, K, linsys_lr)
+        self.u.grad = ug if self.u.grad is None else self.u.grad + ug
+        if self.learn_v:
+            self.v.grad = vg if self.v.grad is None else self.v.grad + vg
+        if self.alpha is not None and self.alpha.requires_grad:
+            self.alpha.grad = ag
+        self._step_outer_optimisers()
+        ll = self.psvi_elbo(xbatch, ybatch, model=self.model)
+        return ll.item()
+
+    def _hyper_step_stream(self, model, S, xbatch, ybatch, K, linsys_lr, hypergrad_approx):
+        """hyper_step through the streaming engine: T plain steps with the hypergrad.DifferentiableAdam arithmetic
+        (psvi/hypergrad/diff_optimizers.py:184-213: u += 1e-12, sqrt(u / (1 - beta2^t)) + eps, no mask), then the implicit
+        hypergradient solver over StreamEngine.hvp / outer_grad."""
+        from psvi.hypergrad.hypergradients import hyper_stream
+        eng = self._stream(model)
+        T, lr = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"])
+        u, _ = self._uv()
+        z32, a = self._z32(), self._a()
+        xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
+        yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        phi = eng.fam.get_phi()
+        m, uu = torch.zeros_like(phi), torch.zeros_like(phi)
+        eps_all = self._noise_tensor(T, eng.Pt, S)
+        for t in range(T):
+            _, g = eng.inner_grad(phi, eps_all[t], u, z32, a)
+            m = 0.9 * m + (1.0 - 0.9) * g
+            uu = 0.999 * uu + (1.0 - 0.999) * g * g + 1e-12
+            phi = phi - lr * (m / (1.0 - 0.9 ** (t + 1)) / (torch.sqrt(uu / (1.0 - 0.999 ** (t + 1))) + 1e-8))
+        ug, vg, ag = hyper_stream(self, eng, S, phi, u, z32, a, xb, yb, K, linsys_lr, hypergrad_approx)
+        eng.fam.set_phi(phi)
+        ug = ug.to(self.u.dtype).reshape(self.u.shape)
         self.u.grad = ug if self.u.grad is None else self.u.grad + ug
         if self.learn_v:
             self.v.grad = vg if self.v.grad is None else self.v.grad + vg

@@ -140,9 +140,11 @@ def test_flow_psvi_cli_writes_results(tmp_path):
     assert os.path.exists(tmp_path / "r.json")
 
 
-def test_hyper_step_matches_reference():
+@pytest.mark.parametrize("stream", [False, True])
+def test_hyper_step_matches_reference(stream):
     """--trainer hyper: PSVI.hyper_step + CG_normaleq (reference psvi_classes.py:602-687, hypergradients.py:199-244) with
-    the reference's noise-consumption order (T inner, outer, w_mapped, 2 per JVP, final outer)."""
+    the reference's noise-consumption order (T inner, outer, w_mapped, 2 per JVP, final outer); through the fused engine
+    and through the streaming engine (the path fn2 / lenet / large models take)."""
     from oracle.ref_import import NoiseFeeder
     from psvi.experiments.experiments_utils import read_dataset
     from psvi.inference.psvi_classes import ExternalNoise, PSVILearnV
@@ -165,6 +167,8 @@ def test_hyper_step_matches_reference():
     obj.z = torch.as_tensor(g["z"]).float().cuda()
     obj.scheduler_optim_net = None
     obj.noise_source = ExternalNoise(eps)
+    if stream:
+        obj._ws[("force_stream", id(obj.model))] = True
     xb, yb = torch.as_tensor(g["xb"]).float().cuda(), torch.as_tensor(g["yb"]).cuda()
     ll = obj.hyper_step(xb, yb, K=K, linsys_lr=float(g["linsys_lr"]))
     assert obj.noise_source.pos == int(g["n_forwards"])            # same number of forwards as the reference
