@@ -39,9 +39,11 @@ struct GemmP {
   int batch, m_tiles, n_tiles, kc;              // kc = K / GK
   int M_valid, N_valid;
   int a_brows, b_brows;                         // rows per batch in the A / B tensor maps (0: operand shared by all batches)
-  const float* bias; long long bias_bs;         // + bias[b * bias_bs + n]
-  int relu;
+  const float* bias; long long bias_bs;         // + bias[b * bias_bs + n]   (bias_row: + bias[b * bias_bs + m])
+  int bias_row, relu;
   const void* mask; long long mask_bs; int mask_ld;             // * (mask[b][m][n] > 0)   (bf16, or the fp32 hi part)
+  int mask_t;                                   // the mask array is [b][n][m]: read it transposed
+  int n_pad;                                    // > N_valid: columns N_valid .. n_pad - 1 are processed too and written as zeros
   float* of; long long of_bs; int of_ld;                       // fp32 out [b][m][n], m < M_valid, n < N_valid
   void *ob, *ob_lo; long long ob_bs; int ob_ld; int ob_rows;    // operand out [b][m][n], m < ob_rows (zeros for m >= M_valid)
   void *obt, *obt_lo; long long obt_bs; int obt_ld;             // transposed operand out [b][n][m], m < ob_rows
@@ -183,8 +185,12 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n0 = nt * GN + part * 64 + g * 32;
         float v[32];
         tmem_ld32(lane_addr + buf * GN + part * 64 + g * 32, v);
-        if (n0 < p.N_valid) {
-          if (p.bias) {
+        if (n0 < (p.n_pad > p.N_valid ? p.n_pad : p.N_valid)) {
+          if (p.bias && p.bias_row) {
+            const float br = vm ? __ldg(p.bias + (long long)b * p.bias_bs + m) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += br;
+          } else if (p.bias) {
             const float* bp = p.bias + (long long)b * p.bias_bs + n0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N_valid) ? __ldg(bp + j) : 0.f;
@@ -193,7 +199,16 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask && vm) {   // N_valid is a multiple of 32 whenever a mask / operand output is used
+          if (p.mask && vm && p.mask_t) {   // mask[b][n][m]: lanes read consecutive m (coalesced)
+            const long long mo = (long long)b * p.mask_bs + (long long)n0 * p.mask_ld + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j >= p.N_valid) continue;
+              const float mk = X3 ? __ldg(static_cast<const float*>(p.mask) + mo + (long long)j * p.mask_ld)
+                                  : __bfloat162float(static_cast<const __nv_bfloat16*>(p.mask)[mo + (long long)j * p.mask_ld]);
+              if (!(mk > 0.f)) v[j] = 0.f;
+            }
+          } else if (p.mask && vm) {   // N_valid is a multiple of 32 whenever a mask / operand output is used
             if (X3) {
               const float4* mp = reinterpret_cast<const float4*>(static_cast<const float*>(p.mask) + (long long)b * p.mask_bs +
                                                                  (long long)m * p.mask_ld + n0);
@@ -224,6 +239,11 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (!vm) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (p.n_pad > p.N_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j >= p.N_valid) v[j] = 0.f;
           }
           if (p.of && vm) {
             float* op = p.of + (long long)b * p.of_bs + (long long)m * p.of_ld + n0;
@@ -583,7 +603,7 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   p.a_brows = A.brows;
   p.b_brows = B.brows;
   p.m_tiles = (p.M_valid + GM - 1) / GM;
-  p.n_tiles = (p.N_valid + GN - 1) / GN;
+  p.n_tiles = ((p.n_pad > p.N_valid ? p.n_pad : p.N_valid) + GN - 1) / GN;
   if ((p.ob || p.obt) && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
@@ -671,10 +691,12 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   };
   // ---- primal forward: h = relu(X W1^T + b1);  o = h W2^T
   {
+    // roles swapped (C^T = W1 X^T, output through the transposed-store path): the row-major store of h is then coalesced
+    // (lanes = consecutive hidden units) and the bias is one scalar per thread
     GemmP p = z;
-    p.M_valid = R; p.N_valid = H; p.bias = theta + o_b1; p.bias_bs = P; p.relu = 1;
-    set_ob(p, w.hh, H);
-    if ((rc = launch_gemm<X3>(opX, opW1, p, sms, st))) return rc;
+    p.M_valid = H; p.N_valid = R; p.n_pad = Rp; p.bias = theta + o_b1; p.bias_bs = P; p.bias_row = 1; p.relu = 1;
+    p.obt = at(w.hh, H, false); p.obt_lo = at(w.hh, H, true); p.obt_bs = hh_bs; p.obt_ld = 2 * H; p.ob_rows = H;
+    if ((rc = launch_gemm<X3>(opW1, opX, p, sms, st))) return rc;
     p = z;
     p.M_valid = R; p.N_valid = CW; p.of = w.o; p.of_bs = (long long)Rp * CW; p.of_ld = CW;
     if ((rc = launch_gemm<X3>(opH, opW2, p, sms, st))) return rc;
@@ -716,8 +738,8 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   }
   // ---- dual pass: tangent forward
   {
-    GemmP p = z;      // hdot = (X W1dot^T + b1dot) * (h > 0)
-    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P;
+    GemmP p = z;      // hdot = (X W1dot^T + b1dot) * (h > 0)   (not role-swapped: the transposed mask read costs more than
+    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P;     //  the coalesced store saves -- measured)
     set_mask_h(p); set_ob(p, w.hh, 0);
     if ((rc = launch_gemm<X3>(opX, opW1d, p, sms, st))) return rc;
     p = z;            // odot = hdot W2^T + h W2dot^T
