@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(256)
 conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__ sel, const float* __restrict__ in, size_t ss,
                        int R, int rows_per_chunk, float* __restrict__ part) {
   constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NOUT = CO * CI * 25, NJ = (NOUT + 255) / 256;
-  __shared__ float s_a[CO * HO * HO], s_in[CI * HP * HP];
+  constexpr int HPP = HP | 1;   // odd row pitch of the padded input: (ky, kx) taps of one warp fall into distinct banks
+  __shared__ float s_a[CO * HO * HO], s_in[CI * HP * HPP], s_pb[CO * HQ * HQ];
+  __shared__ uint8_t s_sel[CO * HQ * HQ];
   const int chunk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const int r0 = chunk * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
   float acc[NJ], bacc[2] = {0.f, 0.f};   // bias gradients: warp w owns channels w and w + 8
@@ -189,24 +191,30 @@ conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__
     const int oo = o < NOUT ? o : 0;
     const int co = oo / (CI * 25), ci = (oo / 25) % CI, ky = (oo % 25) / 5, kx = oo % 5;
     a_off[j] = co * HO * HO;
-    i_off[j] = (ci * HP + ky) * HP + kx;
+    i_off[j] = (ci * HP + ky) * HPP + kx;
   }
   for (int r = r0; r < r1; ++r) {
     const float* ip = in + (size_t)s * ss + (size_t)r * CI * HIN * HIN;
     for (int i = tid; i < CI * HP * HP; i += 256) {
-      const int c = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
-      s_in[i] = (yy >= 0 && yy < HIN && xx >= 0 && xx < HIN) ? ip[(c * HIN + yy) * HIN + xx] : 0.f;
+      const int c = i / (HP * HP), yp = (i / HP) % HP, xp = i % HP, yy = yp - PAD, xx = xp - PAD;
+      s_in[(c * HP + yp) * HPP + xp] = (yy >= 0 && yy < HIN && xx >= 0 && xx < HIN) ? ip[(c * HIN + yy) * HIN + xx] : 0.f;
     }
     const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
-    for (int i = tid; i < CO * HO * HO; i += 256) {   // the pooled adjoint scattered to full resolution, built in one pass
+    for (int i = tid; i < CO * HQ * HQ; i += 256) {   // pooled adjoint + selection code: coalesced, once
+      s_pb[i] = pb[pbase + i];
+      s_sel[i] = sel[pbase + i];
+    }
+    __syncthreads();
+    for (int i = tid; i < CO * HO * HO; i += 256) {   // scattered to full resolution
       const int co = i / (HO * HO), y = (i / HO) % HO, x = i % HO;
-      const int q = (co * HQ + (y >> 1)) * HQ + (x >> 1), c = sel[pbase + q];
-      s_a[i] = ((c & 4) && (c & 3) == ((y & 1) * 2 + (x & 1))) ? pb[pbase + q] : 0.f;
+      const int q = (co * HQ + (y >> 1)) * HQ + (x >> 1), c = s_sel[q];
+      s_a[i] = ((c & 4) && (c & 3) == ((y & 1) * 2 + (x & 1))) ? s_pb[q] : 0.f;
     }
     __syncthreads();
     for (int y = 0; y < HO; ++y)
+#pragma unroll 2
       for (int x = 0; x < HO; ++x) {
-        const int pa = y * HO + x, pi = y * HP + x;
+        const int pa = y * HO + x, pi = y * HPP + x;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[j] = fmaf(s_a[a_off[j] + pa], s_in[i_off[j] + pi], acc[j]);
       }
@@ -357,7 +365,7 @@ lin_bwd_weight_kernel(const float* __restrict__ y, const float* __restrict__ x, 
   int col[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) col[c] = tid + 128 * c;
-#pragma unroll 2
+#pragma unroll 8
   for (int r = 0; r < R; ++r) {
     const float4 yv = *reinterpret_cast<const float4*>(sy + r * 4);
     float xv[4];
