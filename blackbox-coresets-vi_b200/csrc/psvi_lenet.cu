@@ -276,18 +276,31 @@ lin_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     const float b = bias ? bias[(size_t)s * LN_P + o] : 0.f;
 #pragma unroll
     for (int k = 0; k < RT; ++k) acc[k] = b;
+    // (IN is a multiple of 4 for every layer of the stack: 400, 120, 84; eight weights are in flight per batch)
     const float* wa = w1 + (size_t)s * LN_P + (size_t)o * IN;
-    for (int i = 0; i < IN; ++i) {
-      const float w = wa[i];
+    for (int i0 = 0; i0 < IN; i0 += 8) {
+      float wv[8];
 #pragma unroll
-      for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx1[k * IN + i], w, acc[k]);
+      for (int e = 0; e < 8; ++e) wv[e] = i0 + e < IN ? wa[i0 + e] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (i0 + e >= IN) break;
+#pragma unroll
+        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx1[k * IN + i0 + e], wv[e], acc[k]);
+      }
     }
     if (x2) {
       const float* wb = w2 + (size_t)s * LN_P + (size_t)o * IN;
-      for (int i = 0; i < IN; ++i) {
-        const float w = wb[i];
+      for (int i0 = 0; i0 < IN; i0 += 8) {
+        float wv[8];
 #pragma unroll
-        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx2[k * IN + i], w, acc[k]);
+        for (int e = 0; e < 8; ++e) wv[e] = i0 + e < IN ? wb[i0 + e] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (i0 + e >= IN) break;
+#pragma unroll
+          for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx2[k * IN + i0 + e], wv[e], acc[k]);
+        }
       }
     }
 #pragma unroll
@@ -324,14 +337,22 @@ lin_bwd_data_kernel(const float* __restrict__ y1, const float* __restrict__ w1, 
     for (int k = 0; k < RT; ++k) acc[k] = 0.f;
     const float* wa = w1 + (size_t)s * LN_P + i;
     const float* wb = w2 ? w2 + (size_t)s * LN_P + i : nullptr;
-    for (int o = 0; o < OUT; ++o) {
-      const float w = wa[(size_t)o * IN];
+    for (int o0 = 0; o0 < OUT; o0 += 8) {   // eight weights (and eight tangent weights) in flight per batch
+      float wv[8], vv[8];
 #pragma unroll
-      for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy1[k * OUT + o], w, acc[k]);
-      if (wb) {
-        const float v = wb[(size_t)o * IN];
+      for (int e = 0; e < 8; ++e) {
+        wv[e] = o0 + e < OUT ? wa[(size_t)(o0 + e) * IN] : 0.f;
+        vv[e] = (wb && o0 + e < OUT) ? wb[(size_t)(o0 + e) * IN] : 0.f;
+      }
 #pragma unroll
-        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy2[k * OUT + o], v, acc[k]);
+      for (int e = 0; e < 8; ++e) {
+        if (o0 + e >= OUT) break;
+#pragma unroll
+        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy1[k * OUT + o0 + e], wv[e], acc[k]);
+        if (wb) {
+#pragma unroll
+          for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy2[k * OUT + o0 + e], vv[e], acc[k]);
+        }
       }
     }
 #pragma unroll
@@ -365,18 +386,23 @@ lin_bwd_weight_kernel(const float* __restrict__ y, const float* __restrict__ x, 
   int col[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) col[c] = tid + 128 * c;
-#pragma unroll 8
-  for (int r = 0; r < R; ++r) {
-    const float4 yv = *reinterpret_cast<const float4*>(sy + r * 4);
-    float xv[4];
+  for (int r0 = 0; r0 < R; r0 += 8) {   // eight rows per batch: all 32 loads are issued before the first FMA needs one
+    float xv[8][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) xv[c] = col[c] < IN ? xs[(size_t)r * IN + col[c]] : 0.f;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      acc[c][0] = fmaf(yv.x, xv[c], acc[c][0]);
-      acc[c][1] = fmaf(yv.y, xv[c], acc[c][1]);
-      acc[c][2] = fmaf(yv.z, xv[c], acc[c][2]);
-      acc[c][3] = fmaf(yv.w, xv[c], acc[c][3]);
+      for (int c = 0; c < 4; ++c) xv[i][c] = (r0 + i < R && col[c] < IN) ? xs[(size_t)(r0 + i) * IN + col[c]] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (r0 + i >= R) break;
+      const float4 yv = *reinterpret_cast<const float4*>(sy + (r0 + i) * 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[c][0] = fmaf(yv.x, xv[i][c], acc[c][0]);
+        acc[c][1] = fmaf(yv.y, xv[i][c], acc[c][1]);
+        acc[c][2] = fmaf(yv.z, xv[i][c], acc[c][2]);
+        acc[c][3] = fmaf(yv.w, xv[i][c], acc[c][3]);
+      }
     }
   }
 #pragma unroll
