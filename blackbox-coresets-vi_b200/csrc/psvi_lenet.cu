@@ -30,169 +30,258 @@ constexpr int N_CHUNKS = 64;   // row chunks of the conv weight-gradient kernels
 // out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
 // sel = argmax (first maximum in row-major window order, as torch's max_pool2d) | (max > 0) << 2;
 // tangent: the same selection applied to conv(in1, w1) + conv(in2, w2) + bias (all of them tangent quantities).
-// One CTA per (row, sample); a thread owns one pooling window of one output channel: the 6x6 input patch and the 25 weights
-// of a channel pair live in registers for 100 FMAs (0.6 shared-memory loads per FMA instead of 2), and the pooling is
-// thread-local, so the full-resolution map is never materialised.
-template <int CI, int CO, int HIN, int PAD, int NT>
-__global__ void __launch_bounds__(NT)
+// One CTA per (IMGS rows, sample); a thread owns one pooling window of COG output channels: the 6x6 input patch of an input
+// channel is read once (18 64-bit loads) and reused for COG x 100 FMAs, the 25 (padded to 28) weights of a channel pair come in
+// as 7 warp-broadcast 128-bit loads, and the pooling is thread-local, so the full-resolution map is never materialised.
+constexpr int WPAD = 28;   // taps of one (co, ci) filter in shared memory, padded for 128-bit loads
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COG>
+struct ConvFwdCfg {
+  static constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NIN = CI * HP * HP, NWP = CO * CI * WPAD;
+  static constexpr int TPI = (CO / COG) * HQ * HQ, NT = (IMGS * TPI + 31) / 32 * 32;
+  static constexpr size_t SMEM = (size_t)(2 * IMGS * NIN + 2 * NWP) * sizeof(float);
+};
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COG>
+__global__ void __launch_bounds__((ConvFwdCfg<CI, CO, HIN, PAD, IMGS, COG>::NT))
 conv_pool_fwd_kernel(const float* __restrict__ in1, size_t ss1, const float* __restrict__ w1, const float* __restrict__ in2,
                      size_t ss2, const float* __restrict__ w2, const float* __restrict__ bias, int R, uint8_t* sel,
                      int tangent, float* __restrict__ out) {
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25;
-  __shared__ float s_in1[CI * HP * HP], s_in2[CI * HP * HP], s_w1[NW], s_w2[NW];
-  const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
-  const float* i1 = in1 + (size_t)s * ss1 + (size_t)r * CI * HIN * HIN;
-  const float* i2 = in2 ? in2 + (size_t)s * ss2 + (size_t)r * CI * HIN * HIN : nullptr;
-  for (int i = tid; i < CI * HP * HP; i += NT) {
-    const int ci = i / (HP * HP), yy = (i / HP) % HP - PAD, xx = i % HP - PAD;
-    const bool ok = yy >= 0 && yy < HIN && xx >= 0 && xx < HIN;
-    s_in1[i] = ok ? i1[(ci * HIN + yy) * HIN + xx] : 0.f;
-    s_in2[i] = (ok && i2) ? i2[(ci * HIN + yy) * HIN + xx] : 0.f;
+  using C = ConvFwdCfg<CI, CO, HIN, PAD, IMGS, COG>;
+  constexpr int HP = C::HP, HQ = C::HQ, NIN = C::NIN, NWP = C::NWP, TPI = C::TPI, NT = C::NT;
+  static_assert(HP % 2 == 0 && NIN % 4 == 0 && CO % COG == 0, "alignment of the vector loads");
+  extern __shared__ __align__(16) float smem_f[];
+  float* s_in1 = smem_f;               // [IMGS][CI][HP][HP]
+  float* s_in2 = s_in1 + IMGS * NIN;
+  float* s_w1 = s_in2 + IMGS * NIN;    // [CO][CI][WPAD]
+  float* s_w2 = s_w1 + NWP;
+  const int s = blockIdx.y, tid = threadIdx.x, r_base = blockIdx.x * IMGS;
+  for (int i = tid; i < IMGS * NIN; i += NT) {
+    const int img = i / NIN, j = i % NIN, r = r_base + img;
+    const int ci = j / (HP * HP), yy = (j / HP) % HP - PAD, xx = j % HP - PAD;
+    const bool ok = r < R && yy >= 0 && yy < HIN && xx >= 0 && xx < HIN;
+    const size_t off = (size_t)r * CI * HIN * HIN + (ci * HIN + yy) * HIN + xx;
+    s_in1[i] = ok ? in1[(size_t)s * ss1 + off] : 0.f;
+    s_in2[i] = (ok && in2) ? in2[(size_t)s * ss2 + off] : 0.f;
   }
-  for (int i = tid; i < NW; i += NT) {
-    s_w1[i] = w1[(size_t)s * LN_P + i];
-    s_w2[i] = w2 ? w2[(size_t)s * LN_P + i] : 0.f;
+  for (int i = tid; i < NWP; i += NT) {
+    const int f = i / WPAD, t = i % WPAD;
+    s_w1[i] = t < 25 ? w1[(size_t)s * LN_P + f * 25 + t] : 0.f;
+    s_w2[i] = (t < 25 && w2) ? w2[(size_t)s * LN_P + f * 25 + t] : 0.f;
   }
   __syncthreads();
-  const size_t ob = ((size_t)s * R + r) * (CO * HQ * HQ);
-  for (int task = tid; task < CO * HQ * HQ; task += NT) {
-    const int co = task / (HQ * HQ), py = (task / HQ) % HQ, px = task % HQ;
-    const float b0 = bias ? bias[(size_t)s * LN_P + co] : 0.f;
-    float acc[4] = {b0, b0, b0, b0};
+  const int img = tid / TPI, rem = tid % TPI, r = r_base + img;
+  if (img >= IMGS || r >= R) return;
+  const int g = rem / (HQ * HQ), py = (rem / HQ) % HQ, px = rem % HQ;
+  float acc[COG][4];
+#pragma unroll
+  for (int c = 0; c < COG; ++c) {
+    const float b0 = bias ? bias[(size_t)s * LN_P + g * COG + c] : 0.f;
+    acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = b0;
+  }
 #pragma unroll 1
-    for (int term = 0; term < 2; ++term) {
-      if (term == 1 && !i2) break;
-      const float* sin = term ? s_in2 : s_in1;
-      const float* sw = term ? s_w2 : s_w1;
+  for (int term = 0; term < 2; ++term) {
+    if (term == 1 && !in2) break;
+    const float* sin = (term ? s_in2 : s_in1) + img * NIN;
+    const float* sw = term ? s_w2 : s_w1;
 #pragma unroll 1
-      for (int ci = 0; ci < CI; ++ci) {
-        const float* a = sin + (ci * HP + 2 * py) * HP + 2 * px;
-        const float* w = sw + (co * CI + ci) * 25;
-        float pt[6][6], wv[25];
+    for (int ci = 0; ci < CI; ++ci) {
+      const float* a = sin + (ci * HP + 2 * py) * HP + 2 * px;
+      float pt[6][6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) { pt[i][j] = a[i * HP + j]; KEEP_IN_REG(pt[i][j]); }
+        for (int j = 0; j < 3; ++j) {
+          const float2 v = *reinterpret_cast<const float2*>(a + i * HP + 2 * j);
+          pt[i][2 * j] = v.x;
+          pt[i][2 * j + 1] = v.y;
+        }
 #pragma unroll
-        for (int i = 0; i < 25; ++i) { wv[i] = w[i]; KEEP_IN_REG(wv[i]); }
+      for (int c = 0; c < COG; ++c) {
+        const float4* w4 = reinterpret_cast<const float4*>(sw + ((g * COG + c) * CI + ci) * WPAD);
+        float wv[WPAD];
+#pragma unroll
+        for (int i = 0; i < WPAD / 4; ++i) {
+          const float4 v = w4[i];
+          wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
+        }
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
             const float wk = wv[ky * 5 + kx];
-            acc[0] = fmaf(pt[ky][kx], wk, acc[0]);
-            acc[1] = fmaf(pt[ky][kx + 1], wk, acc[1]);
-            acc[2] = fmaf(pt[ky + 1][kx], wk, acc[2]);
-            acc[3] = fmaf(pt[ky + 1][kx + 1], wk, acc[3]);
+            acc[c][0] = fmaf(pt[ky][kx], wk, acc[c][0]);
+            acc[c][1] = fmaf(pt[ky][kx + 1], wk, acc[c][1]);
+            acc[c][2] = fmaf(pt[ky + 1][kx], wk, acc[c][2]);
+            acc[c][3] = fmaf(pt[ky + 1][kx + 1], wk, acc[c][3]);
           }
       }
     }
+  }
+  const size_t ob = ((size_t)s * R + r) * (CO * HQ * HQ);
+#pragma unroll
+  for (int c = 0; c < COG; ++c) {
+    const size_t o = ob + ((g * COG + c) * HQ + py) * HQ + px;
     if (!tangent) {
-      float best = fmaxf(acc[0], 0.f);
+      float best = fmaxf(acc[c][0], 0.f);
       int k = 0;
-      if (fmaxf(acc[1], 0.f) > best) { best = fmaxf(acc[1], 0.f); k = 1; }
-      if (fmaxf(acc[2], 0.f) > best) { best = fmaxf(acc[2], 0.f); k = 2; }
-      if (fmaxf(acc[3], 0.f) > best) { best = fmaxf(acc[3], 0.f); k = 3; }
-      sel[ob + task] = (uint8_t)(k | ((best > 0.f) ? 4 : 0));
-      out[ob + task] = best;
+      if (fmaxf(acc[c][1], 0.f) > best) { best = fmaxf(acc[c][1], 0.f); k = 1; }
+      if (fmaxf(acc[c][2], 0.f) > best) { best = fmaxf(acc[c][2], 0.f); k = 2; }
+      if (fmaxf(acc[c][3], 0.f) > best) { best = fmaxf(acc[c][3], 0.f); k = 3; }
+      sel[o] = (uint8_t)(k | ((best > 0.f) ? 4 : 0));
+      out[o] = best;
     } else {
-      const int c = sel[ob + task], k = c & 3;
-      const float v = k == 0 ? acc[0] : (k == 1 ? acc[1] : (k == 2 ? acc[2] : acc[3]));
-      out[ob + task] = (c & 4) ? v : 0.f;
+      const int cd = sel[o], k = cd & 3;
+      const float v = k == 0 ? acc[c][0] : (k == 1 ? acc[c][1] : (k == 2 ? acc[c][2] : acc[c][3]));
+      out[o] = (cd & 4) ? v : 0.f;
     }
   }
 }
 
 // d/d(input map) of the fused conv + ReLU + pool: the pooled adjoints pb1 (and pb2) are scattered to full resolution through
 // the selection code into a zero-padded map, then out[ci][y][x] = sum_co sum_k a1[co][y+PAD-ky][x+PAD-kx] w1[co][ci][ky][kx]
-// (+ the same with a2, w2).  A thread owns a 2x2 block of one input channel (6x6 adjoint patch + 25 weights in registers per
-// output channel).
-template <int CI, int CO, int HIN, int PAD, int NT>
-__global__ void __launch_bounds__(NT)
+// (+ the same with a2, w2).  A thread owns a 2x2 block of ALL CI input channels of one image: the 6x6 adjoint patch of an
+// output channel is read once (18 64-bit loads) for CI x 100 FMAs; the output channels are staged COCH at a time.
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COCH>
+struct ConvBwdCfg {
+  static constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, LP = 4 - PAD, HA = HO + 2 * LP, HB = HIN / 2;
+  static constexpr int NA = COCH * HA * HA, NWP = CO * CI * WPAD, TPI = HB * HB, NT = (IMGS * TPI + 31) / 32 * 32;
+  static constexpr size_t SMEM = (size_t)(IMGS * NA + NWP) * sizeof(float);
+};
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COCH>
+__global__ void __launch_bounds__((ConvBwdCfg<CI, CO, HIN, PAD, IMGS, COCH>::NT))
 conv_bwd_data_kernel(const float* __restrict__ pb1, const float* __restrict__ w1, const float* __restrict__ pb2,
                      const float* __restrict__ w2, const uint8_t* __restrict__ sel, int R, float* __restrict__ out) {
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NW = CO * CI * 25, LP = 4 - PAD, HA = HO + 2 * LP, HB = HIN / 2;
-  static_assert(NT >= CI * HB * HB, "one 2x2 output block per thread");
-  __shared__ float s_a[CO * HA * HA], s_w[NW];
-  const int r = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
-  const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
-  const bool active = tid < CI * HB * HB;
-  const int ci = active ? tid / (HB * HB) : 0, by = (tid / HB) % HB, bx = tid % HB;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  using C = ConvBwdCfg<CI, CO, HIN, PAD, IMGS, COCH>;
+  constexpr int HQ = C::HQ, LP = C::LP, HA = C::HA, HB = C::HB, NA = C::NA, NWP = C::NWP, TPI = C::TPI, NT = C::NT;
+  static_assert(HA % 2 == 0 && NA % 4 == 0 && CO % COCH == 0 && HIN % 2 == 0, "alignment of the vector loads");
+  extern __shared__ __align__(16) float smem_f[];
+  float* s_a = smem_f;              // [IMGS][COCH][HA][HA]
+  float* s_w = s_a + IMGS * NA;     // [CO][CI][WPAD]
+  const int s = blockIdx.y, tid = threadIdx.x, r_base = blockIdx.x * IMGS;
+  const int img = tid / TPI, rem = tid % TPI, r = r_base + img;
+  const bool active = img < IMGS && r < R;
+  const int by = rem / HB, bx = rem % HB;
+  float acc[CI][4];
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) acc[ci][0] = acc[ci][1] = acc[ci][2] = acc[ci][3] = 0.f;
 #pragma unroll 1
   for (int term = 0; term < 2; ++term) {
     const float* pb = term ? pb2 : pb1;
     const float* wg = term ? w2 : w1;
     if (!pb) break;
-    if (term) __syncthreads();
-    for (int i = tid; i < CO * HA * HA; i += NT) s_a[i] = 0.f;
-    for (int i = tid; i < NW; i += NT) s_w[i] = wg[(size_t)s * LN_P + i];
     __syncthreads();
-    for (int idx = tid; idx < CO * HQ * HQ; idx += NT) {
-      const int c = sel[pbase + idx];
-      if (c & 4) {
-        const int co = idx / (HQ * HQ), py = (idx / HQ) % HQ, px = idx % HQ, k = c & 3;
-        s_a[(co * HA + LP + 2 * py + (k >> 1)) * HA + LP + 2 * px + (k & 1)] = pb[pbase + idx];
-      }
+    for (int i = tid; i < NWP; i += NT) {
+      const int f = i / WPAD, t = i % WPAD;
+      s_w[i] = t < 25 ? wg[(size_t)s * LN_P + f * 25 + t] : 0.f;
     }
-    __syncthreads();
-    if (active) {
 #pragma unroll 1
-      for (int co = 0; co < CO; ++co) {
-        const float* a = s_a + (co * HA + 2 * by) * HA + 2 * bx;
-        const float* w = s_w + (co * CI + ci) * 25;
-        float pt[6][6], wv[25];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 6; ++j) { pt[i][j] = a[i * HA + j]; KEEP_IN_REG(pt[i][j]); }
-#pragma unroll
-        for (int i = 0; i < 25; ++i) { wv[i] = w[i]; KEEP_IN_REG(wv[i]); }
-#pragma unroll
-        for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 5; ++kx) {
-            const float wk = wv[ky * 5 + kx];
-            acc[0] = fmaf(pt[4 - ky][4 - kx], wk, acc[0]);
-            acc[1] = fmaf(pt[4 - ky][5 - kx], wk, acc[1]);
-            acc[2] = fmaf(pt[5 - ky][4 - kx], wk, acc[2]);
-            acc[3] = fmaf(pt[5 - ky][5 - kx], wk, acc[3]);
+    for (int c0 = 0; c0 < CO; c0 += COCH) {
+      if (c0) __syncthreads();
+      for (int i = tid; i < IMGS * NA; i += NT) s_a[i] = 0.f;
+      __syncthreads();
+      for (int i = tid; i < IMGS * COCH * HQ * HQ; i += NT) {
+        const int im = i / (COCH * HQ * HQ), j = i % (COCH * HQ * HQ), rr = r_base + im;
+        if (rr < R) {
+          const size_t gi = ((size_t)s * R + rr) * (CO * HQ * HQ) + c0 * HQ * HQ + j;
+          const int cd = sel[gi];
+          if (cd & 4) {
+            const int c = j / (HQ * HQ), py = (j / HQ) % HQ, px = j % HQ, k = cd & 3;
+            s_a[im * NA + (c * HA + LP + 2 * py + (k >> 1)) * HA + LP + 2 * px + (k & 1)] = pb[gi];
           }
+        }
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll 1
+        for (int c = 0; c < COCH; ++c) {
+          const float* a = s_a + img * NA + (c * HA + 2 * by) * HA + 2 * bx;
+          float pt[6][6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float2 v = *reinterpret_cast<const float2*>(a + i * HA + 2 * j);
+              pt[i][2 * j] = v.x;
+              pt[i][2 * j + 1] = v.y;
+            }
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) {
+            const float4* w4 = reinterpret_cast<const float4*>(s_w + ((c0 + c) * CI + ci) * WPAD);
+            float wv[WPAD];
+#pragma unroll
+            for (int i = 0; i < WPAD / 4; ++i) {
+              const float4 v = w4[i];
+              wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) {
+                const float wk = wv[ky * 5 + kx];
+                acc[ci][0] = fmaf(pt[4 - ky][4 - kx], wk, acc[ci][0]);
+                acc[ci][1] = fmaf(pt[4 - ky][5 - kx], wk, acc[ci][1]);
+                acc[ci][2] = fmaf(pt[5 - ky][4 - kx], wk, acc[ci][2]);
+                acc[ci][3] = fmaf(pt[5 - ky][5 - kx], wk, acc[ci][3]);
+              }
+          }
+        }
       }
     }
   }
   if (active) {
-    float* o = out + ((size_t)s * R + r) * (CI * HIN * HIN) + (ci * HIN + 2 * by) * HIN + 2 * bx;
-    o[0] = acc[0]; o[1] = acc[1]; o[HIN] = acc[2]; o[HIN + 1] = acc[3];
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      float* o = out + ((size_t)s * R + r) * (CI * HIN * HIN) + (ci * HIN + 2 * by) * HIN + 2 * bx;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[ci][0], acc[ci][1]);
+      *reinterpret_cast<float2*>(o + HIN) = make_float2(acc[ci][2], acc[ci][3]);
+    }
   }
 }
 
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COG>
+static void launch_conv_fwd(int S, int R, cudaStream_t st, const float* in1, size_t ss1, const float* w1, const float* in2,
+                            size_t ss2, const float* w2, const float* bias, uint8_t* sel, int tangent, float* out) {
+  using C = ConvFwdCfg<CI, CO, HIN, PAD, IMGS, COG>;
+  auto k = conv_pool_fwd_kernel<CI, CO, HIN, PAD, IMGS, COG>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  k<<<dim3((R + IMGS - 1) / IMGS, S), C::NT, C::SMEM, st>>>(in1, ss1, w1, in2, ss2, w2, bias, R, sel, tangent, out);
+}
+template <int CI, int CO, int HIN, int PAD, int IMGS, int COCH>
+static void launch_conv_bwd_data(int S, int R, cudaStream_t st, const float* pb1, const float* w1, const float* pb2,
+                                 const float* w2, const uint8_t* sel, float* out) {
+  using C = ConvBwdCfg<CI, CO, HIN, PAD, IMGS, COCH>;
+  auto k = conv_bwd_data_kernel<CI, CO, HIN, PAD, IMGS, COCH>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  k<<<dim3((R + IMGS - 1) / IMGS, S), C::NT, C::SMEM, st>>>(pb1, w1, pb2, w2, sel, R, out);
+}
+#define CONV1_FWD launch_conv_fwd<1, 6, 28, 2, 2, 6>
+#define CONV2_FWD launch_conv_fwd<6, 16, 14, 0, 5, 8>
+#define CONV1_BWD launch_conv_bwd_data<1, 6, 28, 2, 2, 6>
+#define CONV2_BWD launch_conv_bwd_data<6, 16, 14, 0, 5, 8>
+
 // d/d(weights, bias) of the fused conv + ReLU + pool.  One CTA per (row chunk, sample) computes the contribution of its
-// rows to ALL CO*CI*25 weight gradients (each thread owns up to ceil(CO*CI*25 / 256) of them in registers) and to the CO
+// rows to ALL CO*CI*25 weight gradients (a thread owns one filter tap for all CO channels, in registers) and to the CO
 // bias gradients, and writes a partial [chunk][s][CO*CI*25 + CO]; conv_wgrad_reduce_kernel sums the chunks in fixed order:
 //   wbar[s][co][ci][ky][kx] (+)= sum_r sum_{y,x} a[s][r][co][y][x] in[(s)][r][ci][y+ky-PAD][x+kx-PAD];  bbar[s][co] = sum a
 template <int CI, int CO, int HIN, int PAD>
 __global__ void __launch_bounds__(256)
 conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__ sel, const float* __restrict__ in, size_t ss,
                        int R, int rows_per_chunk, float* __restrict__ part) {
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NOUT = CO * CI * 25, NJ = (NOUT + 255) / 256;
-  constexpr int HPP = HP | 1;   // odd row pitch of the padded input: (ky, kx) taps of one warp fall into distinct banks
+  // thread <-> (filter tap (ci, ky, kx), row group g): it accumulates the gradients of that tap for ALL CO output channels, so
+  // one input load feeds CO FMAs and the adjoint loads a[co][y][x] are warp-wide broadcasts (no bank conflicts)
+  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NTAP = CI * 25, NOUT = CO * NTAP, NG = 256 / NTAP;
+  constexpr int HPP = HP | 1;   // odd row pitch of the padded input
   __shared__ float s_a[CO * HO * HO], s_in[CI * HP * HPP], s_pb[CO * HQ * HQ];
   __shared__ uint8_t s_sel[CO * HQ * HQ];
   const int chunk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const int r0 = chunk * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
-  float acc[NJ], bacc[2] = {0.f, 0.f};   // bias gradients: warp w owns channels w and w + 8
-  int a_off[NJ], i_off[NJ];
+  const int tap = tid % NTAP, g = tid / NTAP;
+  const bool active = g < NG;
+  const int ci = tap / 25, ky = (tap % 25) / 5, kx = tap % 5;
+  const int i_off = (ci * HP + ky) * HPP + kx;
   const int warp = tid >> 5, lane = tid & 31;
+  float acc[CO], bacc[2] = {0.f, 0.f};   // bias gradients: warp w owns channels w and w + 8
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int o = tid + 256 * j;
-    acc[j] = 0.f;
-    const int oo = o < NOUT ? o : 0;
-    const int co = oo / (CI * 25), ci = (oo / 25) % CI, ky = (oo % 25) / 5, kx = oo % 5;
-    a_off[j] = co * HO * HO;
-    i_off[j] = (ci * HP + ky) * HPP + kx;
-  }
+  for (int co = 0; co < CO; ++co) acc[co] = 0.f;
   for (int r = r0; r < r1; ++r) {
     const float* ip = in + (size_t)s * ss + (size_t)r * CI * HIN * HIN;
     for (int i = tid; i < CI * HP * HP; i += 256) {
@@ -211,13 +300,18 @@ conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__
       s_a[i] = ((c & 4) && (c & 3) == ((y & 1) * 2 + (x & 1))) ? s_pb[q] : 0.f;
     }
     __syncthreads();
-    for (int y = 0; y < HO; ++y)
+    if (active) {
+      for (int y = g; y < HO; y += NG) {
+        const float* arow = s_a + y * HO;
+        const float* irow = s_in + i_off + y * HPP;
 #pragma unroll 2
-      for (int x = 0; x < HO; ++x) {
-        const int pa = y * HO + x, pi = y * HPP + x;
+        for (int x = 0; x < HO; ++x) {
+          const float iv = irow[x];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[j] = fmaf(s_a[a_off[j] + pa], s_in[i_off[j] + pi], acc[j]);
+          for (int co = 0; co < CO; ++co) acc[co] = fmaf(arow[co * HO * HO + x], iv, acc[co]);
+        }
       }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int co = warp + 8 * h;
@@ -229,10 +323,24 @@ conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__
     }
     __syncthreads();
   }
+  // reduce over the row groups (fixed order) through shared memory, then write this chunk's partial
+  float* red = s_a;   // NG * NOUT floats <= CO * HO * HO for both layers (conv1: 10 x 150 <= 4704; conv2: 1 x 2400 > 1600 -> NG = 1)
   float* dst = part + ((size_t)chunk * gridDim.y + s) * (NOUT + CO);
+  if (NG == 1) {
+    if (active)
 #pragma unroll
-  for (int j = 0; j < NJ; ++j)
-    if (tid + 256 * j < NOUT) dst[tid + 256 * j] = acc[j];
+      for (int co = 0; co < CO; ++co) dst[co * NTAP + tap] = acc[co];
+  } else {
+    if (active)
+#pragma unroll
+      for (int co = 0; co < CO; ++co) red[g * NOUT + co * NTAP + tap] = acc[co];
+    __syncthreads();
+    for (int o = tid; o < NOUT; o += 256) {
+      float t = 0.f;
+      for (int k = 0; k < NG; ++k) t += red[k * NOUT + o];
+      dst[o] = t;
+    }
+  }
   if (lane == 0) {
     if (warp < CO) dst[NOUT + warp] = bacc[0];
     if (warp + 8 < CO) dst[NOUT + warp + 8] = bacc[1];
@@ -603,9 +711,9 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     attr_set = true;
   }
   // ---- primal forward
-  conv_pool_fwd_kernel<1, 6, 28, 2, 256><<<gimg, 256, 0, st>>>(x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, R, w.sel1, 0, w.p1);
-  conv_pool_fwd_kernel<6, 16, 14, 0, 416><<<gimg, 416, 0, st>>>(w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2, R,
-                                                          w.sel2, 0, w.p2);
+  CONV1_FWD(S, R, st, x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, w.sel1, 0, w.p1);
+  CONV2_FWD(S, R, st, w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2,
+            w.sel2, 0, w.p2);
   lin_fwd(w.p2, theta + O_W3, nullptr, nullptr, theta + O_B3, N_P2, N_H3, 1, nullptr, w.h3);
   lin_fwd(w.h3, theta + O_W4, nullptr, nullptr, theta + O_B4, N_H3, N_H4, 1, nullptr, w.h4);
   lin_fwd(w.h4, theta + O_W5, nullptr, nullptr, theta + O_B5, N_H4, N_O, 0, nullptr, w.o);
@@ -627,16 +735,16 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
     conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
-    conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1);
+    CONV2_BWD(S, R, st, w.g2, theta + O_W2, nullptr, nullptr, w.sel2, w.g1);
     conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
-    if (xbar) conv_bwd_data_kernel<1, 6, 28, 2, 224><<<gimg, 224, 0, st>>>(w.g1, theta + O_W1, nullptr, nullptr, w.sel1, R, xbar);
+    if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, nullptr, nullptr, w.sel1, xbar);
     LN_CHECK();
     return PSVI_OK;
   }
   // ---- dual pass: tangent forward (x itself carries no tangent)
-  conv_pool_fwd_kernel<1, 6, 28, 2, 256><<<gimg, 256, 0, st>>>(x, 0, thetad + O_W1, nullptr, 0, nullptr, thetad + O_B1, R, w.sel1, 1, w.pd1);
-  conv_pool_fwd_kernel<6, 16, 14, 0, 416><<<gimg, 416, 0, st>>>(w.pd1, sR * N_P1, theta + O_W2, w.p1, sR * N_P1, thetad + O_W2,
-                                                          thetad + O_B2, R, w.sel2, 1, w.pd2);
+  CONV1_FWD(S, R, st, x, 0, thetad + O_W1, nullptr, 0, nullptr, thetad + O_B1, w.sel1, 1, w.pd1);
+  CONV2_FWD(S, R, st, w.pd1, sR * N_P1, theta + O_W2, w.p1, sR * N_P1, thetad + O_W2,
+            thetad + O_B2, w.sel2, 1, w.pd2);
   lin_fwd(w.pd2, theta + O_W3, w.p2, thetad + O_W3, thetad + O_B3, N_P2, N_H3, 0, w.h3, w.hd3);
   lin_fwd(w.hd3, theta + O_W4, w.h3, thetad + O_W4, thetad + O_B4, N_H3, N_H4, 0, w.h4, w.hd4);
   lin_fwd(w.hd4, theta + O_W5, w.h4, thetad + O_W5, thetad + O_B5, N_H4, N_O, 0, nullptr, w.od);
@@ -665,12 +773,12 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
   conv2_wgrad(w.g2d, w.pd1, tbar + O_W2, nullptr, 1);
   conv2_wgrad(w.g2d, w.p1, tdbar + O_W2, tdbar + O_B2, 0);
-  conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, R, w.g1);
-  conv_bwd_data_kernel<6, 16, 14, 0, 320><<<gimg, 320, 0, st>>>(w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, R, w.g1d);
+  CONV2_BWD(S, R, st, w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, w.g1);
+  CONV2_BWD(S, R, st, w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, w.g1d);
   // conv 1
   conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
   conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1, 0);
-  if (xbar) conv_bwd_data_kernel<1, 6, 28, 2, 224><<<gimg, 224, 0, st>>>(w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, R, xbar);
+  if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, xbar);
   LN_CHECK();
   return PSVI_OK;
 }
