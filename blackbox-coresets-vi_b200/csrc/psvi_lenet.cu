@@ -21,7 +21,6 @@ constexpr int LN_P = 61706;
 constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 = 50572, O_W4 = 50692, O_B4 = 60772,
               O_W5 = 60856, O_B5 = 61696;
 constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
-constexpr int RT = 8;   // rows per CTA of the fully connected kernels
 // makes a loaded value opaque to the optimiser, so it stays in a register instead of being re-read from shared memory
 #define KEEP_IN_REG(x) asm volatile("" : "+f"(x))
 constexpr int N_CHUNKS = 64;   // row chunks of the conv weight-gradient kernels (up to 64 x S CTAs)
@@ -363,171 +362,110 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int n_c
 }
 
 // ------------------------------------------------------------------------------------------------ fully connected layers
-// out[s][r][o] = (bias[s][o] + sum_i x1[s][r][i] w1[s][o][i] (+ x2 . w2)); relu -> max(., 0); maskfrom -> * (maskfrom > 0)
-__global__ void __launch_bounds__(128)
-lin_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ x2,
-               const float* __restrict__ w2, const float* __restrict__ bias, int R, int IN, int OUT, int relu,
-               const float* __restrict__ maskfrom, float* __restrict__ out) {
-  extern __shared__ float sm[];
-  float* sx1 = sm;
-  float* sx2 = sm + RT * IN;
-  const int r0 = blockIdx.x * RT, s = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < RT * IN; i += 128) {
-    const int rr = i / IN, row = r0 + rr;
-    const size_t src = ((size_t)s * R + row) * IN + i % IN;
-    sx1[i] = row < R ? x1[src] : 0.f;
-    sx2[i] = (row < R && x2) ? x2[src] : 0.f;
-  }
-  __syncthreads();
-  for (int o = tid; o < OUT; o += 128) {
-    float acc[RT];
-    const float b = bias ? bias[(size_t)s * LN_P + o] : 0.f;
-#pragma unroll
-    for (int k = 0; k < RT; ++k) acc[k] = b;
-    // (IN is a multiple of 4 for every layer of the stack: 400, 120, 84; eight weights are in flight per batch)
-    const float* wa = w1 + (size_t)s * LN_P + (size_t)o * IN;
-    for (int i0 = 0; i0 < IN; i0 += 8) {
-      float wv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) wv[e] = i0 + e < IN ? wa[i0 + e] : 0.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (i0 + e >= IN) break;
-#pragma unroll
-        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx1[k * IN + i0 + e], wv[e], acc[k]);
-      }
-    }
-    if (x2) {
-      const float* wb = w2 + (size_t)s * LN_P + (size_t)o * IN;
-      for (int i0 = 0; i0 < IN; i0 += 8) {
-        float wv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) wv[e] = i0 + e < IN ? wb[i0 + e] : 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (i0 + e >= IN) break;
-#pragma unroll
-          for (int k = 0; k < RT; ++k) acc[k] = fmaf(sx2[k * IN + i0 + e], wv[e], acc[k]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RT; ++k) {
-      const int row = r0 + k;
-      if (row >= R) break;
-      const size_t dst = ((size_t)s * R + row) * OUT + o;
-      float v = relu ? fmaxf(acc[k], 0.f) : acc[k];
-      if (maskfrom) v = maskfrom[dst] > 0.f ? v : 0.f;
-      out[dst] = v;
-    }
-  }
-}
+// The three matrix products of a fully connected layer (forward, data adjoint, weight gradient) are all instances of one
+// per-sample batched product   out[s][m][n] (+)= sum_k A1[s](m, k) B1[s](n, k) (+ sum_k A2[s](m, k) B2[s](n, k))
+// with either operand stored k-contiguous (KC) or m/n-contiguous.  The matrices are small (at most 200 x 400 x 120 per
+// sample) and L2-resident, so the kernel is built for latency: 32 x 32 output tiles (many CTAs), 32-deep k tiles whose
+// global loads for tile t + 1 are all in flight while tile t is multiplied out of shared memory, 4 x 4 register micro-tiles
+// fed by two 128-bit shared loads per k.  Epilogue: + bias[n], relu, mask by (maskfrom > 0), accumulate into out; optional
+// column sums  colsum[s][m] = sum_k A1(m, k)  (the bias gradient of the weight-gradient product), in fixed order.
+struct BGemm {
+  const float *A1, *B1, *A2, *B2;
+  long long sA1, sB1, sA2, sB2;   // per-sample strides (elements)
+  int lda1, ldb1, lda2, ldb2;     // pitch of the non-contiguous dimension
+  int M, N, K;
+  const float* bias; long long sBias;
+  int relu;
+  const float* maskfrom;
+  float* out; long long sO; int ldo; int accumulate;
+  float* colsum; long long sCol;
+};
+constexpr int G_T = 32, G_P = 36;   // tile edge (m, n and k) and shared-memory pitch
 
-// out[s][r][i] = sum_o (y1[s][r][o] w1[s][o][i] (+ y2 . w2)), then * (maskfrom[s][r][i] > 0) if given
-__global__ void __launch_bounds__(128)
-lin_bwd_data_kernel(const float* __restrict__ y1, const float* __restrict__ w1, const float* __restrict__ y2,
-                    const float* __restrict__ w2, int R, int IN, int OUT, const float* __restrict__ maskfrom,
-                    float* __restrict__ out) {
-  extern __shared__ float sm[];
-  float* sy1 = sm;
-  float* sy2 = sm + RT * OUT;
-  const int r0 = blockIdx.x * RT, s = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < RT * OUT; i += 128) {
-    const int rr = i / OUT, row = r0 + rr;
-    const size_t src = ((size_t)s * R + row) * OUT + i % OUT;
-    sy1[i] = row < R ? y1[src] : 0.f;
-    sy2[i] = (row < R && y2) ? y2[src] : 0.f;
-  }
-  __syncthreads();
-  for (int i = tid; i < IN; i += 128) {
-    float acc[RT];
-#pragma unroll
-    for (int k = 0; k < RT; ++k) acc[k] = 0.f;
-    const float* wa = w1 + (size_t)s * LN_P + i;
-    const float* wb = w2 ? w2 + (size_t)s * LN_P + i : nullptr;
-    for (int o0 = 0; o0 < OUT; o0 += 8) {   // eight weights (and eight tangent weights) in flight per batch
-      float wv[8], vv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        wv[e] = o0 + e < OUT ? wa[(size_t)(o0 + e) * IN] : 0.f;
-        vv[e] = (wb && o0 + e < OUT) ? wb[(size_t)(o0 + e) * IN] : 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (o0 + e >= OUT) break;
-#pragma unroll
-        for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy1[k * OUT + o0 + e], wv[e], acc[k]);
-        if (wb) {
-#pragma unroll
-          for (int k = 0; k < RT; ++k) acc[k] = fmaf(sy2[k * OUT + o0 + e], vv[e], acc[k]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RT; ++k) {
-      const int row = r0 + k;
-      if (row >= R) break;
-      const size_t dst = ((size_t)s * R + row) * IN + i;
-      out[dst] = (maskfrom && !(maskfrom[dst] > 0.f)) ? 0.f : acc[k];
-    }
-  }
-}
-
-// wbar[s][o][i] (+)= sum_r y[s][r][o] x[s][r][i];  bbar[s][o] = sum_r y[s][r][o]   (one CTA per 4 outputs and sample; a thread
-// owns up to four input columns i, i + 128, ... at once so that four independent loads are in flight per row)
-__global__ void __launch_bounds__(128)
-lin_bwd_weight_kernel(const float* __restrict__ y, const float* __restrict__ x, int R, int IN, int OUT,
-                      float* __restrict__ wbar, float* __restrict__ bbar, int accumulate) {
-  extern __shared__ float sy[];   // [R][4]
-  const int o0 = blockIdx.x * 4, s = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < R * 4; i += 128) {
-    const int r = i >> 2, o = o0 + (i & 3);
-    sy[i] = o < OUT ? y[((size_t)s * R + r) * OUT + o] : 0.f;
-  }
-  __syncthreads();
-  const float* xs = x + (size_t)s * R * IN;
+template <bool AKC, bool BKC>
+__global__ void __launch_bounds__(64)
+bgemm_kernel(const BGemm p) {
+  __shared__ __align__(16) float As[G_T][G_P], Bs[G_T][G_P];   // [k][m], [k][n]
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int m0 = blockIdx.x * G_T, n0 = blockIdx.y * G_T, s = blockIdx.z;
   float acc[4][4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
-  int col[4];
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;
+  const bool want_csum = p.colsum && blockIdx.y == 0;
+  const int nkt = (p.K + G_T - 1) / G_T;
+#pragma unroll 1
+  for (int term = 0; term < 2; ++term) {
+    const float* A = term ? p.A2 : p.A1;
+    const float* B = term ? p.B2 : p.B1;
+    if (!A) break;
+    A += (size_t)s * (term ? p.sA2 : p.sA1);
+    B += (size_t)s * (term ? p.sB2 : p.sB1);
+    const int lda = term ? p.lda2 : p.lda1, ldb = term ? p.ldb2 : p.ldb1;
+    float ra[16], rb[16];
+    auto fetch = [&](int kt) {
+      const int k0 = kt * G_T;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) col[c] = tid + 128 * c;
-  for (int r0 = 0; r0 < R; r0 += 8) {   // eight rows per batch: all 32 loads are issued before the first FMA needs one
-    float xv[8][4];
+      for (int j = 0; j < 16; ++j) {
+        const int e = tid + j * 64;
+        {
+          const int mm = AKC ? (e >> 5) : (e & 31), kk = AKC ? (e & 31) : (e >> 5);
+          const bool ok = m0 + mm < p.M && k0 + kk < p.K;
+          ra[j] = ok ? (AKC ? A[(size_t)(m0 + mm) * lda + k0 + kk] : A[(size_t)(k0 + kk) * lda + m0 + mm]) : 0.f;
+        }
+        {
+          const int nn = BKC ? (e >> 5) : (e & 31), kk = BKC ? (e & 31) : (e >> 5);
+          const bool ok = n0 + nn < p.N && k0 + kk < p.K;
+          rb[j] = ok ? (BKC ? B[(size_t)(n0 + nn) * ldb + k0 + kk] : B[(size_t)(k0 + kk) * ldb + n0 + nn]) : 0.f;
+        }
+      }
+    };
+    fetch(0);
+#pragma unroll 1
+    for (int kt = 0; kt < nkt; ++kt) {
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 16; ++j) {
+        const int e = tid + j * 64;
+        As[AKC ? (e & 31) : (e >> 5)][AKC ? (e >> 5) : (e & 31)] = ra[j];
+        Bs[BKC ? (e & 31) : (e >> 5)][BKC ? (e >> 5) : (e & 31)] = rb[j];
+      }
+      __syncthreads();
+      if (kt + 1 < nkt) fetch(kt + 1);
+      if (want_csum && term == 0 && tid < G_T) {
+#pragma unroll 8
+        for (int k = 0; k < G_T; ++k) csum += As[k][tid];
+      }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) xv[i][c] = (r0 + i < R && col[c] < IN) ? xs[(size_t)(r0 + i) * IN + col[c]] : 0.f;
+      for (int k = 0; k < G_T; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (r0 + i >= R) break;
-      const float4 yv = *reinterpret_cast<const float4*>(sy + (r0 + i) * 4);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        acc[c][0] = fmaf(yv.x, xv[i][c], acc[c][0]);
-        acc[c][1] = fmaf(yv.y, xv[i][c], acc[c][1]);
-        acc[c][2] = fmaf(yv.z, xv[i][c], acc[c][2]);
-        acc[c][3] = fmaf(yv.w, xv[i][c], acc[c][3]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (col[c] >= IN) continue;
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) break;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (o0 + k >= OUT) break;
-      float* dst = wbar + (size_t)s * LN_P + (size_t)(o0 + k) * IN + col[c];
-      *dst = accumulate ? *dst + acc[c][k] : acc[c][k];
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) break;
+      const size_t dst = (size_t)s * p.sO + (size_t)m * p.ldo + n;
+      float v = acc[i][j] + (p.bias ? p.bias[(size_t)s * p.sBias + n] : 0.f);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.maskfrom && !(p.maskfrom[dst] > 0.f)) v = 0.f;
+      p.out[dst] = p.accumulate ? p.out[dst] + v : v;
     }
   }
-  if (bbar && tid < 4 && o0 + tid < OUT) {
-    float t = 0.f;
-    for (int r = 0; r < R; ++r) t += sy[r * 4 + tid];
-    bbar[(size_t)s * LN_P + o0 + tid] = t;
-  }
+  if (want_csum && tid < G_T && m0 + tid < p.M) p.colsum[(size_t)s * p.sCol + m0 + tid] = csum;
 }
 
 // ------------------------------------------------------------------------------------------------ softmax / NLL head
@@ -683,18 +621,43 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   cudaStream_t st = (cudaStream_t)stream_;
   Ws w;
   carve_ws(S, R, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255), w);
-  const dim3 gimg(R, S), grow((R + RT - 1) / RT, S);
   const size_t sR = (size_t)R;
+  auto tiles = [](int n) { return (n + G_T - 1) / G_T; };
+  // out[s][r][o] = bias[s][o] + sum_i x1[s][r][i] w1[s][o][i] (+ x2 . w2); relu; * (mask > 0)
   auto lin_fwd = [&](const float* x1, const float* w1, const float* x2, const float* w2, const float* b, int IN, int OUT,
                      int relu, const float* mask, float* out) {
-    lin_fwd_kernel<<<grow, 128, 2 * RT * IN * sizeof(float), st>>>(x1, w1, x2, w2, b, R, IN, OUT, relu, mask, out);
+    BGemm g{};
+    g.A1 = x1; g.B1 = w1; g.A2 = x2; g.B2 = w2;
+    g.sA1 = g.sA2 = (long long)sR * IN; g.sB1 = g.sB2 = LN_P;
+    g.lda1 = g.lda2 = g.ldb1 = g.ldb2 = IN;
+    g.M = R; g.N = OUT; g.K = IN;
+    g.bias = b; g.sBias = LN_P; g.relu = relu; g.maskfrom = mask;
+    g.out = out; g.sO = (long long)sR * OUT; g.ldo = OUT;
+    bgemm_kernel<true, true><<<dim3(tiles(R), tiles(OUT), S), 64, 0, st>>>(g);
   };
+  // out[s][r][i] = sum_o y1[s][r][o] w1[s][o][i] (+ y2 . w2); * (mask > 0)
   auto lin_bwd_data = [&](const float* y1, const float* w1, const float* y2, const float* w2, int IN, int OUT, const float* mask,
                           float* out) {
-    lin_bwd_data_kernel<<<grow, 128, 2 * RT * OUT * sizeof(float), st>>>(y1, w1, y2, w2, R, IN, OUT, mask, out);
+    BGemm g{};
+    g.A1 = y1; g.B1 = w1; g.A2 = y2; g.B2 = w2;
+    g.sA1 = g.sA2 = (long long)sR * OUT; g.sB1 = g.sB2 = LN_P;
+    g.lda1 = g.lda2 = OUT; g.ldb1 = g.ldb2 = IN;
+    g.M = R; g.N = IN; g.K = OUT;
+    g.maskfrom = mask;
+    g.out = out; g.sO = (long long)sR * IN; g.ldo = IN;
+    bgemm_kernel<true, false><<<dim3(tiles(R), tiles(IN), S), 64, 0, st>>>(g);
   };
-  auto lin_bwd_weight = [&](const float* yy, const float* xx, int IN, int OUT, float* wb, float* bb, int acc) {
-    lin_bwd_weight_kernel<<<dim3((OUT + 3) / 4, S), 128, sR * 4 * sizeof(float), st>>>(yy, xx, R, IN, OUT, wb, bb, acc);
+  // wbar[s][o][i] = sum_r y1[s][r][o] x1[s][r][i] (+ y2 . x2);  bbar[s][o] = sum_r y1[s][r][o]
+  auto lin_bwd_weight = [&](const float* y1, const float* x1, const float* y2, const float* x2, int IN, int OUT, float* wb,
+                            float* bb) {
+    BGemm g{};
+    g.A1 = y1; g.B1 = x1; g.A2 = y2; g.B2 = x2;
+    g.sA1 = g.sA2 = (long long)sR * OUT; g.sB1 = g.sB2 = (long long)sR * IN;
+    g.lda1 = g.lda2 = OUT; g.ldb1 = g.ldb2 = IN;
+    g.M = OUT; g.N = IN; g.K = R;
+    g.out = wb; g.sO = LN_P; g.ldo = IN;
+    g.colsum = bb; g.sCol = LN_P;
+    bgemm_kernel<false, false><<<dim3(tiles(OUT), tiles(IN), S), 64, 0, st>>>(g);
   };
   const int rpc = (R + N_CHUNKS - 1) / N_CHUNKS, nch = (R + rpc - 1) / rpc;
   auto conv2_wgrad = [&](const float* pbv, const float* inp, float* wb, float* bb, int acc) {
@@ -705,11 +668,6 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(nch, S), 256, 0, st>>>(pbv, w.sel1, x, 0, R, rpc, w.wpart);
     conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 150, 6, wb, bb, acc);
   };
-  static bool attr_set = false;
-  if (!attr_set) {
-    PSVI_CUDA_CHECK(cudaFuncSetAttribute(lin_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   // ---- primal forward
   CONV1_FWD(S, R, st, x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, w.sel1, 0, w.p1);
   CONV2_FWD(S, R, st, w.p1, sR * N_P1, theta + O_W2, nullptr, 0, nullptr, theta + O_B2,
@@ -728,11 +686,11 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   if (!thetad) {
     // ---- gradient pass
     lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, y, cw, S, R, 1, nll, w.go, nullptr, nullptr);
-    lin_bwd_weight(w.go, w.h4, N_H4, N_O, tbar + O_W5, tbar + O_B5, 0);
+    lin_bwd_weight(w.go, w.h4, nullptr, nullptr, N_H4, N_O, tbar + O_W5, tbar + O_B5);
     lin_bwd_data(w.go, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4);
-    lin_bwd_weight(w.g4, w.h3, N_H3, N_H4, tbar + O_W4, tbar + O_B4, 0);
+    lin_bwd_weight(w.g4, w.h3, nullptr, nullptr, N_H3, N_H4, tbar + O_W4, tbar + O_B4);
     lin_bwd_data(w.g4, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3);
-    lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
+    lin_bwd_weight(w.g3, w.p2, nullptr, nullptr, N_P2, N_H3, tbar + O_W3, tbar + O_B3);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
     conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
     CONV2_BWD(S, R, st, w.g2, theta + O_W2, nullptr, nullptr, w.sel2, w.g1);
@@ -751,21 +709,18 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, w.od, y, cw, S, R, 2, nll, w.go, w.god, acbar);
   LN_CHECK();
   // layer 5
-  lin_bwd_weight(w.go, w.h4, N_H4, N_O, tbar + O_W5, tbar + O_B5, 0);
-  lin_bwd_weight(w.god, w.hd4, N_H4, N_O, tbar + O_W5, nullptr, 1);
-  lin_bwd_weight(w.god, w.h4, N_H4, N_O, tdbar + O_W5, tdbar + O_B5, 0);
+  lin_bwd_weight(w.go, w.h4, w.god, w.hd4, N_H4, N_O, tbar + O_W5, tbar + O_B5);
+  lin_bwd_weight(w.god, w.h4, nullptr, nullptr, N_H4, N_O, tdbar + O_W5, tdbar + O_B5);
   lin_bwd_data(w.go, theta + O_W5, w.god, thetad + O_W5, N_H4, N_O, w.h4, w.g4);
   lin_bwd_data(w.god, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4d);
   // layer 4
-  lin_bwd_weight(w.g4, w.h3, N_H3, N_H4, tbar + O_W4, tbar + O_B4, 0);
-  lin_bwd_weight(w.g4d, w.hd3, N_H3, N_H4, tbar + O_W4, nullptr, 1);
-  lin_bwd_weight(w.g4d, w.h3, N_H3, N_H4, tdbar + O_W4, tdbar + O_B4, 0);
+  lin_bwd_weight(w.g4, w.h3, w.g4d, w.hd3, N_H3, N_H4, tbar + O_W4, tbar + O_B4);
+  lin_bwd_weight(w.g4d, w.h3, nullptr, nullptr, N_H3, N_H4, tdbar + O_W4, tdbar + O_B4);
   lin_bwd_data(w.g4, theta + O_W4, w.g4d, thetad + O_W4, N_H3, N_H4, w.h3, w.g3);
   lin_bwd_data(w.g4d, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3d);
   // layer 3
-  lin_bwd_weight(w.g3, w.p2, N_P2, N_H3, tbar + O_W3, tbar + O_B3, 0);
-  lin_bwd_weight(w.g3d, w.pd2, N_P2, N_H3, tbar + O_W3, nullptr, 1);
-  lin_bwd_weight(w.g3d, w.p2, N_P2, N_H3, tdbar + O_W3, tdbar + O_B3, 0);
+  lin_bwd_weight(w.g3, w.p2, w.g3d, w.pd2, N_P2, N_H3, tbar + O_W3, tbar + O_B3);
+  lin_bwd_weight(w.g3d, w.p2, nullptr, nullptr, N_P2, N_H3, tdbar + O_W3, tdbar + O_B3);
   lin_bwd_data(w.g3, theta + O_W3, w.g3d, thetad + O_W3, N_P2, N_H3, nullptr, w.g2);
   lin_bwd_data(w.g3d, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2d);
   LN_CHECK();
