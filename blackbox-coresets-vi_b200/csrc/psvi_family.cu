@@ -110,6 +110,47 @@ __global__ void mf_nkl_finish_kernel(int S, const double* __restrict__ part, con
   out[s] = a;   // out[0..S-1] = nkl_s, out[S] = kl
 }
 
+// One step of the unrolled robust Adam (reference psvi/robust_higher/optim.py:303-367), elementwise over the flat
+// parameter vector, in the rounding order of the reference's tensor expressions (explicit _rn intrinsics: no FMA contraction):
+//   m' = m b1 + (1 - b1) g;  v' = v b2 + (1 - b2) g g;  phi' = phi - k m' / (sqrt(v' + 1e-8) / sq2 + 1e-8)
+// with k = lr / (1 - b1^t), sq2 = sqrt(1 - b2^t) computed by the caller in double.
+__global__ void __launch_bounds__(FT) adam_step_kernel(long long n, float k, float sq2, const float* __restrict__ phi,
+                                                       const float* __restrict__ g, const float* __restrict__ m,
+                                                       const float* __restrict__ v, float* __restrict__ phi_out,
+                                                       float* __restrict__ m_out, float* __restrict__ v_out) {
+  const long long i = (long long)blockIdx.x * FT + threadIdx.x;
+  if (i >= n) return;
+  const float b1 = 0.9f, b2 = 0.999f, ob1 = (float)(1.0 - 0.9), ob2 = (float)(1.0 - 0.999);
+  const float gi = g[i];
+  const float mn = __fadd_rn(__fmul_rn(m[i], b1), __fmul_rn(ob1, gi));
+  const float vn = __fadd_rn(__fmul_rn(v[i], b2), __fmul_rn(__fmul_rn(ob2, gi), gi));
+  const float den = __fadd_rn(__fdiv_rn(__fsqrt_rn(__fadd_rn(vn, 1e-8f)), sq2), 1e-8f);
+  m_out[i] = mn;
+  v_out[i] = vn;
+  phi_out[i] = __fsub_rn(phi[i], __fmul_rn(k, __fdiv_rn(mn, den)));
+}
+
+// Reverse of that step: from the adjoint pbar of phi' and the running adjoints (mbar, vbar) of (m', v') it forms
+//   mb = mbar - k pbar / den;  vb = vbar + (k pbar m' / den^2) / (2 q sq2), zeroed where v' == 0 (the _maybe_mask hook,
+//   optim.py:40-52,346-347);  gbar = (1 - b1) mb + 2 (1 - b2) g vb;  mbar <- b1 mb;  vbar <- b2 vb      (q = sqrt(v' + 1e-8))
+__global__ void __launch_bounds__(FT) adam_reverse_kernel(long long n, float k, float sq2, const float* __restrict__ pbar,
+                                                          const float* __restrict__ g, const float* __restrict__ m_t,
+                                                          const float* __restrict__ v_t, float* __restrict__ mbar,
+                                                          float* __restrict__ vbar, float* __restrict__ gbar) {
+  const long long i = (long long)blockIdx.x * FT + threadIdx.x;
+  if (i >= n) return;
+  const float b1 = 0.9f, b2 = 0.999f, ob1 = (float)(1.0 - 0.9), tob2 = (float)(2.0 * (1.0 - 0.999));
+  const float vt = v_t[i], q = __fsqrt_rn(__fadd_rn(vt, 1e-8f));
+  const float den = __fadd_rn(__fdiv_rn(q, sq2), 1e-8f);
+  const float kp = __fmul_rn(k, pbar[i]);
+  const float mb = __fsub_rn(mbar[i], __fdiv_rn(kp, den));
+  float vb = __fadd_rn(vbar[i], __fdiv_rn(__fdiv_rn(__fmul_rn(kp, m_t[i]), __fmul_rn(den, den)), __fmul_rn(__fmul_rn(2.f, q), sq2)));
+  if (vt == 0.f) vb = 0.f;
+  gbar[i] = __fadd_rn(__fmul_rn(ob1, mb), __fmul_rn(__fmul_rn(tob2, g[i]), vb));
+  mbar[i] = __fmul_rn(b1, mb);
+  vbar[i] = __fmul_rn(b2, vb);
+}
+
 }  // namespace
 
 extern "C" {
@@ -157,6 +198,22 @@ int psvi_mf_nkl_kl(int32_t S, int64_t P, const float* mu, const float* rho, cons
   double* klpart = part + (size_t)S * NB;
   mf_nkl_kernel<<<dim3(NB, S + 1), FT, 0, (cudaStream_t)stream>>>(S, P, mu, rho, eps, theta, mask, part, klpart);
   mf_nkl_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(S, part, klpart, out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_adam_unroll_step(int64_t n, float k, float sq2, const float* phi, const float* g, const float* m, const float* v,
+                          float* phi_out, float* m_out, float* v_out, void* stream) {
+  PSVI_REQUIRE(n >= 1 && phi && g && m && v && phi_out && m_out && v_out, PSVI_ERR_INVALID, "bad argument");
+  adam_step_kernel<<<(unsigned)((n + FT - 1) / FT), FT, 0, (cudaStream_t)stream>>>(n, k, sq2, phi, g, m, v, phi_out, m_out, v_out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_adam_unroll_reverse(int64_t n, float k, float sq2, const float* pbar, const float* g, const float* m_t, const float* v_t,
+                             float* mbar, float* vbar, float* gbar, void* stream) {
+  PSVI_REQUIRE(n >= 1 && pbar && g && m_t && v_t && mbar && vbar && gbar, PSVI_ERR_INVALID, "bad argument");
+  adam_reverse_kernel<<<(unsigned)((n + FT - 1) / FT), FT, 0, (cudaStream_t)stream>>>(n, k, sq2, pbar, g, m_t, v_t, mbar, vbar, gbar);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

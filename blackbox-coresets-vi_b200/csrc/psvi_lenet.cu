@@ -13,6 +13,7 @@
 // reference computes this family in fp32.  One CTA per (row, sample) keeps a whole image's feature maps in shared memory:
 // conv + ReLU + pool are fused (the full-resolution maps never reach global memory; only the pooled map and a 3-bit
 // selection code per pooled element do), and the backward kernels scatter through that code on the fly.
+#include <algorithm>
 #include "psvi_common.cuh"
 
 namespace {
@@ -23,7 +24,7 @@ constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 =
 constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
 // makes a loaded value opaque to the optimiser, so it stays in a register instead of being re-read from shared memory
 #define KEEP_IN_REG(x) asm volatile("" : "+f"(x))
-constexpr int N_CHUNKS = 64;   // row chunks of the conv weight-gradient kernels (up to 64 x S CTAs)
+constexpr int N_CHUNKS = 128;   // row chunks of the conv weight-gradient kernels (up to 128 x S CTAs)
 
 // ------------------------------------------------------------------------------------------------ conv + ReLU + pool
 // out[s][r][co][py][px]: primal: max over the 2x2 window of relu(conv(in1, w1) [+ conv(in2, w2)] + bias), selection code
@@ -258,92 +259,138 @@ static void launch_conv_bwd_data(int S, int R, cudaStream_t st, const float* pb1
 #define CONV2_BWD launch_conv_bwd_data<6, 16, 14, 0, 5, 8>
 
 // d/d(weights, bias) of the fused conv + ReLU + pool.  One CTA per (row chunk, sample) computes the contribution of its
-// rows to ALL CO*CI*25 weight gradients (a thread owns one filter tap for all CO channels, in registers) and to the CO
-// bias gradients, and writes a partial [chunk][s][CO*CI*25 + CO]; conv_wgrad_reduce_kernel sums the chunks in fixed order:
-//   wbar[s][co][ci][ky][kx] (+)= sum_r sum_{y,x} a[s][r][co][y][x] in[(s)][r][ci][y+ky-PAD][x+kx-PAD];  bbar[s][co] = sum a
-template <int CI, int CO, int HIN, int PAD>
-__global__ void __launch_bounds__(256)
-conv_bwd_weight_kernel(const float* __restrict__ pb, const uint8_t* __restrict__ sel, const float* __restrict__ in, size_t ss,
-                       int R, int rows_per_chunk, float* __restrict__ part) {
-  // thread <-> (filter tap (ci, ky, kx), row group g): it accumulates the gradients of that tap for ALL CO output channels, so
-  // one input load feeds CO FMAs and the adjoint loads a[co][y][x] are warp-wide broadcasts (no bank conflicts)
-  constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, NTAP = CI * 25, NOUT = CO * NTAP, NG = 256 / NTAP;
-  constexpr int HPP = HP | 1;   // odd row pitch of the padded input
-  __shared__ float s_a[CO * HO * HO], s_in[CI * HP * HPP], s_pb[CO * HQ * HQ];
-  __shared__ uint8_t s_sel[CO * HQ * HQ];
+// rows to ALL CO*CI*25 weight gradients and to the CO bias gradients, and writes a partial [chunk][s][CO*CI*25 + CO];
+// conv_wgrad_reduce_kernel sums the chunks in fixed order:
+//   wbar[s][co][ci][ky][kx] = sum_r sum_{y,x} a1[s][r][co][y][x] in1[(s)][r][ci][y+ky-PAD][x+kx-PAD] (+ the same with a2, in2)
+//   bbar[s][co] = sum a1
+// A thread owns one filter row (ci, ky) -- its 5 taps for ALL CO channels, 5*CO accumulators -- over the output rows of its
+// row group g: per four output columns it reads 8 inputs (two 128-bit loads) and CO adjoint quads (warp-broadcast 128-bit
+// loads) for 20*CO FMAs, so the loop is FMA-bound instead of shared-memory-bound.
+template <int CI, int CO, int HIN, int PAD, int NG>
+struct ConvWgCfg {
+  static constexpr int HP = HIN + 2 * PAD, HO = HP - 4, HQ = HO / 2, HOP = (HO + 3) / 4 * 4;
+  static constexpr int HPMIN = HP > HOP + 4 ? HP : HOP + 4;
+  static constexpr int HPP = (HPMIN + 3) / 8 * 8 + 4;   // smallest pitch >= HPMIN with pitch % 8 == 4 (conflict-free 128-bit rows)
+  static constexpr int NTR = CI * 5, NT = (NTR * NG + 31) / 32 * 32, NOUT = CO * CI * 25;
+};
+template <int CI, int CO, int HIN, int PAD, int NG>
+__global__ void __launch_bounds__((ConvWgCfg<CI, CO, HIN, PAD, NG>::NT))
+conv_bwd_weight_kernel(const float* __restrict__ pb1, const float* __restrict__ in1, size_t ss1, const float* __restrict__ pb2,
+                       const float* __restrict__ in2, size_t ss2, const uint8_t* __restrict__ sel, int R, int rows_per_chunk,
+                       float* __restrict__ part) {
+  using C = ConvWgCfg<CI, CO, HIN, PAD, NG>;
+  constexpr int HP = C::HP, HO = C::HO, HQ = C::HQ, HOP = C::HOP, HPP = C::HPP, NTR = C::NTR, NT = C::NT, NOUT = C::NOUT;
+  constexpr int NW = NT / 32, NB = (CO + NW - 1) / NW;
+  static_assert(HPP >= C::HPMIN && HPP % 8 == 4, "input pitch");
+  static_assert(HIN % 2 == 0 && PAD % 2 == 0 && HOP % 2 == 0, "64-bit staging");
+  __shared__ __align__(16) float s_a[CO * HO * HOP], s_in[CI * HP * HPP], s_red[NOUT];
   const int chunk = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   const int r0 = chunk * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
-  const int tap = tid % NTAP, g = tid / NTAP;
+  const int tr = tid % NTR, g = tid / NTR;
   const bool active = g < NG;
-  const int ci = tap / 25, ky = (tap % 25) / 5, kx = tap % 5;
-  const int i_off = (ci * HP + ky) * HPP + kx;
+  const int ci = tr / 5, ky = tr % 5;
   const int warp = tid >> 5, lane = tid & 31;
-  float acc[CO], bacc[2] = {0.f, 0.f};   // bias gradients: warp w owns channels w and w + 8
+  float acc[5][CO], bacc[NB];
 #pragma unroll
-  for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[k][co] = 0.f;
+#pragma unroll
+  for (int h = 0; h < NB; ++h) bacc[h] = 0.f;
+  // the zero padding (border of the input, pad columns of the adjoint) is written once; the per-row staging only touches
+  // the interior
+  for (int i = tid; i < CI * HP * HPP; i += NT) s_in[i] = 0.f;
+  for (int i = tid; i < CO * HO * HOP; i += NT) s_a[i] = 0.f;
+  __syncthreads();
+#pragma unroll 1
   for (int r = r0; r < r1; ++r) {
-    const float* ip = in + (size_t)s * ss + (size_t)r * CI * HIN * HIN;
-    for (int i = tid; i < CI * HP * HP; i += 256) {
-      const int c = i / (HP * HP), yp = (i / HP) % HP, xp = i % HP, yy = yp - PAD, xx = xp - PAD;
-      s_in[(c * HP + yp) * HPP + xp] = (yy >= 0 && yy < HIN && xx >= 0 && xx < HIN) ? ip[(c * HIN + yy) * HIN + xx] : 0.f;
-    }
-    const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
-    for (int i = tid; i < CO * HQ * HQ; i += 256) {   // pooled adjoint + selection code: coalesced, once
-      s_pb[i] = pb[pbase + i];
-      s_sel[i] = sel[pbase + i];
-    }
-    __syncthreads();
-    for (int i = tid; i < CO * HO * HO; i += 256) {   // scattered to full resolution
-      const int co = i / (HO * HO), y = (i / HO) % HO, x = i % HO;
-      const int q = (co * HQ + (y >> 1)) * HQ + (x >> 1), c = s_sel[q];
-      s_a[i] = ((c & 4) && (c & 3) == ((y & 1) * 2 + (x & 1))) ? s_pb[q] : 0.f;
-    }
-    __syncthreads();
-    if (active) {
-      for (int y = g; y < HO; y += NG) {
-        const float* arow = s_a + y * HO;
-        const float* irow = s_in + i_off + y * HPP;
-#pragma unroll 2
-        for (int x = 0; x < HO; ++x) {
-          const float iv = irow[x];
+#pragma unroll 1
+    for (int term = 0; term < 2; ++term) {
+      const float* pb = term ? pb2 : pb1;
+      if (!pb) break;
+      const float* ip = (term ? in2 + (size_t)s * ss2 : in1 + (size_t)s * ss1) + (size_t)r * CI * HIN * HIN;
+      for (int i = tid; i < CI * HIN * (HIN / 2); i += NT) {   // interior of the padded input, 64 bits at a time
+        const int c = i / (HIN * (HIN / 2)), yy = (i / (HIN / 2)) % HIN, x2 = i % (HIN / 2);
+        *reinterpret_cast<float2*>(s_in + (c * HP + yy + PAD) * HPP + 2 * x2 + PAD) =
+            *reinterpret_cast<const float2*>(ip + (c * HIN + yy) * HIN + 2 * x2);
+      }
+      const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
+      for (int i = tid; i < CO * HQ * HQ; i += NT) {   // each pooled adjoint owns its 2x2 window of the full-resolution map
+        const int co = i / (HQ * HQ), py = (i / HQ) % HQ, px = i % HQ, c = sel[pbase + i];
+        const float v = (c & 4) ? pb[pbase + i] : 0.f;
+        const int k = c & 3;
+        float* d = s_a + (co * HO + 2 * py) * HOP + 2 * px;
+        *reinterpret_cast<float2*>(d) = make_float2(k == 0 ? v : 0.f, k == 1 ? v : 0.f);
+        *reinterpret_cast<float2*>(d + HOP) = make_float2(k == 2 ? v : 0.f, k == 3 ? v : 0.f);
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll 1
+        for (int y = g; y < HO; y += NG) {
+          const float* irow = s_in + (ci * HP + y + ky) * HPP;
+          const float* arow = s_a + y * HOP;
+#pragma unroll 1
+          for (int x4 = 0; x4 < HOP; x4 += 4) {
+            const float4 i0 = *reinterpret_cast<const float4*>(irow + x4);
+            const float4 i1 = *reinterpret_cast<const float4*>(irow + x4 + 4);
+            const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
-          for (int co = 0; co < CO; ++co) acc[co] = fmaf(arow[co * HO * HO + x], iv, acc[co]);
+            for (int co = 0; co < CO; ++co) {
+              const float4 a4 = *reinterpret_cast<const float4*>(arow + co * HO * HOP + x4);
+              const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int k = 0; k < 5; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[k][co] = fmaf(av[j], iv[j + k], acc[k][co]);
+            }
+          }
         }
       }
-    }
+      if (term == 0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int co = warp + 8 * h;
-      if (co < CO) {
-        float t = 0.f;
-        for (int pos = lane; pos < HO * HO; pos += 32) t += s_a[co * HO * HO + pos];
-        bacc[h] += warp_sum(t);
+        for (int h = 0; h < NB; ++h) {
+          const int co = warp + NW * h;
+          if (co < CO) {
+            float t = 0.f;
+            for (int pos = lane; pos < HO * HOP; pos += 32) t += s_a[co * HO * HOP + pos];
+            bacc[h] += warp_sum(t);
+          }
+        }
       }
+      __syncthreads();
+    }
+  }
+  // reduce over the row groups in fixed order through shared memory, then write this chunk's partial
+#pragma unroll 1
+  for (int gg = 0; gg < NG; ++gg) {
+    if (active && g == gg) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          float* d = s_red + (co * CI + ci) * 25 + ky * 5 + k;
+          *d = gg ? *d + acc[k][co] : acc[k][co];
+        }
     }
     __syncthreads();
   }
-  // reduce over the row groups (fixed order) through shared memory, then write this chunk's partial
-  float* red = s_a;   // NG * NOUT floats <= CO * HO * HO for both layers (conv1: 10 x 150 <= 4704; conv2: 1 x 2400 > 1600 -> NG = 1)
   float* dst = part + ((size_t)chunk * gridDim.y + s) * (NOUT + CO);
-  if (NG == 1) {
-    if (active)
-#pragma unroll
-      for (int co = 0; co < CO; ++co) dst[co * NTAP + tap] = acc[co];
-  } else {
-    if (active)
-#pragma unroll
-      for (int co = 0; co < CO; ++co) red[g * NOUT + co * NTAP + tap] = acc[co];
-    __syncthreads();
-    for (int o = tid; o < NOUT; o += 256) {
-      float t = 0.f;
-      for (int k = 0; k < NG; ++k) t += red[k * NOUT + o];
-      dst[o] = t;
-    }
-  }
+  for (int o = tid; o < NOUT; o += NT) dst[o] = s_red[o];
   if (lane == 0) {
-    if (warp < CO) dst[NOUT + warp] = bacc[0];
-    if (warp + 8 < CO) dst[NOUT + warp + 8] = bacc[1];
+#pragma unroll
+    for (int h = 0; h < NB; ++h)
+      if (warp + NW * h < CO) dst[NOUT + warp + NW * h] = bacc[h];
   }
+}
+
+// CTAs of `kernel` that can be resident on the device at once (one wave)
+template <typename K>
+static int resident_ctas(K kernel, int threads) {
+  int per_sm = 1, dev = 0, sms = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return std::max(1, per_sm) * std::max(1, sms);
 }
 
 // wbar[s][..] (+)= sum_chunks part;  bbar[s][co] = sum_chunks  (bbar nullable)
@@ -659,14 +706,29 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     g.colsum = bb; g.sCol = LN_P;
     bgemm_kernel<false, false><<<dim3(tiles(OUT), tiles(IN), S), 64, 0, st>>>(g);
   };
-  const int rpc = (R + N_CHUNKS - 1) / N_CHUNKS, nch = (R + rpc - 1) / rpc;
-  auto conv2_wgrad = [&](const float* pbv, const float* inp, float* wb, float* bb, int acc) {
-    conv_bwd_weight_kernel<6, 16, 14, 0><<<dim3(nch, S), 256, 0, st>>>(pbv, w.sel2, inp, sR * N_P1, R, rpc, w.wpart);
-    conv_wgrad_reduce_kernel<<<dim3((2416 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 2400, 16, wb, bb, acc);
+  // row chunks of the weight-gradient kernels: as many as fit in ONE wave of resident CTAs (at most N_CHUNKS)
+  auto chunking = [&](int slots, int& rpc, int& nch) {
+    const int target = std::max(1, std::min(N_CHUNKS, slots / S));
+    rpc = (R + target - 1) / target;
+    nch = (R + rpc - 1) / rpc;
   };
-  auto conv1_wgrad = [&](const float* pbv, float* wb, float* bb, int acc) {
-    conv_bwd_weight_kernel<1, 6, 28, 2><<<dim3(nch, S), 256, 0, st>>>(pbv, w.sel1, x, 0, R, rpc, w.wpart);
-    conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 150, 6, wb, bb, acc);
+  auto conv2_wgrad = [&](const float* pb1, const float* i1, const float* pb2, const float* i2, float* wb, float* bb) {
+    using C = ConvWgCfg<6, 16, 14, 0, 5>;
+    auto k = conv_bwd_weight_kernel<6, 16, 14, 0, 5>;
+    static const int slots = resident_ctas(k, C::NT);
+    int rpc, nch;
+    chunking(slots, rpc, nch);
+    k<<<dim3(nch, S), C::NT, 0, st>>>(pb1, i1, sR * N_P1, pb2, i2, sR * N_P1, w.sel2, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((2416 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 2400, 16, wb, bb, 0);
+  };
+  auto conv1_wgrad = [&](const float* pbv, float* wb, float* bb) {
+    using C = ConvWgCfg<1, 6, 28, 2, 28>;
+    auto k = conv_bwd_weight_kernel<1, 6, 28, 2, 28>;
+    static const int slots = resident_ctas(k, C::NT);
+    int rpc, nch;
+    chunking(slots, rpc, nch);
+    k<<<dim3(nch, S), C::NT, 0, st>>>(pbv, x, 0, nullptr, nullptr, 0, w.sel1, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 150, 6, wb, bb, 0);
   };
   // ---- primal forward
   CONV1_FWD(S, R, st, x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, w.sel1, 0, w.p1);
@@ -692,9 +754,9 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     lin_bwd_data(w.g4, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3);
     lin_bwd_weight(w.g3, w.p2, nullptr, nullptr, N_P2, N_H3, tbar + O_W3, tbar + O_B3);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
-    conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
+    conv2_wgrad(w.g2, w.p1, nullptr, nullptr, tbar + O_W2, tbar + O_B2);
     CONV2_BWD(S, R, st, w.g2, theta + O_W2, nullptr, nullptr, w.sel2, w.g1);
-    conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
+    conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1);
     if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, nullptr, nullptr, w.sel1, xbar);
     LN_CHECK();
     return PSVI_OK;
@@ -725,14 +787,13 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   lin_bwd_data(w.g3d, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2d);
   LN_CHECK();
   // conv 2
-  conv2_wgrad(w.g2, w.p1, tbar + O_W2, tbar + O_B2, 0);
-  conv2_wgrad(w.g2d, w.pd1, tbar + O_W2, nullptr, 1);
-  conv2_wgrad(w.g2d, w.p1, tdbar + O_W2, tdbar + O_B2, 0);
+  conv2_wgrad(w.g2, w.p1, w.g2d, w.pd1, tbar + O_W2, tbar + O_B2);
+  conv2_wgrad(w.g2d, w.p1, nullptr, nullptr, tdbar + O_W2, tdbar + O_B2);
   CONV2_BWD(S, R, st, w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, w.g1);
   CONV2_BWD(S, R, st, w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, w.g1d);
   // conv 1
-  conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1, 0);
-  conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1, 0);
+  conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1);
+  conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1);
   if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, xbar);
   LN_CHECK();
   return PSVI_OK;

@@ -118,6 +118,8 @@ _SIGS = {
     "psvi_mf_nkl_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "psvi_mf_nkl_kl": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "psvi_adam_unroll_step": (C.c_int, [C.c_int64, C.c_float, C.c_float] + [C.c_void_p] * 8),
+    "psvi_adam_unroll_reverse": (C.c_int, [C.c_int64, C.c_float, C.c_float] + [C.c_void_p] * 8),
     "psvi_lenet_num_theta": (C.c_int64, []),
     "psvi_lenet_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "psvi_lenet_pass": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
@@ -471,6 +473,23 @@ def mf_reparam_hvp(rho, mud, rhod, eps, A_t, A_td, mask=None):
     _count(1)
     _check(lib().psvi_mf_reparam_hvp(S, P, _p(rho), _p(mud), _p(rhod), _p(eps), _p(A_t), _p(A_td), _p(mask), _p(h), _stream()))
     return h
+
+
+def adam_unroll_step(phi, g, m, v, k, sq2):
+    """One step of the unrolled robust Adam -> (phi', m', v') (new tensors)."""
+    po, mo, vo = torch.empty_like(phi), torch.empty_like(phi), torch.empty_like(phi)
+    _count(1)
+    _check(lib().psvi_adam_unroll_step(phi.numel(), k, sq2, _p(phi), _p(g), _p(m), _p(v), _p(po), _p(mo), _p(vo), _stream()))
+    return po, mo, vo
+
+
+def adam_unroll_reverse(pbar, g, m_t, v_t, mbar, vbar, k, sq2):
+    """Reverse of that step: updates (mbar, vbar) in place and returns gbar."""
+    gbar = torch.empty_like(pbar)
+    _count(1)
+    _check(lib().psvi_adam_unroll_reverse(pbar.numel(), k, sq2, _p(pbar), _p(g), _p(m_t), _p(v_t), _p(mbar), _p(vbar), _p(gbar),
+                                          _stream()))
+    return gbar
 
 
 def mf_nkl_kl(mu, rho, eps, theta, mask=None):

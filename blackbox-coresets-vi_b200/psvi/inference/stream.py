@@ -258,13 +258,16 @@ class StreamEngine:
         self.Pt = fam.Pt
 
     # ---- objectives --------------------------------------------------------------------------------------------------
-    def inner_grad(self, phi, eps, u, z32, a):
+    def inner_grad(self, phi, eps, u, z32, a, want_val=True, a_exp=None, fixed=False):
+        """`a_exp` (a broadcast to [S, M], contiguous) and `fixed` (eps already went through fix_eps) let the unrolled loop
+        hoist the per-call preparation; `want_val=False` skips the objective value."""
         S, M = self.S, u.shape[0]
-        eps = self.fam.fix_eps(eps)
+        if not fixed:
+            eps = self.fam.fix_eps(eps)
         theta = self.fam.sample(phi, eps)
         nll, tbar = torch.empty(S, M, device=u.device), torch.empty(S, self.Pt, device=u.device)
-        self.net.pass_(theta, None, u, z32, a.expand(S, M).contiguous(), nll=nll, tbar=tbar)
-        val = (nll.double() @ a.double()).sum() + self.fam.kl(phi).double()
+        self.net.pass_(theta, None, u, z32, a.expand(S, M).contiguous() if a_exp is None else a_exp, nll=nll, tbar=tbar)
+        val = (nll.double() @ a.double()).sum() + self.fam.kl(phi).double() if want_val else None
         return val, self.fam.grad(phi, eps, tbar, 1.0, 0.0)
 
     ROW_CHUNK = 8192   # data rows per network pass when the minibatch is large (full-data term, sharded over ranks)
@@ -351,13 +354,15 @@ class StreamEngine:
             pbar = self.fam.grad(phi, eps, tbar + beta[:, None] * self.fam.nkl_theta_grad(theta), 0.0, float(beta.sum()))
         return loss.float(), pbar
 
-    def hvp(self, phi, eps, u, z32, a, phidot):
+    def hvp(self, phi, eps, u, z32, a, phidot, a_exp=None, fixed=False):
         S, M, dev = self.S, u.shape[0], u.device
-        eps = self.fam.fix_eps(eps)
+        if not fixed:
+            eps = self.fam.fix_eps(eps)
         theta, thetad = self.fam.sample(phi, eps), self.fam.tangent(phi, phidot, eps)
         tbar, tdbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, self.Pt, device=dev)
         xbar, ac = torch.empty(S, M, u.shape[1], device=dev), torch.empty(S, M, device=dev)
-        self.net.pass_(theta, thetad, u, z32, a.expand(S, M).contiguous(), tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
+        self.net.pass_(theta, thetad, u, z32, a.expand(S, M).contiguous() if a_exp is None else a_exp, tbar=tbar, tdbar=tdbar,
+                       xbar=xbar, acbar=ac)
         return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
@@ -368,18 +373,17 @@ class StreamEngine:
         all-reduces (loss, pbar, ubar, abar) -- the ONE exchange step of the bilevel step; the inner loop and
         the reverse sweep are replicated (identical seeds => identical trajectories on every rank)."""
         eps_all = self.fam.fix_eps(eps_all)
+        a_exp = a.expand(self.S, u.shape[0]).contiguous()
+        phi = phi.contiguous()
         m, v = torch.zeros_like(phi), torch.zeros_like(phi)
         traj, losses = [], []
         for t in range(T):
-            val, g = self.inner_grad(phi, eps_all[t], u, z32, a)
+            val, g = self.inner_grad(phi, eps_all[t], u, z32, a, want_val=want_losses, a_exp=a_exp, fixed=True)
             if want_losses:
                 losses.append(val)
-            m = m * B1 + OMB1 * g
-            v = v * B2 + OMB2 * g * g
-            sq2 = math.sqrt(1.0 - B2 ** (t + 1))
-            den = torch.sqrt(v + 1e-8) / sq2 + AEPS
+            phi_new, m, v = _native.adam_unroll_step(phi, g, m, v, lr / (1.0 - B1 ** (t + 1)), math.sqrt(1.0 - B2 ** (t + 1)))
             traj.append((phi, g, m, v))
-            phi = phi - (lr / (1.0 - B1 ** (t + 1))) * (m / den)
+            phi = phi_new
         if outer == "ablated":
             loss, pbar = self.outer_grad_ablated(phi, eps_all[T], xb, yb32, N, kappa=kappa, n_total=n_total)
             ubar, abar = torch.zeros_like(u), torch.zeros_like(a)
@@ -388,19 +392,13 @@ class StreamEngine:
         if reduce_fn is not None:
             loss, pbar, ubar, abar = reduce_fn(loss, pbar, ubar, abar)
         phi_T = phi
+        pbar = pbar.contiguous()
         mbar, vbar = torch.zeros_like(pbar), torch.zeros_like(pbar)
         for t in range(T - 1, -1, -1):
             phi_t, g, m_t, v_t = traj[t]
-            k = lr / (1.0 - B1 ** (t + 1))
-            sq2 = math.sqrt(1.0 - B2 ** (t + 1))
-            q = torch.sqrt(v_t + 1e-8)
-            den = q / sq2 + AEPS
-            mb = mbar - k * pbar / den
-            vb = vbar + (k * pbar * m_t / (den * den)) / (2.0 * q * sq2)
-            vb = torch.where(v_t == 0, torch.zeros_like(vb), vb)       # _maybe_mask hook (optim.py:40-52,346-347)
-            gbar = OMB1 * mb + 2.0 * OMB2 * g * vb
-            mbar, vbar = B1 * mb, B2 * vb
-            h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar)
+            gbar = _native.adam_unroll_reverse(pbar, g, m_t, v_t, mbar, vbar, lr / (1.0 - B1 ** (t + 1)),
+                                               math.sqrt(1.0 - B2 ** (t + 1)))
+            h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar, a_exp=a_exp, fixed=True)
             pbar, ubar, abar = pbar + h, ubar + hu, abar + ha
         return loss, ubar, abar, phi_T, (torch.stack(losses).float() if want_losses else None)
 

@@ -302,6 +302,16 @@ size_t psvi_mf_nkl_scratch_bytes(int32_t S);
 int psvi_mf_nkl_kl(int32_t S, int64_t P, const float* mu, const float* rho, const float* eps, const float* theta, const float* mask,
                    double* out, void* scratch, void* stream);
 
+/* ---- the unrolled robust Adam of the inner loop, one fused elementwise kernel per direction.  Replace the tensor expressions
+ * of DifferentiableAdam._update and what autograd replays through them (psvi/robust_higher/optim.py:303-367, the
+ * _maybe_mask hook at optim.py:40-52).  k = lr / (1 - 0.9^t), sq2 = sqrt(1 - 0.999^t), t = 1-based step.
+ *   psvi_adam_unroll_step:    (phi, g, m, v) -> (phi', m', v')
+ *   psvi_adam_unroll_reverse: (pbar; g, m', v'; mbar, vbar in/out) -> gbar, the adjoint of this step's gradient g */
+int psvi_adam_unroll_step(int64_t n, float k, float sq2, const float* phi, const float* g, const float* m, const float* v,
+                          float* phi_out, float* m_out, float* v_out, void* stream);
+int psvi_adam_unroll_reverse(int64_t n, float k, float sq2, const float* pbar, const float* g, const float* m_t, const float* v_t,
+                             float* mbar, float* vbar, float* gbar, void* stream);
+
 /* ---- noise: the in-kernel generator, exposed so that callers/tests can materialise the exact slabs a PHILOX-mode
  * call consumes.  out [n_slabs][S][P]. */
 int psvi_philox_normal(uint64_t seed, uint32_t domain, int32_t first_slab, int32_t n_slabs, int32_t S, int32_t P,

@@ -1,0 +1,41 @@
+"""Is the lenet outer step host-bound? Compares wall time per step with the sum of kernel durations (torch profiler)."""
+import sys, os, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "blackbox-coresets-vi_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from psvi.inference.psvi_classes import PSVILearnV
+from tests.fake_mnist import FakeMNIST
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+tr, te = FakeMNIST(2000, 0), FakeMNIST(512, 1)
+kw = dict(mc_samples=10, num_epochs=0, data_minibatch=128, D=784, N=len(tr), inner_it=T, trainer="nested", log_every=10,
+          lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-3, num_pseudo=200, seed=0,
+          architecture="lenet", n_hidden=0, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+          dnm="MNIST", nc=10, compute_weights_entropy=True, register_elbos=False, quiet=True)
+obj = PSVILearnV(**kw)
+obj.run_psvi(**kw)
+xb, yb = obj._next_minibatch()
+for _ in range(3):
+    obj.nested_step(xb, yb)
+torch.cuda.synchronize()
+t0 = time.time()
+for _ in range(3):
+    obj.nested_step(xb, yb)
+t_enq = (time.time() - t0) / 3
+torch.cuda.synchronize()
+t_all = (time.time() - t0) / 3
+print(f"T={T}: host enqueue {1e3*t_enq:.1f} ms/step, wall {1e3*t_all:.1f} ms/step")
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    obj.nested_step(xb, yb)
+    torch.cuda.synchronize()
+ev = prof.events()
+from collections import defaultdict
+d = defaultdict(lambda: [0, 0.0])
+tot = 0.0
+for e in ev:
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        d[e.name[:60]][0] += 1; d[e.name[:60]][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+        tot += e.device_time if hasattr(e, "device_time") else e.cuda_time
+print(f"sum of device activity {tot/1e3:.1f} ms over {sum(v[0] for v in d.values())} launches")
+for k, v in sorted(d.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"  {v[1]/tot*100:5.1f}% n={v[0]:5d} avg {v[1]/v[0]:7.1f} us  {k}")
