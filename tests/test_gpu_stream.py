@@ -176,3 +176,41 @@ def test_fused_meanfield_family_kernels_match_formulas(masked):
                      sig * (t64 * e64).sum(0) + sig * (1 - sig) * rd * (Atd.double() * e64).sum(0)
                      + mk * ((1 + 1 / sg ** 2) * sig ** 2 + (sg - 1 / sg) * sig * (1 - sig)) * rd])
     assert rel_l2(h.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("t", [1, 7, 100])
+def test_fused_unrolled_adam_kernels_match_the_tensor_expressions(t):
+    """psvi_adam_unroll_step / _reverse against the reference's tensor expressions (robust_higher/optim.py:303-367 and what
+    autograd replays through them), evaluated in fp32 by torch op by op and in float64 by autograd."""
+    import math
+    from psvi import _native
+    torch.manual_seed(t)
+    n, lr, B1, B2 = 5003, 1e-3, 0.9, 0.999
+    phi, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda") * 10 ** torch.randint(-6, 2, (n,), device="cuda").float()
+    m, v = torch.randn(n, device="cuda") * 0.1, torch.rand(n, device="cuda") * 0.01
+    g[:17], v[:17] = 0.0, 0.0          # exercises the v' == 0 mask of the reverse sweep
+    k, sq2 = lr / (1.0 - B1 ** t), math.sqrt(1.0 - B2 ** t)
+    # forward, fp32 op by op (the order stream.py used before the fused kernel)
+    m_ref = m * B1 + float(1.0 - B1) * g
+    v_ref = v * B2 + float(1.0 - B2) * g * g
+    phi_ref = phi - k * (m_ref / (torch.sqrt(v_ref + 1e-8) / sq2 + 1e-8))
+    phi_n, m_n, v_n = _native.adam_unroll_step(phi, g, m, v, k, sq2)
+    assert torch.equal(m_n, m_ref) and torch.equal(v_n, v_ref)
+    # (ATen divides by a host scalar as a multiplication by its reciprocal: last-ulp differences in the denominator)
+    torch.testing.assert_close(phi_n, phi_ref, rtol=5e-6, atol=1e-7)
+    # reverse against float64 autograd of the same step
+    pbar, mbar, vbar = torch.randn(n, device="cuda"), torch.randn(n, device="cuda"), torch.randn(n, device="cuda") * 100
+    gd = g.double().requires_grad_(True)
+    md = m.double() * B1 + (1.0 - B1) * gd
+    vd = v.double() * B2 + (1.0 - B2) * gd * gd
+    vd.register_hook(lambda gr: torch.where(vd.detach() == 0, torch.zeros_like(gr), gr))
+    phid = phi.double() - k * (md / (torch.sqrt(vd + 1e-8) / sq2 + 1e-8))
+    mdn, vdn = md * 1.0, vd * 1.0
+    (gbar_ref,) = torch.autograd.grad([phid, mdn, vdn], [gd], [pbar.double(), mbar.double(), vbar.double()])
+    mb_in, vb_in = mbar.clone(), vbar.clone()
+    gbar = _native.adam_unroll_reverse(pbar, g, m_n, v_n, mb_in, vb_in, k, sq2)
+    assert rel_l2(gbar.cpu().numpy(), gbar_ref.cpu().numpy()) < 2e-6
+    torch.testing.assert_close(gbar[:17], float(1.0 - B1) * (mbar[:17] - k * pbar[:17] / (math.sqrt(1e-8) / sq2 + 1e-8)), rtol=1e-5,
+                               atol=0)
+    torch.testing.assert_close(vb_in[:17], torch.zeros(17, device="cuda"), rtol=0, atol=0)
