@@ -488,6 +488,60 @@ __global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int 
   *d = accumulate ? *d + t : t;
 }
 
+// The three weighted column reductions of the dual pass in ONE sweep over hh = [hdot | h] (each element read once):
+//   part[z][s][0][c][h] = sum_r (Wo[s][r][c] h[s][r][h] + Wod[s][r][c] hdot[s][r][h])     (A_o^T h + A_od^T hdot)
+//   part[z][s][1][c][h] = sum_r Wod[s][r][c] h[s][r][h]                                   (A_od^T h)
+template <int X3>
+__global__ void __launch_bounds__(128)
+fnl_colreduce_dual_kernel(const void* Yh, const void* Yl, long long y_bs, const float* __restrict__ Wo,
+                          const float* __restrict__ Wod, int R, int H, int C, float* __restrict__ part) {
+  const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, zc = blockIdx.z;
+  if (h >= H) return;
+  const int rpc = (R + RSPLIT - 1) / RSPLIT, r0 = zc * rpc, r1 = min(R, r0 + rpc);
+  float a1[CW], a2[CW];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) a1[c] = a2[c] = 0.f;
+  const size_t y0 = (size_t)((long long)s * y_bs + h);
+  const float4* wo = reinterpret_cast<const float4*>(Wo + (size_t)s * R * CW);
+  const float4* wd = reinterpret_cast<const float4*>(Wod + (size_t)s * R * CW);
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const float hd = get<X3>(Yh, Yl, y0 + (size_t)r * 2 * H), hv = get<X3>(Yh, Yl, y0 + (size_t)r * 2 * H + H);
+#pragma unroll
+    for (int q = 0; q < CW / 4; ++q) {
+      const float4 u = __ldg(wo + r * (CW / 4) + q), v = __ldg(wd + r * (CW / 4) + q);
+      a1[4 * q + 0] = fmaf(u.x, hv, fmaf(v.x, hd, a1[4 * q + 0]));
+      a1[4 * q + 1] = fmaf(u.y, hv, fmaf(v.y, hd, a1[4 * q + 1]));
+      a1[4 * q + 2] = fmaf(u.z, hv, fmaf(v.z, hd, a1[4 * q + 2]));
+      a1[4 * q + 3] = fmaf(u.w, hv, fmaf(v.w, hd, a1[4 * q + 3]));
+      a2[4 * q + 0] = fmaf(v.x, hv, a2[4 * q + 0]);
+      a2[4 * q + 1] = fmaf(v.y, hv, a2[4 * q + 1]);
+      a2[4 * q + 2] = fmaf(v.z, hv, a2[4 * q + 2]);
+      a2[4 * q + 3] = fmaf(v.w, hv, a2[4 * q + 3]);
+    }
+  }
+  float* p1 = part + (((size_t)zc * gridDim.y + s) * 2) * C * H;
+  for (int c = 0; c < C; ++c) {
+    p1[(size_t)c * H + h] = a1[c];
+    p1[(size_t)(C + c) * H + h] = a2[c];
+  }
+}
+// out1[s * P + i] = sum_z part[z][s][0][i], out2[s * P + i] = sum_z part[z][s][1][i]   (i = c * H + h)
+__global__ void fnl_colreduce_dual_finish_kernel(const float* __restrict__ part, int S, int H, int C, float* __restrict__ out1,
+                                                 float* __restrict__ out2, long long P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (i >= C * H) return;
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int zc = 0; zc < RSPLIT; ++zc) {
+    const float* q = part + (((size_t)zc * S + s) * 2) * C * H;
+    t1 += q[i];
+    t2 += q[(size_t)C * H + i];
+  }
+  out1[(long long)s * P + i] = t1;
+  out2[(long long)s * P + i] = t2;
+}
+
 // out[s * P + h] = sum_r YT[s][h][r]   (row sums of a transposed operand array; one warp per row, fixed order)
 template <int X3>
 __global__ void __launch_bounds__(256)
@@ -548,7 +602,7 @@ void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
   w.od = (float*)take((size_t)S * Rp * CW * 4);
   w.go = (float*)take((size_t)S * R * CW * 4);
   w.god = (float*)take((size_t)S * R * CW * 4);
-  w.cpart = (float*)take((size_t)RSPLIT * S * CW * H * 4);
+  w.cpart = (float*)take((size_t)RSPLIT * S * 2 * CW * H * 4);
   w.total = off;
 }
 
@@ -766,11 +820,12 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
       if ((rc = launch_gemm<X3>(opAAh, opW1TT, p, sms, st))) return rc;
     }
   }
-  colreduce(w.aa, 0, nullptr, 1, tbar + o_b1, 0);      // A_b1
-  colreduce(w.aa, H, nullptr, 1, tdbar + o_b1, 0);     // A_b1dot
-  colreduce(w.hh, H, w.go, C, tbar + o_w2, 0);         // A_o^T h
-  colreduce(w.hh, 0, w.god, C, tbar + o_w2, 1);        // + A_od^T hdot
-  colreduce(w.hh, H, w.god, C, tdbar + o_w2, 0);       // A_od^T h
+  // A_b1 / A_b1dot: row sums of the transposed adjoints (coalesced along r);  A_W2 = A_o^T h + A_od^T hdot and
+  // A_W2dot = A_od^T h in one sweep over hh
+  fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);
+  fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.adT.hi, w.adT.lo, H, Rp, R, tdbar + o_b1, P);
+  fnl_colreduce_dual_kernel<X3><<<dim3(H / 128, S, RSPLIT), 128, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
+  fnl_colreduce_dual_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, C, tbar + o_w2, tdbar + o_w2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.god, R, C, tdbar + o_b2, P);
   PSVI_CUDA_CHECK(cudaGetLastError());
