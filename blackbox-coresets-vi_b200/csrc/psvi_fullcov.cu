@@ -61,6 +61,73 @@ __global__ void fc_outer_kernel(int n, int S, const float* __restrict__ A, int l
   }
 }
 
+// ---- the same two operations working directly on the layer's parameter block phi = [mean | _sd | _corr] (and a direction
+// phidot of the same layout), with the softplus / sigmoid transforms and the KL / nkl terms folded in: the streaming
+// engine's family maps for fn2 are then one launch per layer instead of ~15 elementwise launches.
+//   sample : theta[s]    = mean + L eps[s],         L: diag softplus(_sd), off _corr
+//   tangent: thetadot[s] = meandot + Ldot eps[s],   Ldot: diag sigmoid(_sd) _sddot, off _corrdot
+__global__ void fc_sample_kernel(int n, int S, const float* __restrict__ phi, const float* __restrict__ phid,
+                                 const float* __restrict__ eps, int ld_eps, float* __restrict__ out, int ld_out) {
+  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_off = r >= 1 && r <= n - 2;
+  const float* src = phid ? phid : phi;
+  const float* row = src + 2 * (size_t)n + (size_t)r * (r - 1) / 2;
+  const float base = src[r];
+  const float dg = phid ? sigmoid_f(phi[n + r]) * phid[n + r] : softplus_f(phi[n + r]);
+  for (int s = warp; s < S; s += 8) {
+    const float* e = eps + (size_t)s * ld_eps;
+    float acc = 0.f;
+    if (has_off)
+      for (int c = lane; c < r; c += 32) acc = fmaf(__ldg(row + c), __ldg(e + c), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)s * ld_out + r] = base + dg * e[r] + acc;
+  }
+}
+
+// MODE 0 (gradient): g = [sum_s A + kl m | sig (sum_s A eps + kl (d - 1/d) + nkl / d) | sum_s A[:, r] eps[:, c] + kl corr]
+// MODE 1 (HVP, SURVEY A.6 for the Cholesky family): h = [sum_s A + mdot |
+//          sig sum_s A eps + sig (1 - sig) sddot sum_s Ad eps + ((1 + 1/d^2) sig^2 + (d - 1/d) sig (1 - sig)) sddot |
+//          sum_s A[:, r] eps[:, c] + corrdot]          (d = softplus(_sd), sig = sigmoid(_sd))
+template <int MODE>
+__global__ void fc_reparam_kernel(int n, int S, const float* __restrict__ phi, const float* __restrict__ phid,
+                                  const float* __restrict__ A, const float* __restrict__ Ad, int ld_a,
+                                  const float* __restrict__ eps, int ld_eps, float kl_coef, float nkl_coef,
+                                  float* __restrict__ g) {
+  const int r = blockIdx.x;
+  if (r == n) {  // vector parts
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float a = 0.f, b = 0.f, bd = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const float e = eps[(size_t)s * ld_eps + i], v = A[(size_t)s * ld_a + i];
+        a += v;
+        b = fmaf(v, e, b);
+        if (MODE == 1) bd = fmaf(Ad[(size_t)s * ld_a + i], e, bd);
+      }
+      const float sd = phi[n + i], d = softplus_f(sd), sig = sigmoid_f(sd);
+      if (MODE == 0) {
+        g[i] = a + kl_coef * phi[i];
+        g[n + i] = sig * (b + kl_coef * (d - 1.f / d) + nkl_coef / d);
+      } else {
+        const float sdd = phid[n + i];
+        g[i] = a + phid[i];
+        g[n + i] = sig * b + sig * (1.f - sig) * sdd * bd +
+                   ((1.f + 1.f / (d * d)) * sig * sig + (d - 1.f / d) * sig * (1.f - sig)) * sdd;
+      }
+    }
+    return;
+  }
+  if (r < 1 || r > n - 2) return;
+  extern __shared__ float ar[];  // A[:, r]
+  for (int s = threadIdx.x; s < S; s += blockDim.x) ar[s] = A[(size_t)s * ld_a + r];
+  __syncthreads();
+  const size_t k0 = 2 * (size_t)n + (size_t)r * (r - 1) / 2;
+  for (int c = threadIdx.x; c < r; c += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc = fmaf(ar[s], __ldg(eps + (size_t)s * ld_eps + c), acc);
+    g[k0 + c] = acc + (MODE == 0 ? kl_coef * phi[k0 + c] : phid[k0 + c]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -77,6 +144,32 @@ int psvi_fc_outer(int32_t n, int32_t S, const float* A, int32_t ld_a, const floa
                   float* g_dg, float* g_off, void* stream) {
   PSVI_REQUIRE(n >= 1 && S >= 1 && A && eps && g_base && g_dg && (n < 3 || g_off), PSVI_ERR_INVALID, "bad argument");
   fc_outer_kernel<<<n + 1, 256, S * sizeof(float), (cudaStream_t)stream>>>(n, S, A, ld_a, eps, ld_eps, g_base, g_dg, g_off);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_fc_sample(int32_t n, int32_t S, const float* phi, const float* phidot, const float* eps, int32_t ld_eps, float* out,
+                   int32_t ld_out, void* stream) {
+  PSVI_REQUIRE(n >= 1 && S >= 1 && phi && eps && out, PSVI_ERR_INVALID, "bad argument");
+  fc_sample_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, S, phi, phidot, eps, ld_eps, out, ld_out);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_fc_reparam_grad(int32_t n, int32_t S, const float* phi, const float* A, int32_t ld_a, const float* eps, int32_t ld_eps,
+                         float kl_coef, float nkl_coef, float* g, void* stream) {
+  PSVI_REQUIRE(n >= 1 && S >= 1 && phi && A && eps && g, PSVI_ERR_INVALID, "bad argument");
+  fc_reparam_kernel<0><<<n + 1, 256, S * sizeof(float), (cudaStream_t)stream>>>(n, S, phi, nullptr, A, nullptr, ld_a, eps, ld_eps,
+                                                                               kl_coef, nkl_coef, g);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  return PSVI_OK;
+}
+
+int psvi_fc_reparam_hvp(int32_t n, int32_t S, const float* phi, const float* phidot, const float* A_t, const float* A_td,
+                        int32_t ld_a, const float* eps, int32_t ld_eps, float* h, void* stream) {
+  PSVI_REQUIRE(n >= 1 && S >= 1 && phi && phidot && A_t && A_td && eps && h, PSVI_ERR_INVALID, "bad argument");
+  fc_reparam_kernel<1><<<n + 1, 256, S * sizeof(float), (cudaStream_t)stream>>>(n, S, phi, phidot, A_t, A_td, ld_a, eps, ld_eps, 0.f,
+                                                                               0.f, h);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

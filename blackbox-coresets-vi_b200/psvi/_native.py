@@ -118,6 +118,12 @@ _SIGS = {
     "psvi_mf_nkl_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "psvi_mf_nkl_kl": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "psvi_fc_sample": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.c_void_p]),
+    "psvi_fc_reparam_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p]),
+    "psvi_fc_reparam_hvp": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "psvi_adam_unroll_step": (C.c_int, [C.c_int64, C.c_float, C.c_float] + [C.c_void_p] * 8),
     "psvi_adam_unroll_reverse": (C.c_int, [C.c_int64, C.c_float, C.c_float] + [C.c_void_p] * 8),
     "psvi_lenet_num_theta": (C.c_int64, []),
@@ -393,6 +399,22 @@ def fc_matvec(n, S, base, dg, off, eps_ptr, ld_eps, out_ptr, ld_out):
 def fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, g_base, g_dg, g_off):
     _count(1)
     _check(lib().psvi_fc_outer(n, S, a_ptr, ld_a, eps_ptr, ld_eps, _p(g_base), _p(g_dg), _p(g_off), _stream()))
+
+
+def fc_sample(n, S, phi_ptr, phid_ptr, eps_ptr, ld_eps, out_ptr, ld_out):
+    """Raw device addresses: the layer's block of phi (and of a direction, or None), eps / out at the layer's offset."""
+    _count(1)
+    _check(lib().psvi_fc_sample(n, S, phi_ptr, phid_ptr, eps_ptr, ld_eps, out_ptr, ld_out, _stream()))
+
+
+def fc_reparam_grad(n, S, phi_ptr, a_ptr, ld_a, eps_ptr, ld_eps, kl_coef, nkl_coef, g_ptr):
+    _count(1)
+    _check(lib().psvi_fc_reparam_grad(n, S, phi_ptr, a_ptr, ld_a, eps_ptr, ld_eps, kl_coef, nkl_coef, g_ptr, _stream()))
+
+
+def fc_reparam_hvp(n, S, phi_ptr, phid_ptr, at_ptr, atd_ptr, ld_a, eps_ptr, ld_eps, h_ptr):
+    _count(1)
+    _check(lib().psvi_fc_reparam_hvp(n, S, phi_ptr, phid_ptr, at_ptr, atd_ptr, ld_a, eps_ptr, ld_eps, h_ptr, _stream()))
 
 
 _lenet_ws = {}

@@ -135,21 +135,27 @@ class FullCovFamily:
             out.append((phi[o:o + n], phi[o + n:o + 2 * n], phi[o + 2 * n:o + 2 * n + c], n))
         return out
 
-    def _matvec(self, parts, eps):
+    @staticmethod
+    def _f32c(t):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise _native.NativeError("expected a contiguous CUDA float32 tensor")
+        return t
+
+    def _sample(self, phi, phidot, eps):
         S = eps.shape[0]
+        phi, eps = self._f32c(phi), self._f32c(eps)
+        pd = None if phidot is None else self._f32c(phidot).data_ptr()
         out = torch.empty(S, self.Pt, device=eps.device)
-        for (base, dg, off, n), t in zip(parts, self.toffs):
-            _native.fc_matvec(n, S, base.contiguous(), dg.contiguous(), off.contiguous(), eps.data_ptr() + 4 * t, self.Pt,
+        for o, n, t in zip(self.offs, self.ns, self.toffs):
+            _native.fc_sample(n, S, phi.data_ptr() + 4 * o, None if pd is None else pd + 4 * o, eps.data_ptr() + 4 * t, self.Pt,
                               out.data_ptr() + 4 * t, self.Pt)
         return out
 
     def sample(self, phi, eps):
-        return self._matvec([(m, F.softplus(sd), corr, n) for (m, sd, corr, n) in self._split(phi)], eps)
+        return self._sample(phi, None, eps)
 
     def tangent(self, phi, phidot, eps):
-        parts = [(md, torch.sigmoid(sd) * sdd, corrd, n)
-                 for (m, sd, corr, n), (md, sdd, corrd, _) in zip(self._split(phi), self._split(phidot))]
-        return self._matvec(parts, eps)
+        return self._sample(phi, phidot, eps)
 
     def kl(self, phi):
         t = 0.0
@@ -162,31 +168,23 @@ class FullCovFamily:
         logdet = sum(torch.log(F.softplus(sd)).double().sum() for (_, sd, _, _) in self._split(phi))
         return -0.5 * (theta.double() ** 2).sum(1) + 0.5 * (eps.double() ** 2).sum(1) + logdet
 
-    def _outer(self, A, eps, n, c, t):
-        S = eps.shape[0]
-        gb, gd = torch.empty(n, device=eps.device), torch.empty(n, device=eps.device)
-        go = torch.zeros(max(c, 1), device=eps.device)
-        _native.fc_outer(n, S, A.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t, self.Pt, gb, gd, go)
-        return gb, gd, go[:c]
-
     def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
-        out = []
-        for (m, sd, corr, n), c, t in zip(self._split(phi), self.ncs, self.toffs):
-            gb, gd, go = self._outer(tbar, eps, n, c, t)
-            d, sig = F.softplus(sd), torch.sigmoid(sd)
-            out += [gb + kl_coef * m, sig * (gd + kl_coef * (d - 1 / d) + nkl_coef / d), go + kl_coef * corr]
-        return torch.cat(out)
+        S = eps.shape[0]
+        phi, eps, tbar = self._f32c(phi), self._f32c(eps), self._f32c(tbar)
+        g = torch.empty_like(phi)
+        for o, n, t in zip(self.offs, self.ns, self.toffs):
+            _native.fc_reparam_grad(n, S, phi.data_ptr() + 4 * o, tbar.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t,
+                                    self.Pt, kl_coef, nkl_coef, g.data_ptr() + 4 * o)
+        return g
 
     def hvp(self, phi, phidot, eps, A_t, A_td):
-        out = []
-        for (m, sd, corr, n), (md, sdd, corrd, _), c, t in zip(self._split(phi), self._split(phidot), self.ncs, self.toffs):
-            gb, gd, go = self._outer(A_t, eps, n, c, t)
-            _, gdd, _ = self._outer(A_td, eps, n, c, t)
-            d, sig = F.softplus(sd), torch.sigmoid(sd)
-            out += [gb + md,
-                    sig * gd + sig * (1 - sig) * sdd * gdd + ((1 + 1 / (d * d)) * sig * sig + (d - 1 / d) * sig * (1 - sig)) * sdd,
-                    go + corrd]
-        return torch.cat(out)
+        S = eps.shape[0]
+        phi, phidot, eps, A_t, A_td = (self._f32c(x) for x in (phi, phidot, eps, A_t, A_td))
+        h = torch.empty_like(phi)
+        for o, n, t in zip(self.offs, self.ns, self.toffs):
+            _native.fc_reparam_hvp(n, S, phi.data_ptr() + 4 * o, phidot.data_ptr() + 4 * o, A_t.data_ptr() + 4 * t,
+                                   A_td.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t, self.Pt, h.data_ptr() + 4 * o)
+        return h
 
 
 class MlpNet:

@@ -212,6 +212,19 @@ int psvi_fc_matvec(int32_t n, int32_t S, const float* base, const float* dg, con
                    int32_t ld_eps, float* out, int32_t ld_out, void* stream);
 int psvi_fc_outer(int32_t n, int32_t S, const float* A, int32_t ld_a, const float* eps, int32_t ld_eps, float* g_base,
                   float* g_dg, float* g_off, void* stream);
+/* The same two operations on the layer's parameter block phi = [mean | _sd | _corr] (2n + (n-1)(n-2)/2 floats, the
+ * parameters_to_vector order of VILinearMultivariateNormal) with the transforms folded in (diag = softplus(_sd)) -- what
+ * rsample / kl / sampled_nkl and autograd compute through scale_tril (neural_net.py:435-472):
+ *   psvi_fc_sample:       phidot == NULL: theta[s] = mean + L eps[s];  else the tangent meandot + Ldot eps[s],
+ *                         Ldot: diag sigmoid(_sd) _sddot, off _corrdot
+ *   psvi_fc_reparam_grad: g [2n + c] = d/dphi of (sum_s <A[s], theta[s]> + kl_coef KL + nkl_coef sum log diag)
+ *   psvi_fc_reparam_hvp:  h [2n + c] from A_theta, A_thetadot along phidot (SURVEY A.6 carried over to the Cholesky family) */
+int psvi_fc_sample(int32_t n, int32_t S, const float* phi, const float* phidot, const float* eps, int32_t ld_eps, float* out,
+                   int32_t ld_out, void* stream);
+int psvi_fc_reparam_grad(int32_t n, int32_t S, const float* phi, const float* A, int32_t ld_a, const float* eps, int32_t ld_eps,
+                         float kl_coef, float nkl_coef, float* g, void* stream);
+int psvi_fc_reparam_hvp(int32_t n, int32_t S, const float* phi, const float* phidot, const float* A_t, const float* A_td,
+                        int32_t ld_a, const float* eps, int32_t ld_eps, float* h, void* stream);
 
 /* ---- tensor-core full-data predictive pass for the single-layer model (logistic_regression): the HBM-bound member of
  * the predictive kernels.  Same quantities as psvi_mf_evaluate (PSVI.evaluate,
