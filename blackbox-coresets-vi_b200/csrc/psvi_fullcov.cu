@@ -68,19 +68,31 @@ __global__ void fc_outer_kernel(int n, int S, const float* __restrict__ A, int l
 //   tangent: thetadot[s] = meandot + Ldot eps[s],   Ldot: diag sigmoid(_sd) _sddot, off _corrdot
 __global__ void fc_sample_kernel(int n, int S, const float* __restrict__ phi, const float* __restrict__ phid,
                                  const float* __restrict__ eps, int ld_eps, float* __restrict__ out, int ld_out) {
-  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // longest rows first (row r costs r); a warp carries four samples at once so that a triangle element is loaded once per
+  // four FMAs and five independent loads are in flight per lane
+  const int r = n - 1 - blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_off = r >= 1 && r <= n - 2;
   const float* src = phid ? phid : phi;
   const float* row = src + 2 * (size_t)n + (size_t)r * (r - 1) / 2;
   const float base = src[r];
   const float dg = phid ? sigmoid_f(phi[n + r]) * phid[n + r] : softplus_f(phi[n + r]);
-  for (int s = warp; s < S; s += 8) {
-    const float* e = eps + (size_t)s * ld_eps;
-    float acc = 0.f;
-    if (has_off)
-      for (int c = lane; c < r; c += 32) acc = fmaf(__ldg(row + c), __ldg(e + c), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) out[(size_t)s * ld_out + r] = base + dg * e[r] + acc;
+  for (int s0 = warp * 4; s0 < S; s0 += 32) {
+    const float* e[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = eps + (size_t)min(s0 + j, S - 1) * ld_eps;
+    if (has_off) {
+      for (int c = lane; c < r; c += 32) {
+        const float l = __ldg(row + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(l, __ldg(e[j] + c), acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = warp_sum(acc[j]);
+      if (lane == 0 && s0 + j < S) out[(size_t)(s0 + j) * ld_out + r] = base + dg * e[j][r] + t;
+    }
   }
 }
 
@@ -93,8 +105,8 @@ __global__ void fc_reparam_kernel(int n, int S, const float* __restrict__ phi, c
                                   const float* __restrict__ A, const float* __restrict__ Ad, int ld_a,
                                   const float* __restrict__ eps, int ld_eps, float kl_coef, float nkl_coef,
                                   float* __restrict__ g) {
-  const int r = blockIdx.x;
-  if (r == n) {  // vector parts
+  const int r = blockIdx.x == 0 ? n : n - blockIdx.x;   // block 0: the vector parts; then the longest rows first
+  if (r == n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       float a = 0.f, b = 0.f, bd = 0.f;
       for (int s = 0; s < S; ++s) {
