@@ -412,9 +412,9 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int n_c
 // The three matrix products of a fully connected layer (forward, data adjoint, weight gradient) are all instances of one
 // per-sample batched product   out[s][m][n] (+)= sum_k A1[s](m, k) B1[s](n, k) (+ sum_k A2[s](m, k) B2[s](n, k))
 // with either operand stored k-contiguous (KC) or m/n-contiguous.  The matrices are small (at most 200 x 400 x 120 per
-// sample) and L2-resident, so the kernel is built for latency: 32 x 32 output tiles (many CTAs), 32-deep k tiles whose
-// global loads for tile t + 1 are all in flight while tile t is multiplied out of shared memory, 4 x 4 register micro-tiles
-// fed by two 128-bit shared loads per k.  Epilogue: + bias[n], relu, mask by (maskfrom > 0), accumulate into out; optional
+// sample) and L2-resident, so the kernel is built for latency: 32 x 32 output tiles (many CTAs), 32-deep k tiles in a
+// 4-stage cp.async ring (three tiles in flight while one is multiplied out of shared memory), 2 x 2 register micro-tiles
+// on 256 threads (4 x 4 on 64 threads left the SMs with two warps each: measured 3x slower).  Epilogue: + bias[n], relu, mask by (maskfrom > 0), accumulate into out; optional
 // column sums  colsum[s][m] = sum_k A1(m, k)  (the bias gradient of the weight-gradient product), in fixed order.
 struct BGemm {
   const float *A1, *B1, *A2, *B2;
@@ -429,81 +429,100 @@ struct BGemm {
 };
 constexpr int G_T = 32, G_P = 36;   // tile edge (m, n and k) and shared-memory pitch
 
-template <bool AKC, bool BKC>
-__global__ void __launch_bounds__(64)
+constexpr int G_ST = 4;   // k tiles in flight (cp.async ring)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;   // 0 source bytes: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool AKC, bool BKC, int TM, int TN>
+__global__ void __launch_bounds__((G_T / TM) * (G_T / TN))
 bgemm_kernel(const BGemm p) {
-  __shared__ __align__(16) float As[G_T][G_P], Bs[G_T][G_P];   // [k][m], [k][n]
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  constexpr int NT = (G_T / TM) * (G_T / TN), PER = G_T * G_T / NT;   // threads, tile elements copied per thread and operand
+  static_assert((TM == 2 || TM == 4) && (TN == 2 || TN == 4), "micro-tile");
+  __shared__ __align__(16) float As[G_ST][G_T][G_P], Bs[G_ST][G_T][G_P];   // [stage][k][m], [stage][k][n]
+  const int tid = threadIdx.x, tx = tid % (G_T / TN), ty = tid / (G_T / TN);
   const int m0 = blockIdx.x * G_T, n0 = blockIdx.y * G_T, s = blockIdx.z;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   float csum = 0.f;
   const bool want_csum = p.colsum && blockIdx.y == 0;
-  const int nkt = (p.K + G_T - 1) / G_T;
-#pragma unroll 1
-  for (int term = 0; term < 2; ++term) {
-    const float* A = term ? p.A2 : p.A1;
-    const float* B = term ? p.B2 : p.B1;
-    if (!A) break;
-    A += (size_t)s * (term ? p.sA2 : p.sA1);
-    B += (size_t)s * (term ? p.sB2 : p.sB1);
-    const int lda = term ? p.lda2 : p.lda1, ldb = term ? p.ldb2 : p.ldb1;
-    float ra[16], rb[16];
-    auto fetch = [&](int kt) {
-      const int k0 = kt * G_T;
+  const int nkt = (p.K + G_T - 1) / G_T, ntiles = (p.A2 ? 2 : 1) * nkt;   // the two terms form one sequence of k tiles
+  // 4-byte asynchronous copies place every element at its transposed position directly (zero-filled out of range)
+  auto issue = [&](int it) {
+    if (it < ntiles) {
+      const int term = it >= nkt, k0 = (it - term * nkt) * G_T, st = it % G_ST;
+      const float* A = (term ? p.A2 : p.A1) + (size_t)s * (term ? p.sA2 : p.sA1);
+      const float* B = (term ? p.B2 : p.B1) + (size_t)s * (term ? p.sB2 : p.sB1);
+      const int lda = term ? p.lda2 : p.lda1, ldb = term ? p.ldb2 : p.ldb1;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int e = tid + j * 64;
+      for (int j = 0; j < PER; ++j) {
+        const int e = tid + j * NT;
         {
           const int mm = AKC ? (e >> 5) : (e & 31), kk = AKC ? (e & 31) : (e >> 5);
           const bool ok = m0 + mm < p.M && k0 + kk < p.K;
-          ra[j] = ok ? (AKC ? A[(size_t)(m0 + mm) * lda + k0 + kk] : A[(size_t)(k0 + kk) * lda + m0 + mm]) : 0.f;
+          const size_t off = AKC ? (size_t)(m0 + mm) * lda + k0 + kk : (size_t)(k0 + kk) * lda + m0 + mm;
+          cp_async4(&As[st][kk][mm], ok ? A + off : A, ok);
         }
         {
           const int nn = BKC ? (e >> 5) : (e & 31), kk = BKC ? (e & 31) : (e >> 5);
           const bool ok = n0 + nn < p.N && k0 + kk < p.K;
-          rb[j] = ok ? (BKC ? B[(size_t)(n0 + nn) * ldb + k0 + kk] : B[(size_t)(k0 + kk) * ldb + n0 + nn]) : 0.f;
+          const size_t off = BKC ? (size_t)(n0 + nn) * ldb + k0 + kk : (size_t)(k0 + kk) * ldb + n0 + nn;
+          cp_async4(&Bs[st][kk][nn], ok ? B + off : B, ok);
         }
       }
-    };
-    fetch(0);
+    }
+    cp_async_commit();   // (possibly empty: keeps the group count uniform)
+  };
+#pragma unroll
+  for (int it = 0; it < G_ST - 1; ++it) issue(it);
 #pragma unroll 1
-    for (int kt = 0; kt < nkt; ++kt) {
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int e = tid + j * 64;
-        As[AKC ? (e & 31) : (e >> 5)][AKC ? (e >> 5) : (e & 31)] = ra[j];
-        Bs[BKC ? (e & 31) : (e >> 5)][BKC ? (e >> 5) : (e & 31)] = rb[j];
-      }
-      __syncthreads();
-      if (kt + 1 < nkt) fetch(kt + 1);
-      if (want_csum && term == 0 && tid < G_T) {
+  for (int it = 0; it < ntiles; ++it) {
+    cp_async_wait<G_ST - 2>();   // tile `it` has landed (this thread's copies) ...
+    __syncthreads();             // ... and everybody's; everybody is also done with the stage refilled next
+    issue(it + G_ST - 1);
+    const int st = it % G_ST;
+    if (want_csum && it < nkt && tid < G_T) {
 #pragma unroll 8
-        for (int k = 0; k < G_T; ++k) csum += As[k][tid];
+      for (int k = 0; k < G_T; ++k) csum += As[st][k][tid];
+    }
+#pragma unroll
+    for (int k = 0; k < G_T; ++k) {
+      float av[TM], bv[TN];
+      if (TM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[TM - 2] = a.z; av[TM - 1] = a.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(&As[st][k][ty * 2]);
+        av[0] = a.x; av[1] = a.y;
+      }
+      if (TN == 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[st][k][tx * 4]);
+        bv[0] = b.x; bv[1] = b.y; bv[TN - 2] = b.z; bv[TN - 1] = b.w;
+      } else {
+        const float2 b = *reinterpret_cast<const float2*>(&Bs[st][k][tx * 2]);
+        bv[0] = b.x; bv[1] = b.y;
       }
 #pragma unroll
-      for (int k = 0; k < G_T; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= p.M) break;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
       if (n >= p.N) break;
       const size_t dst = (size_t)s * p.sO + (size_t)m * p.ldo + n;
       float v = acc[i][j] + (p.bias ? p.bias[(size_t)s * p.sBias + n] : 0.f);
@@ -514,6 +533,7 @@ bgemm_kernel(const BGemm p) {
   }
   if (want_csum && tid < G_T && m0 + tid < p.M) p.colsum[(size_t)s * p.sCol + m0 + tid] = csum;
 }
+constexpr int G_TM = 2, G_TN = 2, G_NT = (G_T / G_TM) * (G_T / G_TN);   // micro-tile of the launches below
 
 // ------------------------------------------------------------------------------------------------ softmax / NLL head
 // mode 0: nll;  mode 1: nll, g_o = cw (p - onehot);  mode 2 (dual, needs od): G_o = cw p (od - <p, od>), G_od = cw (p - onehot),
@@ -680,7 +700,7 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     g.M = R; g.N = OUT; g.K = IN;
     g.bias = b; g.sBias = LN_P; g.relu = relu; g.maskfrom = mask;
     g.out = out; g.sO = (long long)sR * OUT; g.ldo = OUT;
-    bgemm_kernel<true, true><<<dim3(tiles(R), tiles(OUT), S), 64, 0, st>>>(g);
+    bgemm_kernel<true, true, G_TM, G_TN><<<dim3(tiles(R), tiles(OUT), S), G_NT, 0, st>>>(g);
   };
   // out[s][r][i] = sum_o y1[s][r][o] w1[s][o][i] (+ y2 . w2); * (mask > 0)
   auto lin_bwd_data = [&](const float* y1, const float* w1, const float* y2, const float* w2, int IN, int OUT, const float* mask,
@@ -692,7 +712,7 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     g.M = R; g.N = IN; g.K = OUT;
     g.maskfrom = mask;
     g.out = out; g.sO = (long long)sR * IN; g.ldo = IN;
-    bgemm_kernel<true, false><<<dim3(tiles(R), tiles(IN), S), 64, 0, st>>>(g);
+    bgemm_kernel<true, false, G_TM, G_TN><<<dim3(tiles(R), tiles(IN), S), G_NT, 0, st>>>(g);
   };
   // wbar[s][o][i] = sum_r y1[s][r][o] x1[s][r][i] (+ y2 . x2);  bbar[s][o] = sum_r y1[s][r][o]
   auto lin_bwd_weight = [&](const float* y1, const float* x1, const float* y2, const float* x2, int IN, int OUT, float* wb,
@@ -704,7 +724,7 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     g.M = OUT; g.N = IN; g.K = R;
     g.out = wb; g.sO = LN_P; g.ldo = IN;
     g.colsum = bb; g.sCol = LN_P;
-    bgemm_kernel<false, false><<<dim3(tiles(OUT), tiles(IN), S), 64, 0, st>>>(g);
+    bgemm_kernel<false, false, G_TM, G_TN><<<dim3(tiles(OUT), tiles(IN), S), G_NT, 0, st>>>(g);
   };
   // row chunks of the weight-gradient kernels: as many as fit in ONE wave of resident CTAs (at most N_CHUNKS)
   auto chunking = [&](int slots, int& rpc, int& nch) {
