@@ -154,7 +154,7 @@ def run_reference_arm(args):
                              "sample": f"{steps} full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single thread); "
                                        "the reference itself is Python and cannot travel to the GPU box"},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -174,6 +174,18 @@ def build_chain(c, seed, device):
     return obj, (x, y, xt, yt)
 
 
+_STDOUT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +194,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner, library
+    # chatter) is sent to stderr for the whole run; the line goes to the saved descriptor at the end
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -194,8 +212,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _native.require_cuda()
     c = CFG
@@ -531,7 +547,7 @@ def main():
                                               "thread) on this box's host CPU"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
