@@ -8,7 +8,7 @@
 // Every matrix product of the pass is ONE launch of a batched "TN" GEMM kernel, C[b] = A[b] B[b]^T with
 // K-major operands and fp32 accumulation: TMA (128-byte swizzle) -> shared-memory ring -> tcgen05.mma (M = N = 128) ->
 // double-buffered TMEM accumulator -> 8 epilogue warps (tcgen05.ld, bias / ReLU / ReLU-mask, plain fp32 stores, operand
-// stores and transposed operand stores).  Two arithmetic modes:
+// stores and transposed operand stores).  Three arithmetic modes:
 //   precision 0 (bf16)    operands rounded to bf16, one kind::f16 MMA per K step: full tensor rate, ~1e-2 relative error per
 //                         pass -- fine for values, first-order training (mfvi) and prediction;
 //   precision 1 (tf32x3)  every operand is kept as an fp32 pair (hi, lo) of TF32-representable numbers (hi = rna_tf32(x),
@@ -16,6 +16,9 @@
 //                         fp32-class accuracy (~2^-21) at 1/6 of the bf16 rate.  The unrolled hypergradient needs it:
 //                         the reverse sweep through Adam divides by |g_i|, so per-coordinate gradient errors of bf16 size
 //                         destroy it (measured in DESIGN.md 4.8).
+//   precision 2 (bf16x3)  the same split with BF16 numbers (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, ~2^-17) and
+//                         three kind::f16 MMAs per K step: twice the MMA rate of tf32x3 and half its operand bytes;
+//                         hypergradients within 1e-2 .. 1e-1 (cosine >= 0.999) of the fp64 oracle -- opt-in.
 // Sums of two products are one GEMM over a concatenated K dimension ([hdot | h] [W2 | W2dot]^T etc.); products with
 // K = C <= 16 use zero-padded K blocks (one 128-byte swizzle row).  Activations that feed a later GEMM as the K dimension
 // are stored transposed by the producing epilogue.  Reductions over rows with a C- or 1-wide output (second-layer and
@@ -34,6 +37,7 @@ constexpr int CW = 16;                          // classes padded to 16 on the f
 template <int X3> struct Prec;
 template <> struct Prec<0> { static constexpr int ES = 2, GK = 64, TILES = 2, GST = 6; };   // bf16
 template <> struct Prec<1> { static constexpr int ES = 4, GK = 32, TILES = 4, GST = 3; };   // tf32 (hi, lo) pairs
+template <> struct Prec<2> { static constexpr int ES = 2, GK = 64, TILES = 4, GST = 3; };   // bf16 (hi, lo) pairs ("bf16x3")
 
 struct GemmP {
   int batch, m_tiles, n_tiles, kc;              // kc = K / GK
@@ -74,6 +78,12 @@ __host__ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
   lo = tf32_rna(x - hi);
+}
+
+// x = hi + lo with hi, lo BF16 numbers, |x - hi - lo| <= 2^-17 |x|   (precision 2)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
 }
 
 template <int X3>
@@ -119,7 +129,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* dst = ring + st * STAGE;
           mbar_expect_tx(&full[st], STAGE);
           tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
-          if (X3) {
+          if (PR::TILES == 4) {
             tma_load_2d(&map_al, &full[st], dst + G_TILE_BYTES, k * PR::GK, arow);
             tma_load_2d(&map_b, &full[st], dst + 2 * G_TILE_BYTES, k * PR::GK, brow);
             tma_load_2d(&map_bl, &full[st], dst + 3 * G_TILE_BYTES, k * PR::GK, brow);
@@ -133,7 +143,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // instruction descriptor: D = f32, A = B = bf16 (format 1) or tf32 (format 2), both K-major, N = 128, M = 128
-    const uint32_t fmt = X3 ? 2u : 1u;
+    const uint32_t fmt = X3 == 1 ? 2u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
     int st = 0, it = 0;
     uint32_t ph = 0;
@@ -148,13 +158,21 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t s0 = smem_u32(ring + st * STAGE);
         const uint32_t acc0 = k != 0;
         if (elect_one()) {
-          if (X3) {
+          if (X3 == 1) {
             const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {   // K = 8 fp32 = 32 bytes per step; small terms first
               umma_tf32(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
               umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
               umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
+            }
+          } else if (X3 == 2) {
+            const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // K = 16 bf16 = 32 bytes per step; lo.hi + hi.lo + hi.hi at the bf16 rate
+              umma_bf16(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
+              umma_bf16(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
+              umma_bf16(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
             }
           } else {
             const uint32_t a0 = s0, b0 = s0 + G_TILE_BYTES;
@@ -204,12 +222,12 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (n0 + j >= p.N_valid) continue;
-              const float mk = X3 ? __ldg(static_cast<const float*>(p.mask) + mo + (long long)j * p.mask_ld)
+              const float mk = X3 == 1 ? __ldg(static_cast<const float*>(p.mask) + mo + (long long)j * p.mask_ld)
                                   : __bfloat162float(static_cast<const __nv_bfloat16*>(p.mask)[mo + (long long)j * p.mask_ld]);
               if (!(mk > 0.f)) v[j] = 0.f;
             }
           } else if (p.mask && vm) {   // N_valid is a multiple of 32 whenever a mask / operand output is used
-            if (X3) {
+            if (X3 == 1) {
               const float4* mp = reinterpret_cast<const float4*>(static_cast<const float*>(p.mask) + (long long)b * p.mask_bs +
                                                                  (long long)m * p.mask_ld + n0);
 #pragma unroll
@@ -253,7 +271,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (p.ob && m < p.ob_rows) {
             const long long off = (long long)b * p.ob_bs + (long long)m * p.ob_ld + n0;
-            if (X3) {
+            if (X3 == 1) {
               float4* oh = reinterpret_cast<float4*>(static_cast<float*>(p.ob) + off);
               float4* ol = reinterpret_cast<float4*>(static_cast<float*>(p.ob_lo) + off);
 #pragma unroll
@@ -263,6 +281,23 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int e = 0; e < 4; ++e) split_tf32(v[4 * i + e], h4[e], l4[e]);
                 oh[i] = make_float4(h4[0], h4[1], h4[2], h4[3]);
                 ol[i] = make_float4(l4[0], l4[1], l4[2], l4[3]);
+              }
+            } else if (X3 == 2) {
+              uint4* oh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob) + off);
+              uint4* ol = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob_lo) + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2, l2;
+                  split_bf16(v[i * 8 + e * 2], h2.x, l2.x);
+                  split_bf16(v[i * 8 + e * 2 + 1], h2.y, l2.y);
+                  wh[e] = *reinterpret_cast<uint32_t*>(&h2);
+                  wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+                }
+                oh[i] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                ol[i] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
               }
             } else {
               uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob) + off);
@@ -280,13 +315,23 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (p.obt && m < p.ob_rows) {
             const long long off = (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + m;
-            if (X3) {
+            if (X3 == 1) {
               float* oh = static_cast<float*>(p.obt) + off;
               float* ol = static_cast<float*>(p.obt_lo) + off;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float hi, lo;
                 split_tf32(v[j], hi, lo);
+                oh[(long long)j * p.obt_ld] = hi;
+                ol[(long long)j * p.obt_ld] = lo;
+              }
+            } else if (X3 == 2) {
+              __nv_bfloat16* oh = static_cast<__nv_bfloat16*>(p.obt) + off;
+              __nv_bfloat16* ol = static_cast<__nv_bfloat16*>(p.obt_lo) + off;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(v[j], hi, lo);
                 oh[(long long)j * p.obt_ld] = hi;
                 ol[(long long)j * p.obt_ld] = lo;
               }
@@ -312,21 +357,28 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ operand stores
-// one operand element: bf16 (X3 = 0) or the (hi, lo) fp32 pair (X3 = 1)
+// one operand element: bf16 (X3 = 0), the (hi, lo) fp32 pair of TF32 numbers (X3 = 1) or the (hi, lo) pair of BF16 numbers (X3 = 2)
 template <int X3>
 __device__ __forceinline__ void put(void* hi_base, void* lo_base, size_t i, float v) {
-  if (X3) {
+  if (X3 == 1) {
     float h, l;
     split_tf32(v, h, l);
     static_cast<float*>(hi_base)[i] = h;
     static_cast<float*>(lo_base)[i] = l;
+  } else if (X3 == 2) {
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    static_cast<__nv_bfloat16*>(hi_base)[i] = h;
+    static_cast<__nv_bfloat16*>(lo_base)[i] = l;
   } else {
     static_cast<__nv_bfloat16*>(hi_base)[i] = __float2bfloat16(v);
   }
 }
 template <int X3>
 __device__ __forceinline__ float get(const void* hi_base, const void* lo_base, size_t i) {
-  if (X3) return static_cast<const float*>(hi_base)[i] + static_cast<const float*>(lo_base)[i];
+  if (X3 == 1) return static_cast<const float*>(hi_base)[i] + static_cast<const float*>(lo_base)[i];
+  if (X3 == 2)
+    return __bfloat162float(static_cast<const __nv_bfloat16*>(hi_base)[i]) + __bfloat162float(static_cast<const __nv_bfloat16*>(lo_base)[i]);
   return __bfloat162float(static_cast<const __nv_bfloat16*>(hi_base)[i]);
 }
 
@@ -582,7 +634,7 @@ struct Lws {
 };
 
 void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
-  const size_t Rp = (size_t)((R + 127) / 128) * 128, es = x3 ? 4 : 2, cp2 = x3 ? 64 : 128;
+  const size_t Rp = (size_t)((R + 127) / 128) * 128, es = x3 == 1 ? 4 : 2, cp2 = x3 == 1 ? 64 : 128;
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
   auto takeb = [&](size_t elems) { Buf b; b.hi = take(elems * es); b.lo = x3 ? take(elems * es) : nullptr; return b; };
@@ -642,7 +694,12 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   using PR = Prec<X3>;
   CUtensorMap ma, mal, mb, mbl;
   int rc;
-  if (X3) {
+  if (X3 == 2) {
+    if ((rc = make_map_2d_bf16_ld(&ma, A.buf.hi + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mal, A.buf.lo + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mb, B.buf.hi + B.eoff * 2, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mbl, B.buf.lo + B.eoff * 2, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+  } else if (X3 == 1) {
     if ((rc = make_map_f32(&ma, A.buf.hi + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
     if ((rc = make_map_f32(&mal, A.buf.lo + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
     if ((rc = make_map_f32(&mb, B.buf.hi + B.eoff * 4, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
@@ -839,7 +896,7 @@ extern "C" {
 size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R, int32_t precision) {
   if (!model || model->n_layers != 2 || R <= 0) return 0;
   Lws w;
-  carve_l(model->mc_samples, R, model->dims[0], model->dims[1], precision ? 1 : 0, nullptr, w);
+  carve_l(model->mc_samples, R, model->dims[0], model->dims[1], precision, nullptr, w);
   return w.total + 1024;
 }
 
@@ -850,10 +907,12 @@ int psvi_fnl_pass(const psvi_mf_model* model, int32_t precision, const float* th
   int rc = check_large(model);
   if (rc) return rc;
   PSVI_REQUIRE(R >= 1, PSVI_ERR_INVALID, "bad R");
-  PSVI_REQUIRE(precision == 0 || precision == 1, PSVI_ERR_INVALID, "precision must be 0 (bf16) or 1 (tf32x3)");
+  PSVI_REQUIRE(precision >= 0 && precision <= 2, PSVI_ERR_INVALID, "precision must be 0 (bf16), 1 (tf32x3) or 2 (bf16x3)");
   PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (precision)
+  if (precision == 2)
+    return fnl_pass_impl<2>(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, workspace, st);
+  if (precision == 1)
     return fnl_pass_impl<1>(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, workspace, st);
   return fnl_pass_impl<0>(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, workspace, st);
 }

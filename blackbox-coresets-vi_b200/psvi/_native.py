@@ -447,11 +447,11 @@ def logits_predict(logits, log_weights, mode, yt, out, probs_out=None):
 _fnl_ws = {}
 
 
-PREC_BF16, PREC_TF32X3 = 0, 1
+PREC_BF16, PREC_TF32X3, PREC_BF16X3 = 0, 1, 2
 
 
 def fnl_pass(model, precision, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, logits=None):
-    """Large-regime fn pass (batched tcgen05 GEMMs; bf16 or tf32x3 arithmetic) on sampled weights theta [S][P]."""
+    """Large-regime fn pass (batched tcgen05 GEMMs; bf16, tf32x3 or bf16x3 arithmetic) on sampled weights theta [S][P]."""
     R = x.shape[0]
     n = (int(lib().psvi_fnl_workspace_bytes(C.byref(model), R, precision)) + 3) // 4
     ws = _fnl_ws.get(theta.device)

@@ -208,8 +208,10 @@ class MlpNet:
 
 class FnLargeNet:
     """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu).
-    `precision`: _native.PREC_TF32X3 (default; fp32-class accuracy, needed by the unrolled hypergradient) or PREC_BF16 (6x
-    the tensor rate, ~1e-2 relative error per pass: values, first-order training, prediction)."""
+    `precision`: _native.PREC_TF32X3 (default; fp32-class accuracy, needed by the unrolled hypergradient), PREC_BF16X3
+    (split-bf16 operand pairs: twice the MMA rate and half the operand bytes of tf32x3, ~2^-17 per operand; hypergradients
+    within 1e-2..1e-1, cosine >= 0.999, of the fp64 oracle -- opt-in) or PREC_BF16 (6x the tensor rate, ~1e-2 relative error
+    per pass: values, first-order training, prediction)."""
 
     def __init__(self, dims, S, precision=_native.PREC_TF32X3):
         self.desc, self.S, self.C, self.precision = _native.make_model(dims, S), S, dims[-1], precision

@@ -266,7 +266,9 @@ int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const fl
  * batched TMA + tcgen05 GEMM with fp32 accumulation (csrc/psvi_fn_large.cu).  precision 0: bf16 operands / activations
  * (full tensor rate, ~1e-2 relative error: values, first-order training, prediction); precision 1: "tf32x3" -- every operand
  * is an fp32 (hi, lo) pair of TF32 numbers and every K step issues three kind::tf32 MMAs (fp32-class accuracy, which the
- * unrolled hypergradient of nested_step needs: its reverse sweep through Adam divides by |g_i|).
+ * unrolled hypergradient of nested_step needs: its reverse sweep through Adam divides by |g_i|); precision 2: "bf16x3" -- the
+ * same split with BF16 numbers and three kind::f16 MMAs (16 mantissa bits per operand, twice the MMA rate and half the operand
+ * bytes of tf32x3; hypergradient cosine >= 0.999 against the fp64 oracle: opt-in).
  *   needs n_layers == 2, D a multiple of 64, H a multiple of 128, C <= 16, S <= 64;  x [R][D] fp32, y [R] int32,
  *   cw [S][R] (nullable -> 1);  outputs as psvi_net_pass (logits [S][R][C]);  workspace: psvi_fnl_workspace_bytes(). */
 size_t psvi_fnl_workspace_bytes(const psvi_mf_model* model, int32_t R, int32_t precision);

@@ -15,6 +15,8 @@ kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=16000, inner_it=T
           n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="synthetic", nc=C,
           compute_weights_entropy=False, register_elbos=False, quiet=True)
 obj = PSVILearnV(**kw)
+obj.large_precision = sys.argv[3] if len(sys.argv) > 3 else 'tf32x3'
+print('precision', obj.large_precision)
 obj.run_psvi(**kw)
 xb, yb = obj._next_minibatch()
 obj.nested_step(xb, yb)

@@ -37,18 +37,38 @@ def make_case(D, H, C, S, R, seed):
     return dims, theta, thetad, X, y, cw
 
 
+def unambiguous_relu(theta, X, dims, margin=1e-3):
+    """Nudges first-layer biases so that no pre-activation lies within `margin` of zero: a unit whose pre-activation is ~1e-6
+    from zero takes either side of the ReLU depending on the arithmetic (fp64 oracle vs split-precision GEMM), and ONE flipped
+    (row, unit) pair moves the rel-L2 of the first-layer gradient by ~sqrt(1 / (H R)) ~ 3e-3 -- a property of ReLU, not of the
+    kernel under test."""
+    D, H, _ = dims
+    for _ in range(8):
+        a1 = np.einsum("rd,shd->srh", X.astype(np.float64), theta[:, :H * D].astype(np.float64).reshape(-1, H, D)) \
+            + theta[:, None, H * D:H * D + H].astype(np.float64)
+        bad = (np.abs(a1) < margin).any(axis=1)
+        if not bad.any():
+            break
+        theta[:, H * D:H * D + H][bad] += np.float32(3.1 * margin)
+    return theta
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16x3"])
 @pytest.mark.parametrize("D,H,C,S,R", [(64, 128, 3, 2, 100), (128, 256, 10, 3, 300), (256, 384, 4, 2, 129), (192, 128, 16, 2, 260)])
-def test_fnl_pass_tf32x3_matches_oracle(D, H, C, S, R):
+def test_fnl_pass_tf32x3_matches_oracle(D, H, C, S, R, prec):
     """precision 1 (three kind::tf32 MMAs on (hi, lo) operand pairs): fp32-class accuracy -- rel-L2 2e-5 on every output
-    against the fp64 oracle with un-rounded operands."""
+    against the fp64 oracle with un-rounded operands.  precision 2 (the same split with bf16 pairs, three kind::f16 MMAs):
+    16 mantissa bits per operand -- the same checks at 10x the tolerance (2e-4 / 5e-4)."""
     from psvi import _native as nat
     nat.require_cuda()
+    PREC, k = (nat.PREC_TF32X3, 1.0) if prec == "tf32x3" else (nat.PREC_BF16X3, 10.0)
     rng = np.random.default_rng(D + H + C + S + R)
     dims = [D, H, C]
     theta = np.concatenate([rng.standard_normal((S, H * D)) / np.sqrt(D), 0.1 * rng.standard_normal((S, H)),
                             rng.standard_normal((S, C * H)) / np.sqrt(H), 0.1 * rng.standard_normal((S, C))], 1).astype(np.float32)
     thetad = (rng.standard_normal(theta.shape) * np.abs(theta).mean() * 0.5).astype(np.float32)
     X = rng.standard_normal((R, D)).astype(np.float32)
+    theta = unambiguous_relu(theta, X, dims)
     y = rng.integers(0, C, R)
     cw = rng.uniform(0.5, 1.5, (S, R)).astype(np.float32)
     model = nat.make_model(dims, S)
@@ -56,31 +76,31 @@ def test_fnl_pass_tf32x3_matches_oracle(D, H, C, S, R):
     th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
     t64, td64, X64, cw64 = theta.astype(np.float64), thetad.astype(np.float64), X.astype(np.float64), cw.astype(np.float64)
     nll, logits = zeros(S, R), zeros(S, R, C)
-    nat.fnl_pass(model, nat.PREC_TF32X3, th, None, x_, y_, None, nll=nll, logits=logits)
+    nat.fnl_pass(model, PREC, th, None, x_, y_, None, nll=nll, logits=logits)
     o, cache = po.mlp_forward(t64, X64, dims)
     ref_nll, p = po.nll_rows(o, y)
-    assert rel_l2(logits.cpu().numpy(), o) < 2e-5
-    np.testing.assert_allclose(nll.cpu().numpy(), ref_nll, rtol=1e-4, atol=2e-5)
+    assert rel_l2(logits.cpu().numpy(), o) < 2e-5 * k
+    np.testing.assert_allclose(nll.cpu().numpy(), ref_nll, rtol=1e-4 * k, atol=2e-5 * k)
     q = p.copy()
     q[:, np.arange(R), y] -= 1.0
     At, Ax = po.mlp_backward(t64, cache, dims, cw64[:, :, None] * q)
     tbar, xbar = zeros(S, P), zeros(S, R, D)
-    nat.fnl_pass(model, nat.PREC_TF32X3, th, None, x_, y_, cw_, nll=nll, tbar=tbar, xbar=xbar)
+    nat.fnl_pass(model, PREC, th, None, x_, y_, cw_, nll=nll, tbar=tbar, xbar=xbar)
     blocks = ((0, H * D), (H * D, H * D + H), (H * D + H, H * D + H + C * H), (H * D + H + C * H, P))
     for lo, hi in blocks:
-        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 2e-5
-    assert rel_l2(xbar.cpu().numpy(), Ax) < 2e-5
+        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 2e-5 * k
+    assert rel_l2(xbar.cpu().numpy(), Ax) < 2e-5 * k
     o, od, c2 = po.mlp_dual_forward(t64, td64, X64, dims)
     c = cw64[:, :, None]
     At, Atd, Ax = po.mlp_dual_backward(t64, td64, c2, dims, c * p * (od - (p * od).sum(-1, keepdims=True)), c * q)
     tbar, tdbar, xbar, ac = zeros(S, P), zeros(S, P), zeros(S, R, D), zeros(S, R)
-    nat.fnl_pass(model, nat.PREC_TF32X3, th, thd, x_, y_, cw_, tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
+    nat.fnl_pass(model, PREC, th, thd, x_, y_, cw_, tbar=tbar, tdbar=tdbar, xbar=xbar, acbar=ac)
     torch.cuda.synchronize()
     for lo, hi in blocks:
-        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 5e-5
-        assert rel_l2(tdbar.cpu().numpy()[:, lo:hi], Atd[:, lo:hi]) < 2e-5
-    assert rel_l2(xbar.cpu().numpy(), Ax) < 5e-5
-    assert rel_l2(ac.cpu().numpy(), (q * od).sum(-1)) < 2e-5
+        assert rel_l2(tbar.cpu().numpy()[:, lo:hi], At[:, lo:hi]) < 5e-5 * k
+        assert rel_l2(tdbar.cpu().numpy()[:, lo:hi], Atd[:, lo:hi]) < 2e-5 * k
+    assert rel_l2(xbar.cpu().numpy(), Ax) < 5e-5 * k
+    assert rel_l2(ac.cpu().numpy(), (q * od).sum(-1)) < 2e-5 * k
 
 
 @pytest.mark.parametrize("D,H,C,S,R", [(64, 128, 3, 2, 100), (128, 256, 10, 3, 300), (256, 384, 4, 2, 129), (192, 128, 16, 2, 260)])
@@ -132,10 +152,12 @@ def test_fnl_pass_bf16_matches_oracle(D, H, C, S, R):
         assert rel_l2(tdbar.cpu().numpy()[:, lo:hi], Atd[:, lo:hi]) < 2e-2
 
 
-def test_large_fn_nested_step_and_evaluate_through_psvi_class():
+@pytest.mark.parametrize("prec,tol,min_cos", [("tf32x3", 5e-3, 0.9999), ("bf16x3", 5e-2, 0.999)])
+def test_large_fn_nested_step_and_evaluate_through_psvi_class(prec, tol, min_cos):
     """PSVILearnV on a model in the large regime (P = 50 691 per sample): the class picks the batched-GEMM tensor path
     (FnLargeNet) for inner_elbo / psvi_elbo / nested_step and the fused tcgen05 forward for evaluate; checked against the
-    fp64 oracle.  The bilevel step runs in tf32x3 arithmetic (fp32-class accuracy): hypergradients rel-L2 5e-3."""
+    fp64 oracle.  The bilevel step runs in tf32x3 arithmetic by default (fp32-class accuracy): hypergradients rel-L2 5e-3,
+    cosine > 0.9999; with the opt-in split-bf16 arithmetic (`large_precision = "bf16x3"`) rel-L2 5e-2, cosine > 0.999."""
     from oracle.ref_import import NoiseFeeder
     from psvi.experiments.experiments_utils import SynthDataset, make_synthetic_rows
     from psvi.inference.psvi_classes import ExternalNoise, PSVILearnV
@@ -148,6 +170,7 @@ def test_large_fn_nested_step_and_evaluate_through_psvi_class():
               n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="synthetic", nc=C,
               compute_weights_entropy=True, register_elbos=False, quiet=True)
     obj = PSVILearnV(**kw)
+    obj.large_precision = prec
     obj.run_psvi(**kw)
     dims = obj.model.dims
     assert dims == [D, H, C] and obj._is_large_fn(obj.model)
@@ -165,8 +188,8 @@ def test_large_fn_nested_step_and_evaluate_through_psvi_class():
                        dims, 1e-3, vmode=1)
     assert abs(loss.item() - r["loss"]) <= 1e-4 * abs(r["loss"])
     gu, gv = obj.u.grad.cpu().numpy(), obj.v.grad.cpu().numpy()
-    assert rel_l2(gu, r["u_grad"]) < 5e-3 and cos(gu, r["u_grad"]) > 0.9999
-    assert rel_l2(gv, r["v_grad"]) < 5e-3 and cos(gv, r["v_grad"]) > 0.9999
+    assert rel_l2(gu, r["u_grad"]) < tol and cos(gu, r["u_grad"]) > min_cos
+    assert rel_l2(gv, r["v_grad"]) < tol and cos(gv, r["v_grad"]) > min_cos
     muT, rhoT = [t.cpu().numpy() for t in obj.model.flat()]
     assert rel_l2(muT, r["mu_T"]) < 1e-5 and rel_l2(rhoT, r["rho_T"]) < 1e-5
     # evaluate: fused tcgen05 forward (in-kernel Philox noise) -- sanity of the metrics on a learnable synthetic problem

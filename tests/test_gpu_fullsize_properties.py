@@ -10,7 +10,8 @@ for the loss L_s(theta) = sum_r cw[s, r] nll[s, r]:
   P5  the Hessian is symmetric: <w, H v> == <v, H w>
 
 and the full-data tensor-core passes must be invariant under splitting / permuting rows.  Tolerances are fp32 accumulation
-order (1e-4 class) and, for the large regime, the tf32x3 arithmetic (1e-3 class); they are written next to each assert."""
+order (1e-4 class) and, for the large regime, the tf32x3 arithmetic (1e-3 class; x10 more for the opt-in split-bf16
+arithmetic); they are written next to each assert."""
 import numpy as np
 import pytest
 import torch
@@ -40,6 +41,7 @@ def _rand_theta_lenet(S, g):
 
 
 def _nets():
+    from psvi import _native
     from psvi.inference.stream import FnLargeNet, LenetNet, MlpNet
     return {
         # name: (net factory, theta factory, D_in, classes, S, rows, tolerance scale)
@@ -48,6 +50,8 @@ def _nets():
         "cfg4_lenet": (lambda: LenetNet(10), lambda g: _rand_theta_lenet(10, g), 784, 10, 10, 328, 1.0),
         "cfg5_fn_large": (lambda: FnLargeNet([256, 1024, 10], 64), lambda g: _rand_theta_mlp([256, 1024, 10], 64, g), 256, 10, 64,
                           1000, 10.0),
+        "cfg5_fn_large_bf16x3": (lambda: FnLargeNet([256, 1024, 10], 64, precision=_native.PREC_BF16X3),
+                                 lambda g: _rand_theta_mlp([256, 1024, 10], 64, g), 256, 10, 64, 1000, 100.0),
     }
 
 
@@ -66,7 +70,7 @@ def _passes(net, theta, thetad, x, y, cw, want_x=False):
     return out
 
 
-@pytest.mark.parametrize("name", ["cfg2_fn", "cfg3_fn2_net", "cfg4_lenet", "cfg5_fn_large"])
+@pytest.mark.parametrize("name", ["cfg2_fn", "cfg3_fn2_net", "cfg4_lenet", "cfg5_fn_large", "cfg5_fn_large_bf16x3"])
 def test_network_pass_properties_at_full_size(name):
     from psvi import _native
     _native.require_cuda()
