@@ -382,6 +382,42 @@ __device__ __forceinline__ float get(const void* hi_base, const void* lo_base, s
   return __bfloat162float(static_cast<const __nv_bfloat16*>(hi_base)[i]);
 }
 
+// 16 consecutive operand elements (the head of one K block; the rest of the block stays zero) at element offset i, a
+// multiple of 16: 128-bit stores
+template <int X3>
+__device__ __forceinline__ void put16(void* hi_base, void* lo_base, size_t i, const float (&v)[16]) {
+  if (X3 == 1) {
+    float4* oh = reinterpret_cast<float4*>(static_cast<float*>(hi_base) + i);
+    float4* ol = reinterpret_cast<float4*>(static_cast<float*>(lo_base) + i);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(v[4 * q + e], h[e], l[e]);
+      oh[q] = make_float4(h[0], h[1], h[2], h[3]);
+      ol[q] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  } else {
+    uint32_t wh[8], wl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __nv_bfloat162 h2, l2;
+      split_bf16(v[2 * e], h2.x, l2.x);
+      split_bf16(v[2 * e + 1], h2.y, l2.y);
+      wh[e] = *reinterpret_cast<uint32_t*>(&h2);
+      wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(hi_base) + i);
+    oh[0] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    oh[1] = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+    if (X3 == 2) {
+      uint4* ol = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(lo_base) + i);
+      ol[0] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      ol[1] = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+    }
+  }
+}
+
 // x fp32 [R][D] -> X [Rp][D] (padding rows zero) and XT [D][Rp]
 template <int X3>
 __global__ void fnl_prep_x_kernel(const float* __restrict__ x, int R, int Rp, int D, void* Xh, void* Xl, void* XTh, void* XTl) {
@@ -448,9 +484,7 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * Rp) return;
   const int s = idx / Rp, r = idx - s * Rp;
-  const size_t ab = (size_t)idx * 2 * CPK;
-  if (mode >= 1)
-    for (int c = 0; c < 2 * CPK; ++c) put<X3>(AAh, AAl, ab + c, 0.f);
+  const size_t ab = (size_t)idx * 2 * CPK;   // (AA is zeroed by the caller: only the 16-entry heads of the K blocks are written)
   if (r >= R) return;
   const float* lo = o + (size_t)idx * CW;
   float lg[CW], p[CW], mx = -INFINITY, se = 0.f;
@@ -475,8 +509,10 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
 #pragma unroll
   for (int c = 0; c < CW; ++c) { p[c] *= inv; q[c] = c < C ? p[c] - (c == lab ? 1.f : 0.f) : 0.f; }
   if (mode == 1) {
+    float g[CW];
 #pragma unroll
-    for (int c = 0; c < CW; ++c) { go[oidx * CW + c] = w * q[c]; put<X3>(AAh, AAl, ab + c, w * q[c]); }
+    for (int c = 0; c < CW; ++c) { g[c] = w * q[c]; go[oidx * CW + c] = g[c]; }
+    put16<X3>(AAh, AAl, ab, g);
     return;
   }
   const float* ld = od + (size_t)idx * CW;
@@ -487,14 +523,16 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
     dot += p[c] * dd[c];
     qd += q[c] * dd[c];
   }
+  float g1[CW], g2[CW];
 #pragma unroll
   for (int c = 0; c < CW; ++c) {
-    const float g1 = c < C ? w * p[c] * (dd[c] - dot) : 0.f, g2 = w * q[c];
-    go[oidx * CW + c] = g1;
-    god[oidx * CW + c] = g2;
-    put<X3>(AAh, AAl, ab + CPK + c, g1);
-    put<X3>(AAh, AAl, ab + c, g2);
+    g1[c] = c < C ? w * p[c] * (dd[c] - dot) : 0.f;
+    g2[c] = w * q[c];
+    go[oidx * CW + c] = g1[c];
+    god[oidx * CW + c] = g2[c];
   }
+  put16<X3>(AAh, AAl, ab + CPK, g1);
+  put16<X3>(AAh, AAl, ab, g2);
   if (acbar) acbar[oidx] = qd;
 }
 
@@ -819,6 +857,8 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     PSVI_CUDA_CHECK(cudaGetLastError());
     return PSVI_OK;
   }
+  for (int part = 0; part < (X3 ? 2 : 1); ++part)   // K blocks of the output adjoints: zero except the 16-entry heads
+    PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.AA.lo : w.AA.hi, 0, (size_t)S * Rp * 2 * CP * ES, st));
   auto colreduce = [&](const Buf& Y, long long y_off, const float* W, int Cc, float* out, int accumulate) {
     fnl_colreduce_kernel<X3><<<dim3(H / 128, S, RSPLIT), 128, 0, st>>>(Y.hi, Y.lo, y_off, hh_bs, 2 * H, W, R, H, Cc, w.cpart);
     fnl_colreduce_finish_kernel<<<dim3((Cc * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, Cc, out, P, accumulate);

@@ -23,6 +23,8 @@ else:
               n_hidden=1024, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="synthetic", nc=10,
               compute_weights_entropy=False, register_elbos=False, quiet=True)
 obj = PSVILearnV(**kw)
+if len(sys.argv) > 2:
+    obj.large_precision = sys.argv[2]
 obj.run_psvi(**kw)
 xb, yb = obj._next_minibatch()
 for _ in range(2):
