@@ -536,36 +536,86 @@ __global__ void fnl_head_kernel(const float* __restrict__ o, const float* __rest
   if (acbar) acbar[oidx] = qd;
 }
 
-// part[z][s][c][h] = sum over the z-th row chunk of W[s][r][c] * Y[s][r][h]   (W == NULL: C = 1, weight 1 -> column sums);
-// fnl_colreduce_finish_kernel adds the chunks in fixed order: out[s * P + c * H + h] (+)= sum_z part[z][s][c][h]
-constexpr int RSPLIT = 8;
+// four consecutive operand elements at element offset i (a multiple of 4) as floats (hi + lo)
 template <int X3>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void get4(const void* hi_base, const void* lo_base, size_t i, float (&v)[4]) {
+  if (X3 == 1) {
+    const float4 h = *reinterpret_cast<const float4*>(static_cast<const float*>(hi_base) + i);
+    const float4 l = *reinterpret_cast<const float4*>(static_cast<const float*>(lo_base) + i);
+    v[0] = h.x + l.x; v[1] = h.y + l.y; v[2] = h.z + l.z; v[3] = h.w + l.w;
+  } else {
+    const uint2 h = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(hi_base) + i);
+    v[0] = __uint_as_float(h.x << 16); v[1] = __uint_as_float(h.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(h.y << 16); v[3] = __uint_as_float(h.y & 0xFFFF0000u);
+    if (X3 == 2) {
+      const uint2 l = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(lo_base) + i);
+      v[0] += __uint_as_float(l.x << 16); v[1] += __uint_as_float(l.x & 0xFFFF0000u);
+      v[2] += __uint_as_float(l.y << 16); v[3] += __uint_as_float(l.y & 0xFFFF0000u);
+    }
+  }
+}
+
+// part[z][s][c][h] = sum over the z-th row chunk of W[s][r][c] * Y[s][r][h]   (W == NULL: C = 1, weight 1 -> column sums);
+// fnl_colreduce_finish_kernel adds the chunks in fixed order: out[s * P + c * H + h] (+)= sum_z part[z][s][c][h].
+// A thread owns FOUR consecutive columns (one 8- / 16-byte load per row and operand part, the row's 16 weights -- four
+// broadcast 128-bit loads -- feed 64 FMAs): enough bytes in flight per SM to stream Y at HBM speed.
+constexpr int RSPLIT = 8, CR_T = 64;   // row chunks; threads per CTA (CR_T * 4 columns)
+template <int X3>
+__global__ void __launch_bounds__(CR_T)
 fnl_colreduce_kernel(const void* Yh, const void* Yl, long long y_off, long long y_bs, int y_ld, const float* __restrict__ W, int R,
                      int H, int C, float* __restrict__ part) {
-  const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, zc = blockIdx.z;
-  if (h >= H) return;
+  const int h_raw = (blockIdx.x * CR_T + threadIdx.x) * 4, s = blockIdx.y, zc = blockIdx.z;
+  const bool live = h_raw < H;
+  const int h = live ? h_raw : 0;   // (idle threads of a partial column block shadow column 0 and do not write)
   const int rpc = (R + RSPLIT - 1) / RSPLIT, r0 = zc * rpc, r1 = min(R, r0 + rpc);
-  float acc[CW];
+  float acc[4][CW];
 #pragma unroll
-  for (int c = 0; c < CW; ++c) acc[c] = 0.f;
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[k][c] = 0.f;
   const size_t y0 = (size_t)(y_off + (long long)s * y_bs + h);
   if (W) {
+    // the row weights of a sub-chunk are staged in shared memory once (coalesced) and read back as broadcast 128-bit loads
+    constexpr int SUB = 64;
+    __shared__ float4 s_w[SUB * (CW / 4)];
     const float4* wp = reinterpret_cast<const float4*>(W + (size_t)s * R * CW);
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-      const float yv = get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
-      const float4 w0 = __ldg(wp + r * 4), w1 = __ldg(wp + r * 4 + 1), w2 = __ldg(wp + r * 4 + 2), w3 = __ldg(wp + r * 4 + 3);
-      acc[0] = fmaf(w0.x, yv, acc[0]); acc[1] = fmaf(w0.y, yv, acc[1]); acc[2] = fmaf(w0.z, yv, acc[2]); acc[3] = fmaf(w0.w, yv, acc[3]);
-      acc[4] = fmaf(w1.x, yv, acc[4]); acc[5] = fmaf(w1.y, yv, acc[5]); acc[6] = fmaf(w1.z, yv, acc[6]); acc[7] = fmaf(w1.w, yv, acc[7]);
-      acc[8] = fmaf(w2.x, yv, acc[8]); acc[9] = fmaf(w2.y, yv, acc[9]); acc[10] = fmaf(w2.z, yv, acc[10]); acc[11] = fmaf(w2.w, yv, acc[11]);
-      acc[12] = fmaf(w3.x, yv, acc[12]); acc[13] = fmaf(w3.y, yv, acc[13]); acc[14] = fmaf(w3.z, yv, acc[14]); acc[15] = fmaf(w3.w, yv, acc[15]);
+#pragma unroll 1
+    for (int rs = r0; rs < r1; rs += SUB) {
+      const int nr = min(SUB, r1 - rs);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nr * (CW / 4); i += CR_T) s_w[i] = __ldg(wp + (size_t)rs * (CW / 4) + i);
+      __syncthreads();
+#pragma unroll 2
+      for (int rr = 0; rr < nr; ++rr) {
+        float yv[4];
+        get4<X3>(Yh, Yl, y0 + (size_t)(rs + rr) * y_ld, yv);
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const float4 wv = s_w[rr * (CW / 4) + q];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[k][4 * q + 0] = fmaf(wv.x, yv[k], acc[k][4 * q + 0]);
+            acc[k][4 * q + 1] = fmaf(wv.y, yv[k], acc[k][4 * q + 1]);
+            acc[k][4 * q + 2] = fmaf(wv.z, yv[k], acc[k][4 * q + 2]);
+            acc[k][4 * q + 3] = fmaf(wv.w, yv[k], acc[k][4 * q + 3]);
+          }
+        }
+      }
     }
   } else {
-#pragma unroll 8
-    for (int r = r0; r < r1; ++r) acc[0] += get<X3>(Yh, Yl, y0 + (size_t)r * y_ld);
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      float yv[4];
+      get4<X3>(Yh, Yl, y0 + (size_t)r * y_ld, yv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k][0] += yv[k];
+    }
   }
-  for (int c = 0; c < C; ++c) part[(((size_t)zc * gridDim.y + s) * C + c) * H + h] = acc[c];
+#pragma unroll
+  for (int c = 0; c < CW; ++c)
+    if (c < C && live)
+      *reinterpret_cast<float4*>(part + (((size_t)zc * gridDim.y + s) * C + c) * H + h) =
+          make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
 }
 __global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int S, int H, int C, float* __restrict__ out, long long P,
                                             int accumulate) {
@@ -581,40 +631,78 @@ __global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int 
 // The three weighted column reductions of the dual pass in ONE sweep over hh = [hdot | h] (each element read once):
 //   part[z][s][0][c][h] = sum_r (Wo[s][r][c] h[s][r][h] + Wod[s][r][c] hdot[s][r][h])     (A_o^T h + A_od^T hdot)
 //   part[z][s][1][c][h] = sum_r Wod[s][r][c] h[s][r][h]                                   (A_od^T h)
+// A thread owns two consecutive columns (2 x 2 x 16 accumulators).
 template <int X3>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void get2(const void* hi_base, const void* lo_base, size_t i, float (&v)[2]) {
+  if (X3 == 1) {
+    const float2 h = *reinterpret_cast<const float2*>(static_cast<const float*>(hi_base) + i);
+    const float2 l = *reinterpret_cast<const float2*>(static_cast<const float*>(lo_base) + i);
+    v[0] = h.x + l.x; v[1] = h.y + l.y;
+  } else {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(hi_base) + i);
+    v[0] = __uint_as_float(h << 16); v[1] = __uint_as_float(h & 0xFFFF0000u);
+    if (X3 == 2) {
+      const uint32_t l = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(lo_base) + i);
+      v[0] += __uint_as_float(l << 16); v[1] += __uint_as_float(l & 0xFFFF0000u);
+    }
+  }
+}
+constexpr int CRD_T = 128;   // threads per CTA of the dual reduction (CRD_T * 2 columns)
+template <int X3>
+__global__ void __launch_bounds__(CRD_T)
 fnl_colreduce_dual_kernel(const void* Yh, const void* Yl, long long y_bs, const float* __restrict__ Wo,
                           const float* __restrict__ Wod, int R, int H, int C, float* __restrict__ part) {
-  const int h = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, zc = blockIdx.z;
-  if (h >= H) return;
+  const int h_raw = (blockIdx.x * CRD_T + threadIdx.x) * 2, s = blockIdx.y, zc = blockIdx.z;
+  const bool live = h_raw < H;
+  const int h = live ? h_raw : 0;   // (idle threads of a partial column block shadow column 0 and do not write)
   const int rpc = (R + RSPLIT - 1) / RSPLIT, r0 = zc * rpc, r1 = min(R, r0 + rpc);
-  float a1[CW], a2[CW];
-#pragma unroll
-  for (int c = 0; c < CW; ++c) a1[c] = a2[c] = 0.f;
   const size_t y0 = (size_t)((long long)s * y_bs + h);
   const float4* wo = reinterpret_cast<const float4*>(Wo + (size_t)s * R * CW);
   const float4* wd = reinterpret_cast<const float4*>(Wod + (size_t)s * R * CW);
-#pragma unroll 2
-  for (int r = r0; r < r1; ++r) {
-    const float hd = get<X3>(Yh, Yl, y0 + (size_t)r * 2 * H), hv = get<X3>(Yh, Yl, y0 + (size_t)r * 2 * H + H);
+  float a1[2][CW], a2[2][CW];
 #pragma unroll
-    for (int q = 0; q < CW / 4; ++q) {
-      const float4 u = __ldg(wo + r * (CW / 4) + q), v = __ldg(wd + r * (CW / 4) + q);
-      a1[4 * q + 0] = fmaf(u.x, hv, fmaf(v.x, hd, a1[4 * q + 0]));
-      a1[4 * q + 1] = fmaf(u.y, hv, fmaf(v.y, hd, a1[4 * q + 1]));
-      a1[4 * q + 2] = fmaf(u.z, hv, fmaf(v.z, hd, a1[4 * q + 2]));
-      a1[4 * q + 3] = fmaf(u.w, hv, fmaf(v.w, hd, a1[4 * q + 3]));
-      a2[4 * q + 0] = fmaf(v.x, hv, a2[4 * q + 0]);
-      a2[4 * q + 1] = fmaf(v.y, hv, a2[4 * q + 1]);
-      a2[4 * q + 2] = fmaf(v.z, hv, a2[4 * q + 2]);
-      a2[4 * q + 3] = fmaf(v.w, hv, a2[4 * q + 3]);
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int c = 0; c < CW; ++c) a1[k][c] = a2[k][c] = 0.f;
+  // the row weights of a sub-chunk are staged in shared memory once (coalesced) and read back as broadcast 128-bit loads
+  constexpr int SUB = 64;
+  __shared__ float4 s_wo[SUB * (CW / 4)], s_wd[SUB * (CW / 4)];
+#pragma unroll 1
+  for (int rs = r0; rs < r1; rs += SUB) {
+    const int nr = min(SUB, r1 - rs);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * (CW / 4); i += CRD_T) {
+      s_wo[i] = __ldg(wo + (size_t)rs * (CW / 4) + i);
+      s_wd[i] = __ldg(wd + (size_t)rs * (CW / 4) + i);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int rr = 0; rr < nr; ++rr) {
+      const int r = rs + rr;
+      float hd[2], hv[2];
+      get2<X3>(Yh, Yl, y0 + (size_t)r * 2 * H, hd);
+      get2<X3>(Yh, Yl, y0 + (size_t)r * 2 * H + H, hv);
+#pragma unroll
+      for (int q = 0; q < CW / 4; ++q) {
+        const float4 u = s_wo[rr * (CW / 4) + q], v = s_wd[rr * (CW / 4) + q];
+        const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            a1[k][4 * q + e] = fmaf(uu[e], hv[k], fmaf(vv[e], hd[k], a1[k][4 * q + e]));
+            a2[k][4 * q + e] = fmaf(vv[e], hv[k], a2[k][4 * q + e]);
+          }
+      }
     }
   }
   float* p1 = part + (((size_t)zc * gridDim.y + s) * 2) * C * H;
-  for (int c = 0; c < C; ++c) {
-    p1[(size_t)c * H + h] = a1[c];
-    p1[(size_t)(C + c) * H + h] = a2[c];
-  }
+#pragma unroll
+  for (int c = 0; c < CW; ++c)
+    if (c < C && live) {
+      *reinterpret_cast<float2*>(p1 + (size_t)c * H + h) = make_float2(a1[0][c], a1[1][c]);
+      *reinterpret_cast<float2*>(p1 + (size_t)(C + c) * H + h) = make_float2(a2[0][c], a2[1][c]);
+    }
 }
 // out1[s * P + i] = sum_z part[z][s][0][i], out2[s * P + i] = sum_z part[z][s][1][i]   (i = c * H + h)
 __global__ void fnl_colreduce_dual_finish_kernel(const float* __restrict__ part, int S, int H, int C, float* __restrict__ out1,
@@ -860,7 +948,7 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   for (int part = 0; part < (X3 ? 2 : 1); ++part)   // K blocks of the output adjoints: zero except the 16-entry heads
     PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.AA.lo : w.AA.hi, 0, (size_t)S * Rp * 2 * CP * ES, st));
   auto colreduce = [&](const Buf& Y, long long y_off, const float* W, int Cc, float* out, int accumulate) {
-    fnl_colreduce_kernel<X3><<<dim3(H / 128, S, RSPLIT), 128, 0, st>>>(Y.hi, Y.lo, y_off, hh_bs, 2 * H, W, R, H, Cc, w.cpart);
+    fnl_colreduce_kernel<X3><<<dim3((H + 4 * CR_T - 1) / (4 * CR_T), S, RSPLIT), CR_T, 0, st>>>(Y.hi, Y.lo, y_off, hh_bs, 2 * H, W, R, H, Cc, w.cpart);
     fnl_colreduce_finish_kernel<<<dim3((Cc * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, Cc, out, P, accumulate);
   };
   if (!dual) {
@@ -921,7 +1009,7 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   // A_W2dot = A_od^T h in one sweep over hh
   fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);
   fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.adT.hi, w.adT.lo, H, Rp, R, tdbar + o_b1, P);
-  fnl_colreduce_dual_kernel<X3><<<dim3(H / 128, S, RSPLIT), 128, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
+  fnl_colreduce_dual_kernel<X3><<<dim3((H + 2 * CRD_T - 1) / (2 * CRD_T), S, RSPLIT), CRD_T, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
   fnl_colreduce_dual_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, C, tbar + o_w2, tdbar + o_w2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.god, R, C, tdbar + o_b2, P);
