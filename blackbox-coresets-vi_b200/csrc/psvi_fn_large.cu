@@ -728,7 +728,12 @@ fnl_rowsum_kernel(const void* Yh, const void* Yl, int H, int Rp, int R, float* _
   if (row >= H) return;
   const size_t base = ((size_t)s * H + row) * Rp;
   float t = 0.f;
-  for (int r = lane; r < R; r += 32) t += get<X3>(Yh, Yl, base + r);
+  for (int r4 = lane * 4; r4 < R; r4 += 128) {   // four consecutive r per lane and load (Rp is a multiple of 128)
+    float v[4];
+    get4<X3>(Yh, Yl, base + r4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t += r4 + k < R ? v[k] : 0.f;
+  }
   t = warp_sum(t);
   if (lane == 0) out[(long long)s * P + row] = t;
 }
