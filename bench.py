@@ -531,6 +531,43 @@ def main():
     except Exception as e:
         fn2 = {"error": repr(e)[:300]}
 
+    # -------- cfg5 (fn D=256 H=1024 C=10, M=1000, S=64, B=128, T=10): one PSVI outer step through the batched tcgen05 GEMM
+    # path of the large regime, in both split-precision arithmetics -----------------------------------
+    fn5 = None
+    try:
+        from psvi.experiments.experiments_utils import SynthDataset as _SD5, make_synthetic_rows as _msr5
+        from psvi.inference.psvi_classes import PSVILearnV as _PL5
+        X5, Y5 = _msr5(20000, 256, 10, seed=0)
+        t5, e5 = _SD5(X5[:16000], Y5[:16000].float()), _SD5(X5[16000:], Y5[16000:].float())
+        k5 = dict(mc_samples=64, num_epochs=0, data_minibatch=128, D=256, N=16000, inner_it=10, trainer="nested", log_every=1000,
+                  lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-3, num_pseudo=1000, seed=rank,
+                  architecture="fn", n_hidden=1024, n_layers=1, logistic_regression=False, train_dataset=t5, test_dataset=e5,
+                  dnm="synthetic", nc=10, compute_weights_entropy=False, register_elbos=False, quiet=True)
+        fn5 = {"what": "PSVILearnV.nested_step, fn D=256 H=1024 C=10 (P = 273 418 per sample), M=1000, S=64, B=128, T=10; "
+                       "batched TMA + tcgen05 GEMMs; algorithmic FLOPs = T 9 F(M) + 3 F(M+B), F(R) = 2 S R (D H + H C)"}
+        f5 = lambda R_: 2.0 * 64 * R_ * (256 * 1024 + 1024 * 10)
+        fl5 = 10 * 9 * f5(1000) + 3 * f5(1128)
+        for prec in ("tf32x3", "bf16x3"):
+            o5 = _PL5(**k5)
+            o5.large_precision = prec
+            o5.run_psvi(**k5)
+            pc._dist_info = lambda: (None, 0, 1)
+            x5b, y5b = o5._next_minibatch()
+            o5.nested_step(x5b, y5b)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(2):
+                o5.nested_step(x5b, y5b)
+            b.record(stream)
+            torch.cuda.synchronize()
+            pc._dist_info = real_dist_info
+            ms5 = a.elapsed_time(b) / 2
+            fn5[prec] = {"ms_per_outer_step": ms5, "outer_steps_per_s": 1e3 / ms5, "algorithmic_TFLOPs": fl5 / ms5 / 1e9}
+            del o5
+            torch.cuda.empty_cache()
+    except Exception as e:
+        fn5 = {"error": repr(e)[:300]}
+
     # -------- extra: several independent chains on ONE GPU (the reference's multi-trial mode) ------------------------
     replicas = bench_replicas(c, dev, 8, min(K, 40), 3) if rank == 0 else None
 
@@ -581,7 +618,7 @@ def main():
                             "time = whole psvi_fn_predictive_tc call incl. weight sampling; peak = measured SUSTAINED bf16 "
                             "matmul throughput (the kernel runs for tens of ms back to back); ncu: "
                             "profiles/r1_fn_tc_ncu_summary.md"},
-                "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fn2_cfg3": fn2, "replicas_one_gpu": replicas, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
+                "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fn2_cfg3": fn2, "fn_large_cfg5": fn5, "replicas_one_gpu": replicas, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
                                                     "full_data_predictive_passes_200rows": pred_evals},
                           "sharded": sharded, "kernel_only_ms": kernel_ms,
                           "per_step_ms_min_med_max": [min(ms), sorted(ms)[len(ms) // 2], max(ms)]}}
