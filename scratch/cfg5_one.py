@@ -13,6 +13,7 @@ kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=2500, inner_it=T,
           n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="synthetic", nc=C,
           compute_weights_entropy=False, register_elbos=False, quiet=True)
 obj = PSVILearnV(**kw)
+obj.large_precision = sys.argv[1] if len(sys.argv) > 1 else 'tf32x3'
 obj.run_psvi(**kw)
 xb, yb = obj._next_minibatch()
 obj.nested_step(xb, yb)
