@@ -249,3 +249,26 @@ def test_prune_and_retrain_on_coreset_run():
     assert obj.num_pseudo == 20 and obj.u.shape[0] == 20 and obj.v.shape[0] == 20 and obj.z.shape[0] == 20
     assert res["csizes"][:5] == [40, 40, 30, 30, 20] and len(res["accs"]) == 10      # 5 PSVI + 5 retraining evaluations
     assert res["accs"][-1] > 0.8 and all(np.isfinite(res["nlls"]))
+
+
+@pytest.mark.parametrize("arch", ["fn2", "lenet"])
+def test_hyper_trainer_runs_on_the_streaming_families(arch):
+    """--trainer hyper (implicit hypergradient, CG on the normal equations) through the streaming engine for the
+    full-covariance and the convolutional family: runs, consumes noise, returns finite metrics and moves u and v."""
+    from psvi.inference.psvi_classes import PSVILearnV
+    if arch == "lenet":
+        from tests.fake_mnist import FakeMNIST
+        tr, te = FakeMNIST(300, 0), FakeMNIST(64, 1)
+        extra = dict(D=784, N=len(tr), dnm="MNIST", nc=10, n_hidden=0, num_pseudo=20, mc_samples=4)
+    else:
+        from psvi.experiments.experiments_utils import read_dataset
+        x, y, xt, yt, N, D, tr, te, nc = read_dataset("halfmoon", {"test_ratio": 0.2})
+        extra = dict(D=D, N=N, dnm="halfmoon", nc=nc, n_hidden=8, num_pseudo=10, mc_samples=6)
+    kw = dict(num_epochs=3, data_minibatch=64, inner_it=4, trainer="hyper", log_every=2, lr0u=1e-3, lr0net=1e-3, lr0v=1e-2,
+              init_args="subsample", init_sd=1e-2, seed=2, architecture=arch, n_layers=1, logistic_regression=False,
+              train_dataset=tr, test_dataset=te, compute_weights_entropy=False, register_elbos=False, quiet=True, **extra)
+    obj = PSVILearnV(**kw)
+    res = obj.run_psvi(**kw)
+    assert len(res["accs"]) == 2 and np.isfinite(res["nlls"]).all()
+    assert torch.isfinite(obj.u).all() and torch.isfinite(obj.v).all()
+    assert float(obj.v.detach().abs().max()) > 0.0          # v started at zero: the outer optimiser moved it
