@@ -179,6 +179,9 @@ def bench_replicas(c, dev, n_chains, K, W):
     independent cfg2 chains, one CUDA stream each.  A chain's step is one 10-CTA cluster launch (10 of the SMs), so several
     chains run concurrently; the aggregate is reported as an extra, never as the headline."""
     import torch
+    import psvi.inference.psvi_classes as pc
+    real = pc._dist_info
+    pc._dist_info = lambda: (None, 0, 1)
     try:
         chains = [build_chain(c, seed=100 + i, device=dev) for i in range(n_chains)]
         streams = [torch.cuda.Stream(device=dev) for _ in range(n_chains)]
@@ -214,6 +217,8 @@ def bench_replicas(c, dev, n_chains, K, W):
                 "wall_ms": wall * 1e3}
     except Exception as e:  # noqa: BLE001 -- an extra must not take the headline down
         return {"error": repr(e)[:300]}
+    finally:
+        pc._dist_info = real
 
 
 _STDOUT_FD = None
@@ -569,7 +574,9 @@ def main():
         fn5 = {"error": repr(e)[:300]}
 
     # -------- extra: several independent chains on ONE GPU (the reference's multi-trial mode) ------------------------
-    replicas = bench_replicas(c, dev, 8, min(K, 40), 3) if rank == 0 else None
+    # (single-process runs only: a chain built here would take the sharded code path under torch.distributed and wait for
+    # collectives the other ranks never join)
+    replicas = bench_replicas(c, dev, 8, min(K, 40), 3) if world == 1 else None
 
     # -------- reduce over ranks ---------------------------------------------------------------------------------------
     value = world * K / (total_ms * 1e-3)
