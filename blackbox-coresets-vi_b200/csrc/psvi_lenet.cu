@@ -10,9 +10,12 @@
 // theta layout (TL): per layer weight then bias: W1[6][1][5][5] b1[6] W2[16][6][5][5] b2[16] W3[120][400] b3[120]
 // W4[84][120] b4[84] W5[10][84] b5[10]  (P = 61 706).
 // fp32 on the CUDA cores: the products have K = 25 / 150 and N = 6 / 16 -- far below a 128-wide UMMA tile -- and the
-// reference computes this family in fp32.  One CTA per (row, sample) keeps a whole image's feature maps in shared memory:
-// conv + ReLU + pool are fused (the full-resolution maps never reach global memory; only the pooled map and a 3-bit
-// selection code per pooled element do), and the backward kernels scatter through that code on the fly.
+// reference computes this family in fp32 (and bf16 operands would destroy the unrolled hypergradient).  A CTA
+// keeps the feature maps of a few rows of one sample in shared memory: conv + ReLU + pool are fused (the full-resolution maps
+// never reach global memory; only the pooled map and a 3-bit selection code per pooled element do), the backward kernels
+// scatter through that code on the fly, and every conv kernel is register-tiled so that the FMA pipe, not shared memory, is
+// the limit (patch reuse across channels, 64/128-bit shared loads); the fully connected layers go through one batched
+// small-GEMM kernel.
 #include <algorithm>
 #include "psvi_common.cuh"
 
@@ -22,8 +25,6 @@ constexpr int LN_P = 61706;
 constexpr int O_W1 = 0, O_B1 = 150, O_W2 = 156, O_B2 = 2556, O_W3 = 2572, O_B3 = 50572, O_W4 = 50692, O_B4 = 60772,
               O_W5 = 60856, O_B5 = 61696;
 constexpr int N_P1 = 6 * 14 * 14, N_P2 = 16 * 5 * 5, N_H3 = 120, N_H4 = 84, N_O = 10, N_X = 28 * 28;
-// makes a loaded value opaque to the optimiser, so it stays in a register instead of being re-read from shared memory
-#define KEEP_IN_REG(x) asm volatile("" : "+f"(x))
 constexpr int N_CHUNKS = 128;   // row chunks of the conv weight-gradient kernels (up to 128 x S CTAs)
 
 // ------------------------------------------------------------------------------------------------ conv + ReLU + pool
