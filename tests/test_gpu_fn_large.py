@@ -196,3 +196,33 @@ def test_large_fn_nested_step_and_evaluate_through_psvi_class(prec, tol, min_cos
     obj.noise_source = None
     acc, nll, went, ness, vent = obj.evaluate()
     assert 0.0 <= acc.item() <= 1.0 and np.isfinite(nll.item()) and nll.item() > 0
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3", "bf16x3"])
+def test_fnl_pass_writes_inside_its_outputs_only(prec):
+    """Guard regions around every output of the gradient and dual passes stay untouched when the row count is not a multiple
+    of the 128-row tile (R = 37) and C = 3 pads to 16; NaN-filled outputs are fully overwritten."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    PREC = {"bf16": nat.PREC_BF16, "tf32x3": nat.PREC_TF32X3, "bf16x3": nat.PREC_BF16X3}[prec]
+    D, H, C, S, R, G = 64, 128, 3, 2, 37, 1024
+    dims, theta, thetad, X, y, cw = make_case(D, H, C, S, R, 9)
+    P = theta.shape[1]
+    model = nat.make_model(dims, S)
+    th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
+
+    def guarded(*shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * G,), 12345.0, device="cuda")
+        view = buf[G:G + n].view(*shape)
+        view.fill_(float("nan"))
+        return buf, view
+    outs = {k: guarded(*shp) for k, shp in dict(nll=(S, R), tbar=(S, P), xbar=(S, R, D), logits=(S, R, C)).items()}
+    nat.fnl_pass(model, PREC, th, None, x_, y_, cw_, **{k: v[1] for k, v in outs.items()})
+    outs2 = {k: guarded(*shp) for k, shp in dict(tbar=(S, P), tdbar=(S, P), xbar=(S, R, D), acbar=(S, R)).items()}
+    nat.fnl_pass(model, PREC, th, thd, x_, y_, cw_, **{k: v[1] for k, v in outs2.items()})
+    torch.cuda.synchronize()
+    for group in (outs, outs2):
+        for k, (buf, view) in group.items():
+            assert torch.all(buf[:G] == 12345.0) and torch.all(buf[-G:] == 12345.0), k
+            assert torch.isfinite(view).all(), k

@@ -149,3 +149,30 @@ def test_lenet_psvi_run_learns_synthetic_digits():
     accs = [float(a) for a in res["accs"]]
     assert accs[0] < 0.3 and accs[-1] > 0.9, accs
     assert all(np.isfinite(float(x)) for x in res["nlls"])
+
+
+@pytest.mark.parametrize("S,R", [(1, 1), (2, 11), (3, 6)])
+def test_lenet_pass_writes_inside_its_outputs_only(S, R):
+    """Guard regions around every output of the gradient and dual passes stay untouched for row counts that leave partial
+    image groups / row chunks / 32-wide tiles in every kernel (R = 1, 11, 6); NaN-filled outputs are fully overwritten."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    theta, thetad, X, y, cw = _case(S, R, 5)
+    P, G = theta.shape[1], 1024
+    th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
+
+    def guarded(*shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * G,), 12345.0, device="cuda")
+        view = buf[G:G + n].view(*shape)
+        view.fill_(float("nan"))
+        return buf, view
+    outs = {k: guarded(*shp) for k, shp in dict(nll=(S, R), tbar=(S, P), xbar=(S, R, 784)).items()}
+    nat.lenet_pass(S, th, None, x_, y_, cw_, **{k: v[1] for k, v in outs.items()})
+    outs2 = {k: guarded(*shp) for k, shp in dict(tbar=(S, P), tdbar=(S, P), xbar=(S, R, 784), acbar=(S, R)).items()}
+    nat.lenet_pass(S, th, thd, x_, y_, cw_, **{k: v[1] for k, v in outs2.items()})
+    torch.cuda.synchronize()
+    for group in (outs, outs2):
+        for k, (buf, view) in group.items():
+            assert torch.all(buf[:G] == 12345.0) and torch.all(buf[-G:] == 12345.0), k
+            assert torch.isfinite(view).all(), k
