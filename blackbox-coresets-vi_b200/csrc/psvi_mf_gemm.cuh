@@ -107,7 +107,32 @@ __device__ __forceinline__ void small_gemm(int nrows, int ncols, int K, const Ge
     const bool cok = cc < ncols;
     const float* Bp = op.B + (cok ? cc : 0) * op.b_cs;
     const float* B2p = two ? op.B2 + (cok ? cc : 0) * op.b_cs : nullptr;
-    if (g == 1) {
+    if (g == 1 && K <= 4) {
+      // short dot products (first layer with D <= 3 inputs + bias, data adjoints with C <= 4 classes): the column of B stays
+      // in registers for all rows and the k loop is fully unrolled (predicated, no loads beyond K)
+      float b[4], b2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        b[k] = (cok && k < K) ? Bp[k * op.b_ks] : 0.f;
+        b2[k] = (two && cok && k < K) ? B2p[k * op.b_ks] : 0.f;
+      }
+      if (cok) {
+        for (int rr = rg; rr < nrows; rr += RG) {
+          const float* A0 = op.A + rr * op.a_rs;
+          float c0 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < K) c0 = fmaf(A0[k * op.a_ks], b[k], c0);
+          if (two) {
+            const float* A20 = op.A2 + rr * op.a_rs;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < K) c0 = fmaf(A20[k * op.a_ks], b2[k], c0);
+          }
+          epi(rr, cc, c0);
+        }
+      }
+    } else if (g == 1) {
       int rr = rg;
       // 4-row register blocking
       for (; rr + 3 * RG < nrows; rr += 4 * RG) {
