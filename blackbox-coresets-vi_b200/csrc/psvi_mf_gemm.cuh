@@ -91,8 +91,8 @@ struct GemmOp {
 
 template <class Epi>
 __device__ __forceinline__ void small_gemm(int nrows, int ncols, int K, const GemmOp& op, Epi epi) {
-  int cl_sh = 0;
-  while ((1 << cl_sh) < ncols && (1 << cl_sh) < NT) ++cl_sh;
+  // smallest power of two >= min(ncols, NT)   (NT = 256 = 2^8)
+  const int cl_sh = ncols <= 1 ? 0 : min(8, 32 - __clz(ncols - 1));
   const int CL = 1 << cl_sh;
   int RG = NT >> cl_sh;  // row groups before the k-split
   int g_sh = 0;
