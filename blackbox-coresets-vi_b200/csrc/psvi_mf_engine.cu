@@ -251,20 +251,14 @@ struct Engine {
       small_gemm(nr, dout, din + 1, op,
                  [&](int rr, int oo, float acc) { out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc; });
       if (dual) {
-        // tangent pre-activation  x Wd^T (+ xd W^T for l > 1; xd of the input layer is zero); masked below
+        // tangent pre-activation  x Wd^T (+ xd W^T for l > 1; xd of the input layer is zero), masked by the primal ReLU:
+        // small_gemm maps (row, column) to threads by (nrows, ncols, K) only, so out[rr][oo] was written by this thread
         GemmOp opd{in, ldi, 1, Wd, ldw, 1, l > 1 ? ind : nullptr, l > 1 ? W : nullptr};
-        small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) { outd[rr * ldo + oo] = acc; });
+        small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) {
+          outd[rr * ldo + oo] = (relu && !(out[rr * ldo + oo] > 0.f)) ? 0.f : acc;
+        });
       }
       __syncthreads();
-      if (dual && relu) {
-        const int cl = 1 << (32 - __clz(dout - 1 | 1));  // power of two >= dout (>= 2)
-        const int sh = 31 - __clz(cl);
-        for (int i = tid; i < (nr << sh); i += NT) {
-          const int rr = i >> sh, oo = i & (cl - 1);
-          if (oo < dout && !(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
-        }
-        __syncthreads();
-      }
     }
   }
 

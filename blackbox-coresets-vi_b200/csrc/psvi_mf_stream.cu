@@ -207,14 +207,11 @@ struct Worker {
       GemmOp op{in, ldi, 1, W, ldw, 1, nullptr, nullptr};
       small_gemm(nr, dout, din + 1, op, [&](int rr, int oo, float acc) { out[rr * ldo + oo] = relu ? fmaxf(acc, 0.f) : acc; });
       GemmOp opd{in, ldi, 1, Wd, ldw, 1, l > 1 ? ind : nullptr, l > 1 ? W : nullptr};
-      small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) { outd[rr * ldo + oo] = acc; });
+      // (masked by the primal ReLU: the same thread wrote out[rr][oo] -- small_gemm maps outputs to threads by shape only)
+      small_gemm(nr, dout, din + 1, opd, [&](int rr, int oo, float acc) {
+        outd[rr * ldo + oo] = (relu && !(out[rr * ldo + oo] > 0.f)) ? 0.f : acc;
+      });
       __syncthreads();
-      if (relu) {
-        for (int rr = 0; rr < nr; ++rr)
-          for (int oo = tid; oo < dout; oo += NT)
-            if (!(out[rr * ldo + oo] > 0.f)) outd[rr * ldo + oo] = 0.f;
-        __syncthreads();
-      }
     }
   }
   __device__ void loss_dual(int nr, float* ac_out) {
