@@ -326,17 +326,21 @@ struct Engine {
       float* acc3 = F(ly.acc3) + mt.woff[l];
       const bool has_ind = dual && l > 1;
       // -- weight + bias adjoints: C(o, i) = sum_r A[r][o] * in[r][i], i <= din (in[r][din] == 1)
-      GemmOp ow{A, 1, ldo, in, 1, ldi, has_ind ? Ad : nullptr, has_ind ? ind : nullptr};
-      small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
-        const int pp = oo * ldw + ii;
-        acc1[pp] += acc;
-        acc2[pp] += acc * eps[pp];
-      });
-      if (dual) {
-        GemmOp owd{Ad, 1, ldo, in, 1, ldi, nullptr, nullptr};
-        small_gemm(dout, din + 1, nr, owd, [&](int oo, int ii, float acc) {
+      if (dual) {   // A_theta = A^T in + Ad^T ind  and  A_thetadot = Ad^T in  in one pass over the shared operands
+        GemmOp ow{A, 1, ldo, in, 1, ldi, Ad, has_ind ? ind : nullptr};
+        small_gemm_pair(dout, din + 1, nr, ow, [&](int oo, int ii, float acc, float accd) {
           const int pp = oo * ldw + ii;
-          acc3[pp] += acc * eps[pp];
+          const float e = eps[pp];
+          acc1[pp] += acc;
+          acc2[pp] += acc * e;
+          acc3[pp] += accd * e;
+        });
+      } else {
+        GemmOp ow{A, 1, ldo, in, 1, ldi, nullptr, nullptr};
+        small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
+          const int pp = oo * ldw + ii;
+          acc1[pp] += acc;
+          acc2[pp] += acc * eps[pp];
         });
       }
       // -- input adjoints: C(r, i) = sum_o A[r][o] * W[o][i]  (+ Ad[r][o] * Wd[o][i])

@@ -205,4 +205,58 @@ __device__ __forceinline__ void small_gemm(int nrows, int ncols, int K, const Ge
 }
 
 
+// Two products that share their operands, in one pass (the weight adjoints of the dual backward):
+//   C (r, c) = sum_k A(r, k) B(k, c) + A2(r, k) B2(k, c)      (A2 / B2 as in GemmOp; B2 may be NULL: second term dropped)
+//   Cd(r, c) = sum_k A2(r, k) B(k, c)
+// epi(r, c, C, Cd) consumes every output pair exactly once.  Same thread mapping as small_gemm.
+template <class Epi>
+__device__ __forceinline__ void small_gemm_pair(int nrows, int ncols, int K, const GemmOp& op, Epi epi) {
+  const int cl_sh = ncols <= 1 ? 0 : min(8, 32 - __clz(ncols - 1));
+  const int CL = 1 << cl_sh;
+  int RG = NT >> cl_sh;
+  int g_sh = 0;
+  while ((2 << g_sh) <= 32 && nrows * (2 << g_sh) <= RG && K >= (8 << g_sh)) ++g_sh;
+  const int g = 1 << g_sh;
+  RG >>= g_sh;
+  const int tid = threadIdx.x;
+  const int ks = tid & (g - 1), col = (tid >> g_sh) & (CL - 1), rg = tid >> (g_sh + cl_sh);
+  const bool two = op.B2 != nullptr;
+  for (int cb = 0; cb < ncols; cb += CL) {
+    const int cc = cb + col;
+    const bool cok = cc < ncols;
+    const float* Bp = op.B + (cok ? cc : 0) * op.b_cs;
+    const float* B2p = two ? op.B2 + (cok ? cc : 0) * op.b_cs : nullptr;
+    for (int rb = 0; rb < nrows; rb += RG) {
+      const int rr = rb + rg;
+      const bool ok = cok && rr < nrows;
+      float c0 = 0.f, d0 = 0.f;
+      if (ok) {
+        const float* A0 = op.A + rr * op.a_rs;
+        const float* A20 = op.A2 + rr * op.a_rs;
+        if (two) {
+#pragma unroll 4
+          for (int k = ks; k < K; k += g) {
+            const float b = Bp[k * op.b_ks], a2 = A20[k * op.a_ks];
+            c0 = fmaf(A0[k * op.a_ks], b, fmaf(a2, B2p[k * op.b_ks], c0));
+            d0 = fmaf(a2, b, d0);
+          }
+        } else {
+#pragma unroll 4
+          for (int k = ks; k < K; k += g) {
+            const float b = Bp[k * op.b_ks];
+            c0 = fmaf(A0[k * op.a_ks], b, c0);
+            d0 = fmaf(A20[k * op.a_ks], b, d0);
+          }
+        }
+      }
+      for (int off = g >> 1; off > 0; off >>= 1) {   // (g == 1: no trips; otherwise every lane of the warp takes part)
+        c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, off);
+      }
+      if (ok && ks == 0) epi(rr, cc, c0, d0);
+    }
+  }
+}
+
+
 }  // namespace psvi_mf

@@ -256,15 +256,17 @@ struct Worker {
       const float* Wd = F(ly.thetad) + mt.woff[l];
       const bool has_ind = dual && l > 1;
       const int tlw = mt.tlw[l], tlb = mt.tlb[l];
-      GemmOp ow{A, 1, ldo, in, 1, ldi, has_ind ? Ad : nullptr, has_ind ? ind : nullptr};
-      small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
-        float* dst = tbar + (ii < din ? tlw + oo * din + ii : tlb + oo);
-        *dst = first_chunk ? acc : *dst + acc;
-      });
-      if (dual) {
-        GemmOp owd{Ad, 1, ldo, in, 1, ldi, nullptr, nullptr};
-        small_gemm(dout, din + 1, nr, owd, [&](int oo, int ii, float acc) {
-          float* dst = tdbar + (ii < din ? tlw + oo * din + ii : tlb + oo);
+      if (dual) {   // A_theta = A^T in + Ad^T ind  and  A_thetadot = Ad^T in  in one pass over the shared operands
+        GemmOp ow{A, 1, ldo, in, 1, ldi, Ad, has_ind ? ind : nullptr};
+        small_gemm_pair(dout, din + 1, nr, ow, [&](int oo, int ii, float acc, float accd) {
+          const int off = ii < din ? tlw + oo * din + ii : tlb + oo;
+          tbar[off] = first_chunk ? acc : tbar[off] + acc;
+          tdbar[off] = first_chunk ? accd : tdbar[off] + accd;
+        });
+      } else {
+        GemmOp ow{A, 1, ldo, in, 1, ldi, nullptr, nullptr};
+        small_gemm(dout, din + 1, nr, ow, [&](int oo, int ii, float acc) {
+          float* dst = tbar + (ii < din ? tlw + oo * din + ii : tlb + oo);
           *dst = first_chunk ? acc : *dst + acc;
         });
       }
