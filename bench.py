@@ -55,13 +55,36 @@ def make_data(seed=42):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class Clocks:
+    """SM clock and throttle reasons of one GPU, sampled WHILE the timed regions run.  In-process NVML (pynvml, one query
+    takes microseconds) on a thread every 10 ms; `nvidia-smi -lms` as the fallback.  start() is called before the warm-up so
+    that NVML / nvidia-smi initialisation (seconds on an 8-GPU box) is over when mark() opens the timed window; stop() keeps
+    the samples taken inside the window."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.nvml, self.stop_flag, self.mx = [], None, index, 0.0, None, False, None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml, self.h = self._handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -71,32 +94,53 @@ class Clocks:
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+    def mark(self):
+        self.t0 = time.monotonic()
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.monotonic(), mhz, self.mx, {name for bit, name in self.REASONS if bits & bit}))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _read(self):
+        names = [name for _, name in self.REASONS]
+        for line in self.proc.stdout:
+            r = [t.strip() for t in line.split(",")]
+            try:
+                self.rows.append((time.monotonic(), float(r[0]), float(r[1]),
+                                  {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi on this box"], "samples": 0}
+        t_end = time.monotonic()
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        rows = [r for r in self.rows if self.t0 <= r[0] <= t_end]
+        note = []
+        if not rows and self.rows:      # timed window shorter than the sampling period: the nearest samples
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - self.t0), abs(r[0] - t_end)))[:3]
+            note = ["no sample fell inside the timed window; nearest samples reported"]
+        sm = sorted(r[1] for r in rows)
+        reasons = set().union(*[r[3] for r in rows]) if rows else set()
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[-1][2] if rows else self.mx,
+               "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+        if note:
+            out["note"] = note[0]
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -286,11 +330,12 @@ def main():
 
     # -------- value: device-resident inputs, per-step CUDA events, L2 flush between steps ----------------------------
     launches0 = _native.launch_count() if hasattr(_native, "launch_count") else 0
+    clocks = Clocks(local)
+    clocks.start()
     for i in range(W):
         obj.nested_step(*dev_batches[i])
     barrier()
-    clocks = Clocks(local)
-    clocks.start()
+    clocks.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches1 = _native.launch_count()
     for i in range(K):
