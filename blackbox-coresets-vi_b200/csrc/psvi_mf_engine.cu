@@ -20,72 +20,13 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
-#include "psvi_mf_gemm.cuh"
+#include "psvi_mf_engine.cuh"
 
 namespace cg = cooperative_groups;
 using namespace psvi_mf;
 
 namespace {
 
-
-enum : int {
-  F_UNROLL = 1,       // T Adam steps on the inner objective
-  F_OUTER = 2,        // psvi_elbo forward + backward at the current phi
-  F_REVERSE = 4,      // reverse sweep through the trajectory
-  F_HVP = 8,          // one Hessian-vector pass along p.gdot
-  F_NOUPDATE = 16,    // F_UNROLL: compute the gradient but do not move phi (inner_grad entry point)
-  F_STORE_GOUT = 32,  // write the phase-boundary buffer (outer gradient wrt phi_T, direct u/a partials, d_s, loss)
-  F_LOAD_GOUT = 64,   // start the reverse sweep from the phase-boundary buffer
-  F_FINAL = 128,      // reduce ubar/abar over the cluster and write u_grad / v_grad
-  F_WRITE_PHI = 256,  // write phi (and Adam moments if given) back after F_UNROLL
-  F_EVAL = 512        // predictive kernels: forward only, lean shared-memory carve-up
-};
-
-struct EP {
-  int L;
-  int dims[MAXL + 1];
-  int S, M, B, Btot;
-  int G, RC, slice;
-  float Nf;
-  int vmode;
-  float alpha;
-  int flags;
-  int T, step0;
-  float lr;
-  int adam_mode;
-  float kappa;
-  int noise_mode;
-  unsigned long long seed;
-  unsigned domain;
-  float* mu;
-  float* rho;
-  float* adam_m;
-  float* adam_v;
-  const float* u;
-  const int* z;
-  const float* v;
-  const float* roww;
-  const float* xb;
-  const int* yb;
-  const float* eps;
-  float* traj;
-  float* gout;
-  float* u_grad;
-  float* v_grad;
-  float* alpha_grad;
-  float* loss_out;
-  float* inner_losses;
-  float* g_out;
-  const float* gdot;
-  float* h_phi;
-  // predictive pass
-  int n_rows, batch, first_slab, eval_mode, n_slabs, chunks_per_slab;
-  float* eval_w;     // [n_slabs][S] LOG importance weights (softmax-ed by the consumers)
-  float* eval_part;  // [n_ctas][4] per-CTA partial sums
-  float* eval_out;   // [8]
-  // plain forward
-  float* logits_out; float* theta_out; float* nkl_out; float* kl_out;
-};
 
 // shared-memory carve-up (offsets in floats)
 struct Lay {
@@ -1134,14 +1075,16 @@ int launch_engine(EP& p, int rows_max, cudaStream_t stream) {
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   int smem_max = 0;
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  {  // one-hidden-layer networks with tiny input / output widths have a shape-specialised engine (psvi_mf_fn1.cu)
+    const int rc = psvi_fn1_launch(p, stream);
+    if (rc != FN1_NOT_APPLICABLE) return rc;
+  }
   Meta mt;
   make_meta(p.dims, p.L, mt);
-  // cluster size: fewest CTAs that give every CTA the minimal number of samples, capped at 16 (non-portable max)
-  static int max_cluster = 0;
-  if (max_cluster == 0) {
-    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_engine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    max_cluster = 16;
-  }
+  // cluster size: fewest CTAs that give every CTA the minimal number of samples, capped at 16 (non-portable max);
+  // function attributes are per device, so they are set on every call (cheap) rather than cached per process
+  const int max_cluster = 16;
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_engine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   int G = p.S < max_cluster ? p.S : max_cluster;
   const int per = (p.S + G - 1) / G;
   G = (p.S + per - 1) / per;
