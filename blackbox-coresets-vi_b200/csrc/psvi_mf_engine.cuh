@@ -63,6 +63,7 @@ struct EP {
   float* eval_out;   // [8]
   // plain forward
   float* logits_out; float* theta_out; float* nkl_out; float* kl_out;
+  long long* tl;     // debug timeline (clock64 stamps of rank 0 / thread 0), normally NULL
 };
 
 

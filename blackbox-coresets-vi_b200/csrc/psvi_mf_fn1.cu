@@ -3,8 +3,7 @@
 //
 // Same contract, phases and arithmetic as the generic engine (psvi_mf_engine.cu; reference psvi/inference/
 // psvi_classes.py:445-600, psvi/robust_higher/optim.py:299-367; math: SURVEY.md Appendix A.1-A.6) -- what changes is
-// how the per-sample network pass maps onto an SM.  The generic engine runs every matrix product as a separate
-// shared-memory GEMM stage with run-time strides (15 instructions per FMA, ~12 block barriers per phase).  Here
+// how the work maps onto the cluster (one CTA per MC sample) and onto an SM:
 //   * (D, C, hidden units per lane) are template parameters: every product loop is fully unrolled;
 //   * a warp owns two rows at a time; its 32 lanes are 2 row lanes x 16 hidden lanes, a hidden lane owns UPL hidden
 //     units (H <= 16 UPL) whose weights it reads as 128-bit words of a conflict-free record layout;
@@ -13,10 +12,14 @@
 //     shuffle steps over the 16 hidden lanes; the per-sample weight adjoints  W1bar = abar^T X,  W2bar = obar^T h
 //     (and their A.6 counterparts) accumulate in REGISTERS across all rows of the pass and are combined across the
 //     two row lanes (one shuffle) and the eight warps (one shared-memory sweep) once per pass;
-//   * one pass costs two block barriers; a phase (all samples of the CTA + exchange) two cluster barriers, the first
-//     split into arrive / wait with the next phase's Philox normals generated in its shadow.
-// Exchange between the CTAs of the cluster (one per MC sample) is the generic engine's: slice owners receive the
-// partial sums through DSMEM, reduce in a fixed order (deterministic), update, and push the new parameters back.
+//   * the variational parameter vector is cut into G slices; CTA k OWNS slice k: phi, the Adam moments, the
+//     reverse-sweep carries AND the noise eps_s of its slice for EVERY sample s live only there.  The owner therefore
+//     also does the sampling: after its update it pushes theta_s = mu + sigma eps_s (and the tangent) of its slice
+//     straight into the weight records of the CTA that runs sample s (st.shared::cluster).  A sample CTA is left
+//     with: row pass -> sum the 8 warps' partial adjoints -> push ONE vector (theta_bar_s; two for the dual pass)
+//     to the owners, who form  sum_s theta_bar_s  and  sum_s theta_bar_s eps_s  in a fixed order (deterministic).
+//     Two cluster barriers per inner step / reverse step; Philox normals and trajectory rows for the next step are
+//     produced by otherwise idle warps while the row pass runs.
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -33,14 +36,18 @@ constexpr int NW = NT / 32;    // warps per CTA
 
 // shared-memory carve-up (offsets in floats)
 struct FL {
-  int rec, part;                                             // (HP+1) records ; NW x (HP+1) records of partial adjoints
-  int mu, rho, sig, sgm, eps, gdm, gdr, accA, accB, accC;    // Pt each (TL order)
-  int q2r;                                                   // Pt ints: TL index -> float offset inside `rec`
-  int recv, ost;                                             // [G][3][slice], [10][slice]
-  int X, Y, cw;                                              // rows: [R][D], [R] ints, [R]
-  int a, f, ubar, abar;                                      // coreset: [M], [M], [M][D], [M]
-  int lw, e, dsv, w, beta, gp;                               // per-sample scalars (lw, e: doubles)
-  int red, lossrecv, psc;                                    // 64, G, NW*2
+  int rec, part;                                 // [nper][(HP+1) records] ; NW x (HP+1) records of partial adjoints
+  int q2r, pdst;                                 // Pt ints: TL index -> float offset inside a record block; Pt uint32:
+                                                 // shared::cluster address of recv[0][0][j] in the owner of q
+  int mu, rho, sig, sgm, gdm, gdr;               // owner state of my slice: slice floats each
+  int ost;                                       // [10][slice]
+  int epsS, recv, trs;                           // [2][S][slice] noise ; [S][2][slice] received partials ; [8][slice]
+  int tab;                                       // [5][T] step-size tables
+  int X, Y, cw;                                  // rows: [R][D], [R] ints, [R]
+  int a, f, ubar, abar;                          // coreset: [M], [M], [M][D], [M]
+  int lw, e, dsv, w, beta, gp;                   // per-sample scalars (lw, e: doubles)
+  int nklp;                                      // [nper][G * NCH] partial sampled-nkl sums
+  int red, lossrecv;
   int total;
 };
 
@@ -50,23 +57,28 @@ __host__ __device__ inline void make_fl(const EP& p, FL& y) {
   const int H = p.dims[1];
   const int Pt = H * (D + 1) + C * (H + 1);
   const int R = p.M + p.B;
+  int spad = 32;
+  while (spad < p.slice) spad <<= 1;
+  const int nper = (p.S + p.G - 1) / p.G, nch = spad / 32;
   int o = 0;
   auto take = [&](int n) {
     int r = o;
     o += (n + 3) & ~3;
     return r;
   };
-  y.rec = take((HP + 1) * REC);
+  y.rec = take(nper * (HP + 1) * REC);
   y.part = take(NW * (HP + 1) * REC);
-  y.mu = take(Pt); y.rho = take(Pt); y.sig = take(Pt); y.sgm = take(Pt); y.eps = take(Pt);
-  y.gdm = take(Pt); y.gdr = take(Pt); y.accA = take(Pt); y.accB = take(Pt); y.accC = take(Pt);
-  y.q2r = take(Pt);
-  y.recv = take(p.G * 3 * p.slice);
+  y.q2r = take(Pt); y.pdst = take(Pt);
+  y.mu = take(p.slice); y.rho = take(p.slice); y.sig = take(p.slice); y.sgm = take(p.slice);
+  y.gdm = take(p.slice); y.gdr = take(p.slice);
   y.ost = take(10 * p.slice);
+  y.epsS = take(2 * p.S * p.slice); y.recv = take(p.S * 2 * p.slice); y.trs = take(8 * p.slice);
+  y.tab = take(5 * (p.T > 0 ? p.T : 1));
   y.X = take(R * D); y.Y = take(R); y.cw = take(R);
   y.a = take(p.M); y.f = take(p.M); y.ubar = take(p.M * D); y.abar = take(p.M);
   y.lw = take(2 * p.S); y.e = take(2 * p.S); y.dsv = take(p.S); y.w = take(p.S); y.beta = take(p.S); y.gp = take(p.S);
-  y.red = take(64); y.lossrecv = take(p.G); y.psc = take(NW * 2);
+  y.nklp = take(nper * p.G * nch);
+  y.red = take(64); y.lossrecv = take(p.G);
   y.total = o;
 }
 
@@ -76,6 +88,16 @@ __device__ __forceinline__ void cl_sync() {
   cl_arrive();
   cl_wait();
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+// shared::cluster address of the same shared-memory location in CTA `r` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, int r) {
+  uint32_t o;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(addr), "r"(r));
+  return o;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 // sum over the 16 hidden lanes of a row lane group (lane bits 0..3); every lane ends with the total
 __device__ __forceinline__ float hl_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -84,11 +106,34 @@ __device__ __forceinline__ float hl_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   return v;
 }
+// sigma = softplus(rho) (F.softplus, threshold 20; neural_net.py:131) and sigmoid(rho) from ONE exponential:
+// y = e^rho, sigmoid = y / (1 + y), softplus = log1p(y) = 2 atanh(z) with z = y / (2 + y) (series to z^11: relative
+// truncation error < 3e-13 for y < 1/4, i.e. sigma < 0.22; log1pf beyond).  Shortens the owner's dependent chain.
+__device__ __forceinline__ void softplus_sigmoid(float r, float& sp, float& sg) {
+  if (r > 20.f) {
+    sp = r;
+    sg = 1.f / (1.f + expf(-r));
+    return;
+  }
+  const float yv = expf(r);
+  sg = yv / (1.f + yv);
+  if (yv < 0.25f) {
+    const float z = yv / (2.f + yv), z2 = z * z;
+    float pl = fmaf(z2, 1.f / 11.f, 1.f / 9.f);
+    pl = fmaf(z2, pl, 1.f / 7.f);
+    pl = fmaf(z2, pl, 1.f / 5.f);
+    pl = fmaf(z2, pl, 1.f / 3.f);
+    pl = fmaf(z2, pl, 1.f);
+    sp = 2.f * z * pl;
+  } else {
+    sp = log1pf(yv);
+  }
+}
 
 template <int D, int C, int UPL>
 struct Fn1 {
   static constexpr int HP = 16 * UPL;
-  static constexpr int PS = (HP + 1) * REC;  // floats of one warp's partial-adjoint block
+  static constexpr int PS = (HP + 1) * REC;  // floats of one record block (one sample's weights / one warp's partials)
   static_assert(D + 1 + C <= 8, "a hidden unit's weights must fit one 8-float record half");
 
   const EP& p;
@@ -96,7 +141,10 @@ struct Fn1 {
   float* sm;
   cg::cluster_group cluster;
   int rank, tid, warp, lane, hl, rl;
-  int H, Pt, n4;
+  int H, Pt, slice, j0, nch, spad_sh;
+  bool own;   // this thread owns TL index q = j0 + tid (load / store phases)
+  int oj, oc; // update phases: thread pair (2 oj, 2 oj + 1) works on TL index j0 + oj, component oc (0 = mu, 1 = rho)
+  bool own2;
 
   __device__ Fn1(const EP& p_, const FL& y_, float* s_) : p(p_), y(y_), sm(s_), cluster(cg::this_cluster()) {
     rank = (int)cluster.block_rank();
@@ -107,68 +155,86 @@ struct Fn1 {
     rl = lane >> 4;
     H = p.dims[1];
     Pt = H * (D + 1) + C * (H + 1);
-    n4 = (Pt + 3) >> 2;
+    slice = p.slice;
+    j0 = rank * slice;
+    spad_sh = 5;
+    while ((1 << spad_sh) < slice) ++spad_sh;   // sampling phase: threads are (sample group, index in padded slice)
+    nch = (1 << spad_sh) >> 5;
+    own = tid < slice && j0 + tid < Pt;
+    oj = tid >> 1;
+    oc = tid & 1;
+    own2 = oj < slice && j0 + oj < Pt;
   }
   __device__ __forceinline__ float* F(int off) const { return sm + off; }
   __device__ __forceinline__ int* I(int off) const { return reinterpret_cast<int*>(sm + off); }
   __device__ __forceinline__ float* remote(int off, int r) { return cluster.map_shared_rank(sm + off, r); }
+  __device__ __forceinline__ float& OST(int row) { return sm[y.ost + row * slice + tid]; }
+  __device__ __forceinline__ float& OS2(int row) { return sm[y.ost + row * slice + oj]; }
 
-  // ---- sigma = softplus(rho), sgm = sigmoid(rho) after phi changed ---------------------------------------------------
-  __device__ void refresh_sigma() {
-    for (int q = tid; q < Pt; q += NT) {
-      const float r = F(y.rho)[q];
-      F(y.sig)[q] = softplus_f(r);
-      F(y.sgm)[q] = sigmoid_f(r);
-    }
-    __syncthreads();
-  }
-
-  // ---- the four standard normals of TL block q4 of (slab, s) ----------------------------------------------------------
-  __device__ __forceinline__ void draw4(int s, int slab, int q4, float e4[4]) const {
-    if (p.noise_mode == PSVI_NOISE_PHILOX) {
-      philox_normal4(p.seed, p.domain, (uint32_t)slab, (uint32_t)s, (uint32_t)q4, e4);
-    } else {
-      const float* src = p.eps + ((size_t)slab * p.S + s) * Pt;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) e4[j] = (4 * q4 + j < Pt) ? __ldg(src + 4 * q4 + j) : 0.f;
+  int tl_n = 0;
+  __device__ __forceinline__ void stamp(int code) {
+    if (p.tl != nullptr && tid == 0 && rank == 0 && tl_n < 4096) {
+      p.tl[2 * tl_n] = code;
+      p.tl[2 * tl_n + 1] = clock64();
+      ++tl_n;
     }
   }
 
-  // ---- theta_s = mu + sigma eps_s (and the tangent) into the unit records; returns this thread's partial of
-  //      sampled_nkl_s (neural_net.py:110-115).  `pre` (nullable): normals of block q4 == tid drawn ahead of time. -----
-  __device__ float sample_theta(int s, int slab, bool tangent, float fold_beta, bool want_nkl, const float* pre) {
-    const int* q2r = I(y.q2r);
-    float* rec = F(y.rec);
-    float nkl = 0.f;
-    for (int q4 = tid; q4 < n4; q4 += NT) {
-      float e4[4];
-      if (pre != nullptr && q4 == tid) {
+  // ---- standard normals of my slice for EVERY sample of noise slab `slab` -> epsS[slab & 1]; done by the LAST threads
+  //      of the CTA (the first warps are the owner threads and carry the longest row loops) ---------------------------
+  __device__ void gen_eps(int slab) {
+    const int nb = slice >> 2;  // Philox blocks per sample (slice is a multiple of 4)
+    const int items = p.S * nb;
+    float* dst = F(y.epsS) + (slab & 1) * p.S * slice;
+    for (int i = NT - 1 - tid; i < items; i += NT) {
+      const int s = i / nb, b = i - s * nb;
+      const int q4 = (j0 >> 2) + b;
+      float e4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (4 * q4 < Pt) {
+        if (p.noise_mode == PSVI_NOISE_PHILOX) {
+          philox_normal4(p.seed, p.domain, (uint32_t)slab, (uint32_t)s, (uint32_t)q4, e4);
+        } else {
+          const float* src = p.eps + ((size_t)slab * p.S + s) * Pt;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) e4[j] = pre[j];
-      } else {
-        draw4(s, slab, q4, e4);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int q = 4 * q4 + j;
-        if (q < Pt) {
-          const float e = e4[j], sg = F(y.sig)[q];
-          const float th = F(y.mu)[q] + sg * e;
-          const int r = q2r[q];
-          F(y.eps)[q] = e;
-          rec[r] = th;
-          if (tangent) rec[r + 8] = F(y.gdm)[q] + F(y.sgm)[q] * F(y.gdr)[q] * e;
-          if (want_nkl) nkl += -0.5f * th * th + 0.5f * e * e + logf(sg);
-          if (fold_beta != 0.f) {  // outer objective: d nkl_s / d theta = -theta, weighted by beta_s (A.2)
-            const float tb = -fold_beta * th;
-            F(y.accA)[q] += tb;
-            F(y.accB)[q] += tb * e;
-          }
+          for (int k = 0; k < 4; ++k) e4[k] = (4 * q4 + k < Pt) ? __ldg(src + 4 * q4 + k) : 0.f;
         }
       }
+      *reinterpret_cast<float4*>(dst + s * slice + 4 * b) = make_float4(e4[0], e4[1], e4[2], e4[3]);
     }
-    __syncthreads();
-    return nkl;
+  }
+
+  // ---- owner: theta_s = mu + sigma eps_s (and the tangent  mudot + sigmoid(rho) rhodot eps_s) of my slice for every
+  //      sample, written into the records of the CTA that runs the sample.  All threads: thread = (sample group, index
+  //      in the padded slice).  want_nkl: also the slice's share of  sampled_nkl_s = sum_i [-theta^2/2 + eps^2/2 +
+  //      log sigma]  (neural_net.py:110-115), one partial per warp. ---------------------------------------------------
+  __device__ void owner_sample(int slab, bool tangent, bool want_nkl) {
+    const int j = tid & ((1 << spad_sh) - 1), sg0 = tid >> spad_sh, nsg = NT >> spad_sh;
+    const bool ok = j < slice && j0 + j < Pt;
+    const float* ep = F(y.epsS) + (slab & 1) * p.S * slice + j;
+    const float mu = ok ? F(y.mu)[j] : 0.f, sg = ok ? F(y.sig)[j] : 1.f;
+    const float md = (ok && tangent) ? F(y.gdm)[j] : 0.f;
+    const float rs = (ok && tangent) ? F(y.sgm)[j] * F(y.gdr)[j] : 0.f;
+    const float lsg = want_nkl ? logf(sg) : 0.f;
+    const uint32_t base = smem_u32(F(y.rec) + (ok ? I(y.q2r)[j0 + j] : 0));
+    const uint32_t nbase = smem_u32(F(y.nklp) + rank * nch + (j >> 5));
+    int cta = sg0 % p.G, li = sg0 / p.G;
+    const int dcta = nsg % p.G, dli = nsg / p.G;
+    for (int s = sg0; s < p.S; s += nsg) {   // (warp-uniform trip count: a warp lies inside one sample group)
+      const float e = ok ? ep[s * slice] : 0.f;
+      const float th = fmaf(sg, e, mu);
+      if (ok) {
+        const uint32_t dst = mapa(base + (uint32_t)(li * PS * 4), cta);
+        st_cluster(dst, th);
+        if (tangent) st_cluster(dst + 32, fmaf(rs, e, md));
+      }
+      if (want_nkl) {
+        float v = ok ? (-0.5f * th * th + 0.5f * e * e + lsg) : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) st_cluster(mapa(nbase + (uint32_t)(li * p.G * nch * 4), cta), v);
+      }
+      cta += dcta; li += dli;
+      if (cta >= p.G) { cta -= p.G; ++li; }
+    }
   }
 
   // ---- one hidden unit's record half as 8 floats ----------------------------------------------------------------------
@@ -186,9 +252,8 @@ struct Fn1 {
   // ---- primal pass over rows [0, R): MODE 0 = values only, 1 = gradient.  Row weights in cw[]; sumA += sum over pseudo
   //      rows of a_m nll, sumD += sum over data rows of nll (held by the hl == 0 lanes).  need_x: input adjoints of the
   //      pseudo rows -> ubar, and abar += gp * nll.  Leaves the per-warp weight adjoints in `part`. ---------------------
-  template <int MODE>
-  __device__ void rows_primal(int R, bool need_x, float gp, float& sumA, float& sumD) {
-    const float* rec = F(y.rec);
+  template <int MODE, bool NLL>
+  __device__ void rows_primal(const float* rec, int R, bool need_x, float gp, float& sumA, float& sumD) {
     const float* X = F(y.X);
     const int* Y = I(y.Y);
     const float* cw = F(y.cw);
@@ -242,22 +307,25 @@ struct Fn1 {
       float mx = o[0];
 #pragma unroll
       for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[c]);
-      float se = 0.f;
+      float se = 0.f, ex[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) se += expf(o[c] - mx);
-      const float lse = mx + logf(se);
-      float oy = o[0];
+      for (int c = 0; c < C; ++c) { ex[c] = expf(o[c] - mx); se += ex[c]; }
+      float nll = 0.f;
+      if (NLL) {   // the value is needed only by the outer objective and by the logged inner losses
+        float oy = o[0];
 #pragma unroll
-      for (int c = 1; c < C; ++c) oy = (yl == c) ? o[c] : oy;
-      const float nll = lse - oy;
-      if (hl == 0 && ok) {
-        if (r < p.M) sumA += av[r] * nll; else sumD += nll;
+        for (int c = 1; c < C; ++c) oy = (yl == c) ? o[c] : oy;
+        nll = mx + logf(se) - oy;
+        if (hl == 0 && ok) {
+          if (r < p.M) sumA += av[r] * nll; else sumD += nll;
+        }
       }
       if (MODE == 1) {
         const float cwr = ok ? cw[r] : 0.f;
+        const float inv = 1.f / se;
         float ob[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) ob[c] = cwr * (expf(o[c] - lse) - (c == yl ? 1.f : 0.f));
+        for (int c = 0; c < C; ++c) ob[c] = cwr * (ex[c] * inv - (c == yl ? 1.f : 0.f));
         float xb[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) xb[d] = 0.f;
@@ -317,8 +385,7 @@ struct Fn1 {
 
   // ---- dual (forward-over-reverse) pass over the M pseudo rows, A.6: leaves A_theta in the first and A_thetadot in the
   //      second half of the `part` records; ubar += A_X, abar += A_c. ---------------------------------------------------
-  __device__ void rows_dual() {
-    const float* rec = F(y.rec);
+  __device__ void rows_dual(const float* rec) {
     const float* X = F(y.X);
     const int* Y = I(y.Y);
     const float* cw = F(y.cw);
@@ -368,13 +435,12 @@ struct Fn1 {
       float mx = o[0];
 #pragma unroll
       for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[c]);
-      float se = 0.f;
+      float se = 0.f, pc[C], pd = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) se += expf(o[c] - mx);
-      const float lse = mx + logf(se);
-      float pc[C], pd = 0.f;
+      for (int c = 0; c < C; ++c) { pc[c] = expf(o[c] - mx); se += pc[c]; }
+      const float inv = 1.f / se;
 #pragma unroll
-      for (int c = 0; c < C; ++c) { pc[c] = expf(o[c] - lse); pd = fmaf(pc[c], od[c], pd); }
+      for (int c = 0; c < C; ++c) { pc[c] *= inv; pd = fmaf(pc[c], od[c], pd); }
       float Aod[C], Ao[C], ac = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -444,53 +510,54 @@ struct Fn1 {
     }
   }
 
-  // ---- fold the eight warps' partial adjoints of the sample just processed into the CTA accumulators ------------------
-  __device__ void fold_part(bool dual) {
+  // ---- sum the eight warps' partial adjoints of sample s and push them to the slice owners ---------------------------
+  __device__ void fold_push(int s, int ncomp) {
     const int* q2r = I(y.q2r);
+    const uint32_t* pdst = reinterpret_cast<const uint32_t*>(sm + y.pdst);
     const float* part = F(y.part);
+    const uint32_t soff = (uint32_t)(s * 2 * slice * 4);
     for (int q = tid; q < Pt; q += NT) {
       const int r = q2r[q];
-      float s = 0.f;
+      float v[NW];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += part[w * PS + r];
-      const float e = F(y.eps)[q];
-      F(y.accA)[q] += s;
-      F(y.accB)[q] += s * e;
-      if (dual) {
-        float sd = 0.f;
+      for (int w = 0; w < NW; ++w) v[w] = part[w * PS + r];
+      float s0 = v[0];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) sd += part[w * PS + r + 8];
-        F(y.accC)[q] += sd * e;
+      for (int w = 1; w < NW; ++w) s0 += v[w];
+      const uint32_t dst = pdst[q] + soff;
+      st_cluster(dst, s0);
+      if (ncomp > 1) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v[w] = part[w * PS + r + 8];
+        float s1 = v[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) s1 += v[w];
+        st_cluster(dst + (uint32_t)(slice * 4), s1);
       }
     }
-    // (same q <-> thread mapping as push_acc: no barrier needed before it; `part` / `eps` are rewritten only after the
-    //  block barrier at the end of the next sample_theta)
   }
 
-  // ---- push this CTA's accumulators to the slice owners, then clear them ----------------------------------------------
-  __device__ void push_acc(int ncomp) {
-    const int slice = p.slice;
-    for (int q = tid; q < Pt; q += NT) {
-      const int owner = q / slice, j = q - owner * slice;
-      float* r = remote(y.recv, owner) + (size_t)rank * 3 * slice + j;
-      r[0] = F(y.accA)[q];
-      r[slice] = F(y.accB)[q];
-      F(y.accA)[q] = 0.f;
-      F(y.accB)[q] = 0.f;
-      if (ncomp > 2) {
-        r[2 * slice] = F(y.accC)[q];
-        F(y.accC)[q] = 0.f;
-      }
+  // ---- owner: sums over the samples of the received partials of TL index j, in a fixed order (deterministic):
+  //      plain sum of component `comp`, or the sum weighted by my eps_s ----------------------------------------------
+  __device__ __forceinline__ float recv_sum(int j, int comp) const {
+    const float* r = sm + y.recv + comp * slice + j;
+    float a0 = 0.f, a1 = 0.f;
+    int s = 0;
+    for (; s + 1 < p.S; s += 2) { a0 += r[(2 * s) * slice]; a1 += r[(2 * s + 2) * slice]; }
+    if (s < p.S) a0 += r[(2 * s) * slice];
+    return a0 + a1;
+  }
+  __device__ __forceinline__ float recv_sum_eps(int j, int comp, int slab) const {
+    const float* r = sm + y.recv + comp * slice + j;
+    const float* ep = sm + y.epsS + (slab & 1) * p.S * slice + j;
+    float a0 = 0.f, a1 = 0.f;
+    int s = 0;
+    for (; s + 1 < p.S; s += 2) {
+      a0 = fmaf(r[(2 * s) * slice], ep[s * slice], a0);
+      a1 = fmaf(r[(2 * s + 2) * slice], ep[(s + 1) * slice], a1);
     }
-  }
-  __device__ __forceinline__ float recv_sum(int comp, int j) const {
-    float s = 0.f;
-    const float* r = sm + y.recv + comp * p.slice + j;
-    for (int c = 0; c < p.G; ++c) s += r[(size_t)c * 3 * p.slice];
-    return s;
-  }
-  __device__ __forceinline__ void bcast(int off, int q, float val) {
-    for (int c = 0; c < p.G; ++c) remote(off, c)[q] = val;
+    if (s < p.S) a0 = fmaf(r[(2 * s) * slice], ep[s * slice], a0);
+    return a0 + a1;
   }
 
   // ---- coreset weights a = N f(v)  (psvi_classes.py:476,505; f per class :111,:1358,:1486) ----------------------------
@@ -522,11 +589,14 @@ struct Fn1 {
     __syncthreads();
   }
 
+
   __device__ void init() {
     for (int i = tid; i < y.total; i += NT) sm[i] = 0.f;
     __syncthreads();
     int* q2r = I(y.q2r);
+    uint32_t* pdst = reinterpret_cast<uint32_t*>(sm + y.pdst);
     const int HD = H * D;
+    const uint32_t recv0 = smem_u32(F(y.recv));
     for (int q = tid; q < Pt; q += NT) {
       int r;
       if (q < HD) {
@@ -541,27 +611,124 @@ struct Fn1 {
         r = HP * REC + (q - HD - H - C * H);
       }
       q2r[q] = r;
-      F(y.mu)[q] = p.mu[q];
-      F(y.rho)[q] = p.rho[q];
+      const int owner = q / slice;
+      pdst[q] = mapa(recv0 + (uint32_t)((q - owner * slice) * 4), owner);
+    }
+    if (own) {
+      const float r = p.rho[j0 + tid];
+      F(y.mu)[tid] = p.mu[j0 + tid];
+      F(y.rho)[tid] = r;
+      softplus_sigmoid(r, F(y.sig)[tid], F(y.sgm)[tid]);
     }
     for (int i = tid; i < p.M * D; i += NT) F(y.X)[i] = __ldg(p.u + i);
     for (int m = tid; m < p.M; m += NT) I(y.Y)[m] = __ldg(p.z + m);
     for (int i = tid; i < p.B * D; i += NT) F(y.X)[p.M * D + i] = __ldg(p.xb + i);
     for (int b = tid; b < p.B; b += NT) I(y.Y)[p.M + b] = __ldg(p.yb + b);
+    // step-size tables.  forward (rows 0..2): the reference's running products beta^t in double, as the generic engine
+    // forms them; reverse (rows 3, 4): lr / (1 - beta1^(t+1)) and sqrt(1 - beta2^(t+1)) from pow().
+    {
+      const double B1 = 0.9, B2 = 0.999;
+      float* tab = F(y.tab);
+      for (int t = tid; t < p.T; t += NT) {
+        double a = pow(B1, (double)p.step0), b = pow(B2, (double)p.step0);
+        for (int i = 0; i <= t; ++i) { a *= B1; b *= B2; }
+        tab[t] = (float)(1.0 - a);
+        tab[p.T + t] = (float)sqrt(1.0 - b);
+        tab[2 * p.T + t] = (float)(1.0 - b);
+        const double b1t = pow(B1, (double)(t + 1)), b2t = pow(B2, (double)(t + 1));
+        tab[3 * p.T + t] = p.lr / (float)(1.0 - b1t);
+        tab[4 * p.T + t] = (float)sqrt(1.0 - b2t);
+      }
+    }
     __syncthreads();
-    refresh_sigma();
     if (p.M > 0) setup_coreset();
+    for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];   // inner passes weight the rows by a_m
+    if (p.adam_m && (p.flags & F_UNROLL) && own) {
+      const int q = j0 + tid;
+      OST(6) = p.adam_m[q];
+      OST(7) = p.adam_m[Pt + q];
+      OST(8) = p.adam_v[q];
+      OST(9) = p.adam_v[Pt + q];
+    }
+    __syncthreads();
+    cl_sync();  // every CTA's shared memory is initialised before anybody pushes into it
   }
 
-  // ---- one gradient / dual pass of the inner objective for sample s; returns (on every thread) nothing; the weighted
-  //      NLL sum of the sample is left in this thread's `sumA` partial (hl == 0 lanes) --------------------------------
-  __device__ void inner_pass(int s, int slab, bool dual, const float* pre, float& sumA) {
-    sample_theta(s, slab, dual, 0.f, false, pre);
-    float sumD = 0.f;
-    if (dual) rows_dual(); else rows_primal<1>(p.M, false, 0.f, sumA, sumD);
-    __syncthreads();
-    fold_part(dual);
-    if (s + p.G < p.S) __syncthreads();   // more samples on this CTA: eps / rec are rewritten by other threads
+  // ---- owner: Adam VJP of step t (A.4) for component oc of TL index oj, from a trajectory row (phi, g, m, v of both
+  //      components at stride `stride`) -> direction gbar; makes phi_t the current parameters of my slice ---------------
+  __device__ void owner_vjp(int t, const float* tr, int stride) {
+    if (!own2) return;
+    const float b1 = 0.9f, b2 = 0.999f, omb1 = (float)(1.0 - 0.9), omb2 = (float)(1.0 - 0.999), aeps = 1e-8f;
+    const float k = F(y.tab)[3 * p.T + t], sq2 = F(y.tab)[4 * p.T + t];
+    const int c = oc;
+    const float g = tr[(2 + c) * stride], m = tr[(4 + c) * stride], v = tr[(6 + c) * stride];
+    const float pb = OS2(0 + c);
+    const float qd = sqrtf(v + 1e-8f);
+    const float den = qd / sq2 + aeps;
+    const float mbar = OS2(2 + c) - k * pb / den;
+    const float denbar = k * pb * m / (den * den);
+    float vbar = OS2(4 + c) + denbar / (2.f * qd * sq2);
+    if (v == 0.f) vbar = 0.f;  // _maybe_mask hook (optim.py:40-52,346-347)
+    const float gb = omb1 * mbar + 2.f * omb2 * g * vbar;
+    OS2(2 + c) = b1 * mbar;
+    OS2(4 + c) = b2 * vbar;
+    const float ph = tr[c * stride];
+    if (c == 0) {
+      F(y.gdm)[oj] = gb;
+      F(y.mu)[oj] = ph;
+    } else {
+      F(y.gdr)[oj] = gb;
+      F(y.rho)[oj] = ph;
+      softplus_sigmoid(ph, F(y.sig)[oj], F(y.sgm)[oj]);
+    }
+  }
+
+  // ---- owner: component oc of (H gbar) at TL index oj from the received dual-pass partials (A.6, last line) -----------
+  __device__ __forceinline__ float owner_hvp(int slab) {
+    if (oc == 0) return recv_sum(oj, 0) + F(y.gdm)[oj];
+    const float Ae = recv_sum_eps(oj, 0, slab), Ade = recv_sum_eps(oj, 1, slab);
+    const float sg = F(y.sig)[oj], sgm = F(y.sgm)[oj], rd = F(y.gdr)[oj];
+    const float isg = 1.f / sg;
+    return sgm * Ae + sgm * (1.f - sgm) * rd * Ade + ((1.f + isg * isg) * sgm * sgm + (sg - isg) * sgm * (1.f - sgm)) * rd;
+  }
+
+  // ---- owner: gradient of component oc of TL index oj after inner step t, Adam arithmetic (three flavours), new
+  //      parameters; trv = (phi, g, m, v) of the component for the trajectory -------------------------------------------
+  __device__ void owner_forward(int t, float trv[4]) {
+    const float b1 = 0.9f, b2 = 0.999f, omb1 = (float)(1.0 - 0.9), omb2 = (float)(1.0 - 0.999), aeps = 1e-8f;
+    if (own2) {
+      const int c = oc;
+      const float sg = F(y.sig)[oj], sgm = F(y.sgm)[oj];
+      const float pv = c == 0 ? F(y.mu)[oj] : F(y.rho)[oj];
+      const float g = c == 0 ? recv_sum(oj, 0) + pv : sgm * (recv_sum_eps(oj, 0, t) + (sg - 1.f / sg));
+      const float bc1 = F(y.tab)[t], sq2 = F(y.tab)[p.T + t], bc2 = F(y.tab)[2 * p.T + t];
+      const float step_size = p.lr / bc1;
+      float m = OS2(6 + c) * b1 + omb1 * g;
+      float v = OS2(8 + c) * b2 + omb2 * g * g;
+      float den, np;
+      if (p.adam_mode == PSVI_ADAM_ROBUST_HIGHER) {
+        den = sqrtf(v + 1e-8f) / sq2 + aeps;                     // optim.py:346-363
+        np = pv - step_size * (m / den);
+      } else if (p.adam_mode == PSVI_ADAM_TORCH) {
+        den = sqrtf(v) / sq2 + aeps;
+        np = pv - step_size * (m / den);
+      } else {                                                    // hypergrad/diff_optimizers.py:184-213
+        v += 1e-12f;
+        den = sqrtf(v / bc2) + aeps;
+        np = pv - p.lr * (m / bc1 / den);
+      }
+      trv[0] = pv; trv[1] = g; trv[2] = m; trv[3] = v;
+      if (!(p.flags & F_NOUPDATE)) {
+        OS2(6 + c) = m;
+        OS2(8 + c) = v;
+        if (c == 0) {
+          F(y.mu)[oj] = np;
+        } else {
+          F(y.rho)[oj] = np;
+          softplus_sigmoid(np, F(y.sig)[oj], F(y.sgm)[oj]);
+        }
+      }
+    }
   }
 
   __device__ void run();
@@ -569,129 +736,82 @@ struct Fn1 {
 
 template <int D, int C, int UPL>
 __device__ void Fn1<D, C, UPL>::run() {
-  const int slice = p.slice, G = p.G;
-  const int j0 = rank * slice;  // first TL index of my slice
-  float* ost = F(y.ost);
-  // owner state rows: 0 pbar_mu 1 pbar_rho 2 mbar_mu 3 mbar_rho 4 vbar_mu 5 vbar_rho 6 am_mu 7 am_rho 8 av_mu 9 av_rho
-  auto OST = [&](int row, int j) -> float& { return ost[row * slice + j]; };
+  const int G = p.G, S = p.S;
+  const int q = j0 + tid;   // my TL index as an owner thread (valid iff own)
   init();
-  // inner passes weight the rows by a_m
-  for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];
-  if (p.adam_m && (p.flags & F_UNROLL)) {
-    for (int j = tid; j < slice; j += NT) {
-      const int q = j0 + j;
-      if (q < Pt) {
-        OST(6, j) = p.adam_m[q];
-        OST(7, j) = p.adam_m[Pt + q];
-        OST(8, j) = p.adam_v[q];
-        OST(9, j) = p.adam_v[Pt + q];
-      }
-    }
-  }
-  __syncthreads();
-  cl_sync();  // every CTA's shared memory is initialised before anybody pushes into it
 
-  const double B1 = 0.9, B2 = 0.999;
-  const float b1 = (float)B1, b2 = (float)B2, omb1 = (float)(1.0 - B1), omb2 = (float)(1.0 - B2), aeps = 1e-8f;
+  const float b1 = 0.9f, b2 = 0.999f, omb1 = (float)(1.0 - 0.9), omb2 = (float)(1.0 - 0.999), aeps = 1e-8f;
   const bool want_loss = p.inner_losses != nullptr;
-  const bool can_pre = n4 <= NT;   // one Philox block per thread can be drawn ahead of time
-  float pre[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* rec0 = F(y.rec);
 
   // =================================================================================================================
   // Phase U: T inner Adam steps  (psvi_classes.py:549-555 ; optim.py:224-229,303-367)
   // =================================================================================================================
-  if (p.flags & F_UNROLL) {
-    double b1t = pow(B1, (double)p.step0), b2t = pow(B2, (double)p.step0);
-    if (can_pre && tid < n4) draw4(rank, 0, tid, pre);
+  if ((p.flags & F_UNROLL) && p.T > 0) {
+    gen_eps(0);
+    __syncthreads();
+    owner_sample(0, false, false);
+    cl_sync();
     for (int t = 0; t < p.T; ++t) {
-      float lpart = 0.f;
-      for (int s = rank; s < p.S; s += G) inner_pass(s, t, false, (can_pre && s == rank) ? pre : nullptr, lpart);
-      push_acc(2);
+      const bool follow = !(p.flags & F_NOUPDATE) && (t + 1 < p.T || (p.flags & F_OUTER));
+      stamp(1);
+      if (follow) gen_eps(t + 1);
+      float lpart = 0.f, dsum = 0.f;
+      int li = 0;
+      for (int s = rank; s < S; s += G, ++li) {
+        if (want_loss) rows_primal<1, true>(rec0 + li * PS, p.M, false, 0.f, lpart, dsum);
+        else rows_primal<1, false>(rec0 + li * PS, p.M, false, 0.f, lpart, dsum);
+        __syncthreads();
+        fold_push(s, 1);
+        if (s + G < S) __syncthreads();
+      }
+      stamp(2);
       if (want_loss) {
         // KL(q||p) of my slice at phi_t (neural_net.py:101-108), added once (Q1)
-        for (int j = tid; j < slice; j += NT) {
-          const int q = j0 + j;
-          if (q < Pt) {
-            const float sg = F(y.sig)[q], m = F(y.mu)[q];
-            lpart += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
-          }
+        if (own) {
+          const float sg = F(y.sig)[tid], m = F(y.mu)[tid];
+          lpart += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
         }
         lpart = block_sum(lpart, F(y.red));
         if (tid == 0) remote(y.lossrecv, 0)[rank] = lpart;
       }
-      cl_arrive();
-      if (can_pre && tid < n4 && t + 1 < p.T) draw4(rank, t + 1, tid, pre);   // in the shadow of the barrier
-      cl_wait();
-      if (want_loss && rank == 0 && tid == 0) {
-        float s = 0.f;
-        for (int c = 0; c < G; ++c) s += F(y.lossrecv)[c];
-        p.inner_losses[t] = s;
-      }
-      // ---- owner: gradient of my slice, Adam, trajectory, broadcast ----
-      b1t *= B1;
-      b2t *= B2;
-      const float bc1 = (float)(1.0 - b1t);
-      const float sq2 = (float)sqrt(1.0 - b2t);
-      const float bc2 = (float)(1.0 - b2t);
-      const float step_size = p.lr / bc1;
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        const float mu = F(y.mu)[q], rho = F(y.rho)[q], sg = F(y.sig)[q], sgm = F(y.sgm)[q];
-        const float g_mu = recv_sum(0, j) + mu;
-        const float g_rho = sgm * (recv_sum(1, j) + (sg - 1.f / sg));
-        float nm[2], nv[2], np[2];
-        const float gg[2] = {g_mu, g_rho}, pv[2] = {mu, rho};
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float g = gg[c];
-          float m = OST(6 + c, j) * b1 + omb1 * g;
-          float v = OST(8 + c, j) * b2 + omb2 * g * g;
-          float den;
-          if (p.adam_mode == PSVI_ADAM_ROBUST_HIGHER) {
-            den = sqrtf(v + 1e-8f) / sq2 + aeps;                     // optim.py:346-363
-            np[c] = pv[c] - step_size * (m / den);
-          } else if (p.adam_mode == PSVI_ADAM_TORCH) {
-            den = sqrtf(v) / sq2 + aeps;
-            np[c] = pv[c] - step_size * (m / den);
-          } else {                                                    // hypergrad/diff_optimizers.py:184-213
-            v += 1e-12f;
-            den = sqrtf(v / bc2) + aeps;
-            np[c] = pv[c] - p.lr * (m / bc1 / den);
-          }
-          nm[c] = m;
-          nv[c] = v;
-        }
-        if (p.g_out) {
-          p.g_out[q] = g_mu;
-          p.g_out[Pt + q] = g_rho;
-        }
-        if (p.traj) {
-          float* tr = p.traj + (size_t)t * 8 * Pt;
-          tr[q] = mu; tr[Pt + q] = rho;
-          tr[2 * Pt + q] = g_mu; tr[3 * Pt + q] = g_rho;
-          tr[4 * Pt + q] = nm[0]; tr[5 * Pt + q] = nm[1];
-          tr[6 * Pt + q] = nv[0]; tr[7 * Pt + q] = nv[1];
-        }
-        if (!(p.flags & F_NOUPDATE)) {
-          OST(6, j) = nm[0]; OST(7, j) = nm[1]; OST(8, j) = nv[0]; OST(9, j) = nv[1];
-          bcast(y.mu, q, np[0]);
-          bcast(y.rho, q, np[1]);
-        }
-      }
       cl_sync();
-      refresh_sigma();
-    }
-    if (p.flags & F_WRITE_PHI) {
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        p.mu[q] = F(y.mu)[q];
-        p.rho[q] = F(y.rho)[q];
-        if (p.adam_m) {
-          p.adam_m[q] = OST(6, j); p.adam_m[Pt + q] = OST(7, j);
-          p.adam_v[q] = OST(8, j); p.adam_v[Pt + q] = OST(9, j);
+      stamp(3);
+      if (want_loss && rank == 0 && tid == 0) {
+        float sl = 0.f;
+        for (int c = 0; c < G; ++c) sl += F(y.lossrecv)[c];
+        p.inner_losses[t] = sl;
+      }
+      // ---- owner: gradient of component oc of TL index oj, Adam, new parameters; then the next sample ----
+      float trv[4] = {0.f, 0.f, 0.f, 0.f};
+      owner_forward(t, trv);
+      stamp(31);
+      if (follow) {
+        __syncthreads();
+        owner_sample(t + 1, false, t + 1 == p.T);
+      }
+      stamp(4);
+      cl_arrive();
+      stamp(32);
+      if (own2) {   // global stores after the release: nobody in the cluster waits for them
+        const int q2 = j0 + oj;
+        if (p.g_out) p.g_out[oc * Pt + q2] = trv[1];
+        if (p.traj) {
+          float* tr = p.traj + (size_t)t * 8 * Pt + q2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tr[(2 * k + oc) * Pt] = trv[k];
         }
+      }
+      stamp(33);
+      cl_wait();
+      stamp(5);
+    }
+    if ((p.flags & F_WRITE_PHI) && own) {
+      p.mu[q] = F(y.mu)[tid];
+      p.rho[q] = F(y.rho)[tid];
+      if (p.adam_m) {
+        p.adam_m[q] = OST(6); p.adam_m[Pt + q] = OST(7);
+        p.adam_v[q] = OST(8); p.adam_v[Pt + q] = OST(9);
       }
     }
   }
@@ -703,26 +823,34 @@ __device__ void Fn1<D, C, UPL>::run() {
     const int slab = p.T;
     const int R = p.M + p.B;
     const float dscale = p.Nf / (float)p.Btot;
+    if (!((p.flags & F_UNROLL) && p.T > 0)) {   // (otherwise the last inner step has already delivered the sample)
+      gen_eps(slab);
+      __syncthreads();
+      owner_sample(slab, false, true);
+      cl_sync();
+    }
     // O1: per-sample p_s, d_s, nkl_s
-    for (int s = rank; s < p.S; s += G) {
-      float nkl = sample_theta(s, slab, false, 0.f, true, nullptr);
-      float ps = 0.f, ds = 0.f;
-      rows_primal<0>(R, false, 0.f, ps, ds);
-      // the S per-sample sums are O(N) while the importance-weight adjoints depend on their *differences*:
-      // reduce and keep them in double (the fp32 reference loses ~2 digits here at init_sd=1e-6)
-      const double nkl_d = block_sum_d((double)nkl, F(y.red));
-      const double ps_d = block_sum_d((double)ps, F(y.red));
-      const double ds_d = block_sum_d((double)ds, F(y.red)) * (double)dscale;
-      if (tid < G) {
-        reinterpret_cast<double*>(remote(y.lw, tid))[s] = -ps_d + nkl_d;
-        reinterpret_cast<double*>(remote(y.e, tid))[s] = ds_d - (double)p.kappa * ps_d;
-        remote(y.dsv, tid)[s] = (float)ds_d;
+    {
+      int li = 0;
+      for (int s = rank; s < S; s += G, ++li) {
+        float ps = 0.f, ds = 0.f;
+        rows_primal<0, true>(rec0 + li * PS, R, false, 0.f, ps, ds);
+        // the S per-sample sums are O(N) while the importance-weight adjoints depend on their *differences*:
+        // reduce and keep them in double (the fp32 reference loses ~2 digits here at init_sd=1e-6)
+        const double ps_d = block_sum_d((double)ps, F(y.red));
+        const double ds_d = block_sum_d((double)ds, F(y.red)) * (double)dscale;
+        double nkl_d = 0.0;
+        for (int k = 0; k < G * nch; ++k) nkl_d += (double)F(y.nklp)[li * G * nch + k];
+        if (tid < G) {
+          reinterpret_cast<double*>(remote(y.lw, tid))[s] = -ps_d + nkl_d;
+          reinterpret_cast<double*>(remote(y.e, tid))[s] = ds_d - (double)p.kappa * ps_d;
+          remote(y.dsv, tid)[s] = (float)ds_d;
+        }
       }
     }
     cl_sync();
     // O2: importance weights and adjoint seeds (every CTA, redundantly; S is tiny)
     if (tid == 0) {
-      const int S = p.S;
       const double* lw = reinterpret_cast<const double*>(F(y.lw));
       const double* ev = reinterpret_cast<const double*>(F(y.e));
       double mx = -INFINITY;
@@ -767,138 +895,124 @@ __device__ void Fn1<D, C, UPL>::run() {
     __syncthreads();
     const float beta_sum = F(y.red)[60];
     // O3: backward with per-sample row weights
-    for (int s = rank; s < p.S; s += G) {
-      const float beta = F(y.beta)[s], gp = F(y.gp)[s], wd = F(y.w)[s] * dscale;
-      for (int r = tid; r < R; r += NT) F(y.cw)[r] = r < p.M ? gp * F(y.a)[r] : wd;
-      sample_theta(s, slab, false, beta, false, nullptr);   // (ends with a block barrier: cw is visible)
-      float ps = 0.f, ds = 0.f;
-      rows_primal<1>(R, true, gp, ps, ds);
-      __syncthreads();
-      fold_part(false);
-      if (s + G < p.S) __syncthreads();
+    {
+      int li = 0;
+      for (int s = rank; s < S; s += G, ++li) {
+        const float gp = F(y.gp)[s], wd = F(y.w)[s] * dscale;
+        for (int r = tid; r < R; r += NT) F(y.cw)[r] = r < p.M ? gp * F(y.a)[r] : wd;
+        __syncthreads();
+        float ps = 0.f, ds = 0.f;
+        rows_primal<1, true>(rec0 + li * PS, R, true, gp, ps, ds);
+        __syncthreads();
+        fold_push(s, 1);
+        if (s + G < S) __syncthreads();
+      }
     }
-    push_acc(2);
     __syncthreads();
     for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];   // back to the inner row weights
     cl_sync();
-    // O4: owner: dLoss/dphi_T of my slice (no analytic-KL term in the outer objective)
-    for (int j = tid; j < slice; j += NT) {
-      const int q = j0 + j;
-      if (q >= Pt) continue;
-      const float g_mu = recv_sum(0, j);
-      const float g_rho = F(y.sgm)[q] * (recv_sum(1, j) + beta_sum / F(y.sig)[q]);
-      OST(0, j) = g_mu;
-      OST(1, j) = g_rho;
+    // O4: owner: dLoss/dphi_T of my TL index (no analytic-KL term in the outer objective); the sampled-nkl part
+    // d nkl_s / d theta = -theta_s, weighted by beta_s (A.2), is formed here from the owner's own eps_s
+    if (own) {
+      float A = recv_sum(tid, 0), Ae = recv_sum_eps(tid, 0, slab);
+      const float mu = F(y.mu)[tid], sg = F(y.sig)[tid];
+      const float* ep = F(y.epsS) + (slab & 1) * S * slice + tid;
+      for (int s = 0; s < S; ++s) {
+        const float e = ep[s * slice];
+        const float tb = -F(y.beta)[s] * fmaf(sg, e, mu);
+        A += tb;
+        Ae = fmaf(tb, e, Ae);
+      }
+      const float g_mu = A;
+      const float g_rho = F(y.sgm)[tid] * (Ae + beta_sum / sg);
+      OST(0) = g_mu;
+      OST(1) = g_rho;
       if (p.flags & F_STORE_GOUT) {
         p.gout[q] = g_mu;
         p.gout[Pt + q] = g_rho;
       }
     }
-    cl_sync();  // recv may be overwritten by the next phase's pushes only after every owner has read it
   }
 
   // =================================================================================================================
   // Phase H: a single Hessian-vector pass along gdot (building block / hyper trainer)
   // =================================================================================================================
   if (p.flags & F_HVP) {
-    for (int q = tid; q < Pt; q += NT) {
-      F(y.gdm)[q] = __ldg(p.gdot + q);
-      F(y.gdr)[q] = __ldg(p.gdot + Pt + q);
+    if (own) {
+      F(y.gdm)[tid] = __ldg(p.gdot + q);
+      F(y.gdr)[tid] = __ldg(p.gdot + Pt + q);
     }
+    gen_eps(0);
     __syncthreads();
-    float dummy = 0.f;
-    for (int s = rank; s < p.S; s += G) inner_pass(s, 0, true, nullptr, dummy);
-    push_acc(3);
+    owner_sample(0, true, false);
     cl_sync();
-    for (int j = tid; j < slice; j += NT) {
-      const int q = j0 + j;
-      if (q >= Pt) continue;
-      const float sg = F(y.sig)[q], sgm = F(y.sgm)[q], md = F(y.gdm)[q], rd = F(y.gdr)[q];
-      const float isg = 1.f / sg;
-      p.h_phi[q] = recv_sum(0, j) + md;
-      p.h_phi[Pt + q] = sgm * recv_sum(1, j) + sgm * (1.f - sgm) * rd * recv_sum(2, j) +
-                        ((1.f + isg * isg) * sgm * sgm + (sg - isg) * sgm * (1.f - sgm)) * rd;
+    int li = 0;
+    for (int s = rank; s < S; s += G, ++li) {
+      rows_dual(rec0 + li * PS);
+      __syncthreads();
+      fold_push(s, 2);
+      if (s + G < S) __syncthreads();
     }
     cl_sync();
+    if (own2) p.h_phi[oc * Pt + j0 + oj] = owner_hvp(0);
   }
 
   // =================================================================================================================
   // Phase R: reverse sweep through the T Adam steps   (A.4 + A.6; replaces autograd's double backward)
   // =================================================================================================================
-  if (p.flags & F_REVERSE) {
+  if ((p.flags & F_REVERSE) && p.T > 0) {
     if (p.flags & F_LOAD_GOUT) {
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        OST(0, j) = p.gout[q];
-        OST(1, j) = p.gout[Pt + q];
+      if (own) {
+        OST(0) = p.gout[q];
+        OST(1) = p.gout[Pt + q];
       }
       if (rank == 0) {
         const int MD = p.M * D;
         for (int i = tid; i < MD; i += NT) F(y.ubar)[i] = p.gout[2 * Pt + i];
         for (int i = tid; i < p.M; i += NT) F(y.abar)[i] = p.gout[2 * Pt + MD + i];
       }
-      __syncthreads();
     }
-    if (can_pre && tid < n4 && p.T > 0) draw4(rank, p.T - 1, tid, pre);
+    gen_eps(p.T - 1);
+    __syncthreads();   // (OST written with the load mapping above)
+    owner_vjp(p.T - 1, p.traj + (size_t)(p.T - 1) * 8 * Pt + j0 + oj, Pt);
+    __syncthreads();
+    owner_sample(p.T - 1, true, false);
+    cl_sync();
     for (int t = p.T - 1; t >= 0; --t) {
-      const double b1t = pow(B1, (double)(t + 1)), b2t = pow(B2, (double)(t + 1));
-      const float k = p.lr / (float)(1.0 - b1t);
-      const float sq2 = (float)sqrt(1.0 - b2t);
-      const float* tr = p.traj + (size_t)t * 8 * Pt;
-      // ---- owner: Adam VJP of my slice -> direction gbar; broadcast gbar and phi_t ----
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        float gb[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float g = tr[(2 + c) * Pt + q], m = tr[(4 + c) * Pt + q], v = tr[(6 + c) * Pt + q];
-          const float pb = OST(0 + c, j);
-          const float qd = sqrtf(v + 1e-8f);
-          const float den = qd / sq2 + aeps;
-          const float mbar = OST(2 + c, j) - k * pb / den;
-          const float denbar = k * pb * m / (den * den);
-          float vbar = OST(4 + c, j) + denbar / (2.f * qd * sq2);
-          if (v == 0.f) vbar = 0.f;  // _maybe_mask hook (optim.py:40-52,346-347)
-          gb[c] = omb1 * mbar + 2.f * omb2 * g * vbar;
-          OST(2 + c, j) = b1 * mbar;
-          OST(4 + c, j) = b2 * vbar;
+      stamp(21);
+      if (t > 0) {   // next step's noise and trajectory row, staged while the row pass runs
+        gen_eps(t - 1);
+        const float* tr = p.traj + (size_t)(t - 1) * 8 * Pt + j0;
+        for (int i = NT - 1 - tid; i < 8 * slice; i += NT) {
+          const int k = i / slice, j = i - k * slice;
+          F(y.trs)[i] = (j0 + j < Pt) ? tr[(size_t)k * Pt + j] : 0.f;
         }
-        bcast(y.gdm, q, gb[0]);
-        bcast(y.gdr, q, gb[1]);
-        bcast(y.mu, q, tr[q]);
-        bcast(y.rho, q, tr[Pt + q]);
       }
+      int li = 0;
+      for (int s = rank; s < S; s += G, ++li) {
+        rows_dual(rec0 + li * PS);
+        __syncthreads();
+        fold_push(s, 2);
+        if (s + G < S) __syncthreads();
+      }
+      stamp(22);
       cl_sync();
-      refresh_sigma();
-      // ---- every CTA: dual pass over its samples ----
-      float dummy = 0.f;
-      for (int s = rank; s < p.S; s += G) inner_pass(s, t, true, (can_pre && s == rank) ? pre : nullptr, dummy);
-      push_acc(3);
-      cl_arrive();
-      if (can_pre && tid < n4 && t > 0) draw4(rank, t - 1, tid, pre);   // in the shadow of the barrier
-      cl_wait();
-      // ---- owner: phibar_t = phibar_{t+1} + H gbar ----
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        const float sg = F(y.sig)[q], sgm = F(y.sgm)[q], md = F(y.gdm)[q], rd = F(y.gdr)[q];
-        const float isg = 1.f / sg;
-        OST(0, j) += recv_sum(0, j) + md;
-        OST(1, j) += sgm * recv_sum(1, j) + sgm * (1.f - sgm) * rd * recv_sum(2, j) +
-                     ((1.f + isg * isg) * sgm * sgm + (sg - isg) * sgm * (1.f - sgm)) * rd;
+      stamp(23);
+      // ---- owner: phibar_t = phibar_{t+1} + H gbar ; then the Adam VJP of step t-1 and its sample ----
+      if (own2) OS2(oc) += owner_hvp(t);
+      if (t > 0) {
+        owner_vjp(t - 1, F(y.trs) + oj, slice);
+        stamp(25);
+        __syncthreads();
+        owner_sample(t - 1, true, false);
+        stamp(24);
+        cl_sync();
       }
-      // (the next iteration's broadcasts happen before anyone pushes into recv again: the pushes come after the
-      //  cluster barrier that follows the broadcasts)
     }
-    if (p.g_out) {  // dLoss/dphi_0, useful for diagnostics
-      for (int j = tid; j < slice; j += NT) {
-        const int q = j0 + j;
-        if (q >= Pt) continue;
-        p.g_out[q] = OST(0, j);
-        p.g_out[Pt + q] = OST(1, j);
-      }
+    __syncthreads();
+    if (p.g_out && own) {  // dLoss/dphi_0, useful for diagnostics
+      p.g_out[q] = OST(0);
+      p.g_out[Pt + q] = OST(1);
     }
   }
 
@@ -940,12 +1054,12 @@ __device__ void Fn1<D, C, UPL>::run() {
   }
 }
 
+// The shared-memory layout is computed on the host and passed as a second __grid_constant__ parameter: its fields are
+// constant-bank operands of the instructions that use them (a layout struct in shared memory costs a dependent LDS per
+// access).
 template <int D, int C, int UPL>
-__global__ void __launch_bounds__(NT, 1) psvi_mf_fn1_kernel(const __grid_constant__ EP p) {
+__global__ void __launch_bounds__(NT, 1) psvi_mf_fn1_kernel(const __grid_constant__ EP p, const __grid_constant__ FL fl) {
   extern __shared__ __align__(16) float smem_dyn[];
-  __shared__ FL fl;
-  if (threadIdx.x == 0) make_fl<D, C, UPL>(p, fl);
-  __syncthreads();
   Fn1<D, C, UPL> e(p, fl, smem_dyn);
   e.run();
 }
@@ -966,7 +1080,8 @@ int launch_inst(EP& p, cudaStream_t stream) {
   for (;; --G) {
     if (G < 1) return FN1_NOT_APPLICABLE;
     p.G = G;
-    p.slice = (Pt + G - 1) / G;
+    p.slice = (((Pt + G - 1) / G) + 3) & ~3;   // multiple of 4: a Philox block never straddles two owners
+    if (p.slice > NT) return FN1_NOT_APPLICABLE;   // one owner thread per TL index
     p.RC = 0;
     FL fl;
     make_fl<D, C, UPL>(p, fl);
@@ -993,7 +1108,7 @@ int launch_inst(EP& p, cudaStream_t stream) {
       if (G == 1) return FN1_NOT_APPLICABLE;
       continue;
     }
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p, fl);
     if (le != cudaSuccess) {
       (void)cudaGetLastError();
       if (G == 1) {
@@ -1019,7 +1134,11 @@ int launch_dc(EP& p, cudaStream_t stream) {
 
 namespace psvi_mf {
 
+static long long* g_timeline = nullptr;
+extern "C" void psvi_internal_set_timeline(void* ptr) { g_timeline = (long long*)ptr; }
+
 int psvi_fn1_launch(EP& p, cudaStream_t stream) {
+  p.tl = g_timeline;
   if (p.L != 2 || (p.flags & F_EVAL)) return FN1_NOT_APPLICABLE;
   if (p.M < 1) return FN1_NOT_APPLICABLE;
   const char* off = getenv("PSVI_DISABLE_FN1");
