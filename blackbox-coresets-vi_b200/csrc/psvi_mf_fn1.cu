@@ -73,7 +73,7 @@ __host__ __device__ inline void make_fl(const EP& p, FL& y) {
   y.gdm = take(p.slice); y.gdr = take(p.slice);
   y.ost = take(10 * p.slice);
   y.epsS = take(2 * p.S * p.slice); y.recv = take(p.S * 2 * p.slice); y.trs = take(8 * p.slice);
-  y.tab = take(5 * (p.T > 0 ? p.T : 1));
+  y.tab = take(6 * (p.T > 0 ? p.T : 1));
   y.X = take(R * D); y.Y = take(R); y.cw = take(R);
   y.a = take(p.M); y.f = take(p.M); y.ubar = take(p.M * D); y.abar = take(p.M);
   y.lw = take(2 * p.S); y.e = take(2 * p.S); y.dsv = take(p.S); y.w = take(p.S); y.beta = take(p.S); y.gp = take(p.S);
@@ -116,9 +116,9 @@ __device__ __forceinline__ void softplus_sigmoid(float r, float& sp, float& sg) 
     return;
   }
   const float yv = expf(r);
-  sg = yv / (1.f + yv);
+  sg = yv * __frcp_rn(1.f + yv);
   if (yv < 0.25f) {
-    const float z = yv / (2.f + yv), z2 = z * z;
+    const float z = yv * __frcp_rn(2.f + yv), z2 = z * z;
     float pl = fmaf(z2, 1.f / 11.f, 1.f / 9.f);
     pl = fmaf(z2, pl, 1.f / 7.f);
     pl = fmaf(z2, pl, 1.f / 5.f);
@@ -143,7 +143,7 @@ struct Fn1 {
   int rank, tid, warp, lane, hl, rl;
   int H, Pt, slice, j0, nch, spad_sh;
   bool own;   // this thread owns TL index q = j0 + tid (load / store phases)
-  int oj, oc; // update phases: thread pair (2 oj, 2 oj + 1) works on TL index j0 + oj, component oc (0 = mu, 1 = rho)
+  int oj, oc; // update phases: thread (oc, oj) works on TL index j0 + oj, component oc (0 = mu, 1 = rho)
   bool own2;
 
   __device__ Fn1(const EP& p_, const FL& y_, float* s_) : p(p_), y(y_), sm(s_), cluster(cg::this_cluster()) {
@@ -161,9 +161,9 @@ struct Fn1 {
     while ((1 << spad_sh) < slice) ++spad_sh;   // sampling phase: threads are (sample group, index in padded slice)
     nch = (1 << spad_sh) >> 5;
     own = tid < slice && j0 + tid < Pt;
-    oj = tid >> 1;
-    oc = tid & 1;
-    own2 = oj < slice && j0 + oj < Pt;
+    oj = tid & ((1 << spad_sh) - 1);     // the two components sit in different warps: no divergence inside a warp
+    oc = tid >> spad_sh;
+    own2 = oc < 2 && oj < slice && j0 + oj < Pt;
   }
   __device__ __forceinline__ float* F(int off) const { return sm + off; }
   __device__ __forceinline__ int* I(int off) const { return reinterpret_cast<int*>(sm + off); }
@@ -249,11 +249,19 @@ struct Fn1 {
     *reinterpret_cast<float4*>(ptr + 4) = make_float4(t[4], t[5], t[6], t[7]);
   }
 
+  // rows in flight per lane: independent rows are interleaved to hide the shuffle / MUFU / FMA latencies of a row's
+  // serial chain (forward -> logits reduction -> softmax -> backward); bounded by the register file
+  static constexpr int KW = D + 1 + C;
+  static constexpr int RU_P = (UPL * KW <= 35) ? 4 : 2;
+  static constexpr int RU_D = 1;
+  static constexpr bool HOIST_D = (UPL * KW <= 35);   // dual pass: both weight sets stay in registers
+
   // ---- primal pass over rows [0, R): MODE 0 = values only, 1 = gradient.  Row weights in cw[]; sumA += sum over pseudo
-  //      rows of a_m nll, sumD += sum over data rows of nll (held by the hl == 0 lanes).  need_x: input adjoints of the
-  //      pseudo rows -> ubar, and abar += gp * nll.  Leaves the per-warp weight adjoints in `part`. ---------------------
+  //      rows of a_m nll, sumD += sum over data rows of nll (held by the hl == 0 lanes; only if NLL).  need_x: input
+  //      adjoints of the pseudo rows -> ubar, and abar += gp * nll.  Leaves the per-warp weight adjoints in `part`. ----
   template <int MODE, bool NLL>
   __device__ void rows_primal(const float* rec, int R, bool need_x, float gp, float& sumA, float& sumD) {
+    constexpr int RU = RU_P;
     const float* X = F(y.X);
     const int* Y = I(y.Y);
     const float* cw = F(y.cw);
@@ -283,78 +291,104 @@ struct Fn1 {
 #pragma unroll
     for (int c = 0; c < C; ++c) gb2[c] = 0.f;
 
-    for (int rb = 2 * warp; rb < R; rb += 2 * NW) {  // warp-uniform trip count (the shuffles need the full warp)
-      const int r = rb + rl;
-      const bool ok = r < R;
-      float x[D];
+    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW) {  // warp-uniform trip count (the shuffles need the full warp)
+      int r[RU], yl[RU];
+      bool ok[RU];
+      float x[RU][D], h[RU][UPL], o[RU][C];
 #pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = ok ? X[r * D + d] : 0.f;
-      const int yl = ok ? Y[r] : 0;
-      float h[UPL], o[C];
+      for (int u = 0; u < RU; ++u) {
+        r[u] = rb + 2 * u + rl;
+        ok[u] = r[u] < R;
 #pragma unroll
-      for (int c = 0; c < C; ++c) o[c] = 0.f;
+        for (int d = 0; d < D; ++d) x[u][d] = ok[u] ? X[r[u] * D + d] : 0.f;
+        yl[u] = ok[u] ? Y[r[u]] : 0;
 #pragma unroll
-      for (int i = 0; i < UPL; ++i) {
-        float a = b1[i];
-#pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(w1[i][d], x[d], a);
-        h[i] = fmaxf(a, 0.f);
-#pragma unroll
-        for (int c = 0; c < C; ++c) o[c] = fmaf(h[i], w2[i][c], o[c]);
+        for (int c = 0; c < C; ++c) o[u][c] = 0.f;
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) o[c] = hl_sum(o[c]) + b2[c];
-      float mx = o[0];
+      for (int i = 0; i < UPL; ++i) {
 #pragma unroll
-      for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[c]);
-      float se = 0.f, ex[C];
+        for (int u = 0; u < RU; ++u) {
+          float a = b1[i];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { ex[c] = expf(o[c] - mx); se += ex[c]; }
-      float nll = 0.f;
-      if (NLL) {   // the value is needed only by the outer objective and by the logged inner losses
-        float oy = o[0];
+          for (int d = 0; d < D; ++d) a = fmaf(w1[i][d], x[u][d], a);
+          h[u][i] = fmaxf(a, 0.f);
 #pragma unroll
-        for (int c = 1; c < C; ++c) oy = (yl == c) ? o[c] : oy;
-        nll = mx + logf(se) - oy;
-        if (hl == 0 && ok) {
-          if (r < p.M) sumA += av[r] * nll; else sumD += nll;
+          for (int c = 0; c < C; ++c) o[u][c] = fmaf(h[u][i], w2[i][c], o[u][c]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[u][c] = hl_sum(o[u][c]) + b2[c];
+      float nll[RU], ob[RU][C];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        float mx = o[u][0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[u][c]);
+        float se = 0.f, ex[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { ex[c] = expf(o[u][c] - mx); se += ex[c]; }
+        nll[u] = 0.f;
+        if (NLL) {   // the value is needed only by the outer objective and by the logged inner losses
+          float oy = o[u][0];
+#pragma unroll
+          for (int c = 1; c < C; ++c) oy = (yl[u] == c) ? o[u][c] : oy;
+          nll[u] = mx + logf(se) - oy;
+          if (hl == 0 && ok[u]) {
+            if (r[u] < p.M) sumA += av[r[u]] * nll[u]; else sumD += nll[u];
+          }
+        }
+        if (MODE == 1) {
+          const float cwr = ok[u] ? cw[r[u]] : 0.f;
+          const float inv = 1.f / se;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            ob[u][c] = cwr * (ex[c] * inv - (c == yl[u] ? 1.f : 0.f));
+            gb2[c] += ob[u][c];
+          }
         }
       }
       if (MODE == 1) {
-        const float cwr = ok ? cw[r] : 0.f;
-        const float inv = 1.f / se;
-        float ob[C];
+        float xb[RU][D];
 #pragma unroll
-        for (int c = 0; c < C; ++c) ob[c] = cwr * (ex[c] * inv - (c == yl ? 1.f : 0.f));
-        float xb[D];
+        for (int u = 0; u < RU; ++u)
 #pragma unroll
-        for (int d = 0; d < D; ++d) xb[d] = 0.f;
+          for (int d = 0; d < D; ++d) xb[u][d] = 0.f;
 #pragma unroll
         for (int i = 0; i < UPL; ++i) {
-          float t = 0.f;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            gw2[i][c] = fmaf(ob[c], h[i], gw2[i][c]);
-            t = fmaf(ob[c], w2[i][c], t);
-          }
-          const float ab = h[i] > 0.f ? t : 0.f;
+          for (int u = 0; u < RU; ++u) {
+            float t = 0.f;
 #pragma unroll
-          for (int d = 0; d < D; ++d) gw1[i][d] = fmaf(ab, x[d], gw1[i][d]);
-          gb1[i] += ab;
-          if (need_x) {
+            for (int c = 0; c < C; ++c) {
+              gw2[i][c] = fmaf(ob[u][c], h[u][i], gw2[i][c]);
+              t = fmaf(ob[u][c], w2[i][c], t);
+            }
+            const float ab = h[u][i] > 0.f ? t : 0.f;
 #pragma unroll
-            for (int d = 0; d < D; ++d) xb[d] = fmaf(ab, w1[i][d], xb[d]);
+            for (int d = 0; d < D; ++d) gw1[i][d] = fmaf(ab, x[u][d], gw1[i][d]);
+            gb1[i] += ab;
+            if (need_x) {
+#pragma unroll
+              for (int d = 0; d < D; ++d) xb[u][d] = fmaf(ab, w1[i][d], xb[u][d]);
+            }
           }
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) gb2[c] += ob[c];
         if (need_x && rb < p.M) {  // (rb is warp-uniform)
 #pragma unroll
-          for (int d = 0; d < D; ++d) xb[d] = hl_sum(xb[d]);
-          if (hl == 0 && ok && r < p.M) {
+          for (int u = 0; u < RU; ++u)
 #pragma unroll
-            for (int d = 0; d < D; ++d) F(y.ubar)[r * D + d] += xb[d];
-            F(y.abar)[r] += gp * nll;
+            for (int d = 0; d < D; ++d) xb[u][d] = hl_sum(xb[u][d]);
+          if (hl == 0) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+              if (ok[u] && r[u] < p.M) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) F(y.ubar)[r[u] * D + d] += xb[u][d];
+                F(y.abar)[r[u]] += gp * nll[u];
+              }
           }
         }
       }
@@ -386,6 +420,8 @@ struct Fn1 {
   // ---- dual (forward-over-reverse) pass over the M pseudo rows, A.6: leaves A_theta in the first and A_thetadot in the
   //      second half of the `part` records; ubar += A_X, abar += A_c. ---------------------------------------------------
   __device__ void rows_dual(const float* rec) {
+    constexpr int RU = RU_D;
+    constexpr bool HOIST = HOIST_D;
     const float* X = F(y.X);
     const int* Y = I(y.Y);
     const float* cw = F(y.cw);
@@ -402,88 +438,131 @@ struct Fn1 {
 #pragma unroll
     for (int c = 0; c < C; ++c) { b2[c] = rec[HP * REC + c]; b2d[c] = rec[HP * REC + 8 + c]; }
 
-    for (int rb = 2 * warp; rb < R; rb += 2 * NW) {
-      const int r = rb + rl;
-      const bool ok = r < R;
-      float x[D];
+    float wh[HOIST ? UPL : 1][8], wdh[HOIST ? UPL : 1][8];
+    if (HOIST) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = ok ? X[r * D + d] : 0.f;
-      const int yl = ok ? Y[r] : 0;
-      const float cwr = ok ? cw[r] : 0.f;
-      float h[UPL], hd[UPL], o[C], od[C];
+      for (int i = 0; i < UPL; ++i) {
+        load8(rec + (hl + 16 * i) * REC, wh[i]);
+        load8(rec + (hl + 16 * i) * REC + 8, wdh[i]);
+      }
+    }
+
+    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW) {
+      int r[RU], yl[RU];
+      bool ok[RU];
+      float x[RU][D], cwr[RU], h[RU][UPL], hd[RU][UPL], o[RU][C], od[RU][C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { o[c] = 0.f; od[c] = 0.f; }
+      for (int u = 0; u < RU; ++u) {
+        r[u] = rb + 2 * u + rl;
+        ok[u] = r[u] < R;
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[u][d] = ok[u] ? X[r[u] * D + d] : 0.f;
+        yl[u] = ok[u] ? Y[r[u]] : 0;
+        cwr[u] = ok[u] ? cw[r[u]] : 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { o[u][c] = 0.f; od[u][c] = 0.f; }
+      }
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
         float w[8], wd[8];
-        load8(rec + (hl + 16 * i) * REC, w);
-        load8(rec + (hl + 16 * i) * REC + 8, wd);
-        float a = w[D], ad = wd[D];
+        if (HOIST) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) { a = fmaf(w[d], x[d], a); ad = fmaf(wd[d], x[d], ad); }
-        const bool k = a > 0.f;
-        h[i] = k ? a : 0.f;
-        hd[i] = k ? ad : 0.f;
+          for (int k = 0; k < 8; ++k) { w[k] = wh[i][k]; wd[k] = wdh[i][k]; }
+        } else {
+          load8(rec + (hl + 16 * i) * REC, w);
+          load8(rec + (hl + 16 * i) * REC + 8, wd);
+        }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          o[c] = fmaf(h[i], w[D + 1 + c], o[c]);
-          od[c] = fmaf(hd[i], w[D + 1 + c], fmaf(h[i], wd[D + 1 + c], od[c]));
+        for (int u = 0; u < RU; ++u) {
+          float a = w[D], ad = wd[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) { a = fmaf(w[d], x[u][d], a); ad = fmaf(wd[d], x[u][d], ad); }
+          const bool k = a > 0.f;
+          h[u][i] = k ? a : 0.f;
+          hd[u][i] = k ? ad : 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            o[u][c] = fmaf(h[u][i], w[D + 1 + c], o[u][c]);
+            od[u][c] = fmaf(hd[u][i], w[D + 1 + c], fmaf(h[u][i], wd[D + 1 + c], od[u][c]));
+          }
         }
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) { o[c] = hl_sum(o[c]) + b2[c]; od[c] = hl_sum(od[c]) + b2d[c]; }
-      float mx = o[0];
+      for (int u = 0; u < RU; ++u)
 #pragma unroll
-      for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[c]);
-      float se = 0.f, pc[C], pd = 0.f;
+        for (int c = 0; c < C; ++c) { o[u][c] = hl_sum(o[u][c]) + b2[c]; od[u][c] = hl_sum(od[u][c]) + b2d[c]; }
+      float Aod[RU][C], Ao[RU][C], ac[RU];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { pc[c] = expf(o[c] - mx); se += pc[c]; }
-      const float inv = 1.f / se;
+      for (int u = 0; u < RU; ++u) {
+        float mx = o[u][0];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { pc[c] *= inv; pd = fmaf(pc[c], od[c], pd); }
-      float Aod[C], Ao[C], ac = 0.f;
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[u][c]);
+        float se = 0.f, pc[C], pd = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float qc = pc[c] - (c == yl ? 1.f : 0.f);
-        Aod[c] = cwr * qc;                    // adjoint of odot
-        Ao[c] = cwr * pc[c] * (od[c] - pd);   // adjoint of o
-        ac = fmaf(qc, od[c], ac);
-        gb2[c] += Ao[c];
-        gb2d[c] += Aod[c];
+        for (int c = 0; c < C; ++c) { pc[c] = expf(o[u][c] - mx); se += pc[c]; }
+        const float inv = 1.f / se;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { pc[c] *= inv; pd = fmaf(pc[c], od[u][c], pd); }
+        ac[u] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float qc = pc[c] - (c == yl[u] ? 1.f : 0.f);
+          Aod[u][c] = cwr[u] * qc;                       // adjoint of odot
+          Ao[u][c] = cwr[u] * pc[c] * (od[u][c] - pd);   // adjoint of o
+          ac[u] = fmaf(qc, od[u][c], ac[u]);
+          gb2[c] += Ao[u][c];
+          gb2d[c] += Aod[u][c];
+        }
       }
-      float ax[D];
+      float ax[RU][D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) ax[d] = 0.f;
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int d = 0; d < D; ++d) ax[u][d] = 0.f;
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
         float w[8], wd[8];
-        load8(rec + (hl + 16 * i) * REC, w);
-        load8(rec + (hl + 16 * i) * REC + 8, wd);
-        float Ahd = 0.f, Ah = 0.f;
+        if (HOIST) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          Ahd = fmaf(Aod[c], w[D + 1 + c], Ahd);
-          Ah = fmaf(Aod[c], wd[D + 1 + c], fmaf(Ao[c], w[D + 1 + c], Ah));
-          g[i][D + 1 + c] = fmaf(Aod[c], hd[i], fmaf(Ao[c], h[i], g[i][D + 1 + c]));
-          gd[i][D + 1 + c] = fmaf(Aod[c], h[i], gd[i][D + 1 + c]);
+          for (int k = 0; k < 8; ++k) { w[k] = wh[i][k]; wd[k] = wdh[i][k]; }
+        } else {
+          load8(rec + (hl + 16 * i) * REC, w);
+          load8(rec + (hl + 16 * i) * REC + 8, wd);
         }
-        const bool k = h[i] > 0.f;
-        const float Aa = k ? Ah : 0.f, Aad = k ? Ahd : 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          g[i][d] = fmaf(Aa, x[d], g[i][d]);
-          gd[i][d] = fmaf(Aad, x[d], gd[i][d]);
-          ax[d] = fmaf(Aa, w[d], fmaf(Aad, wd[d], ax[d]));
+        for (int u = 0; u < RU; ++u) {
+          float Ahd = 0.f, Ah = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            Ahd = fmaf(Aod[u][c], w[D + 1 + c], Ahd);
+            Ah = fmaf(Aod[u][c], wd[D + 1 + c], fmaf(Ao[u][c], w[D + 1 + c], Ah));
+            g[i][D + 1 + c] = fmaf(Aod[u][c], hd[u][i], fmaf(Ao[u][c], h[u][i], g[i][D + 1 + c]));
+            gd[i][D + 1 + c] = fmaf(Aod[u][c], h[u][i], gd[i][D + 1 + c]);
+          }
+          const bool k = h[u][i] > 0.f;
+          const float Aa = k ? Ah : 0.f, Aad = k ? Ahd : 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            g[i][d] = fmaf(Aa, x[u][d], g[i][d]);
+            gd[i][d] = fmaf(Aad, x[u][d], gd[i][d]);
+            ax[u][d] = fmaf(Aa, w[d], fmaf(Aad, wd[d], ax[u][d]));
+          }
+          g[i][D] += Aa;
+          gd[i][D] += Aad;
         }
-        g[i][D] += Aa;
-        gd[i][D] += Aad;
       }
 #pragma unroll
-      for (int d = 0; d < D; ++d) ax[d] = hl_sum(ax[d]);
-      if (hl == 0 && ok) {
+      for (int u = 0; u < RU; ++u)
 #pragma unroll
-        for (int d = 0; d < D; ++d) F(y.ubar)[r * D + d] += ax[d];
-        F(y.abar)[r] += ac;
+        for (int d = 0; d < D; ++d) ax[u][d] = hl_sum(ax[u][d]);
+      if (hl == 0) {
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+          if (ok[u]) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) F(y.ubar)[r[u] * D + d] += ax[u][d];
+            F(y.abar)[r[u]] += ac[u];
+          }
       }
     }
     float* part = F(y.part) + warp * PS;
@@ -541,23 +620,42 @@ struct Fn1 {
   //      plain sum of component `comp`, or the sum weighted by my eps_s ----------------------------------------------
   __device__ __forceinline__ float recv_sum(int j, int comp) const {
     const float* r = sm + y.recv + comp * slice + j;
-    float a0 = 0.f, a1 = 0.f;
-    int s = 0;
-    for (; s + 1 < p.S; s += 2) { a0 += r[(2 * s) * slice]; a1 += r[(2 * s + 2) * slice]; }
-    if (s < p.S) a0 += r[(2 * s) * slice];
-    return a0 + a1;
+    float tot = 0.f;
+    for (int s0 = 0; s0 < p.S; s0 += 16) {   // 16 independent loads, then a fixed-shape tree
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {   // branch-free: clamped (always in-bounds) load, then select
+        const int sk = min(s0 + k, p.S - 1);
+        const float a = r[(2 * sk) * slice];
+        v[k] = (s0 + k < p.S) ? a : 0.f;
+      }
+#pragma unroll
+      for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) v[k] += v[k + w];
+      tot += v[0];
+    }
+    return tot;
   }
   __device__ __forceinline__ float recv_sum_eps(int j, int comp, int slab) const {
     const float* r = sm + y.recv + comp * slice + j;
     const float* ep = sm + y.epsS + (slab & 1) * p.S * slice + j;
-    float a0 = 0.f, a1 = 0.f;
-    int s = 0;
-    for (; s + 1 < p.S; s += 2) {
-      a0 = fmaf(r[(2 * s) * slice], ep[s * slice], a0);
-      a1 = fmaf(r[(2 * s + 2) * slice], ep[(s + 1) * slice], a1);
+    float tot = 0.f;
+    for (int s0 = 0; s0 < p.S; s0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int sk = min(s0 + k, p.S - 1);
+        const float a = r[(2 * sk) * slice] * ep[sk * slice];
+        v[k] = (s0 + k < p.S) ? a : 0.f;
+      }
+#pragma unroll
+      for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) v[k] += v[k + w];
+      tot += v[0];
     }
-    if (s < p.S) a0 = fmaf(r[(2 * s) * slice], ep[s * slice], a0);
-    return a0 + a1;
+    return tot;
   }
 
   // ---- coreset weights a = N f(v)  (psvi_classes.py:476,505; f per class :111,:1358,:1486) ----------------------------
@@ -633,6 +731,7 @@ struct Fn1 {
         double a = pow(B1, (double)p.step0), b = pow(B2, (double)p.step0);
         for (int i = 0; i <= t; ++i) { a *= B1; b *= B2; }
         tab[t] = (float)(1.0 - a);
+        tab[5 * p.T + t] = p.lr / (float)(1.0 - a);
         tab[p.T + t] = (float)sqrt(1.0 - b);
         tab[2 * p.T + t] = (float)(1.0 - b);
         const double b1t = pow(B1, (double)(t + 1)), b2t = pow(B2, (double)(t + 1));
@@ -982,10 +1081,21 @@ __device__ void Fn1<D, C, UPL>::run() {
       stamp(21);
       if (t > 0) {   // next step's noise and trajectory row, staged while the row pass runs
         gen_eps(t - 1);
+        // (warps 1..3: warp 0 carries the longest row loop, the last warps draw the noise; loads first, stores after)
         const float* tr = p.traj + (size_t)(t - 1) * 8 * Pt + j0;
-        for (int i = NT - 1 - tid; i < 8 * slice; i += NT) {
-          const int k = i / slice, j = i - k * slice;
-          F(y.trs)[i] = (j0 + j < Pt) ? tr[(size_t)k * Pt + j] : 0.f;
+        if (warp >= 1 && warp <= 3) {
+          for (int i0 = tid - 32; i0 < 8 * slice; i0 += 4 * 96) {
+            float v[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int i = i0 + k4 * 96;
+              const int k = i / slice, j = i - k * slice;
+              v[k4] = (i < 8 * slice && j0 + j < Pt) ? __ldcg(tr + (size_t)k * Pt + j) : 0.f;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              if (i0 + k4 * 96 < 8 * slice) F(y.trs)[i0 + k4 * 96] = v[k4];
+          }
         }
       }
       int li = 0;
@@ -1081,7 +1191,7 @@ int launch_inst(EP& p, cudaStream_t stream) {
     if (G < 1) return FN1_NOT_APPLICABLE;
     p.G = G;
     p.slice = (((Pt + G - 1) / G) + 3) & ~3;   // multiple of 4: a Philox block never straddles two owners
-    if (p.slice > NT) return FN1_NOT_APPLICABLE;   // one owner thread per TL index
+    if (p.slice > NT / 2) return FN1_NOT_APPLICABLE;   // two owner threads (mu, rho) per TL index
     p.RC = 0;
     FL fl;
     make_fl<D, C, UPL>(p, fl);

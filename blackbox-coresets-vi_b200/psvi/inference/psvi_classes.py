@@ -94,7 +94,10 @@ class PSVI(object):
         scoring_run=False, noise_source=None, **kwargs,
     ):
         np.random.seed(seed), torch.manual_seed(seed)
-        self.device = torch.device(f"cuda:{device_id}" if device_id else ("cuda" if torch.cuda.is_available() else "cpu"))
+        if not torch.cuda.is_available():
+            raise _native.NativeError("PSVI on this package runs on CUDA only (libpsvi_b200, sm_100a): no CUDA device is "
+                                      "visible; there is no CPU fallback")
+        self.device = torch.device(f"cuda:{device_id}" if device_id else "cuda")
         self.u, self.z = u, z
         self.train_dataset, self.test_dataset = train_dataset, test_dataset
         self.N, self.D, self.dnm, self.nc = N, D, dnm, nc
@@ -258,7 +261,12 @@ class PSVI(object):
         return t
 
     def _z32(self):
-        return self.z.detach().to(torch.int32).contiguous()
+        """Labels of the pseudo-data as int32 (what the kernels read); converted once per label tensor, not per step."""
+        c = self._ws.get("z32")
+        if c is None or c[0] is not self.z or c[1] != self.z._version:
+            c = (self.z, self.z._version, self.z.detach().to(torch.int32).contiguous())
+            self._ws["z32"] = c
+        return c[2]
 
     def _alpha_value(self):
         return float(self.alpha.item()) if self.alpha is not None else 0.0
@@ -394,15 +402,23 @@ class PSVI(object):
         lr = float(self.optim_net.param_groups[0]["lr"])
         traj = self._buf("traj", _native.traj_floats(desc, T))
         gout = self._buf("gout", _native.gout_floats(desc, M))
-        ug, vg = torch.zeros(M, D, device=self.device), torch.zeros(M, device=self.device)
-        ag, loss = torch.zeros(1, device=self.device), torch.zeros(1, device=self.device)
+        # outputs the kernel overwrites completely: fresh (uninitialised) storage per step, because u.grad / v.grad keep
+        # referring to it; one allocation instead of four zero-fills
+        obuf = torch.empty(M * D + M + 2, device=self.device)
+        ug, vg = obuf[:M * D].view(M, D), obuf[M * D:M * D + M]
+        ag, loss = obuf[M * D + M:M * D + M + 1], obuf[M * D + M + 1:]
+        if self._vmode != _native.VMODE_EXPALPHA_SOFTMAX:
+            ag = None
         il = self._buf("il", T) if self.register_elbos else None
         xb = xbatch.detach().to(self.device, torch.float32)
-        yb = ybatch.detach().to(self.device).to(torch.int32)
+        yb = ybatch.detach().to(self.device)
+        if yb.dtype != torch.int32:
+            yb = yb.to(torch.int32)
         dist, rank, world = _dist_info()
         n_total = xb.shape[0]
         noise = self._noise(T + 1)
-        args = lambda xs, ys, kappa: (desc, noise, mu, rho, u, self._z32(), v, xs, ys, n_total, float(self.N),  # noqa: E731
+        z32 = self._z32()
+        args = lambda xs, ys, kappa: (desc, noise, mu, rho, u, z32, v, xs, ys, n_total, float(self.N),  # noqa: E731
                                       self._vmode, self._alpha_value(), T, lr, kappa)
         if world == 1:
             _native.nested_step(*args(xb.contiguous(), yb.contiguous(), 1.0),
@@ -424,7 +440,7 @@ class PSVI(object):
         self.u.grad = ug.to(self.u.dtype)
         if self.learn_v:
             self.v.grad = vg.to(self.v.dtype)
-        if self.alpha is not None and self.alpha.requires_grad:
+        if self.alpha is not None and self.alpha.requires_grad and ag is not None:
             self.alpha.grad = ag.to(self.alpha.dtype)
         self._step_outer_optimisers()
         if self.scheduler_optim_net:
