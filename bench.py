@@ -2,7 +2,7 @@
 """bench.py -- PSVI hot-path benchmark on B200 (contract: see the task description; metric from BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched by torchrun, one rank per GPU)
-    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference path
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference (baseline/_ref) on the host CPU
 
 Workload (BASELINE.json configs[1], "cfg2" in SURVEY.md section 8): halfmoon-shaped data (N=800, D=2, C=2),
 `fn` BNN with one hidden layer of 100 units, psvi_learn_v, coreset M=50, S=10 MC samples, T=100 unrolled inner Adam
@@ -10,13 +10,17 @@ steps, minibatch B=128.  One STEP = one PSVI outer step = PSVILearnV.nested_step
 hypergradient on (u, v) + the Adam updates of u and v.
 
   value : outer steps/s with the minibatch already resident in HBM (device-timed, CUDA events per step, L2 flushed
-          between steps)
-  e2e   : outer steps/s through the public API with HOST (pinned) minibatches: H2D copy of x/y and D2H read of the
-          loss inside the timed region
+          between steps); for N > 1: N * K / (max over ranks of the summed step times) -- one all-reduce(MAX)
+  e2e   : outer steps/s through the public API with HOST (pinned) minibatches: H2D copy of x/y and D2H copy of every
+          step's loss inside the timed region
   N > 1 : one independent PSVI chain (trial) per GPU -- the reference's own multi-GPU mode
-          (flow-psvi-parallel.py:455-479) -- so `value` is the sum over ranks ("weak" scaling, no data-path
-          collective); the sharded full-data pass (the part of the path that does shard, one all-reduce) is measured
-          separately and reported under "sharded".
+          (flow-psvi-parallel.py:455-479): cfg2's data term is 128 rows, so this path is "replicas only" (DESIGN.md 6).
+          The part of the hot path that DOES shard -- the full-data pass at BASELINE configs[4] ("cfg5": 10 M rows x 256,
+          fn H=1024, S=64) -- is timed as a STRONG-scaling run (fixed 10 M rows split over the ranks, one all-reduce)
+          and reported in the first-class field `sharded_fulldata`.
+  --impl reference : the reference's own PSVILearnV.nested_step (pip-installed into baseline/_ref, unmodified) on the host
+          CPU with all cores; also, when a GPU is visible, the same unmodified class eagerly on cuda:0
+          (`extra.eager_b200`, SURVEY.md section 8d "the real on-box comparator").
 """
 from __future__ import annotations
 
@@ -35,6 +39,14 @@ sys.path.insert(0, os.path.join(ROOT, "blackbox-coresets-vi_b200"))
 CFG = dict(workload="cfg2: halfmoon N=800 D=2 C=2, fn H=100 (1 hidden layer), psvi_learn_v, M=50, S=10, T=100, B=128",
            D=2, H=100, C=2, M=50, S=10, T=100, B=128, N=800, init_sd=1e-3)
 METRIC, UNIT = "psvi_outer_steps_per_sec", "outer_steps/s"
+
+
+def make_config(world):
+    """The `config` object -- identical in both arms (`--impl ours` / `--impl reference`) for the same --gpus."""
+    return dict(CFG, parallelism="single chain" if world == 1 else
+                f"{world} independent chains (trials), one per GPU, no data-path collective",
+                l2="GPU arm: flushed between timed steps (256 MiB write); CPU arm: n/a",
+                noise="GPU arm: in-kernel Philox4x32-10; reference arm: torch generator")
 
 
 def flops_outer_step(c):
@@ -184,20 +196,56 @@ def time_cpu(c, steps, warmup):
     return steps / dt, dt / steps
 
 
+def reference_sample(steps, warmup, device="cpu", anomaly=False, budget_s=None):
+    """steps/s of the UNMODIFIED reference's outer step (oracle/ref_runner.py drives baseline/_ref); None if the reference
+    tree is not reachable."""
+    try:
+        from oracle.ref_runner import time_reference
+        return time_reference(CFG, steps, warmup, device=device, anomaly=anomaly, threads=os.cpu_count(), budget_s=budget_s)
+    except ImportError as e:
+        return {"error": repr(e)[:200]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40))
-    warm = max(1, min(args.warmup, 3))
-    sps, sec = time_cpu(CFG, steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(CFG),
-            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{steps} full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single thread); "
-                                       "the reference itself is Python and cannot travel to the GPU box"},
-            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    K, W = args.steps, args.warmup
+    r = reference_sample(K, W, "cpu", False, budget_s=240.0)
+    extra = {}
+    if "error" in r:
+        # reference tree not on this box: the oracle port (numpy restatement) stands in, and says so
+        sps, sec = time_cpu(CFG, max(1, min(K, 40)), max(1, W))
+        kind, cores, steps_done = "port", 1, max(1, min(K, 40))
+        sample = (f"{steps_done} full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single thread): the reference "
+                  f"tree was not importable here ({r['error']})")
+    else:
+        sps, sec, kind, cores, steps_done = r["steps_per_s"], r["s_per_step"], "reference", r["threads"], r["steps"]
+        sample = (f"{steps_done} full cfg2 outer steps of the unmodified reference PSVILearnV.nested_step ({r['root']}, "
+                  f"torch CPU, {r['threads']} threads on {r['cores']} cores, set_detect_anomaly off; next(iter(train_loader)) "
+                  "+ nested_step + loss.item() per step)")
+        a = reference_sample(2, 1, "cpu", True, budget_s=60.0)
+        extra["anomaly_on"] = ({"steps_per_s": a["steps_per_s"], "steps": a["steps"],
+                                "what": "same, with torch.autograd.set_detect_anomaly(True) as flow_psvi.py:50 ships"}
+                               if "error" not in a else a)
+        try:
+            import torch
+            if torch.cuda.is_available():
+                g = reference_sample(min(K, 30), max(1, min(W, 3)), "cuda", False, budget_s=90.0)
+                extra["eager_b200"] = ({"steps_per_s": g["steps_per_s"], "ms_per_step": g["s_per_step"] * 1e3, "steps": g["steps"],
+                                        "what": "the same unmodified reference class running eagerly on cuda:0 (PyTorch ATen "
+                                                "kernels + autograd double backward); SURVEY.md section 8d on-box comparator"}
+                                       if "error" not in g else g)
+        except Exception as e:  # noqa: BLE001
+            extra["eager_b200"] = {"error": repr(e)[:200]}
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+            "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": make_config(args.gpus),
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": extra}
     emit(line)
 
 
@@ -365,14 +413,16 @@ def main():
         obj.nested_step(xb.to(dev, non_blocking=True), yb.to(dev, non_blocking=True)).item()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
     e0.record(stream)
     for i in range(K):
         xb, yb = host_batches[W + i]
         loss = obj.nested_step(xb.to(dev, non_blocking=True), yb.to(dev, non_blocking=True))
-        loss.item()
+        loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # every step's loss goes back to the host
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    assert bool(torch.isfinite(loss_host).all()), "non-finite loss in the e2e run"
     clk = clocks.stop()
 
     # -------- secondary metric: MC log-lik evals/s (fn, M=50) -- both readings of SURVEY.md section 8d --------------
@@ -410,19 +460,27 @@ def main():
         obj._dev_data.pop("test", None)
         obj.evaluate()
         barrier()
-        a.record(stream)
-        reps = 3
-        for _ in range(reps):
+        for _ in range(3):
             obj.evaluate()
-        b.record(stream)
         barrier()
-        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        reps = 20
+        per = []
+        for _ in range(reps):
+            a.record(stream)
+            obj.evaluate()
+            b.record(stream)
+            torch.cuda.synchronize()
+            per.append(a.elapsed_time(b))
+        barrier()
+        t = torch.tensor([sorted(per)[len(per) // 2]], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = t.item() * 1e-3 / reps
+        sec = t.item() * 1e-3
         sharded = {"what": f"PSVI.evaluate over {n_big} synthetic rows (D=2, fn H=100, S=10, M=50, batch 8192), rows "
-                           f"sharded over {world} rank(s), one all-reduce of 8 floats",
-                   "passes_per_s": 1.0 / sec, "row_samples_per_s": n_big * c["S"] / sec}
+                           f"sharded over {world} rank(s), one all-reduce of 8 floats; median of {reps} passes, max over ranks; "
+                           "fp32 CUDA-core predictive kernels (compute / latency bound at D=2, DESIGN.md 4.2)",
+                   "passes_per_s": 1.0 / sec, "row_samples_per_s": n_big * c["S"] / sec,
+                   "ms_min_med_max_rank0": [min(per), sorted(per)[len(per) // 2], max(per)]}
     except Exception as e:  # never lose the headline number to the secondary section
         sharded = {"error": repr(e)[:200]}
 
@@ -476,6 +534,7 @@ def main():
     # samples over the full data (psvi_fn_predictive_tc: importance weights from M=1000 pseudo-points + mixture over rows);
     # rows sharded over ranks (weak: 524 288 rows per rank), ONE all-reduce of the 8-float result.
     fn_tc = None
+    fx = fy = fscr = None
     try:
         Df, Hf, Cf, Sf, Mf, rows_f = 256, 1024, 10, 64, 1000, 524_288
         fmodel = _native.make_model([Df, Hf, Cf], Sf)
@@ -618,14 +677,79 @@ def main():
     except Exception as e:
         fn5 = {"error": repr(e)[:300]}
 
+    # -------- the part of the hot path that SHARDS, at the size BASELINE configs[4] names ("cfg5"): full-data pass of fn
+    # D=256 H=1024 C=10 with S=64 MC samples over N = 10 M rows (bf16, 5.12 GB), M=1000 pseudo-points.  STRONG scaling: the
+    # 10 M rows are split contiguously over the ranks, every rank runs the tcgen05 forward over its shard and ONE all-reduce
+    # of the 8-float result closes the pass.  Timed per pass with CUDA events, median of the passes, max over ranks.
+    sharded_fulldata = None
+    try:
+        import gc
+        fx = fy = fscr = None      # release the weak-scaling section's buffers
+        gc.collect()
+        torch.cuda.empty_cache()
+        n_total5 = 10_000_000
+        lo5, hi5 = rank * n_total5 // world, (rank + 1) * n_total5 // world
+        rows5 = hi5 - lo5
+        gg = torch.Generator(device=dev).manual_seed(23 + rank)
+        x5 = torch.empty(rows5, Df, device=dev, dtype=torch.bfloat16)
+        for r0 in range(0, rows5, 1 << 20):     # generate in chunks: no fp32 copy of the whole shard
+            r1 = min(rows5, r0 + (1 << 20))
+            x5[r0:r1] = torch.randn(r1 - r0, Df, device=dev, generator=gg, dtype=torch.bfloat16)
+        y5 = torch.randint(0, Cf, (rows5,), device=dev, dtype=torch.int32, generator=gg)
+        s5 = torch.zeros(_native.fn_tc_scratch_floats(fmodel, rows5, Mf), device=dev)
+        o5 = torch.zeros(8, device=dev)
+
+        def pass5():
+            _native.fn_predictive_tc(fmodel, fnoise, fmu, frho, fu, fz, fv, x5, y5, 0, float(n_total5), 1, 0.0, 0, o5, s5)
+            if world > 1:
+                dist.all_reduce(o5)
+        pass5()
+        barrier()
+        per5, ar5 = [], []
+        for _ in range(5):
+            a.record(stream)
+            _native.fn_predictive_tc(fmodel, fnoise, fmu, frho, fu, fz, fv, x5, y5, 0, float(n_total5), 1, 0.0, 0, o5, s5)
+            b.record(stream)
+            if world > 1:
+                dist.all_reduce(o5)
+            c2 = torch.cuda.Event(enable_timing=True)
+            c2.record(stream)
+            torch.cuda.synchronize()
+            per5.append(a.elapsed_time(c2))
+            ar5.append(b.elapsed_time(c2))
+        barrier()
+        t5 = torch.tensor([sorted(per5)[len(per5) // 2], sorted(ar5)[len(ar5) // 2]], device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        sec5 = t5[0].item() * 1e-3
+        fl5_total = 2.0 * Sf * (n_total5 + world * Mf) * (Df * Hf + Hf * Cf)
+        sharded_fulldata = {
+            "what": f"cfg5 full-data pass, STRONG scaling: psvi_fn_predictive_tc over {n_total5} bf16 rows x D=256 (fn H=1024, "
+                    f"C=10, S=64, M=1000) split over {world} rank(s) ({rows5} rows on rank 0), one all-reduce of 8 floats; "
+                    "median of 5 passes, max over ranks",
+            "scaling": "strong", "n_gpus": world, "rows_total": n_total5, "ms_per_pass": sec5 * 1e3,
+            "passes_per_s": 1.0 / sec5, "row_samples_per_s": n_total5 * Sf / sec5,
+            "allreduce_ms": t5[1].item() if world > 1 else 0.0,
+            "TFLOPs_aggregate": fl5_total / sec5 / 1e12, "TFLOPs_per_gpu": fl5_total / world / sec5 / 1e12,
+            "bound": "tensor", "frac_of_sustained_bf16_peak_per_gpu":
+                fl5_total / world / sec5 / 1e12 / json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None}
+        del x5, y5, s5
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        sharded_fulldata = {"error": repr(e)[:300]}
+
     # -------- extra: several independent chains on ONE GPU (the reference's multi-trial mode) ------------------------
     # (single-process runs only: a chain built here would take the sharded code path under torch.distributed and wait for
     # collectives the other ranks never join)
     replicas = bench_replicas(c, dev, 8, min(K, 40), 3) if world == 1 else None
 
     # -------- reduce over ranks ---------------------------------------------------------------------------------------
-    value = world * K / (total_ms * 1e-3)
-    e2e = world * K / (e2e_ms * 1e-3)
+    tt = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)      # the slowest rank sets the job's time
+    value = world * K / (tt[0].item() * 1e-3)
+    e2e = world * K / (tt[1].item() * 1e-3)
     if rank == 0:
         peaks = {}
         try:
@@ -636,32 +760,41 @@ def main():
         fl = flops_outer_step(c)
         ach = fl / (kernel_ms * 1e-3) / 1e12
         sm = _native.lib().psvi_device_sm_count()
+        n_cta = c["S"]                                  # one CTA (SM) per MC sample in the cluster
+        sm_ghz = (clk.get("sm_mhz") or 1965.0) * 1e-3
+        fp32_peak_used = n_cta * 128 * 2 * sm_ghz * 1e-3      # TFLOP/s of the SMs the cluster occupies (128 FMA lanes per SM)
+        n_barriers = 4 * c["T"] + 8                     # two cluster barriers per inner step and per reverse step
+        barrier_floor_ms = n_barriers * 380.0 / (sm_ghz * 1e6)   # B300_MICROARCH: cluster barrier ~380 cycles
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": tt[0].item() / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": dict(c, parallelism="single chain" if world == 1 else
-                               f"{world} independent chains (trials), one per GPU, no data-path collective",
-                               l2="flushed between timed steps (256 MiB write)", noise="in-kernel Philox4x32-10"),
+                "config": make_config(world),
                 "clocks": clk,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": c["B"] * c["D"] * 4 + c["B"] * 4,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
-                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": ach / peak_tf, "traffic": None,
-                             "kernel": "psvi_mf_engine_kernel", "kernel_ms": kernel_ms,
-                             "flops_per_launch": fl,
-                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
-                             "note": "fp32 CUDA-core kernel on a 10-CTA cluster (10 of %d SMs); the GEMMs have K=D=2 / N=C=2 "
-                                     "and a T=100-long serial dependence, so the step is latency/issue bound and tensor "
-                                     "cores cannot be fed (SURVEY.md section 8d); the fraction against the tensor peak is "
-                                     "reported because the contract asks for it" % sm},
+                "roofline": {"bound": "fp32-issue/latency", "achieved": ach, "peak": fp32_peak_used, "unit": "TFLOP/s",
+                             "frac": ach / fp32_peak_used, "traffic": None,
+                             "kernel": "psvi_mf_fn1_kernel<2,2,7>", "kernel_ms": kernel_ms,
+                             "flops_per_launch": fl, "sms_used": n_cta, "sms_total": sm,
+                             "peak_source": f"fp32 FMA peak of the {n_cta} SMs the cluster occupies at the sampled SM clock "
+                                            f"({sm_ghz:.3f} GHz): {n_cta} x 128 lanes x 2 FLOP",
+                             "frac_of_tensor_peak": ach / peak_tf,
+                             "tensor_peak": peak_tf,
+                             "barrier_floor_ms": barrier_floor_ms,
+                             "note": "one cluster launch per outer step; the products have K = D = 2 / N = C = 2 and the step is a "
+                                     "chain of 2 T = 200 dependent phases, each closed by two cluster barriers, so neither HBM "
+                                     "(0.3 MB of DRAM traffic per launch) nor the tensor pipe can bind (SURVEY.md section 8d): the "
+                                     "roof that applies is fp32 issue on the SMs in use plus the barrier chain "
+                                     "(barrier_floor_ms = barriers x ~380 cycles); frac_of_tensor_peak is kept because the "
+                                     "contract names the tensor roof; ncu: profiles/r2_fn1_engine_ncu_summary.md"},
                 "roofline_fulldata": None if not fulldata or "error" in fulldata else {
                     "bound": "hbm", "achieved": fulldata["GBps"] / world, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
                     "frac": fulldata["GBps"] / world / peaks.get("hbm_gbs", 6650.0),
-                    "traffic": 4.135e9, "kernel": "psvi_lr_predictive_tc_kernel<12>",
-                    "note": "per GPU; algorithmic bytes = rows*(D*2+4) = 4.128 GB per launch; traffic = dram__bytes_read+write of "
-                            "one ncu --set full capture of the same launch (profiles/r1_lr_tc_ncu_summary.md); peak = measured "
-                            "copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"},
+                    "traffic": None, "kernel": "psvi_lr_predictive_tc_kernel<12>",
+                    "note": "per GPU; algorithmic bytes = rows*(D*2+4) = 4.128 GB per launch; DRAM traffic is not measured in this "
+                            "run (one ncu --set full capture of the same launch read 4.135 GB: profiles/r1_lr_tc_ncu_summary.md); "
+                            "peak = measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"},
                 "roofline_fn_tc": None if not fn_tc or "error" in fn_tc else {
                     "bound": "tensor", "achieved": fn_tc["TFLOPs_per_gpu"], "peak": peaks.get("bf16_tflops_sustained", 1400.0),
                     "unit": "TFLOP/s", "frac": fn_tc["TFLOPs_per_gpu"] / peaks.get("bf16_tflops_sustained", 1400.0),
@@ -670,15 +803,34 @@ def main():
                             "time = whole psvi_fn_predictive_tc call incl. weight sampling; peak = measured SUSTAINED bf16 "
                             "matmul throughput (the kernel runs for tens of ms back to back); ncu: "
                             "profiles/r1_fn_tc_ncu_summary.md"},
+                "sharded_fulldata": sharded_fulldata,
                 "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fn2_cfg3": fn2, "fn_large_cfg5": fn5, "replicas_one_gpu": replicas, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
                                                     "full_data_predictive_passes_200rows": pred_evals},
                           "sharded": sharded, "kernel_only_ms": kernel_ms,
                           "per_step_ms_min_med_max": [min(ms), sorted(ms)[len(ms) // 2], max(ms)]}}
         if not args.no_cpu_baseline and world == 1:
-            sps, sec = time_cpu(c, 12, 1)
-            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "12 full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single "
-                                              "thread) on this box's host CPU"}
+            # the reference's own CPU path on this box's host cores, bounded sample (it replaces OUR psvi package in
+            # sys.modules, so it runs last); the oracle port stands in only if the reference tree did not travel
+            r = reference_sample(8, 1, "cpu", False, budget_s=15.0)
+            if "error" not in r:
+                line["cpu_baseline"] = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                        "sample": f"{r['steps']} full cfg2 outer steps of the unmodified reference "
+                                                  f"PSVILearnV.nested_step ({r['root']}) on this box's host CPU, "
+                                                  f"{r['threads']} torch threads on {r['cores']} cores"}
+                g = reference_sample(12, 2, "cuda", False, budget_s=25.0)
+                if "error" not in g:
+                    line["extra"]["eager_b200"] = {
+                        "steps_per_s": g["steps_per_s"], "ms_per_step": g["s_per_step"] * 1e3, "steps": g["steps"],
+                        "what": "the same unmodified reference class running eagerly on this GPU (ATen kernels + autograd "
+                                "double backward), timed like e2e",
+                        "speedup_e2e_over_eager_b200": e2e / g["steps_per_s"]}
+                else:
+                    line["extra"]["eager_b200"] = g
+            else:
+                sps, sec = time_cpu(c, 12, 1)
+                line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "12 full cfg2 outer steps of oracle/psvi_oracle.py (numpy fp32, single "
+                                                  f"thread): reference tree not importable ({r['error']})"}
         else:
             line["cpu_baseline"] = None
         emit(line)

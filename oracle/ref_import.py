@@ -12,7 +12,9 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_CANDIDATES = ["/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+# the pip --target install (python -m pip install --no-index --no-build-isolation --no-deps --target baseline/_ref
+# /root/reference; __graft_entry__.build() does it) comes first: it is what travels to the GPU box
+_CANDIDATES = [os.path.join(os.path.dirname(_HERE), "baseline", "_ref"), "/root/reference"]
 
 
 def reference_root():

@@ -81,5 +81,7 @@ def time_reference(cfg, steps, warmup, device="cpu", anomaly=False, threads=None
         dt = time.perf_counter() - t0
     finally:
         torch.autograd.set_detect_anomaly(False)
+    from oracle.ref_import import reference_root
     return {"steps_per_s": done / dt, "s_per_step": dt / done, "steps": done, "threads": torch.get_num_threads(),
+            "root": reference_root(),
             "cores": os.cpu_count(), "device": device, "anomaly": bool(anomaly)}
