@@ -52,6 +52,7 @@ struct FnParams {
   float* nll_out;        // mode 0: [S][n_rows] (nullable)
   float* part;           // mode 0: [n_tiles][4][S] weighted nll sums; mode >= 1, nsplit == 1: [grid][4] (nll, correct, rows, 0)
   float* probs_out;      // mode >= 1, nsplit > 1: [nsplit][n_rows][CW] partial mixtures
+  __nv_bfloat16* obar;   // mode 3: [S][n_tiles] blocks of 2048 bf16: output-layer adjoint seeds as a UMMA operand (see below)
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -158,7 +159,8 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       for (int s = 0; s < p.S; ++s) mx = fmaxf(mx, p.lw[s]);
       for (int s = 0; s < p.S; ++s) se += expf(p.lw[s] - mx);
     }
-    for (int s = 0; s < 64; ++s) s_w[s] = s < p.S ? (p.mode == 1 ? expf(p.lw[s] - mx) / se : 1.f / (float)p.S) : 0.f;
+    for (int s = 0; s < 64; ++s)
+      s_w[s] = s < p.S ? (p.mode == 1 ? expf(p.lw[s] - mx) / se : (p.mode == 3 ? p.lw[s] : 1.f / (float)p.S)) : 0.f;
     mbar_init(xfull, 8); mbar_init(xempty, 1);
     for (int i = 0; i < BST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // CL MMA warps release a shared stage
     for (int i = 0; i < WST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1 + 4 * EPW); }
@@ -307,7 +309,7 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
       const int row = tile * BM + rl;
       const bool rok = row < p.n_rows;
       const int y = rok ? __ldg(p.labels + row) : 0;
-      const float cwr = (rok && p.mode == 0) ? (p.cw ? __ldg(p.cw + row) : 1.f) : 0.f;
+      const float cwr = (rok && (p.mode == 0 || p.mode == 3)) ? (p.cw ? __ldg(p.cw + row) : 1.f) : 0.f;
       {
         // X tile -> TMEM as the A operand of GEMM1: thread (row) stores its own bf16 row, the two warps of a lane quarter
         // take one half of the K range each (column c holds K elements 2c, 2c+1)
@@ -397,11 +399,29 @@ psvi_fn_forward_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __gr
             lg[c] = ex2_approx(lg[c] - mx);
             se += lg[c];
           }
-          if (p.mode == 0) {
+          if (p.mode == 0 || p.mode == 3) {
             const float nll = rok ? (mx - ly) * LN2 + logf(se) : 0.f;
             if (p.nll_out && rok) p.nll_out[(size_t)s * p.n_rows + row] = nll;
             const float t = warp_sum(cwr * nll);
             if (lane == 0 && tile < p.n_tiles) p.part[((size_t)tile * 4 + q) * p.S + s] = t;
+            if (p.mode == 3 && tile < p.n_tiles) {
+              // adjoint seeds of the output layer, obar[r][c] = coef_s (softmax_c - [c == y_r]) (zero for padding classes
+              // and rows past the end), as bf16 in the canonical no-swizzle UMMA layout of a [128 rows x 16 classes] tile:
+              // element (r, c) at (c / 8) * 2048 + r * 16 + (c % 8) * 2 bytes -- K-major operand (N = rows, K = classes)
+              // with LBO = 2048 / SBO = 128, and at the same time MN-major operand (N = classes, K = rows) with LBO = 128 /
+              // SBO = 2048 (psvi_fn_grad_tc.cuh reads it both ways)
+              const float cf = rok ? s_w[s] * __fdividef(1.f, se) : 0.f, cy = rok ? s_w[s] : 0.f;
+              uint32_t pk[CW / 2];
+#pragma unroll
+              for (int c = 0; c < CW; c += 2) {
+                const float o0 = fmaf(cf, lg[c], (c == y) ? -cy : 0.f), o1 = fmaf(cf, lg[c + 1], (c + 1 == y) ? -cy : 0.f);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(o0, o1);
+                pk[c / 2] = *reinterpret_cast<uint32_t*>(&t2);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(p.obar + ((size_t)s * p.n_tiles + tile) * 2048);
+              dst[rl] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[128 + rl] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           } else {
             const float sc = __fdividef(s_w[s], se);
 #pragma unroll
@@ -714,7 +734,8 @@ int prepare(const psvi_mf_model* model, const psvi_noise* noise, const float* mu
 // one forward over `n_rows` rows with prepared weights
 //   mode 0: out_s[S] = sum_r cw[r] nll[s, r] + add[s]   (nll_out optional);   mode 1 / 2: out[0..4] predictive metrics
 int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16, const int32_t* labels, const float* cw,
-            int64_t n_rows, int mode, const float* lw, const float* add, float* out, float* nll_out, cudaStream_t stream) {
+            int64_t n_rows, int mode, const float* lw, const float* add, float* out, float* nll_out, cudaStream_t stream,
+            __nv_bfloat16* obar = nullptr) {
   const int D = model->dims[0], H = model->dims[1], C = model->dims[2], S = model->mc_samples;
   int dev = 0, sms = 0;
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
@@ -738,6 +759,7 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   p.mode = mode; p.x = static_cast<const __nv_bfloat16*>(x_bf16);
   p.b1 = sc.b1; p.b2 = sc.b2; p.cw = cw; p.lw = lw; p.labels = labels; p.nll_out = nll_out; p.part = sc.part;
   p.probs_out = sc.probs;
+  p.obar = obar;
   const int items = groups * nsplit;
   const int grid = CLv * (items < sms / CLv ? items : sms / CLv);
 #ifdef PSVI_FN_PROF
@@ -783,7 +805,7 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
       }
   }
 #endif
-  if (mode == 0) {
+  if (mode == 0 || mode == 3) {
     fn_sum_tiles_kernel<<<1, 64, 0, stream>>>(sc.part, tiles, S, add, out);
   } else if (nsplit > 1) {
     const int fb = (int)((n_rows + 255) / 256) < 1024 ? (int)((n_rows + 255) / 256) : 1024;
@@ -796,12 +818,31 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   return PSVI_OK;
 }
 
+#include "psvi_fn_grad_tc.cuh"
+
 }  // namespace
 
 // defined in psvi_lr_tc.cu
 extern "C" int psvi_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 extern "C" {
+
+size_t psvi_fn_data_grad_tc_scratch_bytes(const psvi_mf_model* model, int64_t n_rows) {
+  if (!model || model->n_layers != 2 || n_rows <= 0) return 0;
+  GradScratch g;
+  carve_grad(model, n_rows, nullptr, g);
+  return g.total + 256;
+}
+
+int psvi_fn_data_grad_tc(const psvi_mf_model* model, const float* theta, const void* x_bf16, const int32_t* y, int64_t n_rows,
+                         const float* coef, float* dsum, float* tbar, void* scratch, void* stream) {
+  PSVI_REQUIRE(model && theta && x_bf16 && y && coef && dsum && tbar && scratch, PSVI_ERR_INVALID, "null pointer");
+  int rc = check_model(model);
+  if (rc) return rc;
+  PSVI_REQUIRE(n_rows > 0 && n_rows < (1ll << 31), PSVI_ERR_INVALID, "bad n_rows");
+  PSVI_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, PSVI_ERR_INVALID, "x_bf16 must be 16-byte aligned");
+  return data_grad(model, theta, x_bf16, y, coef, n_rows, dsum, tbar, scratch, (cudaStream_t)stream);
+}
 
 size_t psvi_fn_tc_scratch_bytes(const psvi_mf_model* model, int64_t max_rows, int32_t M) {
   if (!model || model->n_layers != 2 || max_rows <= 0) return 0;

@@ -91,6 +91,9 @@ _SIGS = {
     "psvi_fn_nll_tc": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "psvi_fn_data_grad_tc_scratch_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int64]),
+    "psvi_fn_data_grad_tc": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_mf_stream_workspace_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int32]),
     "psvi_mf_unroll_stream": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
@@ -370,6 +373,18 @@ def fn_nll_tc(model, noise, mu, rho, x_bf16, labels, row_weights, slab, wsum_out
     _check(lib().psvi_fn_nll_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x_bf16, torch.bfloat16),
                                 _p(labels, torch.int32), _p(row_weights), x_bf16.shape[0], slab, _p(wsum_out), _p(nkl_out),
                                 _p(nll_out), _p(scratch), _stream()))
+
+
+def fn_data_grad_scratch_floats(model, n_rows):
+    return (int(lib().psvi_fn_data_grad_tc_scratch_bytes(C.byref(model), int(n_rows))) + 3) // 4
+
+
+def fn_data_grad_tc(model, theta, x_bf16, labels, coef, dsum_out, tbar_out, scratch):
+    """Data-term gradient of the outer objective over a shard of rows on the tensor path: dsum [S] = sum_r nll[s, r],
+    tbar [S][P] = coef[s] * sum_r d nll[s, r] / d theta_s (two tcgen05 passes; include/psvi_b200.h)."""
+    _count(6)
+    _check(lib().psvi_fn_data_grad_tc(C.byref(model), _p(theta), _p(x_bf16, torch.bfloat16), _p(labels, torch.int32),
+                                      x_bf16.shape[0], _p(coef), _p(dsum_out), _p(tbar_out), _p(scratch), _stream()))
 
 
 def f32_to_bf16(src, dst):

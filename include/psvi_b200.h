@@ -276,6 +276,21 @@ int psvi_fnl_pass(const psvi_mf_model* model, int32_t precision, const float* th
                   const int32_t* y, const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
                   float* logits, void* workspace, void* stream);
 
+/* ---- full-data DATA-TERM gradient of the outer objective on the tensor path (the part of the hot path that shards).
+ * reference: data_nll = N / Nx * all_nlls[:, Nu:].sum(-1) inside psvi_elbo (psvi/inference/psvi_classes.py:477,484-486)
+ * and what autograd back-propagates through it; SURVEY.md section 7 step 7 / section 8e.
+ * For externally sampled weights theta [S][P] (theta layout) and a shard of R rows x_bf16 [R][D] (bf16), y [R] int32:
+ *     dsum [S]    = sum_r nll[s, r]
+ *     tbar [S][P] = coef[s] * sum_r d nll[s, r] / d theta_s        (overwritten)
+ * coef [S] is the caller's per-sample coefficient (w_s N / B: the importance weights depend on the pseudo-data only, so the
+ * rows enter linearly and ranks add up: ONE all-reduce of the reparameterised gradient + dsum).  Two tcgen05 passes over
+ * the rows (forward + seeds, then the backward with the W1 adjoint slices accumulated in tensor memory across row tiles);
+ * bf16 operands, fp32 accumulation.  Same shape limits as psvi_fn_predictive_tc (D multiple of 64 <= 256, H multiple of
+ * 128, C <= 16, S <= 64).  scratch: psvi_fn_data_grad_tc_scratch_bytes(model, R). */
+size_t psvi_fn_data_grad_tc_scratch_bytes(const psvi_mf_model* model, int64_t n_rows);
+int psvi_fn_data_grad_tc(const psvi_mf_model* model, const float* theta, const void* x_bf16, const int32_t* y, int64_t n_rows,
+                         const float* coef, float* dsum, float* tbar, void* scratch, void* stream);
+
 /* ---- convolutional family (lenet): per-sample network pass on externally supplied weights, same contract as
  * psvi_net_pass.  Replaces VIConv2d.forward (grouped conv over samples), BatchMaxPool2d, nn.Flatten and the three VILinear
  * layers of make_lenet + Categorical.log_prob + autograd (psvi/models/neural_net.py:194-255,334-359).
