@@ -207,6 +207,7 @@ class PSVI(object):
         return (FnLargeNet.fits(dims, model.n_samples()) and dims[1] * (dims[0] + 1) + dims[2] * (dims[1] + 1) > 40000)
 
     _outer_kind = "psvi"      # which outer objective nested_step differentiates ("ablated": PSVI_Ablated / PSVI_No_IW)
+    fulldata_min_rows = 8192  # large fn: data terms with at least this many rows (over all ranks) take the bf16 tensor path
 
     def _inner_pseudo(self, u, z32, a):
         """(u, z, a) as the inner objective sees them (hook for the mc_samples == 1 quirk of PSVI_No_IW)."""
@@ -373,9 +374,19 @@ class PSVI(object):
                 n1, n2 = pbar.numel(), ubar.numel()
                 return flat[0], flat[1:1 + n1], flat[1 + n1:1 + n1 + n2].reshape(ubar.shape), flat[1 + n1 + n2:]
         u_in, z_in, a_in = self._inner_pseudo(u, self._z32(), self._a())
+        # many data rows on a large fn (the full-data / sharded data term of BASELINE configs[4]): fused tensor-core pass over
+        # bf16 rows (psvi_fn_data_grad_tc); below the threshold the exact tf32x3 pass of the minibatch stays
+        xb16 = None
+        if (self._outer_kind == "psvi" and isinstance(model, MeanFieldMLP) and not isinstance(model, MeanFieldLeNet)
+                and self._is_large_fn(model) and self._fits_fn_tc(model)
+                and (n_total if n_total is not None else xb.shape[0]) >= self.fulldata_min_rows):
+            xb16 = torch.empty(xb.shape, device=xb.device, dtype=torch.bfloat16)
+            if xb.numel():
+                _native.f32_to_bf16(xb, xb16)
         loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u_in, z_in, a_in,
                                                  xb, yb, float(self.N), T, lr, want_losses=self.register_elbos,
-                                                 kappa=kappa, n_total=n_total, reduce_fn=reduce_fn, outer=self._outer_kind)
+                                                 kappa=kappa, n_total=n_total, reduce_fn=reduce_fn, outer=self._outer_kind,
+                                                 xb_bf16=xb16)
         ubar, abar = self._collapse_pseudo(ubar, abar)
         eng.fam.set_phi(phi_T)                 # copy-back of the fast weights (reference :596-599)
         if self.register_elbos:
@@ -568,7 +579,9 @@ class PSVI(object):
         outer step -- gathered on the device from the resident copy of the training set."""
         x, y = self._device_dataset(self.train_dataset, "train")
         n = x.shape[0]
-        idx = torch.randperm(n)[: min(int(self.data_minibatch), n)].to(self.device, non_blocking=True)
+        if int(self.data_minibatch) >= n:      # full batch: the data term is a sum over all rows, their order is immaterial
+            return x, y
+        idx = torch.randperm(n, device=self.device)[: int(self.data_minibatch)]   # drawn on the device (no H2D per step)
         return x[idx], y[idx]
 
     # ------------------------------------------------------------------------------------------------ main loop

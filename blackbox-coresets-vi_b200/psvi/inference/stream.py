@@ -232,6 +232,18 @@ class FnLargeNet:
     def predict(self, theta, lw, mode, xt, yt, out):
         _native.logits_predict(self.logits(theta, xt), lw, mode, yt, out)
 
+    def data_grad(self, theta, x_bf16, y32, coef):
+        """Data term of the outer objective over many rows on the fused tensor path (csrc/psvi_fn_grad_tc.cuh): returns
+        (sum_r nll[s, r] [S], coef[s] * sum_r d nll[s, r] / d theta_s [S][P]).  bf16 operands, fp32 accumulation."""
+        S, dev = self.S, theta.device
+        dsum, tbar = torch.empty(S, device=dev), torch.empty(S, theta.shape[1], device=dev)
+        n = _native.fn_data_grad_scratch_floats(self.desc, x_bf16.shape[0])
+        ws = getattr(self, "_dg_ws", None)
+        if ws is None or ws.numel() < n or ws.device != dev:
+            ws = self._dg_ws = torch.empty(n, device=dev)
+        _native.fn_data_grad_tc(self.desc, theta.contiguous(), x_bf16, y32, coef.contiguous(), dsum, tbar, ws)
+        return dsum, tbar
+
 
 class LenetNet:
     """Per-sample lenet pass: fused conv + ReLU + pool kernels and the fc kernels of csrc/psvi_lenet.cu."""
@@ -272,11 +284,13 @@ class StreamEngine:
 
     ROW_CHUNK = 8192   # data rows per network pass when the minibatch is large (full-data term, sharded over ranks)
 
-    def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None):
+    def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None, xb_bf16=None):
         """psvi_elbo value and gradients.  `kappa` / `n_total` describe one rank's share when the data rows are sharded over
         R ranks: L_r = sum_s w_s (d_s^r - kappa p_s) - kappa mean(lw), kappa = 1/R, d_s^r = (N / n_total) * sum over
         this rank's rows; the shares (value and every gradient) add up to the unsharded objective because the importance
         weights depend on the pseudo-data only.  Large minibatches are processed in chunks of ROW_CHUNK rows."""
+        if xb_bf16 is not None:
+            return self._outer_grad_fulldata(phi, eps, u, z32, a, xb_bf16, yb32, N, kappa, n_total)
         S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
         n_total = B if n_total is None else n_total
         eps = self.fam.fix_eps(eps)
@@ -328,6 +342,43 @@ class StreamEngine:
             pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
         return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
+    def _outer_grad_fulldata(self, phi, eps, u, z32, a, xb_bf16, yb32, N, kappa, n_total):
+        """outer_grad with the data rows (bf16, many) on the fused tensor path: the importance weights need the pseudo-data
+        forward only, so the order is  pseudo values -> w -> ONE data pass (nll sums + w_s N / n_total weighted adjoints) ->
+        beta, dL/dp -> pseudo gradient pass.  Same return values and sharding contract (kappa, n_total) as outer_grad."""
+        S, M, B, dev = self.S, u.shape[0], xb_bf16.shape[0], u.device
+        n_total = B if n_total is None else n_total
+        eps = self.fam.fix_eps(eps)
+        theta = self.fam.sample(phi, eps)
+        nll_u = torch.empty(S, M, device=dev)
+        self.net.pass_(theta, None, u, z32, None, nll=nll_u)
+        ps = nll_u.double() @ a.double()
+        lw = -ps + self.fam.nkl(phi, eps, theta)
+        w = torch.softmax(lw, 0)
+        wd = (w * N / n_total).float()
+        if B > 0:
+            dsum, tbar_d = self.net.data_grad(theta, xb_bf16, yb32, wd)
+            ds = (N / n_total) * dsum.double()
+        else:   # a rank without rows still takes part in the exchange
+            tbar_d, ds = None, torch.zeros(S, device=dev, dtype=torch.float64)
+        e = ds - kappa * ps
+        ebar = (w * e).sum()
+        loss = ebar - kappa * lw.mean()
+        beta = w * (e - ebar) - kappa / S
+        gp = -kappa * w - beta
+        cw_u = (gp[:, None] * a.double()[None, :]).float()
+        tbar = torch.empty(S, self.Pt, device=dev)
+        xbar_u = torch.empty(S, M, u.shape[1], device=dev)
+        self.net.pass_(theta, None, u, z32, cw_u.contiguous(), nll=nll_u, tbar=tbar, xbar=xbar_u)
+        if tbar_d is not None:
+            tbar += tbar_d
+        if hasattr(self.fam, "grad_with_nkl"):
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+        else:
+            tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
+            pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
+        return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
+
     def outer_grad_ablated(self, phi, eps, xb, yb32, N, kappa=1.0, n_total=None):
         """PSVI_Ablated.psvi_elbo (reference psvi_classes.py:1397-1408): mean_s (N/B) sum_b nll[s, b] - mean_s sampled_nkl_s --
         no importance weights and no pseudo-data term (its direct partials wrt u, v are zero).  kappa / n_total: one rank's
@@ -367,7 +418,7 @@ class StreamEngine:
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
     def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None, reduce_fn=None,
-               outer="psvi"):
+               outer="psvi", xb_bf16=None):
         """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None).
         Sharded data term: pass this rank's rows with kappa = 1/world, n_total = rows over all ranks and a `reduce_fn` that
         all-reduces (loss, pbar, ubar, abar) -- the ONE exchange step of the bilevel step; the inner loop and
@@ -388,7 +439,8 @@ class StreamEngine:
             loss, pbar = self.outer_grad_ablated(phi, eps_all[T], xb, yb32, N, kappa=kappa, n_total=n_total)
             ubar, abar = torch.zeros_like(u), torch.zeros_like(a)
         else:
-            loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total)
+            loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total,
+                                                        xb_bf16=xb_bf16)
         if reduce_fn is not None:
             loss, pbar, ubar, abar = reduce_fn(loss, pbar, ubar, abar)
         phi_T = phi

@@ -109,3 +109,73 @@ def test_data_grad_is_deterministic_and_additive_over_row_shards():
     db, tb = run(384, R)
     assert torch.allclose(da + db, d0, rtol=1e-5)
     assert float((ta + tb - t0).norm() / t0.norm()) < 1e-5
+
+
+def _large_obj(B, min_rows, T=2, seed=0):
+    from psvi.experiments.experiments_utils import SynthDataset, make_synthetic_rows
+    from psvi.inference.psvi_classes import PSVILearnV
+    D, H, C, S, M = 128, 384, 3, 3, 24
+    X, Y = make_synthetic_rows(B + 200, D, C, seed=seed)
+    tr, te = SynthDataset(X[:B], Y[:B].float()), SynthDataset(X[B:], Y[B:].float())
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=B, inner_it=T, trainer="nested", log_every=10, lr0u=1e-4,
+              lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-2, num_pseudo=M, seed=0, architecture="fn",
+              n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="synthetic", nc=C,
+              compute_weights_entropy=True, register_elbos=False, quiet=True)
+    obj = PSVILearnV(**kw)
+    obj.fulldata_min_rows = min_rows
+    obj.run_psvi(**kw)
+    return obj, X, Y, (D, H, C, S, M, T)
+
+
+def test_nested_step_with_fulldata_tensor_path_matches_oracle():
+    """PSVILearnV.nested_step whose data term covers the whole (2 048-row) training set: the class routes the data rows
+    through psvi_fn_data_grad_tc (bf16 operands); hypergradients against the fp64 oracle of the reference's nested_step
+    (psvi_classes.py:541-600).  Stated tolerance: loss 2e-3 relative, hypergradients rel-L2 5e-2 and cosine >= 0.998 (the
+    data-term gradient carries bf16 operand rounding; the unrolled inner loop stays in tf32x3)."""
+    from oracle import psvi_oracle as po
+    from oracle.ref_import import NoiseFeeder
+    from psvi.inference.psvi_classes import ExternalNoise
+    B = 2048
+    obj, X, Y, (D, H, C, S, M, T) = _large_obj(B, min_rows=1024)
+    dims = obj.model.dims
+    eps = NoiseFeeder.stream(dims, S, 77, T + 1)
+    obj.noise_source = ExternalNoise(eps)
+    obj.scheduler_optim_net = None
+    mu, rho = [t.cpu().numpy().astype(np.float64) for t in obj.model.flat()]
+    u0, z = obj.u.detach().cpu().numpy().astype(np.float64), obj.z.cpu().numpy()
+    v0 = obj.v.detach().cpu().numpy().astype(np.float64)
+    calls = nat.launch_count()
+    xb, yb = obj._next_minibatch()          # full batch: the resident training set itself
+    assert xb.shape[0] == B
+    loss = obj.nested_step(xb, yb)
+    e64 = [e.astype(np.float64) for e in eps]
+    r = po.nested_step(mu, rho, np.stack(e64[:T]), e64[T], u0, z, v0, X[:B].numpy().astype(np.float64), Y[:B].numpy(), float(B),
+                       dims, 1e-3, vmode=1)
+    assert nat.launch_count() > calls
+    assert abs(loss.item() - r["loss"]) <= 2e-3 * abs(r["loss"]), (loss.item(), r["loss"])
+    gu, gv = obj.u.grad.cpu().double().numpy(), obj.v.grad.cpu().double().numpy()
+    cos = lambda a, b: float(a.ravel() @ b.ravel() / (np.linalg.norm(a) * np.linalg.norm(b)))  # noqa: E731
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    assert rel(gu, r["u_grad"]) < 5e-2 and cos(gu, r["u_grad"]) > 0.998, (rel(gu, r["u_grad"]), cos(gu, r["u_grad"]))
+    assert rel(gv, r["v_grad"]) < 5e-2 and cos(gv, r["v_grad"]) > 0.998, (rel(gv, r["v_grad"]), cos(gv, r["v_grad"]))
+
+
+def test_outer_grad_fulldata_shares_add_up():
+    """Two ranks' shares of the outer objective (kappa = 1/2, contiguous row shards) add up to the
+    unsharded value and gradients -- what the one all-reduce of the sharded step relies on -- on the tensor data path."""
+    B = 3000
+    obj, X, Y, (D, H, C, S, M, T) = _large_obj(B, min_rows=1024)
+    eng = obj._stream(obj.model)
+    phi = eng.fam.get_phi()
+    eps = obj._noise_tensor(1, eng.Pt, S)[0]
+    u, _ = obj._uv()
+    z32, a = obj._z32(), obj._a()
+    xb, yb = obj._next_minibatch()
+    x16 = xb.bfloat16().contiguous()
+    full = eng.outer_grad(phi, eps, u, z32, a, None, yb, float(B), xb_bf16=x16)
+    cut = 1700
+    s0 = eng.outer_grad(phi, eps, u, z32, a, None, yb[:cut].contiguous(), float(B), kappa=0.5, n_total=B, xb_bf16=x16[:cut].contiguous())
+    s1 = eng.outer_grad(phi, eps, u, z32, a, None, yb[cut:].contiguous(), float(B), kappa=0.5, n_total=B, xb_bf16=x16[cut:].contiguous())
+    for k in range(4):
+        tot = s0[k] + s1[k]
+        assert float((tot - full[k]).norm() / full[k].norm()) < 2e-4, k
