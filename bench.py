@@ -734,10 +734,71 @@ def main():
             "bound": "tensor", "frac_of_sustained_bf16_peak_per_gpu":
                 fl5_total / world / sec5 / 1e12 / json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None}
-        del x5, y5, s5
+        del s5
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         sharded_fulldata = {"error": repr(e)[:300]}
+
+    # -------- the sharded outer-loss GRADIENT at cfg5 (north_star (4)): psvi_elbo value and
+    # gradient wrt phi_T, u, v with the data term over the SAME 10 M rows split over the ranks (psvi_fn_data_grad_tc: two
+    # tcgen05 passes per shard), pseudo-data terms replicated, and ONE all-reduce of [loss | dL/dphi_T | direct du | direct da].
+    sharded_outer_grad = None
+    try:
+        from psvi.experiments.experiments_utils import SynthDataset as _SDg, make_synthetic_rows as _msrg
+        from psvi.inference.psvi_classes import PSVILearnV as _PLg
+        Xg, Yg = _msrg(4096, Df, Cf, seed=0)
+        tg, eg = _SDg(Xg[:3072], Yg[:3072].float()), _SDg(Xg[3072:], Yg[3072:].float())
+        kg = dict(mc_samples=Sf, num_epochs=0, data_minibatch=128, D=Df, N=n_total5, inner_it=1, trainer="nested", log_every=1000,
+                  lr0u=1e-4, lr0net=1e-3, lr0v=1e-3, init_args="subsample", init_sd=1e-3, num_pseudo=Mf, seed=0,
+                  architecture="fn", n_hidden=Hf, n_layers=1, logistic_regression=False, train_dataset=tg, test_dataset=eg,
+                  dnm="synthetic", nc=Cf, compute_weights_entropy=False, register_elbos=False, quiet=True)
+        og = _PLg(**kg)
+        og.run_psvi(**kg)
+        eng = og._stream(og.model)
+        phi_g = eng.fam.get_phi()
+        eps_g = og._noise_tensor(1, eng.Pt, Sf)[0]
+        ug, _ = og._uv()
+        zg, ag_ = og._z32(), og._a()
+
+        def outer_once():
+            lo_, pb_, ub_, ab_, _d = eng.outer_grad(phi_g, eps_g, ug, zg, ag_, None, y5, float(n_total5), kappa=1.0 / world,
+                                                    n_total=n_total5, xb_bf16=x5)
+            return torch.cat([lo_.reshape(1), pb_.reshape(-1), ub_.reshape(-1), ab_.reshape(-1)]).float()
+        flat = outer_once()
+        if world > 1:
+            dist.all_reduce(flat)
+        barrier()
+        pg, arg = [], []
+        for _ in range(3):
+            a.record(stream)
+            flat = outer_once()
+            b.record(stream)
+            if world > 1:
+                dist.all_reduce(flat)           # the ONE collective of the sharded outer step (NCCL over NVLink)
+            c3 = torch.cuda.Event(enable_timing=True)
+            c3.record(stream)
+            torch.cuda.synchronize()
+            pg.append(a.elapsed_time(c3))
+            arg.append(b.elapsed_time(c3))
+        barrier()
+        tg_ = torch.tensor([sorted(pg)[1], sorted(arg)[1]], device=dev)
+        if world > 1:
+            dist.all_reduce(tg_, op=dist.ReduceOp.MAX)
+        secg = tg_[0].item() * 1e-3
+        flg = 3 * 2.0 * Sf * n_total5 * (Df * Hf + Hf * Cf)      # data term: forward + backward = 3 F_fwd(N)
+        sharded_outer_grad = {
+            "what": f"psvi_elbo value + gradient at cfg5 shapes (fn D=256 H=1024 C=10, S=64, M=1000) with the data term over "
+                    f"{n_total5} bf16 rows split over {world} rank(s): pseudo-data passes replicated (tf32x3), data rows through "
+                    "psvi_fn_data_grad_tc (bf16 tcgen05, W1 adjoints accumulated in TMEM), ONE all-reduce of "
+                    f"{flat.numel()} floats; median of 3, max over ranks",
+            "scaling": "strong", "n_gpus": world, "rows_total": n_total5, "ms_per_outer_gradient": secg * 1e3,
+            "allreduce_ms": tg_[1].item() if world > 1 else 0.0, "allreduce_bytes": int(flat.numel()) * 4,
+            "data_term_algorithmic_TFLOPs_aggregate": flg / secg / 1e12,
+            "data_term_algorithmic_TFLOPs_per_gpu": flg / world / secg / 1e12}
+    except Exception as e:  # noqa: BLE001
+        sharded_outer_grad = {"error": repr(e)[:300]}
+    x5 = y5 = None
+    torch.cuda.empty_cache()
 
     # -------- extra: several independent chains on ONE GPU (the reference's multi-trial mode) ------------------------
     # (single-process runs only: a chain built here would take the sharded code path under torch.distributed and wait for
@@ -804,6 +865,7 @@ def main():
                             "matmul throughput (the kernel runs for tens of ms back to back); ncu: "
                             "profiles/r1_fn_tc_ncu_summary.md"},
                 "sharded_fulldata": sharded_fulldata,
+                "sharded_outer_grad": sharded_outer_grad,
                 "extra": {"fulldata_fn_tc": fn_tc, "lenet_cfg4": lenet, "fn2_cfg3": fn2, "fn_large_cfg5": fn5, "replicas_one_gpu": replicas, "fulldata_lr_tc": fulldata, "mc_loglik_evals_per_s": {"pseudo_data_elbo_fwd_bwd_fn_M50": inner_evals,
                                                     "full_data_predictive_passes_200rows": pred_evals},
                           "sharded": sharded, "kernel_only_ms": kernel_ms,

@@ -850,11 +850,8 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   const size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  // function attributes are per device: set on every call (cheap), not cached per process
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tn_gemm_kernel<X3><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;

@@ -260,7 +260,7 @@ _stream_ws = {}
 
 def _workspace(model, n_rows, device):
     n = (int(lib().psvi_mf_stream_workspace_bytes(C.byref(model), n_rows)) + 3) // 4
-    key = (device, )
+    key = (device, _stream())      # chains on different CUDA streams must not share scratch
     t = _stream_ws.get(key)
     if t is None or t.numel() < n:
         t = torch.zeros(n, device=device, dtype=torch.float32)
@@ -443,10 +443,11 @@ def lenet_pass(S, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar
     """Per-sample lenet pass (forward / gradient / dual) on sampled weights theta [S][P]; x [R][784]."""
     R = x.shape[0]
     n = (int(lib().psvi_lenet_workspace_bytes(S, R)) + 3) // 4
-    ws = _lenet_ws.get(theta.device)
+    key = (theta.device, _stream())
+    ws = _lenet_ws.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.empty(n, device=theta.device, dtype=torch.float32)
-        _lenet_ws[theta.device] = ws
+        _lenet_ws[key] = ws
     _count(6 if tbar is None else (16 if thetad is None else 36))
     _check(lib().psvi_lenet_pass(S, _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll), _p(tbar), _p(tdbar),
                                  _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))
@@ -469,10 +470,11 @@ def fnl_pass(model, precision, theta, thetad, x, y, cw, nll=None, tbar=None, tdb
     """Large-regime fn pass (batched tcgen05 GEMMs; bf16, tf32x3 or bf16x3 arithmetic) on sampled weights theta [S][P]."""
     R = x.shape[0]
     n = (int(lib().psvi_fnl_workspace_bytes(C.byref(model), R, precision)) + 3) // 4
-    ws = _fnl_ws.get(theta.device)
+    key = (theta.device, _stream())
+    ws = _fnl_ws.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.empty(n, device=theta.device, dtype=torch.float32)
-        _fnl_ws[theta.device] = ws
+        _fnl_ws[key] = ws
     _count(8 if tbar is None else (14 if thetad is None else 25))
     _check(lib().psvi_fnl_pass(C.byref(model), precision, _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), R, _p(nll),
                                _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(logits), _p(ws), _stream()))

@@ -233,6 +233,28 @@ class PSVI(object):
             self._noise_domain = dom
             return None
 
+    def _fits_fused(self, model, desc):
+        """Does the model fit the shared-memory-resident cluster engines?  Probed once per model with a throw-away noise
+        stream (nothing of this object's state or noise order is touched), so that callers can pick the streaming path
+        BEFORE they mutate anything."""
+        key = ("fits_fused", id(model), model.n_samples())
+        fit = self._ws.get(key)
+        if fit is None:
+            mu, rho = model.flat()
+            u, v = self._uv()
+            g, val = torch.empty(2 * mu.numel(), device=self.device), torch.empty(1, device=self.device)
+            try:
+                _native.inner_grad(desc, _native.make_noise(None, seed=0, domain=0), mu, rho, u, self._z32(), v, float(self.N),
+                                   self._vmode, self._alpha_value(), g, val)
+                fit = True
+            except _native.NativeError as e:
+                if e.code != _native.ERR_UNSUPPORTED:
+                    raise
+                fit = False
+                self._ws[("force_stream", id(model))] = True
+            self._ws[key] = fit
+        return fit
+
     def _noise_tensor(self, n_slabs, Pt, S):
         if self.noise_source is not None:
             return self.noise_source.take(n_slabs, self.device)
@@ -477,10 +499,17 @@ class PSVI(object):
         of the inner objective -- each one fused CUDA pass.  Noise is consumed in the reference's order (the JVP's
         double-VJP evaluates Phi twice, the first draw is discarded)."""
         from psvi.hypergrad.hypergradients import cg_normaleq_native, fixed_point_native
+        if self._outer_kind != "psvi":
+            # PSVI_Ablated / PSVI_No_IW: the reference's outer_loss_function would call the ablated psvi_elbo (and, for
+            # No_IW, the mc_samples == 1 label-broadcast quirk of inner_elbo); the implicit solvers here differentiate the
+            # importance-weighted objective only -- refuse instead of returning a different hypergradient
+            raise NotImplementedError(f"--trainer hyper is not built for {type(self).__name__} (ablated outer objective); "
+                                      "use --trainer nested")
         T = int(self.inner_it)
         self._zero_grads()
         model, desc, S = self._model_desc()
-        if self._use_stream(model) or (isinstance(model, MeanFieldMLP) and self._is_large_fn(model)):
+        if (self._use_stream(model) or (isinstance(model, MeanFieldMLP) and self._is_large_fn(model))
+                or not self._fits_fused(model, desc)):
             return self._hyper_step_stream(model, S, xbatch, ybatch, K, linsys_lr, hypergrad_approx)
         mu, rho = model.flat()
         P = mu.numel()
@@ -796,8 +825,10 @@ class PSVI(object):
     def weight_reset(self):
         """Reset variational parameters to initialisation (reference :1110-1128)."""
         for layer in self.model.modules():
-            if isinstance(layer, VILinear) and hasattr(layer, "reset_parameters_variational"):
+            if isinstance(layer, (VILinear, VILinearMultivariateNormal)) and hasattr(layer, "reset_parameters_variational"):
                 layer.reset_parameters_variational()   # in-place inits: the flat-buffer views stay valid
+            elif isinstance(layer, nn.Conv2d) and hasattr(layer, "reset_parameters"):
+                layer.reset_parameters()               # reference :1121-1126 (VIConv2d falls in the nn.Conv2d branch)
 
     def pred_on_grid(self, n_test_per_dim=250, correction=True, **kwargs):
         """Predictive probabilities over the 2-d grid [-3, 4] x [-2, 3] (reference :1130-1175): importance-weighted mixture
@@ -879,9 +910,27 @@ class PSVIAV(PSVILearnV):
         self.results["alpha"].append(self.alpha.clone().cpu().detach().numpy())
         return super().evaluate(**kwargs)
 
+    def hyper_step(self, xbatch, ybatch, T=10, inner_opt_class=None, K=10, linsys_lr=1e-1, hypergrad_approx="CG_normaleq",
+                   **kwargs):
+        """Reference :1505-1585: the same implicit step as PSVI.hyper_step with alpha as a third hyper-parameter, but with
+        its own defaults (K = 10 solver iterations, linear-system step 1e-1) -- run_psvi calls it without arguments."""
+        return super().hyper_step(xbatch, ybatch, T=T, inner_opt_class=inner_opt_class, K=K, linsys_lr=linsys_lr,
+                                  hypergrad_approx=hypergrad_approx, **kwargs)
+
+
+def _no_hyper_for_fixed_u(self, *args, **kwargs):
+    # reference :1660-1740 / :1790-1883: the fixed-u variants solve the linear system with an ADAM fixed-point map
+    # (hypergrad.DifferentiableAdam(step_size=linsys_lr), K = 20) whose Jacobian products are not Hessian-vector products of
+    # the inner objective; that solver is not built, and substituting the gradient-descent map would silently change the
+    # hypergradient
+    raise NotImplementedError(f"--trainer hyper is not built for {type(self).__name__} (Adam fixed-point map of the "
+                              "reference, psvi_classes.py:1660-1740); use --trainer nested")
+
 
 class PSVIFixedU(PSVILearnV):
     r"""Fixed coreset locations, learnable weights (reference :1622-1740): the u update is skipped."""
+
+    hyper_step = _no_hyper_for_fixed_u
 
     def _step_outer_optimisers(self):
         self.u.grad = None
@@ -891,6 +940,8 @@ class PSVIFixedU(PSVILearnV):
 
 class PSVIAFixedU(PSVIAV):
     r"""Fixed locations, learnable weights and evidence scale (reference :1743-1883)."""
+
+    hyper_step = _no_hyper_for_fixed_u
 
     def _step_outer_optimisers(self):
         self.u.grad = None

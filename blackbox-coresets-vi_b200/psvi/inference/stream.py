@@ -492,4 +492,14 @@ class StreamEngine:
             self.net.predict(theta, lw, mode, xt[r0:r0 + batch].contiguous(), yt32[r0:r0 + batch].contiguous(), out)
             tot[:3] += out[:3]
             tot[3:5] = out[3:5]
+            if mode != 0 and r0 + batch >= n and u is not None and u.shape[0] > 0:
+                # correction=False still reports the importance-weight diagnostics of the LAST batch (reference
+                # psvi_classes.py:1047-1057,1085-1092: the weights are computed regardless of `correction`)
+                M = u.shape[0]
+                nll = torch.empty(S, M, device=dev)
+                self.net.pass_(theta, None, u, z32, None, nll=nll)
+                lwl = (nll.double() @ a.double()) + self.fam.nkl(phi, eps_slabs[k], theta)
+                w = torch.softmax(lwl, 0)
+                tot[3] = -(w * torch.log(w.clamp_min(1e-300))).sum().float()
+                tot[4] = (w.sum() ** 2 / (w * w).sum() / S).float()
         return tot

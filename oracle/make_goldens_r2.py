@@ -1,0 +1,187 @@
+"""Round-2 goldens from the UNMODIFIED reference (TEST INFRASTRUCTURE ONLY; run in the build container:
+python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (oracle/make_goldens.py):
+
+  variant_<cls>.npz      one nested_step of PSVIAV / PSVIAFixedU / PSVIFixedU / PSVIFreeV / PSVI_No_Rescaling
+                         (psvi/inference/psvi_classes.py:1363-1385,1475-1883) in fp64: loss, hypergradients on u, v and
+                         alpha, fast weights after copy-back, u / v / alpha after their Adam steps
+  logreg_hm_m10_t100.npz BASELINE configs[0] at its own T = 100 (the first set pins it at T = 8)
+  mfvi_hm.npz            run_mfvi (baselines.py:824-920) trace with full-batch steps (the shuffled loader then only permutes
+                         the rows of a sum)
+  fixedpoint_fn_hm.npz   PSVI.hyper_step with hypergrad_approx="fixed_point" (hypergradients.py:83-140)
+
+Noise is injected through oracle.ref_import.NoiseFeeder (fixtures store the seed only).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference, NoiseFeeder  # noqa: E402
+
+import_reference()
+import torch  # noqa: E402
+import psvi.inference.psvi_classes as rc  # noqa: E402
+from psvi.inference.baselines import run_mfvi  # noqa: E402
+
+from oracle.make_goldens import get_data, get_mu_rho, model_dims, run_case  # noqa: E402  (imports only; main() not run)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def run_variant(cls_name, H=30, M=10, S=5, T=4, B=32, init_sd=1e-2, lr0net=1e-3):
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, lr0alpha=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = getattr(rc, cls_name)(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(sum(ord(ch) for ch in cls_name))      # (deterministic: hash() is salted per process)
+    has_alpha = getattr(obj, "alpha", None) is not None
+    if cls_name in ("PSVIFreeV",):
+        v0 = (1.0 / M + 0.05 * rng.uniform(0, 1, M)).astype(np.float32)        # non-negative free weights
+    elif cls_name == "PSVI_No_Rescaling":
+        v0 = obj.v.detach().numpy().astype(np.float32).copy()                   # 1 / (M N), fixed
+    else:
+        v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(bool(obj.learn_v))
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    alpha0 = 0.0
+    if has_alpha:
+        alpha0 = 0.3
+        obj.alpha = torch.tensor([alpha0], dtype=tdt).requires_grad_(True)
+        obj.optim_alpha = torch.optim.Adam([obj.alpha], 1e-3)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    if obj.learn_v:
+        obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, lr0net=lr0net, noise_seed=1212, cls=cls_name, learn_v=int(obj.learn_v),
+               mu0=mu0, rho0=rho0, u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               alpha0=alpha0, xb=xb.numpy().copy(), yb=yb.numpy().copy())
+    with NoiseFeeder(dims, S, 1212) as nf, _quiet():
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_nested_gu"] = (obj.u.grad.numpy().copy() if obj.u.grad is not None else np.zeros_like(out["u0"]))
+        out["ref64_has_gu"] = int(obj.u.grad is not None)
+        if obj.learn_v:
+            out["ref64_nested_gv"] = obj.v.grad.numpy().copy()
+        if has_alpha:
+            out["ref64_nested_galpha"] = obj.alpha.grad.numpy().copy()
+            out["ref64_alpha_after"] = obj.alpha.detach().numpy().copy()
+        out["ref64_nested_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_nested_u_after"] = obj.u.detach().numpy().copy()
+        out["ref64_nested_v_after"] = obj.v.detach().numpy().copy()
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(GOLD, f"variant_{cls_name}.npz")
+    np.savez_compressed(pth, **out)
+    print(cls_name, "forwards", out["n_forwards"], "loss", out["ref64_nested_loss"], "|gu|", np.abs(out["ref64_nested_gu"]).max(),
+          "size", os.path.getsize(pth))
+
+
+def run_cfg1_t100():
+    c = dict(name="logreg_hm_m10_t100", dnm="halfmoon", arch="logistic_regression", H=0, n_layers=0, M=10, S=10, T=100, B=128,
+             init_sd=1e-3, lr0net=1e-3, cls="learn_v")
+    out32, r32 = run_case(c, "32")
+    out64, r64 = run_case(c, "64")
+    blob = dict(out32)
+    blob.update({"ref32_" + k: v for k, v in r32.items()})
+    blob.update({"ref64_" + k: v for k, v in r64.items()})
+    p = os.path.join(GOLD, c["name"] + ".npz")
+    np.savez_compressed(p, **blob)
+    print(c["name"], "forwards", out32["n_forwards"], "nested_loss32/64", r32["nested_loss"], r64["nested_loss"], "size",
+          os.path.getsize(p))
+
+
+def run_mfvi_full():
+    """run_mfvi with data_minibatch = N (every step sees all rows; the loader's shuffle permutes a sum)."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    S, H = 6, 24
+    import random
+    random.seed(5), np.random.seed(5), torch.manual_seed(5)
+    from psvi.experiments.experiments_utils import set_up_model
+    net0 = set_up_model(architecture="fn", D=D, n_hidden=H, nc=nc, mc_samples=S, init_sd=1e-3)
+    mu0, rho0 = get_mu_rho(net0)
+    dims = model_dims(net0)
+    with NoiseFeeder(dims, S, 2323) as nf, _quiet():
+        res = run_mfvi(xt=xt, yt=yt, mc_samples=S, data_minibatch=N, num_epochs=3, log_every=2, N=N, D=D, lr0net=1e-3, seed=5,
+                       architecture="fn", n_hidden=H, nc=nc, train_dataset=tr, test_dataset=te, init_sd=1e-3)
+        nfw = len(nf.history)
+    blob = dict(dims=np.array(dims), N=N, S=S, noise_seed=2323, n_forwards=nfw, lr0net=1e-3, mu0=mu0, rho0=rho0,
+                ref_elbos=np.array(res["elbos"]), ref_accs=np.array(res["accs"]), ref_nlls=np.array(res["nlls"]))
+    p = os.path.join(GOLD, "mfvi_hm.npz")
+    np.savez_compressed(p, **blob)
+    print("mfvi_hm", "forwards", nfw, blob["ref_elbos"], blob["ref_accs"], blob["ref_nlls"])
+
+
+def run_fixed_point(name="fixedpoint_fn_hm", H=20, M=10, S=6, T=6, B=64, K=4, init_sd=1e-2, lr0net=1e-3):
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="hyper", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = rc.PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(6)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, K=K, lr0net=lr0net, linsys_lr=1e-2, noise_seed=4343, vmode=1,
+               mu0=mu0, rho0=rho0, u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy())
+    with NoiseFeeder(dims, S, 4343) as nf, _quiet():
+        ll = obj.hyper_step(xb, yb, K=K, linsys_lr=1e-2, hypergrad_approx="fixed_point")
+        out["ref64_ll"] = ll
+        out["ref64_gu"], out["ref64_gv"] = obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy()
+        out["ref64_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_u_after"], out["ref64_v_after"] = obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy()
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards"], "ll", ll, "|gu|", np.abs(out["ref64_gu"]).max(), "size", os.path.getsize(pth))
+
+
+def main():
+    for cls_name in ("PSVIAV", "PSVIAFixedU", "PSVIFixedU", "PSVIFreeV", "PSVI_No_Rescaling"):
+        run_variant(cls_name)
+    run_fixed_point()
+    run_mfvi_full()
+    run_cfg1_t100()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+"""GPU parity tests that close the round-1 holes: the remaining PSVI variants, the fixed-point implicit solver, run_mfvi,
+BASELINE configs[0] at its own T = 100 (through the generic CASES of the other test files), the tensor-core full-data
+passes at the exact cfg5 shape, and "same seed => same initial weights and pseudo-data as the reference".
+Goldens: tests/golden/variant_*.npz, fixedpoint_fn_hm.npz, mfvi_hm.npz (oracle/make_goldens_r2.py, unmodified reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import psvi_oracle as po
+from tests.gpu_util import GOLDEN, dev, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _halfmoon():
+    from psvi.experiments.experiments_utils import read_dataset
+    torch.manual_seed(0)
+    return read_dataset("halfmoon", {"test_ratio": 0.2})
+
+
+@pytest.mark.parametrize("cls_name", ["PSVIAV", "PSVIAFixedU", "PSVIFixedU", "PSVIFreeV", "PSVI_No_Rescaling"])
+def test_variant_nested_step_matches_reference(cls_name):
+    """One nested_step of every remaining PSVI variant (reference psvi_classes.py:1363-1385,1475-1883) against the reference's
+    fp64 run: hypergradients on u, v and alpha (vmode 2: f = exp(alpha) softmax), which optimisers step, the clamp of the
+    free weights.  Tolerances as for PSVILearnV (rel-L2 1e-3 on hypergradients, 2e-4 on the loss)."""
+    from oracle.ref_import import NoiseFeeder
+    import psvi.inference.psvi_classes as pc
+    g = dict(np.load(os.path.join(GOLDEN, f"variant_{cls_name}.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, M, B = int(g["S"]), int(g["T"]), int(g["M"]), int(g["B"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    x, y, xt, yt, N, D, tr, te, nc = _halfmoon()
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10, lr0u=1e-4,
+              lr0net=float(g["lr0net"]), lr0v=1e-3, lr0alpha=1e-3, init_args="subsample", init_sd=1e-2, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=dims[1], n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, compute_weights_entropy=True, register_elbos=False, quiet=True)
+    obj = getattr(pc, cls_name)(**kw)
+    obj.run_psvi(**kw)
+    assert bool(obj.learn_v) == bool(int(g["learn_v"]))
+    mu, rho = obj.model.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    with torch.no_grad():
+        obj.u.copy_(torch.as_tensor(g["u0"]))
+        obj.v.copy_(torch.as_tensor(g["v0"]))
+        if obj.alpha is not None:
+            obj.alpha.fill_(float(g["alpha0"]))
+    obj.z = torch.as_tensor(g["z"]).float().cuda()
+    obj.scheduler_optim_net = None
+    obj.noise_source = pc.ExternalNoise(eps)
+    xb, yb = torch.as_tensor(g["xb"]).float().cuda(), torch.as_tensor(g["yb"]).cuda()
+    loss = obj.nested_step(xb, yb)
+    assert obj.noise_source.pos == int(g["n_forwards"])
+    assert abs(loss.item() - g["ref64_nested_loss"]) <= 2e-4 * abs(g["ref64_nested_loss"])
+    vec = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().cpu().numpy()
+    assert rel_l2(vec, g["ref64_nested_params"]) < 1e-5
+    if int(g["ref64_has_gu"]):
+        assert rel_l2(obj.u.grad.cpu().numpy(), g["ref64_nested_gu"]) < 1e-3
+    np.testing.assert_allclose(obj.u.detach().cpu().numpy(), g["ref64_nested_u_after"], atol=2e-6)   # fixed-u: unchanged
+    if int(g["learn_v"]):
+        assert rel_l2(obj.v.grad.cpu().numpy(), g["ref64_nested_gv"]) < 1e-3
+    np.testing.assert_allclose(obj.v.detach().cpu().numpy(), g["ref64_nested_v_after"], atol=2e-6)
+    if obj.alpha is not None:
+        np.testing.assert_allclose(obj.alpha.grad.cpu().numpy(), g["ref64_nested_galpha"], rtol=1e-3)
+        np.testing.assert_allclose(obj.alpha.detach().cpu().numpy(), g["ref64_alpha_after"], atol=2e-6)
+
+
+def test_fixed_point_hyper_step_matches_reference():
+    """--trainer hyper with hypergrad_approx="fixed_point" (reference hypergradients.py:83-140, stochastic=True: a fresh noise
+    draw per iteration); fp64 reference, same number of forwards."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.inference.psvi_classes import ExternalNoise, PSVILearnV
+    g = dict(np.load(os.path.join(GOLDEN, "fixedpoint_fn_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, M, B, K = int(g["S"]), int(g["T"]), int(g["M"]), int(g["B"]), int(g["K"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    x, y, xt, yt, N, D, tr, te, nc = _halfmoon()
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="hyper", log_every=10, lr0u=1e-4,
+              lr0net=float(g["lr0net"]), lr0v=1e-3, init_args="subsample", init_sd=1e-2, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=dims[1], n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, compute_weights_entropy=True, register_elbos=False, quiet=True)
+    obj = PSVILearnV(**kw)
+    obj.run_psvi(**kw)
+    mu, rho = obj.model.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    with torch.no_grad():
+        obj.u.copy_(torch.as_tensor(g["u0"]))
+        obj.v.copy_(torch.as_tensor(g["v0"]))
+    obj.z = torch.as_tensor(g["z"]).float().cuda()
+    obj.scheduler_optim_net = None
+    obj.noise_source = ExternalNoise(eps)
+    xb, yb = torch.as_tensor(g["xb"]).float().cuda(), torch.as_tensor(g["yb"]).cuda()
+    ll = obj.hyper_step(xb, yb, K=K, linsys_lr=float(g["linsys_lr"]), hypergrad_approx="fixed_point")
+    assert obj.noise_source.pos == int(g["n_forwards"])
+    assert abs(ll - g["ref64_ll"]) <= 2e-4 * abs(g["ref64_ll"])
+    assert rel_l2(obj.u.grad.cpu().numpy(), g["ref64_gu"]) < 2e-3
+    assert rel_l2(obj.v.grad.cpu().numpy(), g["ref64_gv"]) < 2e-3
+    vec = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().cpu().numpy()
+    assert rel_l2(vec, g["ref64_params"]) < 1e-5
+
+
+def test_run_mfvi_matches_reference_trace():
+    """run_mfvi (reference baselines.py:824-920) with full-batch steps: ELBO trace, accuracies and NLLs."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.inference.baselines import run_mfvi
+    from psvi.inference.psvi_classes import ExternalNoise
+    g = dict(np.load(os.path.join(GOLDEN, "mfvi_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S = int(g["S"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    x, y, xt, yt, N, D, tr, te, nc = _halfmoon()
+    res = run_mfvi(xt=xt, yt=yt, mc_samples=S, data_minibatch=N, num_epochs=3, log_every=2, N=N, D=D, lr0net=1e-3, seed=5,
+                   architecture="fn", n_hidden=dims[1], nc=nc, train_dataset=tr, test_dataset=te, init_sd=1e-3,
+                   noise_source=ExternalNoise(eps), quiet=True)
+    np.testing.assert_allclose(res["elbos"], g["ref_elbos"], rtol=5e-5)
+    np.testing.assert_allclose(res["accs"], g["ref_accs"], atol=1e-6)
+    np.testing.assert_allclose(res["nlls"], g["ref_nlls"], rtol=5e-5)
+    assert res["csizes"] is None
+
+
+def test_same_seed_gives_the_reference_initial_state():
+    """the boundary classes consume the CPU generator in the reference's order, so a fresh
+    PSVILearnV(seed=0) holds the reference's initial weights and pseudo-data -- nothing injected here."""
+    from psvi.inference.psvi_classes import PSVILearnV
+    g = dict(np.load(os.path.join(GOLDEN, "fn_hm_m50_t10.npz")))
+    dims = [int(d) for d in g["dims"]]
+    x, y, xt, yt, N, D, tr, te, nc = _halfmoon()
+    kw = dict(mc_samples=int(g["S"]), num_epochs=0, data_minibatch=int(g["B"]), D=D, N=N, inner_it=int(g["T"]), trainer="nested",
+              log_every=10, lr0u=1e-4, lr0net=float(g["lr0net"]), lr0v=1e-3, init_args="subsample", init_sd=1e-3,
+              num_pseudo=int(g["M"]), seed=0, architecture="fn", n_hidden=dims[1], n_layers=1, logistic_regression=False,
+              train_dataset=tr, test_dataset=te, dnm="halfmoon", nc=nc, compute_weights_entropy=True, register_elbos=True,
+              quiet=True)
+    obj = PSVILearnV(**kw)
+    obj.run_psvi(**kw)
+    mu, rho = obj.model.flat()
+    np.testing.assert_allclose(mu.cpu().numpy(), g["mu0"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(rho.cpu().numpy(), g["rho0"], rtol=1e-6)
+    np.testing.assert_allclose(obj.u.detach().cpu().numpy(), g["u0"], rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(obj.z.cpu().numpy(), g["z"])
+
+
+def test_fn_tc_forward_at_the_exact_cfg5_shape():
+    """psvi_fn_nll_tc at BASELINE configs[4]'s exact shape (D=256, H=1024, C=10, S=64) over 300 rows, against the oracle on
+    the same bf16-rounded operands (the first set stops at S=16 for H=1024)."""
+    from psvi import _native as nat
+    D, H, C, S, R = 256, 1024, 10, 64, 300
+    rng = np.random.default_rng(64)
+    dims = [D, H, C]
+    P = po.p_theta(dims)
+    mu = np.concatenate([rng.standard_normal(H * D) / np.sqrt(D), np.zeros(H), rng.standard_normal(C * H) / np.sqrt(H),
+                         np.zeros(C)]).astype(np.float32)
+    rho = np.full(P, po.inverse_softplus(0.02), np.float32)
+    eps = rng.standard_normal((1, S, P)).astype(np.float32)
+    X, y = rng.standard_normal((R, D)).astype(np.float32), rng.integers(0, C, R)
+    bf = lambda a: torch.as_tensor(np.asarray(a, np.float32)).bfloat16().double().numpy()  # noqa: E731
+    m = nat.make_model(dims, S)
+    wsum, nkl, nll = torch.zeros(S, device="cuda"), torch.zeros(S, device="cuda"), torch.zeros(S, R, device="cuda")
+    scr = torch.zeros(nat.fn_tc_scratch_floats(m, R, 0), device="cuda")
+    nat.fn_nll_tc(m, nat.make_noise(dev(eps)), dev(mu), dev(rho), dev(X).bfloat16().contiguous(), dev(y, torch.int32), None, 0,
+                  wsum, nkl, nll, scr)
+    torch.cuda.synchronize()
+    th = po.mf_sample(mu.astype(np.float64), rho.astype(np.float64), eps[0].astype(np.float64))
+    W1 = bf(th[:, :H * D]).reshape(S, H, D)
+    W2 = bf(th[:, H * D + H:H * D + H + C * H]).reshape(S, C, H)
+    hid = bf(np.maximum(np.einsum("rd,shd->srh", bf(X), W1).astype(np.float32) + th[:, None, H * D:H * D + H], 0))
+    ref = po.nll_rows(np.einsum("srh,sch->src", hid, W2) + th[:, None, H * D + H + C * H:], y)[0]
+    got = nll.cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-2 and rel_l2(got, ref) < 2e-3
+    np.testing.assert_allclose(wsum.cpu().numpy(), ref.sum(1), rtol=2e-3)

@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid")))
+               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint")))
 
 
 def rel_l2(a, b):
@@ -182,3 +182,35 @@ def test_ablated_outer_objective_matches_reference(name):
     assert rel_l2(r["phi_T"], g["ref64_nested_params"]) < 1e-9
     assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-6
     assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-6
+
+
+VARIANTS = {"PSVIAV": 2, "PSVIAFixedU": 2, "PSVIFixedU": 1, "PSVIFreeV": 0, "PSVI_No_Rescaling": 0}
+
+
+@pytest.mark.parametrize("cls", sorted(VARIANTS))
+def test_variant_nested_step_matches_reference(cls):
+    """The remaining PSVI variants (reference psvi_classes.py:1363-1385,1475-1883) through the oracle's nested_step: f = identity
+    / softmax / exp(alpha) softmax, with and without updates of u.  Goldens: oracle/make_goldens_r2.py."""
+    from oracle.ref_import import NoiseFeeder
+    g = dict(np.load(os.path.join(GOLDEN, f"variant_{cls}.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, N, vmode = int(g["S"]), int(g["T"]), float(g["N"]), VARIANTS[cls]
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    r = po.nested_step(g["mu0"], g["rho0"], np.stack(eps[:T]), eps[T], g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N, dims,
+                       float(g["lr0net"]), vmode=vmode, alpha=float(g["alpha0"]))
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-9 * abs(r["loss"])
+    assert rel_l2(po.mu_rho_to_phi(r["mu_T"], r["rho_T"], dims), g["ref64_nested_params"]) < 1e-10
+    if int(g["ref64_has_gu"]):
+        assert rel_l2(r["u_grad"], g["ref64_nested_gu"]) < 1e-7
+        u1, _, _ = po.torch_adam_step(g["u0"], r["u_grad"], 0 * g["u0"], 0 * g["u0"], 1, 1e-4)
+        np.testing.assert_allclose(u1, g["ref64_nested_u_after"], rtol=0, atol=1e-9)
+    else:   # fixed-u variants never touch u
+        np.testing.assert_array_equal(g["ref64_nested_u_after"], g["u0"])
+    if int(g["learn_v"]):
+        assert rel_l2(r["v_grad"], g["ref64_nested_gv"]) < 1e-7
+        v1, _, _ = po.torch_adam_step(g["v0"], r["v_grad"], 0 * g["v0"], 0 * g["v0"], 1, 1e-3)
+        if cls == "PSVIFreeV":
+            v1 = np.maximum(v1, 0.0)     # clamp of the non-parameterised weights (psvi_classes.py:587-591)
+        np.testing.assert_allclose(v1, g["ref64_nested_v_after"], rtol=0, atol=1e-9)
+    if vmode == 2:
+        np.testing.assert_allclose(r["alpha_grad"], g["ref64_nested_galpha"][0], rtol=1e-7)
