@@ -108,7 +108,8 @@ class PSVI(object):
         self.elbos = []
         self.num_pseudo, self.mc_samples = (num_pseudo if not increment else increment_sizes[0]), mc_samples
         self.reset, self.reset_interval, self.learn_v, self.learn_z = reset, reset_interval, learn_v, learn_z
-        for flag, name in ((learn_z, "learn_z"), (increment, "increment"), (scoring_run, "scoring_run")):
+        self.increment_interval, self.increment_sizes = increment_interval, increment_sizes
+        for flag, name in ((learn_z, "learn_z"), (scoring_run, "scoring_run")):
             if flag:
                 raise NotImplementedError(f"{name}=True is outside the hot path built so far (SURVEY.md section 8f)")
         with torch.no_grad():
@@ -603,10 +604,16 @@ class PSVI(object):
             self._dev_data[key] = c
         return c[1], c[2]
 
+    def _train_ds(self):
+        return getattr(self, "_active_train", None) or self.train_dataset
+
+    def _test_ds(self):
+        return getattr(self, "_active_test", None) or self.test_dataset
+
     def _next_minibatch(self):
         """`next(iter(train_loader))` of the reference (:895): a fresh uniformly random batch of min(B, N) rows every
-        outer step -- gathered on the device from the resident copy of the training set."""
-        x, y = self._device_dataset(self.train_dataset, "train")
+        outer step -- gathered on the device from the resident copy of the (current) training set."""
+        x, y = self._device_dataset(self._train_ds(), "train")
         n = x.shape[0]
         if int(self.data_minibatch) >= n:      # full batch: the data term is a sum over all rows, their order is immaterial
             return x, y
@@ -630,6 +637,16 @@ class PSVI(object):
         scheduler_kwargs = {"step_size": epoch_quarter if epoch_quarter > 0 else 10000, "gamma": self.gamma}
         self.train_loader = DataLoader(self.train_dataset, batch_size=self.data_minibatch, shuffle=True)
         self.test_loader = DataLoader(self.test_dataset, batch_size=self.data_minibatch, shuffle=False)
+        if self.increment:
+            # incremental learning (reference :823-832): start with classes {0, 1}; each later task adds one class
+            self.incremental_train_datasets = [self.train_dataset.subset_where(cs=list(range(c + 1)) if c == 1 else [c])
+                                               for c in range(1, self.nc)]
+            self.incremental_test_datasets = [self.test_dataset.subset_where(cs=list(range(c + 1))) for c in range(1, self.nc)]
+            self._active_train, self._active_test = self.incremental_train_datasets[0], self.incremental_test_datasets[0]
+            self.train_loader = DataLoader(self._active_train, batch_size=self.data_minibatch, shuffle=True)
+            self.test_loader = DataLoader(self._active_test, batch_size=self.data_minibatch, shuffle=False)
+            self.train_data_so_far = len(self._active_train)
+            self.nc = 2
         self.set_up_model()
         nlls_psvi, accs_psvi, core_idcs_psvi, iws_entropy, nesses, vs_entropy, us, zs, vs, grid_preds, times = (
             [], [], [], [], [], [], [], [], [], [], [0])
@@ -681,6 +698,22 @@ class PSVI(object):
                 self.prune_coreset(to_size=self.prune_sizes[prune_idx], lr0v=lr0v, lr0net=lr0net)
                 prune_idx += 1
                 self.weight_reset()
+            # add a new learning task and grow the coreset to fit it (reference :945-966)
+            if (self.increment and it > 0 and it % self.increment_interval == 0
+                    and increment_idx < len(self.increment_sizes) - 1):
+                increment_idx += 1
+                samples = torch.multinomial(self.f(self.v.detach(), 0), self.train_data_so_far, replacement=True)
+                self.nc += 1
+                self.set_up_model()          # the model is re-initialised with one more class
+                self.increment_coreset(to_size=self.increment_sizes[increment_idx], lr0v=lr0v, lr0u=lr0u, lr0net=lr0net,
+                                       new_class=increment_idx + 1, increment_idx=increment_idx)
+                self._active_train = self.incremental_train_datasets[increment_idx].concatenate(
+                    self.u.detach()[samples].cpu().clone(), self.z.detach()[samples].cpu().clone().to(
+                        self.incremental_train_datasets[increment_idx].targets.dtype))
+                self._active_test = self.incremental_test_datasets[increment_idx]
+                self.train_loader = DataLoader(self._active_train, batch_size=self.data_minibatch, shuffle=True)
+                self.test_loader = DataLoader(self._active_test, batch_size=self.data_minibatch, shuffle=False)
+                self.train_data_so_far = len(self._active_train)
         # retrain the model on the extracted coreset only, for the same number of epochs (reference :969-997)
         if self.retrain_on_coreset:
             if not isinstance(self.model, MeanFieldMLP):
@@ -728,7 +761,7 @@ class PSVI(object):
         Returns (acc, nll, iw_entropy, ness, v_entropy) as 0-dim tensors."""
         assert self.mc_samples > 1
         model, desc, S = self._model_desc()
-        xt, yt = self._device_dataset(self.test_dataset, "test")
+        xt, yt = self._device_dataset(self._test_ds(), "test")
         large_fn = isinstance(model, MeanFieldMLP) and not isinstance(model, MeanFieldLeNet) and self._is_large_fn(model)
         if large_fn:
             self._ws[("force_stream", id(model))] = True
@@ -854,6 +887,27 @@ class PSVI(object):
         self.optim_u = torch.optim.Adam([self.u], self.optim_u.param_groups[0]["lr"])
         self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
 
+    def increment_coreset(self, to_size, lr0v=1e-3, lr0u=1e-3, lr0net=1e-4, variance=1.0, new_class=2, increment_idx=1):
+        """Grow the coreset to `to_size` points for a new learning task (reference :1194-1217): the new points get the mean
+        weight of the old ones and come from the new task's data (or from the noisy empirical mean with init_args="random")."""
+        n_old = len(self.v)
+        self.num_pseudo, extra = to_size, to_size - n_old
+        with torch.no_grad():
+            vv = self.v.detach()
+            self.v = torch.cat((vv, 1.0 / (n_old + extra) * vv.sum() * torch.ones(extra, device=self.device)))
+        self.v = self.v.detach().requires_grad_(True)
+        self.optim_v = torch.optim.Adam([self.v], lr0v)
+        if self.init_args == "random":
+            new_us = (compute_empirical_mean(self.train_loader) + variance * torch.randn(extra, self.D)).clone()
+            new_zs = new_class * torch.ones(extra)
+        else:
+            ds = self.incremental_train_datasets[increment_idx]
+            new_us, new_zs = ds[torch.randperm(len(ds))[:extra]]
+        self.u = torch.cat((self.u.detach(), new_us.to(self.device).float())).detach().requires_grad_(True)
+        self.z = torch.cat((self.z, new_zs.to(self.device).to(self.z.dtype)))
+        self.optim_u = torch.optim.Adam([self.u], lr0u)
+        self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
+
     def _retrain_step(self, opt, params):
         """One Adam step of the model on inner_elbo over the (fixed) coreset (reference :994-997)."""
         self.inner_elbo(model=self.model)
@@ -909,6 +963,10 @@ class PSVIAV(PSVILearnV):
     def evaluate(self, **kwargs):
         self.results["alpha"].append(self.alpha.clone().cpu().detach().numpy())
         return super().evaluate(**kwargs)
+
+    def increment_coreset(self, lr0alpha=1e-3, **kwargs):
+        super().increment_coreset(**kwargs)          # reference :1501-1503
+        self.optim_alpha = torch.optim.Adam([self.alpha], lr0alpha)
 
     def hyper_step(self, xbatch, ybatch, T=10, inner_opt_class=None, K=10, linsys_lr=1e-1, hypergrad_approx="CG_normaleq",
                    **kwargs):

@@ -168,3 +168,25 @@ def test_fn_tc_forward_at_the_exact_cfg5_shape():
     got = nll.cpu().numpy()
     assert np.abs(got - ref).max() < 1e-2 and rel_l2(got, ref) < 2e-3
     np.testing.assert_allclose(wsum.cpu().numpy(), ref.sum(1), rtol=2e-3)
+
+
+def test_incremental_learning_grows_coreset_and_classes():
+    """increment=True (reference psvi_classes.py:823-832,945-966,1194-1217): start with two classes, add one class and a block
+    of coreset points every `increment_interval` outer steps; the model is rebuilt with one more output each time."""
+    from psvi.experiments.experiments_utils import read_dataset
+    from psvi.inference.psvi_classes import PSVILearnV
+    torch.manual_seed(0)
+    x, y, xt, yt, N, D, tr, te, nc = read_dataset("four_blobs", {"test_ratio": 0.2})
+    assert nc == 4
+    kw = dict(mc_samples=6, num_epochs=13, data_minibatch=64, D=D, N=N, inner_it=5, trainer="nested", log_every=2, lr0u=1e-3,
+              lr0net=1e-2, lr0v=1e-2, init_args="subsample", init_sd=1e-3, num_pseudo=8, seed=0, architecture="fn", n_hidden=30,
+              n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te, dnm="four_blobs", nc=nc,
+              increment=True, increment_interval=4, increment_sizes=[8, 12, 16], compute_weights_entropy=True,
+              register_elbos=False, quiet=True)
+    obj = PSVILearnV(**kw)
+    res = obj.run_psvi(**kw)
+    assert res["csizes"][0] == 8 and res["csizes"][-1] == 16 and sorted(set(res["csizes"])) == [8, 12, 16]
+    assert obj.nc == 4 and obj.model.dims[-1] == 4
+    assert obj.u.shape == (16, D) and obj.v.shape == (16,) and obj.z.shape == (16,)
+    assert set(obj.z.cpu().numpy().astype(int).tolist()) <= {0, 1, 2, 3} and 3 in set(obj.z.cpu().numpy().astype(int).tolist())
+    assert all(np.isfinite(res["nlls"])) and all(0.0 <= a <= 1.0 for a in res["accs"])
