@@ -16,7 +16,7 @@ import torch
 from psvi import _native
 from psvi.experiments.experiments_utils import set_up_model
 from psvi.inference.utils import pseudo_rand_init, pseudo_subsample_init
-from psvi.models.neural_net import MeanFieldMLP, categorical_fn
+from psvi.models.neural_net import FullCovMLP, MeanFieldLeNet, MeanFieldMLP, categorical_fn
 
 
 def _not_built(name, where):
@@ -79,6 +79,68 @@ class _Trainer:
         return (o[1] / o[2]).item(), (o[0] / o[2]).item()
 
 
+class _StreamTrainer:
+    """The same fit for the model families without a flat (mu, rho) cluster-engine form -- fn2 (full covariance) and lenet --
+    through the streaming engine's per-sample network kernels (psvi/inference/stream.py), torch.optim.Adam arithmetic on the
+    flat variational vector.  Quirk Q5 (reference baselines.py:1027): the KL sum filters on VILinear only, so fn2 trains
+    WITHOUT a KL term and lenet's conv layers contribute none."""
+
+    def __init__(self, net, seed, noise_source=None):
+        from psvi.inference.stream import FullCovFamily, LenetFamily, LenetNet, StreamEngine
+        _native.require_cuda()
+        net.check_supported()
+        S = net.n_samples()
+        if isinstance(net, MeanFieldLeNet):
+            self.eng, self.kl_coef = StreamEngine(LenetFamily(net), net.dims, S, net=LenetNet(S)), 1.0
+        else:
+            self.eng, self.kl_coef = StreamEngine(FullCovFamily(net), net.dims, S), 0.0
+        self.net, self.seed, self.noise_source, self.domain, self.S = net, seed, noise_source, 0, S
+        self.device = next(net.parameters()).device
+        self.phi = self.eng.fam.get_phi().clone().contiguous()
+        self.m, self.v, self.steps = torch.zeros_like(self.phi), torch.zeros_like(self.phi), 0
+
+    def _eps(self, n):
+        if self.noise_source is not None:
+            return self.noise_source.take(n, self.device)
+        self.domain += 1
+        eps = torch.empty(n, self.S, self.eng.Pt, device=self.device)
+        _native.philox_normal(self.seed, self.domain, 0, n, self.S, self.eng.Pt, eps)
+        return eps
+
+    def train(self, x, y32, scale, T, lr):
+        eng, fam, M = self.eng, self.eng.fam, x.shape[0]
+        cw = torch.full((self.S, M), float(scale), device=self.device)
+        eps_all = fam.fix_eps(self._eps(T))
+        losses = torch.zeros(T, device=self.device)
+        for t in range(T):
+            theta = fam.sample(self.phi, eps_all[t])
+            nll, tbar = torch.empty(self.S, M, device=self.device), torch.empty(self.S, eng.Pt, device=self.device)
+            eng.net.pass_(theta, None, x, y32, cw, nll=nll, tbar=tbar)
+            losses[t] = (float(scale) * nll.double().sum() + self.kl_coef * fam.kl(self.phi).double()).float()
+            g = fam.grad(self.phi, eps_all[t], tbar, self.kl_coef, 0.0)
+            self.steps += 1
+            self.m = 0.9 * self.m + (1.0 - 0.9) * g
+            self.v = 0.999 * self.v + (1.0 - 0.999) * g * g
+            den = self.v.sqrt() / (1.0 - 0.999 ** self.steps) ** 0.5 + 1e-8
+            self.phi = self.phi - (lr / (1.0 - 0.9 ** self.steps)) * self.m / den
+        fam.set_phi(self.phi)
+        return losses
+
+    def test(self, xt, yt32, batch):
+        n = xt.shape[0]
+        out = self.eng.evaluate(self.phi, self._eps(-(-n // batch)), None, None, None, xt, yt32, batch, mode=2)
+        o = out.cpu()
+        return (o[1] / o[2]).item(), (o[0] / o[2]).item()
+
+
+def _make_trainer(net, seed, noise_source):
+    if isinstance(net, MeanFieldMLP) and not isinstance(net, MeanFieldLeNet):
+        return _Trainer(net, seed, noise_source)
+    if isinstance(net, (FullCovMLP, MeanFieldLeNet)):
+        return _StreamTrainer(net, seed, noise_source)
+    raise NotImplementedError(f"no CUDA path for {type(net).__name__}")
+
+
 def run_mfvi_subset(x=None, y=None, xt=None, yt=None, mc_samples=4, data_minibatch=128, num_epochs=100, log_every=10,
                     D=None, lr0net=1e-3, mul_fact=2, seed=0, distr_fn=categorical_fn, log_pseudodata=False,
                     train_dataset=None, test_dataset=None, num_pseudo=100, init_args="subsample", architecture=None,
@@ -90,13 +152,14 @@ def run_mfvi_subset(x=None, y=None, xt=None, yt=None, mc_samples=4, data_minibat
     t_start = time.time()
     net = set_up_model(architecture=architecture, D=D, n_hidden=n_hidden, nc=nc, mc_samples=mc_samples,
                        init_sd=init_sd).to(device)
-    if dnm == "MNIST":
-        raise NotImplementedError("vision datasets are out of scope (no network; SURVEY.md section 2 row 9)")
+    if dnm == "MNIST" and not torch.is_tensor(x):
+        raise NotImplementedError("vision datasets need a download (no network; SURVEY.md section 2 row 9): pass the images "
+                                  "as tensors x [N, 784] / y [N]")
     xbatch, ybatch = (pseudo_rand_init(x, y, num_pseudo=num_pseudo, seed=seed, nc=nc) if init_args == "random"
                       else pseudo_subsample_init(x, y, num_pseudo=num_pseudo, seed=seed, nc=nc))
     n_train = len(train_dataset)
-    tr = _Trainer(net, seed, noise_source)
-    xs = xbatch.detach().to(device, torch.float32).contiguous()
+    tr = _make_trainer(net, seed, noise_source)
+    xs = xbatch.detach().to(device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
     ys = ybatch.detach().to(device).to(torch.int32).contiguous()
     xtd = torch.as_tensor(test_dataset.data).to(device, torch.float32).reshape(len(test_dataset), -1).contiguous()
     ytd = torch.as_tensor(test_dataset.targets).to(device).to(torch.int32).contiguous()
@@ -135,7 +198,7 @@ def run_mfvi(xt=None, yt=None, mc_samples=4, data_minibatch=128, num_epochs=100,
     t_start = time.time()
     net = set_up_model(architecture=architecture, D=D, n_hidden=n_hidden, nc=nc, mc_samples=mc_samples,
                        init_sd=init_sd).to(device)
-    tr = _Trainer(net, seed, noise_source)
+    tr = _make_trainer(net, seed, noise_source)
     xd = torch.as_tensor(train_dataset.data).to(device, torch.float32).reshape(len(train_dataset), -1).contiguous()
     yd = torch.as_tensor(train_dataset.targets).to(device).to(torch.int32).contiguous()
     xtd = torch.as_tensor(test_dataset.data).to(device, torch.float32).reshape(len(test_dataset), -1).contiguous()
