@@ -81,14 +81,18 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
   uint64_t* abfull = bars + 10;     // epi-2 done (8 warps)
   uint64_t* accfull = bars + 11;    // last Gw1 of the unit done
   uint64_t* accempty = bars + 12;   // epilogue has flushed ACC (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* pread = bars + 13;      // epilogue has read the Gw2 output out of P (4 warps): the next Ga may overwrite P
+  uint64_t* xck = bars + 14;        // [2][4] one per 64-column chunk of an X stage (chunk 0 also covers the seeds block): Ga
+                                    // starts on the first chunk while the others are still in flight
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(w1full, 1); mbar_init(w1empty, 1); mbar_init(w2ready, 8);
     for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
     mbar_init(afull, 1); mbar_init(hfull, 8); mbar_init(qfull, 1); mbar_init(abfull, 8);
-    mbar_init(accfull, 1); mbar_init(accempty, 8);
+    mbar_init(accfull, 1); mbar_init(accempty, 8); mbar_init(pread, 4);
+    for (int i = 0; i < 8; ++i) mbar_init(&xck[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -115,9 +119,11 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         const int st = xi & 1;
         mbar_wait(&xempty[st], ((xi >> 1) & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&xfull[st], (uint32_t)(XS + OB_BYTES));
-          for (int k = 0; k < p.kc; ++k) tma_load_2d(&map_x, &xfull[st], sX + st * XS + k * KCH_BYTES, k * BK, t * BM);
-          bulk_load_1d(sO + st * OB_BYTES, p.obar + ((size_t)gu.s * p.n_tiles + t) * 2048, OB_BYTES, &xfull[st]);
+          for (int k = 0; k < p.kc; ++k) {
+            mbar_expect_tx(&xck[st * 4 + k], (uint32_t)(KCH_BYTES + (k == 0 ? OB_BYTES : 0)));
+            tma_load_2d(&map_x, &xck[st * 4 + k], sX + st * XS + k * KCH_BYTES, k * BK, t * BM);
+            if (k == 0) bulk_load_1d(sO + st * OB_BYTES, p.obar + ((size_t)gu.s * p.n_tiles + t) * 2048, OB_BYTES, &xck[st * 4]);
+          }
         }
         __syncwarp();
       }
@@ -129,27 +135,34 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
     const uint32_t id_w2 = base | ((uint32_t)(CW >> 3) << 17) | (1u << 16);                     // N = 16, B MN-major
     const uint32_t id_w1 = base | ((uint32_t)(p.D >> 3) << 17) | (1u << 16);                    // N = D, B MN-major
     const uint32_t tP = tmem_base + G_COL_P, tQ = tmem_base + G_COL_Q, tACC = tmem_base + G_COL_ACC;
+    // Issue order per unit (tcgen05 operations execute in issue order):
+    //   Ga(t0) | for every tile t:  Gab(t), Gw2(t) | Ga(t+1) | Gw1(t)
+    // so that the tensor pipe runs Ga(t+1) while the epilogue warps build abar(t), and Gw1(t) while they build h(t+1).
     int xi = 0, ui = 0;
+    auto issue_ga = [&](int xj) {      // Ga of the tile with running index xj: P[j, r] = sum_d W1[j, d] X[r, d]
+      const int st = xj & 1;
+      const uint32_t w0 = smem_u32(sW1), x0 = smem_u32(sX + st * XS);
+      for (int k = 0; k < p.kc; ++k) {
+        mbar_wait(&xck[st * 4 + k], (xj >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < BK / 16; ++jj)
+            umma_bf16(tP, make_desc_sw128(w0 + k * KCH_BYTES + jj * 32), make_desc_sw128(x0 + k * KCH_BYTES + jj * 32), id_a,
+                      (k | jj) ? 1u : 0u);
+          if (k == p.kc - 1) umma_commit(afull);
+        }
+        __syncwarp();
+      }
+    };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ui) {
       const GradUnit gu = p.units[u];
       mbar_wait(w1full, ui & 1);
       mbar_wait(w2ready, ui & 1);
+      issue_ga(xi);
       for (int t = gu.tile0; t < gu.tile1; ++t, ++xi) {
         const int st = xi & 1;
         const uint32_t x0 = smem_u32(sX + st * XS), o0 = smem_u32(sO + st * OB_BYTES);
-        mbar_wait(&xfull[st], (xi >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          // Ga: P[j, r] = sum_d W1[j, d] X[r, d]
-          const uint32_t w0 = smem_u32(sW1);
-          for (int k = 0; k < p.kc; ++k)
-#pragma unroll
-            for (int jj = 0; jj < BK / 16; ++jj)
-              umma_bf16(tP, make_desc_sw128(w0 + k * KCH_BYTES + jj * 32), make_desc_sw128(x0 + k * KCH_BYTES + jj * 32), id_a,
-                        (k | jj) ? 1u : 0u);
-          umma_commit(afull);
-        }
-        __syncwarp();
         mbar_wait(hfull, xi & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -164,6 +177,13 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
           umma_commit(qfull);
         }
         __syncwarp();
+        mbar_wait(pread, xi & 1);        // P' has been read: the next Ga (of this or of the next unit) may overwrite P
+        if (t + 1 < gu.tile1) {
+          issue_ga(xi + 1);
+        } else if (elect_one()) {
+          umma_commit(w1empty);          // every Ga of the unit has been issued: the next unit's W1 slice may load
+        }
+        __syncwarp();
         mbar_wait(abfull, xi & 1);
         if (t == gu.tile0) mbar_wait(accempty, (ui & 1) ^ 1);
         tc_fence_after();
@@ -175,7 +195,7 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             umma_bf16_ts(tACC, tQ + k8 * 8, make_desc(x0 + k8 * 2048, KCH_BYTES, 1024, 2), id_w1,
                          (t != gu.tile0 || k8) ? 1u : 0u);
           umma_commit(&xempty[st]);
-          if (t == gu.tile1 - 1) { umma_commit(accfull); umma_commit(w1empty); }
+          if (t == gu.tile1 - 1) umma_commit(accfull);
         }
         __syncwarp();
       }
@@ -242,6 +262,15 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
         // ---- epi-2: abar^T = mask ? Q : 0 -> bf16 pairs, in place; bias adjoint; W2bar contribution of the tile
         mbar_wait(qfull, xi & 1);
         tc_fence_after();
+        if (half == 0) {   // W2bar contribution of the tile first: it releases P for the next tile's Ga
+          float w[CW];
+          tmem_ld16(lane_addr + G_COL_P + 64, w);
+#pragma unroll
+          for (int c = 0; c < CW; ++c) w2acc[c] += w[c];
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pread);
+        }
         {
           float v[32];
           tmem_ld32(lane_addr + G_COL_Q + half * 64, v);
@@ -257,12 +286,6 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             const float a0 = ((m1 >> i) & 1u) ? v[i] : 0.f, a1 = ((m1 >> (i + 1)) & 1u) ? v[i + 1] : 0.f;
             bsum += a0 + a1;
             pk[16 + i / 2] = pack_bf16(a0, a1);
-          }
-          if (half == 0) {
-            float w[CW];
-            tmem_ld16(lane_addr + G_COL_P + 64, w);
-#pragma unroll
-            for (int c = 0; c < CW; ++c) w2acc[c] += w[c];
           }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
@@ -324,16 +347,19 @@ __global__ void fn_theta_prep_kernel(const float* theta, int S, int D, int H, in
     b2[s * CW + threadIdx.x] = threadIdx.x < C ? th[HD + H + (size_t)C * H + threadIdx.x] : -INFINITY;
 }
 
-// b2bar[s][c] = sum over the rows of the seeds (fixed-order block sums: deterministic); one block per sample
-__global__ void fn_b2bar_kernel(const __nv_bfloat16* obar, int n_tiles, int C, int P, int off_b2, float* tbar) {
+// b2bar[s][c] = sum over the rows of the seeds: block (chunk, s) sums its range of tiles in a fixed order into
+// partial[s][chunk][CW]; fn_b2bar_final_kernel adds the chunks in order (deterministic, no atomics)
+constexpr int B2_CHUNKS = 32;
+__global__ void fn_b2bar_kernel(const __nv_bfloat16* obar, int n_tiles, float* partial) {
   __shared__ float red[CW][256];
-  const int s = blockIdx.x;
+  const int s = blockIdx.y, ch = blockIdx.x;
+  const int t0 = (int)((long long)n_tiles * ch / B2_CHUNKS), t1 = (int)((long long)n_tiles * (ch + 1) / B2_CHUNKS);
   float acc[CW];
 #pragma unroll
   for (int c = 0; c < CW; ++c) acc[c] = 0.f;
   // element (r, c) of tile t at t * 2048 + (c / 8) * 1024 + r * 8 + (c % 8)   (bf16 elements)
-  const __nv_bfloat16* base = obar + (size_t)s * n_tiles * 2048;
-  for (size_t i = threadIdx.x; i < (size_t)n_tiles * 256; i += blockDim.x) {   // one 16-byte piece (8 classes of a row) each
+  const __nv_bfloat16* base = obar + ((size_t)s * n_tiles + t0) * 2048;
+  for (size_t i = threadIdx.x; i < (size_t)(t1 - t0) * 256; i += blockDim.x) {   // one 16-byte piece (8 classes of a row) each
     const size_t t = i >> 8, rem = i & 255, hsel = rem >> 7, r = rem & 127;
     const uint4 v = *reinterpret_cast<const uint4*>(base + t * 2048 + hsel * 1024 + r * 8);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -346,10 +372,18 @@ __global__ void fn_b2bar_kernel(const __nv_bfloat16* obar, int n_tiles, int C, i
 #pragma unroll
   for (int c = 0; c < CW; ++c) red[c][threadIdx.x] = acc[c];
   __syncthreads();
-  if (threadIdx.x < C) {
+  if (threadIdx.x < CW) {
     double t = 0.0;
     for (int i = 0; i < 256; ++i) t += (double)red[threadIdx.x][i];
-    tbar[(size_t)s * P + off_b2 + threadIdx.x] = (float)t;
+    partial[((size_t)s * B2_CHUNKS + ch) * CW + threadIdx.x] = (float)t;
+  }
+}
+__global__ void fn_b2bar_final_kernel(const float* partial, int C, int P, int off_b2, float* tbar) {
+  const int s = blockIdx.x, c = threadIdx.x;
+  if (c < C) {
+    double t = 0.0;
+    for (int ch = 0; ch < B2_CHUNKS; ++ch) t += (double)partial[((size_t)s * B2_CHUNKS + ch) * CW + c];
+    tbar[(size_t)s * P + off_b2 + c] = (float)t;
   }
 }
 
@@ -372,7 +406,8 @@ void carve_grad(const psvi_mf_model* model, int64_t rows, uint8_t* base, GradScr
   g.fs.W2b = reinterpret_cast<__nv_bfloat16*>(take(S * CW * H * 2));
   g.fs.b1 = reinterpret_cast<float*>(take(S * H * 4));
   g.fs.b2 = reinterpret_cast<float*>(take(S * CW * 4));
-  const size_t part_floats = tiles * 4 * S > 4096 ? tiles * 4 * S : 4096;
+  size_t part_floats = tiles * 4 * S > 4096 ? tiles * 4 * S : 4096;
+  if (part_floats < S * B2_CHUNKS * CW) part_floats = S * B2_CHUNKS * CW;   // (reused for the b2bar partials)
   g.fs.part = reinterpret_cast<float*>(take(part_floats * 4));
   g.fs.probs = reinterpret_cast<float*>(take(nsplit > 1 ? (size_t)nsplit * rows * CW * 4 : 256));
   g.obar = reinterpret_cast<__nv_bfloat16*>(take(S * tiles * OB_BYTES));
@@ -432,13 +467,16 @@ int data_grad(const psvi_mf_model* model, const float* theta, const void* x_bf16
   memset(&gp, 0, sizeof(gp));
   gp.n_rows = (int)n_rows; gp.n_tiles = tiles; gp.D = D; gp.kc = D / BK; gp.H = H; gp.S = S; gp.C = C; gp.P = P;
   gp.n_units = n_units; gp.units = g.units; gp.obar = g.obar; gp.W2b = g.fs.W2b; gp.b1 = g.fs.b1; gp.tbar = tbar;
-  const size_t smem = (size_t)3 * gp.kc * KCH_BYTES + 3 * OB_BYTES + 256 * 4 + 16 * 8 + 16 + 1024;
+  const size_t smem = (size_t)3 * gp.kc * KCH_BYTES + 3 * OB_BYTES + 256 * 4 + 24 * 8 + 16 + 1024;
   PSVI_REQUIRE(smem <= (size_t)smem_max, PSVI_ERR_UNSUPPORTED, "gradient kernel needs %zu B of shared memory", smem);
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_fn_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = n_units < sms ? n_units : sms;
   psvi_fn_grad_tc_kernel<<<grid, G_THREADS, smem, stream>>>(map_w1, map_x, gp);
   PSVI_CUDA_CHECK(cudaGetLastError());
-  fn_b2bar_kernel<<<S, 256, 0, stream>>>(g.obar, tiles, C, P, H * D + H + C * H, tbar);
+  // (the per-tile partials of pass 1 have been reduced by forward(): g.fs.part is free again)
+  fn_b2bar_kernel<<<dim3(B2_CHUNKS, S), 256, 0, stream>>>(g.obar, tiles, g.fs.part);
+  PSVI_CUDA_CHECK(cudaGetLastError());
+  fn_b2bar_final_kernel<<<S, 32, 0, stream>>>(g.fs.part, C, P, H * D + H + C * H, tbar);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

@@ -605,11 +605,19 @@ __global__ void fn_coreset_weights_kernel(const float* v, int M, float N, int vm
 }
 
 // mode 0: out[s] = sum over (tile, quarter) partials (+ add[s]), fixed order
+// one block per sample: thread i sums the partials i, i + 256, ... in order, then a fixed-order sum over the threads
+// (deterministic, no atomics)
 __global__ void fn_sum_tiles_kernel(const float* part, int n_tiles, int S, const float* add, float* out) {
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-    double a = add ? (double)add[s] : 0.0;
-    for (int t = 0; t < n_tiles * 4; ++t) a += part[(size_t)t * S + s];
-    out[s] = (float)a;
+  __shared__ double red[256];
+  const int s = blockIdx.x;
+  double a = 0.0;
+  for (int t = threadIdx.x; t < n_tiles * 4; t += 256) a += (double)part[(size_t)t * S + s];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = add ? (double)add[s] : 0.0;
+    for (int i = 0; i < 256; ++i) tot += red[i];
+    out[s] = (float)tot;
   }
 }
 
@@ -806,7 +814,7 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
   }
 #endif
   if (mode == 0 || mode == 3) {
-    fn_sum_tiles_kernel<<<1, 64, 0, stream>>>(sc.part, tiles, S, add, out);
+    fn_sum_tiles_kernel<<<S, 256, 0, stream>>>(sc.part, tiles, S, add, out);
   } else if (nsplit > 1) {
     const int fb = (int)((n_rows + 255) / 256) < 1024 ? (int)((n_rows + 255) / 256) : 1024;
     fn_finalize_kernel<<<fb, 256, 0, stream>>>(sc.probs, nsplit, (int)n_rows, C, labels, sc.part);
