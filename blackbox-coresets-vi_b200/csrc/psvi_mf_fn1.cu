@@ -37,8 +37,9 @@ constexpr int NW = NT / 32;    // warps per CTA
 // shared-memory carve-up (offsets in floats)
 struct FL {
   int rec, part;                                 // [nper][(HP+1) records] ; NW x (HP+1) records of partial adjoints
-  int q2r, pdst;                                 // Pt ints: TL index -> float offset inside a record block; Pt uint32:
-                                                 // shared::cluster address of recv[0][0][j] in the owner of q
+  int q2r, pdst, pmb;                            // Pt ints: TL index -> float offset inside a record block; Pt uint32:
+                                                 // shared::cluster address of recv[0][0][j] in the owner of q; of its mbarrier
+  int mb;                                        // two mbarriers: [0] partials received (owner role), [1] weights received
   int mu, rho, sig, sgm, gdm, gdr;               // owner state of my slice: slice floats each
   int ost;                                       // [10][slice]
   int epsS, recv, trs;                           // [2][S][slice] noise ; [S][2][slice] received partials ; [8][slice]
@@ -68,7 +69,8 @@ __host__ __device__ inline void make_fl(const EP& p, FL& y) {
   };
   y.rec = take(nper * (HP + 1) * REC);
   y.part = take(NW * (HP + 1) * REC);
-  y.q2r = take(Pt); y.pdst = take(Pt);
+  y.q2r = take(Pt); y.pdst = take(Pt); y.pmb = take(Pt);
+  y.mb = take(4);
   y.mu = take(p.slice); y.rho = take(p.slice); y.sig = take(p.slice); y.sgm = take(p.slice);
   y.gdm = take(p.slice); y.gdr = take(p.slice);
   y.ost = take(10 * p.slice);
@@ -97,6 +99,35 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, int r) {
 }
 __device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// Asynchronous remote store that signals the DESTINATION CTA's mbarrier with the bytes written: the receiver waits on its own
+// barrier for the byte count it expects, so an exchange costs one one-way DSMEM latency -- no release fence on the sender, no
+// cluster-wide barrier.
+__device__ __forceinline__ void st_async(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+               "r"(__float_as_uint(v)), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mb_arrive_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends for a bounded time per attempt; a broken exchange traps instead of hanging the GPU
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it > (1u << 22)) __trap();
+  }
 }
 // sum over the 16 hidden lanes of a row lane group (lane bits 0..3); every lane ends with the total
 __device__ __forceinline__ float hl_sum(float v) {
@@ -145,6 +176,8 @@ struct Fn1 {
   bool own;   // this thread owns TL index q = j0 + tid (load / store phases)
   int oj, oc; // update phases: thread (oc, oj) works on TL index j0 + oj, component oc (0 = mu, 1 = rho)
   bool own2;
+  uint32_t par_recv = 0, par_rec = 0;   // phase parities of my two mbarriers
+  int n_own, n_loc;                     // valid TL indices of my slice; MC samples this CTA runs
 
   __device__ Fn1(const EP& p_, const FL& y_, float* s_) : p(p_), y(y_), sm(s_), cluster(cg::this_cluster()) {
     rank = (int)cluster.block_rank();
@@ -164,6 +197,8 @@ struct Fn1 {
     oj = tid & ((1 << spad_sh) - 1);     // the two components sit in different warps: no divergence inside a warp
     oc = tid >> spad_sh;
     own2 = oc < 2 && oj < slice && j0 + oj < Pt;
+    n_own = max(0, min(slice, Pt - j0));
+    n_loc = rank < p.S ? (p.S - rank + p.G - 1) / p.G : 0;
   }
   __device__ __forceinline__ float* F(int off) const { return sm + off; }
   __device__ __forceinline__ int* I(int off) const { return reinterpret_cast<int*>(sm + off); }
@@ -178,6 +213,22 @@ struct Fn1 {
       p.tl[2 * tl_n + 1] = clock64();
       ++tl_n;
     }
+  }
+
+  // ---- owner role: wait until every sample CTA's partials of this exchange have landed in recv (ncomp vectors per sample;
+  //      rank 0 also receives the G loss partials when the inner losses are logged) -----------------------------------------
+  __device__ __forceinline__ void wait_recv(int ncomp, bool with_loss) {
+    const uint32_t bar = smem_u32(sm + y.mb);
+    if (tid == 0) mb_arrive_expect(bar, (uint32_t)((p.S * ncomp * n_own + ((with_loss && rank == 0) ? p.G : 0)) * 4));
+    mb_wait(bar, par_recv);
+    par_recv ^= 1u;
+  }
+  // ---- sample role: wait until every owner's slice of my samples' weights (and tangents / nkl partials) has landed ---------
+  __device__ __forceinline__ void wait_rec(bool tangent, bool nkl) {
+    const uint32_t bar = smem_u32(sm + y.mb + 2);
+    if (tid == 0) mb_arrive_expect(bar, (uint32_t)(n_loc * (Pt * (tangent ? 2 : 1) + (nkl ? p.G * nch : 0)) * 4));
+    mb_wait(bar, par_rec);
+    par_rec ^= 1u;
   }
 
   // ---- standard normals of my slice for EVERY sample of noise slab `slab` -> epsS[slab & 1]; done by the LAST threads
@@ -217,20 +268,22 @@ struct Fn1 {
     const float lsg = want_nkl ? logf(sg) : 0.f;
     const uint32_t base = smem_u32(F(y.rec) + (ok ? I(y.q2r)[j0 + j] : 0));
     const uint32_t nbase = smem_u32(F(y.nklp) + rank * nch + (j >> 5));
+    const uint32_t mbar_rec = smem_u32(sm + y.mb + 2);
     int cta = sg0 % p.G, li = sg0 / p.G;
     const int dcta = nsg % p.G, dli = nsg / p.G;
     for (int s = sg0; s < p.S; s += nsg) {   // (warp-uniform trip count: a warp lies inside one sample group)
       const float e = ok ? ep[s * slice] : 0.f;
       const float th = fmaf(sg, e, mu);
+      const uint32_t rbar = mapa(mbar_rec, cta);
       if (ok) {
         const uint32_t dst = mapa(base + (uint32_t)(li * PS * 4), cta);
-        st_cluster(dst, th);
-        if (tangent) st_cluster(dst + 32, fmaf(rs, e, md));
+        st_async(dst, th, rbar);
+        if (tangent) st_async(dst + 32, fmaf(rs, e, md), rbar);
       }
       if (want_nkl) {
         float v = ok ? (-0.5f * th * th + 0.5f * e * e + lsg) : 0.f;
         v = warp_sum(v);
-        if (lane == 0) st_cluster(mapa(nbase + (uint32_t)(li * p.G * nch * 4), cta), v);
+        if (lane == 0) st_async(mapa(nbase + (uint32_t)(li * p.G * nch * 4), cta), v, rbar);
       }
       cta += dcta; li += dli;
       if (cta >= p.G) { cta -= p.G; ++li; }
@@ -593,6 +646,7 @@ struct Fn1 {
   __device__ void fold_push(int s, int ncomp) {
     const int* q2r = I(y.q2r);
     const uint32_t* pdst = reinterpret_cast<const uint32_t*>(sm + y.pdst);
+    const uint32_t* pmb = reinterpret_cast<const uint32_t*>(sm + y.pmb);
     const float* part = F(y.part);
     const uint32_t soff = (uint32_t)(s * 2 * slice * 4);
     for (int q = tid; q < Pt; q += NT) {
@@ -603,15 +657,15 @@ struct Fn1 {
       float s0 = v[0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) s0 += v[w];
-      const uint32_t dst = pdst[q] + soff;
-      st_cluster(dst, s0);
+      const uint32_t dst = pdst[q] + soff, obar = pmb[q];
+      st_async(dst, s0, obar);
       if (ncomp > 1) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) v[w] = part[w * PS + r + 8];
         float s1 = v[0];
 #pragma unroll
         for (int w = 1; w < NW; ++w) s1 += v[w];
-        st_cluster(dst + (uint32_t)(slice * 4), s1);
+        st_async(dst + (uint32_t)(slice * 4), s1, obar);
       }
     }
   }
@@ -694,7 +748,8 @@ struct Fn1 {
     int* q2r = I(y.q2r);
     uint32_t* pdst = reinterpret_cast<uint32_t*>(sm + y.pdst);
     const int HD = H * D;
-    const uint32_t recv0 = smem_u32(F(y.recv));
+    const uint32_t recv0 = smem_u32(F(y.recv)), mb0 = smem_u32(sm + y.mb);
+    uint32_t* pmb = reinterpret_cast<uint32_t*>(sm + y.pmb);
     for (int q = tid; q < Pt; q += NT) {
       int r;
       if (q < HD) {
@@ -711,6 +766,12 @@ struct Fn1 {
       q2r[q] = r;
       const int owner = q / slice;
       pdst[q] = mapa(recv0 + (uint32_t)((q - owner * slice) * 4), owner);
+      pmb[q] = mapa(mb0, owner);
+    }
+    if (tid == 0) {
+      mb_init(mb0, 1);
+      mb_init(mb0 + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (own) {
       const float r = p.rho[j0 + tid];
@@ -850,7 +911,7 @@ __device__ void Fn1<D, C, UPL>::run() {
     gen_eps(0);
     __syncthreads();
     owner_sample(0, false, false);
-    cl_sync();
+    wait_rec(false, false);
     for (int t = 0; t < p.T; ++t) {
       const bool follow = !(p.flags & F_NOUPDATE) && (t + 1 < p.T || (p.flags & F_OUTER));
       stamp(1);
@@ -872,9 +933,9 @@ __device__ void Fn1<D, C, UPL>::run() {
           lpart += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
         }
         lpart = block_sum(lpart, F(y.red));
-        if (tid == 0) remote(y.lossrecv, 0)[rank] = lpart;
+        if (tid == 0) st_async(mapa(smem_u32(F(y.lossrecv) + rank), 0), lpart, mapa(smem_u32(sm + y.mb), 0));
       }
-      cl_sync();
+      wait_recv(1, want_loss);
       stamp(3);
       if (want_loss && rank == 0 && tid == 0) {
         float sl = 0.f;
@@ -890,9 +951,7 @@ __device__ void Fn1<D, C, UPL>::run() {
         owner_sample(t + 1, false, t + 1 == p.T);
       }
       stamp(4);
-      cl_arrive();
-      stamp(32);
-      if (own2) {   // global stores after the release: nobody in the cluster waits for them
+      if (own2) {   // trajectory (global memory): nobody in the cluster waits for these stores
         const int q2 = j0 + oj;
         if (p.g_out) p.g_out[oc * Pt + q2] = trv[1];
         if (p.traj) {
@@ -902,9 +961,10 @@ __device__ void Fn1<D, C, UPL>::run() {
         }
       }
       stamp(33);
-      cl_wait();
+      if (follow) wait_rec(false, t + 1 == p.T);
       stamp(5);
     }
+    __syncthreads();   // (owner state was written with the update mapping, read below with the load / store mapping)
     if ((p.flags & F_WRITE_PHI) && own) {
       p.mu[q] = F(y.mu)[tid];
       p.rho[q] = F(y.rho)[tid];
@@ -926,7 +986,7 @@ __device__ void Fn1<D, C, UPL>::run() {
       gen_eps(slab);
       __syncthreads();
       owner_sample(slab, false, true);
-      cl_sync();
+      wait_rec(false, true);
     }
     // O1: per-sample p_s, d_s, nkl_s
     {
@@ -1009,7 +1069,7 @@ __device__ void Fn1<D, C, UPL>::run() {
     }
     __syncthreads();
     for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];   // back to the inner row weights
-    cl_sync();
+    wait_recv(1, false);
     // O4: owner: dLoss/dphi_T of my TL index (no analytic-KL term in the outer objective); the sampled-nkl part
     // d nkl_s / d theta = -theta_s, weighted by beta_s (A.2), is formed here from the owner's own eps_s
     if (own) {
@@ -1044,7 +1104,7 @@ __device__ void Fn1<D, C, UPL>::run() {
     gen_eps(0);
     __syncthreads();
     owner_sample(0, true, false);
-    cl_sync();
+    wait_rec(true, false);
     int li = 0;
     for (int s = rank; s < S; s += G, ++li) {
       rows_dual(rec0 + li * PS);
@@ -1052,7 +1112,7 @@ __device__ void Fn1<D, C, UPL>::run() {
       fold_push(s, 2);
       if (s + G < S) __syncthreads();
     }
-    cl_sync();
+    wait_recv(2, false);
     if (own2) p.h_phi[oc * Pt + j0 + oj] = owner_hvp(0);
   }
 
@@ -1076,7 +1136,7 @@ __device__ void Fn1<D, C, UPL>::run() {
     owner_vjp(p.T - 1, p.traj + (size_t)(p.T - 1) * 8 * Pt + j0 + oj, Pt);
     __syncthreads();
     owner_sample(p.T - 1, true, false);
-    cl_sync();
+    wait_rec(true, false);
     for (int t = p.T - 1; t >= 0; --t) {
       stamp(21);
       if (t > 0) {   // next step's noise and trajectory row, staged while the row pass runs
@@ -1106,7 +1166,7 @@ __device__ void Fn1<D, C, UPL>::run() {
         if (s + G < S) __syncthreads();
       }
       stamp(22);
-      cl_sync();
+      wait_recv(2, false);
       stamp(23);
       // ---- owner: phibar_t = phibar_{t+1} + H gbar ; then the Adam VJP of step t-1 and its sample ----
       if (own2) OS2(oc) += owner_hvp(t);
@@ -1116,7 +1176,7 @@ __device__ void Fn1<D, C, UPL>::run() {
         __syncthreads();
         owner_sample(t - 1, true, false);
         stamp(24);
-        cl_sync();
+        wait_rec(true, false);
       }
     }
     __syncthreads();
