@@ -828,6 +828,13 @@ int forward(const psvi_mf_model* model, const FnScratch& sc, const void* x_bf16,
 
 #include "psvi_fn_grad_tc.cuh"
 
+// out[0..2] += slab[0..2] (nll sum, correct, rows); out[3..4] = the slab's importance-weight diagnostics (last slab wins, Q12)
+__global__ void slab_accumulate_kernel(const float* slab, float* out) {
+  const int i = threadIdx.x;
+  if (i < 3) out[i] += slab[i];
+  else if (i < 5) out[i] = slab[i];
+}
+
 }  // namespace
 
 // defined in psvi_lr_tc.cu
@@ -887,6 +894,38 @@ int psvi_fn_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
     if (rc) return rc;
   }
   return forward(model, sc, xt_bf16, yt, nullptr, n_rows, mode == 0 ? 1 : 2, sc.lw, nullptr, out, nullptr, stream);
+}
+
+// defined in psvi_lr_tc.cu
+int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho, const float* u,
+                          const int32_t* z, const float* v, int32_t M, const void* xt_bf16, const int32_t* yt, int64_t n_rows,
+                          int32_t slab, float N, int32_t vmode, float alpha, int32_t mode, float* out, void* scratch, void* stream_);
+
+int psvi_predictive_tc_slabs(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                             const float* u, const int32_t* z, const float* v, int32_t M, const void* xt_bf16,
+                             const int32_t* yt, int64_t n_rows, int32_t batch, int32_t first_slab, float N, int32_t vmode,
+                             float alpha, int32_t mode, float* out, void* scratch, void* stream_) {
+  PSVI_REQUIRE(model && xt_bf16 && yt && out && scratch, PSVI_ERR_INVALID, "null pointer");
+  PSVI_REQUIRE(n_rows > 0 && batch > 0 && first_slab >= 0, PSVI_ERR_INVALID, "bad n_rows / batch / first_slab");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
+  float* tmp = reinterpret_cast<float*>(base);
+  const int D = model->dims[0];
+  PSVI_CUDA_CHECK(cudaMemsetAsync(out, 0, 8 * sizeof(float), stream));
+  int k = 0;
+  for (int64_t a0 = 0; a0 < n_rows; a0 += batch, ++k) {
+    const int64_t rows = n_rows - a0 < batch ? n_rows - a0 : batch;
+    const void* xs = static_cast<const uint8_t*>(xt_bf16) + (size_t)a0 * D * 2;
+    const int rc = model->n_layers == 1
+                       ? psvi_lr_predictive_tc(model, noise, mu, rho, u, z, v, M, xs, yt + a0, rows, first_slab + k, N, vmode, alpha,
+                                               mode, tmp, base + 256, stream_)
+                       : psvi_fn_predictive_tc(model, noise, mu, rho, u, z, v, M, xs, yt + a0, rows, first_slab + k, N, vmode, alpha,
+                                               mode, tmp, base + 256, stream_);
+    if (rc) return rc;
+    slab_accumulate_kernel<<<1, 32, 0, stream>>>(tmp, out);
+    PSVI_CUDA_CHECK(cudaGetLastError());
+  }
+  return PSVI_OK;
 }
 
 int psvi_fn_nll_tc(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,

@@ -91,6 +91,9 @@ _SIGS = {
     "psvi_fn_nll_tc": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "psvi_predictive_tc_slabs": (C.c_int, [C.POINTER(MfModel), C.POINTER(Noise), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                           C.c_float, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_fn_data_grad_tc_scratch_bytes": (C.c_size_t, [C.POINTER(MfModel), C.c_int64]),
     "psvi_fn_data_grad_tc": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -373,6 +376,16 @@ def fn_nll_tc(model, noise, mu, rho, x_bf16, labels, row_weights, slab, wsum_out
     _check(lib().psvi_fn_nll_tc(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(x_bf16, torch.bfloat16),
                                 _p(labels, torch.int32), _p(row_weights), x_bf16.shape[0], slab, _p(wsum_out), _p(nkl_out),
                                 _p(nll_out), _p(scratch), _stream()))
+
+
+def predictive_tc_slabs(model, noise, mu, rho, u, z, v, xt_bf16, yt, batch, first_slab, N, vmode, alpha, mode, out, scratch):
+    """PSVI.evaluate over all test batches of this rank in one native call (tcgen05 predictive kernels, one noise slab each)."""
+    n_slabs = -(-xt_bf16.shape[0] // int(batch))
+    _count((((4 if mode == 0 else 3) if model.n_layers == 1 else (10 if mode == 0 else 5)) + 1) * n_slabs)
+    _check(lib().psvi_predictive_tc_slabs(C.byref(model), C.byref(noise), _p(mu), _p(rho), _p(u), _p(z, torch.int32), _p(v),
+                                          0 if u is None else u.shape[0], _p(xt_bf16, torch.bfloat16), _p(yt, torch.int32),
+                                          xt_bf16.shape[0], int(batch), int(first_slab), N, vmode, alpha, mode, _p(out),
+                                          _p(scratch), _stream()))
 
 
 def fn_data_grad_scratch_floats(model, n_rows):

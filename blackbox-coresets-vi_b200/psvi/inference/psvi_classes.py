@@ -790,32 +790,16 @@ class PSVI(object):
             if noise.mode == _native.NOISE_EXTERNAL and lo > 0:   # external slabs are indexed from this rank's first
                 noise = _native.make_noise(noise._keepalive[lo:hi].contiguous())
             first = 0 if noise.mode == _native.NOISE_EXTERNAL else lo
-            if use_fn_tc:
-                # large fn: sampled-GEMM forward on tcgen05 (psvi_fn_predictive_tc), bf16 operands, one launch set per slab
+            if use_fn_tc or self._use_tensor_core_eval(model, r1 - r0, batch):
+                # tensor path (large fn: psvi_fn_predictive_tc; large single-layer model: psvi_lr_predictive_tc, DESIGN.md 4.5 /
+                # 4.7), bf16 operands: ONE native call walks this rank's test batches (one noise slab each)
                 xb16 = self._device_bf16(xt, "test")
-                scratch = self._buf("eval_fn_tc", _native.fn_tc_scratch_floats(desc, min(batch, r1 - r0), u.shape[0]))
-                acc = torch.zeros(8, device=self.device)
-                for k in range(hi - lo):
-                    a0, a1 = r0 + k * batch, min(r0 + (k + 1) * batch, r1)
-                    _native.fn_predictive_tc(desc, noise, mu, rho, u, self._z32(), v, xb16[a0:a1], yt[a0:a1], first + k,
-                                             float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1,
-                                             out, scratch)
-                    acc[:3] += out[:3]
-                acc[3:5] = out[3:5]
-                out = acc
-            elif self._use_tensor_core_eval(model, r1 - r0, batch):
-                # large single-layer case: TMA + tcgen05 kernel, bf16 operands; one launch set per slab
-                xb16 = self._device_bf16(xt, "test")
-                scratch = self._buf("eval_tc", _native.lr_predictive_tc_scratch_floats(desc))
-                acc = torch.zeros(8, device=self.device)
-                for k in range(hi - lo):
-                    a0, a1 = r0 + k * batch, min(r0 + (k + 1) * batch, r1)
-                    _native.lr_predictive_tc(desc, noise, mu, rho, u, self._z32(), v, xb16[a0:a1], yt[a0:a1], first + k,
-                                             float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1,
-                                             out, scratch)
-                    acc[:3] += out[:3]
-                acc[3:5] = out[3:5]
-                out = acc
+                rows_slab = min(batch, r1 - r0)
+                need = (_native.fn_tc_scratch_floats(desc, rows_slab, u.shape[0]) if use_fn_tc
+                        else _native.lr_predictive_tc_scratch_floats(desc)) + 256
+                scratch = self._buf("eval_tc", need)
+                _native.predictive_tc_slabs(desc, noise, mu, rho, u, self._z32(), v, xb16[r0:r1], yt[r0:r1], batch, first,
+                                            float(self.N), self._vmode, self._alpha_value(), 0 if correction else 1, out, scratch)
             else:
                 scratch = self._buf("eval", _native.eval_scratch_floats(desc, r1 - r0, batch))
                 _native.evaluate(desc, noise, mu, rho, u, self._z32(), v, xt[r0:r1], yt[r0:r1], batch, first,

@@ -276,6 +276,16 @@ int psvi_fnl_pass(const psvi_mf_model* model, int32_t precision, const float* th
                   const int32_t* y, const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
                   float* logits, void* workspace, void* stream);
 
+/* ---- PSVI.evaluate over MANY test batches on the tensor path in ONE call (reference psvi_classes.py:1038-1092: a fresh
+ * noise slab per test batch): loops the slabs on the host side of the library -- psvi_lr_predictive_tc for the single-layer model,
+ * psvi_fn_predictive_tc for fn -- and accumulates out[0..2] (nll sum, correct, rows) on the device; out[3..4] are the
+ * importance-weight diagnostics of the LAST slab (Q12).  scratch: the per-slab scratch of the underlying call for `batch` rows
+ * + 512 bytes. */
+int psvi_predictive_tc_slabs(const psvi_mf_model* model, const psvi_noise* noise, const float* mu, const float* rho,
+                             const float* u, const int32_t* z, const float* v, int32_t M, const void* xt_bf16,
+                             const int32_t* yt, int64_t n_rows, int32_t batch, int32_t first_slab, float N, int32_t vmode,
+                             float alpha, int32_t mode, float* out, void* scratch, void* stream);
+
 /* ---- full-data DATA-TERM gradient of the outer objective on the tensor path (the part of the hot path that shards).
  * reference: data_nll = N / Nx * all_nlls[:, Nu:].sum(-1) inside psvi_elbo (psvi/inference/psvi_classes.py:477,484-486)
  * and what autograd back-propagates through it; SURVEY.md section 7 step 7 / section 8e.
