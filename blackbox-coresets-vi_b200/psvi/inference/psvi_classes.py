@@ -562,10 +562,71 @@ class PSVI(object):
         ll = self.psvi_elbo(xbatch, ybatch, model=self.model)
         return ll.item()
 
-    def joint_step(self, xbatch, ybatch):
-        raise NotImplementedError("--trainer joint is outside the hot path (SURVEY.md section 8a: nested / hyper)")
+    # --trainer joint / alternating (reference :517-539): first-order steps on psvi_elbo.  The fused outer pass returns the
+    # value AND the gradients wrt (mu, rho), u and v in one launch (self._last_outer), which is what loss.backward() gave
+    # the reference; the Adam updates are torch.optim.Adam on a flat leaf that mirrors the model's variational parameters
+    # (Adam is elementwise, so one flat tensor == the reference's per-layer parameter list).
+    def _phi_get(self):
+        model = self.model
+        if isinstance(model, MeanFieldMLP):
+            return torch.cat(model.flat())
+        return self._stream(model).fam.get_phi()
 
-    alternating_step = joint_step
+    def _phi_set(self, phi):
+        model = self.model
+        if isinstance(model, MeanFieldMLP):
+            mu, rho = model.flat()
+            mu.copy_(phi[:mu.numel()])
+            rho.copy_(phi[mu.numel():])
+        else:
+            self._stream(model).fam.set_phi(phi)
+
+    def _phi_leaf(self):
+        phi = self._phi_get()
+        leaf = getattr(self, "_phi_param", None)
+        if leaf is None or leaf.shape != phi.shape or leaf.device != phi.device:
+            leaf = self._phi_param = torch.nn.Parameter(phi.clone())
+        else:
+            leaf.data.copy_(phi)        # (weight_reset / increment_coreset may have touched the model in between)
+        return leaf
+
+    def _first_order_step(self, xbatch, ybatch, optim, tag, net, pseudo):
+        """optim.zero_grad(); loss = psvi_elbo(...); loss.backward(); optim.step() of the reference for the parameter groups
+        `net` (model) / `pseudo` (u and, if learnt, v) that `optim` holds."""
+        leaf = self._phi_leaf()
+        optim.zero_grad()
+        loss = self.psvi_elbo(xbatch, ybatch, model=self.model)
+        if self.register_elbos:
+            self.elbos.append((tag, -loss.item()))
+        g = self._last_outer
+        if net:
+            leaf.grad = g["phi_grad"].to(leaf.dtype).reshape(leaf.shape)
+        if pseudo:
+            self.u.grad = g["u_grad"].to(self.u.dtype).reshape(self.u.shape)
+            if self.learn_v and pseudo == "uv":
+                self.v.grad = g["v_grad"].to(self.v.dtype)
+        optim.step()
+        if net:
+            with torch.no_grad():
+                self._phi_set(leaf.data)
+        return loss
+
+    def joint_step(self, xbatch, ybatch):
+        """reference :517-526: one Adam(lr0joint) over model parameters, u and (if learnt) v."""
+        if getattr(self, "_optim_joint_for", None) is not self.model:
+            params = [self._phi_leaf(), self.u] + ([self.v] if self.learn_v else [])
+            self.optim = torch.optim.Adam(params, self._lr0joint)
+            self._optim_joint_for = self.model
+        return self._first_order_step(xbatch, ybatch, self.optim, 2, net=True, pseudo="uv")
+
+    def alternating_step(self, xbatch, ybatch):
+        """reference :528-539: an Adam step of the model (lr of optim_net) on one draw, then an Adam step of u (optim_u) on
+        a fresh draw at the updated model; v is not stepped by this trainer."""
+        if getattr(self, "_optim_alt_for", None) is not self.model:
+            self._optim_alt_net = torch.optim.Adam([self._phi_leaf()], float(self.optim_net.param_groups[0]["lr"]))
+            self._optim_alt_for = self.model
+        self._first_order_step(xbatch, ybatch, self._optim_alt_net, 0, net=True, pseudo=None)
+        return self._first_order_step(xbatch, ybatch, self.optim_u, 1, net=False, pseudo="u")
 
     # ------------------------------------------------------------------------------------------------ model
     def set_up_model(self):
@@ -656,9 +717,9 @@ class PSVI(object):
         self.scheduler_optim_net = torch.optim.lr_scheduler.StepLR(self.optim_net, **scheduler_kwargs)
         if self.learn_v:
             self.optim_v = torch.optim.Adam([self.v], lr0v)
-        optimizers = {"nested": self.nested_step, "hyper": self.hyper_step}
-        if self.trainer not in optimizers:
-            raise NotImplementedError(f"--trainer {self.trainer} is outside the hot path (nested / hyper are built)")
+        self._lr0joint = lr0joint
+        optimizers = {"alternating": self.alternating_step, "nested": self.nested_step, "hyper": self.hyper_step,
+                      "joint": self.joint_step}        # reference :871-886
         psvi_step = optimizers[self.trainer]
         total_checkpts = list(range(self.num_epochs))[::max(int(log_every), 1)]
         downsample = 1

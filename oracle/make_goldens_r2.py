@@ -8,6 +8,8 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
   mfvi_hm.npz            run_mfvi (baselines.py:824-920) trace with full-batch steps (the shuffled loader then only permutes
                          the rows of a sum)
   fixedpoint_fn_hm.npz   PSVI.hyper_step with hypergrad_approx="fixed_point" (hypergradients.py:83-140)
+  joint_fn_hm.npz / alternating_fn_hm.npz   two joint_step / alternating_step calls (psvi_classes.py:517-539); made by
+                         `python oracle/make_goldens_r2.py trainers`
 
 Noise is injected through oracle.ref_import.NoiseFeeder (fixtures store the seed only).
 """
@@ -175,7 +177,54 @@ def run_fixed_point(name="fixedpoint_fn_hm", H=20, M=10, S=6, T=6, B=64, K=4, in
     print(name, "forwards", out["n_forwards"], "ll", ll, "|gu|", np.abs(out["ref64_gu"]).max(), "size", os.path.getsize(pth))
 
 
+def run_joint_alternating(trainer, name, H=20, M=10, S=6, B=64, steps=2, init_sd=1e-2, lr0net=1e-3, lr0joint=1e-3):
+    """`--trainer joint` / `alternating` (psvi_classes.py:517-539,871-880): `steps` calls of joint_step / alternating_step."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=1, trainer=trainer, log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, lr0joint=lr0joint, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm="halfmoon", nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False)
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = rc.PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(9)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.to(tdt)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.optim = torch.optim.Adam(list(obj.model.parameters()) + [obj.u] + [obj.v], lr0joint)
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, M=M, B=B, steps=steps, lr0net=lr0net, lr0joint=lr0joint, lr0u=1e-4, noise_seed=5656,
+               vmode=1, mu0=mu0, rho0=rho0, u0=obj.u.detach().numpy().copy(), z=obj.z.numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy())
+    step = obj.joint_step if trainer == "joint" else obj.alternating_step
+    losses = []
+    with NoiseFeeder(dims, S, 5656) as nf, _quiet():
+        for _ in range(steps):
+            losses.append(step(xb, yb).item())
+        out["n_forwards"] = len(nf.history)
+    out["ref64_losses"] = np.array(losses)
+    out["ref64_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+    out["ref64_u_after"], out["ref64_v_after"] = obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy()
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards"], "losses", losses, "size", os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "trainers":
+        run_joint_alternating("joint", "joint_fn_hm")
+        run_joint_alternating("alternating", "alternating_fn_hm")
+        return
     for cls_name in ("PSVIAV", "PSVIAFixedU", "PSVIFixedU", "PSVIFreeV", "PSVI_No_Rescaling"):
         run_variant(cls_name)
     run_fixed_point()

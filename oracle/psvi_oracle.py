@@ -388,6 +388,43 @@ def torch_adam_step(p, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
     return p - (lr / (1 - b1 ** t)) * m / den, m, v
 
 
+# ------------------------------------------------------------------- --trainer joint / alternating
+def _outer_grads(mu, rho, eps, u, z, v, xb, yb, N, dims, vmode, alpha):
+    a = coreset_weights(v, N, vmode, alpha)
+    loss, mb, rb, ub, ab, _ = psvi_elbo_grad(mu, rho, eps, u, z, a, xb, yb, N, dims)
+    return loss, mb, rb, ub, coreset_weights_vjp(v, N, vmode, ab, alpha)[0]
+
+
+def joint_steps(mu, rho, eps_steps, u, z, v, xb, yb, N, dims, lr, vmode=1, alpha=0.0, learn_v=True):
+    """PSVI.joint_step (psvi_classes.py:517-526) called len(eps_steps) times: ONE torch Adam (lr0joint) over the model
+    parameters, u and (if learnt) v on psvi_elbo; one noise draw per step.  Returns the losses and the final state."""
+    st = {k: [x.copy(), 0 * x, 0 * x] for k, x in (("mu", mu), ("rho", rho), ("u", u), ("v", v))}
+    losses = []
+    for t, eps in enumerate(eps_steps, 1):
+        loss, mb, rb, ub, vb = _outer_grads(st["mu"][0], st["rho"][0], eps, st["u"][0], z, st["v"][0], xb, yb, N, dims, vmode, alpha)
+        losses.append(loss)
+        for k, g in (("mu", mb), ("rho", rb), ("u", ub)) + ((("v", vb),) if learn_v else ()):
+            st[k] = list(torch_adam_step(st[k][0], g, st[k][1], st[k][2], t, lr))
+    return np.array(losses), st["mu"][0], st["rho"][0], st["u"][0], st["v"][0]
+
+
+def alternating_steps(mu, rho, eps_steps, u, z, v, xb, yb, N, dims, lr_net, lr_u, vmode=1, alpha=0.0):
+    """PSVI.alternating_step (psvi_classes.py:528-539): per call, an Adam step of the model (optim_net) on a fresh psvi_elbo
+    draw, then an Adam step of u (optim_u) on another draw at the updated model; v is never stepped.  eps_steps holds two
+    draws per call; the returned loss of a call is the second one."""
+    net = {k: [x.copy(), 0 * x, 0 * x] for k, x in (("mu", mu), ("rho", rho))}
+    us = [u.copy(), 0 * u, 0 * u]
+    losses = []
+    for t in range(1, len(eps_steps) // 2 + 1):
+        _, mb, rb, _, _ = _outer_grads(net["mu"][0], net["rho"][0], eps_steps[2 * t - 2], us[0], z, v, xb, yb, N, dims, vmode, alpha)
+        for k, g in (("mu", mb), ("rho", rb)):
+            net[k] = list(torch_adam_step(net[k][0], g, net[k][1], net[k][2], t, lr_net))
+        loss, _, _, ub, _ = _outer_grads(net["mu"][0], net["rho"][0], eps_steps[2 * t - 1], us[0], z, v, xb, yb, N, dims, vmode, alpha)
+        us = list(torch_adam_step(us[0], ub, us[1], us[2], t, lr_u))
+        losses.append(loss)
+    return np.array(losses), net["mu"][0], net["rho"][0], us[0], v.copy()
+
+
 # ------------------------------------------------------------------------------------ evaluate (a11, Q3, Q12)
 def evaluate(mu, rho, eps_batches, u, z, a, xt, yt, dims, batch, correction=True):
     """PSVI.evaluate (psvi_classes.py:1031-1108).  eps_batches[k] is the draw of test batch k.

@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint")))
+               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating")))
 
 
 def rel_l2(a, b):
@@ -214,3 +214,22 @@ def test_variant_nested_step_matches_reference(cls):
         np.testing.assert_allclose(v1, g["ref64_nested_v_after"], rtol=0, atol=1e-9)
     if vmode == 2:
         np.testing.assert_allclose(r["alpha_grad"], g["ref64_nested_galpha"][0], rtol=1e-7)
+
+
+@pytest.mark.parametrize("trainer", ["joint", "alternating"])
+def test_joint_and_alternating_trainers_match_reference(trainer):
+    """`--trainer joint` / `alternating` (reference psvi_classes.py:517-539,871-880): two steps through the oracle's closed-form
+    psvi_elbo gradients + torch Adam against the fp64 reference.  Goldens: `python oracle/make_goldens_r2.py trainers`."""
+    g = dict(np.load(os.path.join(GOLDEN, f"{trainer}_fn_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, N = int(g["S"]), float(g["N"])
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    if trainer == "joint":
+        r = po.joint_steps(g["mu0"], g["rho0"], eps, g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N, dims, float(g["lr0joint"]))
+    else:
+        r = po.alternating_steps(g["mu0"], g["rho0"], eps, g["u0"], g["z"], g["v0"], g["xb"], g["yb"], N, dims,
+                                 float(g["lr0net"]), float(g["lr0u"]))
+    np.testing.assert_allclose(r[0], g["ref64_losses"], rtol=1e-9)
+    assert rel_l2(po.mu_rho_to_phi(r[1], r[2], dims), g["ref64_params"]) < 1e-9
+    np.testing.assert_allclose(r[3], g["ref64_u_after"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(r[4], g["ref64_v_after"], rtol=0, atol=1e-9)
