@@ -489,44 +489,53 @@ def main():
     # 8 M rows per rank), ONE all-reduce of the 8-float result.
     fulldata = None
     try:
-        Dl, Cl, Sl, Ml, rows = 256, 10, 10, 50, 8_000_000
-        lmodel = _native.make_model([Dl, Cl], Sl)
-        Pl = _native.num_theta(lmodel)
+        Dl, Cl, Ml, rows = 256, 10, 50, 8_000_000
         gg = torch.Generator(device=dev).manual_seed(7 + rank)
-        lmu = 0.1 * torch.randn(Pl, device=dev, generator=gg)
-        lrho = torch.full((Pl,), -2.97, device=dev)
+        xb16 = torch.randn(rows, Dl, device=dev, generator=gg, dtype=torch.bfloat16)
+        yl = torch.randint(0, Cl, (rows,), device=dev, dtype=torch.int32, generator=gg)
         lu = torch.randn(Ml, Dl, device=dev, generator=gg)
         lz = torch.randint(0, Cl, (Ml,), device=dev, dtype=torch.int32, generator=gg)
         lv = torch.zeros(Ml, device=dev)
-        xb16 = torch.randn(rows, Dl, device=dev, generator=gg, dtype=torch.bfloat16)
-        yl = torch.randint(0, Cl, (rows,), device=dev, dtype=torch.int32, generator=gg)
         lout = torch.zeros(8, device=dev)
-        lscr = torch.zeros(_native.lr_predictive_tc_scratch_floats(lmodel), device=dev)
         lnoise = _native.make_noise(None, seed=11, domain=1)
+        try:
+            HBM_PEAK_GBPS = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            HBM_PEAK_GBPS = 6556.2        # the value the driver measured on this pool (fallback when the file did not travel)
 
-        def lr_pass():
-            _native.lr_predictive_tc(lmodel, lnoise, lmu, lrho, lu, lz, lv, xb16, yl, 0, 1.0e4, 1, 0.0, 0, lout, lscr)
+        def lr_case(Sl):
+            lmodel = _native.make_model([Dl, Cl], Sl)
+            Pl = _native.num_theta(lmodel)
+            lmu = 0.1 * torch.randn(Pl, device=dev, generator=gg)
+            lrho = torch.full((Pl,), -2.97, device=dev)
+            lscr = torch.zeros(_native.lr_predictive_tc_scratch_floats(lmodel), device=dev)
+
+            def lr_pass():
+                _native.lr_predictive_tc(lmodel, lnoise, lmu, lrho, lu, lz, lv, xb16, yl, 0, 1.0e4, 1, 0.0, 0, lout, lscr)
+                if world > 1:
+                    dist.all_reduce(lout)
+            for _ in range(3):
+                lr_pass()
+            barrier()
+            reps = 10
+            a.record(stream)
+            for _ in range(reps):
+                lr_pass()
+            b.record(stream)
+            barrier()
+            tt = torch.tensor([a.elapsed_time(b)], device=dev)
             if world > 1:
-                dist.all_reduce(lout)
-        for _ in range(3):
-            lr_pass()
-        barrier()
-        reps = 10
-        a.record(stream)
-        for _ in range(reps):
-            lr_pass()
-        b.record(stream)
-        barrier()
-        tt = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        sec = tt.item() * 1e-3 / reps
-        byts = world * rows * (Dl * 2 + 4)
-        fulldata = {"what": f"psvi_lr_predictive_tc: logistic regression D=256 C=10 S=10 M=50, {rows} bf16 rows per rank x "
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = tt.item() * 1e-3 / reps
+            byts = world * rows * (Dl * 2 + 4)
+            return {"S": Sl, "ms_per_pass": sec * 1e3, "rows_per_s": world * rows / sec, "row_samples_per_s": world * rows * Sl / sec,
+                    "algorithmic_bytes": byts, "GBps": byts / sec / 1e9,
+                    "frac_of_measured_hbm_peak_per_gpu": byts / sec / 1e9 / world / HBM_PEAK_GBPS}
+        fulldata = lr_case(10)
+        fulldata["what"] = (f"psvi_lr_predictive_tc: logistic regression D=256 C=10 S=10 M=50, {rows} bf16 rows per rank x "
                             f"{world} rank(s), whole call (log-weights + weight prep + TMA/tcgen05 kernel + reduce)"
-                            + (" + all-reduce" if world > 1 else ""),
-                    "ms_per_pass": sec * 1e3, "rows_per_s": world * rows / sec, "row_samples_per_s": world * rows * Sl / sec,
-                    "algorithmic_bytes": byts, "GBps": byts / sec / 1e9}
+                            + (" + all-reduce" if world > 1 else ""))
+        fulldata["S16"] = lr_case(16)
     except Exception as e:
         fulldata = {"error": repr(e)[:300]}
 

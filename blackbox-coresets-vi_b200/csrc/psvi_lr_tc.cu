@@ -26,12 +26,12 @@ constexpr int BM = 128;      // rows per tile (UMMA M)
 constexpr int BK = 64;       // bf16 elements per K chunk = one 128-byte swizzle atom
 constexpr int STAGES = 8;    // maximum A-operand pipeline depth (8 x 16 KB); fewer when the weights need the room
 constexpr int CP = 16;       // logit columns reserved per MC sample (C <= 16)
-constexpr int NSPLIT = 3;         // epilogue warps per TMEM lane quarter (they split the MC samples)
-constexpr int TC_THREADS = 128 + 128 * NSPLIT;  // 4 role warps + 4*NSPLIT epilogue warps
+constexpr int NSPLIT_MAX = 4;     // epilogue warps per TMEM lane quarter (they split the MC samples): 3 or 4
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 struct TcParams {
-  int n_rows, n_tiles, D, kc, S, C, NP;  // NP = CP * S accumulator columns
+  int n_rows, n_tiles, D, kc, S, C, NP;  // NP accumulator columns: sample s owns columns [s * cs, s * cs + C)
+  int cs;                                // column stride per sample: C (packed) or CP
   int mode;                              // 0 importance weighted, 1 uniform weights
   int stages;                            // A-operand pipeline depth actually used (2..STAGES)
   const float* bias;                     // [NP]
@@ -43,8 +43,8 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------ the kernel
 // CC = number of logit columns the epilogue touches per sample (C rounded up to 2/4/8/12/16; the padding columns carry
 // bias = -inf, so they drop out of max / exp / sum without any predicate)
-template <int CC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int CC, int NSPLIT>
+__global__ void __launch_bounds__(128 + 128 * NSPLIT, 1)
 psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                              const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -67,7 +67,8 @@ psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __
   float* s_xch = s_red + 8;  // [2 buffers][NSPLIT-1][CP][128 rows] partial mixtures of the helper warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.NP; i += TC_THREADS) s_bias[i] = p.bias[i] * 1.4426950408889634f;  // log2(e) folded in
+  constexpr int TC_THREADS = 128 + 128 * NSPLIT;  // 4 role warps + 4*NSPLIT epilogue warps
+  for (int i = threadIdx.x; i < p.S * CP; i += TC_THREADS) s_bias[i] = p.bias[i] * 1.4426950408889634f;  // log2(e) folded in
   if (threadIdx.x == 0) {  // importance weights: softmax over the S log-weights (mode 0) or uniform
     float mx = -INFINITY, se = 0.f;
     if (p.mode == 0) {
@@ -152,9 +153,10 @@ psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __
 #pragma unroll
       for (int c = 0; c < CC; ++c) probs[c] = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+#pragma unroll 2
       for (int s = half; s < p.S; s += NSPLIT) {
         float v[16];
-        tmem_ld16(taddr + s * CP, v);
+        tmem_ld16(taddr + s * p.cs, v);
         const float* bs = s_bias + s * CP;
         float mx = -INFINITY;
 #pragma unroll
@@ -162,11 +164,19 @@ psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __
           v[c] = fmaf(v[c], LOG2E, bs[c]);
           mx = fmaxf(mx, v[c]);
         }
-        float se = 0.f;
 #pragma unroll
-        for (int c = 0; c < CC; ++c) {
-          v[c] = ex2_approx(v[c] - mx);
-          se += v[c];
+        for (int c = 0; c < CC; ++c) v[c] = ex2_approx(v[c] - mx);
+        float se;
+        {   // pairwise tree: a dependent chain of log2(CC) adds instead of CC
+          float t[CC];
+#pragma unroll
+          for (int c = 0; c < CC; ++c) t[c] = v[c];
+#pragma unroll
+          for (int w = CC; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+            for (int c = 0; c < w / 2; ++c) t[c] = t[c] + t[w - 1 - c];
+          }
+          se = t[0];
         }
         const float sc = __fdividef(s_w[s], se);
 #pragma unroll
@@ -220,13 +230,13 @@ psvi_lr_predictive_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __
 
 // stacked bf16 weights [16 S][D] (rows c >= C of a sample are zero) and fp32 biases from (mu, rho, noise slab)
 __global__ void lr_prep_kernel(const float* mu, const float* rho, psvi_noise noise, int slab, int S, int C, int D,
-                               __nv_bfloat16* Wb, float* bias) {
+                               __nv_bfloat16* Wb, float* bias, int cs, int NP) {
   const int P = C * D + C;
-  const int total = S * CP * D;
+  const int total = NP * D;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int d = i % D, n = i / D, s = n / CP, c = n % CP;
+    const int d = i % D, n = i / D, s = n / cs, c = n % cs;
     float th = 0.f;
-    if (c < C) {
+    if (c < C && s < S) {
       const int q = c * D + d;
       float e;
       if (noise.mode == PSVI_NOISE_PHILOX) {
@@ -331,11 +341,17 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
   PSVI_REQUIRE(mode == 0 || mode == 1, PSVI_ERR_INVALID, "mode must be 0 (importance weighted) or 1 (uniform)");
   PSVI_REQUIRE((reinterpret_cast<uintptr_t>(xt_bf16) & 15) == 0, PSVI_ERR_INVALID, "xt_bf16 must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int NP = CP * S;
+  // epilogue width CC >= C; accumulator columns: sample s at [s * cs, s * cs + C).  Packing the samples (cs = C) instead of
+  // one 16-column group each cuts the MMA N (S = 16, C = 10: 160 instead of 256 -- at N = 256 the kernel is tensor-bound).
+  // The zero weight rows up to NP keep every column the epilogue touches finite (its padding columns carry bias = -inf).
+  const int CCsel = C <= 2 ? 2 : C <= 4 ? 4 : C <= 6 ? 6 : C <= 8 ? 8 : C <= 10 ? 10 : C <= 12 ? 12 : 16;
+  const int np_packed = (((S - 1) * C + CCsel) + 15) & ~15;
+  const int cs = np_packed < CP * S ? C : CP;
+  const int NP = cs == C ? np_packed : CP * S;
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(sc);
-  float* bias = reinterpret_cast<float*>(sc + (size_t)NP * D * 2);
-  float* wts = bias + NP;
+  float* bias = reinterpret_cast<float*>(sc + (size_t)CP * S * D * 2);
+  float* wts = bias + CP * S;
   float* part = wts + 64;
   // 1. log importance weights of this slab from the pseudo-data forward (fp32, one CTA per sample)
   if (mode == 0) {
@@ -344,7 +360,7 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
     if (rc) return rc;
   }
   // 2. stacked sampled weights in bf16
-  lr_prep_kernel<<<(NP * D + 255) / 256, 256, 0, stream>>>(mu, rho, *noise, slab, S, C, D, Wb, bias);
+  lr_prep_kernel<<<(NP * D + 255) / 256, 256, 0, stream>>>(mu, rho, *noise, slab, S, C, D, Wb, bias, cs, NP);
   PSVI_CUDA_CHECK(cudaGetLastError());
   // 3. tensor maps + the streaming kernel
   CUtensorMap map_x, map_w;
@@ -353,7 +369,7 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
   rc = make_map_2d_bf16(&map_w, Wb, (uint64_t)D, (uint64_t)NP, BK, (uint32_t)NP);
   if (rc) return rc;
   TcParams p;
-  p.n_rows = (int)n_rows; p.n_tiles = (int)((n_rows + BM - 1) / BM); p.D = D; p.kc = D / BK; p.S = S; p.C = C; p.NP = NP;
+  p.n_rows = (int)n_rows; p.n_tiles = (int)((n_rows + BM - 1) / BM); p.D = D; p.kc = D / BK; p.S = S; p.C = C; p.NP = NP; p.cs = cs;
   p.mode = mode; p.bias = bias; p.wts = wts; p.labels = yt; p.part = part;
   int dev = 0, sms = 0;
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
@@ -362,23 +378,35 @@ int psvi_lr_predictive_tc(const psvi_mf_model* model, const psvi_noise* noise, c
   PSVI_REQUIRE(grid <= 148 + 16, PSVI_ERR_UNSUPPORTED, "more SMs than the partial buffer holds");
   int smem_max = 0;
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t fixed = (size_t)p.kc * NP * 128 + (256 + 16) * 4 + (2 * STAGES + 5) * 8 + 8 + 32 + 2 * (NSPLIT - 1) * CP * BM * 4 + 1024;
+  const size_t fixed = (size_t)p.kc * NP * 128 + (256 + 16) * 4 + (2 * STAGES + 5) * 8 + 8 + 32 + 2 * (NSPLIT_MAX - 1) * CP * BM * 4 + 1024;
   int stages = (int)(((size_t)smem_max - fixed) / A_STAGE_BYTES);
   if (stages > STAGES) stages = STAGES;
   PSVI_REQUIRE(stages >= 2, PSVI_ERR_UNSUPPORTED, "not enough shared memory for a 2-stage pipeline (S=%d, D=%d)", S, D);
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * A_STAGE_BYTES;
+  // epilogue warps per lane quarter: 3 measured faster than 4 at S = 4, 10 and 16 (profiles/r2_lr_tc_summary.md); the
+  // 4-way instance stays selectable for experiments
+  int ns = 3;
+  if (const char* e = getenv("PSVI_LR_NSPLIT")) ns = atoi(e) == 4 ? 4 : 3;
+#define PSVI_TC_LAUNCH2(CCV, NSV)                                                                                        \
+  do {                                                                                                                  \
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_lr_predictive_tc_kernel<CCV, NSV>,                                         \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+    psvi_lr_predictive_tc_kernel<CCV, NSV><<<grid, 128 + 128 * NSV, smem, stream>>>(map_x, map_w, p);                    \
+  } while (0)
 #define PSVI_TC_LAUNCH(CCV)                                                                                              \
   do {                                                                                                                  \
-    PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_lr_predictive_tc_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem));                                                                   \
-    psvi_lr_predictive_tc_kernel<CCV><<<grid, TC_THREADS, smem, stream>>>(map_x, map_w, p);                             \
+    if (ns == 4) PSVI_TC_LAUNCH2(CCV, 4);                                                                               \
+    else PSVI_TC_LAUNCH2(CCV, 3);                                                                                       \
   } while (0)
   if (C <= 2) PSVI_TC_LAUNCH(2);
   else if (C <= 4) PSVI_TC_LAUNCH(4);
+  else if (C <= 6) PSVI_TC_LAUNCH(6);
   else if (C <= 8) PSVI_TC_LAUNCH(8);
+  else if (C <= 10) PSVI_TC_LAUNCH(10);
   else if (C <= 12) PSVI_TC_LAUNCH(12);
   else PSVI_TC_LAUNCH(16);
+#undef PSVI_TC_LAUNCH2
 #undef PSVI_TC_LAUNCH
   PSVI_CUDA_CHECK(cudaGetLastError());
   // 4. fixed-order reduction + weight diagnostics
