@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import time
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -109,7 +111,7 @@ class PSVI(object):
         self.num_pseudo, self.mc_samples = (num_pseudo if not increment else increment_sizes[0]), mc_samples
         self.reset, self.reset_interval, self.learn_v, self.learn_z = reset, reset_interval, learn_v, learn_z
         self.increment_interval, self.increment_sizes = increment_interval, increment_sizes
-        for flag, name in ((learn_z, "learn_z"), (scoring_run, "scoring_run")):
+        for flag, name in ((scoring_run, "scoring_run"),):
             if flag:
                 raise NotImplementedError(f"{name}=True is outside the hot path built so far (SURVEY.md section 8f)")
         with torch.no_grad():
@@ -152,6 +154,9 @@ class PSVI(object):
                                 batch_size=ppc[c], shuffle=True)
             lst.append(next(iter(loader)).to(device=self.device))
         self.u = torch.cat(lst).float().requires_grad_(True)
+        if self.learn_z:
+            # target logits initialised at the one-hot encoding of the class labels (reference :259-264)
+            self.z = torch.nn.functional.one_hot(self.z.to(torch.int64), num_classes=self.nc).float().requires_grad_(True)
 
     def pseudo_rand_init(self, variance=1.0):
         """Noisy empirical mean + labels split equally among classes (reference :287-308)."""
@@ -218,7 +223,118 @@ class PSVI(object):
         return ubar, abar
 
     def _use_stream(self, model):
-        return isinstance(model, (FullCovMLP, MeanFieldLeNet)) or self._ws.get(("force_stream", id(model)), False)
+        return (isinstance(model, (FullCovMLP, MeanFieldLeNet)) or self.learn_z
+                or self._ws.get(("force_stream", id(model)), False))
+
+    # ---- learn_z: soft pseudo-labels (reference :455-474,499-504, the KLDivLoss branch) ---------------------------------
+    # A soft-label row r with targets t[r, :] contributes  sum_c t[r,c] (log t[r,c] - log p_s[r,c])  =  kappa_r + sum_c t[r,c]
+    # * nll_s(x_r, label c): the kernels see it as C hard-label rows (x_r, c) with row weights t[r,c]; kappa_r = sum_c t log t
+    # does not depend on the network.  t = labels.softmax(0): normalised over the ROWS of the label matrix (per class column),
+    # exactly as the reference does -- the inner objective uses softmax(z, 0), the outer one the joint softmax over
+    # cat(z, nc * one_hot(y)).  Gradients reach z through torch autograd on those two (tiny) softmaxes.
+    def _soft_rows(self, x, t):
+        """[R, D] rows and [R, C] targets -> (R C rows, labels 0..C-1 repeated, flattened targets)."""
+        R, C = t.shape
+        return (x.repeat_interleave(C, 0).contiguous(), torch.arange(C, device=x.device, dtype=torch.int32).repeat(R),
+                t.reshape(-1).float().contiguous())
+
+    def _soft_targets(self, yb=None):
+        z = self.z
+        t_in = torch.softmax(z, 0)
+        if yb is None:
+            return t_in, None, None
+        L = torch.cat([z, self.nc * torch.nn.functional.one_hot(yb.to(torch.int64), num_classes=self.nc).to(z.dtype)])
+        t_all = torch.softmax(L, 0)
+        return t_in, t_all[:z.shape[0]], t_all[z.shape[0]:]
+
+    def _require_single_rank_learn_z(self):
+        if _dist_info()[2] > 1:
+            raise NotImplementedError("learn_z couples all rows of a minibatch through softmax(0): not sharded over ranks")
+
+    def _inner_elbo_learn_z(self, model):
+        eng, S = self._stream(model), model.n_samples()
+        u, _ = self._uv()
+        a = self._a()
+        t_in = self._soft_targets()[0].detach().float()
+        ue, le, te = self._soft_rows(u, t_in)
+        val, g = eng.inner_grad(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], ue, le, (a[:, None] * t_in).reshape(-1))
+        self._last_inner = g
+        return (val + S * (a.double() * torch.xlogy(t_in, t_in).sum(1).double()).sum()).float()
+
+    def _psvi_elbo_learn_z(self, model, xb, yb):
+        eng, S = self._stream(model), model.n_samples()
+        u, _ = self._uv()
+        a, N, B = self._a(), float(self.N), xb.shape[0]
+        _, t_p, t_d = (t.detach().float() for t in self._soft_targets(yb))
+        ue, le, _ = self._soft_rows(u, t_p)
+        xe, ye, dw = self._soft_rows(xb, t_d)
+        ex = {}
+        loss, pbar, ubar, abar, _ = eng.outer_grad(eng.fam.get_phi(), self._noise_tensor(1, eng.Pt, S)[0], ue, le,
+                                                   (a[:, None] * t_p).reshape(-1), xe, ye, N, n_total=B, data_w=dw, extras=ex)
+        M, C = t_p.shape
+        vg, ag = self._v_grad_from_abar((t_p * abar.reshape(M, C)).sum(1))
+        self._last_outer = dict(phi_grad=pbar, u_grad=ubar.reshape(M, C, -1).sum(1), v_grad=vg, alpha_grad=ag)
+        return loss + (N / B) * torch.xlogy(t_d, t_d).sum()
+
+    def _nested_step_learn_z(self, model, S, xbatch, ybatch):
+        """nested_step with soft pseudo-labels (reference :541-600 with :455-474,499-504): hypergradients on u, v AND z."""
+        self._require_single_rank_learn_z()
+        eng = self._stream(model)
+        T, lr, N = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"]), float(self.N)
+        u, _ = self._uv()
+        xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
+        yb = ybatch.detach().to(self.device)
+        a, B = self._a(), xb.shape[0]
+        t_in, t_p, t_d = self._soft_targets(yb)                      # autograd graph z -> targets
+        tin, tp, td = t_in.detach().float(), t_p.detach().float(), t_d.detach().float()
+        M, C = tin.shape
+        ue, le, _ = self._soft_rows(u, tin)
+        xe, ye, dw = self._soft_rows(xb, td)
+        ex = {}
+        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), ue, le,
+                                                 (a[:, None] * tin).reshape(-1), xe, ye, N, T, lr,
+                                                 want_losses=self.register_elbos, n_total=B,
+                                                 a_outer=(a[:, None] * tp).reshape(-1), data_w=dw, extras=ex)
+        eng.fam.set_phi(phi_T)
+        ab_out = ex["abar_outer"].reshape(M, C)
+        ab_in = abar.reshape(M, C) - ab_out
+        kd = (N / B) * torch.xlogy(t_d, t_d).sum()                   # the data rows' sum t log t (times sum_s w_s = 1)
+        loss = loss + kd.detach().float()
+        if self.register_elbos:
+            kin = S * (a.double() * torch.xlogy(tin, tin).sum(1).double()).sum()
+            ilc = (il.double() + kin).cpu()
+            for in_it in range(0, T, max(int(self.log_every), 1)):
+                self.elbos.append((1, -ilc[in_it].item()))
+            self.elbos.append((0, -loss.item()))
+        # dLoss/dz: chain dLoss/dt (pseudo rows: a_m * d/d(a_m t_mc); data rows: dwbar) through the two softmaxes over rows
+        surrogate = ((t_in * (a[:, None] * ab_in).to(t_in.dtype)).sum() + (t_p * (a[:, None] * ab_out).to(t_p.dtype)).sum()
+                     + (t_d * ex["dwbar"].reshape(B, C).to(t_d.dtype)).sum() + kd)
+        self.z.grad = torch.autograd.grad(surrogate, self.z)[0]
+        vg, ag = self._v_grad_from_abar((tin * ab_in).sum(1) + (tp * ab_out).sum(1))
+        self.u.grad = ubar.reshape(M, C, -1).sum(1).to(self.u.dtype).reshape(self.u.shape)
+        if self.learn_v:
+            self.v.grad = vg.to(self.v.dtype)
+        if self.alpha is not None and self.alpha.requires_grad and ag is not None:
+            self.alpha.grad = ag.to(self.alpha.dtype)
+        self._step_outer_optimisers()
+        if self.scheduler_optim_net:
+            self.scheduler_optim_net.step()
+        if self.optim_z is not None:
+            self.optim_z.step()
+        return loss
+
+    def _evaluate_learn_z(self, model, S, correction):
+        """evaluate() with soft labels (reference :1049-1056): the pseudo term is summed over classes AND samples before it
+        meets N f(v), so it shifts every log-weight equally -- the importance weights are softmax(sampled_nkl)."""
+        eng = self._stream(model)
+        xt, yt = self._device_dataset(self._test_ds(), "test")
+        batch = int(self.data_minibatch)
+        n_slabs = -(-xt.shape[0] // batch)
+        out = eng.evaluate(eng.fam.get_phi(), self._noise_tensor(n_slabs, eng.Pt, S), None, None, None, xt, yt, batch,
+                           mode=0 if correction else 1)
+        vs = self.f(self.v.detach(), 0)
+        v_entropy = vs.sum().square() / vs.square().sum() / self.num_pseudo if self.compute_weights_entropy else None
+        return (out[1] / out[2], out[0] / out[2], out[3] if self.compute_weights_entropy else None, out[4], v_entropy)
 
     def _fused(self, model, fn):
         """Run fn() on the fused engine; if the model does not fit it, remember that and return None."""
@@ -307,6 +423,8 @@ class PSVI(object):
         model, desc, S = self._model_desc(model)
         xb = xbatch.detach().to(self.device, torch.float32).reshape(xbatch.shape[0], -1).contiguous()
         yb = ybatch.detach().to(self.device).to(torch.int32).contiguous()
+        if self.learn_z:
+            return self._psvi_elbo_learn_z(model, xb, yb)
         if not self._use_stream(model):
             out = self._fused(model, lambda: self._psvi_elbo_fused(model, desc, xb, yb))
             if out is not None:
@@ -336,6 +454,8 @@ class PSVI(object):
     def inner_elbo(self, model=None, params=None, hyperopt=False):
         """Negative ELBO on the pseudo-data (reference :488-511).  Gradient wrt (mu, rho) in `self._last_inner`."""
         model, desc, S = self._model_desc(model)
+        if self.learn_z:
+            return self._inner_elbo_learn_z(model)
         if not self._use_stream(model):
             out = self._fused(model, lambda: self._inner_elbo_fused(model, desc))
             if out is not None:
@@ -357,7 +477,8 @@ class PSVI(object):
 
     # ------------------------------------------------------------------------------------------------ optimisation
     def _zero_grads(self):
-        for o in (self.optim_u, self.optim_net, self.optim_v if self.learn_v else None, getattr(self, "optim_alpha", None)):
+        for o in (self.optim_u, self.optim_net, self.optim_v if self.learn_v else None, getattr(self, "optim_alpha", None),
+                  self.optim_z if self.learn_z else None):
             if o is not None:
                 o.zero_grad()
 
@@ -368,6 +489,8 @@ class PSVI(object):
             raise NotImplementedError("truncated=True is never taken by run_psvi (SURVEY.md section 8a, a8)")
         self._zero_grads()
         model, desc, S = self._model_desc()
+        if self.learn_z:
+            return self._nested_step_learn_z(model, S, xbatch, ybatch)
         if not self._use_stream(model):
             out = self._fused(model, lambda: self._nested_step_fused(model, desc, S, xbatch, ybatch))
             if out is not None:
@@ -500,6 +623,8 @@ class PSVI(object):
         of the inner objective -- each one fused CUDA pass.  Noise is consumed in the reference's order (the JVP's
         double-VJP evaluates Phi twice, the first draw is discarded)."""
         from psvi.hypergrad.hypergradients import cg_normaleq_native, fixed_point_native
+        if self.learn_z:
+            raise NotImplementedError("--trainer hyper with learn_z (soft pseudo-labels) is not built; use --trainer nested")
         if self._outer_kind != "psvi":
             # PSVI_Ablated / PSVI_No_IW: the reference's outer_loss_function would call the ablated psvi_elbo (and, for
             # No_IW, the mc_samples == 1 label-broadcast quirk of inner_elbo); the implicit solvers here differentiate the
@@ -717,6 +842,8 @@ class PSVI(object):
         self.scheduler_optim_net = torch.optim.lr_scheduler.StepLR(self.optim_net, **scheduler_kwargs)
         if self.learn_v:
             self.optim_v = torch.optim.Adam([self.v], lr0v)
+        if self.learn_z:
+            self.optim_z = torch.optim.Adam([self.z], lr0z)          # reference :869-870
         self._lr0joint = lr0joint
         optimizers = {"alternating": self.alternating_step, "nested": self.nested_step, "hyper": self.hyper_step,
                       "joint": self.joint_step}        # reference :871-886
@@ -822,6 +949,8 @@ class PSVI(object):
         Returns (acc, nll, iw_entropy, ness, v_entropy) as 0-dim tensors."""
         assert self.mc_samples > 1
         model, desc, S = self._model_desc()
+        if self.learn_z:
+            return self._evaluate_learn_z(model, S, correction)
         xt, yt = self._device_dataset(self._test_ds(), "test")
         large_fn = isinstance(model, MeanFieldMLP) and not isinstance(model, MeanFieldLeNet) and self._is_large_fn(model)
         if large_fn:
@@ -1121,7 +1250,53 @@ class PSVI_No_IW(PSVI_Ablated):
             set_mc_samples(self.model, mc_samples_train)  # single-sample for training
 
 
-PSVIEvaluate = _out_of_scope("PSVIEvaluate", "reference psvi_classes.py:1885")
+class PSVIEvaluate(PSVI):
+    r"""Evaluation of a FIXED coreset (reference :1885-1938): only the network is (re)trained -- nested_step runs the T inner
+    Adam steps on the soft-label inner objective, reports psvi_elbo at the result and copies the fast weights back; u, z, v and
+    alpha stay as they are (no hypergradient is taken: the reference calls backward() on frozen leaves).  The coreset comes from
+    the standard initialisers here; the reference's loaders of saved distilled sets (custom_init*, :310-443) are out of scope."""
+
+    _vmode = _native.VMODE_EXPALPHA_SOFTMAX
+
+    def __init__(self, learn_v=False, parameterised=False, **kwargs):
+        kwargs.pop("learn_z", None)
+        super().__init__(learn_z=True, **kwargs)
+        self.learn_v = False
+        self.alpha = torch.tensor([0.0], device=self.device)
+        self.f = lambda *x: torch.exp(self.alpha.detach()) * torch.softmax(x[0], x[1])
+        self.ablated_weights = self.ablated_alpha = self.ablated_labels = True
+
+    def nested_step(self, xbatch, ybatch):
+        from psvi.inference.stream import B1, B2
+        self._require_single_rank_learn_z()
+        model, _, S = self._model_desc()
+        eng = self._stream(model)
+        T, lr = int(self.inner_it), float(self.optim_net.param_groups[0]["lr"])
+        u, _ = self._uv()
+        a = self._a()
+        tin = self._soft_targets()[0].detach().float()
+        ue, le, _ = self._soft_rows(u, tin)
+        ae = (a[:, None] * tin).reshape(-1)
+        a_exp = ae.expand(S, ae.numel()).contiguous()
+        kin = S * (a.double() * torch.xlogy(tin, tin).sum(1).double()).sum()
+        phi = eng.fam.get_phi().contiguous()
+        m, v = torch.zeros_like(phi), torch.zeros_like(phi)
+        eps_all = eng.fam.fix_eps(self._noise_tensor(T, eng.Pt, S))
+        for t in range(T):
+            log = self.register_elbos and t % max(int(self.log_every), 1) == 0
+            val, g = eng.inner_grad(phi, eps_all[t], ue, le, ae, want_val=log, a_exp=a_exp, fixed=True)
+            if log:
+                self.elbos.append((1, -(val + kin).item()))
+            phi, m, v = _native.adam_unroll_step(phi, g, m, v, lr / (1.0 - B1 ** (t + 1)), math.sqrt(1.0 - B2 ** (t + 1)))
+        eng.fam.set_phi(phi)
+        loss = self.psvi_elbo(xbatch, ybatch, model=self.model)
+        if self.register_elbos:
+            self.elbos.append((0, -loss.item()))
+        if self.scheduler_optim_net:
+            self.scheduler_optim_net.step()
+        return loss
+
+
 PSVI_regressor = _out_of_scope("PSVI_regressor", "reference psvi_classes.py:1940")
 PSVILearnV_regressor = _out_of_scope("PSVILearnV_regressor", "reference psvi_classes.py:2100")
 PSVIAV_regressor = _out_of_scope("PSVIAV_regressor", "reference psvi_classes.py:2200")

@@ -284,11 +284,13 @@ class StreamEngine:
 
     ROW_CHUNK = 8192   # data rows per network pass when the minibatch is large (full-data term, sharded over ranks)
 
-    def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None, xb_bf16=None):
+    def outer_grad(self, phi, eps, u, z32, a, xb, yb32, N, kappa=1.0, n_total=None, xb_bf16=None, data_w=None, extras=None):
         """psvi_elbo value and gradients.  `kappa` / `n_total` describe one rank's share when the data rows are sharded over
         R ranks: L_r = sum_s w_s (d_s^r - kappa p_s) - kappa mean(lw), kappa = 1/R, d_s^r = (N / n_total) * sum over
         this rank's rows; the shares (value and every gradient) add up to the unsharded objective because the importance
-        weights depend on the pseudo-data only.  Large minibatches are processed in chunks of ROW_CHUNK rows."""
+        weights depend on the pseudo-data only.  Large minibatches are processed in chunks of ROW_CHUNK rows.
+        `data_w` [B] (optional): per-row weights of the data term, d_s = (N / n_total) sum_b data_w_b nll[s, b] (the soft-label
+        rows of learn_z); `extras` then receives "dwbar" = dLoss / d data_w."""
         if xb_bf16 is not None:
             return self._outer_grad_fulldata(phi, eps, u, z32, a, xb_bf16, yb32, N, kappa, n_total)
         S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
@@ -300,8 +302,10 @@ class StreamEngine:
             nll = torch.empty(S, M + B, device=dev)
             self.net.pass_(theta, None, X, lab, None, nll=nll)
             nd = nll.double()
-            nll_u, ds_sum = nll[:, :M], nd[:, M:].sum(1)
+            nll_u, ds_sum = nll[:, :M], (nd[:, M:].sum(1) if data_w is None else nd[:, M:] @ data_w.double())
         else:
+            if data_w is not None:
+                raise NotImplementedError("per-row data weights are built for minibatches of at most ROW_CHUNK rows")
             nll_u = torch.empty(S, M, device=dev)
             self.net.pass_(theta, None, u, z32, None, nll=nll_u)
             ds_sum = torch.zeros(S, device=dev, dtype=torch.float64)
@@ -322,7 +326,9 @@ class StreamEngine:
         wd = (w * N / n_total).float()
         tbar = torch.empty(S, self.Pt, device=dev)
         if M + B <= self.ROW_CHUNK:
-            cw = torch.cat([cw_u, wd[:, None].expand(S, B)], 1).contiguous()
+            cw = torch.cat([cw_u, wd[:, None].expand(S, B) if data_w is None else wd[:, None] * data_w[None, :]], 1).contiguous()
+            if extras is not None and data_w is not None:
+                extras["dwbar"] = ((w * N / n_total) @ nd[:, M:]).float()
             xbar = torch.empty(S, M + B, X.shape[1], device=dev)
             self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
             xbar_u, nll_u = xbar[:, :M], nll[:, :M]
@@ -418,11 +424,13 @@ class StreamEngine:
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
     def nested(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None, reduce_fn=None,
-               outer="psvi", xb_bf16=None):
+               outer="psvi", xb_bf16=None, a_outer=None, data_w=None, extras=None):
         """eps_all [T+1, S, P].  Returns loss, ubar [M,D], abar [M], phi_T, inner losses (list or None).
         Sharded data term: pass this rank's rows with kappa = 1/world, n_total = rows over all ranks and a `reduce_fn` that
         all-reduces (loss, pbar, ubar, abar) -- the ONE exchange step of the bilevel step; the inner loop and
-        the reverse sweep are replicated (identical seeds => identical trajectories on every rank)."""
+        the reverse sweep are replicated (identical seeds => identical trajectories on every rank).
+        `a_outer` (pseudo-row weights of the OUTER objective when they differ from the inner ones), `data_w` and `extras`
+        serve the soft-label rows of learn_z: extras gets "abar_outer" (the outer objective's direct dLoss/da) and "dwbar"."""
         eps_all = self.fam.fix_eps(eps_all)
         a_exp = a.expand(self.S, u.shape[0]).contiguous()
         phi = phi.contiguous()
@@ -439,8 +447,11 @@ class StreamEngine:
             loss, pbar = self.outer_grad_ablated(phi, eps_all[T], xb, yb32, N, kappa=kappa, n_total=n_total)
             ubar, abar = torch.zeros_like(u), torch.zeros_like(a)
         else:
-            loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total,
-                                                        xb_bf16=xb_bf16)
+            loss, pbar, ubar, abar, _ = self.outer_grad(phi, eps_all[T], u, z32, a if a_outer is None else a_outer, xb, yb32, N,
+                                                        kappa=kappa, n_total=n_total, xb_bf16=xb_bf16, data_w=data_w,
+                                                        extras=extras)
+            if extras is not None:
+                extras["abar_outer"] = abar.clone()
         if reduce_fn is not None:
             loss, pbar, ubar, abar = reduce_fn(loss, pbar, ubar, abar)
         phi_T = phi
@@ -484,7 +495,9 @@ class StreamEngine:
         for k, r0 in enumerate(range(0, n, batch)):
             theta = self.fam.sample(phi, eps_slabs[k])
             lw = None
-            if mode == 0:
+            if mode == 0 and (u is None or u.shape[0] == 0):
+                lw = self.fam.nkl(phi, eps_slabs[k], theta).float().contiguous()     # no pseudo term: weights from nkl alone
+            elif mode == 0:
                 M = u.shape[0]
                 nll = torch.empty(S, M, device=dev)
                 self.net.pass_(theta, None, u, z32, None, nll=nll)

@@ -10,6 +10,8 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
   fixedpoint_fn_hm.npz   PSVI.hyper_step with hypergrad_approx="fixed_point" (hypergradients.py:83-140)
   joint_fn_hm.npz / alternating_fn_hm.npz   two joint_step / alternating_step calls (psvi_classes.py:517-539); made by
                          `python oracle/make_goldens_r2.py trainers`
+  learnz_fn_fb.npz       learn_z=True (soft pseudo-labels, KLDiv branch): inner_elbo, psvi_elbo, one nested_step with z.grad, and
+                         evaluate(); made by `python oracle/make_goldens_r2.py learnz`
 
 Noise is injected through oracle.ref_import.NoiseFeeder (fixtures store the seed only).
 """
@@ -220,7 +222,67 @@ def run_joint_alternating(trainer, name, H=20, M=10, S=6, B=64, steps=2, init_sd
     print(name, "forwards", out["n_forwards"], "losses", losses, "size", os.path.getsize(pth))
 
 
+def run_learn_z(name="learnz_fn_fb", dnm="four_blobs", H=12, M=8, S=5, T=3, B=16, init_sd=1e-2, lr0net=1e-3, lr0z=1e-2):
+    """learn_z=True (soft pseudo-labels, the KLDiv branch of psvi_elbo / inner_elbo / evaluate: psvi_classes.py:455-474,
+    499-504,1049-1056; z.grad and optim_z :546-547,594-595): one nested_step in fp64, then evaluate()."""
+    x, y, xt, yt, N, D, tr, te, nc = get_data(dnm)
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10,
+              lr0u=1e-4, lr0net=lr0net, lr0v=1e-3, lr0z=lr0z, init_args="subsample", init_sd=init_sd, num_pseudo=M, seed=0,
+              architecture="fn", n_hidden=H, n_layers=1, logistic_regression=False, train_dataset=tr, test_dataset=te,
+              dnm=dnm, nc=nc, data_folder="/tmp/psvi_data", compute_weights_entropy=True, register_elbos=False, learn_z=True)
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        obj = rc.PSVILearnV(**kw)
+        obj.run_psvi(**kw)
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(21)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    z0 = (obj.z.detach().numpy() + 0.5 * rng.standard_normal((M, nc))).astype(np.float32)     # soft labels off the one-hot init
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = torch.tensor(z0, dtype=tdt).requires_grad_(True)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u = torch.optim.Adam([obj.u], 1e-4)
+    obj.optim_v = torch.optim.Adam([obj.v], 1e-3)
+    obj.optim_z = torch.optim.Adam([obj.z], lr0z)
+    obj.scheduler_optim_net = None
+    xb, yb = x[:B].to(tdt), y[:B].to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, lr0net=lr0net, lr0z=lr0z, noise_seed=7878, vmode=1, dnm=dnm,
+               mu0=mu0, rho0=rho0, u0=obj.u.detach().numpy().copy(), z0=z0.astype(np.float64), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy(), xt=xt.numpy().copy(), yt=yt.numpy().copy())
+    with NoiseFeeder(dims, S, 7878) as nf, _quiet():
+        ie = obj.inner_elbo(model=obj.model)
+        out["ref64_inner_elbo"] = ie.item()
+        oe = obj.psvi_elbo(xb, yb, model=obj.model)
+        out["ref64_psvi_elbo"] = oe.item()
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_gu"], out["ref64_gv"], out["ref64_gz"] = (obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy(),
+                                                              obj.z.grad.numpy().copy())
+        out["ref64_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_u_after"], out["ref64_v_after"], out["ref64_z_after"] = (
+            obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy(), obj.z.detach().numpy().copy())
+        out["n_forwards_step"] = len(nf.history)
+        obj.model.to(torch.float32)            # evaluate() feeds fp32 test batches through the model
+        obj.u, obj.z, obj.v = obj.u.detach().float(), obj.z.detach().float(), obj.v.detach().float()
+        acc, nll, went, ness, vent = obj.evaluate()
+        out["ref32_eval"] = np.array([acc.item(), nll.item(), went.item(), ness.item(), vent.item()])
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **out)
+    print(name, "forwards", out["n_forwards_step"], out["n_forwards"], "inner", out["ref64_inner_elbo"], "outer", out["ref64_psvi_elbo"],
+          "loss", out["ref64_nested_loss"], "|gz|", np.abs(out["ref64_gz"]).max(), "eval", out["ref32_eval"], "size",
+          os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "learnz":
+        run_learn_z()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "trainers":
         run_joint_alternating("joint", "joint_fn_hm")
         run_joint_alternating("alternating", "alternating_fn_hm")

@@ -425,6 +425,145 @@ def alternating_steps(mu, rho, eps_steps, u, z, v, xb, yb, N, dims, lr_net, lr_u
     return np.array(losses), net["mu"][0], net["rho"][0], us[0], v.copy()
 
 
+# ------------------------------------------------------------------- learn_z: soft pseudo-labels (KLDiv branch)
+def soft_targets(L):
+    """`labels.softmax(0)` of the reference (psvi_classes.py:469-470,501-502): the label matrix [R, C] is normalised over the
+    ROWS (dim 0), per class column -- the rows of a column sum to 1, the classes of a row do not."""
+    return softmax(L, 0)
+
+
+def soft_targets_vjp(L, G):
+    """dLoss/dL given G = dLoss/dt for t = softmax(L, 0)."""
+    t = softmax(L, 0)
+    return t * (G - (t * G).sum(0, keepdims=True))
+
+
+def _xlogx(t):
+    return np.where(t > 0, t * np.log(np.where(t > 0, t, 1.0)), 0.0)
+
+
+def soft_nll_rows(logits, t):
+    """KLDivLoss(reduction="none")(log_softmax(logits), t).sum(classes) (psvi_classes.py:467-474): [S, R], plus softmax p and
+    log-softmax."""
+    ls = log_softmax(logits)
+    return _xlogx(t).sum(-1)[None, :] - (t[None] * ls).sum(-1), np.exp(ls), ls
+
+
+def inner_grad_soft(mu, rho, eps, u, t, a, dims):
+    """value, d/dmu, d/drho of inner_elbo with soft targets t [M, C] (psvi_classes.py:488-511, learn_z branch)."""
+    theta = mf_sample(mu, rho, eps)
+    logits, cache = mlp_forward(theta, u, dims)
+    nll, p, _ = soft_nll_rows(logits, t)
+    obar = a[None, :, None] * (t.sum(-1)[None, :, None] * p - t[None])
+    tb, _ = mlp_backward(theta, cache, dims, obar)
+    mu_bar, rho_bar = reparam_grad(mu, rho, eps, tb)
+    return np.sum(nll @ a) + mf_kl(mu, rho), mu_bar, rho_bar
+
+
+def inner_hvp_soft(mu, rho, eps, u, t, a, dims, mu_dot, rho_dot):
+    """(H_phiphi g, H_uphi g, H_aphi g, H_tphi g) of the soft-target inner objective for g = (mu_dot, rho_dot)."""
+    sg, sig = softplus(rho), sigmoid(rho)
+    theta = mu[None] + sg[None] * eps
+    theta_dot = mu_dot[None] + (sig * rho_dot)[None] * eps
+    o, od, cache = mlp_dual_forward(theta, theta_dot, u, dims)
+    _, p, _ = soft_nll_rows(o, t)
+    tau = t.sum(-1)[None, :, None]
+    q = tau * p - t[None]
+    c = a[None, :, None]
+    lsd = od - (p * od).sum(-1, keepdims=True)          # d/d eps of log_softmax
+    A_od = c * q
+    A_o = c * tau * p * lsd
+    A_c = (q * od).sum(-1).sum(0)                        # [M]  (= sum_s d/d eps of nll[s, m])
+    A_tt = -(c * lsd).sum(0)                             # [M, C]  d/d eps of d inner / d t
+    A_t, A_td, A_x = mlp_dual_backward(theta, theta_dot, cache, dims, A_o, A_od)
+    hmu = A_t.sum(0) + mu_dot
+    hrho = (sig * (A_t * eps).sum(0)
+            + sig * (1 - sig) * rho_dot * (A_td * eps).sum(0)
+            + ((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rho_dot)
+    return hmu, hrho, A_x.sum(0), A_c, A_tt
+
+
+def psvi_elbo_grad_soft(mu, rho, eps, u, t_all, a, xb, N, dims):
+    """value and d/dmu, d/drho, d/du, d/da, d/dt_all of psvi_elbo with soft targets t_all [M + B, C] (psvi_classes.py:445-486,
+    learn_z branch: the data rows carry nc * one_hot(y) pushed through the same softmax over rows)."""
+    theta = mf_sample(mu, rho, eps)
+    M, B = u.shape[0], xb.shape[0]
+    X = np.concatenate([u, xb], 0)
+    logits, cache = mlp_forward(theta, X, dims)
+    nll, p, ls = soft_nll_rows(logits, t_all)
+    S = eps.shape[0]
+    ps, ds = nll[:, :M] @ a, (N / B) * nll[:, M:].sum(-1)
+    lw = -ps + mf_sampled_nkl(mu, rho, eps, theta)
+    w = softmax(lw, 0)
+    e = ds - ps
+    loss = np.sum(w * e) - lw.mean()
+    beta = w * (e - np.sum(w * e)) - 1.0 / S
+    gp = -w - beta
+    rw = np.concatenate([gp[:, None] * a[None, :], np.broadcast_to((w * N / B)[:, None], (S, B))], 1)
+    obar = rw[:, :, None] * (t_all.sum(-1)[None, :, None] * p - t_all[None])
+    tb, xbar = mlp_backward(theta, cache, dims, obar)
+    tb = tb - beta[:, None] * theta
+    sg = softplus(rho)
+    mu_bar, rho_bar = reparam_grad(mu, rho, eps, tb, kl_coef=0.0, rho_extra=beta.sum() / sg)
+    a_bar = gp @ nll[:, :M]
+    dnll_dt = np.where(t_all > 0, np.log(np.where(t_all > 0, t_all, 1.0)) + 1.0, 0.0)[None] - ls      # [S, R, C]
+    t_bar = (rw[:, :, None] * dnll_dt).sum(0)
+    return loss, mu_bar, rho_bar, xbar[:, :M].sum(0), a_bar, t_bar
+
+
+def nested_step_learn_z(mu, rho, eps_inner, eps_outer, u, z, v, xb, yb, N, dims, lr, nc, vmode=1, alpha=0.0):
+    """PSVI.nested_step with learn_z=True (psvi_classes.py:541-600 with the KLDiv branches :455-474,499-504): the inner
+    objective sees t_in = softmax(z, 0), the outer one t_all = softmax(cat(z, nc * one_hot(y)), 0); hypergradients on u, v and
+    the soft labels z."""
+    T, P, M = eps_inner.shape[0], mu.shape[0], u.shape[0]
+    a = coreset_weights(v, N, vmode, alpha)
+    t_in = soft_targets(z)
+    L_all = np.concatenate([z, nc * np.eye(nc)[yb.astype(np.int64)]], 0)
+    t_all = soft_targets(L_all)
+    phi = np.concatenate([mu, rho])
+    m = np.zeros_like(phi); vv = np.zeros_like(phi)
+    traj = []
+    for k in range(T):
+        _, gmu, grho = inner_grad_soft(phi[:P], phi[P:], eps_inner[k], u, t_in, a, dims)
+        g = np.concatenate([gmu, grho])
+        phi_new, m, vv = robust_adam_step(phi, g, m, vv, k + 1, lr)
+        traj.append((phi, g, m, vv))
+        phi = phi_new
+    loss, mu_bar, rho_bar, u_bar, a_bar, tall_bar = psvi_elbo_grad_soft(phi[:P], phi[P:], eps_outer, u, t_all, a, xb, N, dims)
+    pbar = np.concatenate([mu_bar, rho_bar])
+    mbar = np.zeros_like(pbar); vbar = np.zeros_like(pbar)
+    tin_bar = np.zeros_like(t_in)
+    for k in range(T - 1, -1, -1):
+        phi_t, g, m_t, v_t = traj[k]
+        gbar, mbar, vbar = robust_adam_step_vjp(pbar, mbar, vbar, g, m_t, v_t, k + 1, lr)
+        hmu, hrho, hu, ha, ht = inner_hvp_soft(phi_t[:P], phi_t[P:], eps_inner[k], u, t_in, a, dims, gbar[:P], gbar[P:])
+        pbar = pbar + np.concatenate([hmu, hrho])
+        u_bar, a_bar, tin_bar = u_bar + hu, a_bar + ha, tin_bar + ht
+    v_bar, _ = coreset_weights_vjp(v, N, vmode, a_bar, alpha)
+    z_bar = soft_targets_vjp(z, tin_bar) + soft_targets_vjp(L_all, tall_bar)[:M]
+    return dict(loss=loss, u_grad=u_bar, v_grad=v_bar, z_grad=z_bar, mu_T=phi[:P], rho_T=phi[P:])
+
+
+def evaluate_learn_z(mu, rho, eps_batches, xt, yt, dims, batch):
+    """PSVI.evaluate with learn_z=True (psvi_classes.py:1049-1056): the pseudo term is summed over classes AND samples before
+    it meets the weights, so it shifts every log-weight equally and the importance weights reduce to softmax(sampled_nkl)."""
+    nll_sum, correct, k, w = 0.0, 0, 0, None
+    for r0 in range(0, xt.shape[0], batch):
+        eps = eps_batches[k]; k += 1
+        theta = mf_sample(mu, rho, eps)
+        logits, _ = mlp_forward(theta, xt[r0:r0 + batch], dims)
+        w = softmax(mf_sampled_nkl(mu, rho, eps, theta), 0)
+        probs = (softmax(logits, -1) * w[:, None, None]).sum(0)
+        lab = yt[r0:r0 + batch].astype(np.int64)
+        pn = probs / probs.sum(-1, keepdims=True)
+        pn = np.clip(pn, np.finfo(np.float32).eps, 1 - np.finfo(np.float32).eps)
+        nll_sum += -np.log(pn[np.arange(len(lab)), lab]).sum()
+        correct += (probs.argmax(-1) == lab).sum()
+    n = xt.shape[0]
+    S = w.shape[0]
+    return correct / n, nll_sum / n, -(w * np.log(w)).sum(), (w.sum() ** 2 / (w * w).sum()) / S
+
+
 # ------------------------------------------------------------------------------------ evaluate (a11, Q3, Q12)
 def evaluate(mu, rho, eps_batches, u, z, a, xt, yt, dims, batch, correction=True):
     """PSVI.evaluate (psvi_classes.py:1031-1108).  eps_batches[k] is the draw of test batch k.

@@ -264,3 +264,66 @@ def test_run_mfvi_subset_for_fn2_and_lenet(arch):
     else:   # fn2 starts from zero means (make_fc2net): a symmetric point the first steps leave only slowly; stay finite / sane
         assert abs(np.mean(res["elbos"][-5:]) - np.mean(res["elbos"][:5])) < 0.05 * abs(np.mean(res["elbos"][:5]))
     assert all(0.0 <= a <= 1.0 for a in res["accs"])
+
+
+def test_learn_z_soft_labels_match_reference():
+    """learn_z=True (reference psvi_classes.py:455-474,499-504,546-547,594-595,1049-1056): inner_elbo, psvi_elbo, one
+    nested_step with hypergradients on u, v AND the soft labels z, the optim_z update, evaluate(); then PSVIEvaluate and
+    run_psvi end to end.  The kernels see every soft-label row as C weighted hard-label rows."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.experiments_utils import SynthDataset, read_dataset
+    from psvi.inference.psvi_classes import ExternalNoise, PSVIEvaluate, PSVILearnV
+    g = dict(np.load(os.path.join(GOLDEN, "learnz_fn_fb.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, M, B = int(g["S"]), int(g["T"]), int(g["M"]), int(g["B"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    torch.manual_seed(0)
+    x, y, xt, yt, N, D, tr, te, nc = read_dataset("four_blobs", {"test_ratio": 0.2})
+    te = SynthDataset(torch.as_tensor(g["xt"]).float(), torch.as_tensor(g["yt"]).float())     # the golden's own test rows
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", log_every=10, lr0u=1e-4,
+              lr0net=float(g["lr0net"]), lr0v=1e-3, lr0z=float(g["lr0z"]), init_args="subsample", init_sd=1e-2, num_pseudo=M,
+              seed=0, architecture="fn", n_hidden=dims[1], n_layers=1, logistic_regression=False, train_dataset=tr,
+              test_dataset=te, dnm="four_blobs", nc=nc, compute_weights_entropy=True, register_elbos=False, quiet=True,
+              learn_z=True)
+    obj = PSVILearnV(**kw)
+    obj.run_psvi(**kw)
+    assert obj.z.shape == (M, nc) and obj.z.requires_grad and float(obj.z.sum()) == M      # one-hot initial soft labels
+    mu, rho = obj.model.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    with torch.no_grad():
+        obj.u.copy_(torch.as_tensor(g["u0"]))
+        obj.v.copy_(torch.as_tensor(g["v0"]))
+        obj.z.copy_(torch.as_tensor(g["z0"]))
+    obj.scheduler_optim_net = None
+    obj.noise_source = ExternalNoise(eps)
+    xb, yb = torch.as_tensor(g["xb"]).float().cuda(), torch.as_tensor(g["yb"]).cuda()
+    ie = float(obj.inner_elbo(model=obj.model))
+    assert abs(ie - g["ref64_inner_elbo"]) <= 2e-5 * abs(g["ref64_inner_elbo"])
+    oe = float(obj.psvi_elbo(xb, yb, model=obj.model))
+    assert abs(oe - g["ref64_psvi_elbo"]) <= 2e-5 * abs(g["ref64_psvi_elbo"])
+    loss = float(obj.nested_step(xb, yb))
+    assert obj.noise_source.pos == int(g["n_forwards_step"])
+    assert abs(loss - g["ref64_nested_loss"]) <= 2e-5 * abs(g["ref64_nested_loss"])
+    assert rel_l2(obj.u.grad.cpu().numpy(), g["ref64_gu"]) < 2e-3
+    assert rel_l2(obj.v.grad.cpu().numpy(), g["ref64_gv"]) < 2e-3
+    assert rel_l2(obj.z.grad.cpu().numpy(), g["ref64_gz"]) < 2e-3
+    vec = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().cpu().numpy()
+    assert rel_l2(vec, g["ref64_params"]) < 1e-5
+    np.testing.assert_allclose(obj.z.detach().cpu().numpy(), g["ref64_z_after"], atol=2e-5)    # Adam(lr0z) step on z
+    acc, nll, went, ness, vent = obj.evaluate()
+    assert obj.noise_source.pos == int(g["n_forwards"])
+    np.testing.assert_allclose([float(acc), float(nll), float(went), float(ness), float(vent)], g["ref32_eval"], rtol=2e-3)
+    # PSVIEvaluate: only the network trains; u, z, v stay put
+    kw.update(register_elbos=True)
+    ev = PSVIEvaluate(**kw)
+    ev.run_psvi(**kw)
+    u0, z0, v0 = ev.u.detach().clone(), ev.z.detach().clone(), ev.v.detach().clone()
+    p0 = torch.nn.utils.parameters_to_vector(ev.model.parameters()).detach().clone()
+    l1 = float(ev.nested_step(xb, yb))
+    assert np.isfinite(l1) and torch.equal(ev.u.detach(), u0) and torch.equal(ev.z.detach(), z0) and torch.equal(ev.v.detach(), v0)
+    assert not torch.equal(torch.nn.utils.parameters_to_vector(ev.model.parameters()).detach(), p0)
+    assert [t for t, _ in ev.elbos] == [1, 0]
+    # end to end
+    kw.update(num_epochs=6, log_every=3, register_elbos=False)
+    res = PSVILearnV(**kw).run_psvi(**kw)
+    assert len(res["accs"]) == 2 and np.isfinite(res["nlls"]).all()

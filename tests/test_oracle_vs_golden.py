@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating")))
+               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
 
 
 def rel_l2(a, b):
@@ -233,3 +233,35 @@ def test_joint_and_alternating_trainers_match_reference(trainer):
     assert rel_l2(po.mu_rho_to_phi(r[1], r[2], dims), g["ref64_params"]) < 1e-9
     np.testing.assert_allclose(r[3], g["ref64_u_after"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(r[4], g["ref64_v_after"], rtol=0, atol=1e-9)
+
+
+def test_learn_z_soft_labels_match_reference():
+    """learn_z=True (reference psvi_classes.py:455-474,499-504,546-547,594-595,1049-1056): soft pseudo-labels through the KLDiv
+    branch -- inner_elbo, psvi_elbo, one nested_step with the hypergradient on z, and evaluate().  Golden: `python
+    oracle/make_goldens_r2.py learnz`."""
+    g = dict(np.load(os.path.join(GOLDEN, "learnz_fn_fb.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, N, nc = int(g["S"]), int(g["T"]), float(g["N"]), int(dims[-1])
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    a = po.coreset_weights(g["v0"], N, 1)
+    t_in = po.soft_targets(g["z0"])
+    t_all = po.soft_targets(np.concatenate([g["z0"], nc * np.eye(nc)[g["yb"].astype(np.int64)]], 0))
+    val = po.inner_grad_soft(g["mu0"], g["rho0"], eps[0], g["u0"], t_in, a, dims)[0]
+    assert abs(val - g["ref64_inner_elbo"]) <= 1e-9 * abs(val)
+    out = po.psvi_elbo_grad_soft(g["mu0"], g["rho0"], eps[1], g["u0"], t_all, a, g["xb"], N, dims)[0]
+    assert abs(out - g["ref64_psvi_elbo"]) <= 1e-9 * abs(out)
+    r = po.nested_step_learn_z(g["mu0"], g["rho0"], np.stack(eps[2:2 + T]), eps[2 + T], g["u0"], g["z0"], g["v0"], g["xb"],
+                               g["yb"], N, dims, float(g["lr0net"]), nc)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-9 * abs(r["loss"])
+    assert rel_l2(po.mu_rho_to_phi(r["mu_T"], r["rho_T"], dims), g["ref64_params"]) < 1e-10
+    assert rel_l2(r["u_grad"], g["ref64_gu"]) < 1e-7
+    assert rel_l2(r["v_grad"], g["ref64_gv"]) < 1e-7
+    assert rel_l2(r["z_grad"], g["ref64_gz"]) < 1e-7
+    z1, _, _ = po.torch_adam_step(g["z0"], r["z_grad"], 0 * g["z0"], 0 * g["z0"], 1, float(g["lr0z"]))
+    np.testing.assert_allclose(z1, g["ref64_z_after"], rtol=0, atol=1e-9)
+    # evaluate(): fp32 reference run, importance weights = softmax(sampled_nkl)
+    n0 = int(g["n_forwards_step"])
+    e32 = [e.astype(np.float32) for e in eps[n0:]]
+    acc, nll, went, ness = po.evaluate_learn_z(r["mu_T"].astype(np.float32), r["rho_T"].astype(np.float32), e32,
+                                               g["xt"].astype(np.float32), g["yt"], dims, int(g["B"]))
+    np.testing.assert_allclose([acc, nll, went, ness], g["ref32_eval"][:4], rtol=2e-4)
