@@ -32,11 +32,53 @@ using namespace psvi_mf;
 namespace {
 
 constexpr int REC = 20;        // floats per hidden-unit record: [0,8) sampled weights, [8,16) tangent weights, 4 pad
-constexpr int NW = NT / 32;    // warps per CTA
+#ifndef PSVI_FN1_THREADS
+// 256.  Nine warps (288) would finish the 25 row pairs of M = 50 in three rounds of the dual pass instead of four, but the
+// register file is split per scheduler: the sub-partition that hosts three warps leaves 168 registers per thread, the dual
+// pass (230) spills and the step takes 1.43 ms instead of 1.25 ms (measured, profiles/r2_fn1_engine_ncu_summary.md).
+#define PSVI_FN1_THREADS 256
+#endif
+constexpr int NT1 = PSVI_FN1_THREADS;   // threads per CTA of THIS kernel (the generic engine's NT stays 256)
+constexpr int NW1 = NT1 / 32;           // warps per CTA
+
+// block-wide reductions for NW1 warps (the shared helpers of psvi_mf_gemm.cuh are written for 256 threads)
+__device__ __forceinline__ float block_sum1(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NW1) ? red[l] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ double block_sum_d1(double v, float* red_) {
+  double* red = reinterpret_cast<double*>(red_ + 16);  // red[16 .. 16 + 2 NW1) as doubles (red is 16-byte aligned)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < NW1; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float block_max1(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NW1) ? red[l] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return t;
+}
 
 // shared-memory carve-up (offsets in floats)
 struct FL {
-  int rec, part;                                 // [nper][(HP+1) records] ; NW x (HP+1) records of partial adjoints
+  int rec, part;                                 // [nper][(HP+1) records] ; NW1 x (HP+1) records of partial adjoints
   int q2r, pdst, pmb;                            // Pt ints: TL index -> float offset inside a record block; Pt uint32:
                                                  // shared::cluster address of recv[0][0][j] in the owner of q; of its mbarrier
   int mb;                                        // two mbarriers: [0] partials received (owner role), [1] weights received
@@ -68,7 +110,7 @@ __host__ __device__ inline void make_fl(const EP& p, FL& y) {
     return r;
   };
   y.rec = take(nper * (HP + 1) * REC);
-  y.part = take(NW * (HP + 1) * REC);
+  y.part = take(NW1 * (HP + 1) * REC);
   y.q2r = take(Pt); y.pdst = take(Pt); y.pmb = take(Pt);
   y.mb = take(4);
   y.mu = take(p.slice); y.rho = take(p.slice); y.sig = take(p.slice); y.sgm = take(p.slice);
@@ -237,7 +279,7 @@ struct Fn1 {
     const int nb = slice >> 2;  // Philox blocks per sample (slice is a multiple of 4)
     const int items = p.S * nb;
     float* dst = F(y.epsS) + (slab & 1) * p.S * slice;
-    for (int i = NT - 1 - tid; i < items; i += NT) {
+    for (int i = NT1 - 1 - tid; i < items; i += NT1) {
       const int s = i / nb, b = i - s * nb;
       const int q4 = (j0 >> 2) + b;
       float e4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -259,7 +301,7 @@ struct Fn1 {
   //      in the padded slice).  want_nkl: also the slice's share of  sampled_nkl_s = sum_i [-theta^2/2 + eps^2/2 +
   //      log sigma]  (neural_net.py:110-115), one partial per warp. ---------------------------------------------------
   __device__ void owner_sample(int slab, bool tangent, bool want_nkl) {
-    const int j = tid & ((1 << spad_sh) - 1), sg0 = tid >> spad_sh, nsg = NT >> spad_sh;
+    const int j = tid & ((1 << spad_sh) - 1), sg0 = tid >> spad_sh, nsg = NT1 >> spad_sh;
     const bool ok = j < slice && j0 + j < Pt;
     const float* ep = F(y.epsS) + (slab & 1) * p.S * slice + j;
     const float mu = ok ? F(y.mu)[j] : 0.f, sg = ok ? F(y.sig)[j] : 1.f;
@@ -271,7 +313,8 @@ struct Fn1 {
     const uint32_t mbar_rec = smem_u32(sm + y.mb + 2);
     int cta = sg0 % p.G, li = sg0 / p.G;
     const int dcta = nsg % p.G, dli = nsg / p.G;
-    for (int s = sg0; s < p.S; s += nsg) {   // (warp-uniform trip count: a warp lies inside one sample group)
+    // (warp-uniform trip count: a warp lies inside one sample group; threads past the last full group sit out)
+    for (int s = sg0 < nsg ? sg0 : p.S; s < p.S; s += nsg) {
       const float e = ok ? ep[s * slice] : 0.f;
       const float th = fmaf(sg, e, mu);
       const uint32_t rbar = mapa(mbar_rec, cta);
@@ -344,7 +387,7 @@ struct Fn1 {
 #pragma unroll
     for (int c = 0; c < C; ++c) gb2[c] = 0.f;
 
-    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW) {  // warp-uniform trip count (the shuffles need the full warp)
+    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW1) {  // warp-uniform trip count (the shuffles need the full warp)
       int r[RU], yl[RU];
       bool ok[RU];
       float x[RU][D], h[RU][UPL], o[RU][C];
@@ -500,7 +543,7 @@ struct Fn1 {
       }
     }
 
-    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW) {
+    for (int rb = 2 * RU * warp; rb < R; rb += 2 * RU * NW1) {
       int r[RU], yl[RU];
       bool ok[RU];
       float x[RU][D], cwr[RU], h[RU][UPL], hd[RU][UPL], o[RU][C], od[RU][C];
@@ -649,22 +692,22 @@ struct Fn1 {
     const uint32_t* pmb = reinterpret_cast<const uint32_t*>(sm + y.pmb);
     const float* part = F(y.part);
     const uint32_t soff = (uint32_t)(s * 2 * slice * 4);
-    for (int q = tid; q < Pt; q += NT) {
+    for (int q = tid; q < Pt; q += NT1) {
       const int r = q2r[q];
-      float v[NW];
+      float v[NW1];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) v[w] = part[w * PS + r];
+      for (int w = 0; w < NW1; ++w) v[w] = part[w * PS + r];
       float s0 = v[0];
 #pragma unroll
-      for (int w = 1; w < NW; ++w) s0 += v[w];
+      for (int w = 1; w < NW1; ++w) s0 += v[w];
       const uint32_t dst = pdst[q] + soff, obar = pmb[q];
       st_async(dst, s0, obar);
       if (ncomp > 1) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) v[w] = part[w * PS + r + 8];
+        for (int w = 0; w < NW1; ++w) v[w] = part[w * PS + r + 8];
         float s1 = v[0];
 #pragma unroll
-        for (int w = 1; w < NW; ++w) s1 += v[w];
+        for (int w = 1; w < NW1; ++w) s1 += v[w];
         st_async(dst + (uint32_t)(slice * 4), s1, obar);
       }
     }
@@ -718,23 +761,23 @@ struct Fn1 {
     float* f = F(y.f);
     const int M = p.M;
     if (p.roww) {
-      for (int m = tid; m < M; m += NT) { a[m] = __ldg(p.roww + m); f[m] = 0.f; }
+      for (int m = tid; m < M; m += NT1) { a[m] = __ldg(p.roww + m); f[m] = 0.f; }
       __syncthreads();
       return;
     }
     if (p.vmode == PSVI_VMODE_IDENTITY) {
-      for (int m = tid; m < M; m += NT) { f[m] = __ldg(p.v + m); a[m] = p.Nf * f[m]; }
+      for (int m = tid; m < M; m += NT1) { f[m] = __ldg(p.v + m); a[m] = p.Nf * f[m]; }
       __syncthreads();
       return;
     }
     float mx = -INFINITY;
-    for (int m = tid; m < M; m += NT) mx = fmaxf(mx, __ldg(p.v + m));
-    mx = block_max(mx, F(y.red));
+    for (int m = tid; m < M; m += NT1) mx = fmaxf(mx, __ldg(p.v + m));
+    mx = block_max1(mx, F(y.red));
     float se = 0.f;
-    for (int m = tid; m < M; m += NT) se += expf(__ldg(p.v + m) - mx);
-    se = block_sum(se, F(y.red));
+    for (int m = tid; m < M; m += NT1) se += expf(__ldg(p.v + m) - mx);
+    se = block_sum1(se, F(y.red));
     const float sc = p.Nf * (p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? expf(p.alpha) : 1.f);
-    for (int m = tid; m < M; m += NT) {
+    for (int m = tid; m < M; m += NT1) {
       f[m] = expf(__ldg(p.v + m) - mx) / se;
       a[m] = sc * f[m];
     }
@@ -743,14 +786,14 @@ struct Fn1 {
 
 
   __device__ void init() {
-    for (int i = tid; i < y.total; i += NT) sm[i] = 0.f;
+    for (int i = tid; i < y.total; i += NT1) sm[i] = 0.f;
     __syncthreads();
     int* q2r = I(y.q2r);
     uint32_t* pdst = reinterpret_cast<uint32_t*>(sm + y.pdst);
     const int HD = H * D;
     const uint32_t recv0 = smem_u32(F(y.recv)), mb0 = smem_u32(sm + y.mb);
     uint32_t* pmb = reinterpret_cast<uint32_t*>(sm + y.pmb);
-    for (int q = tid; q < Pt; q += NT) {
+    for (int q = tid; q < Pt; q += NT1) {
       int r;
       if (q < HD) {
         const int j = q / D;
@@ -779,16 +822,16 @@ struct Fn1 {
       F(y.rho)[tid] = r;
       softplus_sigmoid(r, F(y.sig)[tid], F(y.sgm)[tid]);
     }
-    for (int i = tid; i < p.M * D; i += NT) F(y.X)[i] = __ldg(p.u + i);
-    for (int m = tid; m < p.M; m += NT) I(y.Y)[m] = __ldg(p.z + m);
-    for (int i = tid; i < p.B * D; i += NT) F(y.X)[p.M * D + i] = __ldg(p.xb + i);
-    for (int b = tid; b < p.B; b += NT) I(y.Y)[p.M + b] = __ldg(p.yb + b);
+    for (int i = tid; i < p.M * D; i += NT1) F(y.X)[i] = __ldg(p.u + i);
+    for (int m = tid; m < p.M; m += NT1) I(y.Y)[m] = __ldg(p.z + m);
+    for (int i = tid; i < p.B * D; i += NT1) F(y.X)[p.M * D + i] = __ldg(p.xb + i);
+    for (int b = tid; b < p.B; b += NT1) I(y.Y)[p.M + b] = __ldg(p.yb + b);
     // step-size tables.  forward (rows 0..2): the reference's running products beta^t in double, as the generic engine
     // forms them; reverse (rows 3, 4): lr / (1 - beta1^(t+1)) and sqrt(1 - beta2^(t+1)) from pow().
     {
       const double B1 = 0.9, B2 = 0.999;
       float* tab = F(y.tab);
-      for (int t = tid; t < p.T; t += NT) {
+      for (int t = tid; t < p.T; t += NT1) {
         double a = pow(B1, (double)p.step0), b = pow(B2, (double)p.step0);
         for (int i = 0; i <= t; ++i) { a *= B1; b *= B2; }
         tab[t] = (float)(1.0 - a);
@@ -802,7 +845,7 @@ struct Fn1 {
     }
     __syncthreads();
     if (p.M > 0) setup_coreset();
-    for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];   // inner passes weight the rows by a_m
+    for (int m = tid; m < p.M; m += NT1) F(y.cw)[m] = F(y.a)[m];   // inner passes weight the rows by a_m
     if (p.adam_m && (p.flags & F_UNROLL) && own) {
       const int q = j0 + tid;
       OST(6) = p.adam_m[q];
@@ -932,7 +975,7 @@ __device__ void Fn1<D, C, UPL>::run() {
           const float sg = F(y.sig)[tid], m = F(y.mu)[tid];
           lpart += 0.5f * (sg * sg + m * m - 1.f) - logf(sg);
         }
-        lpart = block_sum(lpart, F(y.red));
+        lpart = block_sum1(lpart, F(y.red));
         if (tid == 0) st_async(mapa(smem_u32(F(y.lossrecv) + rank), 0), lpart, mapa(smem_u32(sm + y.mb), 0));
       }
       wait_recv(1, want_loss);
@@ -996,8 +1039,8 @@ __device__ void Fn1<D, C, UPL>::run() {
         rows_primal<0, true>(rec0 + li * PS, R, false, 0.f, ps, ds);
         // the S per-sample sums are O(N) while the importance-weight adjoints depend on their *differences*:
         // reduce and keep them in double (the fp32 reference loses ~2 digits here at init_sd=1e-6)
-        const double ps_d = block_sum_d((double)ps, F(y.red));
-        const double ds_d = block_sum_d((double)ds, F(y.red)) * (double)dscale;
+        const double ps_d = block_sum_d1((double)ps, F(y.red));
+        const double ds_d = block_sum_d1((double)ds, F(y.red)) * (double)dscale;
         double nkl_d = 0.0;
         for (int k = 0; k < G * nch; ++k) nkl_d += (double)F(y.nklp)[li * G * nch + k];
         if (tid < G) {
@@ -1058,7 +1101,7 @@ __device__ void Fn1<D, C, UPL>::run() {
       int li = 0;
       for (int s = rank; s < S; s += G, ++li) {
         const float gp = F(y.gp)[s], wd = F(y.w)[s] * dscale;
-        for (int r = tid; r < R; r += NT) F(y.cw)[r] = r < p.M ? gp * F(y.a)[r] : wd;
+        for (int r = tid; r < R; r += NT1) F(y.cw)[r] = r < p.M ? gp * F(y.a)[r] : wd;
         __syncthreads();
         float ps = 0.f, ds = 0.f;
         rows_primal<1, true>(rec0 + li * PS, R, true, gp, ps, ds);
@@ -1068,7 +1111,7 @@ __device__ void Fn1<D, C, UPL>::run() {
       }
     }
     __syncthreads();
-    for (int m = tid; m < p.M; m += NT) F(y.cw)[m] = F(y.a)[m];   // back to the inner row weights
+    for (int m = tid; m < p.M; m += NT1) F(y.cw)[m] = F(y.a)[m];   // back to the inner row weights
     wait_recv(1, false);
     // O4: owner: dLoss/dphi_T of my TL index (no analytic-KL term in the outer objective); the sampled-nkl part
     // d nkl_s / d theta = -theta_s, weighted by beta_s (A.2), is formed here from the owner's own eps_s
@@ -1127,8 +1170,8 @@ __device__ void Fn1<D, C, UPL>::run() {
       }
       if (rank == 0) {
         const int MD = p.M * D;
-        for (int i = tid; i < MD; i += NT) F(y.ubar)[i] = p.gout[2 * Pt + i];
-        for (int i = tid; i < p.M; i += NT) F(y.abar)[i] = p.gout[2 * Pt + MD + i];
+        for (int i = tid; i < MD; i += NT1) F(y.ubar)[i] = p.gout[2 * Pt + i];
+        for (int i = tid; i < p.M; i += NT1) F(y.abar)[i] = p.gout[2 * Pt + MD + i];
       }
     }
     gen_eps(p.T - 1);
@@ -1195,7 +1238,7 @@ __device__ void Fn1<D, C, UPL>::run() {
     if (rank == 0) {
       const int MD = p.M * D;
       float* red = F(y.red);
-      for (int i = tid; i < MD + p.M; i += NT) {
+      for (int i = tid; i < MD + p.M; i += NT1) {
         float s = 0.f;
         const int off = i < MD ? y.ubar + i : y.abar + (i - MD);
         for (int c = 0; c < G; ++c) s += *remote(off, c);
@@ -1204,16 +1247,16 @@ __device__ void Fn1<D, C, UPL>::run() {
       }
       __syncthreads();
       if (p.flags & F_FINAL) {
-        for (int i = tid; i < MD; i += NT) p.u_grad[i] = F(y.ubar)[i];
+        for (int i = tid; i < MD; i += NT1) p.u_grad[i] = F(y.ubar)[i];
         if (p.v_grad) {
           if (p.vmode == PSVI_VMODE_IDENTITY || p.roww) {
-            for (int m = tid; m < p.M; m += NT) p.v_grad[m] = p.Nf * F(y.abar)[m];
+            for (int m = tid; m < p.M; m += NT1) p.v_grad[m] = p.Nf * F(y.abar)[m];
           } else {
             float dot = 0.f;
-            for (int m = tid; m < p.M; m += NT) dot += F(y.f)[m] * F(y.abar)[m];
-            dot = block_sum(dot, red);
+            for (int m = tid; m < p.M; m += NT1) dot += F(y.f)[m] * F(y.abar)[m];
+            dot = block_sum1(dot, red);
             const float sc = p.Nf * (p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? expf(p.alpha) : 1.f);
-            for (int m = tid; m < p.M; m += NT) p.v_grad[m] = sc * F(y.f)[m] * (F(y.abar)[m] - dot);
+            for (int m = tid; m < p.M; m += NT1) p.v_grad[m] = sc * F(y.f)[m] * (F(y.abar)[m] - dot);
             if (p.alpha_grad && tid == 0)
               p.alpha_grad[0] = p.vmode == PSVI_VMODE_EXPALPHA_SOFTMAX ? sc * dot : 0.f;
           }
@@ -1228,7 +1271,7 @@ __device__ void Fn1<D, C, UPL>::run() {
 // constant-bank operands of the instructions that use them (a layout struct in shared memory costs a dependent LDS per
 // access).
 template <int D, int C, int UPL>
-__global__ void __launch_bounds__(NT, 1) psvi_mf_fn1_kernel(const __grid_constant__ EP p, const __grid_constant__ FL fl) {
+__global__ void __launch_bounds__(NT1, 1) psvi_mf_fn1_kernel(const __grid_constant__ EP p, const __grid_constant__ FL fl) {
   extern __shared__ __align__(16) float smem_dyn[];
   Fn1<D, C, UPL> e(p, fl, smem_dyn);
   e.run();
@@ -1251,7 +1294,7 @@ int launch_inst(EP& p, cudaStream_t stream) {
     if (G < 1) return FN1_NOT_APPLICABLE;
     p.G = G;
     p.slice = (((Pt + G - 1) / G) + 3) & ~3;   // multiple of 4: a Philox block never straddles two owners
-    if (p.slice > NT / 2) return FN1_NOT_APPLICABLE;   // two owner threads (mu, rho) per TL index
+    if (p.slice > NT1 / 2) return FN1_NOT_APPLICABLE;   // two owner threads (mu, rho) per TL index
     p.RC = 0;
     FL fl;
     make_fl<D, C, UPL>(p, fl);
@@ -1261,7 +1304,7 @@ int launch_inst(EP& p, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(G, 1, 1);
-    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.blockDim = dim3(NT1, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
