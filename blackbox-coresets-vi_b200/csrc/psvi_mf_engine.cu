@@ -171,7 +171,8 @@ struct Engine {
       }
       for (int r2 = tid; r2 < nr; r2 += NT) a0[r2 * ld0 + D] = 1.f;
     }
-    for (int rr = tid; rr < nr; rr += NT) lab[rr] = __ldg(p.yb + (r0 - p.M) + rr);
+    if (p.yb != nullptr)   // (the module-level forward has no labels)
+      for (int rr = tid; rr < nr; rr += NT) lab[rr] = __ldg(p.yb + (r0 - p.M) + rr);
     return a0;
   }
 

@@ -10,6 +10,7 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
   fixedpoint_fn_hm.npz   PSVI.hyper_step with hypergrad_approx="fixed_point" (hypergradients.py:83-140)
   joint_fn_hm.npz / alternating_fn_hm.npz   two joint_step / alternating_step calls (psvi_classes.py:517-539); made by
                          `python oracle/make_goldens_r2.py trainers`
+  meanfieldvi_hm.npz     MeanFieldVI (inference/utils.py:221-450) with forgetting scores; `python oracle/make_goldens_r2.py meanfieldvi`
   learnz_fn_fb.npz       learn_z=True (soft pseudo-labels, KLDiv branch): inner_elbo, psvi_elbo, one nested_step with z.grad, and
                          evaluate(); made by `python oracle/make_goldens_r2.py learnz`
 
@@ -279,7 +280,46 @@ def run_learn_z(name="learnz_fn_fb", dnm="four_blobs", H=12, M=8, S=5, T=3, B=16
           os.path.getsize(pth))
 
 
+def run_meanfieldvi(name="meanfieldvi_hm"):
+    """MeanFieldVI (psvi/inference/utils.py:221-450) with forgetting scores: sequential minibatches of 400 rows (two per epoch),
+    4 epochs, the 200 test rows in one batch (the reference shuffles the test loader: one batch keeps it order-free)."""
+    from psvi.inference.utils import MeanFieldVI
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    S, H, B = 5, 16, 400
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    import random
+    from psvi.experiments.experiments_utils import set_up_model
+    random.seed(3), np.random.seed(3), torch.manual_seed(3)
+    net0 = set_up_model(architecture="fn", D=D, n_hidden=H, nc=nc, mc_samples=S, init_sd=1e-2)
+    mu0, rho0 = get_mu_rho(net0)
+    dims = model_dims(net0)
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        with NoiseFeeder(dims, S, 9191) as nf, _quiet():
+            m = MeanFieldVI(mc_samples=S, data_minibatch=B, num_epochs=2, log_every=2, N=N, D=D, lr0net=1e-2, mul_fact=2, seed=3,
+                            architecture="fn", n_hidden=H, nc=nc, train_dataset=tr, test_dataset=te, init_sd=1e-2,
+                            forgetting_score_flag=True, data_path=tmp, dnm="halfmoon")
+            m.run()
+            nfw = len(nf.history)
+    finally:
+        torch.cuda.is_available = real
+    blob = dict(dims=np.array(dims), N=N, S=S, B=B, noise_seed=9191, n_forwards=nfw, lr0net=1e-2, mu0=mu0, rho0=rho0,
+                ref_elbos=np.array(m.elbos_mfvi), ref_accs=np.array(m.accs_mfvi), ref_nlls=np.array(m.nlls_mfvi),
+                ref_forgetting=m.forgetting_events.numpy().copy(), ref_last_acc=m.last_acc.numpy().copy(),
+                x=x.numpy().astype(np.float32), y=y.numpy().astype(np.int8), xt=xt.numpy().astype(np.float32),
+                yt=yt.numpy().astype(np.int8))
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **blob)
+    print(name, "forwards", nfw, blob["ref_elbos"], blob["ref_accs"], blob["ref_nlls"], "forgetting sum", blob["ref_forgetting"].sum(),
+          "size", os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "meanfieldvi":
+        run_meanfieldvi()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "learnz":
         run_learn_z()
         return

@@ -327,3 +327,65 @@ def test_learn_z_soft_labels_match_reference():
     kw.update(num_epochs=6, log_every=3, register_elbos=False)
     res = PSVILearnV(**kw).run_psvi(**kw)
     assert len(res["accs"]) == 2 and np.isfinite(res["nlls"]).all()
+
+
+def test_meanfieldvi_class_matches_reference(tmp_path):
+    """MeanFieldVI (reference psvi/inference/utils.py:221-450): the reference's own run() loop -- sequential minibatch Adam
+    steps, forgetting-score bookkeeping after every epoch, mean-of-logits tests -- with the injected noise stream; then save /
+    load of the fitted net."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.experiments_utils import SynthDataset
+    from psvi.inference.psvi_classes import ExternalNoise
+    from psvi.inference.utils import MeanFieldVI
+    g = dict(np.load(os.path.join(GOLDEN, "meanfieldvi_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, B = int(g["S"]), int(g["B"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    tr = SynthDataset(torch.as_tensor(g["x"]).float(), torch.as_tensor(g["y"]).float())
+    te = SynthDataset(torch.as_tensor(g["xt"]).float(), torch.as_tensor(g["yt"]).float())
+    kw = dict(mc_samples=S, data_minibatch=B, num_epochs=2, log_every=2, N=int(g["N"]), D=dims[0], lr0net=float(g["lr0net"]),
+              mul_fact=2, seed=3, architecture="fn", n_hidden=dims[1], nc=dims[-1], train_dataset=tr, test_dataset=te,
+              init_sd=1e-2, forgetting_score_flag=True, data_path=str(tmp_path), dnm="halfmoon", quiet=True)
+    m = MeanFieldVI(noise_source=ExternalNoise(eps), **kw)
+    m.before_train()
+    mu, rho = m.net.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    for i in range(m.total_iterations):                 # reference run(), :396-401
+        m.train_an_epoch()
+        m.after_epoch()
+        if i % m.log_every == 0 or i == m.total_iterations - 1:
+            m.test()
+    assert m.noise_source.pos == int(g["n_forwards"])
+    forgetting = torch.max(m.total_iterations * m.never_learnt_events, m.forgetting_events).cpu().numpy()
+    np.testing.assert_allclose(m.elbos_mfvi, g["ref_elbos"], rtol=1e-4)
+    np.testing.assert_allclose(m.accs_mfvi, g["ref_accs"], atol=5.1e-3)          # (one test row of 200 may flip)
+    np.testing.assert_allclose(m.nlls_mfvi, g["ref_nlls"], rtol=1e-3)
+    assert np.mean(forgetting != g["ref_forgetting"]) <= 0.01
+    assert np.mean(m.last_acc.cpu().numpy() != g["ref_last_acc"]) <= 0.01
+    # run() end to end with Philox noise, then load_from_saved picks the stored net up
+    m2 = MeanFieldVI(**kw)
+    m2.run()
+    assert len(m2.accs_mfvi) == 3 and np.isfinite(m2.nlls_mfvi).all() and m2.elbos_mfvi[-1] > m2.elbos_mfvi[0]
+    m3 = MeanFieldVI(load_from_saved=True, **kw)
+    m3.run()
+    assert m3.accs_mfvi == []                                                       # nothing was retrained
+    p2 = torch.nn.utils.parameters_to_vector(m2.net.parameters())
+    p3 = torch.nn.utils.parameters_to_vector(m3.net.parameters())
+    assert torch.equal(p2, p3) and torch.equal(m2.forgetting_events, m3.forgetting_events)
+
+
+@pytest.mark.parametrize("rows,H,S,L", [(8, 16, 5, 1), (200, 16, 5, 2), (400, 100, 10, 1)])
+def test_module_forward_matches_oracle(rows, H, S, L):
+    """`model(x)` of a mean-field stack (reference neural_net.py:176-179 through nn.Sequential): psvi_mf_forward against the
+    oracle's forward on the sampled weights the kernel reports (tolerance: fp32 accumulation order, 1e-5 relative)."""
+    import torch.nn as nn
+    from psvi.models.neural_net import VILinear, make_fcnet
+    torch.manual_seed(1)
+    net = make_fcnet(2, H, 3, n_layers=L, linear_class=VILinear, nonl_class=nn.ReLU, mc_samples=S, init_sd=0.1).cuda()
+    x = torch.randn(rows, 2, device="cuda")
+    lg = net(x)
+    assert lg.shape == (S, rows, 3)
+    dims = [2] + [H] * L + [3]
+    theta = torch.cat([torch.cat([m._cached_weight.reshape(S, -1), m._cached_bias.reshape(S, -1)], 1) for m in net.vi_layers()], 1)
+    ref, _ = po.mlp_forward(theta.double().cpu().numpy(), x.double().cpu().numpy(), dims)
+    assert rel_l2(lg.cpu().numpy(), ref) < 1e-5

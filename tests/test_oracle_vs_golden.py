@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
+               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
 
 
 def rel_l2(a, b):
@@ -265,3 +265,42 @@ def test_learn_z_soft_labels_match_reference():
     acc, nll, went, ness = po.evaluate_learn_z(r["mu_T"].astype(np.float32), r["rho_T"].astype(np.float32), e32,
                                                g["xt"].astype(np.float32), g["yt"], dims, int(g["B"]))
     np.testing.assert_allclose([acc, nll, went, ness], g["ref32_eval"][:4], rtol=2e-4)
+
+
+def test_meanfieldvi_class_trace_and_forgetting_scores():
+    """MeanFieldVI (reference psvi/inference/utils.py:221-450): sequential minibatches, torch Adam, mean-of-logits test, and the
+    forgetting-event / never-learnt bookkeeping after every epoch.  Golden: `python oracle/make_goldens_r2.py meanfieldvi`."""
+    g = dict(np.load(os.path.join(GOLDEN, "meanfieldvi_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, B, dt = int(g["S"]), int(g["B"]), np.float32
+    eps = [e.astype(dt) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    mu, rho = g["mu0"].astype(dt), g["rho0"].astype(dt)
+    m = np.zeros(2 * len(mu), dt); v = np.zeros(2 * len(mu), dt)
+    x, y, xt, yt = g["x"], g["y"].astype(np.int64), g["xt"], g["yt"].astype(np.int64)
+    n, k, step, total = x.shape[0], 0, 0, 4
+    forgetting, last_acc, never = np.zeros(n), np.zeros(n), np.ones(n)
+    elbos, accs, nlls = [], [], []
+    for i in range(total):
+        for r0 in range(0, n, B):
+            val, gmu, grho = po.mfvi_grad(mu, rho, eps[k], x[r0:r0 + B], y[r0:r0 + B], dt(n / len(x[r0:r0 + B])), dims); k += 1
+            step += 1
+            phi, m, v = po.torch_adam_step(np.concatenate([mu, rho]), np.concatenate([gmu, grho]).astype(dt), m, v, step,
+                                           dt(g["lr0net"]))
+            mu, rho = phi[:len(mu)].astype(dt), phi[len(mu):].astype(dt)
+            elbos.append(-val)
+        for r0 in range(0, n, B):
+            logits, _ = po.mlp_forward(po.mf_sample(mu, rho, eps[k]), x[r0:r0 + B], dims); k += 1
+            cur = (logits.mean(0).argmax(-1) == y[r0:r0 + B]).astype(np.float64)
+            forgetting[r0:r0 + B] += last_acc[r0:r0 + B] > cur
+            last_acc[r0:r0 + B] = cur
+            never[r0:r0 + B] = np.minimum(never[r0:r0 + B], 1.0 - cur)
+        if i % 2 == 0 or i == total - 1:
+            c, nl = po.mfvi_predict(mu, rho, eps[k], xt, yt, dims); k += 1
+            accs.append(c / len(yt)); nlls.append(nl / len(yt))
+    assert k == int(g["n_forwards"])
+    forgetting = np.maximum(total * never, forgetting)
+    np.testing.assert_allclose(elbos, g["ref_elbos"], rtol=5e-5)
+    np.testing.assert_allclose(accs, g["ref_accs"], atol=1e-6)
+    np.testing.assert_allclose(nlls, g["ref_nlls"], rtol=5e-5)
+    assert np.mean(forgetting != g["ref_forgetting"]) <= 0.01      # (a row whose two top logits tie within fp32 noise may flip)
+    assert np.mean(last_acc != g["ref_last_acc"]) <= 0.01
