@@ -665,7 +665,7 @@ def main():
                        "batched TMA + tcgen05 GEMMs; algorithmic FLOPs = T 9 F(M) + 3 F(M+B), F(R) = 2 S R (D H + H C)"}
         f5 = lambda R_: 2.0 * 64 * R_ * (256 * 1024 + 1024 * 10)
         fl5 = 10 * 9 * f5(1000) + 3 * f5(1128)
-        for prec in ("tf32x3", "bf16x3"):
+        for prec in ("tf32x3", "mixed", "bf16x3"):
             o5 = _PL5(**k5)
             o5.large_precision = prec
             o5.run_psvi(**k5)

@@ -980,7 +980,10 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   // ---- dual pass: tangent forward
   {
     GemmP p = z;      // hdot = (X W1dot^T + b1dot) * (h > 0)   (not role-swapped: the transposed mask read costs more than
-    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P;     //  the coalesced store saves -- measured)
+    p.M_valid = R; p.N_valid = H; p.bias = thetad + o_b1; p.bias_bs = P;     //  the coalesced store saves -- measured in
+                                                                            //  tf32x3 (round 1) and in split-bf16: the dual
+                                                                            //  passes of a cfg5 step take 29.4 ms swapped
+                                                                            //  against 21.8 ms as written)
     set_mask_h(p); set_ob(p, w.hh, 0);
     if ((rc = launch_gemm<X3>(opX, opW1d, p, sms, st))) return rc;
     p = z;            // odot = hdot W2^T + h W2dot^T

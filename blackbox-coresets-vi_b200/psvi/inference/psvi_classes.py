@@ -179,9 +179,12 @@ class PSVI(object):
         return model, _native.make_model(model.dims, S), S
 
     # ---- engine choice: fused cluster kernel when the model fits its shared-memory budget, streaming path otherwise ----
-    # arithmetic of the bilevel step in the large regime: "tf32x3" (default, fp32-class accuracy) or "bf16x3"
-    # (split-bf16 pairs: ~1.5x faster step, hypergradient cosine >= 0.999 instead of >= 0.9999); set before the first step
-    large_precision = "tf32x3"
+    # arithmetic of the bilevel step in the large regime, set before the first step:
+    #   "mixed"  (default) gradient / outer passes in tf32x3, Hessian-vector passes of the reverse sweep in split-bf16 pairs:
+    #            hypergradients at the tf32x3 level (the rounding sensitivity sits in the gradient passes), ~20 % faster step
+    #   "tf32x3" every pass in tf32x3 (fp32-class)
+    #   "bf16x3" every pass in split-bf16 pairs: ~1.5x faster than tf32x3, hypergradient cosine >= 0.999 instead of >= 0.9999
+    large_precision = "mixed"
 
     def _stream(self, model):
         """StreamEngine for `model` (fn2, or a mean-field MLP the fused engine reported as PSVI_ERR_UNSUPPORTED)."""
@@ -194,9 +197,11 @@ class PSVI(object):
             elif isinstance(model, MeanFieldMLP) and self._is_large_fn(model):
                 # large regime (BASELINE config 5): batched TMA + tcgen05 GEMMs, bf16 operands
                 from psvi.inference.stream import FnLargeNet
-                prec = {"tf32x3": _native.PREC_TF32X3, "bf16x3": _native.PREC_BF16X3}[self.large_precision]
+                prec, prec_dual = {"tf32x3": (_native.PREC_TF32X3, _native.PREC_TF32X3),
+                                   "bf16x3": (_native.PREC_BF16X3, _native.PREC_BF16X3),
+                                   "mixed": (_native.PREC_TF32X3, _native.PREC_BF16X3)}[self.large_precision]
                 eng = StreamEngine(MeanFieldFamily(model), model.dims, model.n_samples(),
-                                   net=FnLargeNet(model.dims, model.n_samples(), precision=prec))
+                                   net=FnLargeNet(model.dims, model.n_samples(), precision=prec, precision_dual=prec_dual))
             else:
                 fam = FullCovFamily(model) if isinstance(model, FullCovMLP) else MeanFieldFamily(model)
                 eng = StreamEngine(fam, model.dims, model.n_samples())

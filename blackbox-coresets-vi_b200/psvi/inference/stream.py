@@ -213,15 +213,19 @@ class FnLargeNet:
     within 1e-2..1e-1, cosine >= 0.999, of the fp64 oracle -- opt-in) or PREC_BF16 (6x the tensor rate, ~1e-2 relative error
     per pass: values, first-order training, prediction)."""
 
-    def __init__(self, dims, S, precision=_native.PREC_TF32X3):
+    def __init__(self, dims, S, precision=_native.PREC_TF32X3, precision_dual=None):
         self.desc, self.S, self.C, self.precision = _native.make_model(dims, S), S, dims[-1], precision
+        # arithmetic of the Hessian-vector ("dual") passes of the reverse sweep.  Measured (profiles/r2_mixed_precision_study.md):
+        # the hypergradient's sensitivity to operand rounding sits in the GRADIENT passes (their g_i become Adam's denominators
+        # and fix the trajectory); split-bf16 dual passes leave it at the tf32x3 level.
+        self.precision_dual = precision if precision_dual is None else precision_dual
 
     @staticmethod
     def fits(dims, S):
         return len(dims) == 3 and dims[0] % 64 == 0 and dims[1] % 128 == 0 and dims[2] <= 16 and S <= 64
 
     def pass_(self, theta, thetad, x, y, cw, **out):
-        _native.fnl_pass(self.desc, self.precision, theta, thetad, x, y, cw, **out)
+        _native.fnl_pass(self.desc, self.precision if thetad is None else self.precision_dual, theta, thetad, x, y, cw, **out)
 
     def logits(self, theta, x):
         lg = torch.empty(self.S, x.shape[0], self.C, device=x.device)
