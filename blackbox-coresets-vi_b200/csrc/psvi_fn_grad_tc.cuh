@@ -54,6 +54,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46) | ((uint64_t)layout << 61);
 }
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float a, float b) {   // max(., 0) and both conversions in one instruction
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first PTX source -> upper half: a -> low 16 bits
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -242,7 +247,7 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             const float a0 = v[i] + b1v, a1 = v[i + 1] + b1v;
             m0 |= (a0 > 0.f ? 1u : 0u) << i;
             m0 |= (a1 > 0.f ? 1u : 0u) << (i + 1);
-            pk[i / 2] = pack_bf16(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+            pk[i / 2] = pack_relu_bf16x2(a0, a1);
           }
           tmem_ld32(lane_addr + G_COL_P + half * 64 + 32, v);
 #pragma unroll
@@ -250,7 +255,7 @@ psvi_fn_grad_tc_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_
             const float a0 = v[i] + b1v, a1 = v[i + 1] + b1v;
             m1 |= (a0 > 0.f ? 1u : 0u) << i;
             m1 |= (a1 > 0.f ? 1u : 0u) << (i + 1);
-            pk[16 + i / 2] = pack_bf16(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+            pk[16 + i / 2] = pack_relu_bf16x2(a0, a1);
           }
         }
         // the other half's warp of this lane quarter still reads columns this warp is about to overwrite

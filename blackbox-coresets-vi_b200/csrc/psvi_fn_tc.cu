@@ -79,8 +79,10 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));   // .x (first argument) -> low 16 bits
-  return *reinterpret_cast<uint32_t*>(&t);
+  // one instruction for max(., 0) and the conversion of both values (first PTX source -> upper half): a -> low 16 bits
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 // cycle-counter instrumentation of the role warps (build with -DPSVI_FN_PROF; scratch/prof_fn_tc.py prints it)

@@ -38,6 +38,8 @@ real_einsum = np.einsum
 MODE = ["exact"]
 def ein(expr, *ops, **kw):
     m = MODE[0]
+    if isinstance(m, dict):
+        m = m.get(expr, m["default"])
     if len(ops) != 2 or m == "exact":
         return real_einsum(expr, *ops, **kw)
     A, Bm = ops
@@ -72,8 +74,12 @@ t0 = time.time(); ex = run("exact", "exact")
 print(f"case D={D} H={H} C={C} S={S} M={M} T={T} B={B} init_sd={init_sd}: loss {ex['loss']:.4f} ({time.time()-t0:.1f}s per run)")
 print("| gradient pass | dual pass | outer pass | u_grad rel-L2 | u_grad cos | v_grad rel-L2 | v_grad cos |")
 print("|---|---|---|---|---|---|---|")
-for gm, hm, om in (("fp32", "fp32", None), ("tf32x3", "tf32x3", None), ("bf16x3", "bf16x3", None), ("tf32x3", "bf16x3", None),
-                   ("bf16x3", "tf32x3", None), ("tf32x3", "bf16x3", "bf16x3"), ("tf32x3", "bf16", None)):
+FWD, WG, XG = "sri,soi->sro", "sro,sri->soi", "sro,soi->sri"
+extra = [("tf32x3", {"default": "bf16x3", WG: "bf16"}, None), ("tf32x3", {"default": "bf16x3", XG: "bf16"}, None),
+         ("tf32x3", {"default": "bf16x3", WG: "bf16", XG: "bf16"}, None), ("tf32x3", {"default": "bf16x3", FWD: "bf16"}, None)]
+for gm, hm, om in [("fp32", "fp32", None), ("tf32x3", "tf32x3", None), ("bf16x3", "bf16x3", None), ("tf32x3", "bf16x3", None),
+                   ("bf16x3", "tf32x3", None), ("tf32x3", "bf16x3", "bf16x3"), ("tf32x3", "bf16", None)] + extra:
     r = run(gm, hm, om)
+    hm = hm if isinstance(hm, str) else "bf16x3, bf16 for " + "+".join({FWD: "fwd", WG: "wgrad", XG: "xgrad"}[k] for k in hm if k != "default")
     print(f"| {gm} | {hm} | {om or gm} | {rel(r['u_grad'], ex['u_grad']):.2e} | {cos(r['u_grad'], ex['u_grad']):.6f} | "
           f"{rel(r['v_grad'], ex['v_grad']):.2e} | {cos(r['v_grad'], ex['v_grad']):.6f} |", flush=True)
