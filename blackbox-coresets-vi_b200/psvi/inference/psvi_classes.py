@@ -296,7 +296,7 @@ class PSVI(object):
         ue, le, _ = self._soft_rows(u, tin)
         xe, ye, dw = self._soft_rows(xb, td)
         ex = {}
-        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), ue, le,
+        loss, ubar, abar, phi_T, il = eng.nested_cached(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), ue, le,
                                                  (a[:, None] * tin).reshape(-1), xe, ye, N, T, lr,
                                                  want_losses=self.register_elbos, n_total=B,
                                                  a_outer=(a[:, None] * tp).reshape(-1), data_w=dw, extras=ex)
@@ -534,7 +534,7 @@ class PSVI(object):
             xb16 = torch.empty(xb.shape, device=xb.device, dtype=torch.bfloat16)
             if xb.numel():
                 _native.f32_to_bf16(xb, xb16)
-        loss, ubar, abar, phi_T, il = eng.nested(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u_in, z_in, a_in,
+        loss, ubar, abar, phi_T, il = eng.nested_cached(eng.fam.get_phi(), self._noise_tensor(T + 1, eng.Pt, S), u_in, z_in, a_in,
                                                  xb, yb, float(self.N), T, lr, want_losses=self.register_elbos,
                                                  kappa=kappa, n_total=n_total, reduce_fn=reduce_fn, outer=self._outer_kind,
                                                  xb_bf16=xb16)

@@ -70,9 +70,11 @@ class MeanFieldFamily:
     def grad(self, phi, eps, tbar, kl_coef, nkl_coef):
         return _native.mf_reparam_grad(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), tbar, kl_coef, nkl_coef, mask=self.mask)
 
-    def grad_with_nkl(self, phi, eps, tbar, beta, theta):
-        """phi_bar of the outer objective: tbar plus the d nkl_s / d theta_s path (weights beta_s) and the log-sigma term."""
-        return _native.mf_reparam_grad(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), tbar, 0.0, float(beta.sum()), mask=self.mask,
+    def grad_with_nkl(self, phi, eps, tbar, beta, theta, beta_sum):
+        """phi_bar of the outer objective: tbar plus the d nkl_s / d theta_s path (weights beta_s) and the log-sigma term.
+        `beta_sum` = sum_s beta_s as a HOST number: it is -kappa identically (sum_s w_s = 1), so no device read-back is
+        needed -- the step stays free of host synchronisation (CUDA-graph capturable)."""
+        return _native.mf_reparam_grad(phi[:self.Pt], phi[self.Pt:], eps.contiguous(), tbar, 0.0, float(beta_sum), mask=self.mask,
                                        beta=beta.float().contiguous(), theta=theta)
 
     def hvp(self, phi, phidot, eps, A_t, A_td):
@@ -346,10 +348,10 @@ class StreamEngine:
                 self.net.pass_(theta, None, xc, yc, wd[:, None].expand(S, xc.shape[0]).contiguous(), nll=nc, tbar=tb)
                 tbar += tb
         if hasattr(self.fam, "grad_with_nkl"):
-            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta, -kappa)
         else:
             tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
-            pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
+            pbar = self.fam.grad(phi, eps, tbar, 0.0, -kappa)     # sum_s beta_s = -kappa identically
         return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
     def _outer_grad_fulldata(self, phi, eps, u, z32, a, xb_bf16, yb32, N, kappa, n_total):
@@ -383,10 +385,10 @@ class StreamEngine:
         if tbar_d is not None:
             tbar += tbar_d
         if hasattr(self.fam, "grad_with_nkl"):
-            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta, -kappa)
         else:
             tbar = tbar + beta.float()[:, None] * self.fam.nkl_theta_grad(theta)
-            pbar = self.fam.grad(phi, eps, tbar, 0.0, float(beta.sum()))
+            pbar = self.fam.grad(phi, eps, tbar, 0.0, -kappa)     # sum_s beta_s = -kappa identically
         return loss.float(), pbar, xbar_u.sum(0), (gp.float() @ nll_u), ds.float()
 
     def outer_grad_ablated(self, phi, eps, xb, yb32, N, kappa=1.0, n_total=None):
@@ -410,9 +412,9 @@ class StreamEngine:
         loss = (N / n_total) * ds.mean() - kappa * nkl.mean()
         beta = torch.full((S,), -kappa / S, device=dev)
         if hasattr(self.fam, "grad_with_nkl"):
-            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta)
+            pbar = self.fam.grad_with_nkl(phi, eps, tbar, beta, theta, -kappa)
         else:
-            pbar = self.fam.grad(phi, eps, tbar + beta[:, None] * self.fam.nkl_theta_grad(theta), 0.0, float(beta.sum()))
+            pbar = self.fam.grad(phi, eps, tbar + beta[:, None] * self.fam.nkl_theta_grad(theta), 0.0, -kappa)
         return loss.float(), pbar
 
     def hvp(self, phi, eps, u, z32, a, phidot, a_exp=None, fixed=False):
@@ -468,6 +470,64 @@ class StreamEngine:
             h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar, a_exp=a_exp, fixed=True)
             pbar, ubar, abar = pbar + h, ubar + hu, abar + ha
         return loss, ubar, abar, phi_T, (torch.stack(losses).float() if want_losses else None)
+
+    # ---- the same step as ONE CUDA graph ---------------------------------------------------------------------------------
+    # A bilevel step on this path is hundreds of kernel launches sequenced by Python (676 at BASELINE cfg5, 1365 at cfg4, 596
+    # at cfg3): ~45 us of host work per launch, i.e. a host-bound step as soon as the kernels get faster.  The step has no
+    # data-dependent control flow and no host synchronisation, so it is captured once per (shapes, T, lr, ...) into a CUDA
+    # graph -- every launch of libpsvi_b200 goes to torch's current stream, which is the capturing stream -- and replayed:
+    # inputs are copied into the graph's static buffers, the outputs are cloned out.  Falls back to the eager sequence when
+    # the ranks exchange data inside the step (reduce_fn), when capture fails, or with PSVI_NO_GRAPH=1.
+    use_graphs = True
+    MAX_GRAPHS = 4
+
+    def nested_cached(self, phi, eps_all, u, z32, a, xb, yb32, N, T, lr, want_losses=False, kappa=1.0, n_total=None,
+                      reduce_fn=None, outer="psvi", xb_bf16=None, a_outer=None, data_w=None, extras=None):
+        import os
+        scal = dict(N=N, T=T, lr=lr, want_losses=want_losses, kappa=kappa, n_total=n_total, outer=outer)
+        tens = dict(phi=phi, eps_all=eps_all, u=u, z32=z32, a=a, xb=xb, yb32=yb32, xb_bf16=xb_bf16, a_outer=a_outer, data_w=data_w)
+        # (a full-data term -- xb_bf16, millions of rows -- is device-bound and would only be copied around: eager)
+        if reduce_fn is not None or xb_bf16 is not None or not self.use_graphs or os.environ.get("PSVI_NO_GRAPH"):
+            return self.nested(**tens, **scal, reduce_fn=reduce_fn, extras=extras)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (T, float(lr), float(N), bool(want_losses), float(kappa), n_total, outer, extras is not None,
+               tuple((k, None if t is None else (tuple(t.shape), t.dtype)) for k, t in tens.items()))
+        ent = graphs.get(key)
+        if ent is None:
+            if len(graphs) >= self.MAX_GRAPHS:
+                graphs.pop(next(iter(graphs)))
+            try:
+                ent = self._capture_nested(tens, scal, extras is not None)
+            except Exception as e:      # e.g. a host synchronisation inside a family map: keep the eager sequence for this key
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the bilevel step failed ({e!r:.200}); running it eagerly")
+                ent = False
+            graphs[key] = ent
+        if ent is False:
+            return self.nested(**tens, **scal, extras=extras)
+        static_in, graph, outs, ex = ent
+        for k, t in tens.items():
+            if t is not None:
+                static_in[k].copy_(t)
+        graph.replay()
+        if extras is not None:
+            extras.update({k: v.clone() for k, v in ex.items()})
+        return tuple(None if o is None else o.clone() for o in outs)
+
+    def _capture_nested(self, tens, scal, want_extras):
+        static_in = {k: (None if t is None else t.detach().clone().contiguous()) for k, t in tens.items()}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):       # warm-up outside capture: workspaces, function attributes, lazy module loads
+            self.nested(**static_in, **scal, extras={} if want_extras else None)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        ex = {} if want_extras else None
+        with torch.cuda.graph(graph):
+            outs = self.nested(**static_in, **scal, extras=ex)
+        return static_in, graph, outs, ex
 
     def predict_probs(self, phi, eps, u, z32, a, x, correction=True, chunk=8192):
         """Predictive class probabilities of rows x under ONE noise slab (PSVI.pred_on_grid, psvi_classes.py:1130-1175):
