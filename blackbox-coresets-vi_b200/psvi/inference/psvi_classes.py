@@ -65,6 +65,12 @@ class ExternalNoise:
         return torch.as_tensor(np.stack(out)).to(device=device, dtype=torch.float32).contiguous()
 
 
+def _adam(params, lr):
+    """torch.optim.Adam on the outer variables (reference :860-870) as ONE fused kernel per step() (`fused=True`: same update
+    rule; the default foreach form launches seven kernels per optimiser, ~5 % of a cfg2 outer step)."""
+    return torch.optim.Adam(params, lr, fused=all(p.is_cuda for p in params))
+
+
 def _dist_info():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -843,12 +849,12 @@ class PSVI(object):
             [], [], [], [], [], [], [], [], [], [], [0])
         {"random": self.pseudo_rand_init, "subsample": self.pseudo_subsample_init}[self.init_args]()
         self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
-        self.optim_u = torch.optim.Adam([self.u], lr0u)
+        self.optim_u = _adam([self.u], lr0u)
         self.scheduler_optim_net = torch.optim.lr_scheduler.StepLR(self.optim_net, **scheduler_kwargs)
         if self.learn_v:
-            self.optim_v = torch.optim.Adam([self.v], lr0v)
+            self.optim_v = _adam([self.v], lr0v)
         if self.learn_z:
-            self.optim_z = torch.optim.Adam([self.z], lr0z)          # reference :869-870
+            self.optim_z = _adam([self.z], lr0z)          # reference :869-870
         self._lr0joint = lr0joint
         optimizers = {"alternating": self.alternating_step, "nested": self.nested_step, "hyper": self.hyper_step,
                       "joint": self.joint_step}        # reference :871-886
@@ -1060,10 +1066,10 @@ class PSVI(object):
         self.num_pseudo = to_size
         keep_v = torch.multinomial(self.f(self.v.detach(), 0), to_size, replacement=False)
         self.v = torch.zeros_like(self.v[keep_v]).clone().detach().requires_grad_(True)
-        self.optim_v = torch.optim.Adam([self.v], lr0v)
+        self.optim_v = _adam([self.v], lr0v)
         self.u = torch.index_select(self.u.detach(), 0, keep_v).requires_grad_(True)
         self.z = torch.index_select(self.z, 0, keep_v)
-        self.optim_u = torch.optim.Adam([self.u], self.optim_u.param_groups[0]["lr"])
+        self.optim_u = _adam([self.u], self.optim_u.param_groups[0]["lr"])
         self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
 
     def increment_coreset(self, to_size, lr0v=1e-3, lr0u=1e-3, lr0net=1e-4, variance=1.0, new_class=2, increment_idx=1):
@@ -1075,7 +1081,7 @@ class PSVI(object):
             vv = self.v.detach()
             self.v = torch.cat((vv, 1.0 / (n_old + extra) * vv.sum() * torch.ones(extra, device=self.device)))
         self.v = self.v.detach().requires_grad_(True)
-        self.optim_v = torch.optim.Adam([self.v], lr0v)
+        self.optim_v = _adam([self.v], lr0v)
         if self.init_args == "random":
             new_us = (compute_empirical_mean(self.train_loader) + variance * torch.randn(extra, self.D)).clone()
             new_zs = new_class * torch.ones(extra)
@@ -1084,7 +1090,7 @@ class PSVI(object):
             new_us, new_zs = ds[torch.randperm(len(ds))[:extra]]
         self.u = torch.cat((self.u.detach(), new_us.to(self.device).float())).detach().requires_grad_(True)
         self.z = torch.cat((self.z, new_zs.to(self.device).to(self.z.dtype)))
-        self.optim_u = torch.optim.Adam([self.u], lr0u)
+        self.optim_u = _adam([self.u], lr0u)
         self.optim_net = torch.optim.Adam(list(self.model.parameters()), lr0net)
 
     def _retrain_step(self, opt, params):
@@ -1136,7 +1142,7 @@ class PSVIAV(PSVILearnV):
         self.alpha = torch.tensor([0.0], device=self.device)
         self.alpha.requires_grad_(True)
         self.f = lambda *x: torch.exp(self.alpha.detach()) * torch.softmax(x[0], x[1])
-        self.optim_alpha = torch.optim.Adam([self.alpha], self.lr0alpha)
+        self.optim_alpha = _adam([self.alpha], self.lr0alpha)
         self.results["alpha"] = []
 
     def evaluate(self, **kwargs):
@@ -1145,7 +1151,7 @@ class PSVIAV(PSVILearnV):
 
     def increment_coreset(self, lr0alpha=1e-3, **kwargs):
         super().increment_coreset(**kwargs)          # reference :1501-1503
-        self.optim_alpha = torch.optim.Adam([self.alpha], lr0alpha)
+        self.optim_alpha = _adam([self.alpha], lr0alpha)
 
     def hyper_step(self, xbatch, ybatch, T=10, inner_opt_class=None, K=10, linsys_lr=1e-1, hypergrad_approx="CG_normaleq",
                    **kwargs):
