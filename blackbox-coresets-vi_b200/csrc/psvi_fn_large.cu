@@ -51,7 +51,17 @@ struct GemmP {
   float* of; long long of_bs; int of_ld;                       // fp32 out [b][m][n], m < M_valid, n < N_valid
   void *ob, *ob_lo; long long ob_bs; int ob_ld; int ob_rows;    // operand out [b][m][n], m < ob_rows (zeros for m >= M_valid)
   void *obt, *obt_lo; long long obt_bs; int obt_ld;             // transposed operand out [b][n][m], m < ob_rows
+  int ob_tma;                                   // split-bf16 only: the row-major operand store goes through shared memory and
+                                                // cp.async.bulk.tensor (TMA) stores described by map_o / map_ol
 };
+
+constexpr int STG_WARP_BYTES = 2 * 32 * 64;     // per epilogue warp: (hi | lo) x 32 rows x 32 bf16 columns (64-byte swizzle)
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -89,7 +99,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 template <int X3>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_al,
-               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bl, const GemmP p) {
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bl,
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_ol, const GemmP p) {
   using PR = Prec<X3>;
   constexpr int STAGE = PR::TILES * G_TILE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,6 +112,8 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = empty + PR::GST;     // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // staging tiles of the TMA-stored epilogue (split-bf16): 8 warps x (hi | lo) x [32 rows][64 B], 64-byte swizzle
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < PR::GST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -282,6 +295,37 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 oh[i] = make_float4(h4[0], h4[1], h4[2], h4[3]);
                 ol[i] = make_float4(l4[0], l4[1], l4[2], l4[3]);
               }
+            } else if (X3 == 2 && p.ob_tma) {
+              // this warp's [32 rows x 32 columns] piece of (hi, lo): rows into swizzled shared memory (16-byte chunk c of
+              // row r sits at chunk c ^ ((r >> 1) & 3): the 64-byte TMA swizzle, conflict-free for row-per-thread writes),
+              // then two TMA stores; the copies of chunk g overlap the arithmetic of chunk g + 1
+              uint8_t* sh = stg + (warp - 4) * STG_WARP_BYTES;
+              uint8_t* sl = sh + STG_WARP_BYTES / 2;
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous copies have read it
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2, l2;
+                  split_bf16(v[i * 8 + e * 2], h2.x, l2.x);
+                  split_bf16(v[i * 8 + e * 2 + 1], h2.y, l2.y);
+                  wh[e] = *reinterpret_cast<uint32_t*>(&h2);
+                  wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+                }
+                const int phys = (i ^ ((lane >> 1) & 3)) * 16 + lane * 64;
+                *reinterpret_cast<uint4*>(sh + phys) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(sl + phys) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                const int row0 = b * p.ob_rows + mt * GM + q * 32;
+                tma_store_2d(&map_o, sh, n0, row0);
+                tma_store_2d(&map_ol, sl, n0, row0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
             } else if (X3 == 2) {
               uint4* oh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob) + off);
               uint4* ol = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.ob_lo) + off);
@@ -347,6 +391,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+    if (X3 == 2 && p.ob_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete
   }
   tc_fence_before();
   __syncthreads();
@@ -820,10 +865,27 @@ int make_map_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t ou
   return PSVI_OK;
 }
 
+// [outer rows][inner bf16 columns] output view, boxes of 32 x 32 with the 64-byte swizzle (the TMA-stored epilogue)
+int make_map_out_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  PSVI_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr));
+  PSVI_REQUIRE(ptr != nullptr && qr == cudaDriverEntryPointSuccess, PSVI_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = reinterpret_cast<EncodeFn>(ptr)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                                                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PSVI_REQUIRE(r == CUDA_SUCCESS, PSVI_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r);
+  return PSVI_OK;
+}
+
 template <int X3>
 int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream_t st) {
   using PR = Prec<X3>;
-  CUtensorMap ma, mal, mb, mbl;
+  CUtensorMap ma, mal, mb, mbl, mo, mol;
   int rc;
   if (X3 == 2) {
     if ((rc = make_map_2d_bf16_ld(&ma, A.buf.hi + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
@@ -849,10 +911,20 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   if ((p.ob || p.obt) && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  const size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
+  size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
+  mo = ma;
+  mol = ma;
+  p.ob_tma = 0;
+  if (X3 == 2 && p.ob && p.ob_lo && p.ob_rows % GM == 0 && p.ob_bs == (long long)p.ob_rows * p.ob_ld && !getenv("PSVI_FNL_NO_TMASTORE")) {
+    const uint64_t ncols = (uint64_t)(p.n_pad > p.N_valid ? p.n_pad : p.N_valid);
+    if ((rc = make_map_out_bf16(&mo, p.ob, ncols, (uint64_t)p.batch * p.ob_rows, (uint64_t)p.ob_ld))) return rc;
+    if ((rc = make_map_out_bf16(&mol, p.ob_lo, ncols, (uint64_t)p.batch * p.ob_rows, (uint64_t)p.ob_ld))) return rc;
+    p.ob_tma = 1;
+    smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
+  }
   // function attributes are per device: set on every call (cheap), not cached per process
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tn_gemm_kernel<X3><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, p);
+  tn_gemm_kernel<X3><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, mo, mol, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }
