@@ -51,12 +51,21 @@ struct GemmP {
   float* of; long long of_bs; int of_ld;                       // fp32 out [b][m][n], m < M_valid, n < N_valid
   void *ob, *ob_lo; long long ob_bs; int ob_ld; int ob_rows;    // operand out [b][m][n], m < ob_rows (zeros for m >= M_valid)
   void *obt, *obt_lo; long long obt_bs; int obt_ld;             // transposed operand out [b][n][m], m < ob_rows
+  int a_mn, b_mn;                               // split-bf16 only: the operand is read "MN-major" -- its global array is
+                                                // [K rows][M (or N) contiguous], i.e. the product uses the TRANSPOSE of a
+                                                // row-major array without a transposed copy (UMMA a_major / b_major = 1)
   int ob_tma;                                   // split-bf16 only: the row-major operand store goes through shared memory and
                                                 // cp.async.bulk.tensor (TMA) stores described by map_o / map_ol
 };
 
 constexpr int STG_WARP_BYTES = 2 * 32 * 64;     // per epilogue warp: (hi | lo) x 32 rows x 32 bf16 columns (64-byte swizzle)
 
+// MN-major operand tile of one K block: two [64 K-rows x 64 MN-columns] boxes (128-byte swizzle, 8 KB each): LBO = 8 KB between
+// the 64-column halves, SBO = 1 KB between 8-row groups along K; one K = 16 MMA step advances two row groups (2 KB)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((8192 >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
@@ -141,12 +150,35 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elect_one()) {
           uint8_t* dst = ring + st * STAGE;
           mbar_expect_tx(&full[st], STAGE);
-          tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
-          if (PR::TILES == 4) {
+          if (X3 == 2 && (p.a_mn || p.b_mn)) {
+            const int ak = b * p.a_brows + k * PR::GK, bk = b * p.b_brows + k * PR::GK;
+            if (p.a_mn) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                tma_load_2d(&map_a, &full[st], dst + h * 8192, mt * GM + h * 64, ak);
+                tma_load_2d(&map_al, &full[st], dst + G_TILE_BYTES + h * 8192, mt * GM + h * 64, ak);
+              }
+            } else {
+              tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
+              tma_load_2d(&map_al, &full[st], dst + G_TILE_BYTES, k * PR::GK, arow);
+            }
+            if (p.b_mn) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                tma_load_2d(&map_b, &full[st], dst + 2 * G_TILE_BYTES + h * 8192, nt * GN + h * 64, bk);
+                tma_load_2d(&map_bl, &full[st], dst + 3 * G_TILE_BYTES + h * 8192, nt * GN + h * 64, bk);
+              }
+            } else {
+              tma_load_2d(&map_b, &full[st], dst + 2 * G_TILE_BYTES, k * PR::GK, brow);
+              tma_load_2d(&map_bl, &full[st], dst + 3 * G_TILE_BYTES, k * PR::GK, brow);
+            }
+          } else if (PR::TILES == 4) {
+            tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
             tma_load_2d(&map_al, &full[st], dst + G_TILE_BYTES, k * PR::GK, arow);
             tma_load_2d(&map_b, &full[st], dst + 2 * G_TILE_BYTES, k * PR::GK, brow);
             tma_load_2d(&map_bl, &full[st], dst + 3 * G_TILE_BYTES, k * PR::GK, brow);
           } else {
+            tma_load_2d(&map_a, &full[st], dst, k * PR::GK, arow);
             tma_load_2d(&map_b, &full[st], dst + G_TILE_BYTES, k * PR::GK, brow);
           }
         }
@@ -181,11 +213,16 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else if (X3 == 2) {
             const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
+            const uint32_t id2 = idesc | ((uint32_t)(p.a_mn != 0) << 15) | ((uint32_t)(p.b_mn != 0) << 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {   // K = 16 bf16 = 32 bytes per step; lo.hi + hi.lo + hi.hi at the bf16 rate
-              umma_bf16(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
-              umma_bf16(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
-              umma_bf16(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
+            for (int j = 0; j < 4; ++j) {   // K = 16 bf16 per step: 32 bytes along K (K-major) or two 8-row groups (MN-major)
+              const uint64_t dah = p.a_mn ? make_desc_mn(ah + j * 2048) : make_desc_sw128(ah + j * 32);
+              const uint64_t dal = p.a_mn ? make_desc_mn(al + j * 2048) : make_desc_sw128(al + j * 32);
+              const uint64_t dbh = p.b_mn ? make_desc_mn(bh + j * 2048) : make_desc_sw128(bh + j * 32);
+              const uint64_t dbl = p.b_mn ? make_desc_mn(bl + j * 2048) : make_desc_sw128(bl + j * 32);
+              umma_bf16(tmem_d, dal, dbh, id2, j ? 1u : acc0);     // lo.hi + hi.lo + hi.hi at the bf16 rate
+              umma_bf16(tmem_d, dah, dbl, id2, 1u);
+              umma_bf16(tmem_d, dah, dbh, id2, 1u);
             }
           } else {
             const uint32_t a0 = s0, b0 = s0 + G_TILE_BYTES;
@@ -783,6 +820,37 @@ fnl_rowsum_kernel(const void* Yh, const void* Yl, int H, int Rp, int R, float* _
   if (lane == 0) out[(long long)s * P + row] = t;
 }
 
+// column sums of the row-major split-bf16 adjoint array Y[s][r][0 .. 2H): columns < H -> out1[s * P + c], columns >= H ->
+// out2[s * P + c - H]  (the bias adjoints A_b1 / A_b1dot without a transposed copy; a thread owns two adjacent columns)
+__global__ void __launch_bounds__(128)
+fnl_colsum_pair_kernel(const __nv_bfloat16* __restrict__ Yh, const __nv_bfloat16* __restrict__ Yl, long long bs, int ld, int R, int H,
+                       float* __restrict__ out1, float* __restrict__ out2, long long P) {
+  const int c = 2 * (blockIdx.x * 128 + threadIdx.x), s = blockIdx.y;
+  if (c >= 2 * H) return;
+  const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(Yh + (size_t)s * bs + c);
+  const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(Yl + (size_t)s * bs + c);
+  const size_t step = (size_t)ld / 2;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int r = 0;
+  for (; r + 4 <= R; r += 4) {
+    float2 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h[k] = __bfloat1622float2(ph[(size_t)(r + k) * step]);
+      l[k] = __bfloat1622float2(pl[(size_t)(r + k) * step]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a0 += h[k].x; a1 += h[k].y; b0 += l[k].x; b1 += l[k].y; }
+  }
+  for (; r < R; ++r) {
+    const float2 h = __bfloat1622float2(ph[(size_t)r * step]), l = __bfloat1622float2(pl[(size_t)r * step]);
+    a0 += h.x; a1 += h.y; b0 += l.x; b1 += l.y;
+  }
+  float* o = c < H ? out1 + (long long)s * P + c : out2 + (long long)s * P + (c - H);
+  o[0] = a0 + b0;
+  o[1] = a1 + b1;
+}
+
 // out[s * P + c] = sum_r W[s][r][c]
 __global__ void fnl_colsum16_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ out, long long P) {
   const int s = blockIdx.x, c = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 x 16 threads
@@ -839,6 +907,7 @@ struct Operand {
   uint64_t eoff;               // element offset of the view inside the buffer
   uint64_t inner, outer, ld;   // K extent, rows, leading dimension (elements)
   int brows;                   // rows per batch (0: shared)
+  int mn;                      // MN-major view (split-bf16): inner = M (or N) extent, outer / brows count K rows
 };
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -887,11 +956,13 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   using PR = Prec<X3>;
   CUtensorMap ma, mal, mb, mbl, mo, mol;
   int rc;
+  PSVI_REQUIRE(X3 == 2 || (!A.mn && !B.mn), PSVI_ERR_INVALID, "MN-major operands are built for the split-bf16 kernels");
   if (X3 == 2) {
-    if ((rc = make_map_2d_bf16_ld(&ma, A.buf.hi + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
-    if ((rc = make_map_2d_bf16_ld(&mal, A.buf.lo + A.eoff * 2, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
-    if ((rc = make_map_2d_bf16_ld(&mb, B.buf.hi + B.eoff * 2, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
-    if ((rc = make_map_2d_bf16_ld(&mbl, B.buf.lo + B.eoff * 2, B.inner, B.outer, B.ld, PR::GK, GN))) return rc;
+    // K-major: boxes of [GM rows x GK K-elements]; MN-major: boxes of [GK K-rows x 64 MN-elements] (two per tile)
+    if ((rc = make_map_2d_bf16_ld(&ma, A.buf.hi + A.eoff * 2, A.inner, A.outer, A.ld, A.mn ? 64 : PR::GK, A.mn ? PR::GK : GM))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mal, A.buf.lo + A.eoff * 2, A.inner, A.outer, A.ld, A.mn ? 64 : PR::GK, A.mn ? PR::GK : GM))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mb, B.buf.hi + B.eoff * 2, B.inner, B.outer, B.ld, B.mn ? 64 : PR::GK, B.mn ? PR::GK : GN))) return rc;
+    if ((rc = make_map_2d_bf16_ld(&mbl, B.buf.lo + B.eoff * 2, B.inner, B.outer, B.ld, B.mn ? 64 : PR::GK, B.mn ? PR::GK : GN))) return rc;
   } else if (X3 == 1) {
     if ((rc = make_map_f32(&ma, A.buf.hi + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
     if ((rc = make_map_f32(&mal, A.buf.lo + A.eoff * 4, A.inner, A.outer, A.ld, PR::GK, GM))) return rc;
@@ -903,9 +974,11 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
     mal = ma;
     mbl = mb;
   }
-  p.kc = (int)(A.inner / PR::GK);
+  p.kc = (int)((A.mn ? (A.brows ? (uint64_t)A.brows : A.outer) : A.inner) / PR::GK);
   p.a_brows = A.brows;
   p.b_brows = B.brows;
+  p.a_mn = A.mn;
+  p.b_mn = B.mn;
   p.m_tiles = (p.M_valid + GM - 1) / GM;
   p.n_tiles = ((p.n_pad > p.N_valid ? p.n_pad : p.N_valid) + GN - 1) / GN;
   if ((p.ob || p.obt) && p.ob_rows > p.M_valid) p.m_tiles = (p.ob_rows + GM - 1) / GM;
@@ -1065,17 +1138,30 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   fnl_head_kernel<X3><<<hb, 128, 0, st>>>(w.o, w.od, theta + o_b2, thetad + o_b2, P, y, cw, S, R, Rp, C, 2, nll, logits, w.go, w.god,
                                          w.AA.hi, w.AA.lo, acbar);
   {
+    // split-bf16: the products with A_a^T / A_adot^T read the ROW-MAJOR adjoints as MN-major UMMA operands (and X likewise),
+    // so no transposed copies are written (PSVI_FNL_NO_MN=1 restores the transposed-copy form for comparison)
+    const bool mn = X3 == 2 && !getenv("PSVI_FNL_NO_MN");
     GemmP p = z;      // A_a = (A_od W2dot + A_o W2) * (h > 0)
     p.M_valid = R; p.N_valid = H;
-    set_mask_h(p); set_ob(p, w.aa, 0); set_obt(p, w.aT);
+    set_mask_h(p); set_ob(p, w.aa, 0);
+    if (!mn) set_obt(p, w.aT);
     if ((rc = launch_gemm<X3>(opAA, opW2TT, p, sms, st))) return rc;
-    set_ob(p, w.aa, H); set_obt(p, w.adT);      // A_adot = (A_od W2) * (h > 0)
+    set_ob(p, w.aa, H);                         // A_adot = (A_od W2) * (h > 0)
+    if (!mn) set_obt(p, w.adT);
     if ((rc = launch_gemm<X3>(opA0, opW2T1, p, sms, st))) return rc;
     p = z;            // A_W1 = A_a^T X;  A_W1dot = A_adot^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
-    if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
-    p.of = tdbar;
-    if ((rc = launch_gemm<X3>(opADT, opXT, p, sms, st))) return rc;
+    if (mn) {
+      const Operand opAmn{w.aa, 0, uH, uS * Rp, H2, Rp, 1}, opAdmn{w.aa, uH, uH, uS * Rp, H2, Rp, 1};   // M = hidden, K = rows
+      const Operand opXmn{w.X, 0, uD, uRp, uD, 0, 1};                                                     // N = D, K = rows
+      if ((rc = launch_gemm<X3>(opAmn, opXmn, p, sms, st))) return rc;
+      p.of = tdbar;
+      if ((rc = launch_gemm<X3>(opAdmn, opXmn, p, sms, st))) return rc;
+    } else {
+      if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
+      p.of = tdbar;
+      if ((rc = launch_gemm<X3>(opADT, opXT, p, sms, st))) return rc;
+    }
     if (xbar) {
       p = z;          // A_x = A_a W1 + A_adot W1dot
       p.M_valid = R; p.N_valid = D; p.of = xbar; p.of_bs = (long long)R * D; p.of_ld = D;
@@ -1084,8 +1170,14 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   }
   // A_b1 / A_b1dot: row sums of the transposed adjoints (coalesced along r);  A_W2 = A_o^T h + A_od^T hdot and
   // A_W2dot = A_od^T h in one sweep over hh
-  fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);
-  fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.adT.hi, w.adT.lo, H, Rp, R, tdbar + o_b1, P);
+  if (X3 == 2 && !getenv("PSVI_FNL_NO_MN")) {
+    fnl_colsum_pair_kernel<<<dim3((H + 127) / 128, S), 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(w.aa.hi),
+                                                                      reinterpret_cast<const __nv_bfloat16*>(w.aa.lo), hh_bs, 2 * H, R, H,
+                                                                      tbar + o_b1, tdbar + o_b1, P);
+  } else {
+    fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);
+    fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.adT.hi, w.adT.lo, H, Rp, R, tdbar + o_b1, P);
+  }
   fnl_colreduce_dual_kernel<X3><<<dim3((H + 2 * CRD_T - 1) / (2 * CRD_T), S, RSPLIT), CRD_T, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
   fnl_colreduce_dual_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, C, tbar + o_w2, tdbar + o_w2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
