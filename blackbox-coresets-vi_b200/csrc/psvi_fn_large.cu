@@ -851,6 +851,34 @@ fnl_colsum_pair_kernel(const __nv_bfloat16* __restrict__ Yh, const __nv_bfloat16
   o[1] = a1 + b1;
 }
 
+// G2[s][r][0..64) = [go[s][r][0..16) | god[s][r][0..16) | 0 ...] as split-bf16 pairs, rows r >= R zero: the B operand (N = 64
+// columns, K = rows, MN-major) of the W2 adjoint product  hh^T [go | god]
+__global__ void fnl_pack_g2_kernel(const float* __restrict__ go, const float* __restrict__ god, int R, int Rp, __nv_bfloat16* __restrict__ Gh,
+                                   __nv_bfloat16* __restrict__ Gl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over S * Rp * 64
+  const int c = (int)(i & 63);
+  const long long sr = i >> 6;
+  const int r = (int)(sr % Rp);
+  const long long sidx = sr / Rp;
+  float v = 0.f;
+  if (r < R && c < 2 * CW) v = (c < CW ? go : god)[((size_t)sidx * R + r) * CW + (c & (CW - 1))];
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  Gh[i] = h;
+  Gl[i] = l;
+}
+// W2 adjoints from Cm[s][2H][32] = hh^T [go | god]  (rows j < H: hdot, rows H + j: h):
+// out1[s * P + c * H + j] = (h . go)[j][c] + (hdot . god)[j][c],  out2[...] = (h . god)[j][c]
+__global__ void fnl_w2adj_finish_kernel(const float* __restrict__ Cm, int H, int C, float* __restrict__ out1, float* __restrict__ out2,
+                                        long long P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (i >= C * H) return;
+  const int c = i / H, j = i - c * H;
+  const float* q = Cm + (size_t)s * 2 * H * 32;
+  out1[(long long)s * P + i] = q[(size_t)(H + j) * 32 + c] + q[(size_t)j * 32 + CW + c];
+  out2[(long long)s * P + i] = q[(size_t)(H + j) * 32 + CW + c];
+}
+
 // out[s * P + c] = sum_r W[s][r][c]
 __global__ void fnl_colsum16_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ out, long long P) {
   const int s = blockIdx.x, c = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 x 16 threads
@@ -872,7 +900,7 @@ struct Buf {
   uint8_t *hi, *lo;
 };
 struct Lws {
-  Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA;
+  Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA, G2;
   float *o, *od, *go, *god, *cpart;
   size_t total;
 };
@@ -894,6 +922,7 @@ void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
   w.aT = takeb((size_t)S * H * Rp);
   w.adT = takeb((size_t)S * H * Rp);
   w.AA = takeb((size_t)S * Rp * cp2);
+  w.G2 = takeb((size_t)S * Rp * 64);      // [A_o | A_od | 0] as a split-bf16 operand (the W2 adjoint product of the dual pass)
   w.o = (float*)take((size_t)S * Rp * CW * 4);
   w.od = (float*)take((size_t)S * Rp * CW * 4);
   w.go = (float*)take((size_t)S * R * CW * 4);
@@ -1178,8 +1207,21 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);
     fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.adT.hi, w.adT.lo, H, Rp, R, tdbar + o_b1, P);
   }
-  fnl_colreduce_dual_kernel<X3><<<dim3((H + 2 * CRD_T - 1) / (2 * CRD_T), S, RSPLIT), CRD_T, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
-  fnl_colreduce_dual_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, C, tbar + o_w2, tdbar + o_w2, P);
+  if (X3 == 2 && !getenv("PSVI_FNL_NO_MN") && !getenv("PSVI_FNL_NO_W2GEMM")) {
+    // A_W2 = A_o^T h + A_od^T hdot,  A_W2dot = A_od^T h  as ONE tensor-core product  hh^T [A_o | A_od]  (M = 2H hidden columns of
+    // the row-major hh read as an MN-major operand, N = 64, K = rows) instead of a CUDA-core sweep over hh
+    const long long n2 = (long long)S * Rp * 64;
+    fnl_pack_g2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(w.go, w.god, R, Rp, reinterpret_cast<__nv_bfloat16*>(w.G2.hi),
+                                                                      reinterpret_cast<__nv_bfloat16*>(w.G2.lo));
+    const Operand opHmn{w.hh, 0, H2, uS * Rp, H2, Rp, 1}, opGmn{w.G2, 0, 64, uS * Rp, 64, Rp, 1};
+    GemmP p = z;
+    p.M_valid = 2 * H; p.N_valid = 32; p.of = w.cpart; p.of_bs = (long long)2 * H * 32; p.of_ld = 32;
+    if ((rc = launch_gemm<X3>(opHmn, opGmn, p, sms, st))) return rc;
+    fnl_w2adj_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, H, C, tbar + o_w2, tdbar + o_w2, P);
+  } else {
+    fnl_colreduce_dual_kernel<X3><<<dim3((H + 2 * CRD_T - 1) / (2 * CRD_T), S, RSPLIT), CRD_T, 0, st>>>(w.hh.hi, w.hh.lo, hh_bs, w.go, w.god, R, H, C, w.cpart);
+    fnl_colreduce_dual_finish_kernel<<<dim3((C * H + 255) / 256, S), 256, 0, st>>>(w.cpart, S, H, C, tbar + o_w2, tdbar + o_w2, P);
+  }
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
   fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.god, R, C, tdbar + o_b2, P);
   PSVI_CUDA_CHECK(cudaGetLastError());
