@@ -75,11 +75,16 @@ print(f"case D={D} H={H} C={C} S={S} M={M} T={T} B={B} init_sd={init_sd}: loss {
 print("| gradient pass | dual pass | outer pass | u_grad rel-L2 | u_grad cos | v_grad rel-L2 | v_grad cos |")
 print("|---|---|---|---|---|---|---|")
 FWD, WG, XG = "sri,soi->sro", "sro,sri->soi", "sro,soi->sri"
-extra = [("tf32x3", {"default": "bf16x3", WG: "bf16"}, None), ("tf32x3", {"default": "bf16x3", XG: "bf16"}, None),
+extra = [({"default": "tf32x3", WG: "bf16x3"}, "bf16x3", None), ({"default": "tf32x3", XG: "bf16x3"}, "bf16x3", None),
+         ({"default": "tf32x3", FWD: "bf16x3"}, "bf16x3", None), ({"default": "bf16x3", FWD: "tf32x3"}, "bf16x3", None),
+         ("tf32x3", {"default": "bf16x3", WG: "bf16"}, None), ("tf32x3", {"default": "bf16x3", XG: "bf16"}, None),
          ("tf32x3", {"default": "bf16x3", WG: "bf16", XG: "bf16"}, None), ("tf32x3", {"default": "bf16x3", FWD: "bf16"}, None)]
 for gm, hm, om in [("fp32", "fp32", None), ("tf32x3", "tf32x3", None), ("bf16x3", "bf16x3", None), ("tf32x3", "bf16x3", None),
                    ("bf16x3", "tf32x3", None), ("tf32x3", "bf16x3", "bf16x3"), ("tf32x3", "bf16", None)] + extra:
     r = run(gm, hm, om)
+    om = om or (gm if isinstance(gm, str) else gm["default"])
+    if not isinstance(gm, str):
+        gm = gm["default"] + ", " + ", ".join(f"{v} for " + {FWD: "fwd", WG: "wgrad", XG: "xgrad"}[k] for k, v in gm.items() if k != "default")
     hm = hm if isinstance(hm, str) else "bf16x3, bf16 for " + "+".join({FWD: "fwd", WG: "wgrad", XG: "xgrad"}[k] for k in hm if k != "default")
-    print(f"| {gm} | {hm} | {om or gm} | {rel(r['u_grad'], ex['u_grad']):.2e} | {cos(r['u_grad'], ex['u_grad']):.6f} | "
+    print(f"| {gm} | {hm} | {om} | {rel(r['u_grad'], ex['u_grad']):.2e} | {cos(r['u_grad'], ex['u_grad']):.6f} | "
           f"{rel(r['v_grad'], ex['v_grad']):.2e} | {cos(r['v_grad'], ex['v_grad']):.6f} |", flush=True)
