@@ -679,6 +679,29 @@ size_t psvi_lenet_workspace_bytes(int32_t S, int32_t R) {
   return w.total + 256;
 }
 
+// The weight-gradient kernels of a backward pass only produce outputs: nothing later in the pass reads them.  They run on a side
+// stream, forked from the caller's stream after the kernel that produced their adjoint and joined at the end of the pass, so that
+// they overlap the (small-grid) data-adjoint chain.  The fork / join pattern is plain event record / wait: it is captured as
+// parallel branches when the caller's stream is being captured into a CUDA graph.  One side stream and event set per device,
+// created on first use (the first call of a process is never inside a capture: the graph path warms up eagerly).
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[16];
+  cudaEvent_t done = nullptr;
+};
+static SideStream* side_stream() {
+  static SideStream tab[32];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  SideStream& t = tab[dev];
+  if (!t.s) {
+    if (cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) != cudaSuccess) { t.s = nullptr; return nullptr; }
+    for (auto& e : t.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming);
+  }
+  return &t;
+}
+
 int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const float* x, const int32_t* y, const float* cw,
                     int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar, float* logits,
                     void* workspace, void* stream_) {
@@ -687,6 +710,15 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   PSVI_REQUIRE(!thetad || (tbar && tdbar), PSVI_ERR_INVALID, "the dual pass needs tbar and tdbar");
   PSVI_REQUIRE(R * 4 * 4 <= 200 * 1024, PSVI_ERR_UNSUPPORTED, "at most 12800 rows per call");
   cudaStream_t st = (cudaStream_t)stream_;
+  SideStream* side = (tbar && !getenv("PSVI_LENET_NO_FORK")) ? side_stream() : nullptr;
+  cudaStream_t wst = side ? side->s : st;     // where the weight-gradient kernels go
+  int n_ev = 0;
+  auto fork = [&]() {                         // everything launched on st so far is visible to what follows on wst
+    if (side) { cudaEventRecord(side->ev[n_ev], st); cudaStreamWaitEvent(wst, side->ev[n_ev], 0); ++n_ev; }
+  };
+  auto join = [&]() {
+    if (side) { cudaEventRecord(side->done, wst); cudaStreamWaitEvent(st, side->done, 0); }
+  };
   Ws w;
   carve_ws(S, R, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255), w);
   const size_t sR = (size_t)R;
@@ -725,7 +757,7 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     g.M = OUT; g.N = IN; g.K = R;
     g.out = wb; g.sO = LN_P; g.ldo = IN;
     g.colsum = bb; g.sCol = LN_P;
-    bgemm_kernel<false, false, G_TM, G_TN><<<dim3(tiles(OUT), tiles(IN), S), G_NT, 0, st>>>(g);
+    bgemm_kernel<false, false, G_TM, G_TN><<<dim3(tiles(OUT), tiles(IN), S), G_NT, 0, wst>>>(g);
   };
   // row chunks of the weight-gradient kernels: as many as fit in ONE wave of resident CTAs (at most N_CHUNKS)
   auto chunking = [&](int slots, int& rpc, int& nch) {
@@ -739,8 +771,8 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     static const int slots = resident_ctas(k, C::NT);
     int rpc, nch;
     chunking(slots, rpc, nch);
-    k<<<dim3(nch, S), C::NT, 0, st>>>(pb1, i1, sR * N_P1, pb2, i2, sR * N_P1, w.sel2, R, rpc, w.wpart);
-    conv_wgrad_reduce_kernel<<<dim3((2416 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 2400, 16, wb, bb, 0);
+    k<<<dim3(nch, S), C::NT, 0, wst>>>(pb1, i1, sR * N_P1, pb2, i2, sR * N_P1, w.sel2, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((2416 + 127) / 128, S), 128, 0, wst>>>(w.wpart, nch, S, 2400, 16, wb, bb, 0);
   };
   auto conv1_wgrad = [&](const float* pbv, float* wb, float* bb) {
     using C = ConvWgCfg<1, 6, 28, 2, 28>;
@@ -748,8 +780,8 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
     static const int slots = resident_ctas(k, C::NT);
     int rpc, nch;
     chunking(slots, rpc, nch);
-    k<<<dim3(nch, S), C::NT, 0, st>>>(pbv, x, 0, nullptr, nullptr, 0, w.sel1, R, rpc, w.wpart);
-    conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, st>>>(w.wpart, nch, S, 150, 6, wb, bb, 0);
+    k<<<dim3(nch, S), C::NT, 0, wst>>>(pbv, x, 0, nullptr, nullptr, 0, w.sel1, R, rpc, w.wpart);
+    conv_wgrad_reduce_kernel<<<dim3((156 + 127) / 128, S), 128, 0, wst>>>(w.wpart, nch, S, 150, 6, wb, bb, 0);
   };
   // ---- primal forward
   CONV1_FWD(S, R, st, x, 0, theta + O_W1, nullptr, 0, nullptr, theta + O_B1, w.sel1, 0, w.p1);
@@ -769,16 +801,22 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   if (!thetad) {
     // ---- gradient pass
     lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, nullptr, y, cw, S, R, 1, nll, w.go, nullptr, nullptr);
+    fork();
     lin_bwd_weight(w.go, w.h4, nullptr, nullptr, N_H4, N_O, tbar + O_W5, tbar + O_B5);
     lin_bwd_data(w.go, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4);
+    fork();
     lin_bwd_weight(w.g4, w.h3, nullptr, nullptr, N_H3, N_H4, tbar + O_W4, tbar + O_B4);
     lin_bwd_data(w.g4, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3);
+    fork();
     lin_bwd_weight(w.g3, w.p2, nullptr, nullptr, N_P2, N_H3, tbar + O_W3, tbar + O_B3);
     lin_bwd_data(w.g3, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2);
+    fork();
     conv2_wgrad(w.g2, w.p1, nullptr, nullptr, tbar + O_W2, tbar + O_B2);
     CONV2_BWD(S, R, st, w.g2, theta + O_W2, nullptr, nullptr, w.sel2, w.g1);
+    fork();
     conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1);
     if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, nullptr, nullptr, w.sel1, xbar);
+    join();
     LN_CHECK();
     return PSVI_OK;
   }
@@ -792,30 +830,36 @@ int psvi_lenet_pass(int32_t S, const float* theta, const float* thetad, const fl
   lenet_head_kernel<<<hb, 128, 0, st>>>(w.o, w.od, y, cw, S, R, 2, nll, w.go, w.god, acbar);
   LN_CHECK();
   // layer 5
+  fork();
   lin_bwd_weight(w.go, w.h4, w.god, w.hd4, N_H4, N_O, tbar + O_W5, tbar + O_B5);
   lin_bwd_weight(w.god, w.h4, nullptr, nullptr, N_H4, N_O, tdbar + O_W5, tdbar + O_B5);
   lin_bwd_data(w.go, theta + O_W5, w.god, thetad + O_W5, N_H4, N_O, w.h4, w.g4);
   lin_bwd_data(w.god, theta + O_W5, nullptr, nullptr, N_H4, N_O, w.h4, w.g4d);
   // layer 4
+  fork();
   lin_bwd_weight(w.g4, w.h3, w.g4d, w.hd3, N_H3, N_H4, tbar + O_W4, tbar + O_B4);
   lin_bwd_weight(w.g4d, w.h3, nullptr, nullptr, N_H3, N_H4, tdbar + O_W4, tdbar + O_B4);
   lin_bwd_data(w.g4, theta + O_W4, w.g4d, thetad + O_W4, N_H3, N_H4, w.h3, w.g3);
   lin_bwd_data(w.g4d, theta + O_W4, nullptr, nullptr, N_H3, N_H4, w.h3, w.g3d);
   // layer 3
+  fork();
   lin_bwd_weight(w.g3, w.p2, w.g3d, w.pd2, N_P2, N_H3, tbar + O_W3, tbar + O_B3);
   lin_bwd_weight(w.g3d, w.p2, nullptr, nullptr, N_P2, N_H3, tdbar + O_W3, tdbar + O_B3);
   lin_bwd_data(w.g3, theta + O_W3, w.g3d, thetad + O_W3, N_P2, N_H3, nullptr, w.g2);
   lin_bwd_data(w.g3d, theta + O_W3, nullptr, nullptr, N_P2, N_H3, nullptr, w.g2d);
   LN_CHECK();
   // conv 2
+  fork();
   conv2_wgrad(w.g2, w.p1, w.g2d, w.pd1, tbar + O_W2, tbar + O_B2);
   conv2_wgrad(w.g2d, w.p1, nullptr, nullptr, tdbar + O_W2, tdbar + O_B2);
   CONV2_BWD(S, R, st, w.g2, theta + O_W2, w.g2d, thetad + O_W2, w.sel2, w.g1);
   CONV2_BWD(S, R, st, w.g2d, theta + O_W2, nullptr, nullptr, w.sel2, w.g1d);
   // conv 1
+  fork();
   conv1_wgrad(w.g1, tbar + O_W1, tbar + O_B1);
   conv1_wgrad(w.g1d, tdbar + O_W1, tdbar + O_B1);
   if (xbar) CONV1_BWD(S, R, st, w.g1, theta + O_W1, w.g1d, thetad + O_W1, w.sel1, xbar);
+  join();
   LN_CHECK();
   return PSVI_OK;
 }
