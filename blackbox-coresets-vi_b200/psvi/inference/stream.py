@@ -221,13 +221,17 @@ class FnLargeNet:
         # the hypergradient's sensitivity to operand rounding sits in the GRADIENT passes (their g_i become Adam's denominators
         # and fix the trajectory); split-bf16 dual passes leave it at the tf32x3 level.
         self.precision_dual = precision if precision_dual is None else precision_dual
+        # ... and so is the outer objective's value / gradient pass (one per step): same study, row "outer pass = bf16x3"
+        self.precision_outer = self.precision_dual
+        self.phase = None          # StreamEngine.outer_grad sets "outer" around its passes
 
     @staticmethod
     def fits(dims, S):
         return len(dims) == 3 and dims[0] % 64 == 0 and dims[1] % 128 == 0 and dims[2] <= 16 and S <= 64
 
     def pass_(self, theta, thetad, x, y, cw, **out):
-        _native.fnl_pass(self.desc, self.precision if thetad is None else self.precision_dual, theta, thetad, x, y, cw, **out)
+        prec = self.precision_dual if thetad is not None else (self.precision_outer if self.phase == "outer" else self.precision)
+        _native.fnl_pass(self.desc, prec, theta, thetad, x, y, cw, **out)
 
     def logits(self, theta, x):
         lg = torch.empty(self.S, x.shape[0], self.C, device=x.device)
@@ -297,6 +301,13 @@ class StreamEngine:
         weights depend on the pseudo-data only.  Large minibatches are processed in chunks of ROW_CHUNK rows.
         `data_w` [B] (optional): per-row weights of the data term, d_s = (N / n_total) sum_b data_w_b nll[s, b] (the soft-label
         rows of learn_z); `extras` then receives "dwbar" = dLoss / d data_w."""
+        if getattr(self.net, "phase", 0) is None:      # nets with per-phase arithmetic (FnLargeNet): mark the outer passes
+            self.net.phase = "outer"
+            try:
+                return self.outer_grad(phi, eps, u, z32, a, xb, yb32, N, kappa=kappa, n_total=n_total, xb_bf16=xb_bf16,
+                                       data_w=data_w, extras=extras)
+            finally:
+                self.net.phase = None
         if xb_bf16 is not None:
             return self._outer_grad_fulldata(phi, eps, u, z32, a, xb_bf16, yb32, N, kappa, n_total)
         S, M, B, dev = self.S, u.shape[0], xb.shape[0], u.device
