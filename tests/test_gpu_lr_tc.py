@@ -70,3 +70,43 @@ def test_lr_predictive_tc_matches_oracle(D, C, S, n_rows, mode):
     np.testing.assert_allclose(o[0], o2[0], rtol=2e-2)
     if mode == 0:
         np.testing.assert_allclose(o[3:5], o2[3:5], rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["lr", "fn"])
+def test_predictive_tc_slabs_equals_the_per_slab_calls(kind):
+    """psvi_predictive_tc_slabs (one native call over all test batches of a rank: PSVI.evaluate, reference psvi_classes.py:1038-1092,
+    a fresh noise slab per batch) == the per-slab entry points called in a loop: sums bit-identical, the importance-weight
+    diagnostics those of the LAST slab; ragged last batch (n_rows % batch != 0) and a non-zero first slab index."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    rng = np.random.default_rng(3)
+    if kind == "lr":
+        dims, S, n_rows, batch = [128, 10], 8, 1000, 384
+    else:
+        dims, S, n_rows, batch = [64, 128, 3], 4, 700, 256
+    D, C = dims[0], dims[-1]
+    P = po.p_theta(dims)
+    M, N, first = 16, 3000.0, 2
+    mu = dev((0.15 * rng.standard_normal(P)).astype(np.float32))
+    rho = dev(np.full(P, po.inverse_softplus(0.05), np.float32))
+    u, z = dev(rng.standard_normal((M, D)).astype(np.float32)), dev(rng.integers(0, C, M), torch.int32)
+    v = dev((0.3 * rng.standard_normal(M)).astype(np.float32))
+    xb = dev(rng.standard_normal((n_rows, D)).astype(np.float32)).bfloat16().contiguous()
+    y = dev(rng.integers(0, C, n_rows), torch.int32)
+    model = nat.make_model(dims, S)
+    noise = nat.make_noise(None, seed=5, domain=9)
+    n_scr = (nat.lr_predictive_tc_scratch_floats(model) if kind == "lr" else nat.fn_tc_scratch_floats(model, batch, M)) + 256
+    one = nat.lr_predictive_tc if kind == "lr" else nat.fn_predictive_tc
+    for mode in (0, 1):
+        acc, last = torch.zeros(3, device="cuda", dtype=torch.float64), None
+        for k, r0 in enumerate(range(0, n_rows, batch)):
+            out = zeros(8)
+            one(model, noise, mu, rho, u, z, v, xb[r0:r0 + batch], y[r0:r0 + batch], first + k, N, 1, 0.0, mode, out, zeros(n_scr))
+            acc += out[:3].double()
+            last = out[3:5].clone()
+        out = zeros(8)
+        nat.predictive_tc_slabs(model, noise, mu, rho, u, z, v, xb, y, batch, first, N, 1, 0.0, mode, out, zeros(n_scr))
+        torch.cuda.synchronize()
+        assert out[2].item() == n_rows
+        np.testing.assert_allclose(out[:3].cpu().numpy(), acc.cpu().numpy(), rtol=1e-6)
+        assert torch.equal(out[3:5], last)
