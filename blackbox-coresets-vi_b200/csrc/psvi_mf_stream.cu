@@ -44,6 +44,12 @@ struct SP {
   float* xbar;           // [S][R][D]
   float* acbar;          // [S][R]
   float* logits_out;     // [S][R][C] (forward mode)
+  // likelihood of the per-sample pass: 0 = categorical (softmax over C logits, int labels), 1 = Gaussian with precision tau on
+  // ONE output (the regressors, reference psvi_classes.py:1986,2034-2057): labels are float bits in y, nll = tau/2 (o - y)^2 +
+  // 1/2 log(2 pi / tau); ybar [S][R] (nullable) receives d(sum_r cw nll)/dy -- or its directional derivative in the dual pass
+  int like;
+  float tau;
+  float* ybar;
   // predictive
   int n_rows, row0, eval_mode;
   const float* lw;       // [S] log importance weights (mode 0)
@@ -152,10 +158,24 @@ struct Worker {
     }
   }
   // NLL per row; grad != 0: also the output adjoint cw * (softmax - onehot)
-  __device__ void loss(int nr, bool grad) {
+  __device__ void loss(int nr, bool grad, float* yb_out) {
     const int C = p.dims[p.L], ld = mt.lda[p.L];
     const float* o = F(ly.act[p.L]);
     float* ao = F(ly.adj[p.L]);
+    if (p.like == 1) {
+      const float hl = 0.5f * logf(6.283185307179586f / p.tau);
+      for (int rr = tid; rr < nr; rr += NT) {
+        const float r = o[rr * ld] - __int_as_float(I(ly.lab)[rr]);
+        F(ly.nll)[rr] = 0.5f * p.tau * r * r + hl;
+        if (grad) {
+          const float g = F(ly.cw)[rr] * p.tau * r;
+          ao[rr * ld] = g;
+          if (yb_out) yb_out[rr] = -g;
+        }
+      }
+      __syncthreads();
+      return;
+    }
     for (int rr = tid; rr < nr; rr += NT) {
       const float* row = o + rr * ld;
       float mx = row[0];
@@ -214,12 +234,25 @@ struct Worker {
       __syncthreads();
     }
   }
-  __device__ void loss_dual(int nr, float* ac_out) {
+  __device__ void loss_dual(int nr, float* ac_out, float* yb_out) {
     const int C = p.dims[p.L], ld = mt.lda[p.L];
     const float* o = F(ly.act[p.L]);
     const float* od = F(ly.actd[p.L]);
     float* ao = F(ly.adj[p.L]);
     float* aod = F(ly.adjd[p.L]);
+    if (p.like == 1) {
+      const float hl = 0.5f * logf(6.283185307179586f / p.tau);
+      for (int rr = tid; rr < nr; rr += NT) {
+        const float r = o[rr * ld] - __int_as_float(I(ly.lab)[rr]), d = od[rr * ld], w = F(ly.cw)[rr];
+        F(ly.nll)[rr] = 0.5f * p.tau * r * r + hl;
+        aod[rr * ld] = w * p.tau * r;          // adjoint of the tangent output
+        ao[rr * ld] = w * p.tau * d;           // second-order term: d/d eps of (tau (o - y))
+        if (ac_out) ac_out[rr] = p.tau * r * d;
+        if (yb_out) yb_out[rr] = -w * p.tau * d;
+      }
+      __syncthreads();
+      return;
+    }
     for (int rr = tid; rr < nr; rr += NT) {
       const float* row = o + rr * ld;
       const float* rowd = od + rr * ld;
@@ -307,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) fwdbwd_kernel(const __grid_constant__ S
     for (int rr = threadIdx.x; rr < nr; rr += NT) w.F(ly.cw)[rr] = p.roww ? __ldg(p.roww + r0 + rr) : p.wscale;
     __syncthreads();
     w.forward(nr);
-    w.loss(nr, true);
+    w.loss(nr, true, nullptr);
     for (int rr = threadIdx.x; rr < nr; rr += NT) part += w.F(ly.cw)[rr] * w.F(ly.nll)[rr];
     w.backward(nr, p.tbar + (size_t)s * mt.Pt, r0 == 0);
   }
@@ -340,11 +373,11 @@ __global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__
     float* xb = p.xbar ? p.xbar + ((size_t)s * p.R + r0) * D : nullptr;
     if (mode == 2) {
       w.forward_dual(nr);
-      w.loss_dual(nr, p.acbar ? p.acbar + (size_t)s * p.R + r0 : nullptr);
+      w.loss_dual(nr, p.acbar ? p.acbar + (size_t)s * p.R + r0 : nullptr, p.ybar ? p.ybar + (size_t)s * p.R + r0 : nullptr);
       w.backward_any(nr, true, p.tbar + (size_t)s * mt.Pt, p.tdbar + (size_t)s * mt.Pt, xb, r0 == 0);
     } else {
       w.forward(nr);
-      w.loss(nr, mode == 1);
+      w.loss(nr, mode == 1, p.ybar ? p.ybar + (size_t)s * p.R + r0 : nullptr);
       if (mode == 1) w.backward_any(nr, false, p.tbar + (size_t)s * mt.Pt, nullptr, xb, r0 == 0);
     }
     if (p.nll_out)
@@ -442,7 +475,7 @@ __global__ void __launch_bounds__(NT, 1) logweight_kernel(const __grid_constant_
     const int nr = min(p.RC, p.R - r0);
     w.stage(p.x, p.y, r0, nr);
     w.forward(nr);
-    w.loss(nr, false);
+    w.loss(nr, false, nullptr);
     for (int rr = threadIdx.x; rr < nr; rr += NT) ps += __ldg(p.roww + r0 + rr) * w.F(ly.nll)[rr];
     __syncthreads();
   }
@@ -672,9 +705,28 @@ int psvi_mf_evaluate_stream(const psvi_mf_model* model, const psvi_noise* noise,
   return PSVI_OK;
 }
 
+static int net_pass_impl(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+                         const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                         float* logits, int like, float tau, float* ybar, void* stream_);
+
 int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
                   const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
                   float* logits, void* stream_) {
+  return net_pass_impl(model, theta, thetad, x, y, cw, R, nll, tbar, tdbar, xbar, acbar, logits, 0, 0.f, nullptr, stream_);
+}
+
+int psvi_net_pass_gaussian(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const float* y,
+                           const float* cw, int32_t R, float tau, float* nll, float* tbar, float* tdbar, float* xbar,
+                           float* acbar, float* ybar, float* outputs, void* stream_) {
+  PSVI_REQUIRE(model && model->dims[model->n_layers] == 1, PSVI_ERR_UNSUPPORTED, "the Gaussian likelihood is built for ONE output");
+  PSVI_REQUIRE(tau > 0.f, PSVI_ERR_INVALID, "tau must be positive");
+  return net_pass_impl(model, theta, thetad, x, reinterpret_cast<const int32_t*>(y), cw, R, nll, tbar, tdbar, xbar, acbar,
+                       outputs, 1, tau, ybar, stream_);
+}
+
+static int net_pass_impl(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
+                         const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                         float* logits, int like, float tau, float* ybar, void* stream_) {
   PSVI_REQUIRE(model && theta && x && y && R > 0, PSVI_ERR_INVALID, "null pointer or R<=0");
   PSVI_REQUIRE(model->n_layers >= 1 && model->n_layers <= MAXL, PSVI_ERR_INVALID, "bad n_layers");
   const int mode = thetad ? 2 : (tbar ? 1 : 0);
@@ -689,6 +741,7 @@ int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* t
   fill_sp(p, model, &dummy);
   p.theta = const_cast<float*>(theta); p.thetad = thetad; p.x = x; p.y = y; p.cwm = cw; p.R = R;
   p.nll_out = nll; p.tbar = tbar; p.tdbar = tdbar; p.xbar = xbar; p.acbar = acbar; p.logits_out = logits;
+  p.like = like; p.tau = tau; p.ybar = ybar;
   int dev = 0, smem_max = 0;
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

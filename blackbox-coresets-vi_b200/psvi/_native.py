@@ -106,6 +106,9 @@ _SIGS = {
                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_net_pass": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "psvi_net_pass_gaussian": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "psvi_net_predict": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_fc_matvec": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
@@ -409,6 +412,14 @@ def net_pass(model, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xb
     _count(1)
     _check(lib().psvi_net_pass(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y, torch.int32), _p(cw), x.shape[0],
                                _p(nll), _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(logits), _stream()))
+
+
+def net_pass_gaussian(model, theta, thetad, x, y, cw, tau, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, ybar=None,
+                      outputs=None):
+    """Per-sample pass with the Gaussian likelihood of the regressors (y: float targets [R]; one network output)."""
+    _count(1)
+    _check(lib().psvi_net_pass_gaussian(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y), _p(cw), x.shape[0], float(tau),
+                                        _p(nll), _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(ybar), _p(outputs), _stream()))
 
 
 def net_predict(model, theta, log_weights, mode, xt, yt, out):

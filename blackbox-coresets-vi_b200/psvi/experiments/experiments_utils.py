@@ -10,7 +10,22 @@ import torch
 import torch.nn as nn
 from torch.utils.data import Dataset
 
-from psvi.models.neural_net import VILinear, make_fc2net, make_fcnet, make_lenet, make_logistic_regression
+from psvi.models.neural_net import (VILinear, make_fc2net, make_fcnet, make_lenet, make_logistic_regression,
+                                    make_regressor_net)
+
+
+class BaseDataset(Dataset):
+    """(x, y) tensor dataset of the regression flows (reference experiments_utils.py: BaseDataset)."""
+
+    def __init__(self, x, y=None, randomize=False):
+        self.data = x.mean() + 1.0 * torch.randn_like(x) if randomize else x
+        self.targets = y
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, index):
+        return self.data[index], self.targets[index]
 
 
 class SynthDataset(Dataset):
@@ -66,6 +81,8 @@ def set_up_model(D=None, n_hidden=None, nc=None, mc_samples=None, architecture=N
         return make_lenet(mc_samples=mc_samples)
     elif architecture == "logistic_regression":
         return make_logistic_regression(D, nc, mc_samples=mc_samples)
+    elif architecture == "regressor_net":
+        return make_regressor_net(D, n_hidden, nc, linear_class=VILinear, nonl_class=nn.ReLU, mc_samples=mc_samples, **kwargs)
     raise ValueError("Architecture should be one of \n'lenet', 'logistic_regression', "
                      "'logistic_regression_fullcov', 'fn', 'fn2', 'residual_fn'")
 

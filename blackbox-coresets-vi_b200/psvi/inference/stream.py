@@ -208,6 +208,29 @@ class MlpNet:
         return lg
 
 
+class GaussMlpNet(MlpNet):
+    """The same per-sample MLP pass with the Gaussian likelihood of the regressors (psvi_net_pass_gaussian: one output, precision
+    tau, float targets).  `wants_ybar`: the engine also collects d/dy -- the targets z of the pseudo-points are learnable
+    (reference psvi_classes.py:2064-2087)."""
+
+    wants_ybar = True
+
+    def __init__(self, dims, S, tau):
+        super().__init__(dims, S)
+        self.tau = float(tau)
+
+    def pass_(self, theta, thetad, x, y, cw, logits=None, **out):
+        _native.net_pass_gaussian(self.desc, theta, thetad, x, y, cw, self.tau, outputs=logits, **out)
+
+    def logits(self, theta, x):
+        out = torch.empty(theta.shape[0], x.shape[0], 1, device=x.device)
+        _native.net_pass_gaussian(self.desc, theta, None, x, torch.zeros(x.shape[0], device=x.device), None, self.tau, outputs=out)
+        return out
+
+    def predict(self, theta, lw, mode, xt, yt, out):
+        raise NotImplementedError("the regressors evaluate through PSVI_regressor.evaluate (RMSE / log-likelihood)")
+
+
 class FnLargeNet:
     """Per-sample pass of fn with one hidden layer in the large regime: batched TMA + tcgen05 GEMMs (csrc/psvi_fn_large.cu).
     `precision`: _native.PREC_TF32X3 (default; fp32-class accuracy, needed by the unrolled hypergradient), PREC_BF16X3
@@ -347,7 +370,12 @@ class StreamEngine:
             if extras is not None and data_w is not None:
                 extras["dwbar"] = ((w * N / n_total) @ nd[:, M:]).float()
             xbar = torch.empty(S, M + B, X.shape[1], device=dev)
-            self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar)
+            yk = {}
+            if extras is not None and getattr(self.net, "wants_ybar", False):
+                yk["ybar"] = torch.empty(S, M + B, device=dev)
+            self.net.pass_(theta, None, X, lab, cw, nll=nll, tbar=tbar, xbar=xbar, **yk)
+            if yk:
+                extras["zbar_outer"] = yk["ybar"][:, :M].sum(0)
             xbar_u, nll_u = xbar[:, :M], nll[:, :M]
         else:
             xbar_u = torch.empty(S, M, u.shape[1], device=dev)
@@ -435,8 +463,10 @@ class StreamEngine:
         theta, thetad = self.fam.sample(phi, eps), self.fam.tangent(phi, phidot, eps)
         tbar, tdbar = torch.empty(S, self.Pt, device=dev), torch.empty(S, self.Pt, device=dev)
         xbar, ac = torch.empty(S, M, u.shape[1], device=dev), torch.empty(S, M, device=dev)
+        yk = {"ybar": torch.empty(S, M, device=dev)} if getattr(self.net, "wants_ybar", False) else {}
         self.net.pass_(theta, thetad, u, z32, a.expand(S, M).contiguous() if a_exp is None else a_exp, tbar=tbar, tdbar=tdbar,
-                       xbar=xbar, acbar=ac)
+                       xbar=xbar, acbar=ac, **yk)
+        self._last_hz = yk["ybar"].sum(0) if yk else None       # mixed derivative wrt the (learnable) targets
         return self.fam.hvp(phi, phidot, eps, tbar, tdbar), xbar.sum(0), ac.sum(0)
 
     # ---- unrolled robust Adam + reverse sweep (optim.py:303-367) -----------------------------------------
@@ -480,6 +510,8 @@ class StreamEngine:
                                                math.sqrt(1.0 - B2 ** (t + 1)))
             h, hu, ha = self.hvp(phi_t, eps_all[t], u, z32, a, gbar, a_exp=a_exp, fixed=True)
             pbar, ubar, abar = pbar + h, ubar + hu, abar + ha
+            if extras is not None and self._last_hz is not None:
+                extras["zbar"] = extras.get("zbar", extras.get("zbar_outer", 0.0)) + self._last_hz
         return loss, ubar, abar, phi_T, (torch.stack(losses).float() if want_losses else None)
 
     # ---- the same step as ONE CUDA graph ---------------------------------------------------------------------------------

@@ -491,8 +491,27 @@ def make_alexnet(*args, **kwargs):
     raise NotImplementedError("alexnet is outside the PSVI hot-path scope (SURVEY.md section 2, row 1)")
 
 
-def make_regressor_net(*args, **kwargs):
-    raise NotImplementedError("regressor nets are outside the PSVI hot-path scope (SURVEY.md section 8f)")
+def gaussian_fn(loc=None, scale=None):
+    """reference :18-19"""
+    return torch.distributions.normal.Normal(loc, scale)
+
+
+def make_regressor_net(in_dim, h_dim, out_dim=1, n_layers=2, linear_class=None, nonl_class=None, mc_samples=4, residual=False,
+                       **kwargs):
+    """reference :300-331 (module names lin{i}, nonl{i}, regressor; default TWO hidden layers): a mean-field stack, evaluated by
+    the per-sample network kernels with the Gaussian likelihood (psvi_net_pass_gaussian)."""
+    if linear_class is None:
+        linear_class = VILinear
+    if nonl_class is None:
+        nonl_class = nn.ReLU
+    net = MeanFieldMLP() if (linear_class is VILinear and nonl_class is nn.ReLU) else nn.Sequential()
+    for i in range(n_layers):
+        net.add_module(f"lin{i}", linear_class(in_dim if i == 0 else h_dim, h_dim, **kwargs))
+        net.add_module(f"nonl{i}", nonl_class())
+    net.add_module("regressor", linear_class(h_dim, out_dim, **kwargs))
+    for module in net.modules():
+        module.mc_samples = mc_samples
+    return net
 
 
 def make_resnet(*args, **kwargs):

@@ -196,6 +196,16 @@ int psvi_mf_evaluate_stream(const psvi_mf_model* model, const psvi_noise* noise,
 int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,
                   const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
                   float* logits /* [S][R][C], nullable */, void* stream);
+
+/* The same per-sample pass with a GAUSSIAN likelihood of precision tau on a one-output network (the regressors: reference
+ * psvi/inference/psvi_classes.py:1986 `gaussian_fn(scale = 1 / sqrt(tau))`, :2034-2057 psvi_elbo / inner_elbo of PSVI_regressor):
+ *   nll[s][r] = tau / 2 (o_s(x_r) - y_r)^2 + 1/2 log(2 pi / tau),   y [R] float targets.
+ * ybar [S][R] (nullable): gradient pass: d(sum_r cw[s][r] nll[s][r]) / dy_r = -cw tau (o - y); dual pass: its directional derivative
+ * along thetad, -cw tau odot (the mixed term the hypergradient on learnable targets z needs, psvi_classes.py:2064-2087).
+ * outputs [S][R] (nullable, forward mode): the network outputs. */
+int psvi_net_pass_gaussian(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const float* y,
+                           const float* cw, int32_t R, float tau, float* nll, float* tbar, float* tdbar, float* xbar,
+                           float* acbar, float* ybar, float* outputs, void* stream);
 /* psvi_net_predict: predictive metrics of rows xt with sampled weights theta [S][P]; mode 0 needs log_weights [S]
  *   (softmax-ed inside); out [8] as psvi_mf_evaluate; workspace of psvi_mf_stream_workspace_bytes(model, n_rows). */
 int psvi_net_predict(const psvi_mf_model* model, const float* theta, const float* log_weights, int32_t mode,

@@ -10,6 +10,8 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
   fixedpoint_fn_hm.npz   PSVI.hyper_step with hypergrad_approx="fixed_point" (hypergradients.py:83-140)
   joint_fn_hm.npz / alternating_fn_hm.npz   two joint_step / alternating_step calls (psvi_classes.py:517-539); made by
                          `python oracle/make_goldens_r2.py trainers`
+  regressor_*.npz        PSVILearnV_regressor / PSVIAV_regressor (psvi_classes.py:1940-2335; broken upstream, see run_regressor):
+                         `python oracle/make_goldens_r2.py regressor`
   meanfieldvi_hm.npz     MeanFieldVI (inference/utils.py:221-450) with forgetting scores; `python oracle/make_goldens_r2.py meanfieldvi`
   learnz_fn_fb.npz       learn_z=True (soft pseudo-labels, KLDiv branch): inner_elbo, psvi_elbo, one nested_step with z.grad, and
                          evaluate(); made by `python oracle/make_goldens_r2.py learnz`
@@ -316,7 +318,94 @@ def run_meanfieldvi(name="meanfieldvi_hm"):
           "size", os.path.getsize(pth))
 
 
+def regression_data(seed=0, n=300, D=6):
+    """Synthetic regression benchmark in the shape read_regression_dataset gives (experiments_utils.py): inputs and TRAIN targets
+    standardised with the training statistics, validation / test targets raw."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, D))
+    Y = 2.0 + 1.5 * np.sin(X[:, 0]) + 0.5 * X[:, 1] ** 2 - X[:, 2] + 0.1 * rng.standard_normal(n)
+    ntr, nva = 200, 40
+    x, y, xv, yv, xt, yt = X[:ntr], Y[:ntr], X[ntr:ntr + nva], Y[ntr:ntr + nva], X[ntr + nva:], Y[ntr + nva:]
+    xm, xs, ym, ys = x.mean(0), x.std(0), y.mean(), y.std()
+    f32 = lambda a: a.astype(np.float32)
+    return (f32((x - xm) / xs), f32((y - ym) / ys), f32((xv - xm) / xs), f32(yv), f32((xt - xm) / xs), f32(yt), float(ym), float(ys))
+
+
+def run_regressor(cls_name, H=8, M=10, S=4, T=3, B=32, tau=0.5, init_sd=1e-2, lr0net=1e-3, lr0z=1e-2):
+    """The Gaussian-likelihood regressors (psvi_classes.py:1940-2335).  Upstream they cannot be constructed: PSVI_regressor.__init__
+    prints `device_id`, which is neither a parameter nor a global (:1975, NameError), and PSVIAV_regressor.nested_step reads
+    `self.scheduler_optim_net`, which nothing sets (:2329).  The harness supplies both from OUTSIDE (builtins.device_id = None,
+    obj.scheduler_optim_net = None) -- the reference source stays unmodified -- and records one nested_step (loss, hypergradients
+    on u, v, the learnable targets z[, alpha]) in fp64 and evaluate() in fp32."""
+    import builtins
+    builtins.device_id = None
+    from psvi.experiments.experiments_utils import BaseDataset
+    x, y, xv, yv, xt, yt, ym, ys = regression_data()
+    T_ = torch.from_numpy
+    tr, va, te = BaseDataset(T_(x), T_(y)), BaseDataset(T_(xv), T_(yv)), BaseDataset(T_(xt), T_(yt))
+    N, D = x.shape
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=D, N=N, inner_it=T, trainer="nested", architecture="regressor_net",
+              n_hidden=H, nc=1, train_dataset=tr, val_dataset=va, test_dataset=te, y_mean=torch.tensor(ym), y_std=torch.tensor(ys),
+              tau=tau, num_pseudo=M, init_args="subsample", lr0net=lr0net, lr0u=1e-3, lr0v=1e-2, lr0z=lr0z, init_sd=init_sd,
+              log_every=10, seed=0)
+    with _quiet(), contextlib.redirect_stderr(io.StringIO()):
+        obj = getattr(rc, cls_name)(**kw)
+        obj.run_psvi(**kw)
+    obj.scheduler_optim_net = None
+    tdt = torch.float64
+    obj.model.to(tdt)
+    rng = np.random.default_rng(13)
+    v0 = (0.3 * rng.standard_normal(M)).astype(np.float32)
+    obj.v = torch.tensor(v0, dtype=tdt).requires_grad_(True)
+    obj.u = obj.u.detach().to(tdt).requires_grad_(True)
+    obj.z = obj.z.detach().to(tdt).requires_grad_(True)
+    alpha0 = 0.0
+    if cls_name == "PSVIAV_regressor":
+        alpha0 = 0.3
+        obj.alpha = torch.tensor([alpha0], dtype=tdt).requires_grad_(True)
+        obj.optim_alpha = torch.optim.Adam([obj.alpha], 1e-3)
+    obj.optim_net = torch.optim.Adam(list(obj.model.parameters()), lr0net)
+    obj.optim_u, obj.optim_v, obj.optim_z = (torch.optim.Adam([obj.u], 1e-3), torch.optim.Adam([obj.v], 1e-2),
+                                             torch.optim.Adam([obj.z], lr0z))
+    xb, yb = T_(x[:B]).to(tdt), T_(y[:B]).to(tdt)
+    dims = model_dims(obj.model)
+    mu0, rho0 = get_mu_rho(obj.model)
+    out = dict(dims=np.array(dims), N=N, S=S, T=T, M=M, B=B, tau=tau, lr0net=lr0net, lr0z=lr0z, noise_seed=3434, cls=cls_name,
+               vmode=2 if cls_name == "PSVIAV_regressor" else 1, alpha0=alpha0, y_mean=ym, y_std=ys, mu0=mu0, rho0=rho0,
+               u0=obj.u.detach().numpy().copy(), z0=obj.z.detach().numpy().copy(), v0=v0.astype(np.float64),
+               xb=xb.numpy().copy(), yb=yb.numpy().copy(), x=x, y=y, xv=xv, yv=yv, xt=xt, yt=yt)
+    with NoiseFeeder(dims, S, 3434) as nf, _quiet():
+        out["ref64_inner_elbo"] = obj.inner_elbo(model=obj.model).item()
+        out["ref64_psvi_elbo"] = obj.psvi_elbo(xb, yb, model=obj.model).item()
+        loss = obj.nested_step(xb, yb)
+        out["ref64_nested_loss"] = loss.item()
+        out["ref64_gu"], out["ref64_gv"], out["ref64_gz"] = (obj.u.grad.numpy().copy(), obj.v.grad.numpy().copy(),
+                                                              obj.z.grad.numpy().copy())
+        if cls_name == "PSVIAV_regressor":
+            out["ref64_galpha"] = obj.alpha.grad.numpy().copy()
+        out["ref64_params"] = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().numpy().copy()
+        out["ref64_u_after"], out["ref64_v_after"], out["ref64_z_after"] = (
+            obj.u.detach().numpy().copy(), obj.v.detach().numpy().copy(), obj.z.detach().numpy().copy())
+        out["n_forwards_step"] = len(nf.history)
+        obj.model.to(torch.float32)
+        obj.u, obj.z, obj.v = obj.u.detach().float(), obj.z.detach().float(), obj.v.detach().float()
+        if cls_name == "PSVIAV_regressor":
+            obj.alpha = obj.alpha.detach().float()
+        rmse, ll = obj.evaluate()
+        out["ref32_eval"] = np.array([rmse.item(), ll.item()])
+        out["n_forwards"] = len(nf.history)
+    pth = os.path.join(GOLD, f"regressor_{cls_name}.npz")
+    np.savez_compressed(pth, **out)
+    print(cls_name, "dims", dims, "forwards", out["n_forwards_step"], out["n_forwards"], "inner", out["ref64_inner_elbo"], "outer",
+          out["ref64_psvi_elbo"], "loss", out["ref64_nested_loss"], "|gz|", np.abs(out["ref64_gz"]).max(), "eval", out["ref32_eval"],
+          "size", os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "regressor":
+        for c in ("PSVILearnV_regressor", "PSVIAV_regressor"):
+            run_regressor(c)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "meanfieldvi":
         run_meanfieldvi()
         return

@@ -564,6 +564,107 @@ def evaluate_learn_z(mu, rho, eps_batches, xt, yt, dims, batch):
     return correct / n, nll_sum / n, -(w * np.log(w)).sum(), (w.sum() ** 2 / (w * w).sum()) / S
 
 
+# ------------------------------------------------------------------- regressors: Gaussian likelihood, learnable targets z
+def gauss_nll_rows(out, y, tau):
+    """-Normal(out, 1 / sqrt(tau)).log_prob(y)  (psvi_classes.py:1986, neural_net.py:18-19): [S, R] and the residuals."""
+    r = out[..., 0] - y[None, :]
+    return 0.5 * tau * r * r + 0.5 * np.log(2.0 * np.pi / tau), r
+
+
+def inner_grad_gauss(mu, rho, eps, u, z, a, dims, tau):
+    """value, d/dmu, d/drho of PSVI_regressor.inner_elbo (psvi_classes.py:2051-2057)."""
+    theta = mf_sample(mu, rho, eps)
+    out, cache = mlp_forward(theta, u, dims)
+    nll, r = gauss_nll_rows(out, z, tau)
+    tb, _ = mlp_backward(theta, cache, dims, (a[None, :] * tau * r)[..., None])
+    mu_bar, rho_bar = reparam_grad(mu, rho, eps, tb)
+    return np.sum(nll @ a) + mf_kl(mu, rho), mu_bar, rho_bar
+
+
+def inner_hvp_gauss(mu, rho, eps, u, z, a, dims, tau, mu_dot, rho_dot):
+    """(H_phiphi g, H_uphi g, H_aphi g, H_zphi g) of the Gaussian inner objective for g = (mu_dot, rho_dot)."""
+    sg, sig = softplus(rho), sigmoid(rho)
+    theta = mu[None] + sg[None] * eps
+    theta_dot = mu_dot[None] + (sig * rho_dot)[None] * eps
+    o, od, cache = mlp_dual_forward(theta, theta_dot, u, dims)
+    _, r = gauss_nll_rows(o, z, tau)
+    d = od[..., 0]
+    A_od = (a[None, :] * tau * r)[..., None]
+    A_o = (a[None, :] * tau * d)[..., None]
+    A_c = (tau * r * d).sum(0)
+    A_z = -(a[None, :] * tau * d).sum(0)
+    A_t, A_td, A_x = mlp_dual_backward(theta, theta_dot, cache, dims, A_o, A_od)
+    hmu = A_t.sum(0) + mu_dot
+    hrho = (sig * (A_t * eps).sum(0)
+            + sig * (1 - sig) * rho_dot * (A_td * eps).sum(0)
+            + ((1 + 1 / (sg * sg)) * sig * sig + (sg - 1 / sg) * sig * (1 - sig)) * rho_dot)
+    return hmu, hrho, A_x.sum(0), A_c, A_z
+
+
+def psvi_elbo_grad_gauss(mu, rho, eps, u, z, a, xb, yb, N, dims, tau):
+    """value and d/dmu, d/drho, d/du, d/da, d/dz of PSVI_regressor.psvi_elbo (psvi_classes.py:2034-2048)."""
+    theta = mf_sample(mu, rho, eps)
+    M, B, S = u.shape[0], xb.shape[0], eps.shape[0]
+    out, cache = mlp_forward(theta, np.concatenate([u, xb], 0), dims)
+    nll, r = gauss_nll_rows(out, np.concatenate([z, yb]), tau)
+    ps, ds = nll[:, :M] @ a, (N / B) * nll[:, M:].sum(-1)
+    lw = -ps + mf_sampled_nkl(mu, rho, eps, theta)
+    w = softmax(lw, 0)
+    e = ds - ps
+    loss = np.sum(w * e) - lw.mean()
+    beta = w * (e - np.sum(w * e)) - 1.0 / S
+    gp = -w - beta
+    rw = np.concatenate([gp[:, None] * a[None, :], np.broadcast_to((w * N / B)[:, None], (S, B))], 1)
+    tb, xbar = mlp_backward(theta, cache, dims, (rw * tau * r)[..., None])
+    tb = tb - beta[:, None] * theta
+    mu_bar, rho_bar = reparam_grad(mu, rho, eps, tb, kl_coef=0.0, rho_extra=beta.sum() / softplus(rho))
+    return loss, mu_bar, rho_bar, xbar[:, :M].sum(0), gp @ nll[:, :M], -(rw * tau * r)[:, :M].sum(0)
+
+
+def nested_step_regressor(mu, rho, eps_inner, eps_outer, u, z, v, xb, yb, N, dims, lr, tau, vmode=1, alpha=0.0):
+    """PSVI_regressor.nested_step (psvi_classes.py:2059-2093; PSVIAV_regressor :2303-2335): hypergradients on u, v[, alpha] and
+    the learnable targets z through the unrolled inner Adam loop."""
+    T, P = eps_inner.shape[0], mu.shape[0]
+    a = coreset_weights(v, N, vmode, alpha)
+    phi = np.concatenate([mu, rho])
+    m = np.zeros_like(phi); vv = np.zeros_like(phi)
+    traj = []
+    for k in range(T):
+        _, gmu, grho = inner_grad_gauss(phi[:P], phi[P:], eps_inner[k], u, z, a, dims, tau)
+        g = np.concatenate([gmu, grho])
+        phi_new, m, vv = robust_adam_step(phi, g, m, vv, k + 1, lr)
+        traj.append((phi, g, m, vv))
+        phi = phi_new
+    loss, mu_bar, rho_bar, u_bar, a_bar, z_bar = psvi_elbo_grad_gauss(phi[:P], phi[P:], eps_outer, u, z, a, xb, yb, N, dims, tau)
+    pbar = np.concatenate([mu_bar, rho_bar])
+    mbar = np.zeros_like(pbar); vbar = np.zeros_like(pbar)
+    for k in range(T - 1, -1, -1):
+        phi_t, g, m_t, v_t = traj[k]
+        gbar, mbar, vbar = robust_adam_step_vjp(pbar, mbar, vbar, g, m_t, v_t, k + 1, lr)
+        hmu, hrho, hu, ha, hz = inner_hvp_gauss(phi_t[:P], phi_t[P:], eps_inner[k], u, z, a, dims, tau, gbar[:P], gbar[P:])
+        pbar = pbar + np.concatenate([hmu, hrho])
+        u_bar, a_bar, z_bar = u_bar + hu, a_bar + ha, z_bar + hz
+    v_bar, alpha_bar = coreset_weights_vjp(v, N, vmode, a_bar, alpha)
+    return dict(loss=loss, u_grad=u_bar, v_grad=v_bar, z_grad=z_bar, alpha_grad=alpha_bar, mu_T=phi[:P], rho_T=phi[P:])
+
+
+def evaluate_regressor(mu, rho, eps_batches, xt, yt, dims, batch, tau, y_mean, y_std):
+    """PSVI_regressor.evaluate (psvi_classes.py:2221-2264): the pseudo term is `.sum()`-med over samples before it meets the
+    log-weights, so the weights are softmax(sampled_nkl); predictions are de-normalised, the log-likelihood uses them as they
+    are.  Returns (rmse, mean log-likelihood)."""
+    se, ll, k = 0.0, 0.0, 0
+    for r0 in range(0, xt.shape[0], batch):
+        eps = eps_batches[k]; k += 1
+        theta = mf_sample(mu, rho, eps)
+        out, _ = mlp_forward(theta, xt[r0:r0 + batch], dims)
+        w = softmax(mf_sampled_nkl(mu, rho, eps, theta), 0)
+        yp = ((out[..., 0] * y_std + y_mean) * w[:, None]).sum(0)
+        y = yt[r0:r0 + batch]
+        se += ((yp - y) ** 2).sum()
+        ll += (-0.5 * tau * (yp - y) ** 2 - 0.5 * np.log(2.0 * np.pi / tau)).sum()
+    return np.sqrt(se / xt.shape[0]), ll / xt.shape[0]
+
+
 # ------------------------------------------------------------------------------------ evaluate (a11, Q3, Q12)
 def evaluate(mu, rho, eps_batches, u, z, a, xt, yt, dims, batch, correction=True):
     """PSVI.evaluate (psvi_classes.py:1031-1108).  eps_batches[k] is the draw of test batch k.

@@ -389,3 +389,57 @@ def test_module_forward_matches_oracle(rows, H, S, L):
     theta = torch.cat([torch.cat([m._cached_weight.reshape(S, -1), m._cached_bias.reshape(S, -1)], 1) for m in net.vi_layers()], 1)
     ref, _ = po.mlp_forward(theta.double().cpu().numpy(), x.double().cpu().numpy(), dims)
     assert rel_l2(lg.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("cls_name", ["PSVILearnV_regressor", "PSVIAV_regressor"])
+def test_gaussian_regressors_match_reference(cls_name):
+    """The Gaussian-likelihood regressors (reference psvi_classes.py:1940-2335) on psvi_net_pass_gaussian: inner_elbo, psvi_elbo,
+    one nested_step with hypergradients on u, v, the learnable targets z (and alpha), the Adam steps, evaluate() (RMSE / mean
+    log-likelihood), then run_psvi end to end.  Goldens: `python oracle/make_goldens_r2.py regressor`."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.experiments_utils import BaseDataset
+    from psvi.inference import psvi_classes as pc
+    g = dict(np.load(os.path.join(GOLDEN, f"regressor_{cls_name}.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, M, B, tau = int(g["S"]), int(g["T"]), int(g["M"]), int(g["B"]), float(g["tau"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    T_ = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32))
+    tr, va, te = BaseDataset(T_(g["x"]), T_(g["y"])), BaseDataset(T_(g["xv"]), T_(g["yv"])), BaseDataset(T_(g["xt"]), T_(g["yt"]))
+    kw = dict(mc_samples=S, num_epochs=0, data_minibatch=B, D=dims[0], N=int(g["N"]), inner_it=T, trainer="nested",
+              architecture="regressor_net", n_hidden=dims[1], nc=1, train_dataset=tr, val_dataset=va, test_dataset=te,
+              y_mean=torch.tensor(float(g["y_mean"])), y_std=torch.tensor(float(g["y_std"])), tau=tau, num_pseudo=M,
+              init_args="subsample", lr0net=float(g["lr0net"]), lr0u=1e-3, lr0v=1e-2, lr0z=float(g["lr0z"]), init_sd=1e-2,
+              log_every=10, seed=0, quiet=True)
+    obj = getattr(pc, cls_name)(**kw)
+    obj.run_psvi(**kw)
+    assert obj.model.dims == dims and obj.u.shape == (M, dims[0]) and obj.z.shape == (M,) and obj.z.requires_grad
+    mu, rho = obj.model.flat()
+    mu.copy_(torch.as_tensor(g["mu0"])), rho.copy_(torch.as_tensor(g["rho0"]))
+    with torch.no_grad():
+        obj.u.copy_(torch.as_tensor(g["u0"])), obj.v.copy_(torch.as_tensor(g["v0"])), obj.z.copy_(torch.as_tensor(g["z0"]))
+        if obj.alpha is not None:
+            obj.alpha.fill_(float(g["alpha0"]))
+    obj.noise_source = pc.ExternalNoise(eps)
+    xb, yb = T_(g["xb"]).cuda(), T_(g["yb"]).cuda()
+    ie = float(obj.inner_elbo(model=obj.model))
+    assert abs(ie - g["ref64_inner_elbo"]) <= 2e-5 * abs(g["ref64_inner_elbo"])
+    oe = float(obj.psvi_elbo(xb, yb, model=obj.model))
+    assert abs(oe - g["ref64_psvi_elbo"]) <= 2e-5 * abs(g["ref64_psvi_elbo"])
+    loss = float(obj.nested_step(xb, yb))
+    assert obj.noise_source.pos == int(g["n_forwards_step"])
+    assert abs(loss - g["ref64_nested_loss"]) <= 2e-5 * abs(g["ref64_nested_loss"])
+    assert rel_l2(obj.u.grad.cpu().numpy(), g["ref64_gu"]) < 2e-3
+    assert rel_l2(obj.v.grad.cpu().numpy(), g["ref64_gv"]) < 2e-3
+    assert rel_l2(obj.z.grad.cpu().numpy(), g["ref64_gz"]) < 2e-3
+    if obj.alpha is not None:
+        np.testing.assert_allclose(obj.alpha.grad.cpu().numpy(), g["ref64_galpha"], rtol=2e-3)
+    vec = torch.nn.utils.parameters_to_vector(obj.model.parameters()).detach().cpu().numpy()
+    assert rel_l2(vec, g["ref64_params"]) < 1e-5
+    np.testing.assert_allclose(obj.z.detach().cpu().numpy(), g["ref64_z_after"], atol=2e-5)
+    np.testing.assert_allclose(obj.u.detach().cpu().numpy(), g["ref64_u_after"], atol=2e-5)
+    rmse, ll = obj.evaluate()
+    assert obj.noise_source.pos == int(g["n_forwards"])
+    np.testing.assert_allclose([float(rmse), float(ll)], g["ref32_eval"], rtol=1e-3)
+    kw.update(num_epochs=30, log_every=10, inner_it=5, lr0u=1e-2)
+    res = getattr(pc, cls_name)(**kw).run_psvi(**kw)
+    assert len(res["rmses"]) == 3 and np.isfinite(res["rmses"]).all() and np.isfinite(res["lls"]).all()

@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
+               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "regressor", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
 
 
 def rel_l2(a, b):
@@ -304,3 +304,33 @@ def test_meanfieldvi_class_trace_and_forgetting_scores():
     np.testing.assert_allclose(nlls, g["ref_nlls"], rtol=5e-5)
     assert np.mean(forgetting != g["ref_forgetting"]) <= 0.01      # (a row whose two top logits tie within fp32 noise may flip)
     assert np.mean(last_acc != g["ref_last_acc"]) <= 0.01
+
+
+@pytest.mark.parametrize("cls", ["PSVILearnV_regressor", "PSVIAV_regressor"])
+def test_gaussian_regressors_match_reference(cls):
+    """The Gaussian-likelihood regressors (reference psvi_classes.py:1940-2335; constructible only with `device_id` /
+    `scheduler_optim_net` supplied from outside, see oracle/make_goldens_r2.py: run_regressor): inner_elbo, psvi_elbo, one
+    nested_step with hypergradients on u, v, the learnable targets z (and alpha), the optimiser steps, and evaluate()."""
+    g = dict(np.load(os.path.join(GOLDEN, f"regressor_{cls}.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, T, N, tau, vmode, alpha = int(g["S"]), int(g["T"]), float(g["N"]), float(g["tau"]), int(g["vmode"]), float(g["alpha0"])
+    eps = [e.astype(np.float64) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    a = po.coreset_weights(g["v0"], N, vmode, alpha)
+    val = po.inner_grad_gauss(g["mu0"], g["rho0"], eps[0], g["u0"], g["z0"], a, dims, tau)[0]
+    assert abs(val - g["ref64_inner_elbo"]) <= 1e-9 * abs(val)
+    out = po.psvi_elbo_grad_gauss(g["mu0"], g["rho0"], eps[1], g["u0"], g["z0"], a, g["xb"], g["yb"], N, dims, tau)[0]
+    assert abs(out - g["ref64_psvi_elbo"]) <= 1e-9 * abs(out)
+    r = po.nested_step_regressor(g["mu0"], g["rho0"], np.stack(eps[2:2 + T]), eps[2 + T], g["u0"], g["z0"], g["v0"], g["xb"],
+                                 g["yb"], N, dims, float(g["lr0net"]), tau, vmode=vmode, alpha=alpha)
+    assert abs(r["loss"] - g["ref64_nested_loss"]) <= 1e-9 * abs(r["loss"])
+    assert rel_l2(po.mu_rho_to_phi(r["mu_T"], r["rho_T"], dims), g["ref64_params"]) < 1e-10
+    for k, ref in (("u_grad", "ref64_gu"), ("v_grad", "ref64_gv"), ("z_grad", "ref64_gz")):
+        assert rel_l2(r[k], g[ref]) < 1e-7, k
+    if vmode == 2:
+        np.testing.assert_allclose(r["alpha_grad"], g["ref64_galpha"][0], rtol=1e-7)
+    z1, _, _ = po.torch_adam_step(g["z0"], r["z_grad"], 0 * g["z0"], 0 * g["z0"], 1, float(g["lr0z"]))
+    np.testing.assert_allclose(z1, g["ref64_z_after"], rtol=0, atol=1e-9)
+    e32 = [e.astype(np.float32) for e in eps[int(g["n_forwards_step"]):]]
+    rmse, ll = po.evaluate_regressor(r["mu_T"].astype(np.float32), r["rho_T"].astype(np.float32), e32, g["xt"], g["yt"], dims,
+                                     int(g["B"]), np.float32(tau), np.float32(g["y_mean"]), np.float32(g["y_std"]))
+    np.testing.assert_allclose([rmse, ll], g["ref32_eval"], rtol=2e-5)
