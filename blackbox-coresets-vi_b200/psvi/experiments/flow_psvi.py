@@ -210,7 +210,9 @@ def main(argv=None):
     for fold in (method_args["data_folder"], method_args["results_folder"]):
         os.makedirs(fold, exist_ok=True)
     if method_args.get("architecture") == "regressor_net":
-        raise NotImplementedError("regression flows are outside the PSVI hot-path scope (SURVEY.md section 8f)")
+        raise NotImplementedError("the regression flow reads UCI benchmark files that need a download (no network here); the "
+                                  "regressor classes are built: psvi.inference.psvi_classes.PSVI_regressor / "
+                                  "PSVILearnV_regressor / PSVIAV_regressor with (train, val, test) BaseDatasets, y_mean, y_std, tau")
     return experiment_driver(method_args["datasets"], method_args["methods"], method_args)
 
 
