@@ -114,6 +114,35 @@ class FullCovFamily:
             self.toffs.append(t)
             o += 2 * n + c
             t += n
+        # the per-layer launches of a family map are independent: while the step is being captured into a CUDA graph the small
+        # layers go to side streams (parallel branches next to the one big layer); eagerly they stay in line (stream juggling
+        # from Python would cost more than the microsecond kernels it overlaps)
+        self._sides = [torch.cuda.Stream() for _ in self.ns] if torch.cuda.is_available() else []
+
+    def _per_layer(self, fn):
+        items = list(zip(self.offs, self.ns, self.toffs))
+        if len(items) < 2 or not self._sides or not torch.cuda.is_current_stream_capturing():
+            for it in items:
+                fn(*it)
+            return
+        cur = torch.cuda.current_stream()
+        big = max(range(len(items)), key=lambda i: self.ns[i])
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for i, it in enumerate(items):
+            if i == big:
+                continue
+            side = self._sides[i]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                fn(*it)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            joins.append(ev)
+        fn(*items[big])
+        for ev in joins:
+            cur.wait_event(ev)
 
     def fix_eps(self, eps):
         return eps
@@ -148,9 +177,8 @@ class FullCovFamily:
         phi, eps = self._f32c(phi), self._f32c(eps)
         pd = None if phidot is None else self._f32c(phidot).data_ptr()
         out = torch.empty(S, self.Pt, device=eps.device)
-        for o, n, t in zip(self.offs, self.ns, self.toffs):
-            _native.fc_sample(n, S, phi.data_ptr() + 4 * o, None if pd is None else pd + 4 * o, eps.data_ptr() + 4 * t, self.Pt,
-                              out.data_ptr() + 4 * t, self.Pt)
+        self._per_layer(lambda o, n, t: _native.fc_sample(n, S, phi.data_ptr() + 4 * o, None if pd is None else pd + 4 * o,
+                                                          eps.data_ptr() + 4 * t, self.Pt, out.data_ptr() + 4 * t, self.Pt))
         return out
 
     def sample(self, phi, eps):
@@ -174,18 +202,18 @@ class FullCovFamily:
         S = eps.shape[0]
         phi, eps, tbar = self._f32c(phi), self._f32c(eps), self._f32c(tbar)
         g = torch.empty_like(phi)
-        for o, n, t in zip(self.offs, self.ns, self.toffs):
-            _native.fc_reparam_grad(n, S, phi.data_ptr() + 4 * o, tbar.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t,
-                                    self.Pt, kl_coef, nkl_coef, g.data_ptr() + 4 * o)
+        self._per_layer(lambda o, n, t: _native.fc_reparam_grad(n, S, phi.data_ptr() + 4 * o, tbar.data_ptr() + 4 * t, self.Pt,
+                                                                eps.data_ptr() + 4 * t, self.Pt, kl_coef, nkl_coef,
+                                                                g.data_ptr() + 4 * o))
         return g
 
     def hvp(self, phi, phidot, eps, A_t, A_td):
         S = eps.shape[0]
         phi, phidot, eps, A_t, A_td = (self._f32c(x) for x in (phi, phidot, eps, A_t, A_td))
         h = torch.empty_like(phi)
-        for o, n, t in zip(self.offs, self.ns, self.toffs):
-            _native.fc_reparam_hvp(n, S, phi.data_ptr() + 4 * o, phidot.data_ptr() + 4 * o, A_t.data_ptr() + 4 * t,
-                                   A_td.data_ptr() + 4 * t, self.Pt, eps.data_ptr() + 4 * t, self.Pt, h.data_ptr() + 4 * o)
+        self._per_layer(lambda o, n, t: _native.fc_reparam_hvp(n, S, phi.data_ptr() + 4 * o, phidot.data_ptr() + 4 * o,
+                                                               A_t.data_ptr() + 4 * t, A_td.data_ptr() + 4 * t, self.Pt,
+                                                               eps.data_ptr() + 4 * t, self.Pt, h.data_ptr() + 4 * o))
         return h
 
 
