@@ -12,6 +12,7 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
                          `python oracle/make_goldens_r2.py trainers`
   regressor_*.npz        PSVILearnV_regressor / PSVIAV_regressor (psvi_classes.py:1940-2335; broken upstream, see run_regressor):
                          `python oracle/make_goldens_r2.py regressor`
+  regbase_mfvi.npz       run_mfvi_regressor / run_mfvi_subset_regressor (baselines.py:1066-1346); `... regbase`
   meanfieldvi_hm.npz     MeanFieldVI (inference/utils.py:221-450) with forgetting scores; `python oracle/make_goldens_r2.py meanfieldvi`
   learnz_fn_fb.npz       learn_z=True (soft pseudo-labels, KLDiv branch): inner_elbo, psvi_elbo, one nested_step with z.grad, and
                          evaluate(); made by `python oracle/make_goldens_r2.py learnz`
@@ -401,7 +402,57 @@ def run_regressor(cls_name, H=8, M=10, S=4, T=3, B=32, tau=0.5, init_sd=1e-2, lr
           "size", os.path.getsize(pth))
 
 
+def run_regression_baselines(name="regbase_mfvi"):
+    """run_mfvi_regressor (precision selected on the validation set among two values) and run_mfvi_subset_regressor
+    (baselines.py:1066-1346) on the synthetic regression benchmark; fp32, as shipped."""
+    from psvi.experiments.experiments_utils import BaseDataset, set_up_model
+    from psvi.inference.baselines import run_mfvi_regressor, run_mfvi_subset_regressor
+    x, y, xv, yv, xt, yt, ym, ys = regression_data()
+    T_ = torch.from_numpy
+    tr, va, te = BaseDataset(T_(x), T_(y)), BaseDataset(T_(xv), T_(yv)), BaseDataset(T_(xt), T_(yt))
+    S, H, B = 4, 8, 100
+    import random
+    random.seed(0), np.random.seed(0), torch.manual_seed(0)
+    net0 = set_up_model(architecture="regressor_net", D=x.shape[1], n_hidden=H, nc=1, mc_samples=S, init_sd=1e-2)
+    dims = model_dims(net0)
+    common = dict(mc_samples=S, data_minibatch=B, num_epochs=3, log_every=2, D=x.shape[1], lr0net=1e-2, seed=0,
+                  architecture="regressor_net", n_hidden=H, train_dataset=tr, val_dataset=va, test_dataset=te, nc=1,
+                  y_mean=torch.tensor(ym), y_std=torch.tensor(ys), init_sd=1e-2)
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    blob = dict(dims=np.array(dims), S=S, B=B, noise_seed=6767, x=x, y=y, xv=xv, yv=yv, xt=xt, yt=yt, y_mean=ym, y_std=ys)
+    import psvi.inference.baselines as rb
+    inits, real_setup = [], rb.set_up_model
+
+    def recording_setup(**kw):          # the initial (mu, rho) of every net the runs build, in order
+        net = real_setup(**kw)
+        inits.append(get_mu_rho(net))
+        return net
+    rb.set_up_model = recording_setup
+    try:
+        with NoiseFeeder(dims, S, 6767) as nf, _quiet():
+            r1 = run_mfvi_regressor(taus=[0.3, 0.9], model_selection=True, dnm="synthetic", **common)
+            blob["n_forwards_full"] = len(nf.history)
+            r2 = run_mfvi_subset_regressor(taus=[0.5], model_selection=False, num_pseudo=40, **common)
+            blob["n_forwards"] = len(nf.history)
+    finally:
+        torch.cuda.is_available = real
+        rb.set_up_model = real_setup
+    blob["mu0s"], blob["rho0s"] = np.stack([m for m, _ in inits]), np.stack([r for _, r in inits])
+    for tag, r in (("full", r1), ("subset", r2)):
+        for k in ("rmses", "lls", "elbos"):
+            blob[f"ref_{tag}_{k}"] = np.array(r[k])
+        blob[f"ref_{tag}_scale"] = r["scale"]
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **blob)
+    print(name, "forwards", blob["n_forwards_full"], blob["n_forwards"], "full", r1["rmses"], r1["lls"], r1["scale"], "subset",
+          r2["rmses"], r2["lls"], "size", os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "regbase":
+        run_regression_baselines()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "regressor":
         for c in ("PSVILearnV_regressor", "PSVIAV_regressor"):
             run_regressor(c)

@@ -443,3 +443,45 @@ def test_gaussian_regressors_match_reference(cls_name):
     kw.update(num_epochs=30, log_every=10, inner_it=5, lr0u=1e-2)
     res = getattr(pc, cls_name)(**kw).run_psvi(**kw)
     assert len(res["rmses"]) == 3 and np.isfinite(res["rmses"]).all() and np.isfinite(res["lls"]).all()
+
+
+def test_regression_baselines_match_reference():
+    """run_mfvi_regressor (precision selected on the validation set) and run_mfvi_subset_regressor (reference baselines.py:1066-
+    1346) with the injected noise stream: same seeds => the same initial nets as the reference (asserted), same ELBO / RMSE /
+    log-likelihood traces (fp32 reference; 1e-3)."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.experiments_utils import BaseDataset
+    from psvi.inference import baselines as bl
+    from psvi.inference.psvi_classes import ExternalNoise
+    g = dict(np.load(os.path.join(GOLDEN, "regbase_mfvi.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, B = int(g["S"]), int(g["B"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    T_ = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32))
+    tr, va, te = BaseDataset(T_(g["x"]), T_(g["y"])), BaseDataset(T_(g["xv"]), T_(g["yv"])), BaseDataset(T_(g["xt"]), T_(g["yt"]))
+    common = dict(mc_samples=S, data_minibatch=B, num_epochs=3, log_every=2, D=dims[0], lr0net=1e-2, seed=0,
+                  architecture="regressor_net", n_hidden=dims[1], train_dataset=tr, val_dataset=va, test_dataset=te, nc=1,
+                  y_mean=torch.tensor(float(g["y_mean"])), y_std=torch.tensor(float(g["y_std"])), init_sd=1e-2)
+    inits, real_setup = [], bl.set_up_model
+
+    def recording_setup(**kw):
+        net = real_setup(**kw)
+        inits.append(np.concatenate([np.concatenate([m.weight.detach().reshape(-1).numpy(), m.bias.detach().reshape(-1).numpy()])
+                                     for m in net.vi_layers()]))
+        return net
+    bl.set_up_model = recording_setup
+    try:
+        src = ExternalNoise(eps)
+        r1 = bl.run_mfvi_regressor(taus=[0.3, 0.9], model_selection=True, dnm="synthetic", noise_source=src, **common)
+        assert src.pos == int(g["n_forwards_full"])
+        r2 = bl.run_mfvi_subset_regressor(taus=[0.5], model_selection=False, num_pseudo=40, noise_source=src, **common)
+        assert src.pos == int(g["n_forwards"])
+    finally:
+        bl.set_up_model = real_setup
+    np.testing.assert_allclose(np.stack(inits), g["mu0s"], atol=1e-7)          # same seeds, same initial means as the reference
+    assert abs(r1["scale"] - float(g["ref_full_scale"])) < 1e-6 and r1["selected_tau"] == 0.3
+    for tag, r in (("full", r1), ("subset", r2)):
+        np.testing.assert_allclose(r["elbos"], g[f"ref_{tag}_elbos"], rtol=1e-4)
+        np.testing.assert_allclose(r["rmses"], g[f"ref_{tag}_rmses"], rtol=1e-3)
+        np.testing.assert_allclose(r["lls"], g[f"ref_{tag}_lls"], rtol=1e-3)
+    assert r2["csizes"] == [40]

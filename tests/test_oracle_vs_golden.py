@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "regressor", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
+               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "regressor", "regbase", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
 
 
 def rel_l2(a, b):
@@ -334,3 +334,55 @@ def test_gaussian_regressors_match_reference(cls):
     rmse, ll = po.evaluate_regressor(r["mu_T"].astype(np.float32), r["rho_T"].astype(np.float32), e32, g["xt"], g["yt"], dims,
                                      int(g["B"]), np.float32(tau), np.float32(g["y_mean"]), np.float32(g["y_std"]))
     np.testing.assert_allclose([rmse, ll], g["ref32_eval"], rtol=2e-5)
+
+
+def test_regression_baselines_match_reference():
+    """run_mfvi_regressor (precision picked on the validation set) and run_mfvi_subset_regressor (reference baselines.py:1066-1346,
+    `fit` :1283-1346): every step trains on the FIRST minibatch of the unshuffled loader, scaled by len(dataset) / batch (so the
+    subset run is not rescaled at all); predictions = mean over samples of the de-normalised outputs.  fp32 reference."""
+    import random
+    g = dict(np.load(os.path.join(GOLDEN, "regbase_mfvi.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S, B, dt = int(g["S"]), int(g["B"]), np.float32
+    eps = [e.astype(dt) for e in NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))]
+    ym, ys = dt(g["y_mean"]), dt(g["y_std"])
+    k = [0]
+
+    def fit(init, xtr, ytr, n_train, xp, yp, tau, epochs, log_every):
+        mu, rho = g["mu0s"][init].astype(dt), g["rho0s"][init].astype(dt)
+        m = np.zeros(2 * len(mu), dt); v = np.zeros(2 * len(mu), dt)
+        a = np.full(len(xtr), n_train / len(xtr), dt)
+        rm, ll, el = [], [], []
+        for e in range(epochs):
+            val, gmu, grho = po.inner_grad_gauss(mu, rho, eps[k[0]], xtr, ytr, a, dims, dt(tau)); k[0] += 1
+            phi, m, v = po.torch_adam_step(np.concatenate([mu, rho]), np.concatenate([gmu, grho]).astype(dt), m, v, e + 1, dt(1e-2))
+            mu, rho = phi[:len(mu)].astype(dt), phi[len(mu):].astype(dt)
+            el.append(-val)
+            if (e % log_every == 0) if log_every > 0 else (e == epochs - 1):
+                se = l = 0.0
+                for r0 in range(0, len(xp), B):
+                    out, _ = po.mlp_forward(po.mf_sample(mu, rho, eps[k[0]]), xp[r0:r0 + B], dims); k[0] += 1
+                    d = (out[..., 0] * ys + ym).mean(0) - yp[r0:r0 + B]
+                    se += (d * d).sum(); l += (-0.5 * tau * d * d - 0.5 * np.log(2 * np.pi / tau)).sum()
+                rm.append(np.sqrt(se / len(xp))); ll.append(l / len(xp))
+        return rm, ll, el
+    x, y, xv, yv, xt, yt = (g[n] for n in ("x", "y", "xv", "yv", "xt", "yt"))
+    epochs = 3 * max(1, int(len(x) / B))
+    best, best_ll = None, -np.inf
+    for i, tau in enumerate((0.3, 0.9)):
+        _, ll, _ = fit(i, x[:B], y[:B], len(x), xv, yv, tau, epochs, -1)
+        if ll[-1] > best_ll:
+            best, best_ll = tau, ll[-1]
+    assert abs(1.0 / np.sqrt(best) - float(g["ref_full_scale"])) < 1e-9
+    rm, ll, el = fit(2, x[:B], y[:B], len(x), xt, yt, best, epochs, 2)
+    assert k[0] == int(g["n_forwards_full"])
+    np.testing.assert_allclose(rm, g["ref_full_rmses"], rtol=2e-5)
+    np.testing.assert_allclose(ll, g["ref_full_lls"], rtol=2e-5)
+    np.testing.assert_allclose(el, g["ref_full_elbos"], rtol=5e-5)
+    random.seed(0)
+    idx = random.sample(range(len(x)), 40)
+    rm, ll, el = fit(3, x[idx], y[idx], 40, xt, yt, 0.5, epochs, 2)
+    assert k[0] == int(g["n_forwards"])
+    np.testing.assert_allclose(rm, g["ref_subset_rmses"], rtol=2e-5)
+    np.testing.assert_allclose(ll, g["ref_subset_lls"], rtol=2e-5)
+    np.testing.assert_allclose(el, g["ref_subset_elbos"], rtol=5e-5)
