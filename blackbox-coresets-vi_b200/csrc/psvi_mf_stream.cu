@@ -44,7 +44,8 @@ struct SP {
   float* xbar;           // [S][R][D]
   float* acbar;          // [S][R]
   float* logits_out;     // [S][R][C] (forward mode)
-  // likelihood of the per-sample pass: 0 = categorical (softmax over C logits, int labels), 1 = Gaussian with precision tau on
+  // likelihood of the per-sample pass: 0 = categorical (softmax over C logits, int labels), 2 = Bernoulli on ONE logit (labels
+  // 0. / 1. as float bits; sparse-BBVI, reference psvi/inference/utils.py:85-141), 1 = Gaussian with precision tau on
   // ONE output (the regressors, reference psvi_classes.py:1986,2034-2057): labels are float bits in y, nll = tau/2 (o - y)^2 +
   // 1/2 log(2 pi / tau); ybar [S][R] (nullable) receives d(sum_r cw nll)/dy -- or its directional derivative in the dual pass
   int like;
@@ -162,6 +163,15 @@ struct Worker {
     const int C = p.dims[p.L], ld = mt.lda[p.L];
     const float* o = F(ly.act[p.L]);
     float* ao = F(ly.adj[p.L]);
+    if (p.like == 2) {       // -Bernoulli(logits = o).log_prob(y) = softplus(o) - y o
+      for (int rr = tid; rr < nr; rr += NT) {
+        const float ov = o[rr * ld], yv = __int_as_float(I(ly.lab)[rr]);
+        F(ly.nll)[rr] = softplus_f(ov) - yv * ov;
+        if (grad) ao[rr * ld] = F(ly.cw)[rr] * (sigmoid_f(ov) - yv);
+      }
+      __syncthreads();
+      return;
+    }
     if (p.like == 1) {
       const float hl = 0.5f * logf(6.283185307179586f / p.tau);
       for (int rr = tid; rr < nr; rr += NT) {
@@ -240,6 +250,18 @@ struct Worker {
     const float* od = F(ly.actd[p.L]);
     float* ao = F(ly.adj[p.L]);
     float* aod = F(ly.adjd[p.L]);
+    if (p.like == 2) {
+      for (int rr = tid; rr < nr; rr += NT) {
+        const float ov = o[rr * ld], yv = __int_as_float(I(ly.lab)[rr]), d = od[rr * ld], w = F(ly.cw)[rr];
+        const float sg = sigmoid_f(ov);
+        F(ly.nll)[rr] = softplus_f(ov) - yv * ov;
+        aod[rr * ld] = w * (sg - yv);
+        ao[rr * ld] = w * sg * (1.f - sg) * d;
+        if (ac_out) ac_out[rr] = (sg - yv) * d;
+      }
+      __syncthreads();
+      return;
+    }
     if (p.like == 1) {
       const float hl = 0.5f * logf(6.283185307179586f / p.tau);
       for (int rr = tid; rr < nr; rr += NT) {
@@ -722,6 +744,14 @@ int psvi_net_pass_gaussian(const psvi_mf_model* model, const float* theta, const
   PSVI_REQUIRE(tau > 0.f, PSVI_ERR_INVALID, "tau must be positive");
   return net_pass_impl(model, theta, thetad, x, reinterpret_cast<const int32_t*>(y), cw, R, nll, tbar, tdbar, xbar, acbar,
                        outputs, 1, tau, ybar, stream_);
+}
+
+int psvi_net_pass_bernoulli(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const float* y,
+                            const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                            float* outputs, void* stream_) {
+  PSVI_REQUIRE(model && model->dims[model->n_layers] == 1, PSVI_ERR_UNSUPPORTED, "the Bernoulli likelihood takes ONE logit");
+  return net_pass_impl(model, theta, thetad, x, reinterpret_cast<const int32_t*>(y), cw, R, nll, tbar, tdbar, xbar, acbar,
+                       outputs, 2, 0.f, nullptr, stream_);
 }
 
 static int net_pass_impl(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const int32_t* y,

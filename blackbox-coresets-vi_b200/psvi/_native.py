@@ -109,6 +109,8 @@ _SIGS = {
     "psvi_net_pass_gaussian": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    "psvi_net_pass_bernoulli": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_net_predict": (C.c_int, [C.POINTER(MfModel), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "psvi_fc_matvec": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
@@ -420,6 +422,13 @@ def net_pass_gaussian(model, theta, thetad, x, y, cw, tau, nll=None, tbar=None, 
     _count(1)
     _check(lib().psvi_net_pass_gaussian(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y), _p(cw), x.shape[0], float(tau),
                                         _p(nll), _p(tbar), _p(tdbar), _p(xbar), _p(acbar), _p(ybar), _p(outputs), _stream()))
+
+
+def net_pass_bernoulli(model, theta, thetad, x, y, cw, nll=None, tbar=None, tdbar=None, xbar=None, acbar=None, outputs=None):
+    """Per-sample pass with the Bernoulli likelihood on one logit (y: float labels 0. / 1. [R])."""
+    _count(1)
+    _check(lib().psvi_net_pass_bernoulli(C.byref(model), _p(theta), _p(thetad), _p(x), _p(y), _p(cw), x.shape[0], _p(nll), _p(tbar),
+                                         _p(tdbar), _p(xbar), _p(acbar), _p(outputs), _stream()))
 
 
 def net_predict(model, theta, log_weights, mode, xt, yt, out):

@@ -107,8 +107,7 @@ def _method(cls):
     return lambda *args, **kwargs: cls(*args, **kwargs).run_psvi(*args, **kwargs)
 
 
-def _sparsebbvi(*a, **k):
-    raise NotImplementedError("sparsebbvi (reference psvi/inference/sparsebbvi.py) is outside the hot-path scope")
+from psvi.inference.sparsebbvi import run_sparsevi_with_bb_elbo as _sparsebbvi  # noqa: E402
 
 
 # Inference methods (reference :306-354): every key resolves

@@ -206,6 +206,12 @@ int psvi_net_pass(const psvi_mf_model* model, const float* theta, const float* t
 int psvi_net_pass_gaussian(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const float* y,
                            const float* cw, int32_t R, float tau, float* nll, float* tbar, float* tdbar, float* xbar,
                            float* acbar, float* ybar, float* outputs, void* stream);
+
+/* ... and with a BERNOULLI likelihood on one logit (sparse-BBVI: reference psvi/inference/utils.py:85-141, `dist.Bernoulli(logits =
+ * net(x).squeeze(-1)).log_prob(y)`):  nll[s][r] = softplus(o_s(x_r)) - y_r o_s(x_r),  y [R] float labels in {0, 1}. */
+int psvi_net_pass_bernoulli(const psvi_mf_model* model, const float* theta, const float* thetad, const float* x, const float* y,
+                            const float* cw, int32_t R, float* nll, float* tbar, float* tdbar, float* xbar, float* acbar,
+                            float* outputs, void* stream);
 /* psvi_net_predict: predictive metrics of rows xt with sampled weights theta [S][P]; mode 0 needs log_weights [S]
  *   (softmax-ed inside); out [8] as psvi_mf_evaluate; workspace of psvi_mf_stream_workspace_bytes(model, n_rows). */
 int psvi_net_predict(const psvi_mf_model* model, const float* theta, const float* log_weights, int32_t mode,

@@ -12,6 +12,7 @@ python oracle/make_goldens_r2.py).  Closes the parity holes of the first set (or
                          `python oracle/make_goldens_r2.py trainers`
   regressor_*.npz        PSVILearnV_regressor / PSVIAV_regressor (psvi_classes.py:1940-2335; broken upstream, see run_regressor):
                          `python oracle/make_goldens_r2.py regressor`
+  sparsebbvi_hm.npz      run_sparsevi_with_bb_elbo (inference/sparsebbvi.py:28-198); `... sparsebbvi`
   regbase_mfvi.npz       run_mfvi_regressor / run_mfvi_subset_regressor (baselines.py:1066-1346); `... regbase`
   meanfieldvi_hm.npz     MeanFieldVI (inference/utils.py:221-450) with forgetting scores; `python oracle/make_goldens_r2.py meanfieldvi`
   learnz_fn_fb.npz       learn_z=True (soft pseudo-labels, KLDiv branch): inner_elbo, psvi_elbo, one nested_step with z.grad, and
@@ -449,7 +450,36 @@ def run_regression_baselines(name="regbase_mfvi"):
           r2["rmses"], r2["lls"], "size", os.path.getsize(pth))
 
 
+def run_sparsebbvi(name="sparsebbvi_hm"):
+    """run_sparsevi_with_bb_elbo (psvi/inference/sparsebbvi.py:28-198) on halfmoon with a one-hidden-layer net, fp32 as shipped."""
+    from psvi.inference.sparsebbvi import run_sparsevi_with_bb_elbo
+    from psvi.models.neural_net import make_fcnet, VILinear
+    import torch.nn as nn
+    x, y, xt, yt, N, D, tr, te, nc = get_data("halfmoon")
+    S, H = 5, 6
+    torch.manual_seed(4)
+    net0 = make_fcnet(D, H, 1, n_layers=1, linear_class=VILinear, nonl_class=nn.ReLU, mc_samples=S)
+    mu0, rho0 = get_mu_rho(net0)
+    dims = model_dims(net0)
+    kw = dict(n_layers=1, logistic_regression=False, n_hidden=H, log_every=3, lr0=1e-2, register_elbos=False, seed=4, num_epochs=7,
+              inner_it=3, outer_it=2, x=x, y=y.float(), xt=xt, yt=yt.float(), mc_samples=S, data_minibatch=32,
+              scatterplot_coreset=False)
+    with NoiseFeeder(dims, S, 8181) as nf, _quiet():
+        res = run_sparsevi_with_bb_elbo(**kw)
+        nfw = len(nf.history)
+    blob = dict(dims=np.array(dims), S=S, N=N, noise_seed=8181, n_forwards=nfw, mu0=mu0, rho0=rho0, seed=4, num_epochs=7, inner_it=3,
+                outer_it=2, data_minibatch=32, log_every=3, lr0=1e-2, x=x.numpy(), y=y.numpy().astype(np.float32), xt=xt.numpy(),
+                yt=yt.numpy().astype(np.float32), ref_accs=np.array(res["accs"]), ref_nlls=np.array(res["nlls"]),
+                ref_csizes=np.array(res["csizes"]))
+    pth = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(pth, **blob)
+    print(name, "forwards", nfw, res["accs"], res["nlls"], res["csizes"], "size", os.path.getsize(pth))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sparsebbvi":
+        run_sparsebbvi()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "regbase":
         run_regression_baselines()
         return

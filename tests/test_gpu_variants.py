@@ -485,3 +485,31 @@ def test_regression_baselines_match_reference():
         np.testing.assert_allclose(r["rmses"], g[f"ref_{tag}_rmses"], rtol=1e-3)
         np.testing.assert_allclose(r["lls"], g[f"ref_{tag}_lls"], rtol=1e-3)
     assert r2["csizes"] == [40]
+
+
+def test_sparsebbvi_matches_reference():
+    """run_sparsevi_with_bb_elbo (reference psvi/inference/sparsebbvi.py:28-198) on psvi_net_pass_bernoulli with the injected noise
+    stream: coreset sizes, accuracy and NLL trace of the fp32 reference; and through the flow's method table."""
+    from oracle.ref_import import NoiseFeeder
+    from psvi.experiments.flow_psvi import inf_dict
+    from psvi.inference.psvi_classes import ExternalNoise
+    from psvi.inference.sparsebbvi import run_sparsevi_with_bb_elbo
+    g = dict(np.load(os.path.join(GOLDEN, "sparsebbvi_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    S = int(g["S"])
+    eps = NoiseFeeder.stream(dims, S, int(g["noise_seed"]), int(g["n_forwards"]))
+    src = ExternalNoise(eps)
+    kw = dict(n_layers=1, logistic_regression=False, n_hidden=dims[1], log_every=int(g["log_every"]), lr0=float(g["lr0"]),
+              register_elbos=True, seed=int(g["seed"]), num_epochs=int(g["num_epochs"]), inner_it=int(g["inner_it"]),
+              outer_it=int(g["outer_it"]), x=torch.as_tensor(g["x"]), y=torch.as_tensor(g["y"]), xt=torch.as_tensor(g["xt"]),
+              yt=torch.as_tensor(g["yt"]), mc_samples=S, data_minibatch=int(g["data_minibatch"]), scatterplot_coreset=False)
+    res = run_sparsevi_with_bb_elbo(noise_source=src, _init=np.concatenate([g["mu0"], g["rho0"]]), **kw)
+    assert src.pos == int(g["n_forwards"])
+    assert res["csizes"] == [int(c) for c in g["ref_csizes"]]
+    np.testing.assert_allclose(res["accs"], g["ref_accs"], atol=5.1e-3)
+    np.testing.assert_allclose(res["nlls"], g["ref_nlls"], rtol=5e-4)
+    assert len(res["core_idcs"]) == len(set(res["core_idcs"])) and float(res["w"].min()) >= 0.0
+    assert [t for t, _ in res["elbos"]][:2] == [1, 0]
+    assert inf_dict["sparsebbvi"] is run_sparsevi_with_bb_elbo
+    r2 = run_sparsevi_with_bb_elbo(**{**kw, "logistic_regression": True, "register_elbos": False})      # Philox noise, logistic model
+    assert np.isfinite(r2["nlls"]).all() and r2["csizes"][0] == 0

@@ -15,7 +15,7 @@ from oracle.ref_import import NoiseFeeder
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "regressor", "regbase", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
+               if not os.path.basename(p).startswith(("mfvi", "meanfieldvi", "regressor", "regbase", "sparsebbvi", "fn2", "hyper", "lenet", "ablated", "noiw", "grid", "variant", "fixedpoint", "joint", "alternating", "learnz")))
 
 
 def rel_l2(a, b):
@@ -386,3 +386,19 @@ def test_regression_baselines_match_reference():
     np.testing.assert_allclose(rm, g["ref_subset_rmses"], rtol=2e-5)
     np.testing.assert_allclose(ll, g["ref_subset_lls"], rtol=2e-5)
     np.testing.assert_allclose(el, g["ref_subset_elbos"], rtol=5e-5)
+
+
+def test_sparsebbvi_matches_reference():
+    """Sparse-BBVI coreset construction (reference psvi/inference/sparsebbvi.py:28-198 + utils.py:85-141) through the numpy
+    restatement oracle/sparsebbvi_oracle.py (Bernoulli likelihood; accumulating inner gradients, the S-fold data term of `elbo`,
+    the first-index selection): accuracy / NLL trace and coreset sizes of the fp32 reference."""
+    from oracle import sparsebbvi_oracle as so
+    g = dict(np.load(os.path.join(GOLDEN, "sparsebbvi_hm.npz")))
+    dims = [int(d) for d in g["dims"]]
+    eps = iter([e.astype(np.float32) for e in NoiseFeeder.stream(dims, int(g["S"]), int(g["noise_seed"]), int(g["n_forwards"]))])
+    r = so.run(g["mu0"], g["rho0"], eps, g["x"], g["y"], g["xt"], g["yt"], dims, int(g["num_epochs"]), int(g["inner_it"]),
+               int(g["outer_it"]), int(g["data_minibatch"]), int(g["log_every"]), float(g["lr0"]), int(g["seed"]))
+    assert next(eps, None) is None                       # every forward of the reference run was consumed
+    assert r["csizes"] == [int(c) for c in g["ref_csizes"]]
+    np.testing.assert_allclose(r["accs"], g["ref_accs"], atol=1e-6)
+    np.testing.assert_allclose(r["nlls"], g["ref_nlls"], rtol=2e-5)
