@@ -1164,10 +1164,12 @@ class PSVIAV(PSVILearnV):
 def _no_hyper_for_fixed_u(self, *args, **kwargs):
     # reference :1660-1740 / :1790-1883: the fixed-u variants solve the linear system with an ADAM fixed-point map
     # (hypergrad.DifferentiableAdam(step_size=linsys_lr), K = 20) whose Jacobian products are not Hessian-vector products of
-    # the inner objective; that solver is not built, and substituting the gradient-descent map would silently change the
-    # hypergradient
-    raise NotImplementedError(f"--trainer hyper is not built for {type(self).__name__} (Adam fixed-point map of the "
-                              "reference, psvi_classes.py:1660-1740); use --trainer nested")
+    # the inner objective.  Upstream that call cannot run: the map is handed the weights WITHOUT the Adam moment tensors it
+    # unpacks as params[n:2n], params[2n:] (diff_optimizers.py:144-146), so `hyper_step` dies with an IndexError in
+    # robust_higher/patch.py:117 (checked against the unmodified reference).  There is no behaviour to mirror; substituting the
+    # gradient-descent map would invent one.
+    raise NotImplementedError(f"--trainer hyper is not available for {type(self).__name__}: the reference's own hyper_step for "
+                              "the fixed-u variants (psvi_classes.py:1660-1740) raises an IndexError; use --trainer nested")
 
 
 class PSVIFixedU(PSVILearnV):
