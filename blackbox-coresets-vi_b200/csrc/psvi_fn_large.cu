@@ -84,6 +84,70 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a 2-cluster work on ONE 256 x 256 tile; each loads 128 rows of A and 128
+//      rows of B (half the operand bytes per output of the 128 x 128 single-CTA tile), the even CTA issues the MMAs for both
+//      (M = 256: 128 accumulator lanes in each CTA's tensor memory, N = 256 columns), commits are multicast to both CTAs.
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (CG == 1) {
+    umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (CG == 1) {
+    umma_bf16(tmem_d, adesc, bdesc, idesc, acc);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if (CG == 1) {
+    umma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t o;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(addr), "r"(rank));
+  return o;
+}
+// TMA load into MY shared memory whose bytes are counted on the barrier at shared::cluster address `bar_cl` (the pair leader's)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cl, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cl), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cl) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cl) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // x = hi + lo with hi, lo representable in TF32 (10 explicit mantissa bits), |x - hi - lo| <= 2^-22 |x|
 __host__ __device__ __forceinline__ float tf32_rna(float x) {
 #ifdef __CUDA_ARCH__
@@ -105,7 +169,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16(x - __bfloat162float(hi));
 }
 
-template <int X3>
+template <int X3, int CG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bl,
@@ -126,30 +190,47 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < PR::GST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {   // the same warp of both CTAs of the pair: 2 x 256 accumulator columns in each CTA's tensor memory
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads(); else cluster_sync_all();   // pair: the peer's barriers and tensor memory exist before use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int per_b = p.m_tiles * p.n_tiles, n_total = p.batch * per_b;
+  // pair: a work item is a 256 x 256 tile; CTA `crank` of the pair owns its rows [128 crank, +128) of A (its accumulator lanes)
+  // and loads rows [128 crank, +128) of the tile's B operand (accumulator columns [128 crank, +128) of BOTH CTAs)
+  const int crank = CG == 2 ? (int)cluster_rank() : 0;
+  const int nt_w = p.n_tiles / CG;
+  const int per_b = (p.m_tiles / CG) * nt_w, n_total = p.batch * per_b;
+  const int w0 = blockIdx.x / CG, wstride = gridDim.x / CG;
+  constexpr int TN = GN * CG;   // accumulator columns of one work item
 
   if (warp == 0) {
     int st = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < n_total; t += gridDim.x) {
-      const int b = t / per_b, rem = t - b * per_b, mt = rem / p.n_tiles, nt = rem - mt * p.n_tiles;
+    for (int t = w0; t < n_total; t += wstride) {
+      const int b = t / per_b, rem = t - b * per_b, mt = (rem / nt_w) * CG + crank, nt = (rem - (rem / nt_w) * nt_w) * CG + crank;
       const int arow = b * p.a_brows + mt * GM, brow = b * p.b_brows + nt * GN;
       for (int k = 0; k < p.kc; ++k) {
         mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
           uint8_t* dst = ring + st * STAGE;
-          mbar_expect_tx(&full[st], STAGE);
+          // pair: both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
+          if (crank == 0) mbar_expect_tx(&full[st], CG * STAGE);
+          const uint32_t fbar = CG == 2 ? mapa_u32(smem_u32(&full[st]), 0) : 0u;
+          auto tma_load_2d = [&](const CUtensorMap* map, uint64_t* bar, void* d, int c0, int c1) {
+            if (CG == 1) psvi_tc::tma_load_2d(map, bar, d, c0, c1);
+            else tma_load_2d_pair(map, fbar, d, c0, c1);
+          };
           if (X3 == 2 && (p.a_mn || p.b_mn)) {
             const int ak = b * p.a_brows + k * PR::GK, bk = b * p.b_brows + k * PR::GK;
             if (p.a_mn) {
@@ -186,17 +267,18 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++st == PR::GST) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // instruction descriptor: D = f32, A = B = bf16 (format 1) or tf32 (format 2), both K-major, N = 128, M = 128
+  } else if (warp == 1 && crank == 0) {
+    // instruction descriptor: D = f32, A = B = bf16 (format 1) or tf32 (format 2), both K-major, N = 128, M = 128 (pair: 256, 256)
     const uint32_t fmt = X3 == 1 ? 2u : 1u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+    const uint32_t idesc =
+        (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((GN * CG) >> 3) << 17) | ((uint32_t)((GM * CG) >> 4) << 24);
     int st = 0, it = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < n_total; t += gridDim.x, ++it) {
+    for (int t = w0; t < n_total; t += wstride, ++it) {
       const int buf = it & 1;
       mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * GN;
+      const uint32_t tmem_d = tmem_base + buf * TN;
       for (int k = 0; k < p.kc; ++k) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
@@ -207,9 +289,9 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {   // K = 8 fp32 = 32 bytes per step; small terms first
-              umma_tf32(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
-              umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
-              umma_tf32(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
+              umma_tf32_cg<CG>(tmem_d, make_desc_sw128(al + j * 32), make_desc_sw128(bh + j * 32), idesc, j ? 1u : acc0);
+              umma_tf32_cg<CG>(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bl + j * 32), idesc, 1u);
+              umma_tf32_cg<CG>(tmem_d, make_desc_sw128(ah + j * 32), make_desc_sw128(bh + j * 32), idesc, 1u);
             }
           } else if (X3 == 2) {
             const uint32_t ah = s0, al = s0 + G_TILE_BYTES, bh = s0 + 2 * G_TILE_BYTES, bl = s0 + 3 * G_TILE_BYTES;
@@ -220,18 +302,18 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t dal = p.a_mn ? make_desc_mn(al + j * 2048) : make_desc_sw128(al + j * 32);
               const uint64_t dbh = p.b_mn ? make_desc_mn(bh + j * 2048) : make_desc_sw128(bh + j * 32);
               const uint64_t dbl = p.b_mn ? make_desc_mn(bl + j * 2048) : make_desc_sw128(bl + j * 32);
-              umma_bf16(tmem_d, dal, dbh, id2, j ? 1u : acc0);     // lo.hi + hi.lo + hi.hi at the bf16 rate
-              umma_bf16(tmem_d, dah, dbl, id2, 1u);
-              umma_bf16(tmem_d, dah, dbh, id2, 1u);
+              umma_bf16_cg<CG>(tmem_d, dal, dbh, id2, j ? 1u : acc0);     // lo.hi + hi.lo + hi.hi at the bf16 rate
+              umma_bf16_cg<CG>(tmem_d, dah, dbl, id2, 1u);
+              umma_bf16_cg<CG>(tmem_d, dah, dbh, id2, 1u);
             }
           } else {
             const uint32_t a0 = s0, b0 = s0 + G_TILE_BYTES;
 #pragma unroll
             for (int j = 0; j < 4; ++j)     // K = 16 bf16 = 32 bytes per step
-              umma_bf16(tmem_d, make_desc_sw128(a0 + j * 32), make_desc_sw128(b0 + j * 32), idesc, j ? 1u : acc0);
+              umma_bf16_cg<CG>(tmem_d, make_desc_sw128(a0 + j * 32), make_desc_sw128(b0 + j * 32), idesc, j ? 1u : acc0);
           }
-          umma_commit(&empty[st]);
-          if (k == p.kc - 1) umma_commit(&tfull[buf]);
+          umma_commit_cg<CG>(&empty[st]);
+          if (k == p.kc - 1) umma_commit_cg<CG>(&tfull[buf]);
         }
         __syncwarp();
         if (++st == PR::GST) { st = 0; ph ^= 1; }
@@ -241,18 +323,19 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3, part = (warp - 4) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int it = 0;
-    for (int t = blockIdx.x; t < n_total; t += gridDim.x, ++it) {
-      const int b = t / per_b, rem = t - b * per_b, mt = rem / p.n_tiles, nt = rem - mt * p.n_tiles;
+    const uint32_t tempty_cl = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;   // the leader's accumulator-free barriers
+    for (int t = w0; t < n_total; t += wstride, ++it) {
+      const int b = t / per_b, rem = t - b * per_b, mt = (rem / nt_w) * CG + crank, ntw = rem - (rem / nt_w) * nt_w;
       const int buf = it & 1;
       const int m = mt * GM + q * 32 + lane;
       const bool vm = m < p.M_valid;
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < 2; ++g) {
-        const int n0 = nt * GN + part * 64 + g * 32;
+      for (int g = 0; g < 2 * CG; ++g) {
+        const int n0 = ntw * TN + part * (TN / 2) + g * 32;
         float v[32];
-        tmem_ld32(lane_addr + buf * GN + part * 64 + g * 32, v);
+        tmem_ld32(lane_addr + buf * TN + part * (TN / 2) + g * 32, v);
         if (n0 < (p.n_pad > p.N_valid ? p.n_pad : p.N_valid)) {
           if (p.bias && p.bias_row) {
             const float br = vm ? __ldg(p.bias + (long long)b * p.bias_bs + m) : 0.f;
@@ -313,11 +396,33 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j)
               if (n0 + j >= p.N_valid) v[j] = 0.f;
           }
-          if (p.of && vm) {
-            float* op = p.of + (long long)b * p.of_bs + (long long)m * p.of_ld + n0;
+          if (p.of) {
+            // fp32 output: this warp's [32 rows x 32 columns] piece is transposed through shared memory (element (r, c) at
+            // word r * 32 + (c ^ r): conflict-free both ways) so that one store instruction writes 128 contiguous bytes of
+            // ONE output row -- the row-per-thread form wrote 4 bytes of 32 different rows per instruction and left the
+            // epilogue warps waiting on the store queue for half of the kernel (ncu: 47 % of the samples at this line)
+            float* sh = reinterpret_cast<float*>(stg + (warp - 4) * STG_WARP_BYTES);
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N_valid) op[j] = v[j];
+            for (int j = 0; j < 32; ++j) sh[lane * 32 + (j ^ lane)] = v[j];
+            __syncwarp();
+            const int mrow0 = mt * GM + q * 32;
+            float* ob_ = p.of + (long long)b * p.of_bs + n0;
+            if (p.N_valid <= 16) {   // 64-byte rows (of_ld = 16 keeps them contiguous): two rows per instruction
+              const int c = lane & 15;
+#pragma unroll 4
+              for (int r = 0; r < 32; r += 2) {
+                const int rr = r + (lane >> 4), mm = mrow0 + rr;
+                if (mm < p.M_valid && n0 + c < p.N_valid) ob_[(long long)mm * p.of_ld + c] = sh[rr * 32 + (c ^ rr)];
+              }
+            } else {
+              const bool vc = n0 + lane < p.N_valid;
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                const int mm = mrow0 + r;
+                if (mm < p.M_valid && vc) ob_[(long long)mm * p.of_ld + lane] = sh[r * 32 + (lane ^ r)];
+              }
+            }
           }
           if (p.ob && m < p.ob_rows) {
             const long long off = (long long)b * p.ob_bs + (long long)m * p.ob_ld + n0;
@@ -426,15 +531,19 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tempty[buf]);
+        else mbar_arrive_cluster(tempty_cl + buf * 8);
+      }
     }
     if (X3 == 2 && p.ob_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 1) __syncthreads(); else cluster_sync_all();   // pair: no CTA leaves while its peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -1014,19 +1123,44 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   const int total = p.batch * p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
+  // fp32 outputs are transposed through 8 x 4 KB of staging behind the barriers (the same area the TMA-stored epilogue uses)
+  if (p.of) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   mo = ma;
   mol = ma;
   p.ob_tma = 0;
-  if (X3 == 2 && p.ob && p.ob_lo && p.ob_rows % GM == 0 && p.ob_bs == (long long)p.ob_rows * p.ob_ld && !getenv("PSVI_FNL_NO_TMASTORE")) {
+  if (X3 == 2 && !p.of && p.ob && p.ob_lo && p.ob_rows % GM == 0 && p.ob_bs == (long long)p.ob_rows * p.ob_ld && !getenv("PSVI_FNL_NO_TMASTORE")) {
     const uint64_t ncols = (uint64_t)(p.n_pad > p.N_valid ? p.n_pad : p.N_valid);
     if ((rc = make_map_out_bf16(&mo, p.ob, ncols, (uint64_t)p.batch * p.ob_rows, (uint64_t)p.ob_ld))) return rc;
     if ((rc = make_map_out_bf16(&mol, p.ob_lo, ncols, (uint64_t)p.batch * p.ob_rows, (uint64_t)p.ob_ld))) return rc;
     p.ob_tma = 1;
     smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   }
-  // function attributes are per device: set on every call (cheap), not cached per process
-  PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tn_gemm_kernel<X3><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, mo, mol, p);
+  // CTA pairs (cta_group::2, 256 x 256 tiles: half the operand traffic per output) whenever the tile grid is even both ways
+  static const int cg2_mode = getenv("PSVI_FNL_CG2") ? atoi(getenv("PSVI_FNL_CG2")) : 1;
+  const bool pair = X3 != 0 && cg2_mode && p.m_tiles % 2 == 0 && p.n_tiles % 2 == 0 && sms >= 2 &&
+                    (cg2_mode == 2 || p.kc * PR::GK >= 256);
+  if (pair) {
+    const int items = total / 4;
+    const int grid2 = 2 * (items < sms / 2 ? items : sms / 2);
+    // function attributes are per device: set on every call (cheap), not cached per process
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid2);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PSVI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tn_gemm_kernel<X3, 2>, ma, mal, mb, mbl, mo, mol, p));
+    return PSVI_OK;
+  }
+  PSVI_CUDA_CHECK(cudaFuncSetAttribute(tn_gemm_kernel<X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tn_gemm_kernel<X3, 1><<<grid, G_THREADS, smem, st>>>(ma, mal, mb, mbl, mo, mol, p);
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }
