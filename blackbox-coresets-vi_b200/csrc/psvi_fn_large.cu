@@ -47,6 +47,11 @@ struct GemmP {
   int bias_row, relu;
   const void* mask; long long mask_bs; int mask_ld;             // * (mask[b][m][n] > 0)   (bf16, or the fp32 hi part)
   int mask_t;                                   // the mask array is [b][n][m]: read it transposed
+  // ReLU mask as BITS: word [b][row][hidden / 32], bit = hidden % 32.  mbits_out: written by the role-swapped forward product
+  // (accumulator lanes = hidden units, columns = rows: one warp ballot per row); mbits: read by the products whose epilogue
+  // multiplies by (h > 0) (accumulator lanes = rows, columns = hidden units: ONE 32-bit load per 32-column chunk instead of
+  // 64 / 128 bytes of h per thread).  mbits_ld = words per row, mbits_bs = words per batch
+  const uint32_t* mbits; uint32_t* mbits_out; long long mbits_bs; int mbits_ld;
   int n_pad;                                    // > N_valid: columns N_valid .. n_pad - 1 are processed too and written as zeros
   float* of; long long of_bs; int of_ld;                       // fp32 out [b][m][n], m < M_valid, n < N_valid
   void *ob, *ob_lo; long long ob_bs; int ob_ld; int ob_rows;    // operand out [b][m][n], m < ob_rows (zeros for m >= M_valid)
@@ -142,7 +147,9 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cl) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cl) : "memory");
+  // relaxed: the arrive only says "my tcgen05.ld of this accumulator have completed" (tcgen05.wait::ld ran before it); a
+  // release at cluster scope would also wait for the warp's outstanding GLOBAL stores (ncu: 12 % of the samples in membar)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cl) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -335,22 +342,34 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int g = 0; g < 2 * CG; ++g) {
         const int n0 = ntw * TN + part * (TN / 2) + g * 32;
         float v[32];
+        const bool chunk_on = n0 < (p.n_pad > p.N_valid ? p.n_pad : p.N_valid);
+        // loads that do not depend on the accumulator go out before the TMEM load: the bias (one value per lane, broadcast by
+        // shuffles below) and the ReLU-mask word of this (row, 32 hidden units) chunk
+        float bias_v = 0.f;
+        uint32_t mword = 0xFFFFFFFFu;
+        if (chunk_on) {
+          if (p.bias && p.bias_row) bias_v = vm ? __ldg(p.bias + (long long)b * p.bias_bs + m) : 0.f;
+          else if (p.bias) bias_v = (n0 + lane < p.N_valid) ? __ldg(p.bias + (long long)b * p.bias_bs + n0 + lane) : 0.f;
+          if (p.mbits && vm) mword = __ldg(p.mbits + (long long)b * p.mbits_bs + (long long)m * p.mbits_ld + (n0 >> 5));
+        }
         tmem_ld32(lane_addr + buf * TN + part * (TN / 2) + g * 32, v);
-        if (n0 < (p.n_pad > p.N_valid ? p.n_pad : p.N_valid)) {
+        if (chunk_on) {
           if (p.bias && p.bias_row) {
-            const float br = vm ? __ldg(p.bias + (long long)b * p.bias_bs + m) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += br;
+            for (int j = 0; j < 32; ++j) v[j] += bias_v;
           } else if (p.bias) {
-            const float* bp = p.bias + (long long)b * p.bias_bs + n0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N_valid) ? __ldg(bp + j) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_v, j);
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask && vm && p.mask_t) {   // mask[b][n][m]: lanes read consecutive m (coalesced)
+          if (p.mbits) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (!((mword >> j) & 1u)) v[j] = 0.f;
+          } else if (p.mask && vm && p.mask_t) {   // mask[b][n][m]: lanes read consecutive m (coalesced)
             const long long mo = (long long)b * p.mask_bs + (long long)n0 * p.mask_ld + m;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -391,7 +410,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (p.n_pad > p.N_valid) {
+          if (p.n_pad > p.N_valid && n0 + 32 > p.N_valid) {   // only the chunk that straddles N_valid (warp-uniform)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j >= p.N_valid) v[j] = 0.f;
@@ -498,6 +517,23 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 op[i] = make_uint4(w[0], w[1], w[2], w[3]);
               }
             }
+          }
+          if (p.mbits_out) {
+            // (h > 0) for the 32 hidden units of this warp, one word per row: column j's ballot is the word of row n0 + j.
+            // Lane 0 parks the 32 ballots in shared memory (128-bit stores), lane j picks up word j: two instructions per
+            // column plus 8 stores (a per-column "if (lane == j)" select costs four).  Warp-uniform branch; padded hidden
+            // units cannot occur (H is a multiple of 128); columns past N_valid were zeroed above.
+            uint32_t* shw = reinterpret_cast<uint32_t*>(stg + (warp - 4) * STG_WARP_BYTES);
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w4[e] = __ballot_sync(0xffffffffu, v[4 * j4 + e] > 0.f);
+              if (lane == 0) *reinterpret_cast<uint4*>(shw + 4 * j4) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            __syncwarp();
+            p.mbits_out[(long long)b * p.mbits_bs + (long long)(n0 + lane) * p.mbits_ld + ((mt * GM + q * 32) >> 5)] = shw[lane];
           }
           if (p.obt && m < p.ob_rows) {
             const long long off = (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + m;
@@ -1011,6 +1047,7 @@ struct Buf {
 struct Lws {
   Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA, G2;
   float *o, *od, *go, *god, *cpart;
+  uint32_t* mbits;     // ReLU mask bits [S][Rp][H / 32]
   size_t total;
 };
 
@@ -1037,6 +1074,7 @@ void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
   w.go = (float*)take((size_t)S * R * CW * 4);
   w.god = (float*)take((size_t)S * R * CW * 4);
   w.cpart = (float*)take((size_t)RSPLIT * S * 2 * CW * H * 4);
+  w.mbits = (uint32_t*)take((size_t)S * Rp * (H / 32) * 4);
   w.total = off;
 }
 
@@ -1124,7 +1162,7 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   const int grid = total < sms ? total : sms;
   size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
   // fp32 outputs are transposed through 8 x 4 KB of staging behind the barriers (the same area the TMA-stored epilogue uses)
-  if (p.of) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
+  if (p.of || p.mbits_out) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   mo = ma;
   mol = ma;
   p.ob_tma = 0;
@@ -1229,7 +1267,12 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   z.batch = S;
   const long long hh_bs = (long long)Rp * 2 * H;
   auto at = [&](const Buf& b, size_t eoff, bool lo) -> void* { return (lo ? b.lo : b.hi) ? (lo ? b.lo : b.hi) + eoff * ES : nullptr; };
-  auto set_mask_h = [&](GemmP& p) { p.mask = at(w.hh, H, false); p.mask_bs = hh_bs; p.mask_ld = 2 * H; };
+  // the ReLU mask travels as bits (written by the forward product below); PSVI_FNL_NO_MBITS=1 reads the stored h instead
+  static const bool use_mbits = !getenv("PSVI_FNL_NO_MBITS");
+  auto set_mask_h = [&](GemmP& p) {
+    if (use_mbits) { p.mbits = w.mbits; p.mbits_bs = (long long)Rp * (H / 32); p.mbits_ld = H / 32; }
+    else { p.mask = at(w.hh, H, false); p.mask_bs = hh_bs; p.mask_ld = 2 * H; }
+  };
   auto set_ob = [&](GemmP& p, const Buf& b, size_t eoff) {
     p.ob = at(b, eoff, false); p.ob_lo = at(b, eoff, true); p.ob_bs = hh_bs; p.ob_ld = 2 * H; p.ob_rows = Rp;
   };
@@ -1243,6 +1286,7 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     GemmP p = z;
     p.M_valid = H; p.N_valid = R; p.n_pad = Rp; p.bias = theta + o_b1; p.bias_bs = P; p.bias_row = 1; p.relu = 1;
     p.obt = at(w.hh, H, false); p.obt_lo = at(w.hh, H, true); p.obt_bs = hh_bs; p.obt_ld = 2 * H; p.ob_rows = H;
+    if (use_mbits && tbar) { p.mbits_out = w.mbits; p.mbits_bs = (long long)Rp * (H / 32); p.mbits_ld = H / 32; }
     if ((rc = launch_gemm<X3>(opW1, opX, p, sms, st))) return rc;
     p = z;
     p.M_valid = R; p.N_valid = CW; p.of = w.o; p.of_bs = (long long)Rp * CW; p.of_ld = CW;
