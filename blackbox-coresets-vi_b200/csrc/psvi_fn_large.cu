@@ -59,6 +59,8 @@ struct GemmP {
   int a_mn, b_mn;                               // split-bf16 only: the operand is read "MN-major" -- its global array is
                                                 // [K rows][M (or N) contiguous], i.e. the product uses the TRANSPOSE of a
                                                 // row-major array without a transposed copy (UMMA a_major / b_major = 1)
+  int obt_stage;                                // split-bf16 only: the transposed operand store is staged in shared memory
+                                                // (16-byte pieces); needs ob_rows % 32 == 0 and 16-byte aligned rows
   int ob_tma;                                   // split-bf16 only: the row-major operand store goes through shared memory and
                                                 // cp.async.bulk.tensor (TMA) stores described by map_o / map_ol
 };
@@ -174,6 +176,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16(x);
   lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+// the same split for two values with the PACKED conversion (cvt.rn.bf16x2.f32: one full-rate instruction per pair; the scalar
+// cvt.rn.bf16.f32 showed up as "mio" stalls in the epilogues).  Words hold (a | b << 16); results equal split_bf16's bit for bit.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
 template <int X3, int CG>
@@ -469,11 +478,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t wh[4], wl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 h2, l2;
-                  split_bf16(v[i * 8 + e * 2], h2.x, l2.x);
-                  split_bf16(v[i * 8 + e * 2 + 1], h2.y, l2.y);
-                  wh[e] = *reinterpret_cast<uint32_t*>(&h2);
-                  wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+                  split_bf16x2(v[i * 8 + e * 2], v[i * 8 + e * 2 + 1], wh[e], wl[e]);
                 }
                 const int phys = (i ^ ((lane >> 1) & 3)) * 16 + lane * 64;
                 *reinterpret_cast<uint4*>(sh + phys) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
@@ -495,11 +500,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t wh[4], wl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 h2, l2;
-                  split_bf16(v[i * 8 + e * 2], h2.x, l2.x);
-                  split_bf16(v[i * 8 + e * 2 + 1], h2.y, l2.y);
-                  wh[e] = *reinterpret_cast<uint32_t*>(&h2);
-                  wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+                  split_bf16x2(v[i * 8 + e * 2], v[i * 8 + e * 2 + 1], wh[e], wl[e]);
                 }
                 oh[i] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
                 ol[i] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
@@ -546,6 +547,31 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 split_tf32(v[j], hi, lo);
                 oh[(long long)j * p.obt_ld] = hi;
                 ol[(long long)j * p.obt_ld] = lo;
+              }
+            } else if (X3 == 2 && p.obt_stage) {
+              // this warp's [32 columns n][32 lanes m] piece of (hi, lo) is laid out [n][m] in shared memory (2 KB each) and
+              // leaves as 16-byte pieces (8 consecutive m of one n per thread): 8 store instructions of 512 bytes instead of
+              // 64 of 64 bytes (ncu: the two-byte stores were 21 % of the samples of the forward product)
+              uint16_t* sh = reinterpret_cast<uint16_t*>(stg + (warp - 4) * STG_WARP_BYTES);
+              uint16_t* sl = sh + 1024;
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                uint32_t wh, wl;
+                split_bf16x2(v[j], v[j + 1], wh, wl);
+                sh[j * 32 + lane] = (uint16_t)(wh & 0xFFFFu);
+                sh[(j + 1) * 32 + lane] = (uint16_t)(wh >> 16);
+                sl[j * 32 + lane] = (uint16_t)(wl & 0xFFFFu);
+                sl[(j + 1) * 32 + lane] = (uint16_t)(wl >> 16);
+              }
+              __syncwarp();
+              __nv_bfloat16* oh = static_cast<__nv_bfloat16*>(p.obt) + (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + mt * GM + q * 32;
+              __nv_bfloat16* ol = static_cast<__nv_bfloat16*>(p.obt_lo) + (long long)b * p.obt_bs + (long long)n0 * p.obt_ld + mt * GM + q * 32;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int piece = k * 32 + lane, n = piece >> 2, mc = piece & 3;
+                *reinterpret_cast<uint4*>(oh + (long long)n * p.obt_ld + mc * 8) = *reinterpret_cast<const uint4*>(sh + n * 32 + mc * 8);
+                *reinterpret_cast<uint4*>(ol + (long long)n * p.obt_ld + mc * 8) = *reinterpret_cast<const uint4*>(sl + n * 32 + mc * 8);
               }
             } else if (X3 == 2) {
               __nv_bfloat16* oh = static_cast<__nv_bfloat16*>(p.obt) + off;
@@ -628,11 +654,7 @@ __device__ __forceinline__ void put16(void* hi_base, void* lo_base, size_t i, co
     uint32_t wh[8], wl[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      __nv_bfloat162 h2, l2;
-      split_bf16(v[2 * e], h2.x, l2.x);
-      split_bf16(v[2 * e + 1], h2.y, l2.y);
-      wh[e] = *reinterpret_cast<uint32_t*>(&h2);
-      wl[e] = *reinterpret_cast<uint32_t*>(&l2);
+      split_bf16x2(v[2 * e], v[2 * e + 1], wh[e], wl[e]);
     }
     uint4* oh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(hi_base) + i);
     oh[0] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
@@ -663,28 +685,49 @@ __global__ void fnl_prep_x_kernel(const float* __restrict__ x, int R, int Rp, in
   }
 }
 
-// first-layer weights of theta (or thetadot) [S][P] -> W1 [S][H][D] and its transpose into W1T2 [S][D][2H] at column offset
-// `toff` (0: primal, H: tangent)
+// two consecutive operand elements at EVEN element offset i: one packed conversion and 32-bit (bf16) / 64-bit (tf32) stores
 template <int X3>
-__global__ void fnl_pack_w1_kernel(const float* __restrict__ theta, long long P, int D, int H, void* W1h, void* W1l, void* Th,
-                                   void* Tl, int toff) {
-  __shared__ float tile[32][33];
-  const int d0 = blockIdx.x * 32, h0 = blockIdx.y * 32, s = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
-  const float* th = theta + (long long)s * P;
-  for (int i = ty; i < 32; i += 8) {
-    const int h = h0 + i, d = d0 + tx;
-    const float v = th[(size_t)h * D + d];
-    tile[i][tx] = v;
-    put<X3>(W1h, W1l, ((size_t)s * H + h) * D + d, v);
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int d = d0 + i, h = h0 + tx;
-    put<X3>(Th, Tl, ((size_t)s * D + d) * (2 * H) + toff + h, tile[tx][i]);
+__device__ __forceinline__ void put2(void* hi_base, void* lo_base, size_t i, float a, float b) {
+  if (X3 == 1) {
+    float ha, la, hb, lb;
+    split_tf32(a, ha, la);
+    split_tf32(b, hb, lb);
+    *reinterpret_cast<float2*>(static_cast<float*>(hi_base) + i) = make_float2(ha, hb);
+    *reinterpret_cast<float2*>(static_cast<float*>(lo_base) + i) = make_float2(la, lb);
+  } else if (X3 == 2) {
+    uint32_t wh, wl;
+    split_bf16x2(a, b, wh, wl);
+    *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(hi_base) + i) = wh;
+    *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(lo_base) + i) = wl;
+  } else {
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(hi_base) + i) = *reinterpret_cast<uint32_t*>(&t2);
   }
 }
 
-// second-layer weights: W2p [S][128][2H] rows c < C at column offset poff; W2T [S][H][2 CP] at column offset coff
+// first-layer weights of theta (or thetadot) [S][P] -> W1 [S][H][D] and its transpose into W1T2 [S][D][2H] at column offset
+// `toff` (0: primal, H: tangent).  64 x 64 tiles, a thread handles two consecutive elements of the contiguous dimension of
+// either output (packed conversions, 128 / 256 bytes per warp store); D and H are multiples of 64.
+template <int X3>
+__global__ void fnl_pack_w1_kernel(const float* __restrict__ theta, long long P, int D, int H, void* W1h, void* W1l, void* Th,
+                                   void* Tl, int toff) {
+  __shared__ float tile[64][65];
+  const int d0 = blockIdx.x * 64, h0 = blockIdx.y * 64, s = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
+  const float* th = theta + (long long)s * P;
+  for (int i = ty; i < 64; i += 8) {
+    const int h = h0 + i, d = d0 + 2 * tx;
+    const float2 v = make_float2(th[(size_t)h * D + d], th[(size_t)h * D + d + 1]);   // (P may be odd: no 64-bit loads)
+    tile[i][2 * tx] = v.x;
+    tile[i][2 * tx + 1] = v.y;
+    put2<X3>(W1h, W1l, ((size_t)s * H + h) * D + d, v.x, v.y);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int d = d0 + i, h = h0 + 2 * tx;
+    put2<X3>(Th, Tl, ((size_t)s * D + d) * (2 * H) + toff + h, tile[2 * tx][i], tile[2 * tx + 1][i]);
+  }
+}
+
 template <int X3>
 __global__ void fnl_pack_w2_kernel(const float* __restrict__ theta, long long P, int D, int H, int C, void* W2ph, void* W2pl,
                                    int poff, void* W2Th, void* W2Tl, int coff, int cp2) {
@@ -1162,7 +1205,10 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   const int grid = total < sms ? total : sms;
   size_t smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + (2 * PR::GST + 4) * 8 + 16 + 1024;
   // fp32 outputs are transposed through 8 x 4 KB of staging behind the barriers (the same area the TMA-stored epilogue uses)
-  if (p.of || p.mbits_out) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
+  // (one user of the per-warp staging area per launch: not together with a TMA-stored row-major operand output)
+  p.obt_stage = X3 == 2 && p.obt && p.obt_lo && !p.ob && p.ob_rows % 32 == 0 && p.obt_ld % 8 == 0 && p.obt_bs % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(p.obt) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.obt_lo) & 15) == 0;
+  if (p.of || p.mbits_out || p.obt_stage) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   mo = ma;
   mol = ma;
   p.ob_tma = 0;
@@ -1235,10 +1281,10 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.W2p.lo : w.W2p.hi, 0, (size_t)S * 128 * 2 * H * ES, st));
     PSVI_CUDA_CHECK(cudaMemsetAsync(part ? w.W2T.lo : w.W2T.hi, 0, (size_t)S * H * 2 * CP * ES, st));
   }
-  fnl_pack_w1_kernel<X3><<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(theta, P, D, H, w.W1.hi, w.W1.lo, w.W1T2.hi, w.W1T2.lo, 0);
+  fnl_pack_w1_kernel<X3><<<dim3(D / 64, H / 64, S), dim3(32, 8), 0, st>>>(theta, P, D, H, w.W1.hi, w.W1.lo, w.W1T2.hi, w.W1T2.lo, 0);
   fnl_pack_w2_kernel<X3><<<dim3(8, S), 256, 0, st>>>(theta, P, D, H, C, w.W2p.hi, w.W2p.lo, 0, w.W2T.hi, w.W2T.lo, CP, 2 * CP);
   if (dual) {
-    fnl_pack_w1_kernel<X3><<<dim3(D / 32, H / 32, S), dim3(32, 8), 0, st>>>(thetad, P, D, H, w.W1d.hi, w.W1d.lo, w.W1T2.hi,
+    fnl_pack_w1_kernel<X3><<<dim3(D / 64, H / 64, S), dim3(32, 8), 0, st>>>(thetad, P, D, H, w.W1d.hi, w.W1d.lo, w.W1T2.hi,
                                                                          w.W1T2.lo, H);
     fnl_pack_w2_kernel<X3><<<dim3(8, S), 256, 0, st>>>(thetad, P, D, H, C, w.W2p.hi, w.W2p.lo, H, w.W2T.hi, w.W2T.lo, 0, 2 * CP);
   }
