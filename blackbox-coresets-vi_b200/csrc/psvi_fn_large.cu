@@ -1020,15 +1020,18 @@ fnl_colsum_pair_kernel(const __nv_bfloat16* __restrict__ Yh, const __nv_bfloat16
   const size_t step = (size_t)ld / 2;
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
   int r = 0;
-  for (; r + 4 <= R; r += 4) {
-    float2 h[4], l[4];
+  for (; r + 8 <= R; r += 8) {   // 16 independent 4-byte loads in flight per thread (HBM-bound sweep over 0.5 GB at cfg5)
+    __nv_bfloat162 h[8], l[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      h[k] = __bfloat1622float2(ph[(size_t)(r + k) * step]);
-      l[k] = __bfloat1622float2(pl[(size_t)(r + k) * step]);
+    for (int k = 0; k < 8; ++k) {
+      h[k] = ph[(size_t)(r + k) * step];
+      l[k] = pl[(size_t)(r + k) * step];
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { a0 += h[k].x; a1 += h[k].y; b0 += l[k].x; b1 += l[k].y; }
+    for (int k = 0; k < 8; ++k) {
+      const float2 hf = __bfloat1622float2(h[k]), lf = __bfloat1622float2(l[k]);
+      a0 += hf.x; a1 += hf.y; b0 += lf.x; b1 += lf.y;
+    }
   }
   for (; r < R; ++r) {
     const float2 h = __bfloat1622float2(ph[(size_t)r * step]), l = __bfloat1622float2(pl[(size_t)r * step]);
