@@ -55,18 +55,32 @@ conv_pool_fwd_kernel(const float* __restrict__ in1, size_t ss1, const float* __r
   float* s_w1 = s_in2 + IMGS * NIN;    // [CO][CI][WPAD]
   float* s_w2 = s_w1 + NWP;
   const int s = blockIdx.y, tid = threadIdx.x, r_base = blockIdx.x * IMGS;
-  for (int i = tid; i < IMGS * NIN; i += NT) {
-    const int img = i / NIN, j = i % NIN, r = r_base + img;
-    const int ci = j / (HP * HP), yy = (j / HP) % HP - PAD, xx = j % HP - PAD;
-    const bool ok = r < R && yy >= 0 && yy < HIN && xx >= 0 && xx < HIN;
-    const size_t off = (size_t)r * CI * HIN * HIN + (ci * HIN + yy) * HIN + xx;
-    s_in1[i] = ok ? in1[(size_t)s * ss1 + off] : 0.f;
-    s_in2[i] = (ok && in2) ? in2[(size_t)s * ss2 + off] : 0.f;
+  // staging: 64-bit copies of the interior (HIN, PAD, HP even), zero border only where there is one (PAD > 0), and nothing at
+  // all for the second term when it is absent (primal passes: in2 == w2 == nullptr -- s_in2 / s_w2 are never read then)
+  const bool two = in2 != nullptr;
+  if (PAD > 0) {
+    for (int i = tid; i < IMGS * NIN / 4; i += NT) {
+      reinterpret_cast<float4*>(s_in1)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (two) reinterpret_cast<float4*>(s_in2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+  }
+  {
+    constexpr int HH = HIN / 2, PER_IMG = CI * HIN * HH;
+    for (int i = tid; i < IMGS * PER_IMG; i += NT) {
+      const int img = i / PER_IMG, j = i % PER_IMG, r = r_base + img;
+      const int ci = j / (HIN * HH), yy = (j / HH) % HIN, x2 = j % HH;
+      const size_t off = (size_t)r * CI * HIN * HIN + (ci * HIN + yy) * HIN + 2 * x2;
+      const int so = img * NIN + (ci * HP + yy + PAD) * HP + 2 * x2 + PAD;
+      const bool ok = r < R;
+      *reinterpret_cast<float2*>(s_in1 + so) = ok ? *reinterpret_cast<const float2*>(in1 + (size_t)s * ss1 + off) : make_float2(0.f, 0.f);
+      if (two) *reinterpret_cast<float2*>(s_in2 + so) = ok ? *reinterpret_cast<const float2*>(in2 + (size_t)s * ss2 + off) : make_float2(0.f, 0.f);
+    }
   }
   for (int i = tid; i < NWP; i += NT) {
     const int f = i / WPAD, t = i % WPAD;
     s_w1[i] = t < 25 ? w1[(size_t)s * LN_P + f * 25 + t] : 0.f;
-    s_w2[i] = (t < 25 && w2) ? w2[(size_t)s * LN_P + f * 25 + t] : 0.f;
+    if (w2) s_w2[i] = t < 25 ? w2[(size_t)s * LN_P + f * 25 + t] : 0.f;
   }
   __syncthreads();
   const int img = tid / TPI, rem = tid % TPI, r = r_base + img;
@@ -275,7 +289,7 @@ struct ConvWgCfg {
   static constexpr int NTR = CI * 5, NT = (NTR * NG + 31) / 32 * 32, NOUT = CO * CI * 25;
 };
 template <int CI, int CO, int HIN, int PAD, int NG>
-__global__ void __launch_bounds__((ConvWgCfg<CI, CO, HIN, PAD, NG>::NT))
+__global__ void __launch_bounds__((ConvWgCfg<CI, CO, HIN, PAD, NG>::NT), 3)
 conv_bwd_weight_kernel(const float* __restrict__ pb1, const float* __restrict__ in1, size_t ss1, const float* __restrict__ pb2,
                        const float* __restrict__ in2, size_t ss2, const uint8_t* __restrict__ sel, int R, int rows_per_chunk,
                        float* __restrict__ part) {
@@ -303,28 +317,64 @@ conv_bwd_weight_kernel(const float* __restrict__ pb1, const float* __restrict__ 
   for (int i = tid; i < CI * HP * HPP; i += NT) s_in[i] = 0.f;
   for (int i = tid; i < CO * HO * HOP; i += NT) s_a[i] = 0.f;
   __syncthreads();
-#pragma unroll 1
-  for (int r = r0; r < r1; ++r) {
-#pragma unroll 1
-    for (int term = 0; term < 2; ++term) {
-      const float* pb = term ? pb2 : pb1;
-      if (!pb) break;
-      const float* ip = (term ? in2 + (size_t)s * ss2 : in1 + (size_t)s * ss1) + (size_t)r * CI * HIN * HIN;
-      for (int i = tid; i < CI * HIN * (HIN / 2); i += NT) {   // interior of the padded input, 64 bits at a time
+  // Work items = (row, term).  The global data of item i + 1 (its input map and pooled adjoints with their selection codes)
+  // is fetched into REGISTERS right after the barrier that publishes item i, i.e. the loads fly while item i is multiplied
+  // (ncu of the load -> barrier -> multiply form: 33 % of the warp samples waited on these loads).
+  constexpr int NI = CI * HIN * (HIN / 2), NIT = (NI + NT - 1) / NT;   // 64-bit pieces of the input interior, per thread
+  constexpr int NA = CO * HQ * HQ, NAT = (NA + NT - 1) / NT;            // pooled adjoints, per thread
+  float2 pin[NIT];
+  float pv[NAT];
+  int pc[NAT];
+  const int nterm = pb2 ? 2 : 1, n_items = (r1 - r0) * nterm;
+  auto fetch = [&](int item) {
+    const int r = r0 + item / nterm, term = item % nterm;
+    const float* pb = term ? pb2 : pb1;
+    const float* ip = (term ? in2 + (size_t)s * ss2 : in1 + (size_t)s * ss1) + (size_t)r * CI * HIN * HIN;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int i = tid + k * NT;
+      if (i < NI) {
         const int c = i / (HIN * (HIN / 2)), yy = (i / (HIN / 2)) % HIN, x2 = i % (HIN / 2);
-        *reinterpret_cast<float2*>(s_in + (c * HP + yy + PAD) * HPP + 2 * x2 + PAD) =
-            *reinterpret_cast<const float2*>(ip + (c * HIN + yy) * HIN + 2 * x2);
+        pin[k] = *reinterpret_cast<const float2*>(ip + (c * HIN + yy) * HIN + 2 * x2);
       }
-      const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
-      for (int i = tid; i < CO * HQ * HQ; i += NT) {   // each pooled adjoint owns its 2x2 window of the full-resolution map
-        const int co = i / (HQ * HQ), py = (i / HQ) % HQ, px = i % HQ, c = sel[pbase + i];
-        const float v = (c & 4) ? pb[pbase + i] : 0.f;
-        const int k = c & 3;
-        float* d = s_a + (co * HO + 2 * py) * HOP + 2 * px;
-        *reinterpret_cast<float2*>(d) = make_float2(k == 0 ? v : 0.f, k == 1 ? v : 0.f);
-        *reinterpret_cast<float2*>(d + HOP) = make_float2(k == 2 ? v : 0.f, k == 3 ? v : 0.f);
+    }
+    const size_t pbase = ((size_t)s * R + r) * (CO * HQ * HQ);
+#pragma unroll
+    for (int k = 0; k < NAT; ++k) {
+      const int i = tid + k * NT;
+      if (i < NA) {
+        pc[k] = sel[pbase + i];
+        pv[k] = pb[pbase + i];
+      }
+    }
+  };
+  if (n_items > 0) fetch(0);
+#pragma unroll 1
+  for (int item = 0; item < n_items; ++item) {
+    const int term = item % nterm;
+    {
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {   // interior of the padded input, 64 bits at a time
+        const int i = tid + k * NT;
+        if (i < NI) {
+          const int c = i / (HIN * (HIN / 2)), yy = (i / (HIN / 2)) % HIN, x2 = i % (HIN / 2);
+          *reinterpret_cast<float2*>(s_in + (c * HP + yy + PAD) * HPP + 2 * x2 + PAD) = pin[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NAT; ++k) {   // each pooled adjoint owns its 2x2 window of the full-resolution map
+        const int i = tid + k * NT;
+        if (i < NA) {
+          const int co = i / (HQ * HQ), py = (i / HQ) % HQ, px = i % HQ, c = pc[k];
+          const float v = (c & 4) ? pv[k] : 0.f;
+          const int kk = c & 3;
+          float* d = s_a + (co * HO + 2 * py) * HOP + 2 * px;
+          *reinterpret_cast<float2*>(d) = make_float2(kk == 0 ? v : 0.f, kk == 1 ? v : 0.f);
+          *reinterpret_cast<float2*>(d + HOP) = make_float2(kk == 2 ? v : 0.f, kk == 3 ? v : 0.f);
+        }
       }
       __syncthreads();
+      if (item + 1 < n_items) fetch(item + 1);
       if (active) {
 #pragma unroll 1
         for (int y = g; y < HO; y += NG) {
