@@ -12,7 +12,12 @@
 // Covers psvi_mf_unroll (run_mfvi_subset / run_mfvi training, baselines.py:1019-1032,876-890) and psvi_mf_evaluate
 // (baselines.py:1035-1043; PSVI.evaluate psvi_classes.py:1031-1108) for such models.  The bilevel step for this regime
 // is future work.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "psvi_mf_gemm.cuh"
+
+namespace cg = cooperative_groups;
 
 using namespace psvi_mf;
 
@@ -373,6 +378,10 @@ __global__ void __launch_bounds__(NT, 1) fwdbwd_kernel(const __grid_constant__ S
 
 // ---- generic per-sample pass on externally supplied weights (any variational family) ---------------------------------
 // mode 0: forward only (nll); 1: gradient; 2: dual (Hessian-vector) pass
+// Grid (Z, S): the rows of a sample are split over a CLUSTER of Z CTAs (Z = 1: one CTA per sample, plain launch).  With Z > 1 a
+// CTA accumulates its weight adjoints in shared memory behind the activations; after a cluster barrier the Z CTAs sum the
+// partials through distributed shared memory in FIXED rank order (deterministic) -- each CTA reduces every Z-th block of indices
+// -- and write global memory once.  (One CTA per sample left 32 of 148 SMs busy at cfg3: S = 32.)
 __global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__ SP p, int mode) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ Meta mt;
@@ -380,13 +389,21 @@ __global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__
   if (threadIdx.x == 0) { make_meta(p.dims, p.L, mt); make_slay(p, mt, ly, mode > 0, mode == 2); }
   __syncthreads();
   Worker w(p, mt, ly, smem_dyn);
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int Z = (int)gridDim.x, z = (int)blockIdx.x, s = (int)blockIdx.y, tid = threadIdx.x;
+  const int per = (p.R + Z - 1) / Z, rz0 = z * per, rz1 = min(p.R, rz0 + per);
+  const int Ptp = (mt.Pt + 3) & ~3;
+  const bool split = Z > 1 && mode > 0;
+  float* tb = mode > 0 ? (split ? smem_dyn + ly.total : p.tbar + (size_t)s * mt.Pt) : nullptr;
+  float* tdb = mode == 2 ? (split ? smem_dyn + ly.total + Ptp : p.tdbar + (size_t)s * mt.Pt) : nullptr;
+  if (split && rz0 >= rz1) {   // a CTA without rows contributes zeros
+    for (int i = tid; i < (mode == 2 ? 2 : 1) * Ptp; i += NT) tb[i] = 0.f;
+  }
   w.init_ones();
   w.load_theta(s);
   if (mode == 2) { w.load_weights(p.thetad + (size_t)s * mt.Pt, ly.thetad); }
   const int D = p.dims[0];
-  for (int r0 = 0; r0 < p.R; r0 += p.RC) {
-    const int nr = min(p.RC, p.R - r0);
+  for (int r0 = rz0; r0 < rz1; r0 += p.RC) {
+    const int nr = min(p.RC, rz1 - r0);
     w.stage(p.x, p.y, r0, nr);
     if (mode > 0) {
       for (int rr = tid; rr < nr; rr += NT) w.F(ly.cw)[rr] = __ldg(p.cwm + (size_t)s * p.R + r0 + rr);
@@ -396,11 +413,11 @@ __global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__
     if (mode == 2) {
       w.forward_dual(nr);
       w.loss_dual(nr, p.acbar ? p.acbar + (size_t)s * p.R + r0 : nullptr, p.ybar ? p.ybar + (size_t)s * p.R + r0 : nullptr);
-      w.backward_any(nr, true, p.tbar + (size_t)s * mt.Pt, p.tdbar + (size_t)s * mt.Pt, xb, r0 == 0);
+      w.backward_any(nr, true, tb, tdb, xb, r0 == rz0);
     } else {
       w.forward(nr);
       w.loss(nr, mode == 1, p.ybar ? p.ybar + (size_t)s * p.R + r0 : nullptr);
-      if (mode == 1) w.backward_any(nr, false, p.tbar + (size_t)s * mt.Pt, nullptr, xb, r0 == 0);
+      if (mode == 1) w.backward_any(nr, false, tb, nullptr, xb, r0 == rz0);
     }
     if (p.nll_out)
       for (int rr = tid; rr < nr; rr += NT) p.nll_out[(size_t)s * p.R + r0 + rr] = w.F(ly.nll)[rr];
@@ -410,6 +427,21 @@ __global__ void __launch_bounds__(NT, 1) net_pass_kernel(const __grid_constant__
         for (int c = tid; c < C; c += NT) p.logits_out[((size_t)s * p.R + r0 + rr) * C + c] = w.F(ly.act[p.L])[rr * ldc + c];
     }
     __syncthreads();
+  }
+  if (split) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int nvec = mode == 2 ? 2 : 1;
+    for (int v = 0; v < nvec; ++v) {
+      float* local = smem_dyn + ly.total + v * Ptp;
+      float* out = (v ? p.tdbar : p.tbar) + (size_t)s * mt.Pt;
+      for (int i = tid + NT * z; i < mt.Pt; i += NT * Z) {
+        float a = 0.f;
+        for (int k = 0; k < Z; ++k) a += cluster.map_shared_rank(local, k)[i];
+        out[i] = a;
+      }
+    }
+    cluster.sync();   // nobody leaves while its partials may still be read
   }
 }
 
@@ -776,21 +808,55 @@ static int net_pass_impl(const psvi_mf_model* model, const float* theta, const f
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t budget = (size_t)smem_max - 2048;
+  // rows of a sample over a cluster of Z CTAs: ~32 rows per CTA, at most 8 (portable cluster size), at most ~2 CTAs per SM in
+  // total; PSVI_NET_PASS_Z overrides (1 = one CTA per sample)
+  int sms = 1;
+  PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int Z = R / 32;
+  if (Z > 8) Z = 8;
+  while (Z > 1 && p.S * Z > 2 * sms) --Z;
+  if (const char* e = getenv("PSVI_NET_PASS_Z")) Z = atoi(e);
+  if (Z < 1) Z = 1;
+  if (Z > 8) Z = 8;
   SLay ly;
-  int lo = 0, hi = R < 256 ? R : 256;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) / 2;
-    p.RC = mid;
-    make_slay(p, mt, ly, mode > 0, mode == 2);
-    if ((size_t)ly.total * 4 <= budget) lo = mid; else hi = mid - 1;
+  size_t extra = 0;
+  int lo = 0;
+  for (;; --Z) {   // (falls back towards Z = 1 if the partial-adjoint buffers do not fit beside one row of activations)
+    const int per = (R + Z - 1) / Z;
+    extra = (Z > 1 && mode > 0) ? (size_t)(mode == 2 ? 2 : 1) * ((mt.Pt + 3) & ~3) : 0;
+    int hi = per < 256 ? per : 256;
+    lo = 0;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) / 2;
+      p.RC = mid;
+      make_slay(p, mt, ly, mode > 0, mode == 2);
+      if (((size_t)ly.total + extra) * 4 <= budget) lo = mid; else hi = mid - 1;
+    }
+    if (lo >= 1 || Z == 1) break;
   }
   PSVI_REQUIRE(lo >= 1, PSVI_ERR_UNSUPPORTED, "one sample's weights (P_pad=%d floats%s) plus one row of activations must "
                "fit in %zu B of shared memory", mt.Pp, mode == 2 ? ", twice" : "", budget);
   p.RC = lo;
   make_slay(p, mt, ly, mode > 0, mode == 2);
-  const size_t smem = (size_t)ly.total * 4;
+  const size_t smem = ((size_t)ly.total + extra) * 4;
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(net_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  net_pass_kernel<<<p.S, NT, smem, (cudaStream_t)stream_>>>(p, mode);
+  if (Z > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)Z, (unsigned)p.S);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream_;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)Z;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PSVI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, net_pass_kernel, p, mode));
+  } else {
+    net_pass_kernel<<<dim3(1, p.S), NT, smem, (cudaStream_t)stream_>>>(p, mode);
+  }
   PSVI_CUDA_CHECK(cudaGetLastError());
   return PSVI_OK;
 }

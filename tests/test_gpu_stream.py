@@ -255,3 +255,45 @@ def test_net_pass_gaussian_matches_oracle(dims, S, R):
     assert rel_l2(tbar.cpu().numpy(), A_t) < 5e-5 and rel_l2(tdbar.cpu().numpy(), A_td) < 5e-5
     assert rel_l2(xbar.cpu().numpy(), A_x) < 5e-5
     assert rel_l2(ac.cpu().numpy(), tau * r * d) < 5e-5 and rel_l2(ybar.cpu().numpy(), -cw64 * tau * d) < 5e-5
+
+
+@pytest.mark.parametrize("dims,S,R", [([2, 40, 40, 2], 32, 100), ([5, 24, 16, 3], 6, 229), ([7, 12, 3], 3, 65)])
+def test_net_pass_row_split_over_a_cluster(dims, S, R, monkeypatch):
+    """psvi_net_pass splits the rows of a sample over a thread-block cluster (Z = R / 32 <= 8 CTAs, partial weight adjoints
+    summed through distributed shared memory in fixed rank order): gradient and dual passes equal the one-CTA-per-sample form
+    (PSVI_NET_PASS_Z=1) to fp32 summation-order accuracy, match the fp64 oracle, and are bit-reproducible run to run."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    rng = np.random.default_rng(S + R)
+    P = po.p_theta(dims)
+    theta = (0.3 * rng.standard_normal((S, P))).astype(np.float32)
+    thetad = (0.3 * rng.standard_normal((S, P))).astype(np.float32)
+    X = rng.standard_normal((R, dims[0])).astype(np.float32)
+    y = rng.integers(0, dims[-1], R)
+    cw = rng.uniform(0.5, 1.5, (S, R)).astype(np.float32)
+    model = nat.make_model(dims, S)
+    th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
+
+    def run():
+        nll, tb1, xb1 = zeros(S, R), zeros(S, P), zeros(S, R, dims[0])
+        nat.net_pass(model, th, None, x_, y_, cw_, nll=nll, tbar=tb1, xbar=xb1)
+        tb2, tdb2, xb2, ac = zeros(S, P), zeros(S, P), zeros(S, R, dims[0]), zeros(S, R)
+        nat.net_pass(model, th, thd, x_, y_, cw_, tbar=tb2, tdbar=tdb2, xbar=xb2, acbar=ac)
+        torch.cuda.synchronize()
+        return [t.cpu().numpy() for t in (nll, tb1, xb1, tb2, tdb2, xb2, ac)]
+
+    split = run()
+    again = run()
+    for a, b in zip(split, again):
+        np.testing.assert_array_equal(a, b)
+    monkeypatch.setenv("PSVI_NET_PASS_Z", "1")
+    single = run()
+    for a, b in zip(split, single):
+        assert rel_l2(a, b) < 2e-6
+    t64, td64, X64, cw64 = (a.astype(np.float64) for a in (theta, thetad, X, cw))
+    o, cache = po.mlp_forward(t64, X64, dims)
+    ref_nll, p = po.nll_rows(o, y)
+    q = p.copy()
+    q[:, np.arange(R), y] -= 1.0
+    At, Ax = po.mlp_backward(t64, cache, dims, cw64[:, :, None] * q)
+    assert rel_l2(split[0], ref_nll) < 2e-5 and rel_l2(split[1], At) < 2e-5 and rel_l2(split[2], Ax) < 2e-5
