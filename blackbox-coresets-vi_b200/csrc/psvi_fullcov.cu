@@ -125,20 +125,39 @@ fc_reparam_kernel(int n, int S, const float* __restrict__ phi, const float* __re
   for (int s0 = 0; s0 < S; s0 += FS) {
     const int ns = min(FS, S - s0);
     __syncthreads();
-    for (int i = threadIdx.x; i < FS * FT; i += 256) {
-      const int ss = i / FT, k = i % FT;
-      const bool ok = ss < ns;
-      As[ss][k] = (ok && r0 + k < n) ? A[(size_t)(s0 + ss) * ld_a + r0 + k] : 0.f;
-      Es[ss][k] = (ok && c0 + k < n) ? eps[(size_t)(s0 + ss) * ld_eps + c0 + k] : 0.f;
+    {   // 16 global loads per thread in flight before the first store (one memory latency per stage)
+      float av[FS * FT / 256], ev[FS * FT / 256];
+#pragma unroll
+      for (int u = 0; u < FS * FT / 256; ++u) {
+        const int i = threadIdx.x + u * 256, ss = i / FT, k = i % FT;
+        const bool ok = ss < ns;
+        av[u] = (ok && r0 + k < n) ? A[(size_t)(s0 + ss) * ld_a + r0 + k] : 0.f;
+        ev[u] = (ok && c0 + k < n) ? eps[(size_t)(s0 + ss) * ld_eps + c0 + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < FS * FT / 256; ++u) {
+        const int i = threadIdx.x + u * 256;
+        As[i / FT][i % FT] = av[u];
+        Es[i / FT][i % FT] = ev[u];
+      }
+    }
+    float adv[FS];   // HVP, diagonal tiles: the second adjoint's column of this thread's index, loaded as one batch
+    if (MODE == 1 && c0 == r0 && threadIdx.x < FT) {
+#pragma unroll
+      for (int ss = 0; ss < FS; ++ss)
+        adv[ss] = (ss < ns && r0 + (int)threadIdx.x < n) ? Ad[(size_t)(s0 + ss) * ld_a + r0 + threadIdx.x] : 0.f;
     }
     __syncthreads();
     if (c0 == r0 && threadIdx.x < FT) {   // the vector parts of this tile's 64 indices (diagonal tiles only), from the same stage
       const int k = threadIdx.x;
-      for (int ss = 0; ss < ns; ++ss) {
-        const float v = As[ss][k], e = Es[ss][k];
-        va += v;
-        vb = fmaf(v, e, vb);
-        if (MODE == 1) vbd = fmaf((r0 + k < n) ? Ad[(size_t)(s0 + ss) * ld_a + r0 + k] : 0.f, e, vbd);
+#pragma unroll
+      for (int ss = 0; ss < FS; ++ss) {
+        if (ss < ns) {
+          const float v = As[ss][k], e = Es[ss][k];
+          va += v;
+          vb = fmaf(v, e, vb);
+          if (MODE == 1) vbd = fmaf(adv[ss], e, vbd);
+        }
       }
     }
     for (int ss = 0; ss < ns; ++ss) {   // (a padded sample would add +0.f: skipped so that -0.f sums stay bit-identical)

@@ -808,11 +808,12 @@ static int net_pass_impl(const psvi_mf_model* model, const float* theta, const f
   PSVI_CUDA_CHECK(cudaGetDevice(&dev));
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t budget = (size_t)smem_max - 2048;
-  // rows of a sample over a cluster of Z CTAs: ~32 rows per CTA, at most 8 (portable cluster size), at most ~2 CTAs per SM in
-  // total; PSVI_NET_PASS_Z overrides (1 = one CTA per sample)
+  // rows of a sample over a cluster of Z CTAs: >= 16 rows per CTA (cfg3, R = 100, S = 32: Z = 3 / 4 / 6 / 8 -> 4.7 / 4.6 / 4.3 /
+  // 4.3 ms per outer step), at most 8 (portable cluster size), at most ~2 CTAs per SM in total; PSVI_NET_PASS_Z overrides
+  // (1 = one CTA per sample)
   int sms = 1;
   PSVI_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int Z = R / 32;
+  int Z = R / 16;
   if (Z > 8) Z = 8;
   while (Z > 1 && p.S * Z > 2 * sms) --Z;
   if (const char* e = getenv("PSVI_NET_PASS_Z")) Z = atoi(e);

@@ -259,7 +259,7 @@ def test_net_pass_gaussian_matches_oracle(dims, S, R):
 
 @pytest.mark.parametrize("dims,S,R", [([2, 40, 40, 2], 32, 100), ([5, 24, 16, 3], 6, 229), ([7, 12, 3], 3, 65)])
 def test_net_pass_row_split_over_a_cluster(dims, S, R, monkeypatch):
-    """psvi_net_pass splits the rows of a sample over a thread-block cluster (Z = R / 32 <= 8 CTAs, partial weight adjoints
+    """psvi_net_pass splits the rows of a sample over a thread-block cluster (Z = R / 16 <= 8 CTAs, partial weight adjoints
     summed through distributed shared memory in fixed rank order): gradient and dual passes equal the one-CTA-per-sample form
     (PSVI_NET_PASS_Z=1) to fp32 summation-order accuracy, match the fp64 oracle, and are bit-reproducible run to run."""
     from psvi import _native as nat
