@@ -59,6 +59,10 @@ struct GemmP {
   int a_mn, b_mn;                               // split-bf16 only: the operand is read "MN-major" -- its global array is
                                                 // [K rows][M (or N) contiguous], i.e. the product uses the TRANSPOSE of a
                                                 // row-major array without a transposed copy (UMMA a_major / b_major = 1)
+  float* colpart; long long colpart_bs; int colpart_ld;   // column sums of the (masked) output per 32-row group:
+                                                // colpart[b][mt * 4 + q][n] = sum over the 32 rows of epilogue warp q of row tile
+                                                // mt (fixed order); a finish kernel adds the groups -- the bias adjoint of the
+                                                // gradient pass without a second sweep over the adjoint array
   int obt_stage;                                // split-bf16 only: the transposed operand store is staged in shared memory
                                                 // (16-byte pieces); needs ob_rows % 32 == 0 and 16-byte aligned rows
   int ob_tma;                                   // split-bf16 only: the row-major operand store goes through shared memory and
@@ -423,6 +427,19 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j >= p.N_valid) v[j] = 0.f;
+          }
+          if (p.colpart) {   // (warp-uniform; rows >= M_valid and columns >= N_valid hold zeros here)
+            float* sh = reinterpret_cast<float*>(stg + (warp - 4) * STG_WARP_BYTES);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sh[lane * 32 + (j ^ lane)] = v[j];
+            __syncwarp();
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) t += sh[r * 32 + (lane ^ r)];
+            if (n0 + lane < p.N_valid)
+              p.colpart[(long long)b * p.colpart_bs + (long long)(mt * 4 + q) * p.colpart_ld + n0 + lane] = t;
+            __syncwarp();
           }
           if (p.of) {
             // fp32 output: this warp's [32 rows x 32 columns] piece is transposed through shared memory (element (r, c) at
@@ -855,7 +872,7 @@ fnl_colreduce_kernel(const void* Yh, const void* Yl, long long y_off, long long 
       __syncthreads();
       for (int i = threadIdx.x; i < nr * (CW / 4); i += CR_T) s_w[i] = __ldg(wp + (size_t)rs * (CW / 4) + i);
       __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
       for (int rr = 0; rr < nr; ++rr) {
         float yv[4];
         get4<X3>(Yh, Yl, y0 + (size_t)(rs + rr) * y_ld, yv);
@@ -896,6 +913,16 @@ __global__ void fnl_colreduce_finish_kernel(const float* __restrict__ part, int 
   for (int zc = 0; zc < RSPLIT; ++zc) t += part[((size_t)zc * S + s) * C * H + i];
   float* d = out + (long long)s * P + i;
   *d = accumulate ? *d + t : t;
+}
+
+// out[s * P + h] = sum_g part[s][g][h]  (the per-row-group column sums written by the GEMM epilogue, fixed order)
+__global__ void fnl_colpart_finish_kernel(const float* __restrict__ part, int G, int H, float* __restrict__ out, long long P) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (h >= H) return;
+  const float* pp = part + (size_t)s * G * H + h;
+  float t = 0.f;
+  for (int g = 0; g < G; ++g) t += pp[(size_t)g * H];
+  out[(long long)s * P + h] = t;
 }
 
 // The three weighted column reductions of the dual pass in ONE sweep over hh = [hdot | h] (each element read once):
@@ -1094,6 +1121,7 @@ struct Lws {
   Buf X, XT, W1, W1d, W1T2, W2p, W2T, hh, aa, aT, adT, AA, G2;
   float *o, *od, *go, *god, *cpart;
   uint32_t* mbits;     // ReLU mask bits [S][Rp][H / 32]
+  float* bpart;        // column sums of abar per 32-row group [S][Rp / 32][H]
   size_t total;
 };
 
@@ -1121,6 +1149,7 @@ void carve_l(int S, int R, int D, int H, int x3, uint8_t* base, Lws& w) {
   w.god = (float*)take((size_t)S * R * CW * 4);
   w.cpart = (float*)take((size_t)RSPLIT * S * 2 * CW * H * 4);
   w.mbits = (uint32_t*)take((size_t)S * Rp * (H / 32) * 4);
+  w.bpart = (float*)take((size_t)S * (Rp / 32) * H * 4);
   w.total = off;
 }
 
@@ -1211,7 +1240,8 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
   // (one user of the per-warp staging area per launch: not together with a TMA-stored row-major operand output)
   p.obt_stage = X3 == 2 && p.obt && p.obt_lo && !p.ob && p.ob_rows % 32 == 0 && p.obt_ld % 8 == 0 && p.obt_bs % 8 == 0 &&
                 (reinterpret_cast<uintptr_t>(p.obt) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.obt_lo) & 15) == 0;
-  if (p.of || p.mbits_out || p.obt_stage) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
+  if (p.colpart) p.obt_stage = 0;
+  if (p.of || p.mbits_out || p.obt_stage || p.colpart) smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   mo = ma;
   mol = ma;
   p.ob_tma = 0;
@@ -1363,11 +1393,16 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
     set_mask_h(p); set_obt(p, w.aT);
     p.ob_rows = Rp;
     if (xbar) set_ob(p, w.aa, 0);
+    // tf32x3: the bias adjoint b1bar = column sums of abar comes out of this product's epilogue (per 32-row group, then a
+    // finish kernel) instead of a row-sum sweep over the 0.5 GB transposed array (PSVI_FNL_NO_COLPART=1: the sweep)
+    const bool colpart = X3 == 1 && !getenv("PSVI_FNL_NO_COLPART");
+    if (colpart) { p.colpart = w.bpart; p.colpart_bs = (long long)(Rp / 32) * H; p.colpart_ld = H; }
     if ((rc = launch_gemm<X3>(opA0, opW2T1, p, sms, st))) return rc;
     p = z;            // W1bar = abar^T X
     p.M_valid = H; p.N_valid = D; p.of = tbar; p.of_bs = P; p.of_ld = D;
     if ((rc = launch_gemm<X3>(opAT, opXT, p, sms, st))) return rc;
-    fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);   // b1bar
+    if (colpart) fnl_colpart_finish_kernel<<<dim3((H + 255) / 256, S), 256, 0, st>>>(w.bpart, Rp / 32, H, tbar + o_b1, P);
+    else fnl_rowsum_kernel<X3><<<dim3((H + 7) / 8, S), 256, 0, st>>>(w.aT.hi, w.aT.lo, H, Rp, R, tbar + o_b1, P);   // b1bar
     colreduce(w.hh, H, w.go, C, tbar + o_w2, 0);
     fnl_colsum16_kernel<<<S, 256, 0, st>>>(w.go, R, C, tbar + o_b2, P);
     if (xbar) {
