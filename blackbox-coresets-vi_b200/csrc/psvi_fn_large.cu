@@ -1253,7 +1253,8 @@ int launch_gemm(const Operand& A, const Operand& B, GemmP p, int sms, cudaStream
     smem = (size_t)PR::GST * PR::TILES * G_TILE_BYTES + 1024 + 8 * STG_WARP_BYTES + 1024;
   }
   // CTA pairs (cta_group::2, 256 x 256 tiles: half the operand traffic per output) whenever the tile grid is even both ways
-  static const int cg2_mode = getenv("PSVI_FNL_CG2") ? atoi(getenv("PSVI_FNL_CG2")) : 1;
+  const char* cg2_env = getenv("PSVI_FNL_CG2");   // (read per call: the parity tests switch it inside one process)
+  const int cg2_mode = cg2_env ? atoi(cg2_env) : 1;
   const bool pair = X3 != 0 && cg2_mode && p.m_tiles % 2 == 0 && p.n_tiles % 2 == 0 && sms >= 2 &&
                     (cg2_mode == 2 || p.kc * PR::GK >= 256);
   if (pair) {
@@ -1347,7 +1348,7 @@ int fnl_pass_impl(const psvi_mf_model* model, const float* theta, const float* t
   const long long hh_bs = (long long)Rp * 2 * H;
   auto at = [&](const Buf& b, size_t eoff, bool lo) -> void* { return (lo ? b.lo : b.hi) ? (lo ? b.lo : b.hi) + eoff * ES : nullptr; };
   // the ReLU mask travels as bits (written by the forward product below); PSVI_FNL_NO_MBITS=1 reads the stored h instead
-  static const bool use_mbits = !getenv("PSVI_FNL_NO_MBITS");
+  const bool use_mbits = !getenv("PSVI_FNL_NO_MBITS");
   auto set_mask_h = [&](GemmP& p) {
     if (use_mbits) { p.mbits = w.mbits; p.mbits_bs = (long long)Rp * (H / 32); p.mbits_ld = H / 32; }
     else { p.mask = at(w.hh, H, false); p.mask_bs = hh_bs; p.mask_ld = 2 * H; }

@@ -230,3 +230,50 @@ def test_fnl_pass_writes_inside_its_outputs_only(prec):
         for k, (buf, view) in group.items():
             assert torch.all(buf[:G] == 12345.0) and torch.all(buf[-G:] == 12345.0), k
             assert torch.isfinite(view).all(), k
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16x3"])
+def test_fnl_pass_kernel_variants_agree(prec, monkeypatch):
+    """The alternative forms of the batched GEMM kernel compute the same thing: CTA pairs (cta_group::2, 256 x 256 tiles) against
+    single CTAs (PSVI_FNL_CG2=0) bit for bit -- the K order of the accumulation is the same --, the ReLU mask as bits against the
+    mask read from the stored activations (PSVI_FNL_NO_MBITS=1) and the bias adjoint from the epilogue's column sums against the
+    row-sum sweep (PSVI_FNL_NO_COLPART=1) to fp32 summation-order accuracy.  Shape with even tile grids and K >= 256, so that the
+    default run does use the pair kernel."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    D, H, C, S, R = 256, 256, 10, 3, 250
+    PREC = nat.PREC_TF32X3 if prec == "tf32x3" else nat.PREC_BF16X3
+    rng = np.random.default_rng(11)
+    dims = [D, H, C]
+    theta = np.concatenate([rng.standard_normal((S, H * D)) / np.sqrt(D), 0.1 * rng.standard_normal((S, H)),
+                            rng.standard_normal((S, C * H)) / np.sqrt(H), 0.1 * rng.standard_normal((S, C))], 1).astype(np.float32)
+    thetad = (rng.standard_normal(theta.shape) * np.abs(theta).mean() * 0.5).astype(np.float32)
+    X = rng.standard_normal((R, D)).astype(np.float32)
+    theta = unambiguous_relu(theta, X, dims)
+    y = rng.integers(0, C, R)
+    cw = rng.uniform(0.5, 1.5, (S, R)).astype(np.float32)
+    model = nat.make_model(dims, S)
+    P = theta.shape[1]
+    th, thd, x_, y_, cw_ = dev(theta), dev(thetad), dev(X), dev(y, torch.int32), dev(cw)
+
+    def run():
+        nll, tb1, xb1 = zeros(S, R), zeros(S, P), zeros(S, R, D)
+        nat.fnl_pass(model, PREC, th, None, x_, y_, cw_, nll=nll, tbar=tb1, xbar=xb1)
+        tb2, tdb2, xb2, ac = zeros(S, P), zeros(S, P), zeros(S, R, D), zeros(S, R)
+        nat.fnl_pass(model, PREC, th, thd, x_, y_, cw_, tbar=tb2, tdbar=tdb2, xbar=xb2, acbar=ac)
+        torch.cuda.synchronize()
+        return [t.cpu().numpy() for t in (nll, tb1, xb1, tb2, tdb2, xb2, ac)]
+
+    base = run()
+    monkeypatch.setenv("PSVI_FNL_CG2", "0")
+    single = run()
+    for a, b in zip(base, single):
+        np.testing.assert_array_equal(a, b)
+    monkeypatch.delenv("PSVI_FNL_CG2")
+    monkeypatch.setenv("PSVI_FNL_NO_MBITS", "1")
+    for a, b in zip(base, run()):
+        assert rel_l2(a, b) < 1e-6
+    monkeypatch.delenv("PSVI_FNL_NO_MBITS")
+    monkeypatch.setenv("PSVI_FNL_NO_COLPART", "1")
+    for a, b in zip(base, run()):
+        assert rel_l2(a, b) < 1e-6
