@@ -147,3 +147,63 @@ def test_medium_meanfield_nested_step_two_hidden_layers_of_100():
     assert abs(loss.item() - r["loss"]) <= 1e-4 * abs(r["loss"])
     assert rel_l2(obj.u.grad.cpu().numpy(), r["u_grad"]) < 2e-3
     assert rel_l2(obj.v.grad.cpu().numpy(), r["v_grad"]) < 2e-3
+
+
+@pytest.mark.parametrize("n,S", [(5, 3), (70, 5), (150, 40), (257, 32)])
+def test_fc_sample_and_reparam_match_numpy_and_stay_inside_their_outputs(n, S):
+    """psvi_fc_sample / psvi_fc_reparam_grad / psvi_fc_reparam_hvp (the packed-triangle family maps of fn2, reference
+    neural_net.py:408-491) against a dense fp64 restatement, for sizes that span one to five 64 x 64 tiles of the tiled rank-S
+    update and sample counts on both sides of its 32-sample stage; guard bands around every output stay untouched."""
+    from psvi import _native as nat
+    nat.require_cuda()
+    rng = np.random.default_rng(n + S)
+    ntri = (n - 1) * (n - 2) // 2
+    P = 2 * n + ntri
+    phi = np.concatenate([rng.standard_normal(n), rng.standard_normal(n) - 1.0, 0.1 * rng.standard_normal(ntri)]).astype(np.float32)
+    phid = (0.3 * rng.standard_normal(P)).astype(np.float32)
+    eps = rng.standard_normal((S, n)).astype(np.float32)
+    A = rng.standard_normal((S, n)).astype(np.float32)
+    Ad = rng.standard_normal((S, n)).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)
+    mean, sd, corr = f64(phi[:n]), f64(phi[n:2 * n]), f64(phi[2 * n:])
+    d, sig = np.log1p(np.exp(sd)), 1.0 / (1.0 + np.exp(-sd))
+
+    def tril(v):   # strictly-lower entries of the top-left (n-1) x (n-1) block, row-major; the last row has none (quirk Q6)
+        L = np.zeros((n, n))
+        if n >= 3:
+            r, c = np.tril_indices(n - 1, -1)
+            L[r, c] = v
+        return L
+
+    G = 64
+    guard = lambda size: torch.full((size + 2 * G,), 7.25, device="cuda")
+    ok = lambda t, size: bool((t[:G] == 7.25).all() and (t[G + size:] == 7.25).all())
+    phi_d, phid_d, eps_d, A_d, Ad_d = dev(phi), dev(phid), dev(eps), dev(A), dev(Ad)
+    # sample and tangent
+    out = guard(S * n)
+    nat.fc_sample(n, S, phi_d.data_ptr(), None, eps_d.data_ptr(), n, out.data_ptr() + 4 * G, n)
+    ref = mean + f64(eps) * d + f64(eps) @ tril(corr).T
+    assert ok(out, S * n) and rel_l2(out[G:G + S * n].cpu().numpy().reshape(S, n), ref) < 1e-5
+    out = guard(S * n)
+    nat.fc_sample(n, S, phi_d.data_ptr(), phid_d.data_ptr(), eps_d.data_ptr(), n, out.data_ptr() + 4 * G, n)
+    md, sdd, cd = f64(phid[:n]), f64(phid[n:2 * n]), f64(phid[2 * n:])
+    ref = md + f64(eps) * (sig * sdd) + f64(eps) @ tril(cd).T
+    assert ok(out, S * n) and rel_l2(out[G:G + S * n].cpu().numpy().reshape(S, n), ref) < 1e-5
+    # gradient
+    kl, nkl = 0.7, -0.3
+    g = guard(P)
+    nat.fc_reparam_grad(n, S, phi_d.data_ptr(), A_d.data_ptr(), n, eps_d.data_ptr(), n, kl, nkl, g.data_ptr() + 4 * G)
+    AE = f64(A).T @ f64(eps)                                    # [r][c] = sum_s A[s][r] eps[s][c]
+    rr, cc = np.tril_indices(n - 1, -1) if n >= 3 else (np.zeros(0, int), np.zeros(0, int))
+    ref = np.concatenate([f64(A).sum(0) + kl * mean, sig * ((f64(A) * f64(eps)).sum(0) + kl * (d - 1 / d) + nkl / d),
+                          AE[rr, cc] + kl * corr])
+    assert ok(g, P) and rel_l2(g[G:G + P].cpu().numpy(), ref) < 1e-5
+    # Hessian-vector product
+    h = guard(P)
+    nat.fc_reparam_hvp(n, S, phi_d.data_ptr(), phid_d.data_ptr(), A_d.data_ptr(), Ad_d.data_ptr(), n, eps_d.data_ptr(), n,
+                       h.data_ptr() + 4 * G)
+    ref = np.concatenate([f64(A).sum(0) + md,
+                          sig * (f64(A) * f64(eps)).sum(0) + sig * (1 - sig) * sdd * (f64(Ad) * f64(eps)).sum(0)
+                          + ((1 + 1 / d ** 2) * sig ** 2 + (d - 1 / d) * sig * (1 - sig)) * sdd,
+                          AE[rr, cc] + cd])
+    assert ok(h, P) and rel_l2(h[G:G + P].cpu().numpy(), ref) < 1e-5
