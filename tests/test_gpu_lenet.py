@@ -32,7 +32,8 @@ def _case(S, R, seed):
     return theta, thetad, X, y, cw
 
 
-@pytest.mark.parametrize("S,R", [(1, 3), (3, 7), (4, 19)])
+# (10, 200) is the pass of BASELINE configs[3] at full size (S = 10 MC samples, M = 200 pseudo-images): ~20 s of fp64 oracle
+@pytest.mark.parametrize("S,R", [(1, 3), (3, 7), (4, 19), (10, 200)])
 def test_lenet_pass_matches_oracle(S, R):
     from psvi import _native as nat
     nat.require_cuda()
