@@ -57,7 +57,8 @@ def unambiguous_relu(theta, X, dims, margin=1e-3):
 # (cta_group::2, 256 x 256 tiles); (256, 512, 4, 2, 300) mixes pair and single-CTA launches inside one pass
 @pytest.mark.parametrize("prec", ["tf32x3", "bf16x3"])
 @pytest.mark.parametrize("D,H,C,S,R", [(64, 128, 3, 2, 100), (128, 256, 10, 3, 300), (256, 384, 4, 2, 129), (192, 128, 16, 2, 260),
-                                       (256, 256, 10, 3, 200), (256, 512, 4, 2, 300), (512, 256, 16, 2, 500)])
+                                       (256, 256, 10, 3, 200), (256, 512, 4, 2, 300), (512, 256, 16, 2, 500),
+                                       (256, 1024, 10, 4, 1000)])   # the last: BASELINE configs[4]'s exact D / H / C / M (S = 4 of 64)
 def test_fnl_pass_tf32x3_matches_oracle(D, H, C, S, R, prec):
     """precision 1 (three kind::tf32 MMAs on (hi, lo) operand pairs): fp32-class accuracy -- rel-L2 2e-5 on every output
     against the fp64 oracle with un-rounded operands.  precision 2 (the same split with bf16 pairs, three kind::f16 MMAs):
