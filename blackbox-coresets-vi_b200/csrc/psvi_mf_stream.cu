@@ -116,15 +116,25 @@ struct Worker {
   __device__ void load_theta(int s) { load_weights(p.theta + (size_t)s * mt.Pt, ly.theta); }
   __device__ void load_weights(const float* src, int dst_off) {
     for (int l = 1; l <= p.L; ++l) {
-      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l];
+      const int din = mt.din[l], dout = mt.dout[l], ldw = mt.ldw[l], n = dout * din;
       float* W = F(dst_off) + mt.woff[l];
-      int oo = 0, ii = tid;
-      while (ii >= din) { ii -= din; ++oo; }
-      const int so = NT / din, si = NT - so * din;
-      for (int i = tid; i < dout * din; i += NT) {
-        W[oo * ldw + ii] = __ldg(src + mt.tlw[l] + i);
-        oo += so; ii += si;
-        if (ii >= din) { ii -= din; ++oo; }
+      const float* g = src + mt.tlw[l];
+      // eight loads in flight per thread before the first store (a load -> store loop pays one memory latency per element)
+      for (int base = 0; base < n; base += 8 * NT) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * NT + tid;
+          v[u] = i < n ? __ldg(g + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * NT + tid;
+          if (i < n) {
+            const int oo = i / din;
+            W[oo * ldw + (i - oo * din)] = v[u];
+          }
+        }
       }
       for (int o = tid; o < dout; o += NT) W[o * ldw + din] = __ldg(src + mt.tlb[l] + o);
     }
