@@ -478,7 +478,7 @@ def main():
         sec = t.item() * 1e-3
         sharded = {"what": f"PSVI.evaluate over {n_big} synthetic rows (D=2, fn H=100, S=10, M=50, batch 8192), rows "
                            f"sharded over {world} rank(s), one all-reduce of 8 floats; median of {reps} passes, max over ranks; "
-                           "fp32 CUDA-core predictive kernels (compute / latency bound at D=2, DESIGN.md 4.2)",
+                           "fp32 CUDA-core predictive kernels (register-form rows kernel of the cfg2 family, DESIGN.md 4.2)",
                    "passes_per_s": 1.0 / sec, "row_samples_per_s": n_big * c["S"] / sec,
                    "ms_min_med_max_rank0": [min(per), sorted(per)[len(per) // 2], max(per)]}
     except Exception as e:  # never lose the headline number to the secondary section

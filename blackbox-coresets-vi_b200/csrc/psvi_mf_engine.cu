@@ -1009,6 +1009,157 @@ __global__ void __launch_bounds__(NT, 1) psvi_mf_eval_rows_kernel(const __grid_c
   e.eval_rows();
 }
 
+// Predictive rows pass for ONE hidden layer and tiny input / output widths (the cfg2 family: D, C <= 4), register form: a thread
+// owns RPT test rows (inputs and the C mixture accumulators in registers) and walks the H hidden units; a unit's sampled weights
+// (D + 1 + C <= 8 floats) come from shared memory as two warp-broadcast 128-bit loads shared by its RPT rows.  Per MC sample the
+// CTA rebuilds theta_s = mu + sigma eps_s (same noise addressing as Engine::sample_theta: slab, sample, TL index).  The generic
+// kernel above walks the same rows through shared-memory GEMM phases with a block barrier per layer and sample (3.3 G row-samples/s
+// at cfg2 shapes, ~4 % of the instruction issue rate); same per-CTA partials, same reduction kernel.
+constexpr int EV_RPT = 4, EV_T = 256;
+template <int D, int C>
+__global__ void __launch_bounds__(EV_T) psvi_mf_eval_rows_fn1_kernel(const __grid_constant__ EP p) {
+  extern __shared__ __align__(16) float ev_sm[];
+  const int H = p.dims[1], HD = H * D, Pt = HD + H + C * H + C;
+  float* rec = ev_sm;                 // [H][8]: w1[D], b1, w2[C]
+  float* b2 = rec + H * 8;            // [4]
+  float* smu = b2 + 4;                // [Pt]
+  float* ssg = smu + ((Pt + 3) & ~3); // [Pt]
+  float* wts = ssg + ((Pt + 3) & ~3); // [S]
+  __shared__ float red[64];
+  const int tid = threadIdx.x;
+  const int slab_local = blockIdx.x / p.chunks_per_slab, chunk = blockIdx.x - slab_local * p.chunks_per_slab;
+  const int slab = p.first_slab + slab_local;
+  const int row_begin = slab_local * p.batch + chunk * (EV_T * EV_RPT);
+  const int slab_end = min((slab_local + 1) * p.batch, p.n_rows);
+  const int nr = max(0, min(EV_T * EV_RPT, slab_end - row_begin));
+  for (int q = tid; q < Pt; q += EV_T) { smu[q] = p.mu[q]; ssg[q] = softplus_f(p.rho[q]); }
+  for (int i = tid; i < H * 8 + 4; i += EV_T) rec[i] = 0.f;
+  if (tid == 0) {
+    if (p.eval_mode == 0) {   // importance weights of this slab: softmax over the S log-weights of E1
+      const float* lw = p.eval_w + (size_t)slab_local * p.S;
+      float mx = -INFINITY;
+      for (int s = 0; s < p.S; ++s) mx = fmaxf(mx, lw[s]);
+      float se = 0.f;
+      for (int s = 0; s < p.S; ++s) se += expf(lw[s] - mx);
+      for (int s = 0; s < p.S; ++s) wts[s] = expf(lw[s] - mx) / se;
+    } else {
+      for (int s = 0; s < p.S; ++s) wts[s] = 1.f / (float)p.S;
+    }
+  }
+  float x[EV_RPT][D], pr[EV_RPT][C];
+  int yl[EV_RPT];
+  bool ok[EV_RPT];
+#pragma unroll
+  for (int k = 0; k < EV_RPT; ++k) {
+    const int r = tid + k * EV_T;
+    ok[k] = r < nr;
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[k][d] = ok[k] ? __ldg(p.xb + (size_t)(row_begin + r) * D + d) : 0.f;
+    yl[k] = ok[k] ? __ldg(p.yb + row_begin + r) : 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) pr[k][c] = 0.f;
+  }
+  const int n4 = (Pt + 3) >> 2;
+  for (int s = 0; s < p.S; ++s) {
+    __syncthreads();   // the previous sample's records are no longer read (first pass: the staging above is visible)
+    for (int q4 = tid; q4 < n4; q4 += EV_T) {
+      float e4[4];
+      if (p.noise_mode == PSVI_NOISE_PHILOX) {
+        philox_normal4(p.seed, p.domain, (uint32_t)slab, (uint32_t)s, (uint32_t)q4, e4);
+      } else {
+        const float* src = p.eps + ((size_t)slab * p.S + s) * Pt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e4[j] = (4 * q4 + j < Pt) ? __ldg(src + 4 * q4 + j) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = 4 * q4 + j;
+        if (q < Pt) {
+          const float th = smu[q] + ssg[q] * e4[j];
+          int r;
+          if (q < HD) { const int u = q / D; r = u * 8 + (q - u * D); }
+          else if (q < HD + H) r = (q - HD) * 8 + D;
+          else if (q < HD + H + C * H) { const int c = (q - HD - H) / H, u = (q - HD - H) - c * H; r = u * 8 + D + 1 + c; }
+          else r = H * 8 + (q - HD - H - C * H);
+          rec[r] = th;
+        }
+      }
+    }
+    __syncthreads();
+    float o[EV_RPT][C];
+#pragma unroll
+    for (int k = 0; k < EV_RPT; ++k)
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[k][c] = b2[c];
+#pragma unroll 2
+    for (int u = 0; u < H; ++u) {
+      const float4 wa = *reinterpret_cast<const float4*>(rec + u * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(rec + u * 8 + 4);
+      const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int k = 0; k < EV_RPT; ++k) {
+        float a = w[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) a = fmaf(w[d], x[k][d], a);
+        a = fmaxf(a, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[k][c] = fmaf(a, w[D + 1 + c], o[k][c]);
+      }
+    }
+    const float wgt = wts[s];
+#pragma unroll
+    for (int k = 0; k < EV_RPT; ++k) {
+      if (p.eval_mode == 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) pr[k][c] += wgt * o[k][c];
+      } else {
+        float mx = o[k][0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, o[k][c]);
+        float ex[C], se = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { ex[c] = expf(o[k][c] - mx); se += ex[c]; }
+        const float inv = wgt / se;
+#pragma unroll
+        for (int c = 0; c < C; ++c) pr[k][c] += inv * ex[c];
+      }
+    }
+  }
+  float nll_sum = 0.f, correct = 0.f;
+#pragma unroll
+  for (int k = 0; k < EV_RPT; ++k) {
+    if (!ok[k]) continue;
+    int am = 0;
+    float best = pr[k][0], py = pr[k][0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+      if (pr[k][c] > best) { best = pr[k][c]; am = c; }
+      py = (yl[k] == c) ? pr[k][c] : py;
+    }
+    correct += (am == yl[k]) ? 1.f : 0.f;
+    if (p.eval_mode == 2) {  // Categorical(logits=mean logits)
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) se += expf(pr[k][c] - best);
+      nll_sum += best + logf(se) - py;
+    } else {                 // Categorical(probs=...): normalise, clamp to [eps, 1-eps], log
+      float tot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) tot += pr[k][c];
+      float pn = py / tot;
+      pn = fminf(fmaxf(pn, 1.1920929e-07f), 1.f - 1.1920929e-07f);
+      nll_sum -= logf(pn);
+    }
+  }
+  __syncthreads();
+  nll_sum = block_sum(nll_sum, red);
+  correct = block_sum(correct, red);
+  if (tid == 0) {
+    float* out = p.eval_part + (size_t)blockIdx.x * 4;
+    out[0] = nll_sum; out[1] = correct; out[2] = (float)nr; out[3] = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(NT, 1) psvi_mf_forward_kernel(const __grid_constant__ EP p) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ Meta mt;
@@ -1422,8 +1573,22 @@ int psvi_mf_evaluate(const psvi_mf_model* model, const psvi_noise* noise, const 
     psvi_mf_eval_weights_kernel<<<p.n_slabs * p.S, NT, smem, stream>>>(p);
     PSVI_CUDA_CHECK(cudaGetLastError());
   }
-  const int nctas = p.n_slabs * p.chunks_per_slab;
-  psvi_mf_eval_rows_kernel<<<nctas, NT, smem, stream>>>(p);
+  // one hidden layer, D and C in {2, 4} (the cfg2 family), hidden layer within 48 KB of records: the register-form rows pass
+  const bool fn1_rows = p.L == 2 && (p.dims[0] == 2 || p.dims[0] == 4) && (p.dims[2] == 2 || p.dims[2] == 4) &&
+                        p.dims[0] + 1 + p.dims[2] <= 8 && p.dims[1] <= 1024 && !getenv("PSVI_EVAL_GENERIC");
+  int nctas = p.n_slabs * p.chunks_per_slab;
+  if (fn1_rows) {
+    const int H = p.dims[1], Pt = mt.Pt;
+    p.chunks_per_slab = (rows_cap + EV_T * EV_RPT - 1) / (EV_T * EV_RPT);
+    nctas = p.n_slabs * p.chunks_per_slab;
+    const size_t sm1 = (size_t)(H * 8 + 4 + 2 * ((Pt + 3) & ~3) + p.S + 4) * 4;
+    void (*k)(const EP) = p.dims[0] == 2 ? (p.dims[2] == 2 ? psvi_mf_eval_rows_fn1_kernel<2, 2> : psvi_mf_eval_rows_fn1_kernel<2, 4>)
+                                         : (p.dims[2] == 2 ? psvi_mf_eval_rows_fn1_kernel<4, 2> : psvi_mf_eval_rows_fn1_kernel<4, 4>);
+    PSVI_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    k<<<nctas, EV_T, sm1, stream>>>(p);
+  } else {
+    psvi_mf_eval_rows_kernel<<<nctas, NT, smem, stream>>>(p);
+  }
   PSVI_CUDA_CHECK(cudaGetLastError());
   psvi_mf_eval_reduce_kernel<<<1, NT, 0, stream>>>(p.eval_part, nctas, out,
                                                     mode == 0 ? p.eval_w + (size_t)(p.n_slabs - 1) * p.S : nullptr, p.S);

@@ -242,3 +242,39 @@ def test_evaluate(nat, name):
     np.testing.assert_allclose(o[0] / o[2], ref[1], rtol=2e-4)
     np.testing.assert_allclose(o[3], ref[2], rtol=2e-3, atol=1e-5)
     np.testing.assert_allclose(o[4], ref[3], rtol=2e-3)
+
+
+@pytest.mark.parametrize("D,C,H,S,n_rows,batch", [(2, 2, 100, 10, 5000, 1536), (2, 4, 37, 6, 3001, 1024), (4, 2, 128, 3, 777, 8192)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_evaluate_register_rows_kernel_equals_generic(nat, D, C, H, S, n_rows, batch, mode, monkeypatch):
+    """psvi_mf_evaluate for one hidden layer and D, C in {2, 4} runs its rows pass in the register-form kernel
+    (psvi_mf_eval_rows_fn1_kernel: several 1024-row chunks per noise slab, ragged last chunk and slab); with the same Philox
+    noise it must give the generic shared-memory kernel's sums (PSVI_EVAL_GENERIC=1): row count exact, correct count within
+    one borderline row, NLL sum to fp32 summation accuracy -- in all three modes (IW-corrected, mean of softmax, mean logits)."""
+    rng = np.random.default_rng(D + C + H + S + n_rows)
+    dims, M = [D, H, C], 13
+    P = po.p_theta(dims)
+    mu = (0.5 * rng.standard_normal(P)).astype(np.float32)
+    rho = (rng.standard_normal(P) - 2.0).astype(np.float32)
+    u = rng.standard_normal((M, D)).astype(np.float32)
+    z = rng.integers(0, C, M)
+    v = rng.uniform(0.5, 1.5, M).astype(np.float32)
+    xt = rng.standard_normal((n_rows, D)).astype(np.float32)
+    yt = rng.integers(0, C, n_rows)
+    model = nat.make_model(dims, S)
+    args = (dev(mu), dev(rho), dev(u), dev(z, torch.int32), dev(v), dev(xt), dev(yt, torch.int32), batch, 0, 800.0, 0, 0.0, mode)
+
+    def run():
+        out = zeros(8)
+        scratch = zeros(nat.eval_scratch_floats(model, n_rows, batch))
+        nat.evaluate(model, nat.make_noise(None, seed=5, domain=3), *args, out, scratch)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    fast = run()
+    monkeypatch.setenv("PSVI_EVAL_GENERIC", "1")
+    ref = run()
+    assert fast[2] == ref[2] == n_rows
+    assert abs(fast[1] - ref[1]) <= 1.0
+    np.testing.assert_allclose(fast[0], ref[0], rtol=2e-5)
+    np.testing.assert_allclose(fast[3:5], ref[3:5], rtol=1e-5, atol=1e-7)
