@@ -1238,6 +1238,10 @@ int launch_engine(EP& p, int rows_max, cudaStream_t stream) {
   const int max_cluster = 16;
   PSVI_CUDA_CHECK(cudaFuncSetAttribute(psvi_mf_engine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   int G = p.S < max_cluster ? p.S : max_cluster;
+  if (const char* e = getenv("PSVI_ENGINE_G")) {   // diagnostic: cap the cluster size (1 = the whole step in one CTA)
+    const int cap = atoi(e);
+    if (cap >= 1 && cap < G) G = cap;
+  }
   const int per = (p.S + G - 1) / G;
   G = (p.S + per - 1) / per;
   const bool dual = (p.flags & (F_REVERSE | F_HVP)) != 0;
